@@ -1,0 +1,122 @@
+"""ctypes binding of libav1r.so (the C ABI in include/av1r.h, include/av1r_stages.h).
+
+This is the Python stand-in for the cgo package `internal/av1recon` (av1-go_b200/go/): the
+image has no Go toolchain, so tests and bench.py drive the same C entry points from here.
+There is no CPU fallback: if the CUDA library is missing, importing raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libav1r.so")
+
+
+class FilmGrainParams(C.Structure):
+    _fields_ = [
+        ("apply_grain", C.c_int), ("grain_seed", C.c_int), ("update_grain", C.c_int),
+        ("num_y_points", C.c_int), ("point_y_value", C.c_int * 16), ("point_y_scaling", C.c_int * 16),
+        ("chroma_scaling_from_luma", C.c_int),
+        ("num_cb_points", C.c_int), ("point_cb_value", C.c_int * 16), ("point_cb_scaling", C.c_int * 16),
+        ("num_cr_points", C.c_int), ("point_cr_value", C.c_int * 16), ("point_cr_scaling", C.c_int * 16),
+        ("grain_scaling", C.c_int), ("ar_coeff_lag", C.c_int),
+        ("ar_coeffs_y", C.c_int * 24), ("ar_coeffs_cb", C.c_int * 25), ("ar_coeffs_cr", C.c_int * 25),
+        ("ar_coeff_shift", C.c_int), ("grain_scale_shift", C.c_int),
+        ("cb_mult", C.c_int), ("cb_luma_mult", C.c_int), ("cb_offset", C.c_int),
+        ("cr_mult", C.c_int), ("cr_luma_mult", C.c_int), ("cr_offset", C.c_int),
+        ("overlap_flag", C.c_int), ("clip_to_restricted_range", C.c_int),
+    ]
+
+
+class FrameHeaderInfo(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("tu_index", C.c_int),
+        ("frame_type", C.c_int), ("show_frame", C.c_int), ("showable_frame", C.c_int),
+        ("show_existing_frame", C.c_int), ("frame_to_show_map_idx", C.c_int),
+        ("width", C.c_int), ("height", C.c_int), ("upscaled_width", C.c_int), ("bit_depth", C.c_int),
+        ("subsampling_x", C.c_int), ("subsampling_y", C.c_int), ("mono_chrome", C.c_int),
+        ("matrix_coefficients", C.c_int),
+        ("refresh_frame_flags", C.c_int), ("order_hint", C.c_int), ("primary_ref_frame", C.c_int),
+        ("base_q_idx", C.c_int), ("tile_cols", C.c_int), ("tile_rows", C.c_int), ("use_128x128_superblock", C.c_int),
+        ("lf_level", C.c_int * 4), ("cdef_enabled", C.c_int), ("cdef_bits", C.c_int), ("lr_type", C.c_int * 3),
+        ("tx_mode", C.c_int), ("reduced_tx_set", C.c_int), ("header_bytes", C.c_int),
+        ("film_grain", FilmGrainParams),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int), ("streams", C.c_int),
+                ("frames_in_flight", C.c_int), ("parity_md5", C.c_int), ("apply_grain", C.c_int),
+                ("inloop_filters", C.c_int), ("keep_frames", C.c_int)]
+
+
+class FrameResult(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("pts", C.c_int64),
+                ("w", C.c_int), ("h", C.c_int), ("bpc", C.c_int), ("layout", C.c_int),
+                ("status", C.c_int), ("frame_type", C.c_int), ("shown_existing", C.c_int),
+                ("md5", (C.c_uint8 * 16) * 3), ("checksum", C.c_uint64 * 3),
+                ("host_parse_ms", C.c_float), ("device_ms", C.c_float), ("frame_handle", C.c_int64)]
+
+
+class StreamInfo(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("is_av1", C.c_int),
+                ("width", C.c_int), ("height", C.c_int), ("bit_depth", C.c_int), ("profile", C.c_int),
+                ("subsampling_x", C.c_int), ("subsampling_y", C.c_int), ("mono_chrome", C.c_int),
+                ("film_grain_present", C.c_int), ("temporal_units", C.c_int64), ("keyframes", C.c_int64)]
+
+
+class Report(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("status", C.c_int), ("frames", C.c_int64),
+                ("width", C.c_int), ("height", C.c_int), ("bit_depth", C.c_int),
+                ("first_bad_frame", C.c_int64),
+                ("host_parse_ms", C.c_double), ("device_ms", C.c_double), ("wall_ms", C.c_double),
+                ("frames_per_sec", C.c_double), ("message", C.c_char * 512)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} missing: run `make` (or __graft_entry__.build()); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        l.av1r_abi_version.restype = C.c_uint32
+        l.av1r_scan_headers.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int,
+                                        C.POINTER(FrameHeaderInfo), C.c_int, C.POINTER(C.c_int)]
+        l.av1r_film_grain_scratch_bytes.restype = C.c_size_t
+        l.av1r_stage_film_grain.argtypes = [C.POINTER(FilmGrainParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+        l.av1r_stage_plane_checksum.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        l.av1r_plane_checksum_host.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+        l.av1r_plane_checksum_host.restype = C.c_uint64
+        l.av1r_stage_last_error.restype = C.c_char_p
+        l.av1r_probe_buffer.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StreamInfo)]
+        l.av1r_probe_file.argtypes = [C.c_char_p, C.POINTER(StreamInfo)]
+        _lib = l
+    return _lib
+
+
+def scan_headers(tus):
+    """Header-only scan of a list of temporal units -> list of FrameHeaderInfo."""
+    l = lib()
+    n_tus = len(tus)
+    arr = (C.c_char_p * n_tus)(*tus)
+    lens = (C.c_size_t * n_tus)(*[len(t) for t in tus])
+    cap = 4 * n_tus + 8
+    out = (FrameHeaderInfo * cap)()
+    n = C.c_int(0)
+    rc = l.av1r_scan_headers(arr, lens, n_tus, out, cap, C.byref(n))
+    if rc:
+        raise RuntimeError(f"av1r_scan_headers -> {rc}")
+    return [out[i] for i in range(n.value)]
+
+
+def probe_buffer(data):
+    info = StreamInfo()
+    info.struct_size = C.sizeof(StreamInfo)
+    rc = lib().av1r_probe_buffer(data, len(data), C.byref(info))
+    if rc:
+        raise RuntimeError(f"av1r_probe_buffer -> {rc}")
+    return info

@@ -1,0 +1,31 @@
+// Decode engine: one instance = one GPU (one av1r_ctx).  Host side parses OBUs / tiles into
+// work-lists, device side reconstructs.  See DESIGN.md.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "../../include/av1r.h"
+
+namespace av1r {
+
+struct EngineImpl;
+
+class Engine {
+public:
+    Engine();
+    ~Engine();
+    int open(const av1r_config& cfg);
+    int submit_tu(const uint8_t* data, size_t len, int64_t pts);
+    int collect(av1r_frame_result* out, int cap, int* n);
+    int flush();
+    int copy_frame(int64_t handle, int plane, void* dst, size_t dst_stride);
+    int release_frame(int64_t handle);
+    const std::string& error() const;
+    static int verify_file(const char* path, const av1r_config* cfg, av1r_report* out);
+
+private:
+    EngineImpl* impl_;
+};
+
+}  // namespace av1r
