@@ -1,0 +1,127 @@
+// Host-side per-frame state produced by the sequential parse: mode info per block, the device
+// work-lists, and what later frames need from this one (CDFs, segment ids, motion vectors).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <vector>
+
+#include "av1_consts.h"
+#include "hdr.h"
+#include "worklist.h"
+
+namespace av1r {
+
+#include "tables/tables_cdf.inc"   // struct CdfCtx + av1t_default_*_cdf
+
+static_assert(sizeof(CdfCtx) == 2 * (AV1T_NCOEF_CDF + AV1T_NMODE_CDF), "CdfCtx layout");
+
+struct Mv {
+    int16_t row, col;
+};
+
+struct BlockInfo {
+    uint16_t mi_row, mi_col;
+    uint8_t bsize, skip, skip_mode, is_inter, segment_id, use_intrabc;
+    uint8_t y_mode, uv_mode;
+    int8_t angle_y, angle_uv;
+    uint8_t use_filter_intra, fi_mode;
+    int8_t cfl_alpha_u, cfl_alpha_v;
+    uint8_t pal_size[2];
+    uint16_t pal_colors[3][8];
+    int8_t ref_frame[2];
+    Mv mv[2];
+    uint8_t interp_filter[2];
+    uint8_t motion_mode, compound_type, comp_group_idx, compound_idx;
+    uint8_t interintra, interintra_mode, wedge_interintra, wedge_index, wedge_sign, mask_type;
+    uint8_t tx_size;           // luma TxSize (largest when var-tx)
+    uint8_t qidx;              // qindex used by this block's residual
+    int8_t delta_lf[4];
+    uint8_t has_chroma;
+    uint8_t num_mv_found, is_global_or_default;
+    uint8_t lossless;
+};
+
+inline void cdf_load_defaults(CdfCtx& c, int base_q_idx) {
+    int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;
+    uint16_t* p = reinterpret_cast<uint16_t*>(&c);
+    memcpy(p, av1t_default_coef_cdf[q], sizeof(uint16_t) * AV1T_NCOEF_CDF);
+    memcpy(p + AV1T_NCOEF_CDF, av1t_default_mode_cdf, sizeof(uint16_t) * AV1T_NMODE_CDF);
+}
+inline void cdf_load_default_coefs(CdfCtx& c, int base_q_idx) {
+    int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;
+    memcpy(reinterpret_cast<uint16_t*>(&c), av1t_default_coef_cdf[q], sizeof(uint16_t) * AV1T_NCOEF_CDF);
+}
+
+// Loop-restoration parameters of one unit
+struct LrUnit {
+    uint8_t type;          // RESTORE_NONE / WIENER / SGRPROJ
+    uint8_t sgr_set;
+    int8_t wiener[2][3];   // [pass: 0 vertical, 1 horizontal][coef]
+    int8_t sgr_xqd[2];
+};
+
+// Everything the device needs for one frame + what the next frames need from the parse.
+struct FrameWork {
+    FrameHdr fh;
+    int bit_depth = 8, subx = 1, suby = 1, mono = 0, sb128 = 0;
+    int mi_cols = 0, mi_rows = 0;
+    // device work-lists
+    std::vector<TxRec> tx;
+    std::vector<uint32_t> coefs;
+    std::vector<SbRange> sbs;
+    std::vector<uint8_t> pal;
+    std::vector<LfEdge> lf[3];          // per plane, (plane_h4 x plane_w4)
+    std::vector<int8_t> cdef_idx;       // per 64x64 luma block, -1 = skip
+    std::vector<uint8_t> skip_mi;       // per mi: block skip flag (CDEF 8x8 skip condition)
+    std::vector<LrUnit> lr[3];
+    int lr_cols[3] = {0, 0, 0}, lr_rows[3] = {0, 0, 0};
+    // mode info (host only)
+    std::deque<BlockInfo> blocks;
+    std::vector<BlockInfo*> mi;         // per mi -> block
+    std::vector<uint8_t> inter_tx;      // per mi: InterTxSizes
+    std::vector<uint8_t> lf_tx[3];      // per plane 4x4: LoopfilterTxSizes
+    std::vector<uint8_t> tx_types;      // per mi (luma)
+    std::vector<uint8_t> seg_ids;       // per mi
+    // statistics for the roofline model: coded samples A, coefficient bytes C
+    uint64_t coded_samples = 0, coef_tokens = 0, tx_blocks = 0;
+    double parse_ms = 0;
+    // CDFs at the end of the context-update tile (saved into refreshed slots)
+    CdfCtx end_cdf;
+    bool have_end_cdf = false;
+
+    void init(const SeqHdr& seq, const FrameHdr& h) {
+        fh = h;
+        bit_depth = seq.bit_depth;
+        subx = seq.subsampling_x;
+        suby = seq.subsampling_y;
+        mono = seq.mono_chrome;
+        sb128 = seq.use_128x128_superblock;
+        mi_cols = h.mi_cols;
+        mi_rows = h.mi_rows;
+        size_t n = (size_t)mi_cols * mi_rows;
+        mi.assign(n, nullptr);
+        inter_tx.assign(n, 0);
+        tx_types.assign(n, 0);
+        seg_ids.assign(n, 0);
+        skip_mi.assign(n, 0);
+        for (int p = 0; p < 3; p++) {
+            int sx = p ? subx : 0, sy = p ? suby : 0;
+            size_t pn = (size_t)((mi_cols + sx) >> sx) * ((mi_rows + sy) >> sy);
+            lf_tx[p].assign(pn, 0);
+            lf[p].assign(pn, LfEdge{0, 0, 0, 0});
+        }
+        int c64 = (mi_cols + 15) >> 4, r64 = (mi_rows + 15) >> 4;
+        cdef_idx.assign((size_t)c64 * r64, -1);
+        tx.clear();
+        coefs.clear();
+        sbs.clear();
+        pal.clear();
+        blocks.clear();
+    }
+    int plane_w4(int p) const { int sx = p ? subx : 0; return (mi_cols + sx) >> sx; }
+    int plane_h4(int p) const { int sy = p ? suby : 0; return (mi_rows + sy) >> sy; }
+};
+
+}  // namespace av1r

@@ -1,0 +1,97 @@
+// Multi-symbol adaptive arithmetic decoder (AV1 spec 8.2: init_symbol / read_symbol /
+// read_bool / read_literal / exit_symbol) -- host side, sequential by nature.
+// CDFs are stored inverted (32768 - cdf) with the adaptation counter right after the symbols.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace av1r {
+
+struct Msac {
+    const uint8_t* bptr = nullptr;
+    const uint8_t* end = nullptr;
+    uint64_t dif = 0;
+    uint32_t rng = 0;
+    int cnt = 0;
+    bool update = true;
+
+    void init(const uint8_t* data, size_t sz, bool disable_cdf_update) {
+        bptr = data;
+        end = data + sz;
+        dif = ((uint64_t)1 << 63) - 1;
+        rng = 0x8000;
+        cnt = -15;
+        update = !disable_cdf_update;
+        refill();
+    }
+    inline void refill() {
+        int s = 64 - 9 - (cnt + 15);
+        for (; s >= 0 && bptr < end; s -= 8, bptr++) {
+            dif ^= (uint64_t)bptr[0] << s;
+            cnt += 8;
+        }
+        if (bptr >= end) cnt = 0x4000;  // out of data: keep shifting in the implicit padding
+    }
+    inline void normalize(uint64_t d, uint32_t r) {
+        int sh = 15 - (31 - __builtin_clz(r));   // 16 - ilog(r)
+        cnt -= sh;
+        dif = ((d + 1) << sh) - 1;
+        rng = r << sh;
+        if (cnt < 0) refill();
+    }
+    // decode one symbol out of n with inverted cdf `c` (c[n-1] == 0, c[n] = counter); adapts.
+    inline int symbol(uint16_t* c, int n) {
+        const uint32_t r = rng;
+        const uint32_t v16 = (uint32_t)(dif >> 48);
+        uint32_t u, v = r;
+        int s = -1;
+        do {
+            u = v;
+            s++;
+            v = ((r >> 8) * (uint32_t)(c[s] >> 6) >> 1) + 4 * (uint32_t)(n - 1 - s);
+        } while (v16 < v);
+        normalize(dif - ((uint64_t)v << 48), u - v);
+        if (update) adapt(c, s, n);
+        return s;
+    }
+    static inline void adapt(uint16_t* c, int val, int n) {
+        const int cnt_ = c[n];
+        const int rate = 3 + (cnt_ > 15) + (cnt_ > 31) + (n > 3 ? 2 : (n > 2 ? 1 : (n > 1 ? 1 : 0)));
+        // Min(FloorLog2(n), 2): n=2 ->1, n=3 ->1, n>=4 ->2
+        for (int i = 0; i < n - 1; i++) {
+            if (i < val) c[i] += (32768 - c[i]) >> rate;
+            else c[i] -= c[i] >> rate;
+        }
+        c[n] = cnt_ + (cnt_ < 32);
+    }
+    inline int bit() {   // read_bool / one bit of a literal: equiprobable, no adaptation
+        const uint32_t r = rng;
+        const uint32_t v = ((r >> 8) << 7) + 4;
+        const uint64_t vw = (uint64_t)v << 48;
+        int ret;
+        uint64_t d = dif;
+        uint32_t rn;
+        if (d >= vw) { rn = r - v; d -= vw; ret = 0; } else { rn = v; ret = 1; }
+        normalize(d, rn);
+        return ret;
+    }
+    inline int literal(int n) {
+        int x = 0;
+        for (int i = 0; i < n; i++) x = 2 * x + bit();
+        return x;
+    }
+    // non-adaptive symbol with an explicit 2-entry inverted cdf (split_or_horz / split_or_vert)
+    inline int bool_icdf(uint32_t icdf0) {
+        const uint32_t r = rng;
+        const uint32_t v = ((r >> 8) * (icdf0 >> 6) >> 1) + 4;
+        const uint64_t vw = (uint64_t)v << 48;
+        uint64_t d = dif;
+        uint32_t rn;
+        int ret;
+        if (d >= vw) { rn = r - v; d -= vw; ret = 0; } else { rn = v; ret = 1; }
+        normalize(d, rn);
+        return ret;
+    }
+};
+
+}  // namespace av1r

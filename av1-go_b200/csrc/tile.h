@@ -1,0 +1,87 @@
+// Per-tile symbol parse (host, sequential): partition tree, mode info, transform sizes/types,
+// coefficients -> device work-lists.  Spec 5.11 (syntax) + 8.3 (CDF selection).
+#pragma once
+#include <string>
+
+#include "frame_state.h"
+#include "msac.h"
+#include "obu.h"
+
+namespace av1r {
+
+struct RefFrameInfo;   // inter prediction state of reference slots (defined in inter.h)
+
+class TileDecoder {
+public:
+    TileDecoder(const SeqHdr& seq, const HeaderParser& hp, FrameWork& fw, const CdfCtx& init_cdf);
+    // returns 0, AV1R_EBITSTREAM or AV1R_ENOSYS (err holds the reason)
+    int decode_tile(const uint8_t* data, size_t sz, int tile_row, int tile_col);
+    CdfCtx cdf;
+    std::string err;
+
+private:
+    const SeqHdr& seq;
+    const HeaderParser& hp;
+    FrameWork& fw;
+    const FrameHdr& fh;
+    Msac ms;
+    int fail_code = 0;
+    // tile geometry
+    int mi_row_start = 0, mi_row_end = 0, mi_col_start = 0, mi_col_end = 0;
+    int current_q_index = 0;
+    int read_deltas = 0;
+    int delta_lf[4] = {0, 0, 0, 0};
+    // coefficient contexts (absolute 4x4 indices per plane)
+    std::vector<uint8_t> above_level[3], above_dc[3], left_level[3], left_dc[3];
+    std::vector<uint8_t> above_seg_pred, left_seg_pred;
+    // loop restoration references
+    int ref_sgr_xqd[3][2];
+    int ref_lr_wiener[3][2][3];
+    // per-superblock "block decoded" flags: [plane][y+1][x+1], y,x in -1..32
+    uint8_t block_decoded[3][35][35];
+    // current block
+    BlockInfo* b = nullptr;
+    int mi_row = 0, mi_col = 0, bw4 = 0, bh4 = 0;
+    int avail_u = 0, avail_l = 0, avail_u_chroma = 0, avail_l_chroma = 0;
+    int max_luma_w = 0, max_luma_h = 0;
+    int32_t quant[1024];
+
+    bool fail(int code, const char* msg) { if (!fail_code) { fail_code = code; err = msg; } return false; }
+    bool is_inside(int r, int c) const { return c >= mi_col_start && c < mi_col_end && r >= mi_row_start && r < mi_row_end; }
+    BlockInfo* blk(int r, int c) const { return fw.mi[(size_t)r * fw.mi_cols + c]; }
+
+    void clear_block_decoded_flags(int r, int c, int sb4);
+    void read_lr(int r, int c, int bsize);
+    void read_lr_unit(int plane, int unit_row, int unit_col);
+    int decode_subexp_bool(int num_syms, int k);
+    int decode_signed_subexp_with_ref_bool(int low, int high, int k, int r);
+    bool decode_partition(int r, int c, int bsize);
+    bool decode_block(int r, int c, int bsize);
+    void intra_frame_mode_info();
+    void intra_segment_id();
+    void read_segment_id();
+    void read_skip();
+    void read_cdef();
+    void read_delta_qindex();
+    void read_delta_lf();
+    void intra_angle_info_y();
+    void intra_angle_info_uv();
+    void read_cfl_alphas();
+    void filter_intra_mode_info();
+    void read_block_tx_size();
+    void read_tx_size(int allow_select);
+    void reset_block_context();
+    void residual();
+    void transform_block(int plane, int base_x, int base_y, int txsz, int x, int y);
+    int coeffs(int plane, int start_x, int start_y, int txsz, TxRec& rec);
+    int get_tx_set(int txsz) const;
+    void read_transform_type(int x4, int y4, int txsz);
+    int compute_tx_type(int plane, int txsz, int block_x, int block_y) const;
+    int filter_type(int plane) const;
+    // inter (tile_inter.cpp)
+    void inter_frame_mode_info();
+    void read_var_tx_size(int row, int col, int txsz, int depth);
+    void transform_tree(int start_x, int start_y, int w, int h);
+};
+
+}  // namespace av1r

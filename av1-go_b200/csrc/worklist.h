@@ -1,0 +1,81 @@
+// Host <-> device contract: the work-lists the sequential host parse emits and the sm_100a
+// kernels consume.  POD only; shared by g++ (parser, oracle) and nvcc (kernels).
+#pragma once
+#include <stdint.h>
+
+namespace av1r {
+
+// One record per transform block, in decode order (which is also the only valid order for
+// intra prediction inside a superblock).  32 bytes.
+struct TxRec {
+    uint16_t x4, y4;        // top-left in the plane, in units of 4 samples
+    uint8_t plane;          // 0 Y, 1 U, 2 V
+    uint8_t txsz;           // TxSize
+    uint8_t txtp;           // TxType (16 = WHT, lossless)
+    uint8_t mode;           // TXM_* below or intra PredMode 0..12
+    uint16_t eob;           // 0 = no coded residual
+    uint8_t qidx;           // qindex used for dequantisation (segment + delta-q applied)
+    uint8_t flags;          // TXF_*
+    uint32_t coef_off;      // first token of this block in the coefficient token array
+    int8_t angle_delta;     // -3..3 (directional modes)
+    uint8_t fi_mode;        // filter-intra mode 0..4 (mode == TXM_FILTER_INTRA)
+    int16_t cfl_alpha;      // signed CfL alpha for this plane (mode == TXM_CFL)
+    uint16_t cfl_max_w4;    // luma samples available to CfL, /4, absolute (MaxLumaW, MaxLumaH)
+    uint16_t cfl_max_h4;
+    uint32_t pal_off;       // palette: offset into the palette byte array (colours + index map)
+    uint8_t qm_level;       // quantiser-matrix level (15 = flat)
+    uint8_t seg_id;
+    uint8_t bw4_log2;       // log2 of the *prediction block* width/height in 4-sample units (plane),
+    uint8_t bh4_log2;       //   needed by deblock edge classification
+};
+static_assert(sizeof(TxRec) == 32, "TxRec must stay 32 bytes");
+
+enum : uint8_t {
+    TXM_CFL = 13,           // DC_PRED followed by chroma-from-luma
+    TXM_PALETTE = 14,
+    TXM_FILTER_INTRA = 15,
+    TXM_INTER = 255,        // no intra prediction: residual is added to the inter predictor
+};
+enum : uint8_t {
+    TXF_HAVE_LEFT = 1, TXF_HAVE_ABOVE = 2, TXF_HAVE_ABOVE_RIGHT = 4, TXF_HAVE_BELOW_LEFT = 8,
+    TXF_SMOOTH_EDGE = 16,   // get_filter_type(): a neighbour uses a smooth predictor
+    TXF_LOSSLESS = 32,
+    TXF_SB_FIRST = 64,      // first record of a superblock (wavefront bookkeeping)
+};
+
+// coefficient token: bits 0..9 position (row * min(txw,32) + col), bits 10..31 signed level
+static inline uint32_t coef_token(int pos, int level) { return ((uint32_t)level << 10) | (uint32_t)pos; }
+static inline int coef_token_pos(uint32_t t) { return (int)(t & 1023); }
+static inline int coef_token_level(uint32_t t) { return (int32_t)t >> 10; }
+
+// Per-superblock slice of the TxRec list (wavefront unit of the intra kernel).
+struct SbRange {
+    uint32_t first, count;  // TxRec indices
+    uint16_t sb_row, sb_col;  // in superblock units, absolute in the frame
+    uint16_t tile_sb_col0;    // first superblock column of the tile (wavefront does not cross tiles)
+    uint16_t tile_sb_col1;    // one past the last
+    uint16_t tile_sb_row0, pad;
+};
+
+// Per-4x4 loop-filter description, one byte pair per plane 4x4 unit and direction:
+//   len: 0 = no edge here, else filter length 4 / 6 / 8 / 14 (13 for luma-wide is stored as 14)
+//   lvl: filter level 0..63 to use for this edge
+struct LfEdge {
+    uint8_t len_v, lvl_v, len_h, lvl_h;
+};
+
+// Frame-level parameters every kernel needs (kept small; passed by value or via constant memory).
+struct FrameParams {
+    int32_t w[3], h[3];            // visible plane sizes (upscaled == coded here; superres handled separately)
+    int32_t cw[3], ch[3];          // coded plane sizes rounded up to 8 luma samples (MiCols*4, MiRows*4)
+    int32_t bd, subx, suby, mono;
+    int32_t mi_cols, mi_rows, sb128;
+    int32_t dq_dc[3], dq_ac[3];    // per-plane qindex deltas (DeltaQYDc ... DeltaQVAc)
+    int32_t enable_edge_filter;
+    int32_t lf_sharpness;
+    int32_t cdef_damping, cdef_bits;
+    int32_t cdef_y_pri[8], cdef_y_sec[8], cdef_uv_pri[8], cdef_uv_sec[8];
+    int32_t lr_type[3], lr_size[3];
+};
+
+}  // namespace av1r

@@ -88,7 +88,18 @@ def load_base():
     return real - e.addr("aom_codec_av1_cx")
 
 
+_RTCD_DONE = False
+
+
 def call_local(name, restype, argtypes, *args):
+    """Call a (possibly non-exported) libaom function by symbol-table address."""
+    global _RTCD_DONE
     base = load_base()
+    if not _RTCD_DONE:
+        _RTCD_DONE = True
+        # run-time CPU dispatch tables (av1_round_shift_array etc. are function pointers until then)
+        for init in ("av1_rtcd", "aom_dsp_rtcd", "aom_scale_rtcd"):
+            if init in elf().syms:
+                C.CFUNCTYPE(None)(base + elf().addr(init))()
     fn = C.CFUNCTYPE(restype, *argtypes)(base + elf().addr(name))
     return fn(*args)
