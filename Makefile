@@ -32,9 +32,12 @@ $(LIBDIR)/libav1r.so: $(HOST_OBJS) $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -lpthread
 
-oracle/_build/liboracle.so: $(ORACLE_C) $(ORACLE_CPP) $(wildcard $(CSRC)/tables/*.inc)
+# the oracle links the product's *host parser* objects (never the other way round)
+PARSER_OBJS := $(OBJDIR)/obu.o $(OBJDIR)/tile.o $(OBJDIR)/tile_inter.o $(OBJDIR)/stream_parser.o
+oracle/_build/liboracle.so: $(ORACLE_C) $(ORACLE_CPP) $(PARSER_OBJS) $(wildcard oracle/*.h) $(wildcard $(CSRC)/kernels/*.h) $(wildcard $(CSRC)/tables/*.inc)
 	@mkdir -p oracle/_build
-	$(CXX) -O2 -g -fPIC -shared -x c $(ORACLE_C) $(if $(ORACLE_CPP),-x c++ -std=c++17 $(ORACLE_CPP)) -o $@ -ldl
+	$(CC) -O2 -g -fPIC -c oracle/filmgrain.c -o oracle/_build/filmgrain.o
+	$(CXX) -O2 -g -std=c++17 -fPIC -shared -Iinclude $(ORACLE_CPP) oracle/_build/filmgrain.o $(PARSER_OBJS) -o $@ -ldl
 
 clean:
 	rm -rf build $(LIBDIR) oracle/_build

@@ -1,0 +1,49 @@
+// Stream-level host driver: temporal unit -> OBUs -> frame headers -> per-tile parse ->
+// FrameWork (device work-lists) + reference bookkeeping for everything the *parse* needs from
+// earlier frames (CDFs, segment maps, motion fields).  No pixel work happens here.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "frame_state.h"
+#include "obu.h"
+
+namespace av1r {
+
+struct ParsedFrame {
+    std::shared_ptr<FrameWork> fw;   // null when show_existing_slot >= 0
+    int show_existing_slot = -1;     // show_existing_frame: output the frame stored in this slot
+    FrameHdr fh;
+    int64_t pts = 0;
+};
+
+class StreamParser {
+public:
+    StreamParser();
+    HeaderParser hp;
+    std::string err;
+    // Parses one temporal unit; appends one ParsedFrame per frame (shown or not) in decode order.
+    // Returns 0 or AV1R_E*.
+    int parse_tu(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out);
+
+private:
+    CdfCtx slot_cdf_[NUM_REF_FRAMES];
+    std::shared_ptr<FrameWork> slot_fw_[NUM_REF_FRAMES];   // parse-side state of the frame in each slot
+    // frame being assembled (frame header seen, tile groups arriving)
+    std::shared_ptr<FrameWork> cur_;
+    FrameHdr cur_fh_;
+    CdfCtx cur_init_cdf_;
+    int tiles_done_ = 0;
+    bool have_frame_ = false;
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int begin_frame(const FrameHdr& fh);
+    int tile_group(const uint8_t* payload, size_t size, size_t offset);
+    int finish_frame(int64_t pts, std::vector<ParsedFrame>& out);
+};
+
+void cdf_clear_counters(CdfCtx& c);
+// host pre-pass of the deblocking filter: per-4x4 edge length + level (spec 7.14.2 - 7.14.5)
+void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw);
+
+}  // namespace av1r

@@ -804,6 +804,7 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
         if (fail_code) return;
     }
     rec.eob = (uint16_t)eob;
+    rec.ntok = (uint16_t)(fw.coefs.size() - rec.coef_off);
     if (!b->is_inter || eob > 0) {
         fw.tx.push_back(rec);
         fw.tx_blocks++;

@@ -25,8 +25,7 @@ struct TxRec {
     uint32_t pal_off;       // palette: offset into the palette byte array (colours + index map)
     uint8_t qm_level;       // quantiser-matrix level (15 = flat)
     uint8_t seg_id;
-    uint8_t bw4_log2;       // log2 of the *prediction block* width/height in 4-sample units (plane),
-    uint8_t bh4_log2;       //   needed by deblock edge classification
+    uint16_t ntok;          // number of (non-zero) coefficient tokens at coef_off (<= eob)
 };
 static_assert(sizeof(TxRec) == 32, "TxRec must stay 32 bytes");
 
