@@ -120,3 +120,86 @@ def probe_buffer(data):
     if rc:
         raise RuntimeError(f"av1r_probe_buffer -> {rc}")
     return info
+
+
+class Decoder:
+    """Thin wrapper over av1r_open / av1r_submit_tu / av1r_collect (the calls the cgo package makes)."""
+
+    def __init__(self, device=0, parity_md5=0, apply_grain=1, inloop_filters=7, keep_frames=0, streams=2, frames_in_flight=8):
+        l = lib()
+        l.av1r_open.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        l.av1r_close.argtypes = [C.c_void_p]
+        l.av1r_submit_tu.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int64]
+        l.av1r_collect.argtypes = [C.c_void_p, C.POINTER(FrameResult), C.c_int, C.POINTER(C.c_int)]
+        l.av1r_flush.argtypes = [C.c_void_p]
+        l.av1r_last_error.argtypes = [C.c_void_p]
+        l.av1r_last_error.restype = C.c_char_p
+        l.av1r_copy_frame.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t]
+        cfg = Config()
+        l.av1r_default_config(C.byref(cfg))
+        cfg.device, cfg.parity_md5, cfg.apply_grain, cfg.inloop_filters = device, parity_md5, apply_grain, inloop_filters
+        cfg.keep_frames, cfg.streams, cfg.frames_in_flight = keep_frames, streams, frames_in_flight
+        self.l = l
+        self.ctx = C.c_void_p()
+        rc = l.av1r_open(C.byref(cfg), C.byref(self.ctx))
+        if rc:
+            raise RuntimeError(f"av1r_open -> {rc}")
+        self.results = []
+
+    def error(self):
+        return self.l.av1r_last_error(self.ctx).decode()
+
+    def submit(self, tu, pts=0):
+        rc = self.l.av1r_submit_tu(self.ctx, tu, len(tu), pts)
+        if rc:
+            raise RuntimeError(f"av1r_submit_tu -> {rc}: {self.error()}")
+        self._collect()
+
+    def _collect(self):
+        buf = (FrameResult * 32)()
+        while True:
+            n = C.c_int(0)
+            rc = self.l.av1r_collect(self.ctx, buf, 32, C.byref(n))
+            if rc:
+                raise RuntimeError(f"av1r_collect -> {rc}: {self.error()}")
+            for i in range(n.value):
+                r = FrameResult()
+                C.memmove(C.byref(r), C.byref(buf[i]), C.sizeof(FrameResult))
+                self.results.append(r)
+            if n.value == 0:
+                break
+
+    def flush(self):
+        rc = self.l.av1r_flush(self.ctx)
+        if rc:
+            raise RuntimeError(f"av1r_flush -> {rc}: {self.error()}")
+        self._collect()
+
+    def frame_planes(self, res):
+        """keep_frames mode: copy the three planes of a collected frame to numpy arrays."""
+        import numpy as np
+        out = []
+        bps = 1 if res.bpc == 8 else 2
+        for p in range(3):
+            w = res.w if p == 0 else (res.w + 1) // 2
+            h = res.h if p == 0 else (res.h + 1) // 2
+            cw = (w + 7) // 8 * 8 if p == 0 else ((res.w + 7) // 8 * 8) // 2
+            chh = (h + 7) // 8 * 8 if p == 0 else ((res.h + 7) // 8 * 8) // 2
+            a = np.zeros((chh, cw * bps), dtype=np.uint8)
+            rc = self.l.av1r_copy_frame(self.ctx, res.frame_handle, p, a.ctypes.data, cw * bps)
+            if rc:
+                raise RuntimeError(f"av1r_copy_frame -> {rc}")
+            a = a.view(np.uint8 if bps == 1 else np.dtype("<u2"))[:h, :w]
+            out.append(np.ascontiguousarray(a))
+        return out
+
+    def close(self):
+        if self.ctx:
+            self.l.av1r_close(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

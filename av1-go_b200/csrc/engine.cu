@@ -1,77 +1,685 @@
-// Engine skeleton (device plumbing); the frame pipeline is filled in as stages land.
+// Decode engine: host parse -> pinned staging -> one H2D per frame -> reconstruction kernels.
+//
+//   per frame:  [H2D work-list arena] -> K1 itx -> K3 intra wavefront -> K4 deblock (V,H) -> K5 CDEF
+//               -> K8 film grain (display copy) -> plane digests -> [D2H 24 B | D2H planes in parity mode]
+// Frames are issued round-robin over `streams` CUDA streams with `frames_in_flight` resource slots,
+// so the low-occupancy wavefront kernel of one frame overlaps the streaming filters of others.
+// No CPU fallback exists: without a CUDA device av1r_open fails.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <vector>
 
+#include "../../include/av1r_stages.h"
 #include "demux.h"
 #include "engine.h"
-#include "obu.h"
+#include "kernels/intra.h"
+#include "md5.h"
+#include "stream_parser.h"
 
 namespace av1r {
+
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) {                                         \
+            err = std::string(#call) + ": " + cudaGetErrorString(_e);    \
+            return AV1R_EIO;                                             \
+        }                                                                \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = align_up(n + n / 4, 1 << 16);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct PinBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = align_up(n + n / 4, 1 << 16);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+// A frame buffer on the device (3 planes in one allocation).
+struct DevFrameBuf {
+    uint8_t* base = nullptr;
+    DevPlanes pl;
+    int cw[3], ch[3], bps;
+    size_t bytes = 0;
+    ~DevFrameBuf() { if (base) cudaFree(base); }
+};
+
+static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::string& err) {
+    auto f = std::make_shared<DevFrameBuf>();
+    f->bps = fp.bd == 8 ? 1 : 2;
+    size_t off[3], total = 0;
+    for (int p = 0; p < 3; p++) {
+        f->cw[p] = fp.cw[p];
+        f->ch[p] = fp.ch[p];
+        f->pl.pitch[p] = (uint32_t)align_up((size_t)fp.cw[p] * f->bps, 256);
+        off[p] = total;
+        total += align_up((size_t)f->pl.pitch[p] * fp.ch[p], 256);
+    }
+    if (cudaMalloc(&f->base, total) != cudaSuccess) {
+        err = "cudaMalloc(frame) failed";
+        return nullptr;
+    }
+    for (int p = 0; p < 3; p++) f->pl.p[p] = f->base + off[p];
+    f->bytes = total;
+    return f;
+}
+
+// Layout of the per-frame work-list arena (same offsets on host staging and device).
+struct WorkLayout {
+    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, total;
+    int n_recs, n_coefs, n_order, n_sbs, n_items;
+};
+
+struct DevWork {
+    WorkLayout lay;
+    DevFrameParams fp;
+    FrameHdr fh;
+    int lf_on = 0, lf_plane_on[3] = {0, 0, 0}, cdef_on = 0, lr_on = 0;
+    uint64_t coded_samples = 0, coef_tokens = 0;
+    double parse_ms = 0;
+    std::vector<SbRowItem> items_host;
+};
+
+static void fill_params(const SeqHdr& seq, const FrameWork& fw, DevFrameParams& fp) {
+    memset(&fp, 0, sizeof(fp));
+    const FrameHdr& fh = fw.fh;
+    fp.bd = seq.bit_depth;
+    fp.subx = seq.subsampling_x;
+    fp.suby = seq.subsampling_y;
+    fp.mono = seq.mono_chrome;
+    fp.mi_cols = fh.mi_cols;
+    fp.mi_rows = fh.mi_rows;
+    fp.sb128 = seq.use_128x128_superblock;
+    for (int p = 0; p < 3; p++) {
+        const int sx = p ? fp.subx : 0, sy = p ? fp.suby : 0;
+        fp.w[p] = (fh.upscaled_width + sx) >> sx;
+        fp.h[p] = (fh.frame_height + sy) >> sy;
+        fp.cw[p] = (fh.mi_cols * 4) >> sx;
+        fp.ch[p] = (fh.mi_rows * 4) >> sy;
+        fp.pw4[p] = (fh.mi_cols + sx) >> sx;
+        fp.ph4[p] = (fh.mi_rows + sy) >> sy;
+    }
+    fp.dq_dc[0] = fh.delta_q_y_dc; fp.dq_ac[0] = 0;
+    fp.dq_dc[1] = fh.delta_q_u_dc; fp.dq_ac[1] = fh.delta_q_u_ac;
+    fp.dq_dc[2] = fh.delta_q_v_dc; fp.dq_ac[2] = fh.delta_q_v_ac;
+    fp.enable_edge_filter = seq.enable_intra_edge_filter;
+    fp.lf_sharpness = fh.lf.sharpness;
+    fp.cdef_damping = fh.cdef_damping;
+    for (int i = 0; i < 8; i++) {
+        fp.cdef_y_pri[i] = fh.cdef_y_pri[i];
+        fp.cdef_y_sec[i] = fh.cdef_y_sec[i];
+        fp.cdef_uv_pri[i] = fh.cdef_uv_pri[i];
+        fp.cdef_uv_sec[i] = fh.cdef_uv_sec[i];
+    }
+}
+
+// Computes the arena layout of a parsed frame.
+static void plan_layout(const FrameWork& fw, DevWork& dw) {
+    WorkLayout& L = dw.lay;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    L.n_recs = (int)fw.tx.size();
+    L.n_coefs = (int)fw.coefs.size();
+    int n_order = 0;
+    for (const TxRec& r : fw.tx) n_order += r.eob > 0;
+    L.n_order = n_order;
+    L.n_sbs = (int)fw.sbs.size();
+    // work items = runs of superblocks sharing (tile, sb_row); sbs are stored tile by tile, row by row
+    dw.items_host.clear();
+    for (int i = 0; i < L.n_sbs;) {
+        int j = i;
+        while (j < L.n_sbs && fw.sbs[j].sb_row == fw.sbs[i].sb_row && fw.sbs[j].tile_sb_col0 == fw.sbs[i].tile_sb_col0 &&
+               fw.sbs[j].tile_sb_row0 == fw.sbs[i].tile_sb_row0)
+            j++;
+        SbRowItem it;
+        it.first_sb = (uint32_t)i;
+        it.n_sb = (uint32_t)(j - i);
+        it.frame = 0;
+        it.dep_item = -1;
+        if (fw.sbs[i].sb_row > fw.sbs[i].tile_sb_row0) {
+            // the previous item of the same tile is the row above
+            for (int k = (int)dw.items_host.size() - 1; k >= 0; k--) {
+                const SbRange& a = fw.sbs[dw.items_host[k].first_sb];
+                if (a.tile_sb_col0 == fw.sbs[i].tile_sb_col0 && a.tile_sb_row0 == fw.sbs[i].tile_sb_row0 && a.sb_row + 1 == fw.sbs[i].sb_row) {
+                    it.dep_item = k;
+                    break;
+                }
+            }
+        }
+        dw.items_host.push_back(it);
+        i = j;
+    }
+    L.n_items = (int)dw.items_host.size();
+    L.recs = take(sizeof(TxRec) * std::max(1, L.n_recs));
+    L.coefs = take(sizeof(uint32_t) * std::max(1, L.n_coefs));
+    L.order = take(sizeof(uint32_t) * std::max(1, L.n_order));
+    L.sbs = take(sizeof(SbRange) * std::max(1, L.n_sbs));
+    L.items = take(sizeof(SbRowItem) * std::max(1, L.n_items));
+    L.iframe = take(sizeof(IntraFrame));
+    for (int p = 0; p < 3; p++) L.lf[p] = take(sizeof(LfEdge) * std::max<size_t>(1, fw.lf[p].size()));
+    L.cdef_idx = take(std::max<size_t>(1, fw.cdef_idx.size()));
+    L.skip_mi = take(std::max<size_t>(1, fw.skip_mi.size()));
+    L.total = o;
+}
+
+static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
+    const WorkLayout& L = dw.lay;
+    if (L.n_recs) memcpy(h + L.recs, fw.tx.data(), sizeof(TxRec) * L.n_recs);
+    if (L.n_coefs) memcpy(h + L.coefs, fw.coefs.data(), sizeof(uint32_t) * L.n_coefs);
+    uint32_t* ord = (uint32_t*)(h + L.order);
+    int k = 0;
+    for (int i = 0; i < L.n_recs; i++)
+        if (fw.tx[i].eob > 0) ord[k++] = (uint32_t)i;
+    if (L.n_sbs) memcpy(h + L.sbs, fw.sbs.data(), sizeof(SbRange) * L.n_sbs);
+    if (L.n_items) memcpy(h + L.items, dw.items_host.data(), sizeof(SbRowItem) * L.n_items);
+    for (int p = 0; p < 3; p++)
+        if (!fw.lf[p].empty()) memcpy(h + L.lf[p], fw.lf[p].data(), sizeof(LfEdge) * fw.lf[p].size());
+    if (!fw.cdef_idx.empty()) memcpy(h + L.cdef_idx, fw.cdef_idx.data(), fw.cdef_idx.size());
+    if (!fw.skip_mi.empty()) memcpy(h + L.skip_mi, fw.skip_mi.data(), fw.skip_mi.size());
+}
+
+// Execution resources of one in-flight frame.
+struct FrameSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    PinBuf staging;
+    DevBuf arena;        // submit path: the frame's work-lists
+    DevBuf residual;
+    DevBuf sync;         // progress counters + ticket
+    DevBuf grain_scratch;
+    DevBuf cks_dev;
+    PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
+    PinBuf planes_host;
+    bool busy = false;
+    // frame buffers touched by the work queued on this slot: kept alive (out of the recycling pool)
+    // until the slot's completion event has been waited on
+    std::vector<std::shared_ptr<DevFrameBuf>> hold;
+};
+
+struct Pending {
+    av1r_frame_result res;
+    int slot = -1;                    // slot whose events/digests belong to this output (-1: none pending)
+    std::shared_ptr<DevFrameBuf> shown;
+    bool need_md5 = false;
+    int w[3], h[3], bps;
+    size_t host_off[3];
+};
+
+struct ClipFrame {
+    DevWork dw;
+    DevBuf arena;
+    bool shown = false;
+};
 
 struct EngineImpl {
     av1r_config cfg;
     std::string err;
-    HeaderParser hp;
+    StreamParser sp;
     bool opened = false;
-    std::deque<av1r_frame_result> done;
+    std::vector<cudaStream_t> streams;
+    std::vector<std::unique_ptr<FrameSlot>> slots;
+    int next_slot = 0, next_stream = 0;
+    std::deque<Pending> pending;          // outputs in display order
+    std::shared_ptr<DevFrameBuf> refs[8];
+    FilmGrainParams ref_fg[8];
+    std::vector<std::shared_ptr<DevFrameBuf>> kept;   // keep_frames handles
+    std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
+    int64_t frames_decoded = 0;
+
+    int wait_slot(FrameSlot& s);
+    int finish_pending(Pending& p);
+    std::shared_ptr<DevFrameBuf> get_frame(const DevFrameParams& fp);
+    int run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_arena, std::shared_ptr<DevFrameBuf>& out_ref);
+    int emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<DevFrameBuf>& frame, const FrameHdr& fh, const FilmGrainParams& fg,
+                    const DevFrameParams& fp, int64_t pts, double parse_ms, bool existing);
+    int decode_parsed(ParsedFrame& pf);
 };
 
+std::shared_ptr<DevFrameBuf> EngineImpl::get_frame(const DevFrameParams& fp) {
+    for (size_t i = 0; i < pool.size(); i++) {
+        auto& f = pool[i];
+        if (f.use_count() == 1 && f->cw[0] == fp.cw[0] && f->ch[0] == fp.ch[0] && f->cw[1] == fp.cw[1] && f->ch[1] == fp.ch[1] &&
+            f->bps == (fp.bd == 8 ? 1 : 2))
+            return f;
+    }
+    auto f = alloc_frame(fp, err);
+    if (f) pool.push_back(f);
+    return f;
+}
+
+int EngineImpl::wait_slot(FrameSlot& s) {
+    if (s.busy) CK(cudaEventSynchronize(s.ev1));
+    s.busy = false;
+    s.hold.clear();
+    return 0;
+}
+
+// Enqueue the reconstruction of one frame on slot s.  d_arena = device work-list arena.
+int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_arena, std::shared_ptr<DevFrameBuf>& out_ref) {
+    const WorkLayout& L = dw.lay;
+    const DevFrameParams& fp = dw.fp;
+    cudaStream_t st = s.stream;
+    auto recon = get_frame(fp);
+    if (!recon) return AV1R_ENOMEM;
+    s.hold.push_back(recon);
+    // residual planes
+    DevResidual res;
+    size_t roff[3], rtotal = 0;
+    for (int p = 0; p < 3; p++) {
+        res.pitch[p] = (uint32_t)align_up((size_t)fp.cw[p] * 2, 256);
+        roff[p] = rtotal;
+        rtotal += (size_t)res.pitch[p] * fp.ch[p];
+    }
+    CK(s.residual.ensure(rtotal));
+    for (int p = 0; p < 3; p++) res.p[p] = (int16_t*)(s.residual.p + roff[p]);
+    CK(s.sync.ensure(sizeof(int) * (L.n_items + 4)));
+    CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_items + 4), st));
+    // intra frame descriptor lives in the arena (device pointers patched here)
+    IntraFrame ifr;
+    ifr.recs = (const TxRec*)(d_arena + L.recs);
+    ifr.sbs = (const SbRange*)(d_arena + L.sbs);
+    ifr.frame = recon->pl;
+    ifr.res = res;
+    ifr.fp = fp;
+    CK(cudaMemcpyAsync((void*)(d_arena + L.iframe), &ifr, sizeof(ifr), cudaMemcpyHostToDevice, st));
+    CK(launch_itx(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
+    IntraLaunch il;
+    il.frames = (const IntraFrame*)(d_arena + L.iframe);
+    il.items = (const SbRowItem*)(d_arena + L.items);
+    il.progress = (int*)s.sync.p;
+    il.ticket = (int*)s.sync.p + L.n_items;
+    il.n_items = L.n_items;
+    CK(launch_intra(il, fp.bd, st));
+    std::shared_ptr<DevFrameBuf> cur = recon;
+    if (dw.lf_on && (cfg.inloop_filters & 1)) {
+        LfLaunch ll;
+        ll.frame = cur->pl;
+        for (int p = 0; p < 3; p++) {
+            ll.edges[p] = (const LfEdge*)(d_arena + L.lf[p]);
+            ll.plane_on[p] = dw.lf_plane_on[p];
+        }
+        ll.fp = fp;
+        CK(launch_deblock(ll, st));
+    }
+    if (dw.cdef_on && (cfg.inloop_filters & 2)) {
+        auto dst = get_frame(fp);
+        if (!dst) return AV1R_ENOMEM;
+        s.hold.push_back(dst);
+        CdefLaunch cl;
+        cl.src = cur->pl;
+        cl.dst = dst->pl;
+        cl.cdef_idx = (const int8_t*)(d_arena + L.cdef_idx);
+        cl.skip_mi = d_arena + L.skip_mi;
+        cl.fp = fp;
+        CK(launch_cdef(cl, st));
+        cur = dst;
+    }
+    if (dw.lr_on && (cfg.inloop_filters & 4)) {
+        err = "loop restoration is not supported yet";
+        return AV1R_ENOSYS;
+    }
+    out_ref = cur;
+    return 0;
+}
+
+int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<DevFrameBuf>& frame, const FrameHdr& fh, const FilmGrainParams& fg,
+                            const DevFrameParams& fp, int64_t pts, double parse_ms, bool existing) {
+    cudaStream_t st = s->stream;
+    std::shared_ptr<DevFrameBuf> shown = frame;
+    s->hold.push_back(frame);
+    if (cfg.apply_grain && fg.apply_grain) {
+        auto disp = get_frame(fp);
+        if (!disp) return AV1R_ENOMEM;
+        s->hold.push_back(disp);
+        CK(s->grain_scratch.ensure(av1r_film_grain_scratch_bytes()));
+        const void* src[3] = {frame->pl.p[0], frame->pl.p[1], frame->pl.p[2]};
+        void* dst[3] = {disp->pl.p[0], disp->pl.p[1], disp->pl.p[2]};
+        size_t sp_[3] = {frame->pl.pitch[0], frame->pl.pitch[1], frame->pl.pitch[2]};
+        size_t dp_[3] = {disp->pl.pitch[0], disp->pl.pitch[1], disp->pl.pitch[2]};
+        int rc = av1r_stage_film_grain((const av1r_film_grain_params*)&fg, fp.bd, fp.w[0], fp.h[0], fp.subx, fp.suby, fp.mono,
+                                       sp.hp.seq.matrix_coefficients == 0, src, sp_, dst, dp_, s->grain_scratch.p, st);
+        if (rc) {
+            err = av1r_stage_last_error();
+            return rc;
+        }
+        shown = disp;
+    }
+    CK(s->cks_dev.ensure(64));
+    CK(s->cks_host.ensure(64));
+    const int np = fp.mono ? 1 : 3;
+    for (int p = 0; p < np; p++)
+        CK(launch_plane_checksum(shown->pl.p[p], shown->pl.pitch[p], fp.w[p], fp.h[p], fp.bd, (uint64_t*)s->cks_dev.p + p, st));
+    CK(cudaMemcpyAsync(s->cks_host.p, s->cks_dev.p, 24, cudaMemcpyDeviceToHost, st));
+    Pending pd;
+    memset(&pd.res, 0, sizeof(pd.res));
+    pd.res.struct_size = sizeof(pd.res);
+    pd.res.pts = pts;
+    pd.res.w = fp.w[0];
+    pd.res.h = fp.h[0];
+    pd.res.bpc = fp.bd;
+    pd.res.layout = fp.mono ? 0 : (fp.subx && fp.suby ? 1 : (fp.subx ? 2 : 3));
+    pd.res.frame_type = fh.frame_type;
+    pd.res.shown_existing = existing;
+    pd.res.host_parse_ms = (float)parse_ms;
+    pd.res.frame_handle = -1;
+    pd.slot = slot_idx;
+    pd.shown = shown;
+    pd.bps = fp.bd == 8 ? 1 : 2;
+    for (int p = 0; p < 3; p++) { pd.w[p] = fp.w[p]; pd.h[p] = fp.h[p]; }
+    pd.need_md5 = cfg.parity_md5 != 0;
+    if (pd.need_md5) {
+        size_t total = 0;
+        for (int p = 0; p < np; p++) { pd.host_off[p] = total; total += (size_t)fp.w[p] * pd.bps * fp.h[p]; }
+        CK(s->planes_host.ensure(total));
+        for (int p = 0; p < np; p++)
+            CK(cudaMemcpy2DAsync(s->planes_host.p + pd.host_off[p], (size_t)fp.w[p] * pd.bps, shown->pl.p[p], shown->pl.pitch[p],
+                                 (size_t)fp.w[p] * pd.bps, fp.h[p], cudaMemcpyDeviceToHost, st));
+    }
+    if (cfg.keep_frames) {
+        kept.push_back(shown);
+        pd.res.frame_handle = (int64_t)kept.size() - 1;
+    }
+    pending.push_back(pd);
+    return 0;
+}
+
+int EngineImpl::decode_parsed(ParsedFrame& pf) {
+    const int slot_idx = next_slot;
+    FrameSlot& s = *slots[slot_idx];
+    next_slot = (next_slot + 1) % (int)slots.size();
+    // a slot can only be reused once the outputs that still read its pinned buffers were finalised
+    for (auto& p : pending)
+        if (p.slot == slot_idx) {
+            int rc = finish_pending(p);
+            if (rc) return rc;
+        }
+    int rc = wait_slot(s);
+    if (rc) return rc;
+    s.stream = streams[next_stream];
+    next_stream = (next_stream + 1) % (int)streams.size();
+    if (pf.show_existing_slot >= 0) {
+        auto f = refs[pf.show_existing_slot];
+        if (!f) { err = "show_existing_frame of an empty slot"; return AV1R_EBITSTREAM; }
+        DevFrameParams fp;
+        FrameWork dummy;
+        dummy.fh = pf.fh;
+        fill_params(sp.hp.seq, dummy, fp);
+        CK(cudaEventRecord(s.ev0, s.stream));
+        rc = emit_output(&s, slot_idx, f, pf.fh, pf.fh.fg, fp, pf.pts, 0, true);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.ev1, s.stream));
+        s.busy = true;
+        if (pf.fh.frame_type == KEY_FRAME)
+            for (int i = 0; i < 8; i++) refs[i] = f;
+        return 0;
+    }
+    const FrameWork& fw = *pf.fw;
+    if (fw.fh.using_qmatrix) { err = "quantiser matrices are not supported yet"; return AV1R_ENOSYS; }
+    DevWork dw;
+    fill_params(sp.hp.seq, fw, dw.fp);
+    dw.fh = fw.fh;
+    dw.lf_on = fw.fh.lf.level[0] || fw.fh.lf.level[1];
+    dw.lf_plane_on[0] = dw.lf_on;
+    dw.lf_plane_on[1] = dw.lf_on && fw.fh.lf.level[2];
+    dw.lf_plane_on[2] = dw.lf_on && fw.fh.lf.level[3];
+    dw.cdef_on = fw.fh.enable_cdef_frame;
+    dw.lr_on = fw.fh.uses_lr;
+    dw.parse_ms = fw.parse_ms;
+    plan_layout(fw, dw);
+    CK(s.staging.ensure(dw.lay.total));
+    CK(s.arena.ensure(dw.lay.total));
+    fill_arena(fw, dw, s.staging.p);
+    CK(cudaEventRecord(s.ev0, s.stream));
+    CK(cudaMemcpyAsync(s.arena.p, s.staging.p, dw.lay.total, cudaMemcpyHostToDevice, s.stream));
+    std::shared_ptr<DevFrameBuf> out;
+    rc = run_frame(s, dw, s.arena.p, out);
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++)
+        if ((fw.fh.refresh_frame_flags >> i) & 1) refs[i] = out;
+    if (fw.fh.show_frame) {
+        rc = emit_output(&s, slot_idx, out, fw.fh, fw.fh.fg, dw.fp, pf.pts, fw.parse_ms, false);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(s.ev1, s.stream));
+    s.busy = true;
+    frames_decoded++;
+    return 0;
+}
+
+int EngineImpl::finish_pending(Pending& p) {
+    if (p.slot < 0) return 0;
+    FrameSlot& s = *slots[p.slot];
+    CK(cudaEventSynchronize(s.ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s.ev0, s.ev1);
+    p.res.device_ms = ms;
+    memcpy(p.res.checksum, s.cks_host.p, 24);
+    if (p.need_md5) {
+        const int np = p.res.layout == 0 ? 1 : 3;
+        for (int pl = 0; pl < np; pl++) {
+            Md5 m;
+            m.update(s.planes_host.p + p.host_off[pl], (size_t)p.w[pl] * p.bps * p.h[pl]);
+            m.final(p.res.md5[pl]);
+        }
+    }
+    s.busy = false;
+    p.slot = -1;
+    p.shown.reset();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 Engine::Engine() : impl_(new EngineImpl()) {}
-Engine::~Engine() { delete impl_; }
+Engine::~Engine() {
+    if (impl_->opened) {
+        cudaSetDevice(impl_->cfg.device);
+        cudaDeviceSynchronize();
+        for (auto& s : impl_->slots) {
+            if (s->ev0) cudaEventDestroy(s->ev0);
+            if (s->ev1) cudaEventDestroy(s->ev1);
+        }
+        impl_->slots.clear();
+        impl_->pending.clear();
+        impl_->kept.clear();
+        impl_->pool.clear();
+        for (auto& r : impl_->refs) r.reset();
+        for (auto st : impl_->streams) cudaStreamDestroy(st);
+    }
+    delete impl_;
+}
 const std::string& Engine::error() const { return impl_->err; }
 
 int Engine::open(const av1r_config& cfg) {
-    impl_->cfg = cfg;
+    EngineImpl& E = *impl_;
+    std::string& err = E.err;
+    E.cfg = cfg;
+    if (E.cfg.streams <= 0) E.cfg.streams = 2;
+    if (E.cfg.frames_in_flight <= 0) E.cfg.frames_in_flight = 8;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
-        impl_->err = "no CUDA device available (this engine has no CPU fallback)";
+        err = "no CUDA device available (this engine has no CPU fallback)";
         return AV1R_EIO;
     }
     if (cfg.device < 0 || cfg.device >= ndev) {
-        impl_->err = "bad device ordinal";
+        err = "bad device ordinal";
         return AV1R_EINVAL;
     }
-    e = cudaSetDevice(cfg.device);
-    if (e != cudaSuccess) {
-        impl_->err = cudaGetErrorString(e);
-        return AV1R_EIO;
+    CK(cudaSetDevice(cfg.device));
+    E.streams.resize(E.cfg.streams);
+    for (auto& st : E.streams) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (int i = 0; i < E.cfg.frames_in_flight; i++) {
+        auto s = std::make_unique<FrameSlot>();
+        CK(cudaEventCreate(&s->ev0));
+        CK(cudaEventCreate(&s->ev1));
+        E.slots.push_back(std::move(s));
     }
-    impl_->opened = true;
+    E.opened = true;
     return 0;
 }
 
 int Engine::submit_tu(const uint8_t* data, size_t len, int64_t pts) {
-    (void)data; (void)len; (void)pts;
-    impl_->err = "tile reconstruction not built yet";
-    return AV1R_ENOSYS;
+    EngineImpl& E = *impl_;
+    cudaSetDevice(E.cfg.device);
+    std::vector<ParsedFrame> pfs;
+    int prc = E.sp.parse_tu(data, len, pts, pfs);
+    for (ParsedFrame& pf : pfs) {
+        int rc = E.decode_parsed(pf);
+        if (rc) return rc;
+    }
+    if (prc) {
+        E.err = E.sp.err;
+        return prc;
+    }
+    return 0;
 }
 
 int Engine::collect(av1r_frame_result* out, int cap, int* n) {
+    EngineImpl& E = *impl_;
+    cudaSetDevice(E.cfg.device);
     int k = 0;
-    while (k < cap && !impl_->done.empty()) {
-        out[k++] = impl_->done.front();
-        impl_->done.pop_front();
+    while (k < cap && !E.pending.empty()) {
+        Pending& p = E.pending.front();
+        if (p.slot >= 0) {
+            FrameSlot& s = *E.slots[p.slot];
+            if (cudaEventQuery(s.ev1) == cudaErrorNotReady) break;
+            int rc = E.finish_pending(p);
+            if (rc) { *n = k; return rc; }
+        }
+        out[k++] = p.res;
+        E.pending.pop_front();
     }
     *n = k;
     return 0;
 }
 
-int Engine::flush() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : AV1R_EIO; }
-int Engine::copy_frame(int64_t, int, void*, size_t) { return AV1R_EINVAL; }
-int Engine::release_frame(int64_t) { return AV1R_EINVAL; }
+int Engine::flush() {
+    EngineImpl& E = *impl_;
+    cudaSetDevice(E.cfg.device);
+    for (auto& p : E.pending) {
+        int rc = E.finish_pending(p);
+        if (rc) return rc;
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        E.err = "device synchronize failed";
+        return AV1R_EIO;
+    }
+    return 0;
+}
+
+int Engine::copy_frame(int64_t handle, int plane, void* dst, size_t dst_stride) {
+    EngineImpl& E = *impl_;
+    if (handle < 0 || handle >= (int64_t)E.kept.size() || !E.kept[handle] || plane < 0 || plane > 2) return AV1R_EINVAL;
+    cudaSetDevice(E.cfg.device);
+    auto& f = E.kept[handle];
+    // visible size is not stored in the buffer: copy the coded width, callers clip
+    cudaError_t e = cudaMemcpy2D(dst, dst_stride, f->pl.p[plane], f->pl.pitch[plane], std::min(dst_stride, (size_t)f->cw[plane] * f->bps),
+                                 f->ch[plane], cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        E.err = cudaGetErrorString(e);
+        return AV1R_EIO;
+    }
+    return 0;
+}
+
+int Engine::release_frame(int64_t handle) {
+    EngineImpl& E = *impl_;
+    if (handle < 0 || handle >= (int64_t)E.kept.size()) return AV1R_EINVAL;
+    E.kept[handle].reset();
+    return 0;
+}
 
 int Engine::verify_file(const char* path, const av1r_config* cfg, av1r_report* out) {
-    (void)path; (void)cfg;
     memset(out, 0, sizeof(*out));
     out->struct_size = sizeof(*out);
-    out->status = AV1R_ENOSYS;
-    snprintf(out->message, sizeof(out->message), "tile reconstruction not built yet");
-    return AV1R_ENOSYS;
+    out->first_bad_frame = -1;
+    DemuxResult dm;
+    std::string derr;
+    if (!demux_file(path, dm, derr)) {
+        out->status = AV1R_ENOENT;
+        snprintf(out->message, sizeof(out->message), "%s", derr.c_str());
+        return out->status;
+    }
+    av1r_config c;
+    av1r_default_config(&c);
+    if (cfg) c = *cfg;
+    Engine eng;
+    int rc = eng.open(c);
+    if (rc) {
+        out->status = rc;
+        snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str());
+        return rc;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<av1r_frame_result> res(64);
+    auto drain = [&](bool all) -> int {
+        while (true) {
+            int n = 0;
+            if (all) eng.flush();
+            int r = eng.collect(res.data(), (int)res.size(), &n);
+            if (r) return r;
+            for (int i = 0; i < n; i++) {
+                out->frames++;
+                out->host_parse_ms += res[i].host_parse_ms;
+                out->device_ms += res[i].device_ms;
+                out->width = res[i].w;
+                out->height = res[i].h;
+                out->bit_depth = res[i].bpc;
+            }
+            if (n == 0) return 0;
+        }
+    };
+    if (!dm.config_obus.empty()) {
+        // Matroska CodecPrivate carries the sequence header
+        rc = eng.submit_tu(dm.config_obus.data(), dm.config_obus.size(), -1);
+    }
+    for (size_t i = 0; i < dm.tus.size() && !rc; i++) {
+        rc = eng.submit_tu(dm.file.data() + dm.tus[i].offset, dm.tus[i].size, dm.tus[i].pts);
+        if (rc) {
+            out->first_bad_frame = out->frames;
+            snprintf(out->message, sizeof(out->message), "temporal unit %zu: %s", i, eng.error().c_str());
+            break;
+        }
+        int r = drain(false);
+        if (r) { rc = r; snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str()); }
+    }
+    int r = drain(true);
+    if (!rc && r) { rc = r; snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str()); }
+    out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out->frames_per_sec = out->wall_ms > 0 ? out->frames * 1000.0 / out->wall_ms : 0;
+    out->status = rc;
+    if (!rc) snprintf(out->message, sizeof(out->message), "ok: %lld frames", (long long)out->frames);
+    return rc;
 }
 
 }  // namespace av1r

@@ -1,0 +1,198 @@
+// K5 -- constrained directional enhancement filter (AV1 spec 7.15) for sm_100a.
+//
+// One CTA per 64x64 luma filter block (plus its co-located chroma).  The deblocked input tile and a
+// 2-sample halo are staged in shared memory once (samples outside the coded frame are marked
+// unavailable), the 8x8 direction search runs from shared memory, then every thread filters
+// 16 luma + 8 chroma samples.  Out of place (CDEF reads pre-CDEF neighbours); samples of skipped
+// 8x8 blocks are copied through.  Algorithmic bytes 2F; the halo re-reads are L2 hits.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_common.cuh"
+#include "devframe.h"
+#include "intra.h"
+
+namespace av1r {
+
+__constant__ int8_t c_cdef_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
+                                           {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
+__constant__ uint8_t c_cdef_uv_dir[2][2][8] = {{{0, 1, 2, 3, 4, 5, 6, 7}, {1, 2, 2, 2, 3, 4, 6, 0}}, {{7, 0, 2, 4, 5, 6, 6, 6}, {0, 1, 2, 3, 4, 5, 6, 7}}};
+
+static constexpr int CDEF_LT = 68;   // luma tile edge (64 + 2*2)
+
+__device__ __forceinline__ int cdef_constrain(int diff, int threshold, int damping) {
+    if (!threshold) return 0;
+    const int adj = max(0, damping - (31 - __clz(threshold)));
+    const int mag = abs(diff);
+    const int v = min(max(threshold - (mag >> adj), 0), mag);
+    return diff < 0 ? -v : v;
+}
+
+__device__ __forceinline__ int cdef_pixel(const int16_t* tile, int ts, int tx, int ty, int pri, int sec, int damping, int dir, int cs) {
+    const int x = tile[ty * ts + tx];
+    int sum = 0, mx = x, mn = x;
+    const int pt0 = ((pri >> cs) & 1) ? 3 : 4, pt1 = ((pri >> cs) & 1) ? 3 : 2;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int ptap = k ? pt1 : pt0, stap = k ? 1 : 2;
+#pragma unroll
+        for (int sg = -1; sg <= 1; sg += 2) {
+            {
+                const int p = tile[(ty + sg * c_cdef_dir[dir][k][0]) * ts + tx + sg * c_cdef_dir[dir][k][1]];
+                if (p >= 0) {
+                    sum += ptap * cdef_constrain(p - x, pri, damping);
+                    mx = max(mx, p);
+                    mn = min(mn, p);
+                }
+            }
+#pragma unroll
+            for (int off = -2; off <= 2; off += 4) {
+                const int d2 = (dir + off) & 7;
+                const int s = tile[(ty + sg * c_cdef_dir[d2][k][0]) * ts + tx + sg * c_cdef_dir[d2][k][1]];
+                if (s >= 0) {
+                    sum += stap * cdef_constrain(s - x, sec, damping);
+                    mx = max(mx, s);
+                    mn = min(mn, s);
+                }
+            }
+        }
+    }
+    return min(max(x + ((8 + sum - (sum < 0)) >> 4), mn), mx);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
+    __shared__ int16_t s_luma[CDEF_LT * CDEF_LT];
+    __shared__ int16_t s_chroma[2][CDEF_LT * CDEF_LT];   // sized for 4:4:4
+    __shared__ uint8_t s_dir[64], s_skip[64];
+    __shared__ int s_var[64];
+    const DevFrameParams& fp = L.fp;
+    const int tid = threadIdx.x;
+    const int fbx = blockIdx.x, fby = blockIdx.y;
+    const int c64 = (fp.mi_cols + 15) >> 4;
+    const int idx = L.cdef_idx[(size_t)fby * c64 + fbx];
+    const int bd = fp.bd, cs = bd - 8;
+    const int nplanes = fp.mono ? 1 : 3;
+    // ---- stage tiles
+    for (int plane = 0; plane < nplanes; plane++) {
+        const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
+        const int tw = (64 >> sx) + 4, th = (64 >> sy) + 4;
+        const int x0 = (fbx * 64 >> sx) - 2, y0 = (fby * 64 >> sy) - 2;
+        int16_t* tile = plane == 0 ? s_luma : s_chroma[plane - 1];
+        const T* src = (const T*)L.src.p[plane];
+        const int pitch_e = L.src.pitch[plane] / sizeof(T);
+        for (int i = tid; i < tw * th; i += 256) {
+            const int ty = i / tw, tx = i - ty * tw;
+            const int x = x0 + tx, y = y0 + ty;
+            int v = -1;
+            if (x >= 0 && y >= 0 && x < fp.cw[plane] && y < fp.ch[plane]) v = src[(size_t)y * pitch_e + x];
+            tile[ty * CDEF_LT + tx] = (int16_t)v;
+        }
+    }
+    // ---- per 8x8: skip flag
+    if (tid < 64) {
+        const int by = tid >> 3, bx = tid & 7;
+        const int r = fby * 16 + by * 2, c = fbx * 16 + bx * 2;
+        int skip = 1;
+        if (idx >= 0 && r < fp.mi_rows && c < fp.mi_cols) {
+            const uint8_t* s0 = L.skip_mi + (size_t)r * fp.mi_cols + c;
+            const uint8_t* s1 = s0 + fp.mi_cols;
+            skip = s0[0] && s0[1] && s1[0] && s1[1];
+        }
+        s_skip[tid] = (uint8_t)skip;
+    }
+    __syncthreads();
+    // ---- direction search, one thread per 8x8 block
+    if (tid < 64 && !s_skip[tid]) {
+        const int by = tid >> 3, bx = tid & 7;
+        int partial[8][15];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 15; b++) partial[a][b] = 0;
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++) {
+                const int x = (s_luma[(by * 8 + i + 2) * CDEF_LT + bx * 8 + j + 2] >> cs) - 128;
+                partial[0][i + j] += x;
+                partial[1][i + j / 2] += x;
+                partial[2][i] += x;
+                partial[3][3 + i - j / 2] += x;
+                partial[4][7 + i - j] += x;
+                partial[5][3 - i / 2 + j] += x;
+                partial[6][j] += x;
+                partial[7][i / 2 + j] += x;
+            }
+        const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
+        int cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 8; i++) {
+            cost[2] += partial[2][i] * partial[2][i];
+            cost[6] += partial[6][i] * partial[6][i];
+        }
+        cost[2] *= 105;
+        cost[6] *= 105;
+        for (int i = 0; i < 7; i++) {
+            cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * div_table[i + 1];
+            cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * div_table[i + 1];
+        }
+        cost[0] += partial[0][7] * partial[0][7] * 105;
+        cost[4] += partial[4][7] * partial[4][7] * 105;
+        for (int i = 1; i < 8; i += 2) {
+            for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
+            cost[i] *= 105;
+            for (int j = 0; j < 3; j++)
+                cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * div_table[2 * j + 2];
+        }
+        int best = 0, dir = 0;
+        for (int d = 0; d < 8; d++)
+            if (cost[d] > best) { best = cost[d]; dir = d; }
+        s_dir[tid] = (uint8_t)dir;
+        s_var[tid] = (best - cost[(dir + 4) & 7]) >> 10;
+    }
+    __syncthreads();
+    // ---- filter
+    for (int plane = 0; plane < nplanes; plane++) {
+        const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
+        const int bw = 64 >> sx, bh = 64 >> sy;           // plane samples in this filter block
+        const int x0 = fbx * 64 >> sx, y0 = fby * 64 >> sy;
+        const int16_t* tile = plane == 0 ? s_luma : s_chroma[plane - 1];
+        T* dst = (T*)L.dst.p[plane];
+        const int pitch_e = L.dst.pitch[plane] / sizeof(T);
+        const int lbw = 6 - sx;
+        for (int i = tid; i < bw * bh; i += 256) {
+            const int py = i >> lbw, px = i & (bw - 1);
+            const int x = x0 + px, y = y0 + py;
+            if (x >= fp.cw[plane] || y >= fp.ch[plane]) continue;
+            const int blk = ((py << sy) >> 3) * 8 + ((px << sx) >> 3);
+            int v = tile[(py + 2) * CDEF_LT + px + 2];
+            if (!s_skip[blk]) {
+                const int ydir = s_dir[blk];
+                int pri, sec, dir, damping;
+                if (plane == 0) {
+                    pri = fp.cdef_y_pri[idx] << cs;
+                    sec = fp.cdef_y_sec[idx] << cs;
+                    dir = pri == 0 ? 0 : ydir;
+                    const int var = s_var[blk];
+                    const int var_str = (var >> 6) ? min(31 - __clz(var >> 6), 12) : 0;
+                    pri = var ? (pri * (4 + var_str) + 8) >> 4 : 0;
+                    damping = fp.cdef_damping + cs;
+                } else {
+                    pri = fp.cdef_uv_pri[idx] << cs;
+                    sec = fp.cdef_uv_sec[idx] << cs;
+                    dir = pri == 0 ? 0 : c_cdef_uv_dir[fp.subx][fp.suby][ydir];
+                    damping = fp.cdef_damping + cs - 1;
+                }
+                if (pri | sec) v = cdef_pixel(tile, CDEF_LT, px + 2, py + 2, pri, sec, damping, dir, cs);
+            }
+            dst[(size_t)y * pitch_e + x] = (T)v;
+        }
+    }
+}
+
+cudaError_t launch_cdef(const CdefLaunch& L, cudaStream_t s) {
+    dim3 grid((L.fp.mi_cols + 15) >> 4, (L.fp.mi_rows + 15) >> 4);
+    if (L.fp.bd == 8) cdef_kernel<uint8_t><<<grid, 256, 0, s>>>(L);
+    else cdef_kernel<uint16_t><<<grid, 256, 0, s>>>(L);
+    return cudaGetLastError();
+}
+
+}  // namespace av1r

@@ -1,0 +1,435 @@
+// K3 -- intra prediction + residual add, wavefront-scheduled (AV1 spec 7.11.2, 7.11.5, 7.12.3).
+//
+// Intra prediction reads *reconstructed* neighbours, so transform blocks inside a superblock run in
+// decode order and superblock rows run as a wavefront (row r may process SB c once row r-1 has
+// finished SB c+1; rows of different tiles and of different frames are independent).  One warp owns
+// one (tile, SB row) work item and walks its records; lanes split the pixels of each block.
+// Inter-row hand-off uses per-item progress counters in global memory (release: __threadfence +
+// store, acquire: volatile load + __threadfence) and all neighbour reads go through L2 (ld.cg) so a
+// stale L1 line can never be observed.  Work items are claimed through an atomic ticket so a warp
+// only ever waits on items that are already running (no co-residency assumption).
+// Algorithmic bytes: F_intra written + 2A residual read; neighbour edges are L2 hits.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../av1_consts.h"
+#include "dev_common.cuh"
+#include "devframe.h"
+#include "intra.h"
+#include "../tables/tables_pred.inc"
+
+namespace av1r {
+
+__constant__ int16_t c_dr_deriv[90];
+__constant__ uint8_t c_sm_weights[124];
+__constant__ int8_t c_fi_taps[5][8][8];
+__constant__ uint8_t c_itxw_log2[TX_SIZES_ALL];
+__constant__ uint8_t c_itxh_log2[TX_SIZES_ALL];
+static bool g_intra_const_loaded[64] = {false};
+
+static constexpr int INTRA_WARPS = 4;
+static constexpr int EDGE_PAD = 16;
+static constexpr int EDGE_LEN = EDGE_PAD + 2 * 129 + 16;   // room for upsampled edges (index -2 .. 2*(w+h))
+
+struct IntraSmem {
+    int32_t above[2][EDGE_LEN];
+    int32_t left[2][EDGE_LEN];
+    int16_t tile[64 * 64 / 4];   // 32x32 int16: filter-intra predictions / CfL luma terms
+};
+
+template <typename T>
+__device__ __forceinline__ int ldpx(const uint8_t* base, uint32_t pitch, int x, int y) {
+    return (int)__ldcg((const T*)(base + (size_t)y * pitch) + x);
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int edge_filter_strength_d(int w, int h, int filter_type, int delta) {
+    const int d = abs(delta), blk = w + h;
+    int s = 0;
+    if (filter_type == 0) {
+        if (blk <= 8) { if (d >= 56) s = 1; }
+        else if (blk <= 16) { if (d >= 40) s = 1; }
+        else if (blk <= 24) { if (d >= 8) s = 1; if (d >= 16) s = 2; if (d >= 32) s = 3; }
+        else if (blk <= 32) { if (d >= 1) s = 1; if (d >= 4) s = 2; if (d >= 32) s = 3; }
+        else { if (d >= 1) s = 3; }
+    } else {
+        if (blk <= 8) { if (d >= 40) s = 1; if (d >= 64) s = 2; }
+        else if (blk <= 16) { if (d >= 20) s = 1; if (d >= 48) s = 2; }
+        else if (blk <= 24) { if (d >= 4) s = 3; }
+        else { if (d >= 1) s = 3; }
+    }
+    return s;
+}
+__device__ __forceinline__ int edge_upsample_d(int w, int h, int filter_type, int delta) {
+    const int d = abs(delta), blk = w + h;
+    if (d <= 0 || d >= 40) return 0;
+    return filter_type == 0 ? blk <= 16 : blk <= 8;
+}
+
+// src/dst point at element 0 (index -1 is the corner).  sz counts the corner.
+__device__ __forceinline__ void edge_filter_d(const int32_t* src, int32_t* dst, int sz, int strength, int total, int lane) {
+    const int k0 = strength == 3 ? 2 : 0, k1 = strength == 1 ? 4 : (strength == 2 ? 5 : 4), k2 = strength == 1 ? 8 : (strength == 2 ? 6 : 4);
+    for (int i = lane; i < total + 2; i += 32) {
+        // element index e = i - 1 over [-1, total]; filtered for 1 <= i < sz, copied otherwise
+        int v;
+        if (i >= 1 && i < sz) {
+            const int a = src[max(i - 2, 0) - 1], b = src[max(i - 1, 0) - 1], c = src[i - 1], d = src[min(i + 1, sz - 1) - 1],
+                      e = src[min(i + 2, sz - 1) - 1];
+            v = (k0 * a + k1 * b + k2 * c + k1 * d + k0 * e + 8) >> 4;
+        } else {
+            v = src[i - 1];
+        }
+        dst[i - 1] = v;
+    }
+}
+
+// upsample numPx samples: dst gets indices -2 .. 2*numPx-2
+__device__ __forceinline__ void edge_upsample_d(const int32_t* src, int32_t* dst, int num_px, int pixmax, int lane) {
+    for (int i = lane; i < num_px; i += 32) {
+        // dup[k] = src[k-2] for k = 1..numPx+1, dup[0] = src[-1], dup[numPx+2] = src[numPx-1]
+        const int d0 = src[max(i - 2, -1)], d1 = src[i - 1], d2 = src[i], d3 = src[min(i + 1, num_px - 1)];
+        int s = -d0 + 9 * d1 + 9 * d2 - d3;
+        s = min(max((s + 8) >> 4, 0), pixmax);
+        dst[2 * i - 1] = s;
+        dst[2 * i] = d2;
+    }
+    if (lane == 0) dst[-2] = src[-1];
+}
+
+template <typename T>
+__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm, int lane) {
+    const int plane = r.plane;
+    const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
+    const int w = 1 << lw, h = 1 << lh;
+    const int x = r.x4 * 4, y = r.y4 * 4;
+    const int bd = fp.bd, pixmax = (1 << bd) - 1;
+    const int max_x = fp.cw[plane] - 1, max_y = fp.ch[plane] - 1;
+    const uint8_t* base = fr.p[plane];
+    const uint32_t pitch = fr.pitch[plane];
+    const int xe = min(w, fp.cw[plane] - x), ye = min(h, fp.ch[plane] - y);
+    T* out = (T*)(fr.p[plane] + (size_t)y * pitch) + x;
+    const int opitch = pitch / sizeof(T);
+    const int16_t* rp = (const int16_t*)((const uint8_t*)res.p[plane] + (size_t)y * res.pitch[plane]) + x;
+    const int rpitch = res.pitch[plane] >> 1;
+    const bool has_res = r.eob > 0;
+    auto emit = [&](int i, int j, int v) {
+        if (i < ye && j < xe) {
+            if (has_res) v = min(max(v + (int)__ldg(rp + i * rpitch + j), 0), pixmax);
+            out[i * opitch + j] = (T)v;
+        }
+    };
+    if (r.mode == TXM_INTER) {   // residual on top of the inter predictor
+        if (has_res)
+            for (int idx = lane; idx < w * h; idx += 32) {
+                const int i = idx >> lw, j = idx & (w - 1);
+                if (i < ye && j < xe) {
+                    int v = (int)__ldcg(out + i * opitch + j) + (int)__ldg(rp + i * rpitch + j);
+                    out[i * opitch + j] = (T)min(max(v, 0), pixmax);
+                }
+            }
+        return;
+    }
+    const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
+    const int have_ar = r.flags & TXF_HAVE_ABOVE_RIGHT, have_bl = r.flags & TXF_HAVE_BELOW_LEFT;
+    int32_t* above = sm.above[0] + EDGE_PAD;
+    int32_t* left = sm.left[0] + EDGE_PAD;
+    const int n = w + h;
+    // ---- edges
+    for (int i = lane; i < n; i += 32) {
+        int a, l;
+        if (have_above) {
+            const int idx = have_ar ? min(i, 2 * w - 1) : min(i, w - 1);
+            a = ldpx<T>(base, pitch, min(max_x, x + idx), y - 1);
+        } else if (have_left) {
+            a = ldpx<T>(base, pitch, x - 1, y);
+        } else {
+            a = (1 << (bd - 1)) - 1;
+        }
+        if (have_left) {
+            const int idx = have_bl ? min(i, 2 * h - 1) : min(i, h - 1);
+            l = ldpx<T>(base, pitch, x - 1, min(max_y, y + idx));
+        } else if (have_above) {
+            l = ldpx<T>(base, pitch, x, y - 1);
+        } else {
+            l = (1 << (bd - 1)) + 1;
+        }
+        above[i] = a;
+        left[i] = l;
+    }
+    if (lane == 0) {
+        int c;
+        if (have_above && have_left) c = ldpx<T>(base, pitch, x - 1, y - 1);
+        else if (have_above) c = ldpx<T>(base, pitch, x, y - 1);
+        else if (have_left) c = ldpx<T>(base, pitch, x - 1, y);
+        else c = 1 << (bd - 1);
+        above[-1] = c;
+        left[-1] = c;
+    }
+    __syncwarp();
+    int mode = r.mode;
+    if (mode == TXM_CFL) mode = DC_PRED;
+
+    if (mode == TXM_FILTER_INTRA) {
+        const int w4 = w >> 2, h2 = h >> 1;
+        int16_t* pt = sm.tile;   // w x h predictions
+        const int fm = r.fi_mode;
+        for (int d = 0; d < h2 + w4 - 1; d++) {
+            const int i2_lo = max(0, d - (w4 - 1)), i2_hi = min(h2 - 1, d);
+            const int nblk = i2_hi - i2_lo + 1;
+            for (int t = lane; t < nblk * 8; t += 32) {
+                const int i2 = i2_lo + (t >> 3), j4 = d - i2, o = t & 7;
+                int p[7];
+#pragma unroll
+                for (int i = 0; i < 7; i++) {
+                    int v;
+                    if (i < 5) {
+                        if (i2 == 0) v = above[(j4 << 2) + i - 1];
+                        else if (j4 == 0 && i == 0) v = left[(i2 << 1) - 1];
+                        else v = pt[((i2 << 1) - 1) * w + (j4 << 2) + i - 1];
+                    } else {
+                        if (j4 == 0) v = left[(i2 << 1) + i - 5];
+                        else v = pt[((i2 << 1) + i - 5) * w + (j4 << 2) - 1];
+                    }
+                    p[i] = v;
+                }
+                int pr = 0;
+#pragma unroll
+                for (int i = 0; i < 7; i++) pr += c_fi_taps[fm][o][i] * p[i];
+                const int v = pr >= 0 ? (pr + 8) >> 4 : -((-pr + 8) >> 4);
+                pt[((i2 << 1) + (o >> 2)) * w + (j4 << 2) + (o & 3)] = (int16_t)min(max(v, 0), pixmax);
+            }
+            __syncwarp();
+        }
+        for (int idx = lane; idx < w * h; idx += 32) emit(idx >> lw, idx & (w - 1), pt[idx]);
+        return;
+    }
+    if (mode >= V_PRED && mode <= D67_PRED) {
+        const int kModeToAngle[9] = {0, 90, 180, 45, 135, 113, 157, 203, 67};
+        const int p_angle = kModeToAngle[mode] + r.angle_delta * 3;
+        int up_above = 0, up_left = 0;
+        if (fp.enable_edge_filter) {
+            const int filter_type = (r.flags & TXF_SMOOTH_EDGE) ? 1 : 0;
+            if (p_angle != 90 && p_angle != 180) {
+                if (p_angle > 90 && p_angle < 180 && (w + h) >= 24) {
+                    if (lane == 0) {
+                        const int v = (left[0] * 5 + above[-1] * 6 + above[0] * 5 + 8) >> 4;
+                        above[-1] = v;
+                        left[-1] = v;
+                    }
+                    __syncwarp();
+                }
+                if (have_above) {
+                    const int strength = edge_filter_strength_d(w, h, filter_type, p_angle - 90);
+                    if (strength) {
+                        const int num_px = min(w, max_x - x + 1) + (p_angle < 90 ? h : 0) + 1;
+                        int32_t* dst = (above == sm.above[0] + EDGE_PAD) ? sm.above[1] + EDGE_PAD : sm.above[0] + EDGE_PAD;
+                        edge_filter_d(above, dst, num_px, strength, n - 1, lane);
+                        above = dst;
+                        __syncwarp();
+                    }
+                }
+                if (have_left) {
+                    const int strength = edge_filter_strength_d(w, h, filter_type, p_angle - 180);
+                    if (strength) {
+                        const int num_px = min(h, max_y - y + 1) + (p_angle > 180 ? w : 0) + 1;
+                        int32_t* dst = (left == sm.left[0] + EDGE_PAD) ? sm.left[1] + EDGE_PAD : sm.left[0] + EDGE_PAD;
+                        edge_filter_d(left, dst, num_px, strength, n - 1, lane);
+                        left = dst;
+                        __syncwarp();
+                    }
+                }
+            }
+            up_above = edge_upsample_d(w, h, filter_type, p_angle - 90);
+            if (up_above) {
+                int32_t* dst = (above == sm.above[0] + EDGE_PAD) ? sm.above[1] + EDGE_PAD : sm.above[0] + EDGE_PAD;
+                edge_upsample_d(above, dst, w + (p_angle < 90 ? h : 0), pixmax, lane);
+                above = dst;
+                __syncwarp();
+            }
+            up_left = edge_upsample_d(w, h, filter_type, p_angle - 180);
+            if (up_left) {
+                int32_t* dst = (left == sm.left[0] + EDGE_PAD) ? sm.left[1] + EDGE_PAD : sm.left[0] + EDGE_PAD;
+                edge_upsample_d(left, dst, h + (p_angle > 180 ? w : 0), pixmax, lane);
+                left = dst;
+                __syncwarp();
+            }
+        }
+        int dx = 0, dy = 0;
+        if (p_angle < 90) dx = c_dr_deriv[p_angle];
+        else if (p_angle > 90 && p_angle < 180) dx = c_dr_deriv[180 - p_angle];
+        if (p_angle > 90 && p_angle < 180) dy = c_dr_deriv[p_angle - 90];
+        else if (p_angle > 180) dy = c_dr_deriv[270 - p_angle];
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int i = idx >> lw, j = idx & (w - 1);
+            int v;
+            if (p_angle < 90) {
+                const int id = (i + 1) * dx;
+                const int b = (id >> (6 - up_above)) + (j << up_above);
+                const int sh = ((id << up_above) >> 1) & 0x1F;
+                const int max_base = (w + h - 1) << up_above;
+                v = b < max_base ? (above[b] * (32 - sh) + above[b + 1] * sh + 16) >> 5 : above[max_base];
+            } else if (p_angle == 90) {
+                v = above[j];
+            } else if (p_angle < 180) {
+                int id = (j << 6) - (i + 1) * dx;
+                int b = id >> (6 - up_above);
+                if (b >= -(1 << up_above)) {
+                    const int sh = ((id << up_above) >> 1) & 0x1F;
+                    v = (above[b] * (32 - sh) + above[b + 1] * sh + 16) >> 5;
+                } else {
+                    id = (i << 6) - (j + 1) * dy;
+                    b = id >> (6 - up_left);
+                    const int sh = ((id << up_left) >> 1) & 0x1F;
+                    v = (left[b] * (32 - sh) + left[b + 1] * sh + 16) >> 5;
+                }
+            } else if (p_angle == 180) {
+                v = left[i];
+            } else {
+                const int id = (j + 1) * dy;
+                const int b = (id >> (6 - up_left)) + (i << up_left);
+                const int sh = ((id << up_left) >> 1) & 0x1F;
+                const int max_base = (w + h - 1) << up_left;
+                v = b < max_base ? (left[b] * (32 - sh) + left[b + 1] * sh + 16) >> 5 : left[max_base];
+            }
+            emit(i, j, v);
+        }
+        return;
+    }
+    if (mode == SMOOTH_PRED || mode == SMOOTH_V_PRED || mode == SMOOTH_H_PRED) {
+        const uint8_t* ww = c_sm_weights + (w - 4);
+        const uint8_t* wh = c_sm_weights + (h - 4);
+        const int bl = left[h - 1], tr = above[w - 1];
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int i = idx >> lw, j = idx & (w - 1);
+            int v;
+            if (mode == SMOOTH_PRED) v = (wh[i] * above[j] + (256 - wh[i]) * bl + ww[j] * left[i] + (256 - ww[j]) * tr + 256) >> 9;
+            else if (mode == SMOOTH_V_PRED) v = (wh[i] * above[j] + (256 - wh[i]) * bl + 128) >> 8;
+            else v = (ww[j] * left[i] + (256 - ww[j]) * tr + 128) >> 8;
+            emit(i, j, v);
+        }
+        return;
+    }
+    if (mode == PAETH_PRED) {
+        const int tl = above[-1];
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int i = idx >> lw, j = idx & (w - 1);
+            const int b = above[j] + left[i] - tl;
+            const int pl = abs(b - left[i]), pt = abs(b - above[j]), ptl = abs(b - tl);
+            const int v = (pl <= pt && pl <= ptl) ? left[i] : (pt <= ptl ? above[j] : tl);
+            emit(i, j, v);
+        }
+        return;
+    }
+    // ---- DC (and CfL on top of it)
+    int dc;
+    {
+        int s = 0;
+        if (have_left)
+            for (int k = lane; k < h; k += 32) s += left[k];
+        if (have_above)
+            for (int k = lane; k < w; k += 32) s += above[k];
+        s = warp_sum(s);
+        if (have_left && have_above) dc = (s + ((w + h) >> 1)) / (w + h);
+        else if (have_left) dc = (s + (h >> 1)) >> lh;
+        else if (have_above) dc = (s + (w >> 1)) >> lw;
+        else dc = 1 << (bd - 1);
+    }
+    if (r.mode != TXM_CFL) {
+        for (int idx = lane; idx < w * h; idx += 32) emit(idx >> lw, idx & (w - 1), dc);
+        return;
+    }
+    {
+        const int sx = fp.subx, sy = fp.suby;
+        const int max_lw = r.cfl_max_w4 * 4, max_lh = r.cfl_max_h4 * 4;
+        const uint8_t* lbase = fr.p[0];
+        const uint32_t lpitch = fr.pitch[0];
+        int16_t* L = sm.tile;
+        int s = 0;
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int i = idx >> lw, j = idx & (w - 1);
+            const int ly = min((y + i) << sy, max_lh - (1 << sy)), lx = min((x + j) << sx, max_lw - (1 << sx));
+            int t = 0;
+            for (int dy2 = 0; dy2 <= sy; dy2++)
+                for (int dx2 = 0; dx2 <= sx; dx2++) t += ldpx<T>(lbase, lpitch, lx + dx2, ly + dy2);
+            const int v = t << (3 - sx - sy);
+            L[idx] = (int16_t)v;
+            s += v;
+        }
+        s = warp_sum(s);
+        const int sh = lw + lh;
+        const int avg = (s + (1 << (sh - 1))) >> sh;
+        const int alpha = r.cfl_alpha;
+        __syncwarp();
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int t = alpha * ((int)L[idx] - avg);
+            const int scaled = t >= 0 ? (t + 32) >> 6 : -((-t + 32) >> 6);
+            emit(idx >> lw, idx & (w - 1), min(max(dc + scaled, 0), pixmax));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(IntraLaunch L) {
+    __shared__ IntraSmem s_sm[INTRA_WARPS];
+    const int warp_in = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    IntraSmem& sm = s_sm[warp_in];
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(L.ticket, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= L.n_items) return;
+        const SbRowItem it = L.items[item];
+        const IntraFrame& F = L.frames[it.frame];
+        volatile int* dep = it.dep_item >= 0 ? (volatile int*)(L.progress + it.dep_item) : nullptr;
+        for (uint32_t k = 0; k < it.n_sb; k++) {
+            if (dep) {
+                const int need = (int)min(k + 2, it.n_sb);
+                if (lane == 0)
+                    while (*dep < need) __nanosleep(64);
+                __syncwarp();
+                __threadfence();
+            }
+            const SbRange sb = F.sbs[it.first_sb + k];
+            for (uint32_t t = 0; t < sb.count; t++) {
+                const TxRec r = F.recs[sb.first + t];
+                intra_block<T>(r, F.frame, F.res, F.fp, sm, lane);
+                __threadfence_block();
+                __syncwarp();
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *(volatile int*)(L.progress + item) = (int)k + 1;
+        }
+    }
+}
+
+static cudaError_t intra_upload_constants() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && g_intra_const_loaded[dev]) return cudaSuccess;
+    if ((e = cudaMemcpyToSymbol(c_dr_deriv, av1t_dr_intra_derivative, sizeof(av1t_dr_intra_derivative))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_sm_weights, av1t_smooth_weights, sizeof(av1t_smooth_weights))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_fi_taps, av1t_filter_intra_taps, sizeof(av1t_filter_intra_taps))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_itxw_log2, kTxWLog2, sizeof(kTxWLog2))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_itxh_log2, kTxHLog2, sizeof(kTxHLog2))) != cudaSuccess) return e;
+    if (dev < 64) g_intra_const_loaded[dev] = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_intra(const IntraLaunch& L, int bd, cudaStream_t s) {
+    if (L.n_items <= 0) return cudaSuccess;
+    cudaError_t e = intra_upload_constants();
+    if (e != cudaSuccess) return e;
+    int blocks = (L.n_items + INTRA_WARPS - 1) / INTRA_WARPS;
+    if (bd == 8) intra_wavefront_kernel<uint8_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
+    else intra_wavefront_kernel<uint16_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
+    return cudaGetLastError();
+}
+
+}  // namespace av1r

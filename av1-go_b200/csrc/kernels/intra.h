@@ -1,0 +1,53 @@
+// Launch descriptors of the intra wavefront kernel (K3).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "devframe.h"
+
+namespace av1r {
+
+struct IntraFrame {            // one per frame in the batch (device array)
+    const TxRec* recs;
+    const SbRange* sbs;
+    DevPlanes frame;
+    DevResidual res;
+    DevFrameParams fp;
+};
+
+struct SbRowItem {             // one (tile, superblock row): the unit a warp owns
+    uint32_t first_sb, n_sb;   // range in IntraFrame::sbs
+    int32_t dep_item;          // item index of the superblock row above in the same tile, -1 if none
+    int32_t frame;             // index into IntraLaunch::frames
+};
+
+struct IntraLaunch {
+    const IntraFrame* frames;  // device
+    const SbRowItem* items;    // device, ordered so that dep_item < own index
+    int* progress;             // device, n_items ints, zeroed before launch
+    int* ticket;               // device, one int, zeroed before launch
+    int n_items;
+};
+
+cudaError_t launch_intra(const IntraLaunch& L, int bd, cudaStream_t s);
+cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, const uint32_t* coefs, const DevResidual& res,
+                       const DevFrameParams& fp, cudaStream_t s);
+
+struct LfLaunch {
+    DevPlanes frame;
+    const LfEdge* edges[3];    // device, per plane [ph4][pw4]
+    DevFrameParams fp;
+    int plane_on[3];
+};
+cudaError_t launch_deblock(const LfLaunch& L, cudaStream_t s);
+
+struct CdefLaunch {
+    DevPlanes src, dst;
+    const int8_t* cdef_idx;    // device, per 64x64
+    const uint8_t* skip_mi;    // device, per mi
+    DevFrameParams fp;
+};
+cudaError_t launch_cdef(const CdefLaunch& L, cudaStream_t s);
+
+cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s);
+
+}  // namespace av1r

@@ -1,0 +1,50 @@
+"""Generates the small golden AV1 streams under tests/golden/streams/ plus their per-frame per-plane
+MD5 (libdav1d 1.5.3, cross-checked against the libaom decoder).  MD5 domain = visible samples, rows
+tightly packed, 8-bit as bytes, >8-bit as little-endian uint16 (what `ffmpeg -f framemd5` hashes).
+    python tests/golden/make_golden_streams.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import dav1d_ref  # noqa: E402
+from tools import aomenc, obuio, sources  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "streams")
+
+# name: (source, w, h, bpc, frames, opts, cfg)
+CASES = {
+    "intra_8b_200x136": ("panzoom", 200, 136, 8, 3, {"cpu-used": "5", "cq-level": "30", "enable-restoration": "0"}, {14: 0, 48: 0}),
+    "intra_10b_192x128": ("panzoom", 192, 128, 10, 2, {"cpu-used": "4", "cq-level": "24", "enable-restoration": "0"}, {14: 0, 48: 0}),
+    "intra_8b_tiles_320x192": ("noise", 320, 192, 8, 2, {"cpu-used": "6", "cq-level": "12", "enable-restoration": "0", "tile-columns": "1", "tile-rows": "1"}, {14: 0, 48: 0}),
+    "intra_8b_sb128_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "3", "cq-level": "45", "enable-restoration": "0", "sb-size": "128"}, {14: 0, 48: 0}),
+    "intra_8b_grain_160x96": ("noise", 160, 96, 8, 2, {"cpu-used": "8", "cq-level": "30", "enable-restoration": "0", "film-grain-test": "7"}, {14: 0, 48: 0}),
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    index = {}
+    for name, (src, w, h, bpc, n, opts, cfg) in CASES.items():
+        frames = list(sources.SOURCES[src](w, h, n, bpc=bpc, seed=len(name)))
+        tus = aomenc.encode(frames, w, h, bpc=bpc, opts=opts, cfg=cfg, threads=1)
+        ref = dav1d_ref.decode(tus)
+        aom = aomenc.decode(tus)
+        assert len(ref) == len(aom) == n
+        md5 = []
+        for i in range(n):
+            for p in range(3):
+                assert np.array_equal(ref[i][4][p], aom[i][p]), "dav1d and libaom disagree"
+            md5.append(dav1d_ref.plane_md5(ref[i][4]))
+        obuio.write_ivf(os.path.join(OUT, name + ".ivf"), tus, w, h)
+        index[name] = dict(w=w, h=h, bpc=bpc, frames=n, md5=md5, bytes=sum(len(t) for t in tus))
+        print(name, index[name]["bytes"], "bytes")
+    json.dump(index, open(os.path.join(OUT, "index.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
