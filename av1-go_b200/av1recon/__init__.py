@@ -203,3 +203,62 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+
+class ClipInfo(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("width", C.c_int), ("height", C.c_int), ("bit_depth", C.c_int),
+                ("frames_decoded", C.c_int64), ("frames_shown", C.c_int64), ("host_parse_ms", C.c_double),
+                ("worklist_bytes", C.c_uint64), ("frame_bytes", C.c_uint64), ("coded_samples", C.c_uint64),
+                ("coef_tokens", C.c_uint64), ("tx_blocks", C.c_uint64), ("intra_samples", C.c_uint64)]
+
+
+STAGES = ["h2d", "itx", "intra", "inter", "deblock", "cdef", "lr", "grain", "digest"]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("ms", C.c_float * 9), ("launches", C.c_int * 9)]
+
+
+class Clip:
+    """Device-resident clip replay (av1r_clip_*): parse + upload once, time the device path."""
+
+    def __init__(self, dec, tus):
+        l = dec.l
+        l.av1r_clip_load.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_void_p)]
+        l.av1r_clip_info_get.argtypes = [C.c_void_p, C.POINTER(ClipInfo)]
+        l.av1r_clip_decode.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        l.av1r_clip_profile.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(StageTimes)]
+        l.av1r_clip_free.argtypes = [C.c_void_p]
+        self.dec = dec
+        n = len(tus)
+        arr = (C.c_char_p * n)(*tus)
+        lens = (C.c_size_t * n)(*[len(t) for t in tus])
+        self.h = C.c_void_p()
+        rc = l.av1r_clip_load(dec.ctx, arr, lens, n, C.byref(self.h))
+        if rc:
+            raise RuntimeError(f"av1r_clip_load -> {rc}: {dec.error()}")
+        self.info = ClipInfo()
+        l.av1r_clip_info_get(self.h, C.byref(self.info))
+
+    def decode(self):
+        """-> (device_ms, checksums[list of 3-tuples])"""
+        cap = int(self.info.frames_shown) + 4
+        cks = (C.c_uint64 * (3 * cap))()
+        n = C.c_int(0)
+        ms = C.c_float(0)
+        rc = self.dec.l.av1r_clip_decode(self.dec.ctx, self.h, cks, cap, C.byref(n), C.byref(ms))
+        if rc:
+            raise RuntimeError(f"av1r_clip_decode -> {rc}: {self.dec.error()}")
+        return ms.value, [tuple(cks[3 * i:3 * i + 3]) for i in range(n.value)]
+
+    def profile(self):
+        st = StageTimes()
+        rc = self.dec.l.av1r_clip_profile(self.dec.ctx, self.h, C.byref(st))
+        if rc:
+            raise RuntimeError(f"av1r_clip_profile -> {rc}: {self.dec.error()}")
+        return {STAGES[i]: (st.ms[i], st.launches[i]) for i in range(9)}
+
+    def free(self):
+        if self.h:
+            self.dec.l.av1r_clip_free(self.h)
+            self.h = C.c_void_p()

@@ -21,6 +21,8 @@
 #include "md5.h"
 #include "stream_parser.h"
 
+struct av1r_clip;
+
 namespace av1r {
 
 #define CK(call)                                                         \
@@ -236,9 +238,44 @@ struct Pending {
 };
 
 struct ClipFrame {
+    bool show_existing = false;
+    int show_slot = -1;
+    FrameHdr fh;
+    int64_t pts = 0;
     DevWork dw;
     DevBuf arena;
-    bool shown = false;
+};
+
+// cudaEvent-based per-stage timer (profile replay only)
+struct StageTimer {
+    struct Span { int stage; cudaEvent_t a, b; int launches; };
+    std::vector<Span> spans;
+    cudaEvent_t cur = nullptr;
+    void begin(cudaStream_t st) {
+        cudaEventCreate(&cur);
+        cudaEventRecord(cur, st);
+    }
+    void end(int stage, int launches, cudaStream_t st) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        spans.push_back({stage, cur, e, launches});
+        cudaEventCreate(&cur);
+        cudaEventRecord(cur, st);
+    }
+    void collect(av1r_stage_times* out) {
+        for (auto& sp : spans) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, sp.a, sp.b);
+            out->ms[sp.stage] += ms;
+            out->launches[sp.stage] += sp.launches;
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        spans.clear();
+        if (cur) cudaEventDestroy(cur);
+        cur = nullptr;
+    }
 };
 
 struct EngineImpl {
@@ -259,10 +296,15 @@ struct EngineImpl {
     int wait_slot(FrameSlot& s);
     int finish_pending(Pending& p);
     std::shared_ptr<DevFrameBuf> get_frame(const DevFrameParams& fp);
+    StageTimer* tm = nullptr;             // set during av1r_clip_profile
     int run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_arena, std::shared_ptr<DevFrameBuf>& out_ref);
     int emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<DevFrameBuf>& frame, const FrameHdr& fh, const FilmGrainParams& fg,
                     const DevFrameParams& fp, int64_t pts, double parse_ms, bool existing);
     int decode_parsed(ParsedFrame& pf);
+    int prepare_work(const FrameWork& fw, DevWork& dw);
+    int acquire_slot(int& slot_idx);
+    int exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_arena, int64_t pts);
+    int exec_show_existing(int slot_idx, const FrameHdr& fh, int show_slot, int64_t pts);
 };
 
 std::shared_ptr<DevFrameBuf> EngineImpl::get_frame(const DevFrameParams& fp) {
@@ -312,7 +354,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     ifr.res = res;
     ifr.fp = fp;
     CK(cudaMemcpyAsync((void*)(d_arena + L.iframe), &ifr, sizeof(ifr), cudaMemcpyHostToDevice, st));
+    if (tm) tm->begin(st);
     CK(launch_itx(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
+    if (tm) tm->end(AV1R_ST_ITX, L.n_order > 0, st);
     IntraLaunch il;
     il.frames = (const IntraFrame*)(d_arena + L.iframe);
     il.items = (const SbRowItem*)(d_arena + L.items);
@@ -320,6 +364,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     il.ticket = (int*)s.sync.p + L.n_items;
     il.n_items = L.n_items;
     CK(launch_intra(il, fp.bd, st));
+    if (tm) tm->end(AV1R_ST_INTRA, L.n_items > 0, st);
     std::shared_ptr<DevFrameBuf> cur = recon;
     if (dw.lf_on && (cfg.inloop_filters & 1)) {
         LfLaunch ll;
@@ -330,6 +375,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         ll.fp = fp;
         CK(launch_deblock(ll, st));
+        if (tm) tm->end(AV1R_ST_DEBLOCK, 2, st);
     }
     if (dw.cdef_on && (cfg.inloop_filters & 2)) {
         auto dst = get_frame(fp);
@@ -342,6 +388,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         cl.skip_mi = d_arena + L.skip_mi;
         cl.fp = fp;
         CK(launch_cdef(cl, st));
+        if (tm) tm->end(AV1R_ST_CDEF, 1, st);
         cur = dst;
     }
     if (dw.lr_on && (cfg.inloop_filters & 4)) {
@@ -357,6 +404,7 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
     cudaStream_t st = s->stream;
     std::shared_ptr<DevFrameBuf> shown = frame;
     s->hold.push_back(frame);
+    if (tm) tm->begin(st);
     if (cfg.apply_grain && fg.apply_grain) {
         auto disp = get_frame(fp);
         if (!disp) return AV1R_ENOMEM;
@@ -373,12 +421,14 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
             return rc;
         }
         shown = disp;
+        if (tm) tm->end(AV1R_ST_GRAIN, 2, st);
     }
     CK(s->cks_dev.ensure(64));
     CK(s->cks_host.ensure(64));
     const int np = fp.mono ? 1 : 3;
     for (int p = 0; p < np; p++)
         CK(launch_plane_checksum(shown->pl.p[p], shown->pl.pitch[p], fp.w[p], fp.h[p], fp.bd, (uint64_t*)s->cks_dev.p + p, st));
+    if (tm) tm->end(AV1R_ST_DIGEST, np, st);
     CK(cudaMemcpyAsync(s->cks_host.p, s->cks_dev.p, 24, cudaMemcpyDeviceToHost, st));
     Pending pd;
     memset(&pd.res, 0, sizeof(pd.res));
@@ -413,8 +463,8 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
     return 0;
 }
 
-int EngineImpl::decode_parsed(ParsedFrame& pf) {
-    const int slot_idx = next_slot;
+int EngineImpl::acquire_slot(int& slot_idx) {
+    slot_idx = next_slot;
     FrameSlot& s = *slots[slot_idx];
     next_slot = (next_slot + 1) % (int)slots.size();
     // a slot can only be reused once the outputs that still read its pinned buffers were finalised
@@ -427,25 +477,11 @@ int EngineImpl::decode_parsed(ParsedFrame& pf) {
     if (rc) return rc;
     s.stream = streams[next_stream];
     next_stream = (next_stream + 1) % (int)streams.size();
-    if (pf.show_existing_slot >= 0) {
-        auto f = refs[pf.show_existing_slot];
-        if (!f) { err = "show_existing_frame of an empty slot"; return AV1R_EBITSTREAM; }
-        DevFrameParams fp;
-        FrameWork dummy;
-        dummy.fh = pf.fh;
-        fill_params(sp.hp.seq, dummy, fp);
-        CK(cudaEventRecord(s.ev0, s.stream));
-        rc = emit_output(&s, slot_idx, f, pf.fh, pf.fh.fg, fp, pf.pts, 0, true);
-        if (rc) return rc;
-        CK(cudaEventRecord(s.ev1, s.stream));
-        s.busy = true;
-        if (pf.fh.frame_type == KEY_FRAME)
-            for (int i = 0; i < 8; i++) refs[i] = f;
-        return 0;
-    }
-    const FrameWork& fw = *pf.fw;
+    return 0;
+}
+
+int EngineImpl::prepare_work(const FrameWork& fw, DevWork& dw) {
     if (fw.fh.using_qmatrix) { err = "quantiser matrices are not supported yet"; return AV1R_ENOSYS; }
-    DevWork dw;
     fill_params(sp.hp.seq, fw, dw.fp);
     dw.fh = fw.fh;
     dw.lf_on = fw.fh.lf.level[0] || fw.fh.lf.level[1];
@@ -455,25 +491,64 @@ int EngineImpl::decode_parsed(ParsedFrame& pf) {
     dw.cdef_on = fw.fh.enable_cdef_frame;
     dw.lr_on = fw.fh.uses_lr;
     dw.parse_ms = fw.parse_ms;
+    dw.coded_samples = fw.coded_samples;
+    dw.coef_tokens = fw.coefs.size();
     plan_layout(fw, dw);
-    CK(s.staging.ensure(dw.lay.total));
-    CK(s.arena.ensure(dw.lay.total));
-    fill_arena(fw, dw, s.staging.p);
+    return 0;
+}
+
+int EngineImpl::exec_show_existing(int slot_idx, const FrameHdr& fh, int show_slot, int64_t pts) {
+    FrameSlot& s = *slots[slot_idx];
+    auto f = refs[show_slot];
+    if (!f) { err = "show_existing_frame of an empty slot"; return AV1R_EBITSTREAM; }
+    DevFrameParams fp;
+    FrameWork dummy;
+    dummy.fh = fh;
+    fill_params(sp.hp.seq, dummy, fp);
     CK(cudaEventRecord(s.ev0, s.stream));
-    CK(cudaMemcpyAsync(s.arena.p, s.staging.p, dw.lay.total, cudaMemcpyHostToDevice, s.stream));
+    int rc = emit_output(&s, slot_idx, f, fh, fh.fg, fp, pts, 0, true);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.ev1, s.stream));
+    s.busy = true;
+    if (fh.frame_type == KEY_FRAME)
+        for (int i = 0; i < 8; i++) refs[i] = f;
+    return 0;
+}
+
+// d_arena must already be (or be queued to become) valid on the slot's stream.
+int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_arena, int64_t pts) {
+    FrameSlot& s = *slots[slot_idx];
     std::shared_ptr<DevFrameBuf> out;
-    rc = run_frame(s, dw, s.arena.p, out);
+    int rc = run_frame(s, dw, d_arena, out);
     if (rc) return rc;
     for (int i = 0; i < 8; i++)
-        if ((fw.fh.refresh_frame_flags >> i) & 1) refs[i] = out;
-    if (fw.fh.show_frame) {
-        rc = emit_output(&s, slot_idx, out, fw.fh, fw.fh.fg, dw.fp, pf.pts, fw.parse_ms, false);
+        if ((dw.fh.refresh_frame_flags >> i) & 1) refs[i] = out;
+    if (dw.fh.show_frame) {
+        rc = emit_output(&s, slot_idx, out, dw.fh, dw.fh.fg, dw.fp, pts, dw.parse_ms, false);
         if (rc) return rc;
     }
     CK(cudaEventRecord(s.ev1, s.stream));
     s.busy = true;
     frames_decoded++;
     return 0;
+}
+
+int EngineImpl::decode_parsed(ParsedFrame& pf) {
+    int slot_idx;
+    int rc = acquire_slot(slot_idx);
+    if (rc) return rc;
+    FrameSlot& s = *slots[slot_idx];
+    if (pf.show_existing_slot >= 0) return exec_show_existing(slot_idx, pf.fh, pf.show_existing_slot, pf.pts);
+    const FrameWork& fw = *pf.fw;
+    DevWork dw;
+    rc = prepare_work(fw, dw);
+    if (rc) return rc;
+    CK(s.staging.ensure(dw.lay.total));
+    CK(s.arena.ensure(dw.lay.total));
+    fill_arena(fw, dw, s.staging.p);
+    CK(cudaEventRecord(s.ev0, s.stream));
+    CK(cudaMemcpyAsync(s.arena.p, s.staging.p, dw.lay.total, cudaMemcpyHostToDevice, s.stream));
+    return exec_decoded(slot_idx, dw, s.arena.p, pf.pts);
 }
 
 int EngineImpl::finish_pending(Pending& p) {
@@ -682,4 +757,156 @@ int Engine::verify_file(const char* path, const av1r_config* cfg, av1r_report* o
     return rc;
 }
 
+
 }  // namespace av1r
+
+struct av1r_clip {
+    std::vector<std::unique_ptr<av1r::ClipFrame>> frames;
+    av1r_clip_info info;
+};
+
+namespace av1r {
+
+int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r_clip** out) {
+    EngineImpl& E = *impl_;
+    std::string& err = E.err;
+    cudaSetDevice(E.cfg.device);
+    auto clip = std::make_unique<av1r_clip>();
+    memset(&clip->info, 0, sizeof(clip->info));
+    clip->info.struct_size = sizeof(clip->info);
+    StreamParser parser;   // independent of the streaming state of this ctx
+    PinBuf staging;
+    for (int t = 0; t < n; t++) {
+        std::vector<ParsedFrame> pfs;
+        int rc = parser.parse_tu(tus[t], lens[t], t, pfs);
+        if (rc) { err = parser.err; return rc; }
+        for (ParsedFrame& pf : pfs) {
+            auto cf = std::make_unique<ClipFrame>();
+            cf->fh = pf.fh;
+            cf->pts = pf.pts;
+            if (pf.show_existing_slot >= 0) {
+                cf->show_existing = true;
+                cf->show_slot = pf.show_existing_slot;
+                clip->info.frames_shown++;
+            } else {
+                const FrameWork& fw = *pf.fw;
+                E.sp.hp.seq = parser.hp.seq;   // fill_params reads the sequence header of this ctx
+                rc = E.prepare_work(fw, cf->dw);
+                if (rc) return rc;
+                CK(staging.ensure(cf->dw.lay.total));
+                CK(cf->arena.ensure(cf->dw.lay.total));
+                fill_arena(fw, cf->dw, staging.p);
+                CK(cudaMemcpy(cf->arena.p, staging.p, cf->dw.lay.total, cudaMemcpyHostToDevice));
+                clip->info.frames_decoded++;
+                clip->info.frames_shown += fw.fh.show_frame;
+                clip->info.host_parse_ms += fw.parse_ms;
+                clip->info.worklist_bytes += cf->dw.lay.total;
+                clip->info.coded_samples += fw.coded_samples;
+                clip->info.coef_tokens += fw.coefs.size();
+                clip->info.tx_blocks += fw.tx.size();
+                for (const TxRec& r : fw.tx)
+                    if (r.mode != TXM_INTER) clip->info.intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+                clip->info.width = fw.fh.upscaled_width;
+                clip->info.height = fw.fh.frame_height;
+                clip->info.bit_depth = parser.hp.seq.bit_depth;
+                const DevFrameParams& fp = cf->dw.fp;
+                clip->info.frame_bytes = 0;
+                for (int p = 0; p < (fp.mono ? 1 : 3); p++) clip->info.frame_bytes += (uint64_t)fp.w[p] * fp.h[p] * (fp.bd == 8 ? 1 : 2);
+            }
+            clip->frames.push_back(std::move(cf));
+        }
+    }
+    *out = clip.release();
+    return 0;
+}
+
+static int replay(EngineImpl& E, av1r_clip* clip) {
+    for (auto& cf : clip->frames) {
+        int slot_idx;
+        int rc = E.acquire_slot(slot_idx);
+        if (rc) return rc;
+        FrameSlot& s = *E.slots[slot_idx];
+        if (cf->show_existing) {
+            rc = E.exec_show_existing(slot_idx, cf->fh, cf->show_slot, cf->pts);
+        } else {
+            if (cudaEventRecord(s.ev0, s.stream) != cudaSuccess) return AV1R_EIO;
+            rc = E.exec_decoded(slot_idx, cf->dw, cf->arena.p, cf->pts);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, float* device_ms) {
+    EngineImpl& E = *impl_;
+    std::string& err = E.err;
+    cudaSetDevice(E.cfg.device);
+    int rc = flush();
+    if (rc) return rc;
+    E.pending.clear();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    std::vector<cudaEvent_t> done(E.streams.size());
+    for (auto& d : done) CK(cudaEventCreateWithFlags(&d, cudaEventDisableTiming));
+    // fence: every stream starts after e0 (recorded on stream 0)
+    CK(cudaEventRecord(e0, E.streams[0]));
+    for (size_t i = 1; i < E.streams.size(); i++) CK(cudaStreamWaitEvent(E.streams[i], e0, 0));
+    rc = replay(E, clip);
+    if (rc) return rc;
+    for (size_t i = 1; i < E.streams.size(); i++) {
+        CK(cudaEventRecord(done[i], E.streams[i]));
+        CK(cudaStreamWaitEvent(E.streams[0], done[i], 0));
+    }
+    CK(cudaEventRecord(e1, E.streams[0]));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (device_ms) *device_ms = ms;
+    int k = 0;
+    for (auto& p : E.pending) {
+        rc = E.finish_pending(p);
+        if (rc) return rc;
+        if (cks && k < cap) memcpy(cks + 3 * k, p.res.checksum, 24);
+        k++;
+    }
+    E.pending.clear();
+    if (n_frames) *n_frames = k;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (auto& d : done) cudaEventDestroy(d);
+    return 0;
+}
+
+int Engine::clip_profile(av1r_clip* clip, av1r_stage_times* out) {
+    EngineImpl& E = *impl_;
+    cudaSetDevice(E.cfg.device);
+    int rc = flush();
+    if (rc) return rc;
+    E.pending.clear();
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    // serialise on one stream so that the spans do not overlap
+    std::vector<cudaStream_t> saved = E.streams;
+    for (auto& st : E.streams) st = saved[0];
+    StageTimer tm;
+    E.tm = &tm;
+    rc = replay(E, clip);
+    E.tm = nullptr;
+    E.streams = saved;
+    if (rc) return rc;
+    if (cudaDeviceSynchronize() != cudaSuccess) return AV1R_EIO;
+    tm.collect(out);
+    for (auto& p : E.pending) E.finish_pending(p);
+    E.pending.clear();
+    return 0;
+}
+
+}  // namespace av1r
+
+extern "C" int av1r_clip_info_get(const av1r_clip* clip, av1r_clip_info* out) {
+    if (!clip || !out) return AV1R_EINVAL;
+    *out = clip->info;
+    return 0;
+}
+extern "C" void av1r_clip_free(av1r_clip* clip) { delete clip; }

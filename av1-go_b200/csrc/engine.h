@@ -6,6 +6,7 @@
 #include <string>
 
 #include "../../include/av1r.h"
+#include "../../include/av1r_stages.h"
 
 namespace av1r {
 
@@ -22,6 +23,10 @@ public:
     int copy_frame(int64_t handle, int plane, void* dst, size_t dst_stride);
     int release_frame(int64_t handle);
     const std::string& error() const;
+    // measurement: device-resident replay (include/av1r_stages.h)
+    int clip_load(const uint8_t* const* tus, const size_t* lens, int n, struct ::av1r_clip** out);
+    int clip_decode(struct ::av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, float* device_ms);
+    int clip_profile(struct ::av1r_clip* clip, struct ::av1r_stage_times* out);
     static int verify_file(const char* path, const av1r_config* cfg, av1r_report* out);
 
 private:

@@ -78,3 +78,18 @@ extern "C" int av1r_verify_file(const char* path, const av1r_config* cfg, av1r_r
     if (!path || !out) return AV1R_EINVAL;
     return Engine::verify_file(path, cfg, out);
 }
+
+extern "C" int av1r_clip_load(av1r_ctx* ctx, const uint8_t* const* tus, const size_t* lens, int n_tus, av1r_clip** out) {
+    if (!ctx || !tus || !lens || !out) return AV1R_EINVAL;
+    return ctx->eng->clip_load(tus, lens, n_tus, out);
+}
+extern "C" int av1r_clip_decode(av1r_ctx* ctx, av1r_clip* clip, uint64_t* checksums, int cap_frames, int* n_frames, float* device_ms) {
+    if (!ctx || !clip) return AV1R_EINVAL;
+    return ctx->eng->clip_decode(clip, checksums, cap_frames, n_frames, device_ms);
+}
+extern "C" int av1r_clip_profile(av1r_ctx* ctx, av1r_clip* clip, av1r_stage_times* out) {
+    if (!ctx || !clip || !out) return AV1R_EINVAL;
+    return ctx->eng->clip_profile(clip, out);
+}
+
+// clip info / free need the full type: provided by engine.cu

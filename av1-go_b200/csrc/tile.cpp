@@ -78,6 +78,7 @@ TileDecoder::TileDecoder(const SeqHdr& s, const HeaderParser& h, FrameWork& f, c
     }
     above_seg_pred.assign(fw.mi_cols + 64, 0);
     left_seg_pred.assign(fw.mi_rows + 64, 0);
+    memset(quant, 0, sizeof(quant));
 }
 
 void TileDecoder::clear_block_decoded_flags(int r, int c, int sb4) {
@@ -965,8 +966,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             }
         }
         if (eob > width * height) { fail(AV1R_EBITSTREAM, "eob exceeds transform size"); return 0; }
-        // levels, reverse scan
-        memset(quant, 0, sizeof(int32_t) * width * height);
+        // levels, reverse scan (quant[] is all-zero on entry: touched positions are cleared on exit)
         static const int8_t sig_ref[3][5][2] = {{{0, 1}, {1, 0}, {1, 1}, {0, 2}, {2, 0}},
                                                 {{0, 1}, {1, 0}, {0, 2}, {0, 3}, {0, 4}},
                                                 {{0, 1}, {1, 0}, {2, 0}, {3, 0}, {4, 0}}};
@@ -1061,6 +1061,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             if (cul_level > 63) cul_level = 63;
             fw.coefs.push_back(coef_token(pos, sign ? -level : level));
         }
+        for (int c = 0; c < eob; c++) quant[scan[c]] = 0;
         fw.coef_tokens += eob;
     }
     for (int i = 0; i < w4; i++) {

@@ -70,6 +70,43 @@ uint64_t av1r_plane_checksum_host(const void* src, size_t pitch, int w, int h, i
 
 const char* av1r_stage_last_error(void);
 
+/* ---- device-resident clip replay (measurement): parse + upload once, then time the device path ----
+ * av1r_clip_load runs the sequential host parse of every temporal unit and uploads the work-lists to
+ * HBM (untimed).  av1r_clip_decode replays the reconstruction of the whole clip from those resident
+ * work-lists: this is the region `value` in bench.py times (CUDA events, all streams fenced by the
+ * start/stop events).  av1r_clip_profile replays serially on one stream with an event between the
+ * stages and reports per-stage device time and launch counts (the live roofline input). */
+struct av1r_ctx;
+typedef struct av1r_clip av1r_clip;
+
+typedef struct av1r_clip_info {
+    uint32_t struct_size;
+    int width, height, bit_depth;
+    int64_t frames_decoded, frames_shown;
+    double host_parse_ms;          /* sequential symbol parse, reported separately (north_star) */
+    uint64_t worklist_bytes;       /* H2D bytes of all work-lists */
+    uint64_t frame_bytes;          /* F: bytes of one frame (all planes, visible size) */
+    uint64_t coded_samples;        /* A summed over frames */
+    uint64_t coef_tokens;          /* non-zero coefficients summed over frames (4 B each = C) */
+    uint64_t tx_blocks;            /* transform-block records summed over frames (32 B each) */
+    uint64_t intra_samples;        /* samples reconstructed by the intra wavefront kernel */
+} av1r_clip_info;
+
+enum { AV1R_ST_H2D = 0, AV1R_ST_ITX, AV1R_ST_INTRA, AV1R_ST_INTER, AV1R_ST_DEBLOCK, AV1R_ST_CDEF, AV1R_ST_LR, AV1R_ST_GRAIN,
+       AV1R_ST_DIGEST, AV1R_ST_COUNT };
+typedef struct av1r_stage_times {
+    uint32_t struct_size;
+    float ms[AV1R_ST_COUNT];       /* summed over the clip */
+    int launches[AV1R_ST_COUNT];   /* kernel launches (copies for H2D) */
+} av1r_stage_times;
+
+int av1r_clip_load(struct av1r_ctx* ctx, const uint8_t* const* tus, const size_t* lens, int n_tus, av1r_clip** out);
+int av1r_clip_info_get(const av1r_clip* clip, av1r_clip_info* out);
+/* checksums: caller array of cap_frames*3 uint64 (display order); *n_frames = frames produced. */
+int av1r_clip_decode(struct av1r_ctx* ctx, av1r_clip* clip, uint64_t* checksums, int cap_frames, int* n_frames, float* device_ms);
+int av1r_clip_profile(struct av1r_ctx* ctx, av1r_clip* clip, av1r_stage_times* out);
+void av1r_clip_free(av1r_clip* clip);
+
 #ifdef __cplusplus
 }
 #endif

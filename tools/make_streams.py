@@ -1,0 +1,50 @@
+"""Deterministic synthetic AV1 clips for the BASELINE configs.  Clips are cached under
+streams_cache/ (git-ignored, shipped to the GPU box by gpurun); regenerate with
+    python -m tools.make_streams c2 [--frames N]
+No ffmpeg / lavfi exists in the image, so `testsrc2` is re-synthesised in numpy ("testsrc2-like")."""
+import argparse
+import os
+import sys
+
+from . import aomenc, obuio, sources
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CACHE = os.path.join(ROOT, "streams_cache")
+
+# name: (source, w, h, bpc, frames, opts, cfg)   cfg[14] = lag_in_frames, cfg[48] = kf_max_dist
+CONFIGS = {
+    # configs[1]: 1080p 8-bit intra-only (every frame KEY), inverse transform + intra + deblock/CDEF only
+    "c2": ("panzoom", 1920, 1080, 8, 60, {"cpu-used": "8", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "1"}, {14: 0, 48: 0}),
+    "c2_small": ("panzoom", 640, 360, 8, 8, {"cpu-used": "8", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "1"}, {14: 0, 48: 0}),
+}
+
+
+def clip_path(name, frames=None):
+    src, w, h, bpc, n, opts, cfg = CONFIGS[name]
+    n = frames or n
+    return os.path.join(CACHE, f"{name}_{w}x{h}_{bpc}b_{n}f.ivf")
+
+
+def get_clip(name, frames=None, verbose=False):
+    """Returns the list of temporal units of a config clip, generating (and caching) it if needed."""
+    path = clip_path(name, frames)
+    if os.path.exists(path):
+        return obuio.read_ivf(path)
+    src, w, h, bpc, n, opts, cfg = CONFIGS[name]
+    n = frames or n
+    if verbose:
+        print(f"encoding {name}: {w}x{h} {bpc}-bit {n} frames with libaom ...", file=sys.stderr)
+    fr = sources.SOURCES[src](w, h, n, bpc=bpc, seed=3)
+    tus = aomenc.encode(fr, w, h, bpc=bpc, opts=opts, cfg=cfg, threads=os.cpu_count() or 8)
+    os.makedirs(CACHE, exist_ok=True)
+    obuio.write_ivf(path, tus, w, h)
+    return tus
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("name")
+    ap.add_argument("--frames", type=int, default=None)
+    a = ap.parse_args()
+    t = get_clip(a.name, a.frames, verbose=True)
+    print(clip_path(a.name, a.frames), len(t), "TUs", sum(len(x) for x in t), "bytes")
