@@ -46,7 +46,7 @@ class FrameHeaderInfo(C.Structure):
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int), ("streams", C.c_int),
                 ("frames_in_flight", C.c_int), ("parity_md5", C.c_int), ("apply_grain", C.c_int),
-                ("inloop_filters", C.c_int), ("keep_frames", C.c_int)]
+                ("inloop_filters", C.c_int), ("keep_frames", C.c_int), ("host_threads", C.c_int)]
 
 
 class FrameResult(C.Structure):
@@ -262,3 +262,18 @@ class Clip:
         if self.h:
             self.dec.l.av1r_clip_free(self.h)
             self.h = C.c_void_p()
+
+
+def verify_buffer(data, device=0, host_threads=0, apply_grain=1, inloop_filters=7, streams=16, frames_in_flight=32, want_digests=True, max_frames=100000):
+    """av1r_verify_buffer: whole container in host memory -> (Report, [digest triples])."""
+    l = lib()
+    l.av1r_verify_buffer.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(Config), C.POINTER(Report), C.POINTER(C.c_uint64), C.c_int64]
+    cfg = Config()
+    l.av1r_default_config(C.byref(cfg))
+    cfg.device, cfg.host_threads, cfg.apply_grain, cfg.inloop_filters = device, host_threads, apply_grain, inloop_filters
+    cfg.streams, cfg.frames_in_flight = streams, frames_in_flight
+    rep = Report()
+    dig = (C.c_uint64 * (3 * max_frames))() if want_digests else None
+    rc = l.av1r_verify_buffer(data, len(data), C.byref(cfg), C.byref(rep), dig, max_frames if want_digests else 0)
+    digs = [tuple(dig[3 * i:3 * i + 3]) for i in range(int(rep.frames))] if want_digests else []
+    return rc, rep, digs

@@ -16,4 +16,5 @@ extern "C" void av1r_default_config(av1r_config* cfg) {
     cfg->apply_grain = 1;
     cfg->inloop_filters = 7;
     cfg->keep_frames = 0;
+    cfg->host_threads = 0;
 }

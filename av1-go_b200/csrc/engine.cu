@@ -7,7 +7,11 @@
 // No CPU fallback exists: without a CUDA device av1r_open fails.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -156,7 +160,7 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     for (const TxRec& r : fw.tx) n_order += r.eob > 0;
     L.n_order = n_order;
     L.n_sbs = (int)fw.sbs.size();
-    // work items = runs of superblocks sharing (tile, sb_row); sbs are stored tile by tile, row by row
+    // work items = runs of 64x64 units sharing (tile, sb_row); units are stored tile by tile, SB row by SB row
     dw.items_host.clear();
     for (int i = 0; i < L.n_sbs;) {
         int j = i;
@@ -164,14 +168,14 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
                fw.sbs[j].tile_sb_row0 == fw.sbs[i].tile_sb_row0)
             j++;
         SbRowItem it;
-        it.first_sb = (uint32_t)i;
-        it.n_sb = (uint32_t)(j - i);
+        it.first_unit = (uint32_t)i;
+        it.n_units = (uint32_t)(j - i);
+        it.n_sb = (uint32_t)(fw.sbs[i].tile_sb_col1 - fw.sbs[i].tile_sb_col0);
         it.frame = 0;
         it.dep_item = -1;
         if (fw.sbs[i].sb_row > fw.sbs[i].tile_sb_row0) {
-            // the previous item of the same tile is the row above
             for (int k = (int)dw.items_host.size() - 1; k >= 0; k--) {
-                const SbRange& a = fw.sbs[dw.items_host[k].first_sb];
+                const SbRange& a = fw.sbs[dw.items_host[k].first_unit];
                 if (a.tile_sb_col0 == fw.sbs[i].tile_sb_col0 && a.tile_sb_row0 == fw.sbs[i].tile_sb_row0 && a.sb_row + 1 == fw.sbs[i].sb_row) {
                     it.dep_item = k;
                     break;
@@ -287,8 +291,10 @@ struct EngineImpl {
     std::vector<std::unique_ptr<FrameSlot>> slots;
     int next_slot = 0, next_stream = 0;
     std::deque<Pending> pending;          // outputs in display order
-    std::shared_ptr<DevFrameBuf> refs[8];
-    FilmGrainParams ref_fg[8];
+    // reference slots of the GOP segment currently being issued (av1r_verify_* switches between segments)
+    struct RefState { std::shared_ptr<DevFrameBuf> refs[8]; };
+    RefState main_refs;
+    RefState* rs = &main_refs;
     std::vector<std::shared_ptr<DevFrameBuf>> kept;   // keep_frames handles
     std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
     int64_t frames_decoded = 0;
@@ -363,7 +369,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     il.progress = (int*)s.sync.p;
     il.ticket = (int*)s.sync.p + L.n_items;
     il.n_items = L.n_items;
-    CK(launch_intra(il, fp.bd, st));
+    il.smem_per_warp = 0;
+    CK(launch_intra(il, fp.bd, fp.subx, fp.suby, st));
     if (tm) tm->end(AV1R_ST_INTRA, L.n_items > 0, st);
     std::shared_ptr<DevFrameBuf> cur = recon;
     if (dw.lf_on && (cfg.inloop_filters & 1)) {
@@ -499,7 +506,7 @@ int EngineImpl::prepare_work(const FrameWork& fw, DevWork& dw) {
 
 int EngineImpl::exec_show_existing(int slot_idx, const FrameHdr& fh, int show_slot, int64_t pts) {
     FrameSlot& s = *slots[slot_idx];
-    auto f = refs[show_slot];
+    auto f = rs->refs[show_slot];
     if (!f) { err = "show_existing_frame of an empty slot"; return AV1R_EBITSTREAM; }
     DevFrameParams fp;
     FrameWork dummy;
@@ -511,7 +518,7 @@ int EngineImpl::exec_show_existing(int slot_idx, const FrameHdr& fh, int show_sl
     CK(cudaEventRecord(s.ev1, s.stream));
     s.busy = true;
     if (fh.frame_type == KEY_FRAME)
-        for (int i = 0; i < 8; i++) refs[i] = f;
+        for (int i = 0; i < 8; i++) rs->refs[i] = f;
     return 0;
 }
 
@@ -522,7 +529,7 @@ int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_a
     int rc = run_frame(s, dw, d_arena, out);
     if (rc) return rc;
     for (int i = 0; i < 8; i++)
-        if ((dw.fh.refresh_frame_flags >> i) & 1) refs[i] = out;
+        if ((dw.fh.refresh_frame_flags >> i) & 1) rs->refs[i] = out;
     if (dw.fh.show_frame) {
         rc = emit_output(&s, slot_idx, out, dw.fh, dw.fh.fg, dw.fp, pts, dw.parse_ms, false);
         if (rc) return rc;
@@ -587,7 +594,7 @@ Engine::~Engine() {
         impl_->pending.clear();
         impl_->kept.clear();
         impl_->pool.clear();
-        for (auto& r : impl_->refs) r.reset();
+        for (auto& r : impl_->main_refs.refs) r.reset();
         for (auto st : impl_->streams) cudaStreamDestroy(st);
     }
     delete impl_;
@@ -600,6 +607,9 @@ int Engine::open(const av1r_config& cfg) {
     E.cfg = cfg;
     if (E.cfg.streams <= 0) E.cfg.streams = 2;
     if (E.cfg.frames_in_flight <= 0) E.cfg.frames_in_flight = 8;
+    // frame-level overlap uses many streams: give them their own hardware queues (default is 8, which caps
+    // the number of concurrently running wavefront kernels).  Only effective before the context exists.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -698,34 +708,165 @@ int Engine::verify_file(const char* path, const av1r_config* cfg, av1r_report* o
     memset(out, 0, sizeof(*out));
     out->struct_size = sizeof(*out);
     out->first_bad_frame = -1;
-    DemuxResult dm;
-    std::string derr;
-    if (!demux_file(path, dm, derr)) {
+    FILE* f = fopen(path, "rb");
+    if (!f) {
         out->status = AV1R_ENOENT;
-        snprintf(out->message, sizeof(out->message), "%s", derr.c_str());
+        snprintf(out->message, sizeof(out->message), "cannot open %s", path);
         return out->status;
     }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf(n > 0 ? n : 0);
+    size_t got = n > 0 ? fread(buf.data(), 1, n, f) : 0;
+    fclose(f);
+    if ((long)got != n) {
+        out->status = AV1R_EIO;
+        snprintf(out->message, sizeof(out->message), "short read on %s", path);
+        return out->status;
+    }
+    return verify_buffer(buf.data(), buf.size(), cfg, out, nullptr, 0);
+}
+
+// One key-frame-delimited GOP segment: parsed by one host thread, issued to the GPU in order.
+struct Segment {
+    size_t tu0 = 0, tu1 = 0;                       // temporal units [tu0, tu1)
+    std::vector<std::vector<ParsedFrame>> parsed;  // per TU
+    std::vector<int> rc;
+    std::vector<std::string> errs;
+    std::mutex m;
+    std::condition_variable cv;
+    size_t n_done = 0;                              // TUs parsed so far
+};
+
+int Engine::verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out, uint64_t* digests, int64_t cap_frames) {
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    out->first_bad_frame = -1;
+    auto fail = [&](int rc, const std::string& msg) {
+        out->status = rc;
+        snprintf(out->message, sizeof(out->message), "%s", msg.c_str());
+        return rc;
+    };
+    DemuxResult dm;
+    std::string derr;
+    if (!demux_buffer(data, len, dm, derr)) return fail(AV1R_EBITSTREAM, derr);
     av1r_config c;
     av1r_default_config(&c);
-    if (cfg) c = *cfg;
+    if (cfg) {
+        size_t n = cfg->struct_size && cfg->struct_size < sizeof(c) ? cfg->struct_size : sizeof(c);
+        memcpy(&c, cfg, n);
+        c.struct_size = sizeof(c);
+    }
+    if (c.streams <= 2) c.streams = 16;
+    if (c.frames_in_flight <= 8) c.frames_in_flight = 32;
+    int nthreads = c.host_threads > 0 ? c.host_threads : (int)std::thread::hardware_concurrency();
+    nthreads = std::max(1, std::min(nthreads, 32));
+    auto t0 = std::chrono::steady_clock::now();
+    // ---- pre-scan: sequence header + segment boundaries (TUs that start with a shown key frame)
+    HeaderParser scan;
+    if (!dm.config_obus.empty()) {
+        std::vector<ObuUnit> obus;
+        if (scan.split_obus(dm.config_obus.data(), dm.config_obus.size(), obus))
+            for (auto& u : obus)
+                if (u.type == OBU_SEQUENCE_HEADER) scan.parse_sequence_header(u.data, u.size);
+    }
+    std::vector<size_t> starts;
+    for (size_t i = 0; i < dm.tus.size(); i++) {
+        std::vector<ObuUnit> obus;
+        if (!scan.split_obus(data + dm.tus[i].offset, dm.tus[i].size, obus)) return fail(AV1R_EBITSTREAM, scan.error);
+        bool first_frame = true;
+        for (const ObuUnit& u : obus) {
+            if (u.type == OBU_SEQUENCE_HEADER) {
+                if (!scan.parse_sequence_header(u.data, u.size)) return fail(AV1R_EBITSTREAM, scan.error);
+            } else if (u.type == OBU_FRAME || u.type == OBU_FRAME_HEADER) {
+                BitReader br(u.data, u.size);
+                FrameHdr fh;
+                if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) return fail(AV1R_EBITSTREAM, scan.error);
+                if (first_frame && !fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
+                if (!fh.show_existing_frame) scan.reference_update(fh);
+                else if (fh.frame_type == KEY_FRAME) {
+                    RefHdrState r = scan.refs[fh.frame_to_show_map_idx];
+                    for (auto& x : scan.refs) x = r;
+                }
+                first_frame = false;
+            }
+        }
+    }
+    if (!scan.seq.valid) return fail(AV1R_EBITSTREAM, "no sequence header");
+    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+    const size_t nseg = starts.size();
+    std::vector<std::unique_ptr<Segment>> segs(nseg);
+    for (size_t s = 0; s < nseg; s++) {
+        segs[s] = std::make_unique<Segment>();
+        segs[s]->tu0 = starts[s];
+        segs[s]->tu1 = s + 1 < nseg ? starts[s + 1] : dm.tus.size();
+        const size_t n = segs[s]->tu1 - segs[s]->tu0;
+        segs[s]->parsed.resize(n);
+        segs[s]->rc.assign(n, 0);
+        segs[s]->errs.resize(n);
+    }
     Engine eng;
     int rc = eng.open(c);
-    if (rc) {
-        out->status = rc;
-        snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str());
-        return rc;
-    }
-    auto t0 = std::chrono::steady_clock::now();
+    if (rc) return fail(rc, eng.error());
+    EngineImpl& E = *eng.impl_;
+    E.sp.hp.seq = scan.seq;
+    // ---- parser threads: claim segments in order; bounded look-ahead (frames parsed but not yet issued)
+    std::atomic<size_t> next_seg{0};
+    std::atomic<bool> abort_flag{false};
+    std::mutex la_m;
+    std::condition_variable la_cv;
+    int64_t la_outstanding = 0;
+    const int64_t la_limit = std::max<int64_t>(2 * nthreads, 8);
+    auto worker = [&]() {
+        while (!abort_flag.load()) {
+            const size_t s = next_seg.fetch_add(1);
+            if (s >= nseg) return;
+            Segment& sg = *segs[s];
+            StreamParser sp;
+            sp.hp.seq = scan.seq;
+            for (size_t t = sg.tu0; t < sg.tu1 && !abort_flag.load(); t++) {
+                {
+                    std::unique_lock<std::mutex> lk(la_m);
+                    la_cv.wait(lk, [&] { return la_outstanding < la_limit || abort_flag.load(); });
+                    la_outstanding++;
+                }
+                std::vector<ParsedFrame> pfs;
+                int prc = sp.parse_tu(data + dm.tus[t].offset, dm.tus[t].size, dm.tus[t].pts, pfs);
+                {
+                    std::lock_guard<std::mutex> lk(sg.m);
+                    sg.parsed[t - sg.tu0] = std::move(pfs);
+                    sg.rc[t - sg.tu0] = prc;
+                    if (prc) sg.errs[t - sg.tu0] = sp.err;
+                    sg.n_done++;
+                }
+                sg.cv.notify_all();
+                if (prc) break;
+            }
+            {   // mark the remaining TUs of a failed segment as done so the consumer never blocks
+                std::lock_guard<std::mutex> lk(sg.m);
+                sg.n_done = sg.tu1 - sg.tu0;
+            }
+            sg.cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 0; i < nthreads; i++) pool.emplace_back(worker);
+    // ---- consumer: issue GPU work segment by segment, TU by TU (display order)
     std::vector<av1r_frame_result> res(64);
+    int64_t shown = 0;
     auto drain = [&](bool all) -> int {
         while (true) {
             int n = 0;
-            if (all) eng.flush();
+            if (all) {
+                int r = eng.flush();
+                if (r) return r;
+            }
             int r = eng.collect(res.data(), (int)res.size(), &n);
             if (r) return r;
             for (int i = 0; i < n; i++) {
-                out->frames++;
-                out->host_parse_ms += res[i].host_parse_ms;
+                if (digests && shown < cap_frames) memcpy(digests + 3 * shown, res[i].checksum, 24);
+                shown++;
                 out->device_ms += res[i].device_ms;
                 out->width = res[i].w;
                 out->height = res[i].h;
@@ -734,29 +875,57 @@ int Engine::verify_file(const char* path, const av1r_config* cfg, av1r_report* o
             if (n == 0) return 0;
         }
     };
-    if (!dm.config_obus.empty()) {
-        // Matroska CodecPrivate carries the sequence header
-        rc = eng.submit_tu(dm.config_obus.data(), dm.config_obus.size(), -1);
-    }
-    for (size_t i = 0; i < dm.tus.size() && !rc; i++) {
-        rc = eng.submit_tu(dm.file.data() + dm.tus[i].offset, dm.tus[i].size, dm.tus[i].pts);
-        if (rc) {
-            out->first_bad_frame = out->frames;
-            snprintf(out->message, sizeof(out->message), "temporal unit %zu: %s", i, eng.error().c_str());
-            break;
+    std::string msg;
+    for (size_t s = 0; s < nseg && !rc; s++) {
+        Segment& sg = *segs[s];
+        EngineImpl::RefState seg_refs;
+        E.rs = &seg_refs;
+        for (size_t t = 0; t < sg.tu1 - sg.tu0 && !rc; t++) {
+            std::vector<ParsedFrame> pfs;
+            int prc;
+            {
+                std::unique_lock<std::mutex> lk(sg.m);
+                sg.cv.wait(lk, [&] { return sg.n_done > t; });
+                pfs = std::move(sg.parsed[t]);
+                prc = sg.rc[t];
+                if (prc) msg = sg.errs[t];
+            }
+            for (ParsedFrame& pf : pfs) {
+                if (pf.fw) out->host_parse_ms += pf.fw->parse_ms;
+                int r = E.decode_parsed(pf);
+                if (r) { rc = r; msg = E.err; break; }
+            }
+            {
+                std::lock_guard<std::mutex> lk(la_m);
+                la_outstanding--;
+            }
+            la_cv.notify_all();
+            if (!rc && prc) rc = prc;
+            if (rc) {
+                out->first_bad_frame = shown;
+                char tmp[600];
+                snprintf(tmp, sizeof(tmp), "temporal unit %zu: %s", sg.tu0 + t, msg.c_str());
+                msg = tmp;
+                break;
+            }
+            int r = drain(false);
+            if (r) { rc = r; msg = E.err; }
         }
-        int r = drain(false);
-        if (r) { rc = r; snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str()); }
+        E.rs = &E.main_refs;
     }
+    abort_flag.store(true);
+    la_cv.notify_all();
+    for (auto& th : pool) th.join();
     int r = drain(true);
-    if (!rc && r) { rc = r; snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str()); }
+    if (!rc && r) { rc = r; msg = E.err; }
+    out->frames = shown;
     out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     out->frames_per_sec = out->wall_ms > 0 ? out->frames * 1000.0 / out->wall_ms : 0;
     out->status = rc;
-    if (!rc) snprintf(out->message, sizeof(out->message), "ok: %lld frames", (long long)out->frames);
+    if (rc) snprintf(out->message, sizeof(out->message), "%s", msg.c_str());
+    else snprintf(out->message, sizeof(out->message), "ok: %lld frames, %zu GOP segments, %d parser threads", (long long)out->frames, nseg, nthreads);
     return rc;
 }
-
 
 }  // namespace av1r
 

@@ -78,6 +78,11 @@ extern "C" int av1r_verify_file(const char* path, const av1r_config* cfg, av1r_r
     if (!path || !out) return AV1R_EINVAL;
     return Engine::verify_file(path, cfg, out);
 }
+extern "C" int av1r_verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out, uint64_t* digests,
+                                  int64_t cap_frames) {
+    if (!data || !out) return AV1R_EINVAL;
+    return Engine::verify_buffer(data, len, cfg, out, digests, cap_frames);
+}
 
 extern "C" int av1r_clip_load(av1r_ctx* ctx, const uint8_t* const* tus, const size_t* lens, int n_tus, av1r_clip** out) {
     if (!ctx || !tus || !lens || !out) return AV1R_EINVAL;

@@ -190,6 +190,12 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
 
 cudaError_t launch_cdef(const CdefLaunch& L, cudaStream_t s) {
     dim3 grid((L.fp.mi_cols + 15) >> 4, (L.fp.mi_rows + 15) >> 4);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(cdef_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(cdef_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_done = true;
+    }
     if (L.fp.bd == 8) cdef_kernel<uint8_t><<<grid, 256, 0, s>>>(L);
     else cdef_kernel<uint16_t><<<grid, 256, 0, s>>>(L);
     return cudaGetLastError();

@@ -1,14 +1,18 @@
-// K3 -- intra prediction + residual add, wavefront-scheduled (AV1 spec 7.11.2, 7.11.5, 7.12.3).
+// K3 -- intra prediction + residual add, wavefront over superblock rows with the current 64x64 unit
+// resident in shared memory (AV1 spec 7.11.2, 7.11.5, 7.12.3).
 //
-// Intra prediction reads *reconstructed* neighbours, so transform blocks inside a superblock run in
-// decode order and superblock rows run as a wavefront (row r may process SB c once row r-1 has
-// finished SB c+1; rows of different tiles and of different frames are independent).  One warp owns
-// one (tile, SB row) work item and walks its records; lanes split the pixels of each block.
-// Inter-row hand-off uses per-item progress counters in global memory (release: __threadfence +
-// store, acquire: volatile load + __threadfence) and all neighbour reads go through L2 (ld.cg) so a
-// stale L1 line can never be observed.  Work items are claimed through an atomic ticket so a warp
-// only ever waits on items that are already running (no co-residency assumption).
-// Algorithmic bytes: F_intra written + 2A residual read; neighbour edges are L2 hits.
+// Intra prediction reads *reconstructed* neighbours and the decode order inside a superblock is a
+// Z-order whose bottom-left quadrant depends on the top-right one, so the blocks of a superblock form
+// one long dependency chain; the only parallelism is across superblock rows (row r may process SB c once
+// row r-1 has finished SB c+1), across tiles and across frames.  What can be optimised is the *latency
+// of one link of the chain*: one warp owns one (tile, SB row) item and keeps the 64x64 luma unit (+ its
+// chroma) it is working on in shared memory together with the row above / column left of the unit
+// (loaded from HBM/L2 once per unit), so the neighbour fetches of every block are shared-memory reads
+// instead of L2 round trips; reconstructed samples are written through to the frame in HBM.
+// Inter-row hand-off: per-item progress counters (release: __threadfence + store, acquire: volatile
+// load + __threadfence); halo reads use ld.cg so a stale L1 line can never be observed.  Items are
+// claimed through an atomic ticket, so a warp only waits on items that are already running.
+// Algorithmic bytes: F_intra written + 2A residual read + 32 B/record; halos are L2 hits.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,6 +39,21 @@ struct IntraSmem {
     int32_t above[2][EDGE_LEN];
     int32_t left[2][EDGE_LEN];
     int16_t tile[64 * 64 / 4];   // 32x32 int16: filter-intra predictions / CfL luma terms
+};
+
+// The 64x64 unit being reconstructed, resident in shared memory (per warp).
+template <typename T>
+struct UnitView {
+    T* tile[3];        // [th][tw] samples of the unit
+    T* above[3];       // index -1 .. 2*tw-1 : frame row just above the unit
+    T* left[3];        // index 0 .. 2*th-1  : frame column just left of the unit
+    int ux0[3], uy0[3], tw[3], th[3];
+    __device__ __forceinline__ int px(int plane, int x, int y) const {
+        const int dx = x - ux0[plane], dy = y - uy0[plane];
+        if (dy < 0) return above[plane][dx];
+        if (dx < 0) return left[plane][dy];
+        return tile[plane][dy * tw[plane] + dx];
+    }
 };
 
 template <typename T>
@@ -102,16 +121,18 @@ __device__ __forceinline__ void edge_upsample_d(const int32_t* src, int32_t* dst
 }
 
 template <typename T>
-__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm, int lane) {
+__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
+                            const UnitView<T>& uv, int lane) {
     const int plane = r.plane;
     const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
     const int w = 1 << lw, h = 1 << lh;
     const int x = r.x4 * 4, y = r.y4 * 4;
     const int bd = fp.bd, pixmax = (1 << bd) - 1;
     const int max_x = fp.cw[plane] - 1, max_y = fp.ch[plane] - 1;
-    const uint8_t* base = fr.p[plane];
     const uint32_t pitch = fr.pitch[plane];
     const int xe = min(w, fp.cw[plane] - x), ye = min(h, fp.ch[plane] - y);
+    T* tl = uv.tile[plane] + (y - uv.uy0[plane]) * uv.tw[plane] + (x - uv.ux0[plane]);
+    const int tpitch = uv.tw[plane];
     T* out = (T*)(fr.p[plane] + (size_t)y * pitch) + x;
     const int opitch = pitch / sizeof(T);
     const int16_t* rp = (const int16_t*)((const uint8_t*)res.p[plane] + (size_t)y * res.pitch[plane]) + x;
@@ -121,6 +142,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
         if (i < ye && j < xe) {
             if (has_res) v = min(max(v + (int)__ldg(rp + i * rpitch + j), 0), pixmax);
             out[i * opitch + j] = (T)v;
+            tl[i * tpitch + j] = (T)v;
         }
     };
     if (r.mode == TXM_INTER) {   // residual on top of the inter predictor
@@ -129,7 +151,9 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
                 const int i = idx >> lw, j = idx & (w - 1);
                 if (i < ye && j < xe) {
                     int v = (int)__ldcg(out + i * opitch + j) + (int)__ldg(rp + i * rpitch + j);
-                    out[i * opitch + j] = (T)min(max(v, 0), pixmax);
+                    v = min(max(v, 0), pixmax);
+                    out[i * opitch + j] = (T)v;
+                    tl[i * tpitch + j] = (T)v;
                 }
             }
         return;
@@ -144,17 +168,17 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
         int a, l;
         if (have_above) {
             const int idx = have_ar ? min(i, 2 * w - 1) : min(i, w - 1);
-            a = ldpx<T>(base, pitch, min(max_x, x + idx), y - 1);
+            a = uv.px(plane, min(max_x, x + idx), y - 1);
         } else if (have_left) {
-            a = ldpx<T>(base, pitch, x - 1, y);
+            a = uv.px(plane, x - 1, y);
         } else {
             a = (1 << (bd - 1)) - 1;
         }
         if (have_left) {
             const int idx = have_bl ? min(i, 2 * h - 1) : min(i, h - 1);
-            l = ldpx<T>(base, pitch, x - 1, min(max_y, y + idx));
+            l = uv.px(plane, x - 1, min(max_y, y + idx));
         } else if (have_above) {
-            l = ldpx<T>(base, pitch, x, y - 1);
+            l = uv.px(plane, x, y - 1);
         } else {
             l = (1 << (bd - 1)) + 1;
         }
@@ -163,9 +187,9 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
     }
     if (lane == 0) {
         int c;
-        if (have_above && have_left) c = ldpx<T>(base, pitch, x - 1, y - 1);
-        else if (have_above) c = ldpx<T>(base, pitch, x, y - 1);
-        else if (have_left) c = ldpx<T>(base, pitch, x - 1, y);
+        if (have_above && have_left) c = uv.px(plane, x - 1, y - 1);
+        else if (have_above) c = uv.px(plane, x, y - 1);
+        else if (have_left) c = uv.px(plane, x - 1, y);
         else c = 1 << (bd - 1);
         above[-1] = c;
         left[-1] = c;
@@ -346,8 +370,6 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
     {
         const int sx = fp.subx, sy = fp.suby;
         const int max_lw = r.cfl_max_w4 * 4, max_lh = r.cfl_max_h4 * 4;
-        const uint8_t* lbase = fr.p[0];
-        const uint32_t lpitch = fr.pitch[0];
         int16_t* L = sm.tile;
         int s = 0;
         for (int idx = lane; idx < w * h; idx += 32) {
@@ -355,7 +377,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
             const int ly = min((y + i) << sy, max_lh - (1 << sy)), lx = min((x + j) << sx, max_lw - (1 << sx));
             int t = 0;
             for (int dy2 = 0; dy2 <= sy; dy2++)
-                for (int dx2 = 0; dx2 <= sx; dx2++) t += ldpx<T>(lbase, lpitch, lx + dx2, ly + dy2);
+                for (int dx2 = 0; dx2 <= sx; dx2++) t += uv.px(0, lx + dx2, ly + dy2);
             const int v = t << (3 - sx - sy);
             L[idx] = (int16_t)v;
             s += v;
@@ -375,9 +397,26 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
 
 template <typename T>
 __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(IntraLaunch L) {
-    __shared__ IntraSmem s_sm[INTRA_WARPS];
+    extern __shared__ __align__(16) uint8_t s_raw[];
     const int warp_in = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    IntraSmem& sm = s_sm[warp_in];
+    uint8_t* wbase = s_raw + (size_t)warp_in * L.smem_per_warp;
+    IntraSmem& sm = *reinterpret_cast<IntraSmem*>(wbase);
+    UnitView<T> uv;
+    {
+        T* p = reinterpret_cast<T*>(wbase + sizeof(IntraSmem));
+        const DevFrameParams& fp0 = L.frames[0].fp;
+        for (int pl = 0; pl < 3; pl++) {
+            const int sx = pl ? fp0.subx : 0, sy = pl ? fp0.suby : 0;
+            uv.tw[pl] = 64 >> sx;
+            uv.th[pl] = 64 >> sy;
+            uv.tile[pl] = p;
+            p += uv.tw[pl] * uv.th[pl];
+            uv.above[pl] = p + 8;            // index -1 valid
+            p += 2 * uv.tw[pl] + 16;
+            uv.left[pl] = p;
+            p += 2 * uv.th[pl] + 8;
+        }
+    }
     while (true) {
         int item = 0;
         if (lane == 0) item = atomicAdd(L.ticket, 1);
@@ -385,26 +424,60 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(Intra
         if (item >= L.n_items) return;
         const SbRowItem it = L.items[item];
         const IntraFrame& F = L.frames[it.frame];
+        const DevFrameParams& fp = F.fp;
+        const int nplanes = fp.mono ? 1 : 3;
         volatile int* dep = it.dep_item >= 0 ? (volatile int*)(L.progress + it.dep_item) : nullptr;
-        for (uint32_t k = 0; k < it.n_sb; k++) {
-            if (dep) {
-                const int need = (int)min(k + 2, it.n_sb);
+        int sb_done = 0;
+        for (uint32_t k = 0; k < it.n_units; k++) {
+            const SbRange un = F.sbs[it.first_unit + k];
+            const bool first_of_sb = (k == 0) || (F.sbs[it.first_unit + k - 1].sb_col != un.sb_col);
+            if (first_of_sb && dep) {
+                // superblock index inside the tile row
+                const int c = un.sb_col - un.tile_sb_col0;
+                const int need = min(c + 2, (int)it.n_sb);
                 if (lane == 0)
                     while (*dep < need) __nanosleep(64);
                 __syncwarp();
-                __threadfence();
-            }
-            const SbRange sb = F.sbs[it.first_sb + k];
-            for (uint32_t t = 0; t < sb.count; t++) {
-                const TxRec r = F.recs[sb.first + t];
-                intra_block<T>(r, F.frame, F.res, F.fp, sm, lane);
-                __threadfence_block();
-                __syncwarp();
             }
             __threadfence();
+            // ---- load the halo of the unit: row above (-1 .. 2tw-1) and column left (0 .. 2th-1)
+            for (int pl = 0; pl < nplanes; pl++) {
+                const int sx = pl ? fp.subx : 0, sy = pl ? fp.suby : 0;
+                const int ux0 = (un.ux * 64) >> sx, uy0 = (un.uy * 64) >> sy;
+                uv.ux0[pl] = ux0;
+                uv.uy0[pl] = uy0;
+                const T* base = (const T*)F.frame.p[pl];
+                const int pe = F.frame.pitch[pl] / sizeof(T);
+                const int max_x = fp.cw[pl] - 1, max_y = fp.ch[pl] - 1;
+                if (uy0 > 0)
+                    for (int i = lane - 1; i < 2 * uv.tw[pl]; i += 32) {
+                        const int x = min(max(ux0 + i, 0), max_x);
+                        uv.above[pl][i] = __ldcg(base + (size_t)(uy0 - 1) * pe + x);
+                    }
+                if (ux0 > 0)
+                    for (int i = lane; i < 2 * uv.th[pl]; i += 32) {
+                        const int y = min(uy0 + i, max_y);
+                        uv.left[pl][i] = __ldcg(base + (size_t)y * pe + ux0 - 1);
+                    }
+            }
             __syncwarp();
-            if (lane == 0) *(volatile int*)(L.progress + item) = (int)k + 1;
+            for (uint32_t t = 0; t < un.count; t++) {
+                const TxRec r = F.recs[un.first + t];
+                intra_block<T>(r, F.frame, F.res, fp, sm, uv, lane);
+                __syncwarp();
+            }
+            const bool last_of_sb = (k + 1 == it.n_units) || (F.sbs[it.first_unit + k + 1].sb_col != un.sb_col);
+            if (last_of_sb) {
+                __threadfence();
+                __syncwarp();
+                sb_done = un.sb_col - un.tile_sb_col0 + 1;
+                if (lane == 0) *(volatile int*)(L.progress + item) = sb_done;
+            }
         }
+        // superblocks without any intra record never appear in the list: publish the full row at the end
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *(volatile int*)(L.progress + item) = (int)it.n_sb;
     }
 }
 
@@ -422,13 +495,43 @@ static cudaError_t intra_upload_constants() {
     return cudaSuccess;
 }
 
-cudaError_t launch_intra(const IntraLaunch& L, int bd, cudaStream_t s) {
-    if (L.n_items <= 0) return cudaSuccess;
+size_t intra_smem_per_warp(int bd, int subx, int suby) {
+    const size_t ts = bd == 8 ? 1 : 2;
+    size_t n = sizeof(IntraSmem);
+    for (int pl = 0; pl < 3; pl++) {
+        const int sx = pl ? subx : 0, sy = pl ? suby : 0;
+        const int tw = 64 >> sx, th = 64 >> sy;
+        n += ts * (tw * th + 2 * tw + 16 + 2 * th + 8);
+    }
+    return (n + 15) & ~(size_t)15;
+}
+
+cudaError_t launch_intra(const IntraLaunch& L_, int bd, int subx, int suby, cudaStream_t s) {
+    if (L_.n_items <= 0) return cudaSuccess;
     cudaError_t e = intra_upload_constants();
     if (e != cudaSuccess) return e;
-    int blocks = (L.n_items + INTRA_WARPS - 1) / INTRA_WARPS;
-    if (bd == 8) intra_wavefront_kernel<uint8_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
-    else intra_wavefront_kernel<uint16_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
+    IntraLaunch L = L_;
+    L.smem_per_warp = (int)intra_smem_per_warp(bd, subx, suby);
+    const size_t smem = (size_t)L.smem_per_warp * INTRA_WARPS;
+    const int blocks = (L.n_items + INTRA_WARPS - 1) / INTRA_WARPS;
+    static bool attr_done[2] = {false, false};
+    if (bd == 8) {
+        auto k = intra_wavefront_kernel<uint8_t>;
+        if (!attr_done[0]) {
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr_done[0] = true;
+        }
+        k<<<blocks, INTRA_WARPS * 32, smem, s>>>(L);
+    } else {
+        auto k = intra_wavefront_kernel<uint16_t>;
+        if (!attr_done[1]) {
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr_done[1] = true;
+        }
+        k<<<blocks, INTRA_WARPS * 32, smem, s>>>(L);
+    }
     return cudaGetLastError();
 }
 

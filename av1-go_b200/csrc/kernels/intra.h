@@ -14,8 +14,9 @@ struct IntraFrame {            // one per frame in the batch (device array)
     DevFrameParams fp;
 };
 
-struct SbRowItem {             // one (tile, superblock row): the unit a warp owns
-    uint32_t first_sb, n_sb;   // range in IntraFrame::sbs
+struct SbRowItem {             // one (tile, superblock row): the work item a warp owns
+    uint32_t first_unit, n_units;   // 64x64 unit ranges in IntraFrame::sbs (decode order)
+    uint32_t n_sb;             // superblocks in this tile row (progress counts completed superblocks)
     int32_t dep_item;          // item index of the superblock row above in the same tile, -1 if none
     int32_t frame;             // index into IntraLaunch::frames
 };
@@ -26,9 +27,10 @@ struct IntraLaunch {
     int* progress;             // device, n_items ints, zeroed before launch
     int* ticket;               // device, one int, zeroed before launch
     int n_items;
+    int smem_per_warp;         // filled by launch_intra
 };
 
-cudaError_t launch_intra(const IntraLaunch& L, int bd, cudaStream_t s);
+cudaError_t launch_intra(const IntraLaunch& L, int bd, int subx, int suby, cudaStream_t s);
 cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, const uint32_t* coefs, const DevResidual& res,
                        const DevFrameParams& fp, cudaStream_t s);
 

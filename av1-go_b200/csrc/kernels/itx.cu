@@ -198,6 +198,11 @@ cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, const ui
     cudaError_t e = itx_upload_constants();
     if (e != cudaSuccess) return e;
     const int blocks = (n + ITX_WARPS - 1) / ITX_WARPS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(itx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_done = true;
+    }
     itx_kernel<<<blocks, ITX_WARPS * 32, 0, s>>>(recs, order, n, coefs, res, fp);
     return cudaGetLastError();
 }

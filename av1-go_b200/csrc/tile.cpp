@@ -143,19 +143,15 @@ int TileDecoder::decode_tile(const uint8_t* data, size_t sz, int tile_row, int t
                     }
             }
             clear_block_decoded_flags(r, c, sb4);
-            SbRange sr;
-            sr.first = (uint32_t)fw.tx.size();
-            sr.count = 0;
-            sr.sb_row = (uint16_t)(r >> sb_shift);
-            sr.sb_col = (uint16_t)(c >> sb_shift);
-            sr.tile_sb_col0 = (uint16_t)(mi_col_start >> sb_shift);
-            sr.tile_sb_col1 = (uint16_t)((mi_col_end + sb4 - 1) >> sb_shift);
-            sr.tile_sb_row0 = (uint16_t)(mi_row_start >> sb_shift);
-            sr.pad = 0;
+            memset(&cur_sb, 0, sizeof(cur_sb));
+            cur_sb.sb_row = (uint16_t)(r >> sb_shift);
+            cur_sb.sb_col = (uint16_t)(c >> sb_shift);
+            cur_sb.tile_sb_col0 = (uint16_t)(mi_col_start >> sb_shift);
+            cur_sb.tile_sb_col1 = (uint16_t)((mi_col_end + sb4 - 1) >> sb_shift);
+            cur_sb.tile_sb_row0 = (uint16_t)(mi_row_start >> sb_shift);
+            cur_unit = -1;
             read_lr(r, c, sb_size);
             if (!decode_partition(r, c, sb_size)) return fail_code ? fail_code : AV1R_EBITSTREAM;
-            sr.count = (uint32_t)fw.tx.size() - sr.first;
-            fw.sbs.push_back(sr);
         }
     }
     return fail_code;
@@ -807,6 +803,19 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
     rec.eob = (uint16_t)eob;
     rec.ntok = (uint16_t)(fw.coefs.size() - rec.coef_off);
     if (!b->is_inter || eob > 0) {
+        // records are grouped by 64x64 luma unit (decode order visits each unit contiguously)
+        const int ux = (start_x << sx) >> 6, uy = (start_y << sy) >> 6;
+        const int key = (uy << 16) | ux;
+        if (key != cur_unit) {
+            cur_unit = key;
+            SbRange sr = cur_sb;
+            sr.first = (uint32_t)fw.tx.size();
+            sr.count = 0;
+            sr.ux = (uint16_t)ux;
+            sr.uy = (uint16_t)uy;
+            fw.sbs.push_back(sr);
+        }
+        fw.sbs.back().count++;
         fw.tx.push_back(rec);
         fw.tx_blocks++;
     }

@@ -44,6 +44,8 @@ private:
     int mi_row = 0, mi_col = 0, bw4 = 0, bh4 = 0;
     int avail_u = 0, avail_l = 0, avail_u_chroma = 0, avail_l_chroma = 0;
     int max_luma_w = 0, max_luma_h = 0;
+    SbRange cur_sb;
+    int cur_unit = -1;
     int32_t quant[1024];
 
     bool fail(int code, const char* msg) { if (!fail_code) { fail_code = code; err = msg; } return false; }

@@ -48,12 +48,15 @@ static inline int coef_token_pos(uint32_t t) { return (int)(t & 1023); }
 static inline int coef_token_level(uint32_t t) { return (int32_t)t >> 10; }
 
 // Per-superblock slice of the TxRec list (wavefront unit of the intra kernel).
+// (a superblock is split into its 64x64 luma units: the unit is what the intra kernel keeps on chip)
 struct SbRange {
-    uint32_t first, count;  // TxRec indices
+    uint32_t first, count;  // TxRec indices of this 64x64 unit
     uint16_t sb_row, sb_col;  // in superblock units, absolute in the frame
     uint16_t tile_sb_col0;    // first superblock column of the tile (wavefront does not cross tiles)
     uint16_t tile_sb_col1;    // one past the last
-    uint16_t tile_sb_row0, pad;
+    uint16_t tile_sb_row0;
+    uint16_t ux, uy;          // unit position in 64-luma-sample units
+    uint16_t pad;
 };
 
 // Per-4x4 loop-filter description, one byte pair per plane 4x4 unit and direction:

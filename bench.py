@@ -10,6 +10,9 @@ synthetic input.  Workloads:
 The default is the most complete workload the engine currently decodes bit-exactly.
 PyTorch is used only for device buffers / events / torch.distributed plumbing.
 """
+import os as _os
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # frame-level overlap: one hardware queue per stream
+
 import argparse
 import ctypes as C
 import json
@@ -267,7 +270,7 @@ def run_c2(args, torch, dist, rank, world, local):
     import av1recon
     tus = c2_clip()
     torch.cuda.set_device(local)
-    dec = av1recon.Decoder(device=local, streams=4, frames_in_flight=16)
+    dec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
     clip = av1recon.Clip(dec, tus)
     info = clip.info
     nfr = int(info.frames_shown)
@@ -322,22 +325,31 @@ def run_c2(args, torch, dist, rank, world, local):
     dom_ms = stages[dom]["ms_per_clip"] / stages[dom]["launches"]
     dom_bytes = stage_bytes[dom] / stages[dom]["launches"]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
-    # e2e: the call a user makes -- av1r_submit_tu with HOST bitstream buffers (host parse + H2D of the
-    # work-lists + kernels + D2H of the 24-byte digests), wall clock
-    dec2 = av1recon.Decoder(device=local, streams=4, frames_in_flight=16)
-    for tu in tus[:4]:
-        dec2.submit(tu)
-    dec2.flush()
-    dec2.results.clear()
+    # e2e: the call a user makes -- av1r_verify_buffer on the HOST container bytes: demux, GOP-segment-parallel
+    # host symbol parse (all host cores), H2D of the work-lists, reconstruction kernels, D2H of the 24-byte
+    # plane digests of every frame.  Wall clock.
+    from tools.make_streams import clip_path
+    blob = open(clip_path("c2"), "rb").read()
+    av1recon.verify_buffer(blob, device=local)                      # warm-up (allocations, first-touch)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rc, rep, digs = av1recon.verify_buffer(blob, device=local)
+        dt = time.perf_counter() - t0
+        if rc:
+            raise RuntimeError(f"av1r_verify_buffer failed: {rep.message}")
+        if digs != cks0:
+            raise RuntimeError("e2e digests differ from replay digests")
+        best = dt if best is None else min(best, dt)
+    e2e_s = best
+    parse_ms = rep.host_parse_ms
+    # single-threaded streaming API (av1r_submit_tu per temporal unit), for reference
+    dec2 = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
     t0 = time.perf_counter()
     for i, tu in enumerate(tus):
         dec2.submit(tu, i)
     dec2.flush()
-    e2e_s = time.perf_counter() - t0
-    e2e_cks = [tuple(r.checksum) for r in dec2.results]
-    if e2e_cks != cks0:
-        raise RuntimeError("e2e digests differ from replay digests")
-    parse_ms = sum(r.host_parse_ms for r in dec2.results)
+    e2e_1t = nfr / (time.perf_counter() - t0)
     if world > 1:
         t = torch.tensor([e2e_s], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -349,10 +361,11 @@ def run_c2(args, torch, dist, rank, world, local):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": C2_DESC, "frames_per_step": nfr, "parallelism": f"replicas{world} (independent clips per GPU, no collective)",
-                   "streams": 4, "frames_in_flight": 16},
+                   "streams": 16, "frames_in_flight": 32},
         "gpu_launches": launches_per_step * args.steps,
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr,
-                "host_parse_ms_per_step": parse_ms, "note": "single host thread: sequential symbol parse dominates (reported separately per north_star)"},
+                "host_parse_ms_per_step": parse_ms, "host_threads": os.cpu_count(), "single_thread_submit_tu_fps": e2e_1t,
+                "note": "av1r_verify_buffer: key-frame-delimited GOP segments parsed on all host cores; host_parse_ms is the summed sequential symbol-parse time (north_star: reported separately)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "kernel": dom, "algorithmic_bytes_per_launch": dom_bytes,
                      "avg_launch_ms": dom_ms, "stages": stages,

@@ -49,6 +49,8 @@ typedef struct av1r_config {
     int apply_grain;       /* 1 (default): film grain synthesis on output frames, as libdav1d does */
     int inloop_filters;    /* bit mask 1=deblock 2=CDEF 4=loop restoration (7 = all; same meaning as dav1d) */
     int keep_frames;       /* 1: keep shown frames on the device so av1r_copy_frame can read them (tests) */
+    int host_threads;      /* av1r_verify_*: host threads parsing independent key-frame-delimited GOP segments
+                              in parallel (0 = number of online cores, capped at 32) */
 } av1r_config;
 
 typedef struct av1r_frame_result {
@@ -108,6 +110,10 @@ int av1r_release_frame(av1r_ctx* ctx, int64_t frame_handle);
 
 /* Whole-file convenience: demux (IVF / raw OBU / Matroska), decode every frame, report. */
 int av1r_verify_file(const char* path, const av1r_config* cfg, av1r_report* out);
+/* Same on a container already in host memory (IVF / raw OBU / Matroska bytes).  If `digests` is non-NULL it
+ * receives 3 x uint64 plane digests per shown frame in display order (cap_frames entries). */
+int av1r_verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out,
+                       uint64_t* digests, int64_t cap_frames);
 int av1r_probe_file(const char* path, av1r_stream_info* out);
 int av1r_probe_buffer(const uint8_t* data, size_t len, av1r_stream_info* out);
 

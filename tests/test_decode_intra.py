@@ -123,3 +123,31 @@ def test_cuda_checksum_matches_host_digest(built):
             want = l.av1r_plane_checksum_host(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], r.bpc)
             assert r.checksum[p] == want
     dec.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 4])
+def test_cuda_verify_buffer_segment_parallel(built, threads):
+    """av1r_verify_buffer (GOP-segment-parallel host parse) returns the same plane digests, in display
+    order, as the single-threaded streaming API."""
+    import av1recon
+    for name in ("intra_8b_200x136", "intra_8b_tiles_320x192", "intra_8b_grain_160x96"):
+        data = open(os.path.join(GOLD, name + ".ivf"), "rb").read()
+        rc, rep, digs = av1recon.verify_buffer(data, host_threads=threads)
+        assert rc == 0, rep.message
+        assert rep.frames == INDEX[name]["frames"] and rep.width == INDEX[name]["w"]
+        dec = _gpu_decode(name)
+        want = [tuple(r.checksum) for r in dec.results]
+        dec.close()
+        assert digs == want
+
+
+@pytest.mark.gpu
+def test_cuda_verify_reports_corruption(built):
+    """A truncated / corrupted stream must come back as an error with first_bad_frame set, like a failed
+    RunTranscode sets job.Reason (/root/reference/internal/daemon/daemon.go:102-112)."""
+    import av1recon
+    data = bytearray(open(os.path.join(GOLD, "intra_8b_200x136.ivf"), "rb").read())
+    cut = bytes(data[: len(data) // 2])
+    rc, rep, _ = av1recon.verify_buffer(cut, host_threads=2)
+    assert rc != 0 and rep.status == rc and len(rep.message) > 0
