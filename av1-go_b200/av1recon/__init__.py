@@ -125,7 +125,7 @@ def probe_buffer(data):
 class Decoder:
     """Thin wrapper over av1r_open / av1r_submit_tu / av1r_collect (the calls the cgo package makes)."""
 
-    def __init__(self, device=0, parity_md5=0, apply_grain=1, inloop_filters=7, keep_frames=0, streams=2, frames_in_flight=8):
+    def __init__(self, device=0, parity_md5=0, apply_grain=1, inloop_filters=7, keep_frames=0, streams=2, frames_in_flight=8, host_threads=0):
         l = lib()
         l.av1r_open.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         l.av1r_close.argtypes = [C.c_void_p]
@@ -139,6 +139,7 @@ class Decoder:
         l.av1r_default_config(C.byref(cfg))
         cfg.device, cfg.parity_md5, cfg.apply_grain, cfg.inloop_filters = device, parity_md5, apply_grain, inloop_filters
         cfg.keep_frames, cfg.streams, cfg.frames_in_flight = keep_frames, streams, frames_in_flight
+        cfg.host_threads = host_threads
         self.l = l
         self.ctx = C.c_void_p()
         rc = l.av1r_open(C.byref(cfg), C.byref(self.ctx))
@@ -192,6 +193,15 @@ class Decoder:
             a = a.view(np.uint8 if bps == 1 else np.dtype("<u2"))[:h, :w]
             out.append(np.ascontiguousarray(a))
         return out
+
+    def verify_buffer(self, data, want_digests=True, max_frames=100000):
+        """av1r_ctx_verify_buffer on this (persistent) engine -> (rc, Report, digests)."""
+        self.l.av1r_ctx_verify_buffer.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(Report), C.POINTER(C.c_uint64), C.c_int64]
+        rep = Report()
+        dig = (C.c_uint64 * (3 * max_frames))() if want_digests else None
+        rc = self.l.av1r_ctx_verify_buffer(self.ctx, data, len(data), C.byref(rep), dig, max_frames if want_digests else 0)
+        digs = [tuple(dig[3 * i:3 * i + 3]) for i in range(int(rep.frames))] if want_digests else []
+        return rc, rep, digs
 
     def close(self):
         if self.ctx:

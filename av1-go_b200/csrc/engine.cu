@@ -740,6 +740,32 @@ struct Segment {
 };
 
 int Engine::verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out, uint64_t* digests, int64_t cap_frames) {
+    av1r_config c;
+    av1r_default_config(&c);
+    if (cfg) {
+        size_t n = cfg->struct_size && cfg->struct_size < sizeof(c) ? cfg->struct_size : sizeof(c);
+        memcpy(&c, cfg, n);
+        c.struct_size = sizeof(c);
+    }
+    if (c.streams <= 2) c.streams = 16;
+    if (c.frames_in_flight <= 8) c.frames_in_flight = 32;
+    Engine eng;
+    int rc = eng.open(c);
+    if (rc) {
+        memset(out, 0, sizeof(*out));
+        out->struct_size = sizeof(*out);
+        out->first_bad_frame = -1;
+        out->status = rc;
+        snprintf(out->message, sizeof(out->message), "%s", eng.error().c_str());
+        return rc;
+    }
+    return eng.verify(data, len, out, digests, cap_frames);
+}
+
+// Verify a whole container with this (already open, reusable) engine.
+int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames) {
+    Engine& eng = *this;
+    const av1r_config& c = impl_->cfg;
     memset(out, 0, sizeof(*out));
     out->struct_size = sizeof(*out);
     out->first_bad_frame = -1;
@@ -751,17 +777,11 @@ int Engine::verify_buffer(const uint8_t* data, size_t len, const av1r_config* cf
     DemuxResult dm;
     std::string derr;
     if (!demux_buffer(data, len, dm, derr)) return fail(AV1R_EBITSTREAM, derr);
-    av1r_config c;
-    av1r_default_config(&c);
-    if (cfg) {
-        size_t n = cfg->struct_size && cfg->struct_size < sizeof(c) ? cfg->struct_size : sizeof(c);
-        memcpy(&c, cfg, n);
-        c.struct_size = sizeof(c);
-    }
-    if (c.streams <= 2) c.streams = 16;
-    if (c.frames_in_flight <= 8) c.frames_in_flight = 32;
     int nthreads = c.host_threads > 0 ? c.host_threads : (int)std::thread::hardware_concurrency();
     nthreads = std::max(1, std::min(nthreads, 32));
+    int rc = eng.flush();
+    if (rc) return fail(rc, eng.error());
+    impl_->pending.clear();
     auto t0 = std::chrono::steady_clock::now();
     // ---- pre-scan: sequence header + segment boundaries (TUs that start with a shown key frame)
     HeaderParser scan;
@@ -806,9 +826,6 @@ int Engine::verify_buffer(const uint8_t* data, size_t len, const av1r_config* cf
         segs[s]->rc.assign(n, 0);
         segs[s]->errs.resize(n);
     }
-    Engine eng;
-    int rc = eng.open(c);
-    if (rc) return fail(rc, eng.error());
     EngineImpl& E = *eng.impl_;
     E.sp.hp.seq = scan.seq;
     // ---- parser threads: claim segments in order; bounded look-ahead (frames parsed but not yet issued)

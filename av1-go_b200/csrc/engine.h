@@ -27,6 +27,7 @@ public:
     int clip_load(const uint8_t* const* tus, const size_t* lens, int n, struct ::av1r_clip** out);
     int clip_decode(struct ::av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, float* device_ms);
     int clip_profile(struct ::av1r_clip* clip, struct ::av1r_stage_times* out);
+    int verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames);
     static int verify_file(const char* path, const av1r_config* cfg, av1r_report* out);
     static int verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out, uint64_t* digests,
                              int64_t cap_frames);

@@ -98,3 +98,8 @@ extern "C" int av1r_clip_profile(av1r_ctx* ctx, av1r_clip* clip, av1r_stage_time
 }
 
 // clip info / free need the full type: provided by engine.cu
+
+extern "C" int av1r_ctx_verify_buffer(av1r_ctx* ctx, const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames) {
+    if (!ctx || !data || !out) return AV1R_EINVAL;
+    return ctx->eng->verify(data, len, out, digests, cap_frames);
+}

@@ -32,7 +32,7 @@ struct Msac {
         }
         if (bptr >= end) cnt = 0x4000;  // out of data: keep shifting in the implicit padding
     }
-    inline void normalize(uint64_t d, uint32_t r) {
+    __attribute__((always_inline)) inline void normalize(uint64_t d, uint32_t r) {
         int sh = 15 - (31 - __builtin_clz(r));   // 16 - ilog(r)
         cnt -= sh;
         dif = ((d + 1) << sh) - 1;
@@ -40,31 +40,55 @@ struct Msac {
         if (cnt < 0) refill();
     }
     // decode one symbol out of n with inverted cdf `c` (c[n-1] == 0, c[n] = counter); adapts.
-    inline int symbol(uint16_t* c, int n) {
+    // n is a compile-time constant at every call site; small alphabets (the coefficient symbols, > 90 % of
+    // all symbols) take a branch-free path: entropy-coded symbols are unpredictable by construction, so a
+    // compare-and-count beats the data-dependent search loop.
+    __attribute__((always_inline)) inline int symbol(uint16_t* c, int n) {
         const uint32_t r = rng;
         const uint32_t v16 = (uint32_t)(dif >> 48);
-        uint32_t u, v = r;
-        int s = -1;
-        do {
-            u = v;
-            s++;
-            v = ((r >> 8) * (uint32_t)(c[s] >> 6) >> 1) + 4 * (uint32_t)(n - 1 - s);
-        } while (v16 < v);
+        const uint32_t r8 = r >> 8;
+        int s;
+        uint32_t u, v;
+        if (n <= 4) {
+            uint32_t t[4];
+            t[0] = ((r8 * (uint32_t)(c[0] >> 6)) >> 1) + 4 * (uint32_t)(n - 1);
+            t[1] = n > 2 ? ((r8 * (uint32_t)(c[1] >> 6)) >> 1) + 4 * (uint32_t)(n - 2) : 0;
+            t[2] = n > 3 ? ((r8 * (uint32_t)(c[2] >> 6)) >> 1) + 4 * (uint32_t)(n - 3) : 0;
+            t[3] = 0;
+            s = (v16 < t[0]) + (n > 2 ? (v16 < t[1]) : 0) + (n > 3 ? (v16 < t[2]) : 0);
+            u = s ? t[s - 1] : r;
+            v = t[s];
+        } else {
+            v = r;
+            s = -1;
+            do {
+                u = v;
+                s++;
+                v = ((r8 * (uint32_t)(c[s] >> 6)) >> 1) + 4 * (uint32_t)(n - 1 - s);
+            } while (v16 < v);
+        }
         normalize(dif - ((uint64_t)v << 48), u - v);
         if (update) adapt(c, s, n);
         return s;
     }
-    static inline void adapt(uint16_t* c, int val, int n) {
+    __attribute__((always_inline)) static inline void adapt(uint16_t* c, int val, int n) {
         const int cnt_ = c[n];
-        const int rate = 3 + (cnt_ > 15) + (cnt_ > 31) + (n > 3 ? 2 : (n > 2 ? 1 : (n > 1 ? 1 : 0)));
-        // Min(FloorLog2(n), 2): n=2 ->1, n=3 ->1, n>=4 ->2
-        for (int i = 0; i < n - 1; i++) {
-            if (i < val) c[i] += (32768 - c[i]) >> rate;
-            else c[i] -= c[i] >> rate;
+        const int rate = 3 + (cnt_ > 15) + (cnt_ > 31) + (n > 3 ? 2 : 1);   // + Min(FloorLog2(n), 2)
+        if (n <= 4) {
+#pragma GCC unroll 3
+            for (int i = 0; i < n - 1; i++) {
+                const int up = c[i] + ((32768 - c[i]) >> rate), dn = c[i] - (c[i] >> rate);
+                c[i] = (uint16_t)(i < val ? up : dn);
+            }
+        } else {
+            for (int i = 0; i < n - 1; i++) {
+                if (i < val) c[i] += (32768 - c[i]) >> rate;
+                else c[i] -= c[i] >> rate;
+            }
         }
-        c[n] = cnt_ + (cnt_ < 32);
+        c[n] = (uint16_t)(cnt_ + (cnt_ < 32));
     }
-    inline int bit() {   // read_bool / one bit of a literal: equiprobable, no adaptation
+    __attribute__((always_inline)) inline int bit() {   // read_bool / one bit of a literal: equiprobable, no adaptation
         const uint32_t r = rng;
         const uint32_t v = ((r >> 8) << 7) + 4;
         const uint64_t vw = (uint64_t)v << 48;

@@ -78,7 +78,7 @@ TileDecoder::TileDecoder(const SeqHdr& s, const HeaderParser& h, FrameWork& f, c
     }
     above_seg_pred.assign(fw.mi_cols + 64, 0);
     left_seg_pred.assign(fw.mi_rows + 64, 0);
-    memset(quant, 0, sizeof(quant));
+    memset(levels, 0, sizeof(levels));
 }
 
 void TileDecoder::clear_block_decoded_flags(int r, int c, int sb4) {
@@ -382,6 +382,7 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
     }
     b->ref_frame[0] = INTRA_FRAME;
     b->ref_frame[1] = -1;
+    ftype_cache[0] = ftype_cache[1] = -1;
     if (fh.frame_is_intra) intra_frame_mode_info();
     else inter_frame_mode_info();
     if (fail_code) return false;
@@ -772,7 +773,11 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
         if (have_above) rec.flags |= TXF_HAVE_ABOVE;
         if (have_ar) rec.flags |= TXF_HAVE_ABOVE_RIGHT;
         if (have_bl) rec.flags |= TXF_HAVE_BELOW_LEFT;
-        if (seq.enable_intra_edge_filter && filter_type(plane)) rec.flags |= TXF_SMOOTH_EDGE;
+        if (seq.enable_intra_edge_filter) {
+            int& ft = ftype_cache[plane > 0];
+            if (ft < 0) ft = filter_type(plane);
+            if (ft) rec.flags |= TXF_SMOOTH_EDGE;
+        }
         if (plane == 0) {
             if (b->use_filter_intra) {
                 rec.mode = TXM_FILTER_INTRA;
@@ -975,14 +980,22 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             }
         }
         if (eob > width * height) { fail(AV1R_EBITSTREAM, "eob exceeds transform size"); return 0; }
-        // levels, reverse scan (quant[] is all-zero on entry: touched positions are cleared on exit)
+        // levels, reverse scan.  lv[] is a zero-padded (stride = width + 4) byte map of min(level, 15): the
+        // neighbour sums of the context derivation never need a bounds check; touched entries are cleared on exit.
+        const int ls = width + 4;
+        uint8_t* lv = levels;
         static const int8_t sig_ref[3][5][2] = {{{0, 1}, {1, 0}, {1, 1}, {0, 2}, {2, 0}},
                                                 {{0, 1}, {1, 0}, {0, 2}, {0, 3}, {0, 4}},
                                                 {{0, 1}, {1, 0}, {2, 0}, {3, 0}, {4, 0}}};
-        static const int8_t mag_ref[3][3][2] = {{{0, 1}, {1, 0}, {1, 1}}, {{0, 1}, {1, 0}, {0, 2}}, {{0, 1}, {1, 0}, {2, 0}}};
+        int so[5], mo[3];
+        for (int i = 0; i < 5; i++) so[i] = sig_ref[cls][i][0] * ls + sig_ref[cls][i][1];
+        mo[0] = 1; mo[1] = ls; mo[2] = cls == TX_CLASS_2D ? ls + 1 : (cls == TX_CLASS_HORIZ ? 2 : 2 * ls);
+        uint16_t (*cb_cdf)[5] = cdf.coeff_base[tx_ctx][ptype];
+        uint16_t (*br_cdf)[5] = cdf.coeff_br[std::min(tx_ctx, 3)][ptype];
         for (int c = eob - 1; c >= 0; c--) {
             const int pos = scan[c];
             const int row = pos >> bwl, col = pos - (row << bwl);
+            uint8_t* lp = lv + row * ls + col;
             int level;
             if (c == eob - 1) {
                 int ectx;
@@ -992,46 +1005,41 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                 else ectx = 3;
                 level = ms.symbol(cdf.coeff_base_eob[tx_ctx][ptype][ectx], 3) + 1;
             } else {
-                int mag = 0;
-                for (int idx = 0; idx < 5; idx++) {
-                    const int rr = row + sig_ref[cls][idx][0], cc = col + sig_ref[cls][idx][1];
-                    if (rr < height && cc < width) mag += std::min(quant[(rr << bwl) + cc], 3);
-                }
+                int mag = std::min<int>(lp[so[0]], 3) + std::min<int>(lp[so[1]], 3) + std::min<int>(lp[so[2]], 3) + std::min<int>(lp[so[3]], 3) +
+                          std::min<int>(lp[so[4]], 3);
                 int bctx = std::min((mag + 1) >> 1, 4);
                 if (cls == TX_CLASS_2D) {
-                    if (row == 0 && col == 0) bctx = 0;
+                    if (pos == 0) bctx = 0;
                     else bctx += av1t_coeff_base_ctx_offset[txsz][std::min(row, 4)][std::min(col, 4)];
                 } else {
                     const int idx = cls == TX_CLASS_VERT ? row : col;
                     bctx += 26 + 5 * std::min(idx, 2);
                 }
-                level = ms.symbol(cdf.coeff_base[tx_ctx][ptype][bctx], 4);
+                level = ms.symbol(cb_cdf[bctx], 4);
             }
             if (level > 2) {
-                int mag = 0;
-                for (int idx = 0; idx < 3; idx++) {
-                    const int rr = row + mag_ref[cls][idx][0], cc = col + mag_ref[cls][idx][1];
-                    if (rr < height && cc < width) mag += std::min(quant[(rr << bwl) + cc], 15);
-                }
+                int mag = lp[mo[0]] + lp[mo[1]] + lp[mo[2]];
                 mag = std::min((mag + 1) >> 1, 6);
                 int rctx;
                 if (pos == 0) rctx = mag;
                 else if (cls == TX_CLASS_2D) rctx = (row < 2 && col < 2) ? mag + 7 : mag + 14;
                 else if (cls == TX_CLASS_HORIZ) rctx = col == 0 ? mag + 7 : mag + 14;
                 else rctx = row == 0 ? mag + 7 : mag + 14;
-                uint16_t* bc = cdf.coeff_br[std::min(tx_ctx, 3)][ptype][rctx];
+                uint16_t* bc = br_cdf[rctx];
                 for (int idx = 0; idx < 4; idx++) {
                     const int br = ms.symbol(bc, 4);
                     level += br;
                     if (br < 3) break;
                 }
             }
-            quant[pos] = level;
+            *lp = (uint8_t)level;
         }
         // signs + golomb, forward scan
         for (int c = 0; c < eob; c++) {
             const int pos = scan[c];
-            int level = quant[pos];
+            uint8_t* lp = lv + (pos >> bwl) * ls + (pos & (width - 1));
+            int level = *lp;
+            *lp = 0;
             if (!level) continue;
             int sign;
             if (c == 0) {
@@ -1058,7 +1066,11 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                 do {
                     length++;
                     bit = ms.literal(1);
-                    if (length > 32) { fail(AV1R_EBITSTREAM, "golomb too long"); return 0; }
+                    if (length > 32) {
+                        for (int cc = c; cc < eob; cc++) lv[(scan[cc] >> bwl) * ls + (scan[cc] & (width - 1))] = 0;
+                        fail(AV1R_EBITSTREAM, "golomb too long");
+                        return 0;
+                    }
                 } while (!bit);
                 int x = 1;
                 for (int i = length - 2; i >= 0; i--) x = (x << 1) + ms.literal(1);
@@ -1070,7 +1082,6 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             if (cul_level > 63) cul_level = 63;
             fw.coefs.push_back(coef_token(pos, sign ? -level : level));
         }
-        for (int c = 0; c < eob; c++) quant[scan[c]] = 0;
         fw.coef_tokens += eob;
     }
     for (int i = 0; i < w4; i++) {

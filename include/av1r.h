@@ -114,6 +114,9 @@ int av1r_verify_file(const char* path, const av1r_config* cfg, av1r_report* out)
  * receives 3 x uint64 plane digests per shown frame in display order (cap_frames entries). */
 int av1r_verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out,
                        uint64_t* digests, int64_t cap_frames);
+/* Same, on an engine that stays open between files (what the daemon's job loop wants: one av1r_open at start-up,
+ * one call per job; /root/reference/cmd/av1d/main.go:312-349).  Uses cfg.host_threads / streams of the ctx. */
+int av1r_ctx_verify_buffer(av1r_ctx* ctx, const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames);
 int av1r_probe_file(const char* path, av1r_stream_info* out);
 int av1r_probe_buffer(const uint8_t* data, size_t len, av1r_stream_info* out);
 
