@@ -102,9 +102,11 @@ static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, total;
+    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, lr[3], total;
     int n_recs, n_coefs, n_order, n_sbs, n_items;
 };
+
+static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
 
 struct DevWork {
     WorkLayout lay;
@@ -113,6 +115,7 @@ struct DevWork {
     int lf_on = 0, lf_plane_on[3] = {0, 0, 0}, cdef_on = 0, lr_on = 0;
     uint64_t coded_samples = 0, coef_tokens = 0;
     double parse_ms = 0;
+    int lr_rows[3] = {0, 0, 0}, lr_cols[3] = {0, 0, 0}, lr_has[3] = {0, 0, 0};
     std::vector<SbRowItem> items_host;
 };
 
@@ -195,6 +198,12 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     for (int p = 0; p < 3; p++) L.lf[p] = take(sizeof(LfEdge) * std::max<size_t>(1, fw.lf[p].size()));
     L.cdef_idx = take(std::max<size_t>(1, fw.cdef_idx.size()));
     L.skip_mi = take(std::max<size_t>(1, fw.skip_mi.size()));
+    for (int p = 0; p < 3; p++) {
+        L.lr[p] = take(sizeof(LrUnit) * std::max<size_t>(1, fw.lr[p].size()));
+        dw.lr_rows[p] = fw.lr_rows[p];
+        dw.lr_cols[p] = fw.lr_cols[p];
+        dw.lr_has[p] = !fw.lr[p].empty();
+    }
     L.total = o;
 }
 
@@ -212,6 +221,8 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
         if (!fw.lf[p].empty()) memcpy(h + L.lf[p], fw.lf[p].data(), sizeof(LfEdge) * fw.lf[p].size());
     if (!fw.cdef_idx.empty()) memcpy(h + L.cdef_idx, fw.cdef_idx.data(), fw.cdef_idx.size());
     if (!fw.skip_mi.empty()) memcpy(h + L.skip_mi, fw.skip_mi.data(), fw.skip_mi.size());
+    for (int p = 0; p < 3; p++)
+        if (!fw.lr[p].empty()) memcpy(h + L.lr[p], fw.lr[p].data(), sizeof(LrUnit) * fw.lr[p].size());
 }
 
 // Execution resources of one in-flight frame.
@@ -399,8 +410,24 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         cur = dst;
     }
     if (dw.lr_on && (cfg.inloop_filters & 4)) {
-        err = "loop restoration is not supported yet";
-        return AV1R_ENOSYS;
+        auto dst = get_frame(fp);
+        if (!dst) return AV1R_ENOMEM;
+        s.hold.push_back(dst);
+        LrLaunch ll;
+        ll.cdef = cur->pl;
+        ll.deblocked = recon->pl;
+        ll.dst = dst->pl;
+        for (int p = 0; p < 3; p++) {
+            ll.units[p] = (const LrUnitDev*)(d_arena + L.lr[p]);
+            ll.lr_type[p] = dw.lr_has[p] ? dw.fh.lr_type[p] : 0;
+            ll.unit_size[p] = dw.fh.lr_size[p];
+            ll.unit_rows[p] = dw.lr_rows[p];
+            ll.unit_cols[p] = dw.lr_cols[p];
+        }
+        ll.fp = fp;
+        CK(launch_lr(ll, st));
+        if (tm) tm->end(AV1R_ST_LR, 1, st);
+        cur = dst;
     }
     out_ref = cur;
     return 0;

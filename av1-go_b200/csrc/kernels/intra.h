@@ -50,6 +50,20 @@ struct CdefLaunch {
 };
 cudaError_t launch_cdef(const CdefLaunch& L, cudaStream_t s);
 
+enum { RESTORE_NONE_D = 0, RESTORE_WIENER_D = 1, RESTORE_SGRPROJ_D = 2 };
+struct LrUnitDev {             // same layout as the host LrUnit (frame_state.h)
+    uint8_t type, sgr_set;
+    int8_t wiener[2][3];
+    int8_t sgr_xqd[2];
+};
+struct LrLaunch {
+    DevPlanes cdef, deblocked, dst;
+    const LrUnitDev* units[3];  // device, [unit_rows][unit_cols]
+    int lr_type[3], unit_size[3], unit_rows[3], unit_cols[3];
+    DevFrameParams fp;
+};
+cudaError_t launch_lr(const LrLaunch& L, cudaStream_t s);
+
 cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s);
 
 }  // namespace av1r

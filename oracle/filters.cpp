@@ -230,6 +230,160 @@ void cdef_frame(const FrameWork& fw, const Frame& in, Frame& out) {
         }
 }
 
-void lr_frame(const FrameWork&, const Frame&, const Frame& cdef, Frame& out) { out = cdef; }
+// ------------------------------------------------------------------------------------ loop restoration
+// AV1 spec 7.17: 64-row stripes offset by 8 luma rows; rows outside the stripe come from the deblocked
+// (pre-CDEF) frame, at most 2 rows deep; Wiener 7-tap separable, self-guided with two box radii.
+#include "../av1-go_b200/csrc/tables/tables_filter.inc"
+
+struct LrCtx {
+    const Plane* cdef;
+    const Plane* deblocked;
+    int plane_end_x, plane_end_y, stripe_start, stripe_end;
+    int sample(int x, int y) const {
+        x = std::max(0, std::min(plane_end_x, x));
+        y = std::max(0, std::min(plane_end_y, y));
+        if (y < stripe_start) {
+            y = std::max(stripe_start - 2, y);
+            return deblocked->at(x, y);
+        }
+        if (y > stripe_end) {
+            y = std::min(stripe_end + 2, y);
+            return deblocked->at(x, y);
+        }
+        return cdef->at(x, y);
+    }
+};
+
+static void wiener_block(const LrCtx& c, const LrUnit& u, int bd, int x, int y, int w, int h, Plane& out) {
+    const int round0 = bd == 12 ? 5 : 3, round1 = bd == 12 ? 9 : 11;
+    int vf[7], hf[7];
+    auto get_filter = [](const int8_t* co, int* f) {
+        f[3] = 128;
+        for (int i = 0; i < 3; i++) {
+            f[i] = f[6 - i] = co[i];
+            f[3] -= 2 * co[i];
+        }
+    };
+    get_filter(u.wiener[0], vf);
+    get_filter(u.wiener[1], hf);
+    const int offset = 1 << (bd + 7 - round0 - 1);
+    const int limit = (1 << (bd + 1 + 7 - round0)) - 1;
+    std::vector<int> inter((size_t)(h + 6) * w);
+    for (int r = 0; r < h + 6; r++)
+        for (int cc = 0; cc < w; cc++) {
+            int s = 0;
+            for (int t = 0; t < 7; t++) s += hf[t] * c.sample(x + cc + t - 3, y + r - 3);
+            int v = round2(s, round0);
+            inter[(size_t)r * w + cc] = clip3(-offset, limit - offset, v);
+        }
+    const int pixmax = (1 << bd) - 1;
+    for (int r = 0; r < h; r++)
+        for (int cc = 0; cc < w; cc++) {
+            int s = 0;
+            for (int t = 0; t < 7; t++) s += vf[t] * inter[(size_t)(r + t) * w + cc];
+            out.at(x + cc, y + r) = (uint16_t)clip3(0, pixmax, round2(s, round1));
+        }
+}
+
+static void sgr_box(const LrCtx& c, int bd, int x, int y, int w, int h, int r, int s_param, int pass, std::vector<int>& F) {
+    const int n = (2 * r + 1) * (2 * r + 1);
+    const int one_by_n = ((1 << 12) + n / 2) / n;
+    std::vector<int> A((size_t)(h + 2) * (w + 2)), B((size_t)(h + 2) * (w + 2));
+    for (int i = -1; i <= h; i++)
+        for (int j = -1; j <= w; j++) {
+            uint32_t a = 0, b = 0;
+            for (int dy = -r; dy <= r; dy++)
+                for (int dx = -r; dx <= r; dx++) {
+                    const uint32_t v = (uint32_t)c.sample(x + j + dx, y + i + dy);
+                    a += v * v;
+                    b += v;
+                }
+            a = (uint32_t)round2((int)a, 2 * (bd - 8));
+            const uint32_t d = (uint32_t)round2((int)b, bd - 8);
+            const uint32_t p = a * n < d * d ? 0 : a * n - d * d;
+            const uint32_t z = (uint32_t)(((uint64_t)p * s_param + (1 << 19)) >> 20);
+            uint32_t a2;
+            if (z >= 255) a2 = 256;
+            else if (z == 0) a2 = 1;
+            else a2 = ((z << 8) + z / 2) / (z + 1);
+            const uint32_t b2 = (256 - a2) * b * one_by_n;
+            A[(size_t)(i + 1) * (w + 2) + j + 1] = (int)a2;
+            B[(size_t)(i + 1) * (w + 2) + j + 1] = (int)((b2 + (1 << 11)) >> 12);
+        }
+    F.assign((size_t)w * h, 0);
+    for (int i = 0; i < h; i++) {
+        int shift = 5;
+        if (pass == 0 && (i & 1)) shift = 4;
+        for (int j = 0; j < w; j++) {
+            int a = 0, b = 0;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int weight;
+                    if (pass == 0) {
+                        if ((i + dy) & 1) weight = dx == 0 ? 6 : 5;
+                        else weight = 0;
+                    } else {
+                        weight = (dx == 0 || dy == 0) ? 4 : 3;
+                    }
+                    a += weight * A[(size_t)(i + 1 + dy) * (w + 2) + j + 1 + dx];
+                    b += weight * B[(size_t)(i + 1 + dy) * (w + 2) + j + 1 + dx];
+                }
+            const int v = a * c.cdef->at(x + j, y + i) + b;
+            F[(size_t)i * w + j] = round2(v, 8 + shift - 4);
+        }
+    }
+}
+
+static void sgr_block(const LrCtx& c, const LrUnit& u, int bd, int x, int y, int w, int h, Plane& out) {
+    const int r0 = av1t_sgr_params[u.sgr_set][0], r1 = av1t_sgr_params[u.sgr_set][1];
+    const int s0 = av1t_sgr_params[u.sgr_set][2], s1 = av1t_sgr_params[u.sgr_set][3];
+    std::vector<int> f0, f1;
+    if (r0) sgr_box(c, bd, x, y, w, h, r0, s0, 0, f0);
+    if (r1) sgr_box(c, bd, x, y, w, h, r1, s1, 1, f1);
+    const int w0 = u.sgr_xqd[0], w1 = u.sgr_xqd[1], w2 = 128 - w0 - w1;
+    const int pixmax = (1 << bd) - 1;
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++) {
+            const int uu = c.cdef->at(x + j, y + i) << 4;
+            int v = w1 * uu;
+            v += w0 * (r0 ? f0[(size_t)i * w + j] : uu);
+            v += w2 * (r1 ? f1[(size_t)i * w + j] : uu);
+            out.at(x + j, y + i) = (uint16_t)clip3(0, pixmax, round2(v, 11));
+        }
+}
+
+void lr_frame(const FrameWork& fw, const Frame& deblocked, const Frame& cdef, Frame& out) {
+    const FrameGeom& g = cdef.g;
+    out = cdef;
+    for (int plane = 0; plane < (g.mono ? 1 : 3); plane++) {
+        if (fw.fh.lr_type[plane] == RESTORE_NONE) continue;
+        const int sx = plane ? g.subx : 0, sy = plane ? g.suby : 0;
+        const int unit_size = fw.fh.lr_size[plane];
+        const int pw = g.w[plane], ph = g.h[plane];
+        const int unit_rows = fw.lr_rows[plane], unit_cols = fw.lr_cols[plane];
+        if (fw.lr[plane].empty()) continue;
+        LrCtx c;
+        c.cdef = &cdef.p[plane];
+        c.deblocked = &deblocked.p[plane];
+        c.plane_end_x = pw - 1;
+        c.plane_end_y = ph - 1;
+        for (int stripe = 0;; stripe++) {
+            const int ls = -8 + stripe * 64;                 // luma stripe start
+            int ys = ls >> sy, ye = ys + (64 >> sy) - 1;      // plane rows [StripeStartY, StripeEndY]
+            if (std::max(ys, 0) > ph - 1) break;
+            c.stripe_start = ys;
+            c.stripe_end = ye;
+            const int y0 = std::max(ys, 0), y1 = std::min(ye, ph - 1);
+            // all rows of a stripe belong to one unit row: ((lumaY + 8) >> sy) / unitSize
+            const int unit_row = std::min(unit_rows - 1, ((std::max(ls, 0) + 8) >> sy) / unit_size);
+            for (int uc = 0; uc < unit_cols; uc++) {
+                const int x0 = uc * unit_size, x1 = uc == unit_cols - 1 ? pw - 1 : (uc + 1) * unit_size - 1;
+                const LrUnit& u = fw.lr[plane][(size_t)unit_row * unit_cols + uc];
+                if (u.type == RESTORE_WIENER) wiener_block(c, u, g.bd, x0, y0, x1 - x0 + 1, y1 - y0 + 1, out.p[plane]);
+                else if (u.type == RESTORE_SGRPROJ) sgr_block(c, u, g.bd, x0, y0, x1 - x0 + 1, y1 - y0 + 1, out.p[plane]);
+            }
+        }
+    }
+}
 
 }  // namespace orc

@@ -22,6 +22,8 @@ CASES = {
     "intra_10b_192x128": ("panzoom", 192, 128, 10, 2, {"cpu-used": "4", "cq-level": "24", "enable-restoration": "0"}, {14: 0, 48: 0}),
     "intra_8b_tiles_320x192": ("noise", 320, 192, 8, 2, {"cpu-used": "6", "cq-level": "12", "enable-restoration": "0", "tile-columns": "1", "tile-rows": "1"}, {14: 0, 48: 0}),
     "intra_8b_sb128_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "3", "cq-level": "45", "enable-restoration": "0", "sb-size": "128"}, {14: 0, 48: 0}),
+    "intra_8b_lr_480x272": ("panzoom", 480, 272, 8, 2, {"cpu-used": "1", "cq-level": "40", "enable-restoration": "1"}, {14: 0, 48: 0}),
+    "intra_8b_lr_tiles_616x376": ("panzoom", 616, 376, 8, 2, {"cpu-used": "3", "cq-level": "50", "enable-restoration": "1", "tile-columns": "1"}, {14: 0, 48: 0}),
     "intra_8b_grain_160x96": ("noise", 160, 96, 8, 2, {"cpu-used": "8", "cq-level": "30", "enable-restoration": "0", "film-grain-test": "7"}, {14: 0, 48: 0}),
 }
 
@@ -30,7 +32,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     index = {}
     for name, (src, w, h, bpc, n, opts, cfg) in CASES.items():
-        frames = list(sources.SOURCES[src](w, h, n, bpc=bpc, seed=len(name)))
+        frames = list(sources.SOURCES[src](w, h, n, bpc=bpc, seed=7 if "lr" in name else len(name)))
         tus = aomenc.encode(frames, w, h, bpc=bpc, opts=opts, cfg=cfg, threads=1)
         ref = dav1d_ref.decode(tus)
         aom = aomenc.decode(tus)

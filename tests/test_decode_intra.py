@@ -36,11 +36,11 @@ def test_oracle_matches_golden_md5(built, name):
         assert _md5(planes, meta["bpc"]) == meta["md5"][i], f"{name} frame {i}"
 
 
-@pytest.mark.parametrize("filters", [0, 1, 3])
+@pytest.mark.parametrize("filters", [0, 1, 3, 7])
 def test_oracle_stage_isolation_vs_dav1d(built, filters):
-    """inloop_filters = 0 (recon only), 1 (+deblock), 3 (+CDEF): oracle == dav1d at every stage."""
+    """inloop_filters = 0 (recon only), 1 (+deblock), 3 (+CDEF), 7 (+LR): oracle == dav1d at every stage."""
     from oracle import dav1d_ref, oracle_lib
-    for name in ("intra_8b_200x136", "intra_10b_192x128"):
+    for name in ("intra_8b_200x136", "intra_10b_192x128", "intra_8b_lr_480x272"):
         tus = _tus(name)
         ref = dav1d_ref.decode(tus, inloop_filters=filters, apply_grain=0)
         got, _ = oracle_lib.decode_stream(tus, inloop_filters=filters, apply_grain=0)
@@ -93,11 +93,11 @@ def test_cuda_matches_golden_md5(built, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("filters", [0, 1, 3])
+@pytest.mark.parametrize("filters", [0, 1, 3, 7])
 def test_cuda_stage_isolation(built, filters):
     """CUDA engine with inloop_filters masked, vs the oracle at the same stage (oracle == dav1d above)."""
     from oracle import oracle_lib
-    for name in ("intra_8b_200x136", "intra_10b_192x128", "intra_8b_sb128_264x200"):
+    for name in ("intra_8b_200x136", "intra_10b_192x128", "intra_8b_sb128_264x200", "intra_8b_lr_480x272"):
         ref, _ = oracle_lib.decode_stream(_tus(name), inloop_filters=filters, apply_grain=0)
         dec = _gpu_decode(name, inloop_filters=filters, apply_grain=0)
         assert len(dec.results) == len(ref)
