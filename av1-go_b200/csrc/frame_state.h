@@ -41,7 +41,23 @@ struct BlockInfo {
     uint8_t has_chroma;
     uint8_t num_mv_found, is_global_or_default;
     uint8_t lossless;
+    uint8_t warp_valid;        // LocalValid (motion_mode == WARPED_CAUSAL)
+    int32_t warp[6];           // LocalWarpParams
 };
+
+// Motion vector + reference saved per 8x8 for later frames (spec 7.19), and the projected field (7.9)
+struct SavedMv {
+    Mv mv;
+    int8_t ref;                // 0 = none
+};
+struct MfMv {
+    Mv mv;
+    int8_t ref_offset;         // 0 = invalid entry
+};
+
+enum { TOOL_INTER_BLOCKS, TOOL_COMPOUND_AVG, TOOL_COMPOUND_DIST, TOOL_COMPOUND_WEDGE, TOOL_COMPOUND_DIFFWTD, TOOL_INTERINTRA,
+       TOOL_INTERINTRA_WEDGE, TOOL_OBMC, TOOL_LOCAL_WARP, TOOL_GLOBAL_WARP, TOOL_SKIP_MODE, TOOL_DUAL_FILTER, TOOL_TEMPORAL_MV,
+       TOOL_INTRA_IN_INTER, TOOL_SUB8X8_CHROMA, TOOL_NEWMV, TOOL_VARTX_SPLIT, TOOL_SWITCHABLE_FILTER, TOOL_COUNT };
 
 inline void cdf_load_defaults(CdfCtx& c, int base_q_idx) {
     int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;
@@ -77,6 +93,18 @@ struct FrameWork {
     std::vector<uint8_t> skip_mi;       // per mi: block skip flag (CDEF 8x8 skip condition)
     std::vector<LrUnit> lr[3];
     int lr_cols[3] = {0, 0, 0}, lr_rows[3] = {0, 0, 0};
+    std::vector<InterBlk> inter;        // K2 work-list
+    std::vector<ObmcNb> obmc;
+    std::vector<WarpRec> warps;         // [0..7] global models per reference frame (slot 0 unused), then local ones
+    uint8_t gm_warp_valid[8] = {0};
+    // motion state: what this frame's parse reads from earlier frames and what it leaves for later ones
+    std::vector<uint8_t> prev_seg_ids;  // PrevSegmentIds (empty = all zero)
+    std::vector<MfMv> mfmv;             // projected motion field per 8x8 (empty = no temporal candidates)
+    std::vector<SavedMv> saved_mvs;     // per 8x8, filled at frame end
+    int saved_order_hints[8] = {0};
+    uint64_t inter_samples = 0, inter_ref_samples = 0;
+    // tool histogram (blocks): see TOOL_* below; reported by the bench so the exercised tool set is visible
+    uint32_t tool_hist[24] = {0};   // predicted samples / reference samples fetched (roofline model)
     // mode info (host only)
     std::deque<BlockInfo> blocks;
     std::vector<BlockInfo*> mi;         // per mi -> block
@@ -119,6 +147,9 @@ struct FrameWork {
         sbs.clear();
         pal.clear();
         blocks.clear();
+        inter.clear();
+        obmc.clear();
+        warps.clear();
     }
     int plane_w4(int p) const { int sx = p ? subx : 0; return (mi_cols + sx) >> sx; }
     int plane_h4(int p) const { int sy = p ? suby : 0; return (mi_rows + sy) >> sy; }

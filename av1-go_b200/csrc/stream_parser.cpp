@@ -1,6 +1,8 @@
 #include "stream_parser.h"
 
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstddef>
 
 #include "../../include/av1r.h"
@@ -79,11 +81,89 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
     }
     if (hp.seq.mono_chrome) return fail(AV1R_ENOSYS, "monochrome streams are not supported yet");
     if (fh.use_superres) return fail(AV1R_ENOSYS, "super-resolution is not supported yet");
-    if (fh.frame_width != hp.seq.max_frame_width || fh.frame_height != hp.seq.max_frame_height) {
-        // reference scaling is not implemented; intra frames of a different size would still work
-        if (!fh.frame_is_intra) return fail(AV1R_ENOSYS, "scaled reference frames are not supported yet");
+    if (!fh.frame_is_intra) {
+        for (int i = 0; i < REFS_PER_FRAME; i++) {
+            const RefHdrState& r = hp.refs[fh.ref_frame_idx[i]];
+            if (!r.valid) return fail(AV1R_EBITSTREAM, "inter frame references an empty slot");
+            if (r.upscaled_width != fh.upscaled_width || r.frame_height != fh.frame_height)
+                return fail(AV1R_ENOSYS, "scaled reference frames are not supported yet");
+        }
+        // global warp models of the 7 references (spec 7.11.3.6 validity)
+        cur_->warps.resize(8);
+        for (int ref = LAST_FRAME; ref <= ALTREF_FRAME; ref++) {
+            WarpRec& w = cur_->warps[ref];
+            memcpy(w.mat, fh.gm_params[ref], sizeof(w.mat));
+            int16_t sh[4] = {0, 0, 0, 0};
+            cur_->gm_warp_valid[ref] = (uint8_t)(fh.gm_type[ref] > GM_TRANSLATION ? setup_shear(w.mat, sh) : 0);
+            w.alpha = sh[0]; w.beta = sh[1]; w.gamma = sh[2]; w.delta = sh[3];
+        }
+        memset(&cur_->warps[0], 0, sizeof(WarpRec));
+        if (fh.use_ref_frame_mvs) motion_field_estimation();
+    }
+    // load_previous_segment_ids (spec 7.20)
+    if (fh.seg.enabled && fh.primary_ref_frame != PRIMARY_REF_NONE) {
+        const auto& prev = slot_fw_[fh.ref_frame_idx[fh.primary_ref_frame]];
+        if (prev && prev->mi_cols == fh.mi_cols && prev->mi_rows == fh.mi_rows) cur_->prev_seg_ids = prev->seg_ids;
     }
     return 0;
+}
+
+// spec 7.9: project the motion vectors saved with earlier frames onto the current frame (8x8 granularity)
+void StreamParser::motion_field_estimation() {
+    const FrameHdr& fh = cur_fh_;
+    FrameWork& fw = *cur_;
+    const int w8 = fh.mi_cols >> 1, h8 = fh.mi_rows >> 1;
+    fw.mfmv.assign((size_t)w8 * h8, MfMv{{0, 0}, 0});
+    static const int kDivMult[32] = {0,    16384, 8192, 5461, 4096, 3276, 2730, 2340, 2048, 1820, 1638, 1489, 1365, 1260, 1170, 1092,
+                                     1024, 963,   910,  862,  819,  780,  744,  712,  682,  655,  630,  606,  585,  564,  546,  528};
+    auto project = [&](int src, int dst_sign) -> int {
+        const int src_idx = fh.ref_frame_idx[src - LAST_FRAME];
+        const RefHdrState& r = hp.refs[src_idx];
+        const auto& sfw = slot_fw_[src_idx];
+        if (!sfw || r.mi_rows != fh.mi_rows || r.mi_cols != fh.mi_cols || r.frame_type == INTRA_ONLY_FRAME || r.frame_type == KEY_FRAME ||
+            sfw->saved_mvs.empty())
+            return 0;
+        const int ref_to_cur = hp.get_relative_dist(fh.order_hints[src], fh.order_hint);
+        for (int row8 = 0; row8 < h8; row8++)
+            for (int col8 = 0; col8 < w8; col8++) {
+                const SavedMv& sm = sfw->saved_mvs[(size_t)row8 * w8 + col8];
+                if (sm.ref <= INTRA_FRAME) continue;
+                const int ref_offset = hp.get_relative_dist(fh.order_hints[src], r.saved_order_hints[sm.ref]);
+                if (!(std::abs(ref_to_cur) <= 31 && std::abs(ref_offset) <= 31 && ref_offset > 0)) continue;
+                const int num = std::max(-31, std::min(31, ref_to_cur * dst_sign));
+                const int den = std::min(31, ref_offset);
+                int proj[2];
+                const int mvc[2] = {sm.mv.row, sm.mv.col};
+                for (int i = 0; i < 2; i++) {
+                    const int64_t v = (int64_t)mvc[i] * num * kDivMult[den];
+                    const int64_t sc = v >= 0 ? (v + 8192) >> 14 : -((-v + 8192) >> 14);
+                    proj[i] = (int)std::max<int64_t>(-(1 << 14) + 1, std::min<int64_t>((1 << 14) - 1, sc));
+                }
+                auto pos = [&](int v8, int delta, int max8, int max_off8, bool& ok) {
+                    const int base8 = (v8 >> 3) << 3;
+                    const int off8 = delta >= 0 ? (delta >> 6) : -((-delta) >> 6);
+                    v8 += dst_sign * off8;
+                    if (v8 < 0 || v8 >= max8 || v8 < base8 - max_off8 || v8 >= base8 + 8 + max_off8) ok = false;
+                    return v8;
+                };
+                bool ok = true;
+                const int py = pos(row8, proj[0], h8, 0, ok);
+                const int px = pos(col8, proj[1], w8, 8, ok);
+                if (!ok) continue;
+                MfMv& m = fw.mfmv[(size_t)py * w8 + px];
+                m.mv = sm.mv;
+                m.ref_offset = (int8_t)ref_offset;
+            }
+        return 1;
+    };
+    const int last_idx = fh.ref_frame_idx[0];
+    const int last_alt = hp.refs[last_idx].saved_order_hints[ALTREF_FRAME];
+    if (last_alt != fh.order_hints[GOLDEN_FRAME]) project(LAST_FRAME, -1);
+    int ref_stamp = 1;
+    if (hp.get_relative_dist(fh.order_hints[BWDREF_FRAME], fh.order_hint) > 0 && project(BWDREF_FRAME, 1)) ref_stamp--;
+    if (hp.get_relative_dist(fh.order_hints[ALTREF2_FRAME], fh.order_hint) > 0 && project(ALTREF2_FRAME, 1)) ref_stamp--;
+    if (hp.get_relative_dist(fh.order_hints[ALTREF_FRAME], fh.order_hint) > 0 && ref_stamp >= 0 && project(ALTREF_FRAME, 1)) ref_stamp--;
+    if (ref_stamp >= 0) project(LAST2_FRAME, -1);
 }
 
 int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset) {
@@ -122,6 +202,34 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
 int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
     auto t0 = std::chrono::steady_clock::now();
     build_loopfilter_edges(hp.seq, *cur_);
+    {
+        FrameWork& fw = *cur_;
+        // segment map kept for later frames (spec 7.4 decode frame wrapup)
+        if (cur_fh_.seg.enabled && !cur_fh_.seg.update_map) {
+            if (!fw.prev_seg_ids.empty()) fw.seg_ids = fw.prev_seg_ids;
+            else std::fill(fw.seg_ids.begin(), fw.seg_ids.end(), 0);
+        }
+        // motion field motion vector storage (spec 7.19)
+        for (int i = 0; i < 8; i++) fw.saved_order_hints[i] = cur_fh_.order_hints[i];
+        if (!cur_fh_.frame_is_intra) {
+            const int w8 = fw.mi_cols >> 1, h8 = fw.mi_rows >> 1;
+            fw.saved_mvs.assign((size_t)w8 * h8, SavedMv{{0, 0}, 0});
+            for (int row8 = 0; row8 < h8; row8++)
+                for (int col8 = 0; col8 < w8; col8++) {
+                    const BlockInfo* b = fw.mi[(size_t)(row8 * 2 + 1) * fw.mi_cols + col8 * 2 + 1];
+                    if (!b) continue;
+                    SavedMv& sm = fw.saved_mvs[(size_t)row8 * w8 + col8];
+                    for (int list = 0; list < 2; list++) {
+                        const int r = b->ref_frame[list];
+                        if (r <= INTRA_FRAME) continue;
+                        if (hp.get_relative_dist(cur_fh_.order_hints[r], cur_fh_.order_hint) >= 0) continue;
+                        if (std::abs(b->mv[list].row) > 4095 || std::abs(b->mv[list].col) > 4095) continue;
+                        sm.mv = b->mv[list];
+                        sm.ref = (int8_t)r;
+                    }
+                }
+        }
+    }
     cur_->parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     CdfCtx save = cur_init_cdf_;
     if (!cur_fh_.disable_frame_end_update_cdf && cur_->have_end_cdf) {

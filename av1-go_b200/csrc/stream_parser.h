@@ -38,6 +38,7 @@ private:
     bool have_frame_ = false;
     int fail(int code, const std::string& m) { err = m; return code; }
     int begin_frame(const FrameHdr& fh);
+    void motion_field_estimation();
     int tile_group(const uint8_t* payload, size_t size, size_t offset);
     int finish_frame(int64_t pts, std::vector<ParsedFrame>& out);
 };

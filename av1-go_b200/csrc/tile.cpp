@@ -403,6 +403,7 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
             sg[x] = b->segment_id;
         }
     }
+    if (b->is_inter) emit_inter_block();
     residual();
     return fail_code == 0;
 }
@@ -433,6 +434,10 @@ void TileDecoder::intra_frame_mode_info() {
     const int lctx = kIntraModeCtx[left_mode < INTRA_MODES ? left_mode : DC_PRED];
     b->y_mode = (uint8_t)ms.symbol(cdf.kf_y_mode[actx][lctx], 13);
     intra_angle_info_y();
+    intra_mode_tail();
+}
+
+void TileDecoder::intra_mode_tail() {
     if (b->has_chroma) {
         int cfl_allowed;
         if (b->lossless && plane_residual_size((BlockSize)b->bsize, seq.subsampling_x, seq.subsampling_y) == BLOCK_4X4) cfl_allowed = 1;
@@ -807,23 +812,8 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
     }
     rec.eob = (uint16_t)eob;
     rec.ntok = (uint16_t)(fw.coefs.size() - rec.coef_off);
-    if (!b->is_inter || eob > 0) {
-        // records are grouped by 64x64 luma unit (decode order visits each unit contiguously)
-        const int ux = (start_x << sx) >> 6, uy = (start_y << sy) >> 6;
-        const int key = (uy << 16) | ux;
-        if (key != cur_unit) {
-            cur_unit = key;
-            SbRange sr = cur_sb;
-            sr.first = (uint32_t)fw.tx.size();
-            sr.count = 0;
-            sr.ux = (uint16_t)ux;
-            sr.uy = (uint16_t)uy;
-            fw.sbs.push_back(sr);
-        }
-        fw.sbs.back().count++;
-        fw.tx.push_back(rec);
-        fw.tx_blocks++;
-    }
+    if (b->is_inter && b->interintra) rec.flags |= TXF_II;
+    if (!b->is_inter || eob > 0) push_record(rec, (start_x << sx) >> 6, (start_y << sy) >> 6);
     if (eob > 0) fw.coded_samples += (uint64_t)kTxW[txsz] * kTxH[txsz];
     // LoopfilterTxSizes + BlockDecoded
     const int pw4 = fw.plane_w4(plane), ph4 = fw.plane_h4(plane);
@@ -834,6 +824,54 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
             const int by = (sub_row >> sy) + i + 1, bx = (sub_col >> sx) + j + 1;
             if (by < 35 && bx < 35) block_decoded[plane][by][bx] = 1;
         }
+}
+
+// records are grouped by 64x64 luma unit (decode order visits each unit contiguously)
+void TileDecoder::push_record(const TxRec& rec, int ux, int uy) {
+    const int key = (uy << 16) | ux;
+    if (key != cur_unit) {
+        cur_unit = key;
+        SbRange sr = cur_sb;
+        sr.first = (uint32_t)fw.tx.size();
+        sr.count = 0;
+        sr.ux = (uint16_t)ux;
+        sr.uy = (uint16_t)uy;
+        fw.sbs.push_back(sr);
+    }
+    fw.sbs.back().count++;
+    fw.tx.push_back(rec);
+    fw.tx_blocks++;
+}
+
+// inter-intra (spec 7.11.3.1 / compute_prediction): one record per plane asks the wavefront kernel to form the intra
+// predictor of the whole block from reconstructed neighbours and blend it over the inter predictor
+void TileDecoder::emit_interintra_records() {
+    static const uint8_t ii_to_intra[4] = {DC_PRED, V_PRED, H_PRED, SMOOTH_PRED};
+    const int sb_mask = seq.use_128x128_superblock ? 31 : 15;
+    const int sub_row = mi_row & sb_mask, sub_col = mi_col & sb_mask;
+    for (int plane = 0; plane < 1 + 2 * b->has_chroma; plane++) {
+        const int sx = plane ? seq.subsampling_x : 0, sy = plane ? seq.subsampling_y : 0;
+        const int psz = plane_residual_size((BlockSize)b->bsize, sx, sy);
+        const int n4w = kBlockW4[psz], n4h = kBlockH4[psz];
+        int txsz = TX_4X4;
+        for (int t = 0; t < TX_SIZES_ALL; t++)
+            if (kTxW[t] == n4w * 4 && kTxH[t] == n4h * 4) txsz = t;
+        TxRec rec;
+        memset(&rec, 0, sizeof(rec));
+        rec.x4 = (uint16_t)(mi_col >> sx);
+        rec.y4 = (uint16_t)(mi_row >> sy);
+        rec.plane = (uint8_t)plane;
+        rec.txsz = (uint8_t)txsz;
+        rec.mode = ii_to_intra[b->interintra_mode];
+        rec.flags = TXF_II;
+        if (plane == 0 ? avail_l : avail_l_chroma) rec.flags |= TXF_HAVE_LEFT;
+        if (plane == 0 ? avail_u : avail_u_chroma) rec.flags |= TXF_HAVE_ABOVE;
+        if (block_decoded[plane][(sub_row >> sy) - 1 + 1][(sub_col >> sx) + n4w + 1]) rec.flags |= TXF_HAVE_ABOVE_RIGHT;
+        if (block_decoded[plane][(sub_row >> sy) + n4h + 1][(sub_col >> sx) - 1 + 1]) rec.flags |= TXF_HAVE_BELOW_LEFT;
+        rec.cfl_alpha = ii_pack(b->wedge_interintra, b->wedge_index, b->interintra_mode, b->bsize);
+        rec.coef_off = (uint32_t)fw.coefs.size();
+        push_record(rec, (mi_col * 4) >> 6, (mi_row * 4) >> 6);
+    }
 }
 
 int TileDecoder::get_tx_set(int txsz) const {

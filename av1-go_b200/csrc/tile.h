@@ -81,10 +81,65 @@ private:
     void read_transform_type(int x4, int y4, int txsz);
     int compute_tx_type(int plane, int txsz, int block_x, int block_y) const;
     int filter_type(int plane) const;
+    void push_record(const TxRec& rec, int ux, int uy);
+    void intra_mode_tail();   // uv mode, palette, filter-intra: shared by intra frames and intra blocks of inter frames
     // inter (tile_inter.cpp)
     void inter_frame_mode_info();
     void read_var_tx_size(int row, int col, int txsz, int depth);
     void transform_tree(int start_x, int start_y, int w, int h);
+    void inter_segment_id(int pre_skip);
+    void read_skip_mode();
+    void read_is_inter();
+    void intra_block_mode_info();
+    void inter_block_mode_info();
+    void read_ref_frames();
+    int count_refs(int frame_type) const;
+    int seg_feature_active(int f) const { return fh.seg.enabled && fh.seg.feature_enabled[b->segment_id][f]; }
+    void assign_mv(int is_compound);
+    void read_mv(int list);
+    int read_mv_component(int comp);
+    void read_interintra_mode(int is_compound);
+    void read_motion_mode(int is_compound);
+    void read_compound_type(int is_compound);
+    int has_overlappable_candidates() const;
+    void find_warp_samples();
+    void add_warp_sample(int delta_row, int delta_col);
+    void warp_estimation();
+    // motion vector prediction (spec 7.10.2)
+    void find_mv_stack(int is_compound);
+    void setup_global_mv(int list);
+    void lower_mv_precision(Mv& mv) const;
+    void scan_row(int delta_row, int is_compound);
+    void scan_col(int delta_col, int is_compound);
+    void scan_point(int delta_row, int delta_col, int is_compound);
+    void add_ref_mv_candidate(int r, int c, int is_compound, int weight);
+    void temporal_scan(int is_compound);
+    void add_tpl_ref_mv(int delta_row, int delta_col, int is_compound);
+    void sort_stack(int start, int end);
+    void extra_search(int is_compound);
+    void add_extra_mv_candidate(int r, int c, int is_compound);
+    void context_and_clamping(int is_compound, int num_new);
+    void emit_inter_block();
+    void emit_interintra_records();
+
+    // neighbour context of the current block (spec 5.11.7: AboveRefFrame, LeftIntra ...)
+    int above_ref[2] = {0, -1}, left_ref[2] = {0, -1};
+    int above_intra = 1, left_intra = 1, above_single = 1, left_single = 1;
+    // mv stack
+    int num_mv_found = 0, new_mv_count = 0, found_match = 0, close_matches = 0, total_matches = 0;
+    int zero_mv_ctx = 0, new_mv_ctx = 0, ref_mv_ctx = 0, ref_mv_idx = 0;
+    Mv ref_stack[12][2];
+    int weight_stack[12];
+    Mv global_mvs[2];
+    int ref_id_count[2], ref_diff_count[2];
+    Mv ref_id_mvs[2][2], ref_diff_mvs[2][2];
+    // warp samples
+    int num_samples = 0, num_samples_scanned = 0;
+    int cand_list[8][4];
+    std::vector<uint8_t> above_seg_pred_ctx_unused;
 };
+
+// spec 7.11.3.6: shear parameters of a warp model; returns warpValid
+int setup_shear(const int32_t* mat, int16_t out[4]);
 
 }  // namespace av1r

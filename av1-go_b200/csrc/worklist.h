@@ -29,6 +29,46 @@ struct TxRec {
 };
 static_assert(sizeof(TxRec) == 32, "TxRec must stay 32 bytes");
 
+// ---- inter prediction work-lists (K2) -------------------------------------------------------------
+// One record per prediction rectangle: normally one per inter block (all planes); the chroma of a group of
+// sub-8x8 luma blocks is predicted from each block's own motion, so such groups add chroma-only records.
+struct InterBlk {
+    uint16_t x, y;          // luma sample position of the rectangle
+    uint8_t w, h;           // luma size (4..128)
+    uint8_t planes;         // bit 0 luma, bit 1 chroma
+    uint8_t bsize;          // MiSize of the block (wedge mask geometry)
+    int8_t ref[2];          // reference *slot* (ref_frame_idx[refFrame - LAST_FRAME]); ref[1] = -1: single prediction
+    uint8_t filt[2];        // interp_filter[0] (vertical), interp_filter[1] (horizontal)
+    int16_t mv[2][2];       // [list][row, col] in 1/8 luma sample
+    int16_t warp[2];        // index into the WarpRec list per list (-1: translational)
+    uint8_t comp_type;      // COMPOUND_WEDGE / DIFFWTD / AVERAGE / INTRA / DISTANCE
+    uint8_t wedge_index, wedge_sign, mask_type;
+    uint8_t fwd_w, bck_w;   // distance weights (COMPOUND_DISTANCE)
+    uint8_t interintra;     // 1: K2 leaves the clipped inter predictor, the wavefront kernel blends the intra part
+    uint8_t obmc_above, obmc_left;   // neighbour counts in the ObmcNb list
+    uint8_t obmc_chroma_above;       // chroma plane is >= 8x8: the above pass applies to chroma too
+    uint16_t pad;
+    uint32_t obmc_first;
+};
+static_assert(sizeof(InterBlk) == 40, "InterBlk must stay 40 bytes");
+
+// One overlapped-motion neighbour (spec 7.11.3.10): predict the overlap area with the neighbour's motion and blend.
+struct ObmcNb {
+    uint16_t x4, y4;        // luma mi position where the overlap area starts
+    uint8_t step4;          // neighbour extent along the edge, in mi units (clipped 2..16)
+    int8_t ref;             // reference slot
+    uint8_t filt[2];
+    int16_t mv[2];
+};
+static_assert(sizeof(ObmcNb) == 12, "ObmcNb must stay 12 bytes");
+
+// Warp model (global or local) with its shear decomposition (spec 7.11.3.6).
+struct WarpRec {
+    int32_t mat[6];
+    int16_t alpha, beta, gamma, delta;
+};
+static_assert(sizeof(WarpRec) == 32, "WarpRec must stay 32 bytes");
+
 enum : uint8_t {
     TXM_CFL = 13,           // DC_PRED followed by chroma-from-luma
     TXM_PALETTE = 14,
@@ -40,7 +80,14 @@ enum : uint8_t {
     TXF_SMOOTH_EDGE = 16,   // get_filter_type(): a neighbour uses a smooth predictor
     TXF_LOSSLESS = 32,
     TXF_SB_FIRST = 64,      // first record of a superblock (wavefront bookkeeping)
+    TXF_II = 128,           // inter-intra: (with an intra mode) blend the intra predictor of the whole block over the inter
+                            // predictor already in the frame, cfl_alpha = ii_pack(); (with TXM_INTER) residual of such a block
 };
+// inter-intra parameters packed into TxRec::cfl_alpha: bit 0 wedge_interintra, bits 1..4 wedge_index, bits 5..6 interintra_mode,
+// bits 7..11 MiSize
+static inline int16_t ii_pack(int wedge, int wedge_index, int ii_mode, int bsize) {
+    return (int16_t)(wedge | (wedge_index << 1) | (ii_mode << 5) | (bsize << 7));
+}
 
 // coefficient token: bits 0..9 position (row * min(txw,32) + col), bits 10..31 signed level
 static inline uint32_t coef_token(int pos, int level) { return ((uint32_t)level << 10) | (uint32_t)pos; }

@@ -35,7 +35,7 @@ struct Frame {
     Plane p[3];
 };
 
-void reconstruct_frame(const av1r::FrameWork& fw, Frame& f);
+void reconstruct_frame(const av1r::FrameWork& fw, Frame& f, const Frame* const refs[8]);
 void deblock_frame(const av1r::FrameWork& fw, Frame& f);
 void cdef_frame(const av1r::FrameWork& fw, const Frame& in, Frame& out);
 void lr_frame(const av1r::FrameWork& fw, const Frame& deblocked, const Frame& cdef, Frame& out);

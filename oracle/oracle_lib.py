@@ -35,6 +35,12 @@ def film_grain(fg_params, planes, bpc, subx=1, suby=1, mono=0, mc_identity=0):
     return dst
 
 
+TOOL_NAMES = ["inter_blocks", "compound_avg", "compound_dist", "compound_wedge", "compound_diffwtd", "interintra", "interintra_wedge",
+              "obmc", "local_warp", "global_warp", "skip_mode", "dual_filter", "temporal_mv", "intra_in_inter", "sub8x8_chroma", "newmv",
+              "vartx_split", "switchable_filter"]
+LAST_TOOL_HIST = {}
+
+
 def decode_stream(tus, inloop_filters=7, apply_grain=1):
     """Whole-stream CPU decode (product host parser + scalar oracle reconstruction).
     Returns (frames, info) with frames = list of [Y,U,V] uint16 arrays."""
@@ -55,6 +61,11 @@ def decode_stream(tus, inloop_filters=7, apply_grain=1):
             if rc < 0:
                 raise RuntimeError(f"oracle decode failed at TU {i}: rc={rc} {l.orc_stream_error(h).decode()}")
         n = l.orc_stream_num_frames(h)
+        hist = (C.c_uint64 * 24)()
+        l.orc_stream_tool_hist.argtypes = [C.c_void_p, C.c_void_p]
+        l.orc_stream_tool_hist(h, hist)
+        global LAST_TOOL_HIST
+        LAST_TOOL_HIST = dict(zip(TOOL_NAMES, list(hist)))
         frames, info = [], []
         for i in range(n):
             w, hh, bd = C.c_int(), C.c_int(), C.c_int()

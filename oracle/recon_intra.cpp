@@ -323,8 +323,12 @@ static void dequant_block(const FrameWork& fw, const FrameGeom& g, const TxRec& 
     }
 }
 
-void reconstruct_frame(const FrameWork& fw, Frame& f) {
+void predict_inter_frame(const FrameWork& fw, Frame& f, const Frame* const refs[8]);
+void interintra_blend(Frame& f, const TxRec& r, const int* intra);
+
+void reconstruct_frame(const FrameWork& fw, Frame& f, const Frame* const refs[8]) {
     const FrameGeom& g = f.g;
+    if (!fw.inter.empty()) predict_inter_frame(fw, f, refs);
     static thread_local int pred[64 * 64];
     static thread_local int32_t coef[32 * 32], res[64 * 64];
     const int pixmax = (1 << g.bd) - 1;
@@ -334,6 +338,11 @@ void reconstruct_frame(const FrameWork& fw, Frame& f) {
         const int w = kTxW[r.txsz], h = kTxH[r.txsz];
         const int x = r.x4 * 4, y = r.y4 * 4;
         const int xe = std::min(x + w, g.cw[r.plane]), ye = std::min(y + h, g.ch[r.plane]);
+        if (r.mode != TXM_INTER && (r.flags & TXF_II)) {
+            predict_intra_block(pl, g, r, r.plane, pred);
+            interintra_blend(f, r, pred);
+            continue;
+        }
         if (r.mode != TXM_INTER) {
             predict_intra_block(pl, g, r, r.plane, pred);
             if (r.mode == TXM_CFL) cfl_apply(f.p[0], g, r, pred);

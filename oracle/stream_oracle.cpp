@@ -32,6 +32,7 @@ struct Stream {
     FilmGrainParams slot_fg[8];
     std::vector<OutFrame> out;
     std::string err;
+    uint64_t tool_hist[24] = {0};
 };
 
 static std::shared_ptr<Frame> make_frame(const SeqHdr& seq, const FrameHdr& fh) {
@@ -122,8 +123,11 @@ extern "C" int orc_stream_decode(void* h, const uint8_t* tu, size_t len) {
             continue;
         }
         const FrameWork& fw = *pf.fw;
+        for (int i = 0; i < 24; i++) s->tool_hist[i] += fw.tool_hist[i];
         auto rec = make_frame(s->sp.hp.seq, pf.fh);
-        reconstruct_frame(fw, *rec);
+        const Frame* refs[8];
+        for (int i = 0; i < 8; i++) refs[i] = s->slots[i].get();
+        reconstruct_frame(fw, *rec, refs);
         std::shared_ptr<Frame> cur = rec;
         const bool do_db = (s->inloop_filters & 1) && (pf.fh.lf.level[0] || pf.fh.lf.level[1]);
         if (do_db) deblock_frame(fw, *cur);
@@ -168,3 +172,5 @@ extern "C" int orc_stream_frame_copy(void* h, int idx, int plane, uint16_t* dst,
         memcpy(dst + (size_t)y * dst_stride, &f.p[plane].d[(size_t)y * f.p[plane].stride], sizeof(uint16_t) * f.g.w[plane]);
     return 0;
 }
+
+extern "C" void orc_stream_tool_hist(void* h, uint64_t* out24) { memcpy(out24, ((Stream*)h)->tool_hist, sizeof(uint64_t) * 24); }
