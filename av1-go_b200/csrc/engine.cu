@@ -21,6 +21,7 @@
 #include "../../include/av1r_stages.h"
 #include "demux.h"
 #include "engine.h"
+#include "kernels/inter.h"
 #include "kernels/intra.h"
 #include "md5.h"
 #include "stream_parser.h"
@@ -77,7 +78,11 @@ struct DevFrameBuf {
     DevPlanes pl;
     int cw[3], ch[3], bps;
     size_t bytes = 0;
-    ~DevFrameBuf() { if (base) cudaFree(base); }
+    cudaEvent_t ready = nullptr;   // recorded when the frame's last kernel has been queued; readers on other streams wait on it
+    ~DevFrameBuf() {
+        if (base) cudaFree(base);
+        if (ready) cudaEventDestroy(ready);
+    }
 };
 
 static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::string& err) {
@@ -97,13 +102,17 @@ static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::s
     }
     for (int p = 0; p < 3; p++) f->pl.p[p] = f->base + off[p];
     f->bytes = total;
+    if (cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess) {
+        err = "cudaEventCreate(frame) failed";
+        return nullptr;
+    }
     return f;
 }
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, lr[3], total;
-    int n_recs, n_coefs, n_order, n_sbs, n_items;
+    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, total;
+    int n_recs, n_coefs, n_order, n_sbs, n_items, n_inter, n_obmc, n_warps;
 };
 
 static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
@@ -204,6 +213,12 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
         dw.lr_cols[p] = fw.lr_cols[p];
         dw.lr_has[p] = !fw.lr[p].empty();
     }
+    L.n_inter = (int)fw.inter.size();
+    L.n_obmc = (int)fw.obmc.size();
+    L.n_warps = (int)fw.warps.size();
+    L.inter = take(sizeof(InterBlk) * std::max(1, L.n_inter));
+    L.obmc = take(sizeof(ObmcNb) * std::max(1, L.n_obmc));
+    L.warps = take(sizeof(WarpRec) * std::max(1, L.n_warps));
     L.total = o;
 }
 
@@ -223,6 +238,9 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
     if (!fw.skip_mi.empty()) memcpy(h + L.skip_mi, fw.skip_mi.data(), fw.skip_mi.size());
     for (int p = 0; p < 3; p++)
         if (!fw.lr[p].empty()) memcpy(h + L.lr[p], fw.lr[p].data(), sizeof(LrUnit) * fw.lr[p].size());
+    if (L.n_inter) memcpy(h + L.inter, fw.inter.data(), sizeof(InterBlk) * L.n_inter);
+    if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
+    if (L.n_warps) memcpy(h + L.warps, fw.warps.data(), sizeof(WarpRec) * L.n_warps);
 }
 
 // Execution resources of one in-flight frame.
@@ -308,6 +326,7 @@ struct EngineImpl {
     RefState* rs = &main_refs;
     std::vector<std::shared_ptr<DevFrameBuf>> kept;   // keep_frames handles
     std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
+    DevBuf wedge_master;                              // 6 x 64 x 64 wedge master masks (inter-intra blends in K3)
     int64_t frames_decoded = 0;
 
     int wait_slot(FrameSlot& s);
@@ -370,10 +389,40 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     ifr.frame = recon->pl;
     ifr.res = res;
     ifr.fp = fp;
+    ifr.inter_frame = L.n_inter > 0;
+    ifr.wedge_master = wedge_master.p;
     CK(cudaMemcpyAsync((void*)(d_arena + L.iframe), &ifr, sizeof(ifr), cudaMemcpyHostToDevice, st));
     if (tm) tm->begin(st);
     CK(launch_itx(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, L.n_order > 0, st);
+    if (L.n_inter > 0) {
+        InterLaunch xl;
+        xl.blks = (const InterBlk*)(d_arena + L.inter);
+        xl.obmc = (const ObmcNb*)(d_arena + L.obmc);
+        xl.warps = (const WarpRec*)(d_arena + L.warps);
+        xl.n = L.n_inter;
+        memset(xl.refs, 0, sizeof(xl.refs));
+        for (int i = 0; i < REFS_PER_FRAME; i++) {
+            const int slot = dw.fh.ref_frame_idx[i];
+            auto& rf = rs->refs[slot];
+            if (!rf) { err = "inter frame references an empty slot"; return AV1R_EBITSTREAM; }
+            if (rf->cw[0] != fp.cw[0] || rf->ch[0] != fp.ch[0] || rf->bps != (fp.bd == 8 ? 1 : 2)) {
+                err = "reference frame geometry differs from the current frame";
+                return AV1R_ENOSYS;
+            }
+            if (!xl.refs[slot].p[0]) {
+                xl.refs[slot] = rf->pl;
+                s.hold.push_back(rf);
+                CK(cudaStreamWaitEvent(st, rf->ready, 0));   // produced on another stream
+            }
+        }
+        xl.cur = recon->pl;
+        xl.fp = fp;
+        CK(launch_inter(xl, st));
+        if (tm) tm->end(AV1R_ST_INTER, 1, st);
+        CK(launch_inter_residual(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
+        if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
+    }
     IntraLaunch il;
     il.frames = (const IntraFrame*)(d_arena + L.iframe);
     il.items = (const SbRowItem*)(d_arena + L.items);
@@ -429,6 +478,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         if (tm) tm->end(AV1R_ST_LR, 1, st);
         cur = dst;
     }
+    CK(cudaEventRecord(cur->ready, st));
     out_ref = cur;
     return 0;
 }
@@ -438,6 +488,7 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
     cudaStream_t st = s->stream;
     std::shared_ptr<DevFrameBuf> shown = frame;
     s->hold.push_back(frame);
+    if (existing) CK(cudaStreamWaitEvent(st, frame->ready, 0));
     if (tm) tm->begin(st);
     if (cfg.apply_grain && fg.apply_grain) {
         auto disp = get_frame(fp);
@@ -656,6 +707,9 @@ int Engine::open(const av1r_config& cfg) {
         CK(cudaEventCreate(&s->ev1));
         E.slots.push_back(std::move(s));
     }
+    CK(E.wedge_master.ensure(6 * 64 * 64));
+    CK(inter_copy_wedge_master(E.wedge_master.p, E.streams[0]));
+    CK(cudaStreamSynchronize(E.streams[0]));
     E.opened = true;
     return 0;
 }

@@ -1,0 +1,347 @@
+// K2 -- inter prediction (AV1 spec 7.11.3): one CTA per prediction rectangle of the host's InterBlk list.
+//
+//   translation : separable 8-tap sub-pel filter (regular / smooth / sharp / bilinear, 4-tap variants for
+//                 dimensions <= 4), reference coordinates clamped to the visible reference frame, intermediate
+//                 rounding InterRound0 = 3, InterRound1 = 11 (single) / 7 (compound)              (7.11.3.3/4)
+//   warp        : local (least-squares) or global affine model, 8x8 sub-blocks, 193x8 filter table   (7.11.3.5)
+//   compound    : average, distance weights, wedge mask, difference-weighted mask (luma mask reused by chroma)
+//                                                                                        (7.11.3.11/12/14/15)
+//   OBMC        : blend with predictions formed from the above / left neighbours' motion             (7.11.3.10)
+// Inter-intra blocks get their (clipped) inter predictor here; the intra part is blended by the wavefront kernel
+// (K3), which is the only stage that may read reconstructed neighbours.  Every block is independent of every
+// other block of the frame (it reads reference frames only), so the whole frame is one launch.
+// The block is processed in 32x32 tiles so that the working set (two int32 predictions + the 39x32 intermediate)
+// stays in 13 KB of shared memory whatever the block size; reference samples come through the read-only path
+// (L1/L2 hits: neighbouring blocks share most of their 8-tap support).
+// Algorithmic bytes: Rbar * F_inter read + F_inter written.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "../av1_consts.h"
+#include "dev_common.cuh"
+#include "devframe.h"
+#include "inter.h"
+#include "../tables/tables_inter.inc"
+
+namespace av1r {
+
+__constant__ int16_t c_subpel[6][16][8];
+__constant__ uint8_t c_wedge_codebook[3][16][3];
+__constant__ uint8_t c_wedge_signflip[BLOCK_SIZES_ALL][16];
+__constant__ uint8_t c_blk_w[BLOCK_SIZES_ALL];
+__constant__ uint8_t c_blk_h[BLOCK_SIZES_ALL];
+__device__ int16_t d_warped_filter[193][8];
+__device__ uint8_t d_obmc_mask[7][64];
+__device__ uint8_t d_wedge_master[6][64][64];
+static bool g_inter_const_loaded[64] = {false};
+
+static constexpr int IT = 32;                 // tile edge
+static constexpr int INTER_THREADS = 128;
+
+__device__ __forceinline__ int wedge_mask_d(int bsize, int flip, int wedge, int i, int j) {
+    const int w = c_blk_w[bsize], h = c_blk_h[bsize];
+    const uint8_t* cb = c_wedge_codebook[h > w ? 0 : (h < w ? 1 : 2)][wedge];
+    const int dir = cb[0], xoff = 32 - ((cb[1] * w) >> 3), yoff = 32 - ((cb[2] * h) >> 3);
+    const int m = d_wedge_master[dir][yoff + i][xoff + j];
+    return (flip ^ c_wedge_signflip[bsize][wedge]) ? 64 - m : m;
+}
+
+__device__ __forceinline__ int filter_index_d(int type, int len) {
+    if (len <= 4) {
+        if (type == 0 || type == 2) return 4;
+        if (type == 1) return 5;
+    }
+    return type;
+}
+
+struct InterSmem {
+    int32_t pred[2][IT * IT];
+    int32_t mid[(IT + 7) * IT];
+    uint8_t mask[128 * 128];
+};
+
+template <typename T>
+__device__ __forceinline__ int ld_ref(const uint8_t* base, uint32_t pitch, int x, int y) {
+    return (int)__ldg((const T*)(base + (size_t)y * pitch) + x);
+}
+
+// translational prediction of a tw x th tile whose top-left plane sample is (x0, y0); (fx, fy) = 1/16 phases,
+// (ix, iy) = integer reference position of the tile's top-left sample.
+template <typename T>
+__device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, int fx, int fy, int fidx_h, int fidx_v,
+                             int tw, int th, int round1, int32_t* mid, int32_t* out) {
+    const int16_t* fh = c_subpel[fidx_h][fx];
+    const int16_t* fv = c_subpel[fidx_v][fy];
+    const int n1 = (th + 7) * tw;
+    for (int idx = threadIdx.x; idx < n1; idx += INTER_THREADS) {
+        const int r = idx / tw, c = idx - r * tw;
+        const int yy = min(max(iy + r - 3, 0), lasty);
+        int s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) s += fh[t] * ld_ref<T>(ref, pitch, min(max(ix + c + t - 3, 0), lastx), yy);
+        mid[r * IT + c] = (s + 4) >> 3;
+    }
+    __syncthreads();
+    const int n2 = th * tw;
+    const int rnd = 1 << (round1 - 1);
+    for (int idx = threadIdx.x; idx < n2; idx += INTER_THREADS) {
+        const int r = idx / tw, c = idx - r * tw;
+        int s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) s += fv[t] * mid[(r + t) * IT + c];
+        out[r * IT + c] = (s + rnd) >> round1;
+    }
+    __syncthreads();
+}
+
+// warped prediction of a tile (multiples of 8): one warp per 8x8 sub-block
+template <typename T>
+__device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw, int th,
+                          int round1, int32_t* mid, int32_t* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* wm = mid + warp * 128;
+    const int nbx = tw >> 3, nb = nbx * (th >> 3);
+    const int rnd = 1 << (round1 - 1);
+    for (int b = warp; b < nb; b += INTER_THREADS / 32) {
+        const int i8 = b / nbx, j8 = b - i8 * nbx;
+        const int src_x = (x0 + j8 * 8 + 4) << sx, src_y = (y0 + i8 * 8 + 4) << sy;
+        const long long dst_x = (long long)wr.mat[2] * src_x + (long long)wr.mat[3] * src_y + wr.mat[0];
+        const long long dst_y = (long long)wr.mat[4] * src_x + (long long)wr.mat[5] * src_y + wr.mat[1];
+        const long long x4 = dst_x >> sx, y4 = dst_y >> sy;
+        const int ix4 = (int)(x4 >> 16), sx4 = (int)(x4 & 0xFFFF), iy4 = (int)(y4 >> 16), sy4 = (int)(y4 & 0xFFFF);
+        for (int idx = lane; idx < 15 * 8; idx += 32) {
+            const int i1 = (idx >> 3) - 7, i2 = (idx & 7) - 4;
+            const int sxx = sx4 + wr.alpha * i2 + wr.beta * i1;
+            const int offs = ((sxx + 512) >> 10) + 64;
+            const int yy = min(max(iy4 + i1, 0), lasty);
+            int s = 0;
+#pragma unroll
+            for (int i3 = 0; i3 < 8; i3++) s += d_warped_filter[offs][i3] * ld_ref<T>(ref, pitch, min(max(ix4 + i2 - 3 + i3, 0), lastx), yy);
+            wm[idx] = (s + 4) >> 3;
+        }
+        __syncwarp();
+        for (int idx = lane; idx < 64; idx += 32) {
+            const int i1 = (idx >> 3) - 4, i2 = (idx & 7) - 4;
+            const int syy = sy4 + wr.gamma * i2 + wr.delta * i1;
+            const int offs = ((syy + 512) >> 10) + 64;
+            int s = 0;
+#pragma unroll
+            for (int i3 = 0; i3 < 8; i3++) s += d_warped_filter[offs][i3] * wm[(i1 + i3 + 4) * 8 + i2 + 4];
+            out[(i8 * 8 + i1 + 4) * IT + j8 * 8 + i2 + 4] = (s + rnd) >> round1;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(INTER_THREADS) inter_pred_kernel(InterLaunch L) {
+    __shared__ InterSmem sm;
+    const InterBlk r = L.blks[blockIdx.x];
+    const DevFrameParams& fp = L.fp;
+    const int pixmax = (1 << fp.bd) - 1;
+    const int is_compound = r.ref[1] >= 0;
+    const int round1 = is_compound ? 7 : 11, post = 11 - round1;
+    for (int plane = 0; plane < 3; plane++) {
+        if (plane == 0 && !(r.planes & 1)) continue;
+        if (plane > 0 && !(r.planes & 2)) continue;
+        const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
+        const int px = r.x >> sx, py = r.y >> sy, pw = r.w >> sx, ph = r.h >> sy;
+        const int lastx = fp.w[plane] - 1, lasty = fp.h[plane] - 1;
+        T* cur = (T*)L.cur.p[plane];
+        const int cpe = L.cur.pitch[plane] / sizeof(T);
+        for (int ty = 0; ty < ph; ty += IT)
+            for (int tx = 0; tx < pw; tx += IT) {
+                const int tw = min(IT, pw - tx), th = min(IT, ph - ty);
+                for (int l = 0; l < 1 + is_compound; l++) {
+                    const DevPlanes& rf = L.refs[r.ref[l]];
+                    if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) {
+                        warp_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm.mid,
+                                     sm.pred[l]);
+                    } else {
+                        const int posx = ((px + tx) << 4) + ((2 * r.mv[l][1]) >> sx), posy = ((py + ty) << 4) + ((2 * r.mv[l][0]) >> sy);
+                        predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
+                                        filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tw, th, round1, sm.mid, sm.pred[l]);
+                    }
+                }
+                for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
+                    const int i = idx / tw, j = idx - i * tw;
+                    const int gx = px + tx + j, gy = py + ty + i;
+                    const int a = sm.pred[0][i * IT + j];
+                    int v;
+                    if (!is_compound) {
+                        v = a;
+                    } else {
+                        const int b = sm.pred[1][i * IT + j];
+                        if (r.comp_type == COMPOUND_WEDGE || r.comp_type == COMPOUND_DIFFWTD) {
+                            const int bi = ty + i, bj = tx + j;
+                            int m;
+                            if (r.comp_type == COMPOUND_DIFFWTD) {
+                                if (plane == 0) {
+                                    int diff = abs(a - b);
+                                    diff = d_round2(diff, (fp.bd - 8) + post);
+                                    m = min(max(38 + diff / 16, 0), 64);
+                                    if (r.mask_type) m = 64 - m;
+                                    sm.mask[bi * 128 + bj] = (uint8_t)m;
+                                } else if (sx && sy) {
+                                    m = (sm.mask[2 * bi * 128 + 2 * bj] + sm.mask[2 * bi * 128 + 2 * bj + 1] + sm.mask[(2 * bi + 1) * 128 + 2 * bj] +
+                                         sm.mask[(2 * bi + 1) * 128 + 2 * bj + 1] + 2) >> 2;
+                                } else if (sx) {
+                                    m = (sm.mask[bi * 128 + 2 * bj] + sm.mask[bi * 128 + 2 * bj + 1] + 1) >> 1;
+                                } else {
+                                    m = sm.mask[bi * 128 + bj];
+                                }
+                            } else {
+                                if (!sx && !sy) m = wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, bi, bj);
+                                else if (sx && !sy)
+                                    m = (wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, bi, 2 * bj) +
+                                         wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, bi, 2 * bj + 1) + 1) >> 1;
+                                else
+                                    m = (wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, 2 * bi, 2 * bj) +
+                                         wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, 2 * bi, 2 * bj + 1) +
+                                         wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, 2 * bi + 1, 2 * bj) +
+                                         wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, 2 * bi + 1, 2 * bj + 1) + 2) >> 2;
+                            }
+                            v = d_round2(m * a + (64 - m) * b, 6 + post);
+                        } else if (r.comp_type == COMPOUND_DISTANCE) {
+                            v = d_round2(a * r.fwd_w + b * r.bck_w, 4 + post);
+                        } else {
+                            v = d_round2(a + b, 1 + post);
+                        }
+                    }
+                    if (gx < fp.cw[plane] && gy < fp.ch[plane]) cur[(size_t)gy * cpe + gx] = (T)min(max(v, 0), pixmax);
+                }
+                __syncthreads();
+            }
+        // ---- overlapped motion compensation: blend with the neighbours' predictions, above pass then left pass
+        const int n_nb = r.obmc_above + r.obmc_left;
+        for (int k = 0; k < n_nb; k++) {
+            const int above = k < r.obmc_above;
+            if (above && plane > 0 && !r.obmc_chroma_above) continue;
+            const ObmcNb nb = L.obmc[r.obmc_first + k];
+            int ow, oh;
+            if (above) {
+                ow = min(pw, (nb.step4 * 4) >> sx);
+                oh = min(ph >> 1, 32 >> sy);
+            } else {
+                ow = min(pw >> 1, 32 >> sx);
+                oh = min(ph, (nb.step4 * 4) >> sy);
+            }
+            const int ox = (nb.x4 * 4) >> sx, oy = (nb.y4 * 4) >> sy;
+            const DevPlanes& rf = L.refs[nb.ref];
+            const uint8_t* m = d_obmc_mask[31 - __clz(above ? oh : ow)];
+            for (int ty = 0; ty < oh; ty += IT)
+                for (int tx = 0; tx < ow; tx += IT) {
+                    const int tw = min(IT, ow - tx), th = min(IT, oh - ty);
+                    const int posx = ((ox + tx) << 4) + ((2 * nb.mv[1]) >> sx), posy = ((oy + ty) << 4) + ((2 * nb.mv[0]) >> sy);
+                    predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
+                                    filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm.mid, sm.pred[0]);
+                    for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
+                        const int i = idx / tw, j = idx - i * tw;
+                        const int gx = ox + tx + j, gy = oy + ty + i;
+                        if (gx >= fp.cw[plane] || gy >= fp.ch[plane]) continue;
+                        const int o = min(max(sm.pred[0][i * IT + j], 0), pixmax);
+                        const int mm = above ? m[ty + i] : m[tx + j];
+                        T* p = cur + (size_t)gy * cpe + gx;
+                        *p = (T)((mm * (int)*p + (64 - mm) * o + 32) >> 6);
+                    }
+                    __syncthreads();
+                }
+        }
+    }
+}
+
+// residual of plain inter transform blocks: frame += residual (records with mode TXM_INTER that are not part of an
+// inter-intra block; those wait for the blend in K3).  One warp per record.
+template <typename T>
+__global__ void __launch_bounds__(128) inter_residual_kernel(const TxRec* recs, const uint32_t* order, int n, DevPlanes cur, DevResidual res,
+                                                             DevFrameParams fp) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n) return;
+    const TxRec r = recs[order[wid]];
+    if (r.mode != TXM_INTER || (r.flags & TXF_II)) return;
+    static const uint8_t kW[TX_SIZES_ALL] = {2, 3, 4, 5, 6, 2, 3, 3, 4, 4, 5, 5, 6, 2, 4, 3, 5, 4, 6};
+    static const uint8_t kH[TX_SIZES_ALL] = {2, 3, 4, 5, 6, 3, 2, 4, 3, 5, 4, 6, 5, 4, 2, 5, 3, 6, 4};
+    const int plane = r.plane, lw = kW[r.txsz], w = 1 << lw, h = 1 << kH[r.txsz];
+    const int x = r.x4 * 4, y = r.y4 * 4;
+    const int xe = min(w, fp.cw[plane] - x), ye = min(h, fp.ch[plane] - y);
+    const int pixmax = (1 << fp.bd) - 1;
+    T* out = (T*)(cur.p[plane] + (size_t)y * cur.pitch[plane]) + x;
+    const int ope = cur.pitch[plane] / sizeof(T);
+    const int16_t* rp = (const int16_t*)((const uint8_t*)res.p[plane] + (size_t)y * res.pitch[plane]) + x;
+    const int rpe = res.pitch[plane] >> 1;
+    for (int idx = lane; idx < w * h; idx += 32) {
+        const int i = idx >> lw, j = idx & (w - 1);
+        if (i < ye && j < xe) {
+            const int v = (int)out[i * ope + j] + (int)rp[i * rpe + j];
+            out[i * ope + j] = (T)min(max(v, 0), pixmax);
+        }
+    }
+}
+
+static cudaError_t inter_upload_constants() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && g_inter_const_loaded[dev]) return cudaSuccess;
+    if ((e = cudaMemcpyToSymbol(c_subpel, av1t_subpel_filters, sizeof(av1t_subpel_filters))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_wedge_codebook, av1t_wedge_codebook, sizeof(av1t_wedge_codebook))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_wedge_signflip, av1t_wedge_signflip, sizeof(av1t_wedge_signflip))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_blk_w, kBlockW, sizeof(kBlockW))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_blk_h, kBlockH, sizeof(kBlockH))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(d_warped_filter, av1t_warped_filter, sizeof(av1t_warped_filter))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(d_obmc_mask, av1t_obmc_mask, sizeof(av1t_obmc_mask))) != cudaSuccess) return e;
+    // wedge master masks (spec 7.11.3.11)
+    static uint8_t master[6][64][64];
+    enum { WH = 0, WV = 1, W27 = 2, W63 = 3, W117 = 4, W153 = 5 };
+    for (int j = 0; j < 64; j++) {
+        int shift = 16;
+        for (int i = 0; i < 64; i += 2) {
+            master[W63][i][j] = av1t_wedge_master_oblique_even[std::min(std::max(j - shift, 0), 63)];
+            shift--;
+            master[W63][i + 1][j] = av1t_wedge_master_oblique_odd[std::min(std::max(j - shift, 0), 63)];
+            master[WV][i][j] = master[WV][i + 1][j] = av1t_wedge_master_vertical[j];
+        }
+    }
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 64; j++) {
+            const int msk = master[W63][i][j];
+            master[W27][j][i] = (uint8_t)msk;
+            master[W117][i][63 - j] = (uint8_t)(64 - msk);
+            master[W153][63 - j][i] = (uint8_t)(64 - msk);
+            master[WH][j][i] = master[WV][i][j];
+        }
+    if ((e = cudaMemcpyToSymbol(d_wedge_master, master, sizeof(master))) != cudaSuccess) return e;
+    if (dev < 64) g_inter_const_loaded[dev] = true;
+    return cudaSuccess;
+}
+
+cudaError_t inter_copy_wedge_master(uint8_t* dst_dev, cudaStream_t s) {
+    cudaError_t e = inter_upload_constants();
+    if (e != cudaSuccess) return e;
+    void* src = nullptr;
+    if ((e = cudaGetSymbolAddress(&src, d_wedge_master)) != cudaSuccess) return e;
+    return cudaMemcpyAsync(dst_dev, src, 6 * 64 * 64, cudaMemcpyDeviceToDevice, s);
+}
+
+cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
+    if (L.n <= 0) return cudaSuccess;
+    cudaError_t e = inter_upload_constants();
+    if (e != cudaSuccess) return e;
+    if (L.fp.bd == 8) inter_pred_kernel<uint8_t><<<L.n, INTER_THREADS, 0, s>>>(L);
+    else inter_pred_kernel<uint16_t><<<L.n, INTER_THREADS, 0, s>>>(L);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inter_residual(const TxRec* recs, const uint32_t* order, int n, const DevPlanes& cur, const DevResidual& res,
+                                  const DevFrameParams& fp, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int blocks = (n + 3) / 4;
+    if (fp.bd == 8) inter_residual_kernel<uint8_t><<<blocks, 128, 0, s>>>(recs, order, n, cur, res, fp);
+    else inter_residual_kernel<uint16_t><<<blocks, 128, 0, s>>>(recs, order, n, cur, res, fp);
+    return cudaGetLastError();
+}
+
+}  // namespace av1r

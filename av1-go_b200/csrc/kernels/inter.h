@@ -1,0 +1,26 @@
+// Launch descriptors of the inter prediction kernels (K2).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "devframe.h"
+
+namespace av1r {
+
+struct InterLaunch {
+    const InterBlk* blks;      // device, n records
+    const ObmcNb* obmc;        // device
+    const WarpRec* warps;      // device
+    int n;
+    DevPlanes refs[8];         // reference slots (same geometry as the current frame: scaled references are rejected by the host)
+    DevPlanes cur;             // frame being reconstructed
+    DevFrameParams fp;
+};
+
+cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s);
+// frame += residual for the plain inter transform blocks (order = indices of records with eob > 0)
+cudaError_t launch_inter_residual(const TxRec* recs, const uint32_t* order, int n, const DevPlanes& cur, const DevResidual& res,
+                                  const DevFrameParams& fp, cudaStream_t s);
+// wedge master masks (6 x 64 x 64 bytes) for kernels outside inter.cu
+cudaError_t inter_copy_wedge_master(uint8_t* dst_dev, cudaStream_t s);
+
+}  // namespace av1r

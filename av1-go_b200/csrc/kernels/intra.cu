@@ -21,6 +21,7 @@
 #include "devframe.h"
 #include "intra.h"
 #include "../tables/tables_pred.inc"
+#include "../tables/tables_inter.inc"
 
 namespace av1r {
 
@@ -29,6 +30,11 @@ __constant__ uint8_t c_sm_weights[124];
 __constant__ int8_t c_fi_taps[5][8][8];
 __constant__ uint8_t c_itxw_log2[TX_SIZES_ALL];
 __constant__ uint8_t c_itxh_log2[TX_SIZES_ALL];
+__constant__ uint8_t c_ii_weights[128];
+__constant__ uint8_t c_ii_codebook[3][16][3];
+__constant__ uint8_t c_ii_signflip[BLOCK_SIZES_ALL][16];
+__constant__ uint8_t c_ii_blk_w[BLOCK_SIZES_ALL];
+__constant__ uint8_t c_ii_blk_h[BLOCK_SIZES_ALL];
 static bool g_intra_const_loaded[64] = {false};
 
 static constexpr int INTRA_WARPS = 4;
@@ -120,9 +126,34 @@ __device__ __forceinline__ void edge_upsample_d(const int32_t* src, int32_t* dst
     if (lane == 0) dst[-2] = src[-1];
 }
 
+// inter-intra blend weight of sample (i, j) of a w x h plane block (spec 7.11.3.13 / wedge 7.11.3.11)
+__device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int j, int w, int h, int sx, int sy) {
+    const int wedge = pk & 1, wedge_index = (pk >> 1) & 15, ii_mode = (pk >> 5) & 3, bsize = (pk >> 7) & 31;
+    if (wedge) {
+        const int bw = c_ii_blk_w[bsize], bh = c_ii_blk_h[bsize];
+        const uint8_t* cb = c_ii_codebook[bh > bw ? 0 : (bh < bw ? 1 : 2)][wedge_index];
+        const int xoff = 32 - ((cb[1] * bw) >> 3), yoff = 32 - ((cb[2] * bh) >> 3);
+        const uint8_t* mm = master + cb[0] * 4096;
+        const int flip = c_ii_signflip[bsize][wedge_index];
+        int acc = 0;
+        for (int dy = 0; dy <= sy; dy++)
+            for (int dx = 0; dx <= sx; dx++) {
+                const int m = __ldg(mm + (yoff + (i << sy) + dy) * 64 + xoff + (j << sx) + dx);
+                acc += flip ? 64 - m : m;
+            }
+        const int sh = sx + sy;
+        return sh ? (acc + (1 << (sh - 1))) >> sh : acc;
+    }
+    const int scale = 128 / max(w, h);
+    if (ii_mode == II_V_PRED) return c_ii_weights[i * scale];
+    if (ii_mode == II_H_PRED) return c_ii_weights[j * scale];
+    if (ii_mode == II_SMOOTH_PRED) return c_ii_weights[min(i, j) * scale];
+    return 32;
+}
+
 template <typename T>
 __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
-                            const UnitView<T>& uv, int lane) {
+                            const UnitView<T>& uv, int lane, const uint8_t* wedge_master) {
     const int plane = r.plane;
     const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
     const int w = 1 << lw, h = 1 << lh;
@@ -138,19 +169,27 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
     const int16_t* rp = (const int16_t*)((const uint8_t*)res.p[plane] + (size_t)y * res.pitch[plane]) + x;
     const int rpitch = res.pitch[plane] >> 1;
     const bool has_res = r.eob > 0;
+    const bool ii = (r.flags & TXF_II) != 0;
+    const int ii_pk = (uint16_t)r.cfl_alpha;
+    const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
     auto emit = [&](int i, int j, int v) {
         if (i < ye && j < xe) {
+            if (ii) {   // blend the intra predictor over the inter predictor already in the unit
+                const int m = ii_mask(ii_pk, wedge_master, i, j, w, h, psx, psy);
+                v = (m * v + (64 - m) * (int)tl[i * tpitch + j] + 32) >> 6;
+            }
             if (has_res) v = min(max(v + (int)__ldg(rp + i * rpitch + j), 0), pixmax);
             out[i * opitch + j] = (T)v;
             tl[i * tpitch + j] = (T)v;
         }
     };
-    if (r.mode == TXM_INTER) {   // residual on top of the inter predictor
-        if (has_res)
+    if (r.mode == TXM_INTER) {
+        // plain inter residuals were added by the K2 residual kernel; only inter-intra blocks wait for their blend
+        if (has_res && ii)
             for (int idx = lane; idx < w * h; idx += 32) {
                 const int i = idx >> lw, j = idx & (w - 1);
                 if (i < ye && j < xe) {
-                    int v = (int)__ldcg(out + i * opitch + j) + (int)__ldg(rp + i * rpitch + j);
+                    int v = (int)tl[i * tpitch + j] + (int)__ldg(rp + i * rpitch + j);
                     v = min(max(v, 0), pixmax);
                     out[i * opitch + j] = (T)v;
                     tl[i * tpitch + j] = (T)v;
@@ -459,11 +498,19 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(Intra
                         const int y = min(uy0 + i, max_y);
                         uv.left[pl][i] = __ldcg(base + (size_t)y * pe + ux0 - 1);
                     }
+                if (F.inter_frame) {
+                    // inter-predicted (and residual-added) samples of this unit were produced by K2: bring them on chip
+                    const int tw = uv.tw[pl], th = uv.th[pl];
+                    for (int i = lane; i < tw * th; i += 32) {
+                        const int yy = i / tw, xx = i - yy * tw;
+                        uv.tile[pl][i] = __ldcg(base + (size_t)min(uy0 + yy, max_y) * pe + min(ux0 + xx, max_x));
+                    }
+                }
             }
             __syncwarp();
             for (uint32_t t = 0; t < un.count; t++) {
                 const TxRec r = F.recs[un.first + t];
-                intra_block<T>(r, F.frame, F.res, fp, sm, uv, lane);
+                intra_block<T>(r, F.frame, F.res, fp, sm, uv, lane, F.wedge_master);
                 __syncwarp();
             }
             const bool last_of_sb = (k + 1 == it.n_units) || (F.sbs[it.first_unit + k + 1].sb_col != un.sb_col);
@@ -491,6 +538,11 @@ static cudaError_t intra_upload_constants() {
     if ((e = cudaMemcpyToSymbol(c_fi_taps, av1t_filter_intra_taps, sizeof(av1t_filter_intra_taps))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_itxw_log2, kTxWLog2, sizeof(kTxWLog2))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_itxh_log2, kTxHLog2, sizeof(kTxHLog2))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_ii_weights, av1t_ii_weights1d, sizeof(av1t_ii_weights1d))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_ii_codebook, av1t_wedge_codebook, sizeof(av1t_wedge_codebook))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_ii_signflip, av1t_wedge_signflip, sizeof(av1t_wedge_signflip))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_ii_blk_w, kBlockW, sizeof(kBlockW))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_ii_blk_h, kBlockH, sizeof(kBlockH))) != cudaSuccess) return e;
     if (dev < 64) g_intra_const_loaded[dev] = true;
     return cudaSuccess;
 }

@@ -12,6 +12,8 @@ struct IntraFrame {            // one per frame in the batch (device array)
     DevPlanes frame;
     DevResidual res;
     DevFrameParams fp;
+    int inter_frame;               // 1: units start from the K2 output (inter predictor + residual) instead of nothing
+    const uint8_t* wedge_master;   // device, 6 x 64 x 64 (inter-intra wedge blends)
 };
 
 struct SbRowItem {             // one (tile, superblock row): the work item a warp owns

@@ -27,11 +27,32 @@ CASES = {
     "intra_8b_grain_160x96": ("noise", 160, 96, 8, 2, {"cpu-used": "8", "cq-level": "30", "enable-restoration": "0", "film-grain-test": "7"}, {14: 0, 48: 0}),
 }
 
+# inter streams (index_inter.json): cfg[14] = lag_in_frames, cfg[48] = kf_max_dist.  The low cpu-used cases make libaom use
+# every inter tool (see the tool histogram printed by tools/dbg_inter.py): compound average / distance / wedge / diff-weighted,
+# inter-intra (smooth + wedge), OBMC, local + global warp, skip mode, dual filters, temporal MVs, sub-8x8 chroma, var-tx.
+INTER_CASES = {
+    "inter_8b_base_192x128": ("panzoom", 192, 128, 8, 8, {"cpu-used": "6", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "0",
+                                                         "enable-obmc": "0", "enable-warped-motion": "0", "enable-global-motion": "0"}, {14: 0, 48: 9999}),
+    "inter_8b_alltools_352x288": ("panzoom", 352, 288, 8, 12, {"cpu-used": "2", "cq-level": "32"}, {14: 10, 48: 9999}),
+    "inter_10b_alltools_208x144": ("panzoom", 208, 144, 10, 12, {"cpu-used": "0", "cq-level": "32"}, {14: 10, 48: 9999}),
+    "inter_8b_sb128_tiles_640x360": ("panzoom", 640, 360, 8, 10, {"cpu-used": "5", "cq-level": "40", "sb-size": "128", "tile-columns": "1", "tile-rows": "1"},
+                                     {14: 9, 48: 6}),
+    "inter_10b_grain_208x144": ("noise", 208, 144, 10, 8, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "3"}, {14: 6, 48: 9999}),
+}
+
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "inter"):
+        build(INTER_CASES, "index_inter.json")
+    if which in ("all", "intra"):
+        build(CASES, "index.json")
+
+
+def build(cases, index_name):
     index = {}
-    for name, (src, w, h, bpc, n, opts, cfg) in CASES.items():
+    for name, (src, w, h, bpc, n, opts, cfg) in cases.items():
         frames = list(sources.SOURCES[src](w, h, n, bpc=bpc, seed=7 if "lr" in name else len(name)))
         tus = aomenc.encode(frames, w, h, bpc=bpc, opts=opts, cfg=cfg, threads=1)
         ref = dav1d_ref.decode(tus)
@@ -45,7 +66,7 @@ def main():
         obuio.write_ivf(os.path.join(OUT, name + ".ivf"), tus, w, h)
         index[name] = dict(w=w, h=h, bpc=bpc, frames=n, md5=md5, bytes=sum(len(t) for t in tus))
         print(name, index[name]["bytes"], "bytes")
-    json.dump(index, open(os.path.join(OUT, "index.json"), "w"), indent=1)
+    json.dump(index, open(os.path.join(OUT, index_name), "w"), indent=1)
 
 
 if __name__ == "__main__":
