@@ -111,7 +111,7 @@ static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, total;
+    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, total;
     int n_recs, n_coefs, n_order, n_sbs, n_items, n_inter, n_obmc, n_warps;
 };
 
@@ -219,6 +219,7 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     L.inter = take(sizeof(InterBlk) * std::max(1, L.n_inter));
     L.obmc = take(sizeof(ObmcNb) * std::max(1, L.n_obmc));
     L.warps = take(sizeof(WarpRec) * std::max(1, L.n_warps));
+    L.pal = take(std::max<size_t>(4, fw.pal.size()));
     L.total = o;
 }
 
@@ -241,6 +242,7 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
     if (L.n_inter) memcpy(h + L.inter, fw.inter.data(), sizeof(InterBlk) * L.n_inter);
     if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
     if (L.n_warps) memcpy(h + L.warps, fw.warps.data(), sizeof(WarpRec) * L.n_warps);
+    if (!fw.pal.empty()) memcpy(h + L.pal, fw.pal.data(), fw.pal.size());
 }
 
 // Execution resources of one in-flight frame.
@@ -391,6 +393,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     ifr.fp = fp;
     ifr.inter_frame = L.n_inter > 0;
     ifr.wedge_master = wedge_master.p;
+    ifr.pal = d_arena + L.pal;
     CK(cudaMemcpyAsync((void*)(d_arena + L.iframe), &ifr, sizeof(ifr), cudaMemcpyHostToDevice, st));
     if (tm) tm->begin(st);
     CK(launch_itx(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));

@@ -57,7 +57,7 @@ struct MfMv {
 
 enum { TOOL_INTER_BLOCKS, TOOL_COMPOUND_AVG, TOOL_COMPOUND_DIST, TOOL_COMPOUND_WEDGE, TOOL_COMPOUND_DIFFWTD, TOOL_INTERINTRA,
        TOOL_INTERINTRA_WEDGE, TOOL_OBMC, TOOL_LOCAL_WARP, TOOL_GLOBAL_WARP, TOOL_SKIP_MODE, TOOL_DUAL_FILTER, TOOL_TEMPORAL_MV,
-       TOOL_INTRA_IN_INTER, TOOL_SUB8X8_CHROMA, TOOL_NEWMV, TOOL_VARTX_SPLIT, TOOL_SWITCHABLE_FILTER, TOOL_COUNT };
+       TOOL_INTRA_IN_INTER, TOOL_SUB8X8_CHROMA, TOOL_NEWMV, TOOL_VARTX_SPLIT, TOOL_SWITCHABLE_FILTER, TOOL_PALETTE, TOOL_INTRABC, TOOL_COUNT };
 
 inline void cdf_load_defaults(CdfCtx& c, int base_q_idx) {
     int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;

@@ -153,7 +153,7 @@ __device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int
 
 template <typename T>
 __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
-                            const UnitView<T>& uv, int lane, const uint8_t* wedge_master) {
+                            const UnitView<T>& uv, int lane, const uint8_t* wedge_master, const uint8_t* pal) {
     const int plane = r.plane;
     const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
     const int w = 1 << lw, h = 1 << lh;
@@ -195,6 +195,17 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
                     tl[i * tpitch + j] = (T)v;
                 }
             }
+        return;
+    }
+    if (r.mode == TXM_PALETTE) {   // spec 7.11.4; entry layout documented at TileDecoder::palette_tokens
+        const uint8_t* e = pal + r.pal_off;
+        const uint16_t* hdr = reinterpret_cast<const uint16_t*>(e);
+        const uint8_t* map = e + 24;
+        const int ox = hdr[8], oy = hdr[9], stride = hdr[10];
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int i = idx >> lw, j = idx & (w - 1);
+            emit(i, j, (int)hdr[map[(size_t)(y - oy + i) * stride + (x - ox + j)]]);
+        }
         return;
     }
     const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(Intra
             __syncwarp();
             for (uint32_t t = 0; t < un.count; t++) {
                 const TxRec r = F.recs[un.first + t];
-                intra_block<T>(r, F.frame, F.res, fp, sm, uv, lane, F.wedge_master);
+                intra_block<T>(r, F.frame, F.res, fp, sm, uv, lane, F.wedge_master, F.pal);
                 __syncwarp();
             }
             const bool last_of_sb = (k + 1 == it.n_units) || (F.sbs[it.first_unit + k + 1].sb_col != un.sb_col);

@@ -14,6 +14,7 @@ struct IntraFrame {            // one per frame in the batch (device array)
     DevFrameParams fp;
     int inter_frame;               // 1: units start from the K2 output (inter predictor + residual) instead of nothing
     const uint8_t* wedge_master;   // device, 6 x 64 x 64 (inter-intra wedge blends)
+    const uint8_t* pal;            // device, palette entries (colours + colour index maps)
 };
 
 struct SbRowItem {             // one (tile, superblock row): the work item a warp owns

@@ -386,7 +386,10 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
     if (fh.frame_is_intra) intra_frame_mode_info();
     else inter_frame_mode_info();
     if (fail_code) return false;
-    if (b->pal_size[0] || b->pal_size[1]) return fail(AV1R_ENOSYS, "palette blocks are not supported yet");
+    if (b->pal_size[0] || b->pal_size[1]) {
+        fw.tool_hist[TOOL_PALETTE]++;
+        palette_tokens();
+    }
     read_block_tx_size();
     if (b->skip) reset_block_context();
     b->qidx = (uint8_t)get_qidx(fh, 0, b->segment_id, current_q_index);
@@ -449,26 +452,204 @@ void TileDecoder::intra_mode_tail() {
     }
     b->pal_size[0] = b->pal_size[1] = 0;
     if (b->bsize >= BLOCK_8X8 && kBlockW[b->bsize] <= 64 && kBlockH[b->bsize] <= 64 && fh.allow_screen_content_tools) {
-        // palette_mode_info(): has_palette_y / has_palette_uv
-        const int bsize_ctx = kBlockWLog2[b->bsize] + kBlockHLog2[b->bsize] - 6;   // Mi_Width_Log2 + Mi_Height_Log2 - 2
-        if (b->y_mode == DC_PRED) {
-            int ctx = 0;
-            if (avail_u && blk(mi_row - 1, mi_col)->pal_size[0] > 0) ctx++;
-            if (avail_l && blk(mi_row, mi_col - 1)->pal_size[0] > 0) ctx++;
-            if (ms.symbol(cdf.palette_y_mode[bsize_ctx][ctx], 2)) {
-                fail(AV1R_ENOSYS, "palette blocks are not supported yet");
-                return;
-            }
+        palette_mode_info();
+    }
+    filter_intra_mode_info();
+}
+
+// ---------------------------------------------------------------- palette (spec 5.11.46, 5.11.49, 7.11.4)
+int TileDecoder::get_palette_cache(int plane, uint16_t* cache) const {
+    int above_n = 0, left_n = 0;
+    const BlockInfo *a = nullptr, *l = nullptr;
+    if (((mi_row * 4) % 64) && avail_u) {
+        a = blk(mi_row - 1, mi_col);
+        above_n = a->pal_size[plane];
+    }
+    if (avail_l) {
+        l = blk(mi_row, mi_col - 1);
+        left_n = l->pal_size[plane];
+    }
+    int ai = 0, li = 0, n = 0;
+    while (ai < above_n && li < left_n) {
+        const int ac = a->pal_colors[plane][ai], lc = l->pal_colors[plane][li];
+        if (lc < ac) {
+            if (n == 0 || lc != cache[n - 1]) cache[n++] = (uint16_t)lc;
+            li++;
+        } else {
+            if (n == 0 || ac != cache[n - 1]) cache[n++] = (uint16_t)ac;
+            ai++;
+            if (lc == ac) li++;
         }
-        if (b->has_chroma && b->uv_mode == DC_PRED) {
-            int ctx = b->pal_size[0] > 0;
-            if (ms.symbol(cdf.palette_uv_mode[ctx], 2)) {
-                fail(AV1R_ENOSYS, "palette blocks are not supported yet");
-                return;
+    }
+    while (ai < above_n) {
+        const int v = a->pal_colors[plane][ai++];
+        if (n == 0 || v != cache[n - 1]) cache[n++] = (uint16_t)v;
+    }
+    while (li < left_n) {
+        const int v = l->pal_colors[plane][li++];
+        if (n == 0 || v != cache[n - 1]) cache[n++] = (uint16_t)v;
+    }
+    return n;
+}
+
+static int ceil_log2(int x) {
+    if (x < 2) return 0;
+    int i = 1, p = 2;
+    while (p < x) { i++; p <<= 1; }
+    return i;
+}
+
+void TileDecoder::palette_mode_info() {
+    const int bd = seq.bit_depth, pixmax = (1 << bd) - 1;
+    const int bsize_ctx = kBlockWLog2[b->bsize] + kBlockHLog2[b->bsize] - 6;   // Mi_Width_Log2 + Mi_Height_Log2 - 2
+    uint16_t cache[16];
+    if (b->y_mode == DC_PRED) {
+        int ctx = 0;
+        if (avail_u && blk(mi_row - 1, mi_col)->pal_size[0] > 0) ctx++;
+        if (avail_l && blk(mi_row, mi_col - 1)->pal_size[0] > 0) ctx++;
+        if (ms.symbol(cdf.palette_y_mode[bsize_ctx][ctx], 2)) {
+            const int n = ms.symbol(cdf.palette_y_size[bsize_ctx], 7) + 2;
+            b->pal_size[0] = (uint8_t)n;
+            uint16_t* col = b->pal_colors[0];
+            const int cache_n = get_palette_cache(0, cache);
+            int idx = 0;
+            for (int i = 0; i < cache_n && idx < n; i++)
+                if (ms.literal(1)) col[idx++] = cache[i];
+            if (idx < n) {
+                col[idx++] = (uint16_t)ms.literal(bd);
+                if (idx < n) {
+                    int bits = bd - 3 + ms.literal(2);
+                    while (idx < n) {
+                        const int delta = ms.literal(bits) + 1;
+                        col[idx] = (uint16_t)std::min(pixmax, col[idx - 1] + delta);
+                        const int range = (1 << bd) - col[idx] - 1;
+                        bits = std::min(bits, ceil_log2(range));
+                        idx++;
+                    }
+                }
+            }
+            std::sort(col, col + n);
+        }
+    }
+    if (b->has_chroma && b->uv_mode == DC_PRED) {
+        const int ctx = b->pal_size[0] > 0;
+        if (ms.symbol(cdf.palette_uv_mode[ctx], 2)) {
+            const int n = ms.symbol(cdf.palette_uv_size[bsize_ctx], 7) + 2;
+            b->pal_size[1] = (uint8_t)n;
+            uint16_t* cu = b->pal_colors[1];
+            uint16_t* cv = b->pal_colors[2];
+            const int cache_n = get_palette_cache(1, cache);
+            int idx = 0;
+            for (int i = 0; i < cache_n && idx < n; i++)
+                if (ms.literal(1)) cu[idx++] = cache[i];
+            if (idx < n) {
+                cu[idx++] = (uint16_t)ms.literal(bd);
+                if (idx < n) {
+                    int bits = bd - 3 + ms.literal(2);
+                    while (idx < n) {
+                        const int delta = ms.literal(bits);
+                        cu[idx] = (uint16_t)std::min(pixmax, cu[idx - 1] + delta);
+                        const int range = (1 << bd) - cu[idx];
+                        bits = std::min(bits, ceil_log2(range));
+                        idx++;
+                    }
+                }
+            }
+            std::sort(cu, cu + n);
+            if (ms.literal(1)) {   // delta_encode_palette_colors_v
+                const int max_val = 1 << bd;
+                const int bits = bd - 4 + ms.literal(2);
+                cv[0] = (uint16_t)ms.literal(bd);
+                for (idx = 1; idx < n; idx++) {
+                    int delta = ms.literal(bits);
+                    if (delta && ms.literal(1)) delta = -delta;
+                    int val = cv[idx - 1] + delta;
+                    if (val < 0) val += max_val;
+                    if (val >= max_val) val -= max_val;
+                    cv[idx] = (uint16_t)std::min(pixmax, std::max(0, val));
+                }
+            } else {
+                for (idx = 0; idx < n; idx++) cv[idx] = (uint16_t)ms.literal(bd);
             }
         }
     }
-    filter_intra_mode_info();
+}
+
+// Colour index maps.  Layout of one palette entry in FrameWork::pal (TxRec::pal_off points at it):
+//   uint16 colours[8] | uint16 origin_x, origin_y (plane samples) | uint16 stride | uint16 0 | uint8 map[rows * stride]
+void TileDecoder::palette_tokens() {
+    static const int8_t kColorCtx[9] = {-1, -1, 0, -1, -1, 4, 3, 2, 1};
+    for (int pi = 0; pi < 2; pi++) {
+        const int n = b->pal_size[pi];
+        pal_entry[pi] = pal_entry[2] = 0;
+        if (!n) continue;
+        const int sx = pi ? seq.subsampling_x : 0, sy = pi ? seq.subsampling_y : 0;
+        int bw = kBlockW[b->bsize] >> sx, bh = kBlockH[b->bsize] >> sy;
+        int ow = std::min((int)kBlockW[b->bsize], (fw.mi_cols - mi_col) * 4) >> sx, oh = std::min((int)kBlockH[b->bsize], (fw.mi_rows - mi_row) * 4) >> sy;
+        if (pi && bw < 4) { bw += 2; ow += 2; }
+        if (pi && bh < 4) { bh += 2; oh += 2; }
+        std::vector<uint8_t> map((size_t)bw * bh, 0);
+        auto at = [&](int r, int c) -> uint8_t& { return map[(size_t)r * bw + c]; };
+        {   // color_index_map: NS(n)
+            int w = 0, x = n;
+            while (x) { x >>= 1; w++; }
+            const int m = (1 << w) - n;
+            int v = ms.literal(w - 1);
+            if (v >= m) v = (v << 1) - m + ms.literal(1);
+            at(0, 0) = (uint8_t)v;
+        }
+        for (int i = 1; i < oh + ow - 1; i++)
+            for (int j = std::min(i, ow - 1); j >= std::max(0, i - oh + 1); j--) {
+                const int r = i - j, c = j;
+                int scores[8] = {0, 0, 0, 0, 0, 0, 0, 0}, order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                if (c > 0) scores[at(r, c - 1)] += 2;
+                if (r > 0 && c > 0) scores[at(r - 1, c - 1)] += 1;
+                if (r > 0) scores[at(r - 1, c)] += 2;
+                for (int a = 0; a < 3; a++) {
+                    int max_score = scores[a], max_idx = a;
+                    for (int k = a + 1; k < n; k++)
+                        if (scores[k] > max_score) { max_score = scores[k]; max_idx = k; }
+                    if (max_idx != a) {
+                        const int mo = order[max_idx];
+                        for (int k = max_idx; k > a; k--) { scores[k] = scores[k - 1]; order[k] = order[k - 1]; }
+                        scores[a] = max_score;
+                        order[a] = mo;
+                    }
+                }
+                const int hash = scores[0] * 1 + scores[1] * 2 + scores[2] * 2;
+                const int ctx = kColorCtx[hash];
+                uint16_t* c_ = pi ? cdf.palette_uv_color_index[n - 2][ctx] : cdf.palette_y_color_index[n - 2][ctx];
+                int sym;
+                switch (n) {   // the symbol decoder wants a compile-time alphabet size
+                    case 2: sym = ms.symbol(c_, 2); break;
+                    case 3: sym = ms.symbol(c_, 3); break;
+                    case 4: sym = ms.symbol(c_, 4); break;
+                    case 5: sym = ms.symbol(c_, 5); break;
+                    case 6: sym = ms.symbol(c_, 6); break;
+                    case 7: sym = ms.symbol(c_, 7); break;
+                    default: sym = ms.symbol(c_, 8); break;
+                }
+                at(r, c) = (uint8_t)order[sym];
+            }
+        for (int i = 0; i < oh; i++)
+            for (int j = ow; j < bw; j++) at(i, j) = at(i, ow - 1);
+        for (int i = oh; i < bh; i++)
+            for (int j = 0; j < bw; j++) at(i, j) = at(oh - 1, j);
+        // emit one entry per plane (U and V share the map)
+        for (int plane = pi ? 1 : 0; plane <= (pi ? 2 : 0); plane++) {
+            while (fw.pal.size() & 3) fw.pal.push_back(0);
+            pal_entry[plane] = (uint32_t)fw.pal.size();
+            uint16_t hdr[12];
+            for (int k = 0; k < 8; k++) hdr[k] = b->pal_colors[plane][k];
+            hdr[8] = (uint16_t)((mi_col >> sx) * 4);
+            hdr[9] = (uint16_t)((mi_row >> sy) * 4);
+            hdr[10] = (uint16_t)bw;
+            hdr[11] = 0;
+            const uint8_t* hb = reinterpret_cast<const uint8_t*>(hdr);
+            fw.pal.insert(fw.pal.end(), hb, hb + sizeof(hdr));
+            fw.pal.insert(fw.pal.end(), map.begin(), map.end());
+        }
+    }
 }
 
 void TileDecoder::intra_segment_id() {
@@ -783,7 +964,14 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
             if (ft < 0) ft = filter_type(plane);
             if (ft) rec.flags |= TXF_SMOOTH_EDGE;
         }
-        if (plane == 0) {
+        if (b->pal_size[plane > 0]) {
+            rec.mode = TXM_PALETTE;
+            rec.pal_off = pal_entry[plane];
+            if (plane == 0) {
+                max_luma_w = start_x + step_x * 4;
+                max_luma_h = start_y + step_y * 4;
+            }
+        } else if (plane == 0) {
             if (b->use_filter_intra) {
                 rec.mode = TXM_FILTER_INTRA;
                 rec.fi_mode = b->fi_mode;

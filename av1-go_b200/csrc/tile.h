@@ -82,6 +82,10 @@ private:
     int compute_tx_type(int plane, int txsz, int block_x, int block_y) const;
     int filter_type(int plane) const;
     void push_record(const TxRec& rec, int ux, int uy);
+    void palette_mode_info();
+    void palette_tokens();
+    int get_palette_cache(int plane, uint16_t* cache) const;
+    uint32_t pal_entry[3] = {0, 0, 0};
     void intra_mode_tail();   // uv mode, palette, filter-intra: shared by intra frames and intra blocks of inter frames
     // inter (tile_inter.cpp)
     void inter_frame_mode_info();

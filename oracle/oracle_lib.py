@@ -37,7 +37,7 @@ def film_grain(fg_params, planes, bpc, subx=1, suby=1, mono=0, mc_identity=0):
 
 TOOL_NAMES = ["inter_blocks", "compound_avg", "compound_dist", "compound_wedge", "compound_diffwtd", "interintra", "interintra_wedge",
               "obmc", "local_warp", "global_warp", "skip_mode", "dual_filter", "temporal_mv", "intra_in_inter", "sub8x8_chroma", "newmv",
-              "vartx_split", "switchable_filter"]
+              "vartx_split", "switchable_filter", "palette", "intrabc"]
 LAST_TOOL_HIST = {}
 
 

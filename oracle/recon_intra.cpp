@@ -343,7 +343,17 @@ void reconstruct_frame(const FrameWork& fw, Frame& f, const Frame* const refs[8]
             interintra_blend(f, r, pred);
             continue;
         }
-        if (r.mode != TXM_INTER) {
+        if (r.mode == TXM_PALETTE) {
+            // spec 7.11.4: pred = palette[ColorMap]; entry layout documented at TileDecoder::palette_tokens
+            const uint8_t* e = fw.pal.data() + r.pal_off;
+            const uint16_t* hdr = reinterpret_cast<const uint16_t*>(e);
+            const uint8_t* map = e + 24;
+            const int ox = hdr[8], oy = hdr[9], stride = hdr[10];
+            for (int i = 0; i < h; i++)
+                for (int j = 0; j < w; j++) pred[i * w + j] = hdr[map[(size_t)(y - oy + i) * stride + (x - ox + j)]];
+            for (int yy = y; yy < ye; yy++)
+                for (int xx = x; xx < xe; xx++) pl.at(xx, yy) = (uint16_t)pred[(yy - y) * w + (xx - x)];
+        } else if (r.mode != TXM_INTER) {
             predict_intra_block(pl, g, r, r.plane, pred);
             if (r.mode == TXM_CFL) cfl_apply(f.p[0], g, r, pred);
             for (int yy = y; yy < ye; yy++)

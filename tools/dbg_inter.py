@@ -77,3 +77,9 @@ if __name__ == "__main__":
         for name, o in [("no-ii", {"enable-interintra-comp": "0"}), ("no-dist", {"enable-dist-wtd-comp": "0"}), ("no-dual", {"enable-dual-filter": "0"}),
                         ("no-ii-dist", {"enable-interintra-comp": "0", "enable-dist-wtd-comp": "0"})]:
             run(name, o, w=208, h=144, n=4, lag=10, bpc=10, src="panzoom", cpu="0", filters=0, grain=0)
+    if which == "pal":
+        BASE_OFF.clear()
+        run("pal-intra", {"tune-content": "screen"}, w=320, h=192, n=3, lag=0, kf=0, src="testsrc2", cpu="4", filters=7)
+        run("pal-inter", {"tune-content": "screen"}, w=320, h=192, n=6, lag=0, src="testsrc2", cpu="4", filters=7)
+        run("pal-auto", {}, w=320, h=192, n=6, lag=4, src="testsrc2", cpu="1", filters=7)
+        run("pal-10b", {"tune-content": "screen", "enable-intrabc": "0"}, w=320, h=192, n=4, lag=0, src="testsrc2", cpu="4", filters=7, bpc=10)

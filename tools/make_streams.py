@@ -15,6 +15,16 @@ CACHE = os.path.join(ROOT, "streams_cache")
 CONFIGS = {
     # configs[1]: 1080p 8-bit intra-only (every frame KEY), inverse transform + intra + deblock/CDEF only
     "c2": ("panzoom", 1920, 1080, 8, 60, {"cpu-used": "8", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "1"}, {14: 0, 48: 0}),
+    # configs[0]: 1080p 8-bit Main-profile clip, testsrc2-like, 60 frames, 2 closed GOPs, 2 tile columns, all default tools
+    "c1": ("testsrc2", 1920, 1080, 8, 60, {"cpu-used": "8", "cq-level": "32", "tile-columns": "1"}, {14: 19, 48: 30}),
+    # configs[2]: 4K 10-bit, full inter tools (compound, OBMC, warped / global motion) + loop restoration, 4x2 tiles
+    "c3": ("panzoom", 3840, 2160, 10, 60, {"cpu-used": "6", "cq-level": "32", "tile-columns": "2", "tile-rows": "1", "enable-obmc": "1",
+                                          "enable-warped-motion": "1", "enable-global-motion": "1", "enable-restoration": "1"}, {14: 19, 48: 30}),
+    # configs[3]: as c3 on a noise-heavy source with film grain synthesis
+    "c4": ("noise", 3840, 2160, 10, 60, {"cpu-used": "6", "cq-level": "32", "tile-columns": "2", "tile-rows": "1", "enable-restoration": "1",
+                                        "film-grain-test": "5"}, {14: 19, 48: 30}),
+    "c3_small": ("panzoom", 960, 544, 10, 20, {"cpu-used": "6", "cq-level": "32", "tile-columns": "1", "tile-rows": "1", "enable-restoration": "1"},
+                 {14: 19, 48: 10}),
     "c2_small": ("panzoom", 640, 360, 8, 8, {"cpu-used": "8", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "1"}, {14: 0, 48: 0}),
 }
 
