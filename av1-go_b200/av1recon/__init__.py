@@ -219,7 +219,15 @@ class ClipInfo(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("width", C.c_int), ("height", C.c_int), ("bit_depth", C.c_int),
                 ("frames_decoded", C.c_int64), ("frames_shown", C.c_int64), ("host_parse_ms", C.c_double),
                 ("worklist_bytes", C.c_uint64), ("frame_bytes", C.c_uint64), ("coded_samples", C.c_uint64),
-                ("coef_tokens", C.c_uint64), ("tx_blocks", C.c_uint64), ("intra_samples", C.c_uint64)]
+                ("coef_tokens", C.c_uint64), ("tx_blocks", C.c_uint64), ("intra_samples", C.c_uint64),
+                ("inter_samples", C.c_uint64), ("inter_ref_samples", C.c_uint64), ("lr_frames", C.c_uint64), ("cdef_frames", C.c_uint64),
+                ("deblock_frames", C.c_uint64), ("grain_frames", C.c_uint64), ("inter_blocks", C.c_uint64), ("obmc_neighbours", C.c_uint64),
+                ("tool_hist", C.c_uint64 * 24)]
+
+
+TOOL_NAMES = ["inter_blocks", "compound_avg", "compound_dist", "compound_wedge", "compound_diffwtd", "interintra", "interintra_wedge",
+              "obmc", "local_warp", "global_warp", "skip_mode", "dual_filter", "temporal_mv", "intra_in_inter", "sub8x8_chroma", "newmv",
+              "vartx_split", "switchable_filter", "palette", "intrabc"]
 
 
 STAGES = ["h2d", "itx", "intra", "inter", "deblock", "cdef", "lr", "grain", "digest"]

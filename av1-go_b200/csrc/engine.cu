@@ -124,6 +124,7 @@ struct DevWork {
     int lf_on = 0, lf_plane_on[3] = {0, 0, 0}, cdef_on = 0, lr_on = 0;
     uint64_t coded_samples = 0, coef_tokens = 0;
     double parse_ms = 0;
+    int grain_on = 0;
     int lr_rows[3] = {0, 0, 0}, lr_cols[3] = {0, 0, 0}, lr_has[3] = {0, 0, 0};
     std::vector<SbRowItem> items_host;
 };
@@ -1074,6 +1075,15 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
                 clip->info.coded_samples += fw.coded_samples;
                 clip->info.coef_tokens += fw.coefs.size();
                 clip->info.tx_blocks += fw.tx.size();
+                clip->info.inter_samples += fw.inter_samples;
+                clip->info.inter_ref_samples += fw.inter_ref_samples;
+                clip->info.inter_blocks += fw.inter.size();
+                clip->info.obmc_neighbours += fw.obmc.size();
+                clip->info.lr_frames += cf->dw.lr_on && (E.cfg.inloop_filters & 4);
+                clip->info.cdef_frames += cf->dw.cdef_on && (E.cfg.inloop_filters & 2);
+                clip->info.deblock_frames += cf->dw.lf_on && (E.cfg.inloop_filters & 1);
+                clip->info.grain_frames += fw.fh.show_frame && fw.fh.fg.apply_grain && E.cfg.apply_grain;
+                for (int i = 0; i < 24; i++) clip->info.tool_hist[i] += fw.tool_hist[i];
                 for (const TxRec& r : fw.tx)
                     if (r.mode != TXM_INTER) clip->info.intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
                 clip->info.width = fw.fh.upscaled_width;

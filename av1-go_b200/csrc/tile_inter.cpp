@@ -1159,7 +1159,11 @@ void TileDecoder::emit_inter_block() {
     if (b->has_chroma && sub8) fw.tool_hist[TOOL_SUB8X8_CHROMA]++;
     if (b->has_chroma && !sub8) r.planes |= 2;
     fw.inter.push_back(r);
-    fw.inter_samples += (uint64_t)bw * bh * ((r.planes & 2) ? 3 : 2) / 2;
+    {
+        const uint64_t area = (uint64_t)bw * bh * ((r.planes & 2) ? 3 : 2) / 2;
+        fw.inter_samples += area;
+        fw.inter_ref_samples += area * (1 + is_compound);
+    }
     if (b->has_chroma && sub8) {
         // chroma of a group of sub-8x8 luma blocks (spec 7.11.3.1 / compute_prediction)
         const int psz = plane_residual_size((BlockSize)b->bsize, subx, suby);
@@ -1193,6 +1197,7 @@ void TileDecoder::emit_inter_block() {
                 }
         }
         fw.inter_samples += (uint64_t)(n4w * 4) * (n4h * 4) * 2;
+        fw.inter_ref_samples += (uint64_t)(n4w * 4) * (n4h * 4) * 2;
     }
     if (b->interintra) emit_interintra_records();
 }

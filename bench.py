@@ -255,20 +255,32 @@ def cpu_baseline_filmgrain():
 # ------------------------------------------------------------------------------------------
 # workload: BASELINE configs[1] -- 1080p 8-bit intra-only clip, full GPU reconstruction
 # ------------------------------------------------------------------------------------------
+CLIP_DESC = {
+    "c1": ("c1_1080p8: BASELINE configs[0] -- 1920x1080 8-bit 4:2:0 Main profile, 60 frames, testsrc2-like source, libaom 3.13.1 cq 32, "
+           "lag_in_frames 19 (hidden ARFs + show_existing_frame), kf_max_dist 30 (2 closed GOPs), 2 tile columns, all default tools"),
+    "c3": ("c3_4k10_inter: BASELINE configs[2] -- 3840x2160 10-bit 4:2:0, 60 frames, pan/zoom/rotation texture with moving patches, "
+           "libaom cq 32, compound + OBMC + warped/global motion + loop restoration, 4x2 tiles, lag 19, kf_max_dist 30"),
+    "c4": ("c4_4k10_grain: BASELINE configs[3] -- as c3 on a noise-heavy source with film grain synthesis (libaom film-grain-test 5)"),
+    "c3_small": "c3_small: 960x544 10-bit inter clip (smoke-size version of c3)",
+}
 C2_DESC = ("c2_intra_1080p8: BASELINE configs[1] -- 1920x1080 8-bit 4:2:0, 60 frames, every frame KEY (libaom 3.13.1, cq 32, "
            "CDEF on, LR off, synthetic pan/zoom texture); step = one pass over the 60-frame clip; "
            "value = device path from HBM-resident work-lists (sequential host symbol parse reported separately as host_parse_ms); "
            "per-step working set (work-lists + frame buffers of 60 frames) exceeds the 126 MB L2, no flush needed")
 
 
-def c2_clip():
+def c2_clip(name="c2"):
     from tools.make_streams import get_clip
-    return get_clip("c2", verbose=True)
+    return get_clip(name, verbose=True)
 
 
-def run_c2(args, torch, dist, rank, world, local):
+STEP_NOTE = ("; step = one pass over the clip; value = device path from HBM-resident work-lists (sequential host symbol parse reported "
+             "separately as host_parse_ms); per-step working set (work-lists + frame buffers in flight) exceeds the 126 MB L2, no flush needed")
+
+
+def run_c2(args, torch, dist, rank, world, local, name="c2"):
     import av1recon
-    tus = c2_clip()
+    tus = c2_clip(name)
     torch.cuda.set_device(local)
     dec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
     clip = av1recon.Clip(dec, tus)
@@ -305,13 +317,16 @@ def run_c2(args, torch, dist, rank, world, local):
     nrec = int(info.tx_blocks)
     nf = int(info.frames_decoded)
     bps = 1 if info.bit_depth == 8 else 2
+    intra_s, inter_s, ref_s = int(info.intra_samples), int(info.inter_samples), int(info.inter_ref_samples)
     stage_bytes = {
         "itx": 4 * ntok + 32 * nrec + 2 * A,                 # C (tokens) + records + residual write
-        "intra": F * nf + 2 * A + 32 * nrec,                  # frame write + residual read + records
-        "deblock": 2 * F * nf,
-        "cdef": 2 * F * nf,
-        "grain": 2 * F * nf,
-        "digest": F * nf,
+        "intra": bps * intra_s + 2 * A + 32 * nrec,           # intra samples written + residual read + records
+        "inter": bps * (ref_s + inter_s) + 40 * int(info.inter_blocks),   # Rbar * F_inter read + F_inter written + records
+        "deblock": 2 * F * int(info.deblock_frames),
+        "cdef": 2 * F * int(info.cdef_frames),
+        "lr": int(2.0625 * F) * int(info.lr_frames),
+        "grain": 2 * F * int(info.grain_frames),
+        "digest": F * nfr,
     }
     stages = {}
     for k, (ms, launches) in prof.items():
@@ -329,7 +344,7 @@ def run_c2(args, torch, dist, rank, world, local):
     # host symbol parse (all host cores), H2D of the work-lists, reconstruction kernels, D2H of the 24-byte
     # plane digests of every frame.  Wall clock.
     from tools.make_streams import clip_path
-    blob = open(clip_path("c2"), "rb").read()
+    blob = open(clip_path(name), "rb").read()
     vdec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)   # the daemon keeps one engine open
     vdec.verify_buffer(blob)                                                  # warm-up (allocations, first-touch)
     best = None
@@ -361,8 +376,8 @@ def run_c2(args, torch, dist, rank, world, local):
     out = {
         "metric": "AV1 decode-verify frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": C2_DESC, "frames_per_step": nfr, "parallelism": f"replicas{world} (independent clips per GPU, no collective)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8" if info.bit_depth == 8 else "u16", "data": "synthetic",
+        "config": {"workload": C2_DESC if name == "c2" else CLIP_DESC[name] + STEP_NOTE, "frames_per_step": nfr, "parallelism": f"replicas{world} (independent clips per GPU, no collective)",
                    "streams": 16, "frames_in_flight": 32},
         "gpu_launches": launches_per_step * args.steps,
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr,
@@ -374,7 +389,10 @@ def run_c2(args, torch, dist, rank, world, local):
                      "pipeline_algorithmic_gbs": sum(stage_bytes[k] for k in stages if k in stage_bytes) / (total_ms / args.steps / 1e3) / 1e9},
         "host_parse_ms_per_frame": float(info.host_parse_ms) / max(1, nf),
         "clip": {"bytes": sum(len(t) for t in tus), "frames": nfr, "coded_sample_fraction": A / max(1, nf * (F // bps)),
-                 "coef_tokens_per_frame": ntok / max(1, nf), "tx_blocks_per_frame": nrec / max(1, nf)},
+                 "coef_tokens_per_frame": ntok / max(1, nf), "tx_blocks_per_frame": nrec / max(1, nf),
+                 "frames_decoded": nf, "inter_sample_fraction": inter_s / max(1, nf * (F // bps)),
+                 "mean_refs_per_inter_sample": ref_s / max(1, inter_s),
+                 "tools": {k: int(v) for k, v in zip(av1recon.TOOL_NAMES, info.tool_hist) if v}},
         "clocks": clocks,
     }
     clip.free()
@@ -383,10 +401,10 @@ def run_c2(args, torch, dist, rank, world, local):
     return out
 
 
-def cpu_baseline_c2():
+def cpu_baseline_c2(name="c2"):
     """libdav1d 1.5.3 (the decoder inside the reference's FFmpeg build) on the host cores, same clip."""
     from oracle import dav1d_ref
-    tus = c2_clip()
+    tus = c2_clip(name)
     ncpu = os.cpu_count() or 1
     dav1d_ref.decode(tus[:8], n_threads=ncpu, keep=False)
     best = None
@@ -399,11 +417,17 @@ def cpu_baseline_c2():
     dav1d_ref.decode(tus[:20], n_threads=1, keep=False)
     dt1 = time.perf_counter() - t0
     return {"value": len(out) / best, "unit": "frames/s", "cores": ncpu, "kind": "reference",
-            "sample": f"libdav1d {dav1d_ref.version()} driven directly (no ffmpeg binary in the image), n_threads={ncpu}, whole 60-frame clip "
+            "sample": f"libdav1d {dav1d_ref.version()} driven directly (no ffmpeg binary in the image), n_threads={ncpu}, whole {len(tus)}-TU clip "
                       f"preloaded in RAM, best of 3, no MD5; single-thread figure {20 / dt1:.1f} frames/s on 20 frames"}
 
 
-WORKLOADS = {"filmgrain_4k10": (run_filmgrain, cpu_baseline_filmgrain), "c2_intra_1080p8": (run_c2, cpu_baseline_c2)}
+def _clip_workload(name):
+    return (lambda *a: run_c2(*a, name=name)), (lambda: cpu_baseline_c2(name))
+
+
+WORKLOADS = {"filmgrain_4k10": (run_filmgrain, cpu_baseline_filmgrain), "c2_intra_1080p8": (run_c2, cpu_baseline_c2),
+             "c1_1080p8": _clip_workload("c1"), "c3_4k10_inter": _clip_workload("c3"), "c4_4k10_grain": _clip_workload("c4"),
+             "c3_small": _clip_workload("c3_small")}
 DEFAULT_WORKLOAD = "c2_intra_1080p8"
 
 

@@ -90,6 +90,11 @@ typedef struct av1r_clip_info {
     uint64_t coef_tokens;          /* non-zero coefficients summed over frames (4 B each = C) */
     uint64_t tx_blocks;            /* transform-block records summed over frames (32 B each) */
     uint64_t intra_samples;        /* samples reconstructed by the intra wavefront kernel */
+    uint64_t inter_samples;        /* samples predicted by K2 (all planes), summed over frames */
+    uint64_t inter_ref_samples;    /* reference samples those predictions are formed from (2x for compound): Rbar * inter_samples */
+    uint64_t lr_frames, cdef_frames, deblock_frames, grain_frames;   /* frames on which each post-filter stage runs */
+    uint64_t inter_blocks, obmc_neighbours;
+    uint64_t tool_hist[24];        /* block counts per coding tool, order of TOOL_* in csrc/frame_state.h */
 } av1r_clip_info;
 
 enum { AV1R_ST_H2D = 0, AV1R_ST_ITX, AV1R_ST_INTRA, AV1R_ST_INTER, AV1R_ST_DEBLOCK, AV1R_ST_CDEF, AV1R_ST_LR, AV1R_ST_GRAIN,

@@ -122,3 +122,33 @@ def test_cuda_verify_buffer_inter(built):
     for i, r in enumerate(dec.results):
         assert [int(x) for x in r.checksum] == [int(x) for x in digests[i]], f"frame {i}"
     dec.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clip", ["c1", "c3_small", "c3", "c4"])
+def test_cuda_full_size_clip_vs_dav1d(built, clip):
+    """BASELINE-size clips (when present in streams_cache/): every plane digest of every frame from av1r_verify_buffer equals the
+    digest of libdav1d's output for the same frame (the digest is a position-salted 64-bit hash; host restatement in the library)."""
+    import ctypes as C
+    import av1recon
+    from oracle import dav1d_ref
+    from tools.make_streams import clip_path
+    path = clip_path(clip)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    data = open(path, "rb").read()
+    from tools.obuio import read_ivf
+    tus = read_ivf(path)
+    rc, rep, digests = av1recon.verify_buffer(data)
+    assert rc == 0 and rep.status == 0, rep.message
+    l = av1recon.lib()
+    l.av1r_plane_checksum_host.restype = C.c_uint64
+    l.av1r_plane_checksum_host.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    ref = dav1d_ref.decode(tus, n_threads=os.cpu_count() or 4)
+    assert len(ref) == rep.frames == len(digests)
+    bpc = rep.bit_depth
+    for i, fr in enumerate(ref):
+        for p in range(3):
+            a = np.ascontiguousarray(fr[4][p].astype(np.uint8 if bpc == 8 else "<u2"))
+            want = l.av1r_plane_checksum_host(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], bpc)
+            assert int(digests[i][p]) == int(want), f"{clip} frame {i} plane {p}: digest differs from libdav1d"
