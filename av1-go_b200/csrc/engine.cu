@@ -373,16 +373,23 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     auto recon = get_frame(fp);
     if (!recon) return AV1R_ENOMEM;
     s.hold.push_back(recon);
-    // residual planes
+    // residual: unit-major tiles (devframe.h)
     DevResidual res;
-    size_t roff[3], rtotal = 0;
-    for (int p = 0; p < 3; p++) {
-        res.pitch[p] = (uint32_t)align_up((size_t)fp.cw[p] * 2, 256);
-        roff[p] = rtotal;
-        rtotal += (size_t)res.pitch[p] * fp.ch[p];
+    {
+        const int units_x = (fp.cw[0] + 63) >> 6, units_y = (fp.ch[0] + 63) >> 6;
+        int off = 0;
+        for (int p = 0; p < 3; p++) {
+            const int sx = p ? fp.subx : 0, sy = p ? fp.suby : 0;
+            res.tw_log2[p] = 6 - sx;
+            res.th_log2[p] = 6 - sy;
+            res.plane_off[p] = off;
+            off += 1 << (res.tw_log2[p] + res.th_log2[p]);
+        }
+        res.units_x = units_x;
+        res.unit_elems = off;
+        CK(s.residual.ensure((size_t)units_x * units_y * off * sizeof(int16_t)));
+        res.base = (int16_t*)s.residual.p;
     }
-    CK(s.residual.ensure(rtotal));
-    for (int p = 0; p < 3; p++) res.p[p] = (int16_t*)(s.residual.p + roff[p]);
     CK(s.sync.ensure(sizeof(int) * (L.n_items + 4)));
     CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_items + 4), st));
     // intra frame descriptor lives in the arena (device pointers patched here)

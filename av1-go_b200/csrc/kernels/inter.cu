@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(128) inter_residual_kernel(const TxRec* recs, 
     const int pixmax = (1 << fp.bd) - 1;
     T* out = (T*)(cur.p[plane] + (size_t)y * cur.pitch[plane]) + x;
     const int ope = cur.pitch[plane] / sizeof(T);
-    const int16_t* rp = (const int16_t*)((const uint8_t*)res.p[plane] + (size_t)y * res.pitch[plane]) + x;
-    const int rpe = res.pitch[plane] >> 1;
+    const int16_t* rp = res_ptr(res, plane, x, y);
+    const int rpe = 1 << res.tw_log2[plane];
     for (int idx = lane; idx < w * h; idx += 32) {
         const int i = idx >> lw, j = idx & (w - 1);
         if (i < ye && j < xe) {

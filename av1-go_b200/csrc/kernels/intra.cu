@@ -12,6 +12,10 @@
 // Inter-row hand-off: per-item progress counters (release: __threadfence + store, acquire: volatile
 // load + __threadfence); halo reads use ld.cg so a stale L1 line can never be observed.  Items are
 // claimed through an atomic ticket, so a warp only waits on items that are already running.
+// v4: the chain link is kept off HBM/L2 latency entirely -- the unit's int16 residual (12 KB, unit-major layout written by K1),
+// the unit's 32-byte records (chunks of 64) and the item's unit table are brought into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx), double-buffered so that unit k+1 / chunk q+1 are in flight while unit k / chunk q
+// are being reconstructed; a block then costs shared-memory reads, ALU work and fire-and-forget stores only.
 // Algorithmic bytes: F_intra written + 2A residual read + 32 B/record; halos are L2 hits.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -61,6 +65,30 @@ struct UnitView {
         return tile[plane][dy * tw[plane] + dx];
     }
 };
+
+// ---- TMA bulk copy + mbarrier helpers (sm_90+; SASS UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+static constexpr int REC_CHUNK = 64;     // records per bulk copy
+static constexpr int SBS_CAP = 128;      // unit descriptors staged per item
 
 template <typename T>
 __device__ __forceinline__ int ldpx(const uint8_t* base, uint32_t pitch, int x, int y) {
@@ -152,7 +180,7 @@ __device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int
 }
 
 template <typename T>
-__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
+__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const int16_t* res_s, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
                             const UnitView<T>& uv, int lane, const uint8_t* wedge_master, const uint8_t* pal) {
     const int plane = r.plane;
     const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
@@ -166,8 +194,9 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
     const int tpitch = uv.tw[plane];
     T* out = (T*)(fr.p[plane] + (size_t)y * pitch) + x;
     const int opitch = pitch / sizeof(T);
-    const int16_t* rp = (const int16_t*)((const uint8_t*)res.p[plane] + (size_t)y * res.pitch[plane]) + x;
-    const int rpitch = res.pitch[plane] >> 1;
+    // residual of the unit, resident in shared memory (same tile geometry as the sample tile)
+    const int16_t* rp = res_s + res.plane_off[plane] + (y - uv.uy0[plane]) * uv.tw[plane] + (x - uv.ux0[plane]);
+    const int rpitch = uv.tw[plane];
     const bool has_res = r.eob > 0;
     const bool ii = (r.flags & TXF_II) != 0;
     const int ii_pk = (uint16_t)r.cfl_alpha;
@@ -178,7 +207,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
                 const int m = ii_mask(ii_pk, wedge_master, i, j, w, h, psx, psy);
                 v = (m * v + (64 - m) * (int)tl[i * tpitch + j] + 32) >> 6;
             }
-            if (has_res) v = min(max(v + (int)__ldg(rp + i * rpitch + j), 0), pixmax);
+            if (has_res) v = min(max(v + (int)rp[i * rpitch + j], 0), pixmax);
             out[i * opitch + j] = (T)v;
             tl[i * tpitch + j] = (T)v;
         }
@@ -189,7 +218,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
             for (int idx = lane; idx < w * h; idx += 32) {
                 const int i = idx >> lw, j = idx & (w - 1);
                 if (i < ye && j < xe) {
-                    int v = (int)tl[i * tpitch + j] + (int)__ldg(rp + i * rpitch + j);
+                    int v = (int)tl[i * tpitch + j] + (int)rp[i * rpitch + j];
                     v = min(max(v, 0), pixmax);
                     out[i * opitch + j] = (T)v;
                     tl[i * tpitch + j] = (T)v;
@@ -447,14 +476,23 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
 
 template <typename T>
 __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(IntraLaunch L) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
+    extern __shared__ __align__(128) uint8_t s_raw[];
     const int warp_in = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* wbase = s_raw + (size_t)warp_in * L.smem_per_warp;
-    IntraSmem& sm = *reinterpret_cast<IntraSmem*>(wbase);
+    // per-warp shared memory: [residual x2][records x2][unit table][barriers][IntraSmem][sample tiles + halos]
+    const DevFrameParams& fp0 = L.frames[0].fp;
+    const int unit_elems = L.frames[0].res.unit_elems;
+    const uint32_t unit_bytes = (uint32_t)unit_elems * 2;
+    int16_t* res_s[2] = {reinterpret_cast<int16_t*>(wbase), reinterpret_cast<int16_t*>(wbase + unit_bytes)};
+    TxRec* rec_s[2];
+    rec_s[0] = reinterpret_cast<TxRec*>(wbase + 2 * unit_bytes);
+    rec_s[1] = rec_s[0] + REC_CHUNK;
+    SbRange* sbs_s = reinterpret_cast<SbRange*>(rec_s[1] + REC_CHUNK);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbs_s + SBS_CAP);   // [0,1] residual, [2,3] records, [4] unit table
+    IntraSmem& sm = *reinterpret_cast<IntraSmem*>(bars + 8);
     UnitView<T> uv;
     {
-        T* p = reinterpret_cast<T*>(wbase + sizeof(IntraSmem));
-        const DevFrameParams& fp0 = L.frames[0].fp;
+        T* p = reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(&sm) + sizeof(IntraSmem));
         for (int pl = 0; pl < 3; pl++) {
             const int sx = pl ? fp0.subx : 0, sy = pl ? fp0.suby : 0;
             uv.tw[pl] = 64 >> sx;
@@ -467,6 +505,13 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(Intra
             p += 2 * uv.th[pl] + 8;
         }
     }
+    const uint32_t bar0 = smem_u32(bars);
+    if (lane == 0) {
+        for (int i = 0; i < 5; i++) mbar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t par = 0;   // bit i = parity to wait for on barrier i
     while (true) {
         int item = 0;
         if (lane == 0) item = atomicAdd(L.ticket, 1);
@@ -476,17 +521,58 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(Intra
         const IntraFrame& F = L.frames[it.frame];
         const DevFrameParams& fp = F.fp;
         const int nplanes = fp.mono ? 1 : 3;
+        const int n_units = (int)it.n_units;
         volatile int* dep = it.dep_item >= 0 ? (volatile int*)(L.progress + it.dep_item) : nullptr;
+        // ---- stage the item's unit table, then start the first residual / record transfers
+        const int n_tab = min(n_units, SBS_CAP);
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar0 + 32, (uint32_t)(n_tab * sizeof(SbRange)));
+            bulk_g2s(smem_u32(sbs_s), F.sbs + it.first_unit, (uint32_t)(n_tab * sizeof(SbRange)), bar0 + 32);
+        }
+        mbar_wait(bar0 + 32, (par >> 4) & 1);
+        par ^= 16;
+        auto unit_desc = [&](int k) -> SbRange { return k < SBS_CAP ? sbs_s[k] : F.sbs[it.first_unit + k]; };
+        auto issue_res = [&](int k) {
+            const SbRange u = unit_desc(k);
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar0 + 8 * (k & 1), unit_bytes);
+                bulk_g2s(smem_u32(res_s[k & 1]), F.res.base + ((size_t)u.uy * F.res.units_x + u.ux) * unit_elems, unit_bytes, bar0 + 8 * (k & 1));
+            }
+        };
+        int ld_unit = 0, ld_chunk = 0, q_load = 0, q_use = 0;
+        auto issue_rec = [&]() {
+            if (ld_unit >= n_units) return;
+            const SbRange u = unit_desc(ld_unit);
+            const int first = (int)u.first + ld_chunk * REC_CHUNK;
+            const int cnt = min(REC_CHUNK, (int)u.count - ld_chunk * REC_CHUNK);
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar0 + 16 + 8 * (q_load & 1), (uint32_t)(cnt * sizeof(TxRec)));
+                bulk_g2s(smem_u32(rec_s[q_load & 1]), F.recs + first, (uint32_t)(cnt * sizeof(TxRec)), bar0 + 16 + 8 * (q_load & 1));
+            }
+            q_load++;
+            ld_chunk++;
+            if (ld_chunk * REC_CHUNK >= (int)u.count) {
+                ld_unit++;
+                ld_chunk = 0;
+            }
+        };
+        __syncwarp();
+        issue_res(0);
+        issue_rec();
         int sb_done = 0;
-        for (uint32_t k = 0; k < it.n_units; k++) {
-            const SbRange un = F.sbs[it.first_unit + k];
-            const bool first_of_sb = (k == 0) || (F.sbs[it.first_unit + k - 1].sb_col != un.sb_col);
+        for (int k = 0; k < n_units; k++) {
+            const SbRange un = unit_desc(k);
+            __syncwarp();
+            if (k + 1 < n_units) issue_res(k + 1);   // buffer (k+1)&1 was last read by unit k-1
+            const bool first_of_sb = (k == 0) || (unit_desc(k - 1).sb_col != un.sb_col);
             if (first_of_sb && dep) {
-                // superblock index inside the tile row
                 const int c = un.sb_col - un.tile_sb_col0;
                 const int need = min(c + 2, (int)it.n_sb);
                 if (lane == 0)
-                    while (*dep < need) __nanosleep(64);
+                    while (*dep < need) __nanosleep(32);
                 __syncwarp();
             }
             __threadfence();
@@ -518,13 +604,25 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(Intra
                     }
                 }
             }
+            mbar_wait(bar0 + 8 * (k & 1), (par >> (k & 1)) & 1);
+            par ^= 1u << (k & 1);
             __syncwarp();
-            for (uint32_t t = 0; t < un.count; t++) {
-                const TxRec r = F.recs[un.first + t];
-                intra_block<T>(r, F.frame, F.res, fp, sm, uv, lane, F.wedge_master, F.pal);
+            const int16_t* rs = res_s[k & 1];
+            for (int c0 = 0; c0 < (int)un.count; c0 += REC_CHUNK) {
+                const int qb = q_use & 1;
+                mbar_wait(bar0 + 16 + 8 * qb, (par >> (2 + qb)) & 1);
+                par ^= 4u << qb;
                 __syncwarp();
+                issue_rec();                              // next chunk -> the buffer chunk q_use-1 used
+                const int cnt = min(REC_CHUNK, (int)un.count - c0);
+                const TxRec* rb = rec_s[qb];
+                for (int t = 0; t < cnt; t++) {
+                    intra_block<T>(rb[t], F.frame, rs, F.res, fp, sm, uv, lane, F.wedge_master, F.pal);
+                    __syncwarp();
+                }
+                q_use++;
             }
-            const bool last_of_sb = (k + 1 == it.n_units) || (F.sbs[it.first_unit + k + 1].sb_col != un.sb_col);
+            const bool last_of_sb = (k + 1 == n_units) || (unit_desc(k + 1).sb_col != un.sb_col);
             if (last_of_sb) {
                 __threadfence();
                 __syncwarp();
@@ -560,13 +658,15 @@ static cudaError_t intra_upload_constants() {
 
 size_t intra_smem_per_warp(int bd, int subx, int suby) {
     const size_t ts = bd == 8 ? 1 : 2;
-    size_t n = sizeof(IntraSmem);
+    size_t unit_elems = 0, n = 0;
     for (int pl = 0; pl < 3; pl++) {
         const int sx = pl ? subx : 0, sy = pl ? suby : 0;
         const int tw = 64 >> sx, th = 64 >> sy;
+        unit_elems += (size_t)tw * th;
         n += ts * (tw * th + 2 * tw + 16 + 2 * th + 8);
     }
-    return (n + 15) & ~(size_t)15;
+    n += 2 * unit_elems * sizeof(int16_t) + 2 * REC_CHUNK * sizeof(TxRec) + SBS_CAP * sizeof(SbRange) + 8 * sizeof(uint64_t) + sizeof(IntraSmem);
+    return (n + 127) & ~(size_t)127;
 }
 
 cudaError_t launch_intra(const IntraLaunch& L_, int bd, int subx, int suby, cudaStream_t s) {
@@ -581,7 +681,7 @@ cudaError_t launch_intra(const IntraLaunch& L_, int bd, int subx, int suby, cuda
     if (bd == 8) {
         auto k = intra_wavefront_kernel<uint8_t>;
         if (!attr_done[0]) {
-            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return e;
             cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr_done[0] = true;
         }
@@ -589,7 +689,7 @@ cudaError_t launch_intra(const IntraLaunch& L_, int bd, int subx, int suby, cuda
     } else {
         auto k = intra_wavefront_kernel<uint16_t>;
         if (!attr_done[1]) {
-            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return e;
             cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr_done[1] = true;
         }

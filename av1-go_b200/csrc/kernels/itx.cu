@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(ITX_WARPS * 32) itx_kernel(const TxRec* __rest
         }
     }
     __syncwarp();
-    int16_t* dst = (int16_t*)((uint8_t*)res.p[plane] + (size_t)(r.y4 * 4) * res.pitch[plane]) + r.x4 * 4;
-    const int dpe = res.pitch[plane] >> 1;
+    int16_t* dst = res_ptr(res, plane, r.x4 * 4, r.y4 * 4);   // a transform block never straddles a unit
+    const int dpe = 1 << res.tw_log2[plane];
     const int cols_valid = min(w, fp.cw[plane] - r.x4 * 4), rows_valid = min(h, fp.ch[plane] - r.y4 * 4);
     if (r.txtp == WHT_WHT) {
         if (lane < 4) {

@@ -103,8 +103,9 @@ struct SbRange {
     uint16_t tile_sb_col1;    // one past the last
     uint16_t tile_sb_row0;
     uint16_t ux, uy;          // unit position in 64-luma-sample units
-    uint16_t pad;
+    uint16_t pad[5];          // 32 bytes: the unit table of a work item is fetched with one bulk copy (16-byte granules)
 };
+static_assert(sizeof(SbRange) == 32, "SbRange must stay 32 bytes");
 
 // Per-4x4 loop-filter description, one byte pair per plane 4x4 unit and direction:
 //   len: 0 = no edge here, else filter length 4 / 6 / 8 / 14 (13 for luma-wide is stored as 14)
