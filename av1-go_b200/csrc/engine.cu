@@ -111,8 +111,8 @@ static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, sbs, items, iframe, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, total;
-    int n_recs, n_coefs, n_order, n_sbs, n_items, n_inter, n_obmc, n_warps;
+    size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, k3order, total;
+    int n_recs, n_coefs, n_order, n_inter, n_obmc, n_warps, n_k3;
 };
 
 static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
@@ -126,7 +126,6 @@ struct DevWork {
     double parse_ms = 0;
     int grain_on = 0;
     int lr_rows[3] = {0, 0, 0}, lr_cols[3] = {0, 0, 0}, lr_has[3] = {0, 0, 0};
-    std::vector<SbRowItem> items_host;
 };
 
 static void fill_params(const SeqHdr& seq, const FrameWork& fw, DevFrameParams& fp) {
@@ -172,39 +171,9 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     int n_order = 0;
     for (const TxRec& r : fw.tx) n_order += r.eob > 0;
     L.n_order = n_order;
-    L.n_sbs = (int)fw.sbs.size();
-    // work items = runs of 64x64 units sharing (tile, sb_row); units are stored tile by tile, SB row by SB row
-    dw.items_host.clear();
-    for (int i = 0; i < L.n_sbs;) {
-        int j = i;
-        while (j < L.n_sbs && fw.sbs[j].sb_row == fw.sbs[i].sb_row && fw.sbs[j].tile_sb_col0 == fw.sbs[i].tile_sb_col0 &&
-               fw.sbs[j].tile_sb_row0 == fw.sbs[i].tile_sb_row0)
-            j++;
-        SbRowItem it;
-        it.first_unit = (uint32_t)i;
-        it.n_units = (uint32_t)(j - i);
-        it.n_sb = (uint32_t)(fw.sbs[i].tile_sb_col1 - fw.sbs[i].tile_sb_col0);
-        it.frame = 0;
-        it.dep_item = -1;
-        if (fw.sbs[i].sb_row > fw.sbs[i].tile_sb_row0) {
-            for (int k = (int)dw.items_host.size() - 1; k >= 0; k--) {
-                const SbRange& a = fw.sbs[dw.items_host[k].first_unit];
-                if (a.tile_sb_col0 == fw.sbs[i].tile_sb_col0 && a.tile_sb_row0 == fw.sbs[i].tile_sb_row0 && a.sb_row + 1 == fw.sbs[i].sb_row) {
-                    it.dep_item = k;
-                    break;
-                }
-            }
-        }
-        dw.items_host.push_back(it);
-        i = j;
-    }
-    L.n_items = (int)dw.items_host.size();
     L.recs = take(sizeof(TxRec) * std::max(1, L.n_recs));
     L.coefs = take(sizeof(uint32_t) * std::max(1, L.n_coefs));
     L.order = take(sizeof(uint32_t) * std::max(1, L.n_order));
-    L.sbs = take(sizeof(SbRange) * std::max(1, L.n_sbs));
-    L.items = take(sizeof(SbRowItem) * std::max(1, L.n_items));
-    L.iframe = take(sizeof(IntraFrame));
     for (int p = 0; p < 3; p++) L.lf[p] = take(sizeof(LfEdge) * std::max<size_t>(1, fw.lf[p].size()));
     L.cdef_idx = take(std::max<size_t>(1, fw.cdef_idx.size()));
     L.skip_mi = take(std::max<size_t>(1, fw.skip_mi.size()));
@@ -221,6 +190,10 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     L.obmc = take(sizeof(ObmcNb) * std::max(1, L.n_obmc));
     L.warps = take(sizeof(WarpRec) * std::max(1, L.n_warps));
     L.pal = take(std::max<size_t>(4, fw.pal.size()));
+    int n_k3 = 0;
+    for (const TxRec& r : fw.tx) n_k3 += (r.mode != TXM_INTER) || (r.flags & TXF_II);
+    L.n_k3 = n_k3;
+    L.k3order = take(sizeof(uint32_t) * std::max(1, n_k3));
     L.total = o;
 }
 
@@ -232,8 +205,6 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
     int k = 0;
     for (int i = 0; i < L.n_recs; i++)
         if (fw.tx[i].eob > 0) ord[k++] = (uint32_t)i;
-    if (L.n_sbs) memcpy(h + L.sbs, fw.sbs.data(), sizeof(SbRange) * L.n_sbs);
-    if (L.n_items) memcpy(h + L.items, dw.items_host.data(), sizeof(SbRowItem) * L.n_items);
     for (int p = 0; p < 3; p++)
         if (!fw.lf[p].empty()) memcpy(h + L.lf[p], fw.lf[p].data(), sizeof(LfEdge) * fw.lf[p].size());
     if (!fw.cdef_idx.empty()) memcpy(h + L.cdef_idx, fw.cdef_idx.data(), fw.cdef_idx.size());
@@ -244,6 +215,42 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
     if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
     if (L.n_warps) memcpy(h + L.warps, fw.warps.data(), sizeof(WarpRec) * L.n_warps);
     if (!fw.pal.empty()) memcpy(h + L.pal, fw.pal.data(), fw.pal.size());
+    {   // K3 order: records sorted (stably) by key = 4 * (sbx + 2 * sby) + z, (sbx, sby) = superblock coordinates and z = Z-index of
+        // the 64x64 unit inside a 128x128 superblock (0 for 64x64 superblocks); decode order inside a unit.  Every sample a record
+        // may read lies in a unit with a strictly smaller key or earlier in its own unit: the left superblock has base key - 4
+        // (this covers the below-left samples a 128x128 superblock may take from its left neighbour's bottom half), above-right
+        // base - 4, above base - 8.  "Wait only for lower positions" therefore stays deadlock-free while the ticket window
+        // advances along the superblock wavefront instead of along one superblock row.
+        uint32_t* k3 = (uint32_t*)(h + L.k3order);
+        TxRec* recs = (TxRec*)(h + L.recs);
+        const int sx1 = dw.fp.subx, sy1 = dw.fp.suby;
+        const int sb128 = dw.fp.sb128;
+        auto key_of = [&](const TxRec& r) -> int {
+            const int sx = r.plane ? sx1 : 0, sy = r.plane ? sy1 : 0;
+            const int ux = ((r.x4 * 4) << sx) >> 6, uy = ((r.y4 * 4) << sy) >> 6;
+            if (sb128) return 4 * ((ux >> 1) + 2 * (uy >> 1)) + ((uy & 1) << 1 | (ux & 1));
+            return 4 * (ux + 2 * uy);
+        };
+        std::vector<uint32_t> cnt(4096, 0);
+        for (int i = 0; i < L.n_recs; i++) {
+            const TxRec& r = fw.tx[i];
+            if (r.mode != TXM_INTER || (r.flags & TXF_II)) cnt[std::min(4095, key_of(r))]++;
+        }
+        uint32_t acc = 0;
+        for (auto& c : cnt) { const uint32_t t = c; c = acc; acc += t; }
+        for (int i = 0; i < L.n_recs; i++) {
+            const TxRec& r = fw.tx[i];
+            if (r.mode != TXM_INTER || (r.flags & TXF_II)) k3[cnt[std::min(4095, key_of(r))]++] = (uint32_t)i;
+        }
+        // explicit dependency of inter-intra residual records on their blend record (position in K3 order)
+        uint32_t blend_pos[3] = {0, 0, 0};
+        for (int n = 0; n < L.n_k3; n++) {
+            TxRec& r = recs[k3[n]];
+            if (!(r.flags & TXF_II)) continue;
+            if (r.mode != TXM_INTER) blend_pos[r.plane] = (uint32_t)n;
+            else r.pal_off = blend_pos[r.plane];
+        }
+    }
 }
 
 // Execution resources of one in-flight frame.
@@ -253,12 +260,14 @@ struct FrameSlot {
     PinBuf staging;
     DevBuf arena;        // submit path: the frame's work-lists
     DevBuf residual;
-    DevBuf sync;         // progress counters + ticket
+    DevBuf sync;         // K3 done flags + ticket
+    DevBuf wmap;         // K3 owner map (int32 per 4x4 cell, 3 planes)
     DevBuf grain_scratch;
     DevBuf cks_dev;
     PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
     PinBuf planes_host;
     bool busy = false;
+    bool k3_heavy = false;   // the frame queued on this slot has a large intra (K3) record list
     // frame buffers touched by the work queued on this slot: kept alive (out of the recycling pool)
     // until the slot's completion event has been waited on
     std::vector<std::shared_ptr<DevFrameBuf>> hold;
@@ -330,6 +339,7 @@ struct EngineImpl {
     std::vector<std::shared_ptr<DevFrameBuf>> kept;   // keep_frames handles
     std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
     DevBuf wedge_master;                              // 6 x 64 x 64 wedge master masks (inter-intra blends in K3)
+    int k3_ctas = 0;                                  // ticket window of the K3 dataflow kernel in 2-warp CTAs; 0 = adaptive (AV1R_K3_CTAS)
     int64_t frames_decoded = 0;
 
     int wait_slot(FrameSlot& s);
@@ -390,21 +400,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         CK(s.residual.ensure((size_t)units_x * units_y * off * sizeof(int16_t)));
         res.base = (int16_t*)s.residual.p;
     }
-    CK(s.sync.ensure(sizeof(int) * (L.n_items + 4)));
-    CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_items + 4), st));
-    // intra frame descriptor lives in the arena (device pointers patched here)
-    IntraFrame ifr;
-    ifr.recs = (const TxRec*)(d_arena + L.recs);
-    ifr.sbs = (const SbRange*)(d_arena + L.sbs);
-    ifr.frame = recon->pl;
-    ifr.res = res;
-    ifr.fp = fp;
-    ifr.inter_frame = L.n_inter > 0;
-    ifr.wedge_master = wedge_master.p;
-    ifr.pal = d_arena + L.pal;
-    CK(cudaMemcpyAsync((void*)(d_arena + L.iframe), &ifr, sizeof(ifr), cudaMemcpyHostToDevice, st));
+    const TxRec* d_recs = (const TxRec*)(d_arena + L.recs);
     if (tm) tm->begin(st);
-    CK(launch_itx(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
+    CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, L.n_order > 0, st);
     if (L.n_inter > 0) {
         InterLaunch xl;
@@ -431,18 +429,40 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.fp = fp;
         CK(launch_inter(xl, st));
         if (tm) tm->end(AV1R_ST_INTER, 1, st);
-        CK(launch_inter_residual(ifr.recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
+        CK(launch_inter_residual(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
         if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
     }
-    IntraLaunch il;
-    il.frames = (const IntraFrame*)(d_arena + L.iframe);
-    il.items = (const SbRowItem*)(d_arena + L.items);
-    il.progress = (int*)s.sync.p;
-    il.ticket = (int*)s.sync.p + L.n_items;
-    il.n_items = L.n_items;
-    il.smem_per_warp = 0;
-    CK(launch_intra(il, fp.bd, fp.subx, fp.suby, st));
-    if (tm) tm->end(AV1R_ST_INTRA, L.n_items > 0, st);
+    if (L.n_k3 > 0) {
+        IntraLaunch il;
+        il.recs = d_recs;
+        il.order = (const uint32_t*)(d_arena + L.k3order);
+        il.n = L.n_k3;
+        // ticket window: a lone intra-heavy frame gets (almost) the whole machine, several concurrent ones share it -- spinning
+        // warps of one frame must not crowd out the runnable records of the others
+        s.k3_heavy = L.n_k3 > 8192;
+        int heavy = 0;
+        for (auto& o : slots) heavy += (o->busy || o.get() == &s) && o->k3_heavy;
+        il.ctas = k3_ctas > 0 ? k3_ctas : std::max(148, std::min(1184, 2368 / std::max(1, heavy)));
+        size_t moff[3], mtotal = 0;
+        for (int p = 0; p < 3; p++) {
+            moff[p] = mtotal;
+            mtotal += align_up(sizeof(int32_t) * (size_t)fp.pw4[p] * fp.ph4[p], 256);
+        }
+        CK(s.wmap.ensure(mtotal));
+        CK(cudaMemsetAsync(s.wmap.p, 0xFF, mtotal, st));
+        for (int p = 0; p < 3; p++) il.wmap[p] = (int32_t*)(s.wmap.p + moff[p]);
+        CK(s.sync.ensure(sizeof(int) * (L.n_k3 + 4)));
+        CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_k3 + 4), st));
+        il.flags = (int*)s.sync.p;
+        il.ticket = (int*)s.sync.p + L.n_k3;
+        il.frame = recon->pl;
+        il.res = res;
+        il.fp = fp;
+        il.wedge_master = wedge_master.p;
+        il.pal = d_arena + L.pal;
+        CK(launch_intra(il, st));
+    }
+    if (tm) tm->end(AV1R_ST_INTRA, L.n_k3 > 0 ? 2 : 0, st);
     std::shared_ptr<DevFrameBuf> cur = recon;
     if (dw.lf_on && (cfg.inloop_filters & 1)) {
         LfLaunch ll;
@@ -718,6 +738,7 @@ int Engine::open(const av1r_config& cfg) {
         CK(cudaEventCreate(&s->ev1));
         E.slots.push_back(std::move(s));
     }
+    if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));
     CK(E.wedge_master.ensure(6 * 64 * 64));
     CK(inter_copy_wedge_master(E.wedge_master.p, E.streams[0]));
     CK(cudaStreamSynchronize(E.streams[0]));

@@ -1,24 +1,23 @@
-// K3 -- intra prediction + residual add, wavefront over superblock rows with the current 64x64 unit
-// resident in shared memory (AV1 spec 7.11.2, 7.11.5, 7.12.3).
+// K3 -- intra prediction + residual add as a *record-level dataflow* kernel (AV1 spec 7.11.2, 7.11.4, 7.11.5, 7.12.3).
 //
-// Intra prediction reads *reconstructed* neighbours and the decode order inside a superblock is a
-// Z-order whose bottom-left quadrant depends on the top-right one, so the blocks of a superblock form
-// one long dependency chain; the only parallelism is across superblock rows (row r may process SB c once
-// row r-1 has finished SB c+1), across tiles and across frames.  What can be optimised is the *latency
-// of one link of the chain*: one warp owns one (tile, SB row) item and keeps the 64x64 luma unit (+ its
-// chroma) it is working on in shared memory together with the row above / column left of the unit
-// (loaded from HBM/L2 once per unit), so the neighbour fetches of every block are shared-memory reads
-// instead of L2 round trips; reconstructed samples are written through to the frame in HBM.
-// Inter-row hand-off: per-item progress counters (release: __threadfence + store, acquire: volatile
-// load + __threadfence); halo reads use ld.cg so a stale L1 line can never be observed.  Items are
-// claimed through an atomic ticket, so a warp only waits on items that are already running.
-// v4: the chain link is kept off HBM/L2 latency entirely -- the unit's int16 residual (12 KB, unit-major layout written by K1),
-// the unit's 32-byte records (chunks of 64) and the item's unit table are brought into shared memory by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx), double-buffered so that unit k+1 / chunk q+1 are in flight while unit k / chunk q
-// are being reconstructed; a block then costs shared-memory reads, ALU work and fire-and-forget stores only.
-// Algorithmic bytes: F_intra written + 2A residual read + 32 B/record; halos are L2 hits.
+// Intra prediction reads reconstructed neighbours, so transform blocks form a dependency DAG: a block needs the blocks that
+// own its above row (plus above-right when the mode looks there), its left column (plus below-left) and, for CfL, the luma
+// blocks under it.  Walking the blocks of a superblock row in decode order (v1-v4 of this kernel) serialises ~5000 blocks per
+// row although the DAG is only a few hundred blocks deep (a 2:1 wavefront at *block* granularity).  v5 therefore gives every
+// record to its own warp:
+//   1. `wmap_scatter_kernel` writes, for every 4x4 cell of every plane, the position (in K3 order) of the record that
+//      reconstructs it (atomicMax: for inter-intra blocks the residual record wins over the blend record).
+//   2. `intra_dataflow_kernel`: persistent warps claim records in decode order through an atomic ticket, look up the owners of
+//      the edge cells they are about to read, spin (with back-off) on those owners' done-flags, predict, add the residual,
+//      store, fence and raise their own flag.  A warp only ever waits for lower tickets, which are held by resident warps, so
+//      the lowest unfinished record can always run: no deadlock, no host-built dependency lists.
+// Edge samples come from L2 (ld.global.cg; the frame is being written by other SMs), the residual from K1's unit-major
+// buffer.  The critical path is the DAG depth (W/bw + 2H/bh blocks) times one L2 round trip, instead of the record count.
+// Algorithmic bytes: F_intra written + 2A residual read + 32 B/record (+ edge re-reads, all L2 hits).
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <algorithm>
 
 #include "../av1_consts.h"
 #include "dev_common.cuh"
@@ -41,7 +40,7 @@ __constant__ uint8_t c_ii_blk_w[BLOCK_SIZES_ALL];
 __constant__ uint8_t c_ii_blk_h[BLOCK_SIZES_ALL];
 static bool g_intra_const_loaded[64] = {false};
 
-static constexpr int INTRA_WARPS = 4;
+static constexpr int INTRA_WARPS = 2;
 static constexpr int EDGE_PAD = 16;
 static constexpr int EDGE_LEN = EDGE_PAD + 2 * 129 + 16;   // room for upsampled edges (index -2 .. 2*(w+h))
 
@@ -49,46 +48,16 @@ struct IntraSmem {
     int32_t above[2][EDGE_LEN];
     int32_t left[2][EDGE_LEN];
     int16_t tile[64 * 64 / 4];   // 32x32 int16: filter-intra predictions / CfL luma terms
+    int16_t res[256];            // residual of blocks up to 256 samples, fetched before the dependency wait
 };
 
-// The 64x64 unit being reconstructed, resident in shared memory (per warp).
+// Samples of the frame under reconstruction, read through L2 (other SMs are writing it).
 template <typename T>
-struct UnitView {
-    T* tile[3];        // [th][tw] samples of the unit
-    T* above[3];       // index -1 .. 2*tw-1 : frame row just above the unit
-    T* left[3];        // index 0 .. 2*th-1  : frame column just left of the unit
-    int ux0[3], uy0[3], tw[3], th[3];
-    __device__ __forceinline__ int px(int plane, int x, int y) const {
-        const int dx = x - ux0[plane], dy = y - uy0[plane];
-        if (dy < 0) return above[plane][dx];
-        if (dx < 0) return left[plane][dy];
-        return tile[plane][dy * tw[plane] + dx];
-    }
+struct FrameView {
+    const uint8_t* p[3];
+    uint32_t pitch[3];
+    __device__ __forceinline__ int px(int plane, int x, int y) const { return (int)__ldcg((const T*)(p[plane] + (size_t)y * pitch[plane]) + x); }
 };
-
-// ---- TMA bulk copy + mbarrier helpers (sm_90+; SASS UBLKCP / SYNCS)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-static constexpr int REC_CHUNK = 64;     // records per bulk copy
-static constexpr int SBS_CAP = 128;      // unit descriptors staged per item
 
 template <typename T>
 __device__ __forceinline__ int ldpx(const uint8_t* base, uint32_t pitch, int x, int y) {
@@ -180,8 +149,8 @@ __device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int
 }
 
 template <typename T>
-__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const int16_t* res_s, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
-                            const UnitView<T>& uv, int lane, const uint8_t* wedge_master, const uint8_t* pal) {
+__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
+                            const FrameView<T>& uv, int lane, const uint8_t* wedge_master, const uint8_t* pal) {
     const int plane = r.plane;
     const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
     const int w = 1 << lw, h = 1 << lh;
@@ -190,26 +159,23 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const int16_t* 
     const int max_x = fp.cw[plane] - 1, max_y = fp.ch[plane] - 1;
     const uint32_t pitch = fr.pitch[plane];
     const int xe = min(w, fp.cw[plane] - x), ye = min(h, fp.ch[plane] - y);
-    T* tl = uv.tile[plane] + (y - uv.uy0[plane]) * uv.tw[plane] + (x - uv.ux0[plane]);
-    const int tpitch = uv.tw[plane];
     T* out = (T*)(fr.p[plane] + (size_t)y * pitch) + x;
     const int opitch = pitch / sizeof(T);
-    // residual of the unit, resident in shared memory (same tile geometry as the sample tile)
-    const int16_t* rp = res_s + res.plane_off[plane] + (y - uv.uy0[plane]) * uv.tw[plane] + (x - uv.ux0[plane]);
-    const int rpitch = uv.tw[plane];
     const bool has_res = r.eob > 0;
+    const bool res_pre = (w * h) <= 256;     // prefetched into sm.res (row-major w x h) by the caller
+    const int16_t* rp = res_pre ? sm.res : res_ptr(res, plane, x, y);
+    const int rpitch = res_pre ? w : (1 << res.tw_log2[plane]);
     const bool ii = (r.flags & TXF_II) != 0;
     const int ii_pk = (uint16_t)r.cfl_alpha;
     const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
     auto emit = [&](int i, int j, int v) {
         if (i < ye && j < xe) {
-            if (ii) {   // blend the intra predictor over the inter predictor already in the unit
+            if (ii) {   // blend the intra predictor over the inter predictor K2 left in the frame
                 const int m = ii_mask(ii_pk, wedge_master, i, j, w, h, psx, psy);
-                v = (m * v + (64 - m) * (int)tl[i * tpitch + j] + 32) >> 6;
+                v = (m * v + (64 - m) * (int)__ldcg(out + i * opitch + j) + 32) >> 6;
             }
             if (has_res) v = min(max(v + (int)rp[i * rpitch + j], 0), pixmax);
             out[i * opitch + j] = (T)v;
-            tl[i * tpitch + j] = (T)v;
         }
     };
     if (r.mode == TXM_INTER) {
@@ -218,10 +184,8 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const int16_t* 
             for (int idx = lane; idx < w * h; idx += 32) {
                 const int i = idx >> lw, j = idx & (w - 1);
                 if (i < ye && j < xe) {
-                    int v = (int)tl[i * tpitch + j] + (int)rp[i * rpitch + j];
-                    v = min(max(v, 0), pixmax);
-                    out[i * opitch + j] = (T)v;
-                    tl[i * tpitch + j] = (T)v;
+                    int v = (int)__ldcg(out + i * opitch + j) + (int)rp[i * rpitch + j];
+                    out[i * opitch + j] = (T)min(max(v, 0), pixmax);
                 }
             }
         return;
@@ -474,166 +438,138 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const int16_t* 
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(INTRA_WARPS * 32) intra_wavefront_kernel(IntraLaunch L) {
-    extern __shared__ __align__(128) uint8_t s_raw[];
-    const int warp_in = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* wbase = s_raw + (size_t)warp_in * L.smem_per_warp;
-    // per-warp shared memory: [residual x2][records x2][unit table][barriers][IntraSmem][sample tiles + halos]
-    const DevFrameParams& fp0 = L.frames[0].fp;
-    const int unit_elems = L.frames[0].res.unit_elems;
-    const uint32_t unit_bytes = (uint32_t)unit_elems * 2;
-    int16_t* res_s[2] = {reinterpret_cast<int16_t*>(wbase), reinterpret_cast<int16_t*>(wbase + unit_bytes)};
-    TxRec* rec_s[2];
-    rec_s[0] = reinterpret_cast<TxRec*>(wbase + 2 * unit_bytes);
-    rec_s[1] = rec_s[0] + REC_CHUNK;
-    SbRange* sbs_s = reinterpret_cast<SbRange*>(rec_s[1] + REC_CHUNK);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sbs_s + SBS_CAP);   // [0,1] residual, [2,3] records, [4] unit table
-    IntraSmem& sm = *reinterpret_cast<IntraSmem*>(bars + 8);
-    UnitView<T> uv;
-    {
-        T* p = reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(&sm) + sizeof(IntraSmem));
-        for (int pl = 0; pl < 3; pl++) {
-            const int sx = pl ? fp0.subx : 0, sy = pl ? fp0.suby : 0;
-            uv.tw[pl] = 64 >> sx;
-            uv.th[pl] = 64 >> sy;
-            uv.tile[pl] = p;
-            p += uv.tw[pl] * uv.th[pl];
-            uv.above[pl] = p + 8;            // index -1 valid
-            p += 2 * uv.tw[pl] + 16;
-            uv.left[pl] = p;
-            p += 2 * uv.th[pl] + 8;
-        }
+// 1. owner map: position (K3 order) of the record that reconstructs each 4x4 cell
+__global__ void __launch_bounds__(128) wmap_scatter_kernel(IntraLaunch L) {
+    const int pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (pos >= L.n) return;
+    const TxRec r = L.recs[L.order[pos]];
+    const int plane = r.plane;
+    const int w4 = 1 << (c_itxw_log2[r.txsz] - 2), h4 = 1 << (c_itxh_log2[r.txsz] - 2);
+    const int pw4 = L.fp.pw4[plane], ph4 = L.fp.ph4[plane];
+    int32_t* m = L.wmap[plane];
+    for (int c = lane; c < w4 * h4; c += 32) {
+        const int cy = r.y4 + c / w4, cx = r.x4 + c % w4;
+        if (cx < pw4 && cy < ph4) atomicMax(m + (size_t)cy * pw4 + cx, pos);
     }
-    const uint32_t bar0 = smem_u32(bars);
-    if (lane == 0) {
-        for (int i = 0; i < 5; i++) mbar_init(bar0 + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void wait_flag(const int* flags, int id) {
+    const volatile int* f = flags + id;
+    int ns = 32;
+    while (*f == 0) {
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
     }
-    __syncwarp();
-    uint32_t par = 0;   // bit i = parity to wait for on barrier i
+}
+
+// Warp-collective wait: every lane names one owner position (or -1).  All pending flags are sampled once per round with a
+// single warp-wide load; only lane 0 then spins, on the highest pending position (the one most likely to finish last), so a
+// waiting warp costs L2 one poll per back-off period instead of one per lane.
+__device__ __forceinline__ void wait_deps_warp(const int* flags, int id, int lane) {
     while (true) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(L.ticket, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= L.n_items) return;
-        const SbRowItem it = L.items[item];
-        const IntraFrame& F = L.frames[it.frame];
-        const DevFrameParams& fp = F.fp;
-        const int nplanes = fp.mono ? 1 : 3;
-        const int n_units = (int)it.n_units;
-        volatile int* dep = it.dep_item >= 0 ? (volatile int*)(L.progress + it.dep_item) : nullptr;
-        // ---- stage the item's unit table, then start the first residual / record transfers
-        const int n_tab = min(n_units, SBS_CAP);
-        if (lane == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(bar0 + 32, (uint32_t)(n_tab * sizeof(SbRange)));
-            bulk_g2s(smem_u32(sbs_s), F.sbs + it.first_unit, (uint32_t)(n_tab * sizeof(SbRange)), bar0 + 32);
-        }
-        mbar_wait(bar0 + 32, (par >> 4) & 1);
-        par ^= 16;
-        auto unit_desc = [&](int k) -> SbRange { return k < SBS_CAP ? sbs_s[k] : F.sbs[it.first_unit + k]; };
-        auto issue_res = [&](int k) {
-            const SbRange u = unit_desc(k);
-            if (lane == 0) {
-                fence_proxy_async();
-                mbar_expect_tx(bar0 + 8 * (k & 1), unit_bytes);
-                bulk_g2s(smem_u32(res_s[k & 1]), F.res.base + ((size_t)u.uy * F.res.units_x + u.ux) * unit_elems, unit_bytes, bar0 + 8 * (k & 1));
-            }
-        };
-        int ld_unit = 0, ld_chunk = 0, q_load = 0, q_use = 0;
-        auto issue_rec = [&]() {
-            if (ld_unit >= n_units) return;
-            const SbRange u = unit_desc(ld_unit);
-            const int first = (int)u.first + ld_chunk * REC_CHUNK;
-            const int cnt = min(REC_CHUNK, (int)u.count - ld_chunk * REC_CHUNK);
-            if (lane == 0) {
-                fence_proxy_async();
-                mbar_expect_tx(bar0 + 16 + 8 * (q_load & 1), (uint32_t)(cnt * sizeof(TxRec)));
-                bulk_g2s(smem_u32(rec_s[q_load & 1]), F.recs + first, (uint32_t)(cnt * sizeof(TxRec)), bar0 + 16 + 8 * (q_load & 1));
-            }
-            q_load++;
-            ld_chunk++;
-            if (ld_chunk * REC_CHUNK >= (int)u.count) {
-                ld_unit++;
-                ld_chunk = 0;
-            }
-        };
+        const bool pend = id >= 0 && *(const volatile int*)(flags + id) == 0;
+        if (!__any_sync(0xffffffffu, pend)) return;
+        const int mx = __reduce_max_sync(0xffffffffu, pend ? id : -1);
+        if (lane == 0) wait_flag(flags, mx);
         __syncwarp();
-        issue_res(0);
-        issue_rec();
-        int sb_done = 0;
-        for (int k = 0; k < n_units; k++) {
-            const SbRange un = unit_desc(k);
-            __syncwarp();
-            if (k + 1 < n_units) issue_res(k + 1);   // buffer (k+1)&1 was last read by unit k-1
-            const bool first_of_sb = (k == 0) || (unit_desc(k - 1).sb_col != un.sb_col);
-            if (first_of_sb && dep) {
-                const int c = un.sb_col - un.tile_sb_col0;
-                const int need = min(c + 2, (int)it.n_sb);
-                if (lane == 0)
-                    while (*dep < need) __nanosleep(32);
-                __syncwarp();
-            }
-            __threadfence();
-            // ---- load the halo of the unit: row above (-1 .. 2tw-1) and column left (0 .. 2th-1)
-            for (int pl = 0; pl < nplanes; pl++) {
-                const int sx = pl ? fp.subx : 0, sy = pl ? fp.suby : 0;
-                const int ux0 = (un.ux * 64) >> sx, uy0 = (un.uy * 64) >> sy;
-                uv.ux0[pl] = ux0;
-                uv.uy0[pl] = uy0;
-                const T* base = (const T*)F.frame.p[pl];
-                const int pe = F.frame.pitch[pl] / sizeof(T);
-                const int max_x = fp.cw[pl] - 1, max_y = fp.ch[pl] - 1;
-                if (uy0 > 0)
-                    for (int i = lane - 1; i < 2 * uv.tw[pl]; i += 32) {
-                        const int x = min(max(ux0 + i, 0), max_x);
-                        uv.above[pl][i] = __ldcg(base + (size_t)(uy0 - 1) * pe + x);
-                    }
-                if (ux0 > 0)
-                    for (int i = lane; i < 2 * uv.th[pl]; i += 32) {
-                        const int y = min(uy0 + i, max_y);
-                        uv.left[pl][i] = __ldcg(base + (size_t)y * pe + ux0 - 1);
-                    }
-                if (F.inter_frame) {
-                    // inter-predicted (and residual-added) samples of this unit were produced by K2: bring them on chip
-                    const int tw = uv.tw[pl], th = uv.th[pl];
-                    for (int i = lane; i < tw * th; i += 32) {
-                        const int yy = i / tw, xx = i - yy * tw;
-                        uv.tile[pl][i] = __ldcg(base + (size_t)min(uy0 + yy, max_y) * pe + min(ux0 + xx, max_x));
-                    }
-                }
-            }
-            mbar_wait(bar0 + 8 * (k & 1), (par >> (k & 1)) & 1);
-            par ^= 1u << (k & 1);
-            __syncwarp();
-            const int16_t* rs = res_s[k & 1];
-            for (int c0 = 0; c0 < (int)un.count; c0 += REC_CHUNK) {
-                const int qb = q_use & 1;
-                mbar_wait(bar0 + 16 + 8 * qb, (par >> (2 + qb)) & 1);
-                par ^= 4u << qb;
-                __syncwarp();
-                issue_rec();                              // next chunk -> the buffer chunk q_use-1 used
-                const int cnt = min(REC_CHUNK, (int)un.count - c0);
-                const TxRec* rb = rec_s[qb];
-                for (int t = 0; t < cnt; t++) {
-                    intra_block<T>(rb[t], F.frame, rs, F.res, fp, sm, uv, lane, F.wedge_master, F.pal);
-                    __syncwarp();
-                }
-                q_use++;
-            }
-            const bool last_of_sb = (k + 1 == n_units) || (unit_desc(k + 1).sb_col != un.sb_col);
-            if (last_of_sb) {
-                __threadfence();
-                __syncwarp();
-                sb_done = un.sb_col - un.tile_sb_col0 + 1;
-                if (lane == 0) *(volatile int*)(L.progress + item) = sb_done;
+    }
+}
+
+// 2. the dataflow kernel
+template <typename T>
+__global__ void __launch_bounds__(INTRA_WARPS * 32) intra_dataflow_kernel(IntraLaunch L) {
+    __shared__ IntraSmem s_sm[INTRA_WARPS];
+    const int warp_in = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    IntraSmem& sm = s_sm[warp_in];
+    const DevFrameParams& fp = L.fp;
+    FrameView<T> uv;
+    for (int pl = 0; pl < 3; pl++) {
+        uv.p[pl] = L.frame.p[pl];
+        uv.pitch[pl] = L.frame.pitch[pl];
+    }
+    while (true) {
+        // persistent warps claim records in K3 order; the grid (L.ctas) bounds the ticket window of one frame so that the frames
+        // in flight on other streams share the machine instead of one frame's spinning warps monopolising it
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(L.ticket, 1);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (pos >= L.n) return;
+        __syncwarp();
+        const TxRec r = L.recs[L.order[pos]];
+        // residual of small blocks: fetch now (it has no dependency), so it is off the critical path after the wait
+        if (r.eob > 0) {
+            const int lw = c_itxw_log2[r.txsz], w = 1 << lw, n = w << c_itxh_log2[r.txsz];
+            if (n <= 256) {
+                const int16_t* rp = res_ptr(L.res, r.plane, r.x4 * 4, r.y4 * 4);
+                const int rpitch = 1 << L.res.tw_log2[r.plane];
+                for (int idx = lane; idx < n; idx += 32) sm.res[idx] = __ldg(rp + (idx >> lw) * rpitch + (idx & (w - 1)));
             }
         }
-        // superblocks without any intra record never appear in the list: publish the full row at the end
-        __threadfence();
+        // ---- wait for the owners of everything this record reads
+        if (r.mode == TXM_INTER) {
+            if (r.flags & TXF_II) {   // residual of an inter-intra block: after its blend record
+                if (lane == 0) wait_flag(L.flags, (int)r.pal_off);
+            }
+        } else if (r.mode != TXM_PALETTE) {
+            const int plane = r.plane;
+            const int w4 = 1 << (c_itxw_log2[r.txsz] - 2), h4 = 1 << (c_itxh_log2[r.txsz] - 2);
+            const int pw4 = fp.pw4[plane], ph4 = fp.ph4[plane];
+            const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
+            int need_ar = 0, need_bl = 0;
+            if (r.mode >= V_PRED && r.mode <= D67_PRED) {
+                const int kModeToAngle[9] = {0, 90, 180, 45, 135, 113, 157, 203, 67};
+                const int p_angle = kModeToAngle[r.mode] + r.angle_delta * 3;
+                need_ar = p_angle < 90 && (r.flags & TXF_HAVE_ABOVE_RIGHT);
+                need_bl = p_angle > 180 && (r.flags & TXF_HAVE_BELOW_LEFT);
+            }
+            // V_PRED reads only the row above, H_PRED only the left column (unless that edge is missing and the other one stands in)
+            const int want_above = have_above && !(r.mode == H_PRED && r.angle_delta == 0 && have_left);
+            const int want_left = have_left && !(r.mode == V_PRED && r.angle_delta == 0 && have_above);
+            const int na = want_above ? w4 * (need_ar ? 2 : 1) + 1 : 0;      // cells x4-1 .. on row y4-1 (the first is the corner)
+            const int nl = want_left ? h4 * (need_bl ? 2 : 1) : 0;            // cells y4 .. on column x4-1
+            const int32_t* m = L.wmap[plane];
+            for (int c0 = 0; c0 < na + nl; c0 += 32) {       // warp-uniform trip count: the wait is collective
+                const int c = c0 + lane;
+                int id = -1;
+                if (c < na + nl) {
+                    int cx, cy;
+                    if (c < na) {
+                        cx = r.x4 - 1 + c;
+                        cy = r.y4 - 1;
+                    } else {
+                        cx = r.x4 - 1;
+                        cy = r.y4 + (c - na);
+                    }
+                    cx = min(max(cx, 0), pw4 - 1);
+                    cy = min(max(cy, 0), ph4 - 1);
+                    id = __ldg(m + (size_t)cy * pw4 + cx);
+                    if (id >= pos) id = -1;
+                }
+                wait_deps_warp(L.flags, id, lane);
+            }
+            if (r.mode == TXM_CFL) {   // luma samples under this chroma block
+                const int sx = fp.subx, sy = fp.suby;
+                const int lx0 = (r.x4 << sx), ly0 = (r.y4 << sy);
+                const int lx1 = min((r.x4 + w4) << sx, (int)r.cfl_max_w4), ly1 = min((r.y4 + h4) << sy, (int)r.cfl_max_h4);
+                const int lw4 = max(lx1 - lx0, 0), lh4 = max(ly1 - ly0, 0);
+                const int lpw4 = fp.pw4[0];
+                for (int c0 = 0; c0 < lw4 * lh4; c0 += 32) {
+                    const int c = c0 + lane;
+                    int id = -1;
+                    if (c < lw4 * lh4) {
+                        id = __ldg(L.wmap[0] + (size_t)(ly0 + c / lw4) * lpw4 + lx0 + c % lw4);
+                        if (id >= pos) id = -1;
+                    }
+                    wait_deps_warp(L.flags, id, lane);
+                }
+            }
+        }
         __syncwarp();
-        if (lane == 0) *(volatile int*)(L.progress + item) = (int)it.n_sb;
+        __threadfence();   // acquire: the owners' samples are visible in L2
+        intra_block<T>(r, L.frame, L.res, fp, sm, uv, lane, L.wedge_master, L.pal);
+        __threadfence();   // release: this record's samples before its flag
+        __syncwarp();
+        if (lane == 0) *(volatile int*)(L.flags + pos) = 1;
     }
 }
 
@@ -656,45 +592,20 @@ static cudaError_t intra_upload_constants() {
     return cudaSuccess;
 }
 
-size_t intra_smem_per_warp(int bd, int subx, int suby) {
-    const size_t ts = bd == 8 ? 1 : 2;
-    size_t unit_elems = 0, n = 0;
-    for (int pl = 0; pl < 3; pl++) {
-        const int sx = pl ? subx : 0, sy = pl ? suby : 0;
-        const int tw = 64 >> sx, th = 64 >> sy;
-        unit_elems += (size_t)tw * th;
-        n += ts * (tw * th + 2 * tw + 16 + 2 * th + 8);
-    }
-    n += 2 * unit_elems * sizeof(int16_t) + 2 * REC_CHUNK * sizeof(TxRec) + SBS_CAP * sizeof(SbRange) + 8 * sizeof(uint64_t) + sizeof(IntraSmem);
-    return (n + 127) & ~(size_t)127;
-}
-
-cudaError_t launch_intra(const IntraLaunch& L_, int bd, int subx, int suby, cudaStream_t s) {
-    if (L_.n_items <= 0) return cudaSuccess;
+cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s) {
+    if (L.n <= 0) return cudaSuccess;
     cudaError_t e = intra_upload_constants();
     if (e != cudaSuccess) return e;
-    IntraLaunch L = L_;
-    L.smem_per_warp = (int)intra_smem_per_warp(bd, subx, suby);
-    const size_t smem = (size_t)L.smem_per_warp * INTRA_WARPS;
-    const int blocks = (L.n_items + INTRA_WARPS - 1) / INTRA_WARPS;
-    static bool attr_done[2] = {false, false};
-    if (bd == 8) {
-        auto k = intra_wavefront_kernel<uint8_t>;
-        if (!attr_done[0]) {
-            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return e;
-            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            attr_done[0] = true;
-        }
-        k<<<blocks, INTRA_WARPS * 32, smem, s>>>(L);
-    } else {
-        auto k = intra_wavefront_kernel<uint16_t>;
-        if (!attr_done[1]) {
-            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return e;
-            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            attr_done[1] = true;
-        }
-        k<<<blocks, INTRA_WARPS * 32, smem, s>>>(L);
+    wmap_scatter_kernel<<<(L.n + 3) / 4, 128, 0, s>>>(L);
+    const int blocks = std::min((L.n + INTRA_WARPS - 1) / INTRA_WARPS, std::max(1, L.ctas));
+    static bool attr_done = false;
+    if (!attr_done) {   // 14 KB of static shared memory per 2-warp CTA: ask for the large carve-out so 15 CTAs fit per SM
+        cudaFuncSetAttribute(intra_dataflow_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(intra_dataflow_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_done = true;
     }
+    if (L.fp.bd == 8) intra_dataflow_kernel<uint8_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
+    else intra_dataflow_kernel<uint16_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
     return cudaGetLastError();
 }
 

@@ -6,34 +6,22 @@
 
 namespace av1r {
 
-struct IntraFrame {            // one per frame in the batch (device array)
-    const TxRec* recs;
-    const SbRange* sbs;
+struct IntraLaunch {            // passed by value
+    const TxRec* recs;          // device, all records of the frame
+    const uint32_t* order;      // device, K3 order: indices of the records K3 owns (intra, palette, inter-intra blend + residual)
+    int n;                      // entries in order
+    int ctas;                   // persistent CTAs (2 warps each) this frame may occupy = its ticket window / 2
+    int32_t* wmap[3];           // device, per plane [ph4][pw4]: owner position of every 4x4 cell, pre-set to -1
+    int* flags;                 // device, n ints, zeroed before launch: done flag per position
+    int* ticket;                // device, one int, zeroed before launch
     DevPlanes frame;
     DevResidual res;
     DevFrameParams fp;
-    int inter_frame;               // 1: units start from the K2 output (inter predictor + residual) instead of nothing
     const uint8_t* wedge_master;   // device, 6 x 64 x 64 (inter-intra wedge blends)
     const uint8_t* pal;            // device, palette entries (colours + colour index maps)
 };
 
-struct SbRowItem {             // one (tile, superblock row): the work item a warp owns
-    uint32_t first_unit, n_units;   // 64x64 unit ranges in IntraFrame::sbs (decode order)
-    uint32_t n_sb;             // superblocks in this tile row (progress counts completed superblocks)
-    int32_t dep_item;          // item index of the superblock row above in the same tile, -1 if none
-    int32_t frame;             // index into IntraLaunch::frames
-};
-
-struct IntraLaunch {
-    const IntraFrame* frames;  // device
-    const SbRowItem* items;    // device, ordered so that dep_item < own index
-    int* progress;             // device, n_items ints, zeroed before launch
-    int* ticket;               // device, one int, zeroed before launch
-    int n_items;
-    int smem_per_warp;         // filled by launch_intra
-};
-
-cudaError_t launch_intra(const IntraLaunch& L, int bd, int subx, int suby, cudaStream_t s);
+cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s);
 cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, const uint32_t* coefs, const DevResidual& res,
                        const DevFrameParams& fp, cudaStream_t s);
 
