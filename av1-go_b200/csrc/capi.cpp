@@ -1,4 +1,5 @@
 // C ABI glue that needs no GPU (version / defaults).
+#include <cstdio>
 #include <cstring>
 
 #include "../../include/av1r.h"
@@ -17,4 +18,87 @@ extern "C" void av1r_default_config(av1r_config* cfg) {
     cfg->inloop_filters = 7;
     cfg->keep_frames = 0;
     cfg->host_threads = 0;
+}
+
+// ---- host-only: demux + sequential symbol parse of a whole container, no device work (measurement / diagnostics).
+// This is the stage north_star asks to be timed separately; it mirrors the host half of av1r_verify_buffer
+// (GOP segments on host_threads workers, tiles of a frame on the process-wide pool).
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+#include "demux.h"
+#include "parallel.h"
+#include "stream_parser.h"
+
+extern "C" int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threads, int tile_threads, av1r_report* out) {
+    using namespace av1r;
+    if (!data || !out) return AV1R_EINVAL;
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    out->first_bad_frame = -1;
+    DemuxResult dm;
+    std::string derr;
+    if (!demux_buffer(data, len, dm, derr)) {
+        snprintf(out->message, sizeof(out->message), "%s", derr.c_str());
+        return out->status = AV1R_EBITSTREAM;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    // segment starts: temporal units whose first frame is a shown key frame
+    HeaderParser scan;
+    std::vector<size_t> starts;
+    for (size_t i = 0; i < dm.tus.size(); i++) {
+        std::vector<ObuUnit> obus;
+        if (!scan.split_obus(data + dm.tus[i].offset, dm.tus[i].size, obus)) break;
+        bool first = true;
+        for (const ObuUnit& u : obus) {
+            if (u.type == OBU_SEQUENCE_HEADER) scan.parse_sequence_header(u.data, u.size);
+            else if (u.type == OBU_FRAME || u.type == OBU_FRAME_HEADER) {
+                BitReader br(u.data, u.size);
+                FrameHdr fh;
+                if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) break;
+                if (first && !fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
+                if (!fh.show_existing_frame) scan.reference_update(fh);
+                first = false;
+            }
+        }
+    }
+    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+    const int nseg = (int)starts.size();
+    int nthreads = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+    nthreads = std::max(1, std::min(nthreads, nseg));
+    std::atomic<int> next{0}, rc_all{0};
+    std::atomic<long long> frames{0};
+    std::vector<double> parse_ms(nseg, 0.0);
+    auto worker = [&]() {
+        while (true) {
+            const int s = next.fetch_add(1);
+            if (s >= nseg) return;
+            StreamParser sp;
+            sp.hp.seq = scan.seq;
+            sp.tile_threads = tile_threads != 0;
+            const size_t t1 = s + 1 < nseg ? starts[s + 1] : dm.tus.size();
+            for (size_t t = starts[s]; t < t1; t++) {
+                std::vector<ParsedFrame> pfs;
+                const int rc = sp.parse_tu(data + dm.tus[t].offset, dm.tus[t].size, dm.tus[t].pts, pfs);
+                for (auto& pf : pfs) {
+                    if (pf.fw) parse_ms[s] += pf.fw->parse_ms;
+                    if (pf.show_existing_slot >= 0 || pf.fh.show_frame) frames++;
+                }
+                if (rc) { rc_all = rc; return; }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nthreads; i++) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (double v : parse_ms) out->host_parse_ms += v;
+    out->frames = frames;
+    out->frames_per_sec = out->wall_ms > 0 ? out->frames * 1000.0 / out->wall_ms : 0;
+    out->status = rc_all;
+    snprintf(out->message, sizeof(out->message), "parse only: %lld frames, %d GOP segments, %d segment threads, tile threads %s", (long long)out->frames, nseg,
+             nthreads, tile_threads ? "on" : "off");
+    return rc_all;
 }

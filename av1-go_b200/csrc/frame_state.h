@@ -5,6 +5,7 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "av1_consts.h"
@@ -78,6 +79,24 @@ struct LrUnit {
     int8_t sgr_xqd[2];
 };
 
+// What one tile's parse produces.  Tiles are independent given the frame's initial CDFs, so they are parsed concurrently, each
+// into its own TileOut; StreamParser merges the lists in tile order (offsets inside the records are rebased there).
+struct TileOut {
+    std::vector<TxRec> tx;
+    std::vector<uint32_t> coefs;
+    std::vector<SbRange> sbs;
+    std::vector<uint8_t> pal;
+    std::vector<InterBlk> inter;
+    std::vector<ObmcNb> obmc;
+    std::vector<WarpRec> warps;         // local warp models of this tile (InterBlk::warp = 8 + index until merged)
+    std::deque<BlockInfo> blocks;       // mode info storage; FrameWork::mi points into it
+    uint64_t coded_samples = 0, coef_tokens = 0, tx_blocks = 0, inter_samples = 0, inter_ref_samples = 0;
+    uint32_t tool_hist[24] = {0};
+    CdfCtx end_cdf;
+    int rc = 0;
+    std::string err;
+};
+
 // Everything the device needs for one frame + what the next frames need from the parse.
 struct FrameWork {
     FrameHdr fh;
@@ -106,7 +125,7 @@ struct FrameWork {
     // tool histogram (blocks): see TOOL_* below; reported by the bench so the exercised tool set is visible
     uint32_t tool_hist[24] = {0};   // predicted samples / reference samples fetched (roofline model)
     // mode info (host only)
-    std::deque<BlockInfo> blocks;
+    std::vector<std::unique_ptr<TileOut>> tiles;   // per-tile outputs (own the BlockInfo storage)
     std::vector<BlockInfo*> mi;         // per mi -> block
     std::vector<uint8_t> inter_tx;      // per mi: InterTxSizes
     std::vector<uint8_t> lf_tx[3];      // per plane 4x4: LoopfilterTxSizes
@@ -146,7 +165,7 @@ struct FrameWork {
         coefs.clear();
         sbs.clear();
         pal.clear();
-        blocks.clear();
+        tiles.clear();
         inter.clear();
         obmc.clear();
         warps.clear();

@@ -2,10 +2,12 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstddef>
 
 #include "../../include/av1r.h"
+#include "parallel.h"
 #include "tile.h"
 
 namespace av1r {
@@ -64,11 +66,18 @@ void cdf_clear_counters(CdfCtx& c) {
 #undef CLR
 }
 
+static double g_prof[8];
+struct ProfPrinter { ~ProfPrinter() { if (getenv("AV1R_PROFILE")) fprintf(stderr, "[prof] tiles %.1f merge %.1f lf %.1f wrap %.1f begin %.1f ms\n", g_prof[0], g_prof[1], g_prof[2], g_prof[3], g_prof[4]); } } g_prof_printer;
+#define PROF_T() std::chrono::steady_clock::now()
+#define PROF_ADD(i, a) g_prof[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()
+
 StreamParser::StreamParser() {
     for (auto& c : slot_cdf_) cdf_load_defaults(c, 0);
 }
 
 int StreamParser::begin_frame(const FrameHdr& fh) {
+    auto tb = std::chrono::steady_clock::now();
+    struct Fin { std::chrono::steady_clock::time_point t; ~Fin() { g_prof[4] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } fin{tb};
     cur_ = std::make_shared<FrameWork>();
     cur_->init(hp.seq, fh);
     cur_fh_ = fh;
@@ -79,6 +88,21 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
     } else {
         cur_init_cdf_ = slot_cdf_[fh.ref_frame_idx[fh.primary_ref_frame]];
     }
+    // restoration unit arrays (tiles fill disjoint ranges concurrently)
+    if (!fh.allow_intrabc)
+        for (int plane = 0; plane < hp.seq.num_planes; plane++) {
+            if (fh.lr_type[plane] == RESTORE_NONE) continue;
+            const int sx = plane ? hp.seq.subsampling_x : 0, sy = plane ? hp.seq.subsampling_y : 0;
+            const int unit_size = fh.lr_size[plane];
+            auto count_units = [](int us, int fs) { return std::max((fs + (us >> 1)) / us, 1); };
+            cur_->lr_rows[plane] = count_units(unit_size, (fh.frame_height + sy) >> sy);
+            cur_->lr_cols[plane] = count_units(unit_size, (fh.upscaled_width + sx) >> sx);
+            LrUnit z;
+            memset(&z, 0, sizeof(z));
+            cur_->lr[plane].assign((size_t)cur_->lr_rows[plane] * cur_->lr_cols[plane], z);
+        }
+    cur_->warps.resize(8);
+    memset(cur_->warps.data(), 0, sizeof(WarpRec) * 8);
     if (hp.seq.mono_chrome) return fail(AV1R_ENOSYS, "monochrome streams are not supported yet");
     if (fh.use_superres) return fail(AV1R_ENOSYS, "super-resolution is not supported yet");
     if (!fh.frame_is_intra) {
@@ -124,7 +148,10 @@ void StreamParser::motion_field_estimation() {
             sfw->saved_mvs.empty())
             return 0;
         const int ref_to_cur = hp.get_relative_dist(fh.order_hints[src], fh.order_hint);
-        for (int row8 = 0; row8 < h8; row8++)
+        // a projected position never leaves the 8-row band of its source (MAX_OFFSET_HEIGHT = 0): bands are independent and each
+        // is walked in raster order, so "the later source wins" stays deterministic
+        WorkerPool::get().parallel_for((h8 + 7) >> 3, [&](int band) {
+        for (int row8 = band * 8; row8 < std::min(h8, band * 8 + 8); row8++)
             for (int col8 = 0; col8 < w8; col8++) {
                 const SavedMv& sm = sfw->saved_mvs[(size_t)row8 * w8 + col8];
                 if (sm.ref <= INTRA_FRAME) continue;
@@ -154,6 +181,7 @@ void StreamParser::motion_field_estimation() {
                 m.mv = sm.mv;
                 m.ref_offset = (int8_t)ref_offset;
             }
+        });
         return 1;
     };
     const int last_idx = fh.ref_frame_idx[0];
@@ -172,8 +200,10 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
     if (!hp.parse_tile_group_header(br, cur_fh_, tg)) return fail(AV1R_EBITSTREAM, hp.error);
     size_t pos = offset + tg.data_offset;
     auto t0 = std::chrono::steady_clock::now();
+    // ---- locate the tiles of this group, then parse them concurrently (each tile is an independent symbol stream)
+    struct Task { const uint8_t* data; size_t size; int row, col, tile; };
+    std::vector<Task> tasks;
     for (int tile = tg.tg_start; tile <= tg.tg_end; tile++) {
-        const int tile_row = tile / cur_fh_.tile_cols, tile_col = tile % cur_fh_.tile_cols;
         size_t tile_size;
         if (tile == tg.tg_end) {
             tile_size = size - pos;
@@ -185,16 +215,70 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
             pos += cur_fh_.tile_size_bytes;
         }
         if (pos + tile_size > size) return fail(AV1R_EBITSTREAM, "tile exceeds tile group");
-        TileDecoder td(hp.seq, hp, *cur_, cur_init_cdf_);
-        int rc = td.decode_tile(payload + pos, tile_size, tile_row, tile_col);
-        if (rc) return fail(rc, td.err);
-        if (tile == cur_fh_.context_update_tile_id) {
-            cur_->end_cdf = td.cdf;
-            cur_->have_end_cdf = true;
-        }
+        tasks.push_back(Task{payload + pos, tile_size, tile / cur_fh_.tile_cols, tile % cur_fh_.tile_cols, tile});
         pos += tile_size;
+    }
+    FrameWork& fw = *cur_;
+    const size_t first_out = fw.tiles.size();
+    for (size_t i = 0; i < tasks.size(); i++) fw.tiles.push_back(std::make_unique<TileOut>());
+    auto parse_one = [&](int i) {
+        const Task& t = tasks[i];
+        TileOut& to = *fw.tiles[first_out + i];
+        TileDecoder td(hp.seq, hp, fw, to, cur_init_cdf_);
+        to.rc = td.decode_tile(t.data, t.size, t.row, t.col);
+        if (to.rc) to.err = td.err;
+        if (t.tile == cur_fh_.context_update_tile_id) to.end_cdf = td.cdf;
+    };
+    if (tile_threads && tasks.size() > 1) WorkerPool::get().parallel_for((int)tasks.size(), parse_one);
+    else for (size_t i = 0; i < tasks.size(); i++) parse_one((int)i);
+    PROF_ADD(0, t0);
+    auto tm = PROF_T();
+    // ---- merge in tile order: rebase the offsets the records carry
+    for (size_t i = 0; i < tasks.size(); i++) {
+        TileOut& to = *fw.tiles[first_out + i];
+        if (to.rc) return fail(to.rc, to.err);
+        if (tasks[i].tile == cur_fh_.context_update_tile_id) {
+            fw.end_cdf = to.end_cdf;
+            fw.have_end_cdf = true;
+        }
+        const uint32_t coef_base = (uint32_t)fw.coefs.size(), pal_base = (uint32_t)fw.pal.size();
+        const uint32_t tx_base = (uint32_t)fw.tx.size(), obmc_base = (uint32_t)fw.obmc.size();
+        const int warp_base = (int)fw.warps.size() - 8;   // slots 0..7 hold the global models
+        const size_t tx0 = fw.tx.size();
+        fw.tx.insert(fw.tx.end(), to.tx.begin(), to.tx.end());
+        for (size_t k = tx0; k < fw.tx.size(); k++) {
+            fw.tx[k].coef_off += coef_base;
+            if (fw.tx[k].mode == TXM_PALETTE) fw.tx[k].pal_off += pal_base;
+        }
+        fw.coefs.insert(fw.coefs.end(), to.coefs.begin(), to.coefs.end());
+        fw.pal.insert(fw.pal.end(), to.pal.begin(), to.pal.end());
+        const size_t sb0 = fw.sbs.size();
+        fw.sbs.insert(fw.sbs.end(), to.sbs.begin(), to.sbs.end());
+        for (size_t k = sb0; k < fw.sbs.size(); k++) fw.sbs[k].first += tx_base;
+        const size_t in0 = fw.inter.size();
+        fw.inter.insert(fw.inter.end(), to.inter.begin(), to.inter.end());
+        for (size_t k = in0; k < fw.inter.size(); k++) {
+            InterBlk& r = fw.inter[k];
+            r.obmc_first += obmc_base;
+            for (int l = 0; l < 2; l++)
+                if (r.warp[l] >= 8) r.warp[l] = (int16_t)(r.warp[l] + warp_base);
+        }
+        fw.obmc.insert(fw.obmc.end(), to.obmc.begin(), to.obmc.end());
+        fw.warps.insert(fw.warps.end(), to.warps.begin(), to.warps.end());
+        fw.coded_samples += to.coded_samples;
+        fw.coef_tokens += to.coef_tokens;
+        fw.tx_blocks += to.tx_blocks;
+        fw.inter_samples += to.inter_samples;
+        fw.inter_ref_samples += to.inter_ref_samples;
+        for (int k = 0; k < 24; k++) fw.tool_hist[k] += to.tool_hist[k];
+        // the lists now live in the frame; keep only the mode-info storage of the tile
+        std::vector<TxRec>().swap(to.tx);
+        std::vector<uint32_t>().swap(to.coefs);
+        std::vector<uint8_t>().swap(to.pal);
+        std::vector<InterBlk>().swap(to.inter);
         tiles_done_++;
     }
+    PROF_ADD(1, tm);
     cur_->parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }
@@ -202,6 +286,8 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
 int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
     auto t0 = std::chrono::steady_clock::now();
     build_loopfilter_edges(hp.seq, *cur_);
+    PROF_ADD(2, t0);
+    auto tw = PROF_T();
     {
         FrameWork& fw = *cur_;
         // segment map kept for later frames (spec 7.4 decode frame wrapup)
@@ -214,7 +300,8 @@ int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
         if (!cur_fh_.frame_is_intra) {
             const int w8 = fw.mi_cols >> 1, h8 = fw.mi_rows >> 1;
             fw.saved_mvs.assign((size_t)w8 * h8, SavedMv{{0, 0}, 0});
-            for (int row8 = 0; row8 < h8; row8++)
+            WorkerPool::get().parallel_for((h8 + 15) >> 4, [&](int job) {
+            for (int row8 = job * 16; row8 < std::min(h8, job * 16 + 16); row8++)
                 for (int col8 = 0; col8 < w8; col8++) {
                     const BlockInfo* b = fw.mi[(size_t)(row8 * 2 + 1) * fw.mi_cols + col8 * 2 + 1];
                     if (!b) continue;
@@ -228,8 +315,10 @@ int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
                         sm.ref = (int8_t)r;
                     }
                 }
+            });
         }
     }
+    PROF_ADD(3, tw);
     cur_->parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     CdfCtx save = cur_init_cdf_;
     if (!cur_fh_.disable_frame_end_update_cdf && cur_->have_end_cdf) {
@@ -351,7 +440,10 @@ void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
             }
             return lvl;
         };
-        for (int r4 = 0; r4 < ph4; r4++)
+        const int rows_per_job = 16;
+        const int n_jobs = (ph4 + rows_per_job - 1) / rows_per_job;
+        WorkerPool::get().parallel_for(n_jobs, [&](int job) {
+        for (int r4 = job * rows_per_job; r4 < std::min(ph4, (job + 1) * rows_per_job); r4++)
             for (int c4 = 0; c4 < pw4; c4++) {
                 // luma mi position visited by the spec's loop for this plane unit
                 const int row = r4 << sy, col = c4 << sx;
@@ -390,6 +482,7 @@ void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
                     else { e.len_h = (uint8_t)fsz; e.lvl_h = (uint8_t)lvl; }
                 }
             }
+        });
     }
 }
 

@@ -23,6 +23,7 @@ public:
     StreamParser();
     HeaderParser hp;
     std::string err;
+    bool tile_threads = true;   // parse the tiles of a tile group concurrently on the process-wide worker pool
     // Parses one temporal unit; appends one ParsedFrame per frame (shown or not) in decode order.
     // Returns 0 or AV1R_E*.
     int parse_tu(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out);

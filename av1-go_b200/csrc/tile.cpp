@@ -68,8 +68,8 @@ static const uint16_t* get_scan(int txsz, int txtp) {
     return s ? s : default_scan(txsz);
 }
 
-TileDecoder::TileDecoder(const SeqHdr& s, const HeaderParser& h, FrameWork& f, const CdfCtx& init_cdf)
-    : cdf(init_cdf), seq(s), hp(h), fw(f), fh(f.fh) {
+TileDecoder::TileDecoder(const SeqHdr& s, const HeaderParser& h, FrameWork& f, TileOut& t, const CdfCtx& init_cdf)
+    : cdf(init_cdf), seq(s), hp(h), fw(f), to(t), fh(f.fh) {
     for (int p = 0; p < 3; p++) {
         above_level[p].assign(fw.mi_cols + 64, 0);
         above_dc[p].assign(fw.mi_cols + 64, 0);
@@ -224,13 +224,6 @@ void TileDecoder::read_lr(int r, int c, int bsize) {
         int unit_col_end = ((c + w) * numerator + denominator - 1) / denominator;
         unit_row_end = std::min(unit_row_end, unit_rows);
         unit_col_end = std::min(unit_col_end, unit_cols);
-        if (fw.lr[plane].empty()) {
-            fw.lr_rows[plane] = unit_rows;
-            fw.lr_cols[plane] = unit_cols;
-            LrUnit z;
-            memset(&z, 0, sizeof(z));
-            fw.lr[plane].assign((size_t)unit_rows * unit_cols, z);
-        }
         for (int ur = unit_row_start; ur < unit_row_end; ur++)
             for (int uc = unit_col_start; uc < unit_col_end; uc++) read_lr_unit(plane, ur, uc);
     }
@@ -355,8 +348,8 @@ bool TileDecoder::decode_partition(int r, int c, int bsize) {
 // ---------------------------------------------------------------- block
 bool TileDecoder::decode_block(int r, int c, int bsize) {
     if (fail_code) return false;
-    fw.blocks.emplace_back();
-    b = &fw.blocks.back();
+    to.blocks.emplace_back();
+    b = &to.blocks.back();
     memset(b, 0, sizeof(*b));
     mi_row = r;
     mi_col = c;
@@ -387,7 +380,7 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
     else inter_frame_mode_info();
     if (fail_code) return false;
     if (b->pal_size[0] || b->pal_size[1]) {
-        fw.tool_hist[TOOL_PALETTE]++;
+        to.tool_hist[TOOL_PALETTE]++;
         palette_tokens();
     }
     read_block_tx_size();
@@ -637,8 +630,8 @@ void TileDecoder::palette_tokens() {
             for (int j = 0; j < bw; j++) at(i, j) = at(oh - 1, j);
         // emit one entry per plane (U and V share the map)
         for (int plane = pi ? 1 : 0; plane <= (pi ? 2 : 0); plane++) {
-            while (fw.pal.size() & 3) fw.pal.push_back(0);
-            pal_entry[plane] = (uint32_t)fw.pal.size();
+            while (to.pal.size() & 3) to.pal.push_back(0);
+            pal_entry[plane] = (uint32_t)to.pal.size();
             uint16_t hdr[12];
             for (int k = 0; k < 8; k++) hdr[k] = b->pal_colors[plane][k];
             hdr[8] = (uint16_t)((mi_col >> sx) * 4);
@@ -646,8 +639,8 @@ void TileDecoder::palette_tokens() {
             hdr[10] = (uint16_t)bw;
             hdr[11] = 0;
             const uint8_t* hb = reinterpret_cast<const uint8_t*>(hdr);
-            fw.pal.insert(fw.pal.end(), hb, hb + sizeof(hdr));
-            fw.pal.insert(fw.pal.end(), map.begin(), map.end());
+            to.pal.insert(to.pal.end(), hb, hb + sizeof(hdr));
+            to.pal.insert(to.pal.end(), map.begin(), map.end());
         }
     }
 }
@@ -948,7 +941,7 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
     rec.qidx = b->qidx;
     rec.seg_id = b->segment_id;
     rec.qm_level = (uint8_t)fh.seg_qm_level[plane][b->segment_id];
-    rec.coef_off = (uint32_t)fw.coefs.size();
+    rec.coef_off = (uint32_t)to.coefs.size();
     if (b->lossless) rec.flags |= TXF_LOSSLESS;
     if (!b->is_inter) {
         const int have_left = (plane == 0 ? avail_l : avail_l_chroma) || start_x > base_x;
@@ -999,10 +992,10 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
         if (fail_code) return;
     }
     rec.eob = (uint16_t)eob;
-    rec.ntok = (uint16_t)(fw.coefs.size() - rec.coef_off);
+    rec.ntok = (uint16_t)(to.coefs.size() - rec.coef_off);
     if (b->is_inter && b->interintra) rec.flags |= TXF_II;
     if (!b->is_inter || eob > 0) push_record(rec, (start_x << sx) >> 6, (start_y << sy) >> 6);
-    if (eob > 0) fw.coded_samples += (uint64_t)kTxW[txsz] * kTxH[txsz];
+    if (eob > 0) to.coded_samples += (uint64_t)kTxW[txsz] * kTxH[txsz];
     // LoopfilterTxSizes + BlockDecoded
     const int pw4 = fw.plane_w4(plane), ph4 = fw.plane_h4(plane);
     for (int i = 0; i < step_y; i++)
@@ -1020,15 +1013,15 @@ void TileDecoder::push_record(const TxRec& rec, int ux, int uy) {
     if (key != cur_unit) {
         cur_unit = key;
         SbRange sr = cur_sb;
-        sr.first = (uint32_t)fw.tx.size();
+        sr.first = (uint32_t)to.tx.size();
         sr.count = 0;
         sr.ux = (uint16_t)ux;
         sr.uy = (uint16_t)uy;
-        fw.sbs.push_back(sr);
+        to.sbs.push_back(sr);
     }
-    fw.sbs.back().count++;
-    fw.tx.push_back(rec);
-    fw.tx_blocks++;
+    to.sbs.back().count++;
+    to.tx.push_back(rec);
+    to.tx_blocks++;
 }
 
 // inter-intra (spec 7.11.3.1 / compute_prediction): one record per plane asks the wavefront kernel to form the intra
@@ -1057,7 +1050,7 @@ void TileDecoder::emit_interintra_records() {
         if (block_decoded[plane][(sub_row >> sy) - 1 + 1][(sub_col >> sx) + n4w + 1]) rec.flags |= TXF_HAVE_ABOVE_RIGHT;
         if (block_decoded[plane][(sub_row >> sy) + n4h + 1][(sub_col >> sx) - 1 + 1]) rec.flags |= TXF_HAVE_BELOW_LEFT;
         rec.cfl_alpha = ii_pack(b->wedge_interintra, b->wedge_index, b->interintra_mode, b->bsize);
-        rec.coef_off = (uint32_t)fw.coefs.size();
+        rec.coef_off = (uint32_t)to.coefs.size();
         push_record(rec, (mi_col * 4) >> 6, (mi_row * 4) >> 6);
     }
 }
@@ -1306,9 +1299,9 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             level &= 0xFFFFF;
             cul_level += level;
             if (cul_level > 63) cul_level = 63;
-            fw.coefs.push_back(coef_token(pos, sign ? -level : level));
+            to.coefs.push_back(coef_token(pos, sign ? -level : level));
         }
-        fw.coef_tokens += eob;
+        to.coef_tokens += eob;
     }
     for (int i = 0; i < w4; i++) {
         above_level[plane][x4 + i] = (uint8_t)cul_level;

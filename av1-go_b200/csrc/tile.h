@@ -13,7 +13,7 @@ struct RefFrameInfo;   // inter prediction state of reference slots (defined in 
 
 class TileDecoder {
 public:
-    TileDecoder(const SeqHdr& seq, const HeaderParser& hp, FrameWork& fw, const CdfCtx& init_cdf);
+    TileDecoder(const SeqHdr& seq, const HeaderParser& hp, FrameWork& fw, TileOut& to, const CdfCtx& init_cdf);
     // returns 0, AV1R_EBITSTREAM or AV1R_ENOSYS (err holds the reason)
     int decode_tile(const uint8_t* data, size_t sz, int tile_row, int tile_col);
     CdfCtx cdf;
@@ -23,6 +23,7 @@ private:
     const SeqHdr& seq;
     const HeaderParser& hp;
     FrameWork& fw;
+    TileOut& to;
     const FrameHdr& fh;
     Msac ms;
     int fail_code = 0;

@@ -171,7 +171,7 @@ void TileDecoder::read_is_inter() {
 }
 
 void TileDecoder::intra_block_mode_info() {
-    fw.tool_hist[TOOL_INTRA_IN_INTER]++;
+    to.tool_hist[TOOL_INTRA_IN_INTER]++;
     b->ref_frame[0] = INTRA_FRAME;
     b->ref_frame[1] = -1;
     b->y_mode = (uint8_t)ms.symbol(cdf.y_mode[kSizeGroup[b->bsize]], 13);
@@ -752,7 +752,7 @@ void TileDecoder::add_tpl_ref_mv(int delta_row, int delta_col, int is_compound) 
     if (delta_row == 0 && delta_col == 0) zero_mv_ctx = 1;
     const MfMv& m = fw.mfmv[(size_t)y8 * (fw.mi_cols >> 1) + x8];
     if (!m.ref_offset) return;
-    fw.tool_hist[TOOL_TEMPORAL_MV]++;
+    to.tool_hist[TOOL_TEMPORAL_MV]++;
     Mv cand[2];
     for (int i = 0; i < 1 + is_compound; i++) {
         const int cur_offset = hp.get_relative_dist(fh.order_hint, fh.order_hints[b->ref_frame[i]]);
@@ -1069,8 +1069,8 @@ void TileDecoder::emit_inter_block() {
         int16_t sh[4];
         setup_shear(b->warp, sh);
         wr.alpha = sh[0]; wr.beta = sh[1]; wr.gamma = sh[2]; wr.delta = sh[3];
-        r.warp[0] = (int16_t)fw.warps.size();
-        fw.warps.push_back(wr);
+        r.warp[0] = (int16_t)(8 + to.warps.size());   // rebased when the tiles are merged
+        to.warps.push_back(wr);
     } else if ((b->y_mode == GLOBALMV || b->y_mode == GLOBAL_GLOBALMV) && std::min(bw, bh) >= 8) {
         for (int l = 0; l < 1 + is_compound; l++) {
             const int ref = b->ref_frame[l];
@@ -1098,7 +1098,7 @@ void TileDecoder::emit_inter_block() {
     }
     // overlapped motion compensation neighbours (7.11.3.10)
     if (b->motion_mode == OBMC_CAUSAL) {
-        r.obmc_first = (uint32_t)fw.obmc.size();
+        r.obmc_first = (uint32_t)to.obmc.size();
         if (b->has_chroma) r.obmc_chroma_above = plane_residual_size((BlockSize)b->bsize, subx, suby) >= BLOCK_8X8;
         auto push_nb = [&](const BlockInfo* n, int x4, int y4, int step4) {
             ObmcNb o;
@@ -1110,7 +1110,7 @@ void TileDecoder::emit_inter_block() {
             o.filt[1] = n->interp_filter[1];
             o.mv[0] = n->mv[0].row;
             o.mv[1] = n->mv[0].col;
-            fw.obmc.push_back(o);
+            to.obmc.push_back(o);
         };
         if (avail_u) {
             int n_count = 0;
@@ -1142,7 +1142,7 @@ void TileDecoder::emit_inter_block() {
         }
     }
     {
-        uint32_t* th = fw.tool_hist;
+        uint32_t* th = to.tool_hist;
         th[TOOL_INTER_BLOCKS]++;
         if (is_compound) th[b->compound_type == COMPOUND_AVERAGE ? TOOL_COMPOUND_AVG : b->compound_type == COMPOUND_DISTANCE ? TOOL_COMPOUND_DIST
                             : b->compound_type == COMPOUND_WEDGE ? TOOL_COMPOUND_WEDGE : TOOL_COMPOUND_DIFFWTD]++;
@@ -1156,13 +1156,13 @@ void TileDecoder::emit_inter_block() {
         if (has_newmv(b->y_mode)) th[TOOL_NEWMV]++;
     }
     const int sub8 = (bw4 == 1 && subx) || (bh4 == 1 && suby);
-    if (b->has_chroma && sub8) fw.tool_hist[TOOL_SUB8X8_CHROMA]++;
+    if (b->has_chroma && sub8) to.tool_hist[TOOL_SUB8X8_CHROMA]++;
     if (b->has_chroma && !sub8) r.planes |= 2;
-    fw.inter.push_back(r);
+    to.inter.push_back(r);
     {
         const uint64_t area = (uint64_t)bw * bh * ((r.planes & 2) ? 3 : 2) / 2;
-        fw.inter_samples += area;
-        fw.inter_ref_samples += area * (1 + is_compound);
+        to.inter_samples += area;
+        to.inter_ref_samples += area * (1 + is_compound);
     }
     if (b->has_chroma && sub8) {
         // chroma of a group of sub-8x8 luma blocks (spec 7.11.3.1 / compute_prediction)
@@ -1182,7 +1182,7 @@ void TileDecoder::emit_inter_block() {
             c.w = (uint8_t)((n4w * 4) << subx);
             c.h = (uint8_t)((n4h * 4) << suby);
             c.planes = 2;
-            fw.inter.push_back(c);
+            to.inter.push_back(c);
         } else {
             for (int rr = 0, y = 0; y < n4h * 4; y += bh >> suby, rr++)
                 for (int cc = 0, x = 0; x < n4w * 4; x += bw >> subx, cc++) {
@@ -1193,11 +1193,11 @@ void TileDecoder::emit_inter_block() {
                     c.w = (uint8_t)bw;
                     c.h = (uint8_t)bh;
                     c.planes = 2;
-                    fw.inter.push_back(c);
+                    to.inter.push_back(c);
                 }
         }
-        fw.inter_samples += (uint64_t)(n4w * 4) * (n4h * 4) * 2;
-        fw.inter_ref_samples += (uint64_t)(n4w * 4) * (n4h * 4) * 2;
+        to.inter_samples += (uint64_t)(n4w * 4) * (n4h * 4) * 2;
+        to.inter_ref_samples += (uint64_t)(n4w * 4) * (n4h * 4) * 2;
     }
     if (b->interintra) emit_interintra_records();
 }
@@ -1228,7 +1228,7 @@ void TileDecoder::read_var_tx_size(int row, int col, int txsz, int depth) {
         const int max_tx = find_tx_size(size, size);
         const int ctx = (kTxSqrUp[txsz] != max_tx) * 3 + (4 - max_tx) * 6 + above + left;
         split = ms.symbol(cdf.txfm_partition[ctx], 2);
-        if (split) fw.tool_hist[TOOL_VARTX_SPLIT]++;
+        if (split) to.tool_hist[TOOL_VARTX_SPLIT]++;
     }
     const int w4 = kTxW[txsz] / 4, h4 = kTxH[txsz] / 4;
     if (split) {

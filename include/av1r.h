@@ -117,6 +117,10 @@ int av1r_verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, 
 /* Same, on an engine that stays open between files (what the daemon's job loop wants: one av1r_open at start-up,
  * one call per job; /root/reference/cmd/av1d/main.go:312-349).  Uses cfg.host_threads / streams of the ctx. */
 int av1r_ctx_verify_buffer(av1r_ctx* ctx, const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames);
+/* Host half only (no device): demux + symbol parse of every frame, GOP segments on `host_threads` threads (0 = all cores), the
+ * tiles of a frame on the process-wide worker pool when tile_threads != 0.  Fills frames, host_parse_ms (summed over frames),
+ * wall_ms and frames_per_sec: the "sequential parse, timed and reported separately" of the hot path. */
+int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threads, int tile_threads, av1r_report* out);
 int av1r_probe_file(const char* path, av1r_stream_info* out);
 int av1r_probe_buffer(const uint8_t* data, size_t len, av1r_stream_info* out);
 
