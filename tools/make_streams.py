@@ -25,12 +25,15 @@ CONFIGS = {
                                         "film-grain-test": "5"}, {14: 19, 48: 30}),
     "c3_small": ("panzoom", 960, 544, 10, 20, {"cpu-used": "6", "cq-level": "32", "tile-columns": "1", "tile-rows": "1", "enable-restoration": "1"},
                  {14: 19, 48: 10}),
+    **{f"c5_{i:02d}": ("panzoom", 3840, 2160, 10, 16, {"cpu-used": "8", "cq-level": "32", "tile-columns": "2", "tile-rows": "1", "enable-obmc": "1",
+                                                          "enable-warped-motion": "1", "enable-global-motion": "1", "enable-restoration": "1"},
+                       {14: 3, 48: 4}, 100 + i) for i in range(32)},
     "c2_small": ("panzoom", 640, 360, 8, 8, {"cpu-used": "8", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "1"}, {14: 0, 48: 0}),
 }
 
 
 def clip_path(name, frames=None):
-    src, w, h, bpc, n, opts, cfg = CONFIGS[name]
+    src, w, h, bpc, n, opts, cfg = CONFIGS[name][:7]
     n = frames or n
     return os.path.join(CACHE, f"{name}_{w}x{h}_{bpc}b_{n}f.ivf")
 
@@ -40,11 +43,12 @@ def get_clip(name, frames=None, verbose=False):
     path = clip_path(name, frames)
     if os.path.exists(path):
         return obuio.read_ivf(path)
-    src, w, h, bpc, n, opts, cfg = CONFIGS[name]
+    src, w, h, bpc, n, opts, cfg = CONFIGS[name][:7]
+    seed = CONFIGS[name][7] if len(CONFIGS[name]) > 7 else 3
     n = frames or n
     if verbose:
         print(f"encoding {name}: {w}x{h} {bpc}-bit {n} frames with libaom ...", file=sys.stderr)
-    fr = sources.SOURCES[src](w, h, n, bpc=bpc, seed=3)
+    fr = sources.SOURCES[src](w, h, n, bpc=bpc, seed=seed)
     tus = aomenc.encode(fr, w, h, bpc=bpc, opts=opts, cfg=cfg, threads=os.cpu_count() or 8)
     os.makedirs(CACHE, exist_ok=True)
     obuio.write_ivf(path, tus, w, h)
@@ -56,5 +60,10 @@ if __name__ == "__main__":
     ap.add_argument("name")
     ap.add_argument("--frames", type=int, default=None)
     a = ap.parse_args()
+    if a.name == "c5":
+        for i in range(32):
+            t = get_clip(f"c5_{i:02d}", verbose=True)
+            print(clip_path(f"c5_{i:02d}"), len(t), "TUs", sum(len(x) for x in t), "bytes", flush=True)
+        sys.exit(0)
     t = get_clip(a.name, a.frames, verbose=True)
     print(clip_path(a.name, a.frames), len(t), "TUs", sum(len(x) for x in t), "bytes")
