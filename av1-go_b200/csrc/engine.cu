@@ -41,15 +41,21 @@ namespace av1r {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Slot buffers of the same kind see similar sizes on every slot: `hw` (a high-water mark shared by that kind) lets a slot that has
+// to grow jump straight to the largest size any slot has needed so far, so a new engine stops (re)allocating after a few frames.
 struct DevBuf {
     uint8_t* p = nullptr;
     size_t cap = 0;
-    cudaError_t ensure(size_t n) {
+    cudaError_t ensure(size_t n, size_t* hw = nullptr) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = align_up(n + n / 4, 1 << 16);
+        size_t want = align_up(n + n / 2, 1 << 20);
+        if (hw) {
+            want = std::max(want, *hw);
+            *hw = want;
+        }
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -59,12 +65,16 @@ struct DevBuf {
 struct PinBuf {
     uint8_t* p = nullptr;
     size_t cap = 0;
-    cudaError_t ensure(size_t n) {
+    cudaError_t ensure(size_t n, size_t* hw = nullptr) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        size_t want = align_up(n + n / 4, 1 << 16);
+        size_t want = align_up(n + n / 2, 1 << 20);
+        if (hw) {
+            want = std::max(want, *hw);
+            *hw = want;
+        }
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -73,40 +83,59 @@ struct PinBuf {
 };
 
 // A frame buffer on the device (3 planes in one allocation).
+struct FrameSlab {                 // one cudaMalloc shared by several frame buffers
+    uint8_t* p = nullptr;
+    ~FrameSlab() { if (p) cudaFree(p); }
+};
+
 struct DevFrameBuf {
     uint8_t* base = nullptr;
+    std::shared_ptr<FrameSlab> slab;   // owner of `base` when set
     DevPlanes pl;
     int cw[3], ch[3], bps;
     size_t bytes = 0;
     cudaEvent_t ready = nullptr;   // recorded when the frame's last kernel has been queued; readers on other streams wait on it
     ~DevFrameBuf() {
-        if (base) cudaFree(base);
+        if (base && !slab) cudaFree(base);
         if (ready) cudaEventDestroy(ready);
     }
 };
 
-static std::shared_ptr<DevFrameBuf> alloc_frame(const DevFrameParams& fp, std::string& err) {
-    auto f = std::make_shared<DevFrameBuf>();
-    f->bps = fp.bd == 8 ? 1 : 2;
+// Allocates `count` frame buffers of one geometry out of a single device allocation (cudaMalloc is a synchronising, millisecond-scale
+// call: a decoder that keeps 2-3 buffers per in-flight frame must not pay it per frame).
+static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::shared_ptr<DevFrameBuf>>& out, std::string& err) {
+    const int bps = fp.bd == 8 ? 1 : 2;
     size_t off[3], total = 0;
+    uint32_t pitch[3];
     for (int p = 0; p < 3; p++) {
-        f->cw[p] = fp.cw[p];
-        f->ch[p] = fp.ch[p];
-        f->pl.pitch[p] = (uint32_t)align_up((size_t)fp.cw[p] * f->bps, 256);
+        pitch[p] = (uint32_t)align_up((size_t)fp.cw[p] * bps, 256);
         off[p] = total;
-        total += align_up((size_t)f->pl.pitch[p] * fp.ch[p], 256);
+        total += align_up((size_t)pitch[p] * fp.ch[p], 256);
     }
-    if (cudaMalloc(&f->base, total) != cudaSuccess) {
-        err = "cudaMalloc(frame) failed";
-        return nullptr;
+    auto slab = std::make_shared<FrameSlab>();
+    if (cudaMalloc(&slab->p, total * count) != cudaSuccess) {
+        err = "cudaMalloc(frame buffers) failed";
+        return false;
     }
-    for (int p = 0; p < 3; p++) f->pl.p[p] = f->base + off[p];
-    f->bytes = total;
-    if (cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess) {
-        err = "cudaEventCreate(frame) failed";
-        return nullptr;
+    for (int i = 0; i < count; i++) {
+        auto f = std::make_shared<DevFrameBuf>();
+        f->bps = bps;
+        f->slab = slab;
+        f->base = slab->p + (size_t)i * total;
+        for (int p = 0; p < 3; p++) {
+            f->cw[p] = fp.cw[p];
+            f->ch[p] = fp.ch[p];
+            f->pl.pitch[p] = pitch[p];
+            f->pl.p[p] = f->base + off[p];
+        }
+        f->bytes = total;
+        if (cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess) {
+            err = "cudaEventCreate(frame) failed";
+            return false;
+        }
+        out.push_back(f);
     }
-    return f;
+    return true;
 }
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
@@ -253,6 +282,40 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
     }
 }
 
+// Pinned staging of one frame's work-lists, filled by the thread that parsed the frame (so the copy into pinned memory and the K3
+// ordering run on the parser threads, not on the single thread that issues GPU work) and recycled through a pool.
+struct HostArena {
+    PinBuf pin;
+    DevWork dw;
+};
+struct HostArenaPool {
+    std::mutex m;
+    std::vector<std::unique_ptr<HostArena>> free_;
+    size_t hw = 0;
+    std::unique_ptr<HostArena> get() {
+        std::lock_guard<std::mutex> lk(m);
+        if (free_.empty()) return std::make_unique<HostArena>();
+        auto a = std::move(free_.back());
+        free_.pop_back();
+        return a;
+    }
+    void put(std::unique_ptr<HostArena> a) {
+        std::lock_guard<std::mutex> lk(m);
+        free_.push_back(std::move(a));
+    }
+    cudaError_t ensure(HostArena& a, size_t n) {
+        size_t h;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            h = hw;
+        }
+        cudaError_t e = a.pin.ensure(n, &h);
+        std::lock_guard<std::mutex> lk(m);
+        hw = std::max(hw, h);
+        return e;
+    }
+};
+
 // Execution resources of one in-flight frame.
 struct FrameSlot {
     cudaStream_t stream = nullptr;
@@ -262,12 +325,14 @@ struct FrameSlot {
     DevBuf residual;
     DevBuf sync;         // K3 done flags + ticket
     DevBuf wmap;         // K3 owner map (int32 per 4x4 cell, 3 planes)
+    DevBuf diffmask;     // K2 difference-weighted compound masks (luma-sized byte plane)
     DevBuf grain_scratch;
     DevBuf cks_dev;
     PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
     PinBuf planes_host;
     bool busy = false;
     bool k3_heavy = false;   // the frame queued on this slot has a large intra (K3) record list
+    std::shared_ptr<void> host_arena;   // pinned staging the queued H2D copy reads from (returned to the pool when the slot is reused)
     // frame buffers touched by the work queued on this slot: kept alive (out of the recycling pool)
     // until the slot's completion event has been waited on
     std::vector<std::shared_ptr<DevFrameBuf>> hold;
@@ -339,6 +404,9 @@ struct EngineImpl {
     std::vector<std::shared_ptr<DevFrameBuf>> kept;   // keep_frames handles
     std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
     DevBuf wedge_master;                              // 6 x 64 x 64 wedge master masks (inter-intra blends in K3)
+    HostArenaPool host_pool;
+    std::shared_ptr<void> make_host_arena(const FrameWork& fw, const SeqHdr& seq, std::string& e, int& rc);
+    size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_wmap = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
     int k3_ctas = 0;                                  // ticket window of the K3 dataflow kernel in 2-warp CTAs; 0 = adaptive (AV1R_K3_CTAS)
     int64_t frames_decoded = 0;
 
@@ -363,15 +431,16 @@ std::shared_ptr<DevFrameBuf> EngineImpl::get_frame(const DevFrameParams& fp) {
             f->bps == (fp.bd == 8 ? 1 : 2))
             return f;
     }
-    auto f = alloc_frame(fp, err);
-    if (f) pool.push_back(f);
-    return f;
+    const size_t first_new = pool.size();
+    if (!alloc_frames(fp, 8, pool, err)) return nullptr;
+    return pool[first_new];
 }
 
 int EngineImpl::wait_slot(FrameSlot& s) {
     if (s.busy) CK(cudaEventSynchronize(s.ev1));
     s.busy = false;
     s.hold.clear();
+    s.host_arena.reset();
     return 0;
 }
 
@@ -397,7 +466,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         res.units_x = units_x;
         res.unit_elems = off;
-        CK(s.residual.ensure((size_t)units_x * units_y * off * sizeof(int16_t)));
+        CK(s.residual.ensure((size_t)units_x * units_y * off * sizeof(int16_t), &hw_residual));
         res.base = (int16_t*)s.residual.p;
     }
     const TxRec* d_recs = (const TxRec*)(d_arena + L.recs);
@@ -427,6 +496,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         xl.cur = recon->pl;
         xl.fp = fp;
+        xl.mask_pitch = (uint32_t)align_up((size_t)fp.cw[0], 256);
+        CK(s.diffmask.ensure((size_t)xl.mask_pitch * fp.ch[0], &hw_mask));
+        xl.mask = s.diffmask.p;
         CK(launch_inter(xl, st));
         if (tm) tm->end(AV1R_ST_INTER, 1, st);
         CK(launch_inter_residual(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
@@ -448,10 +520,10 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             moff[p] = mtotal;
             mtotal += align_up(sizeof(int32_t) * (size_t)fp.pw4[p] * fp.ph4[p], 256);
         }
-        CK(s.wmap.ensure(mtotal));
+        CK(s.wmap.ensure(mtotal, &hw_wmap));
         CK(cudaMemsetAsync(s.wmap.p, 0xFF, mtotal, st));
         for (int p = 0; p < 3; p++) il.wmap[p] = (int32_t*)(s.wmap.p + moff[p]);
-        CK(s.sync.ensure(sizeof(int) * (L.n_k3 + 4)));
+        CK(s.sync.ensure(sizeof(int) * (L.n_k3 + 4), &hw_sync));
         CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_k3 + 4), st));
         il.flags = (int*)s.sync.p;
         il.ticket = (int*)s.sync.p + L.n_k3;
@@ -596,9 +668,9 @@ int EngineImpl::acquire_slot(int& slot_idx) {
     return 0;
 }
 
-int EngineImpl::prepare_work(const FrameWork& fw, DevWork& dw) {
+static int prepare_work_seq(const SeqHdr& seq, const FrameWork& fw, DevWork& dw, std::string& err) {
     if (fw.fh.using_qmatrix) { err = "quantiser matrices are not supported yet"; return AV1R_ENOSYS; }
-    fill_params(sp.hp.seq, fw, dw.fp);
+    fill_params(seq, fw, dw.fp);
     dw.fh = fw.fh;
     dw.lf_on = fw.fh.lf.level[0] || fw.fh.lf.level[1];
     dw.lf_plane_on[0] = dw.lf_on;
@@ -611,6 +683,27 @@ int EngineImpl::prepare_work(const FrameWork& fw, DevWork& dw) {
     dw.coef_tokens = fw.coefs.size();
     plan_layout(fw, dw);
     return 0;
+}
+
+int EngineImpl::prepare_work(const FrameWork& fw, DevWork& dw) { return prepare_work_seq(sp.hp.seq, fw, dw, err); }
+
+// Runs on the thread that parsed the frame: layout + copy of the work-lists into pinned memory.
+std::shared_ptr<void> EngineImpl::make_host_arena(const FrameWork& fw, const SeqHdr& seq, std::string& e, int& rc) {
+    auto a = host_pool.get();
+    rc = prepare_work_seq(seq, fw, a->dw, e);
+    if (rc) {
+        host_pool.put(std::move(a));
+        return nullptr;
+    }
+    if (host_pool.ensure(*a, a->dw.lay.total) != cudaSuccess) {
+        e = "cudaHostAlloc(staging) failed";
+        rc = AV1R_ENOMEM;
+        host_pool.put(std::move(a));
+        return nullptr;
+    }
+    fill_arena(fw, a->dw, a->pin.p);
+    HostArenaPool* pool = &host_pool;
+    return std::shared_ptr<void>(a.release(), [pool](void* p) { pool->put(std::unique_ptr<HostArena>((HostArena*)p)); });
 }
 
 int EngineImpl::exec_show_existing(int slot_idx, const FrameHdr& fh, int show_slot, int64_t pts) {
@@ -649,22 +742,57 @@ int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_a
     return 0;
 }
 
+static double g_eprof[8];
+struct EProfPrinter {
+    ~EProfPrinter() {
+        if (getenv("AV1R_PROFILE"))
+            fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f ms\n", g_eprof[0], g_eprof[1],
+                    g_eprof[2], g_eprof[3], g_eprof[4], g_eprof[5]);
+    }
+} g_eprof_printer;
+extern "C" void av1r_debug_engine_prof(double* out6, int reset) {
+    for (int i = 0; i < 6; i++) out6[i] = g_eprof[i];
+    if (reset) memset(g_eprof, 0, sizeof(g_eprof));
+}
+#define EP_T() std::chrono::steady_clock::now()
+#define EP_ADD(i, a) g_eprof[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()
+
 int EngineImpl::decode_parsed(ParsedFrame& pf) {
     int slot_idx;
+    auto ta = EP_T();
     int rc = acquire_slot(slot_idx);
+    EP_ADD(0, ta);
     if (rc) return rc;
     FrameSlot& s = *slots[slot_idx];
     if (pf.show_existing_slot >= 0) return exec_show_existing(slot_idx, pf.fh, pf.show_existing_slot, pf.pts);
     const FrameWork& fw = *pf.fw;
+    if (pf.host) {   // staged by the parser thread
+        HostArena& ha = *(HostArena*)pf.host.get();
+        auto ti = EP_T();
+        CK(s.arena.ensure(ha.dw.lay.total, &hw_arena));
+        s.host_arena = pf.host;
+        CK(cudaEventRecord(s.ev0, s.stream));
+        CK(cudaMemcpyAsync(s.arena.p, ha.pin.p, ha.dw.lay.total, cudaMemcpyHostToDevice, s.stream));
+        rc = exec_decoded(slot_idx, ha.dw, s.arena.p, pf.pts);
+        EP_ADD(3, ti);
+        return rc;
+    }
     DevWork dw;
+    auto tp = EP_T();
     rc = prepare_work(fw, dw);
+    EP_ADD(1, tp);
     if (rc) return rc;
-    CK(s.staging.ensure(dw.lay.total));
-    CK(s.arena.ensure(dw.lay.total));
+    auto tf = EP_T();
+    CK(s.staging.ensure(dw.lay.total, &hw_staging));
+    CK(s.arena.ensure(dw.lay.total, &hw_arena));
     fill_arena(fw, dw, s.staging.p);
+    EP_ADD(2, tf);
+    auto ti = EP_T();
     CK(cudaEventRecord(s.ev0, s.stream));
     CK(cudaMemcpyAsync(s.arena.p, s.staging.p, dw.lay.total, cudaMemcpyHostToDevice, s.stream));
-    return exec_decoded(slot_idx, dw, s.arena.p, pf.pts);
+    rc = exec_decoded(slot_idx, dw, s.arena.p, pf.pts);
+    EP_ADD(3, ti);
+    return rc;
 }
 
 int EngineImpl::finish_pending(Pending& p) {
@@ -949,6 +1077,7 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     int64_t la_outstanding = 0;
     const int64_t la_limit = std::max<int64_t>(2 * nthreads, 8);
     auto worker = [&]() {
+        cudaSetDevice(E.cfg.device);   // pinned staging is allocated from this thread
         while (!abort_flag.load()) {
             const size_t s = next_seg.fetch_add(1);
             if (s >= nseg) return;
@@ -963,6 +1092,13 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
                 }
                 std::vector<ParsedFrame> pfs;
                 int prc = sp.parse_tu(data + dm.tus[t].offset, dm.tus[t].size, dm.tus[t].pts, pfs);
+                std::string herr;
+                for (ParsedFrame& pf : pfs)
+                    if (pf.fw && !prc) {
+                        int hrc = 0;
+                        pf.host = E.make_host_arena(*pf.fw, sp.hp.seq, herr, hrc);
+                        if (hrc) { prc = hrc; sp.err = herr; }
+                    }
                 {
                     std::lock_guard<std::mutex> lk(sg.m);
                     sg.parsed[t - sg.tu0] = std::move(pfs);
@@ -1014,8 +1150,10 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
             std::vector<ParsedFrame> pfs;
             int prc;
             {
+                auto tw = EP_T();
                 std::unique_lock<std::mutex> lk(sg.m);
                 sg.cv.wait(lk, [&] { return sg.n_done > t; });
+                EP_ADD(4, tw);
                 pfs = std::move(sg.parsed[t]);
                 prc = sg.rc[t];
                 if (prc) msg = sg.errs[t];
@@ -1038,7 +1176,9 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
                 msg = tmp;
                 break;
             }
+            auto td = EP_T();
             int r = drain(false);
+            EP_ADD(5, td);
             if (r) { rc = r; msg = E.err; }
         }
         E.rs = &E.main_refs;

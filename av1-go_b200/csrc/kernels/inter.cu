@@ -56,10 +56,11 @@ __device__ __forceinline__ int filter_index_d(int type, int len) {
     return type;
 }
 
+static constexpr int RW = IT + 8;             // reference window row stride (tw + 7 samples used)
 struct InterSmem {
     int32_t pred[2][IT * IT];
     int32_t mid[(IT + 7) * IT];
-    uint8_t mask[128 * 128];
+    uint16_t refwin[(IT + 7) * RW];           // clamped reference samples of the tile's 8-tap support, loaded once
 };
 
 template <typename T>
@@ -67,20 +68,28 @@ __device__ __forceinline__ int ld_ref(const uint8_t* base, uint32_t pitch, int x
     return (int)__ldg((const T*)(base + (size_t)y * pitch) + x);
 }
 
-// translational prediction of a tw x th tile whose top-left plane sample is (x0, y0); (fx, fy) = 1/16 phases,
-// (ix, iy) = integer reference position of the tile's top-left sample.
+// translational prediction of a tw x th tile; (fx, fy) = 1/16 phases, (ix, iy) = integer reference position of the tile's
+// top-left sample.  The (tw + 7) x (th + 7) support is fetched once (coordinates clamped to the visible reference frame, spec
+// 7.11.3.4) into shared memory; both filter passes then run out of shared memory.
 template <typename T>
 __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, int fx, int fy, int fidx_h, int fidx_v,
-                             int tw, int th, int round1, int32_t* mid, int32_t* out) {
+                             int tw, int th, int round1, InterSmem& sm, int32_t* out) {
     const int16_t* fh = c_subpel[fidx_h][fx];
     const int16_t* fv = c_subpel[fidx_v][fy];
-    const int n1 = (th + 7) * tw;
+    const int ww = tw + 7, wh = th + 7;
+    for (int idx = threadIdx.x; idx < ww * wh; idx += INTER_THREADS) {
+        const int r = idx / ww, c = idx - r * ww;
+        sm.refwin[r * RW + c] = (uint16_t)ld_ref<T>(ref, pitch, min(max(ix + c - 3, 0), lastx), min(max(iy + r - 3, 0), lasty));
+    }
+    __syncthreads();
+    int32_t* mid = sm.mid;
+    const int n1 = wh * tw;
     for (int idx = threadIdx.x; idx < n1; idx += INTER_THREADS) {
         const int r = idx / tw, c = idx - r * tw;
-        const int yy = min(max(iy + r - 3, 0), lasty);
+        const uint16_t* w = sm.refwin + r * RW + c;
         int s = 0;
 #pragma unroll
-        for (int t = 0; t < 8; t++) s += fh[t] * ld_ref<T>(ref, pitch, min(max(ix + c + t - 3, 0), lastx), yy);
+        for (int t = 0; t < 8; t++) s += fh[t] * (int)w[t];
         mid[r * IT + c] = (s + 4) >> 3;
     }
     __syncthreads();
@@ -99,9 +108,10 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
 // warped prediction of a tile (multiples of 8): one warp per 8x8 sub-block
 template <typename T>
 __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw, int th,
-                          int round1, int32_t* mid, int32_t* out) {
+                          int round1, InterSmem& sm, int32_t* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int32_t* wm = mid + warp * 128;
+    int32_t* wm = sm.mid + warp * 128;
+    uint16_t* win = sm.refwin + warp * 240;   // 15 x 15 support of one 8x8 block (16-sample rows)
     const int nbx = tw >> 3, nb = nbx * (th >> 3);
     const int rnd = 1 << (round1 - 1);
     for (int b = warp; b < nb; b += INTER_THREADS / 32) {
@@ -111,14 +121,19 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
         const long long dst_y = (long long)wr.mat[4] * src_x + (long long)wr.mat[5] * src_y + wr.mat[1];
         const long long x4 = dst_x >> sx, y4 = dst_y >> sy;
         const int ix4 = (int)(x4 >> 16), sx4 = (int)(x4 & 0xFFFF), iy4 = (int)(y4 >> 16), sy4 = (int)(y4 & 0xFFFF);
+        for (int idx = lane; idx < 15 * 15; idx += 32) {
+            const int wr_ = idx / 15, wc = idx - wr_ * 15;
+            win[wr_ * 16 + wc] = (uint16_t)ld_ref<T>(ref, pitch, min(max(ix4 + wc - 7, 0), lastx), min(max(iy4 + wr_ - 7, 0), lasty));
+        }
+        __syncwarp();
         for (int idx = lane; idx < 15 * 8; idx += 32) {
             const int i1 = (idx >> 3) - 7, i2 = (idx & 7) - 4;
             const int sxx = sx4 + wr.alpha * i2 + wr.beta * i1;
             const int offs = ((sxx + 512) >> 10) + 64;
-            const int yy = min(max(iy4 + i1, 0), lasty);
+            const uint16_t* w = win + (i1 + 7) * 16 + (i2 - 3 + 7);
             int s = 0;
 #pragma unroll
-            for (int i3 = 0; i3 < 8; i3++) s += d_warped_filter[offs][i3] * ld_ref<T>(ref, pitch, min(max(ix4 + i2 - 3 + i3, 0), lastx), yy);
+            for (int i3 = 0; i3 < 8; i3++) s += d_warped_filter[offs][i3] * (int)w[i3];
             wm[idx] = (s + 4) >> 3;
         }
         __syncwarp();
@@ -137,13 +152,16 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
 }
 
 template <typename T>
-__global__ void __launch_bounds__(INTER_THREADS) inter_pred_kernel(InterLaunch L) {
+__global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunch L) {
     __shared__ InterSmem sm;
     const InterBlk r = L.blks[blockIdx.x];
     const DevFrameParams& fp = L.fp;
     const int pixmax = (1 << fp.bd) - 1;
     const int is_compound = r.ref[1] >= 0;
     const int round1 = is_compound ? 7 : 11, post = 11 - round1;
+    // difference-weighted masks live in a frame-sized luma plane in global memory (written by this CTA's luma pass, read by its
+    // chroma passes after the barrier + fence below): rare, so it does not deserve 16 KB of shared memory per CTA
+    uint8_t* gmask = L.mask + (size_t)r.y * L.mask_pitch + r.x;
     for (int plane = 0; plane < 3; plane++) {
         if (plane == 0 && !(r.planes & 1)) continue;
         if (plane > 0 && !(r.planes & 2)) continue;
@@ -158,12 +176,12 @@ __global__ void __launch_bounds__(INTER_THREADS) inter_pred_kernel(InterLaunch L
                 for (int l = 0; l < 1 + is_compound; l++) {
                     const DevPlanes& rf = L.refs[r.ref[l]];
                     if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) {
-                        warp_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm.mid,
+                        warp_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
                                      sm.pred[l]);
                     } else {
                         const int posx = ((px + tx) << 4) + ((2 * r.mv[l][1]) >> sx), posy = ((py + ty) << 4) + ((2 * r.mv[l][0]) >> sy);
                         predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
-                                        filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tw, th, round1, sm.mid, sm.pred[l]);
+                                        filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tw, th, round1, sm, sm.pred[l]);
                     }
                 }
                 for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
@@ -184,14 +202,15 @@ __global__ void __launch_bounds__(INTER_THREADS) inter_pred_kernel(InterLaunch L
                                     diff = d_round2(diff, (fp.bd - 8) + post);
                                     m = min(max(38 + diff / 16, 0), 64);
                                     if (r.mask_type) m = 64 - m;
-                                    sm.mask[bi * 128 + bj] = (uint8_t)m;
+                                    gmask[(size_t)bi * L.mask_pitch + bj] = (uint8_t)m;
                                 } else if (sx && sy) {
-                                    m = (sm.mask[2 * bi * 128 + 2 * bj] + sm.mask[2 * bi * 128 + 2 * bj + 1] + sm.mask[(2 * bi + 1) * 128 + 2 * bj] +
-                                         sm.mask[(2 * bi + 1) * 128 + 2 * bj + 1] + 2) >> 2;
+                                    m = (__ldcg(gmask + (size_t)(2 * bi) * L.mask_pitch + 2 * bj) + __ldcg(gmask + (size_t)(2 * bi) * L.mask_pitch + 2 * bj + 1) +
+                                         __ldcg(gmask + (size_t)(2 * bi + 1) * L.mask_pitch + 2 * bj) +
+                                         __ldcg(gmask + (size_t)(2 * bi + 1) * L.mask_pitch + 2 * bj + 1) + 2) >> 2;
                                 } else if (sx) {
-                                    m = (sm.mask[bi * 128 + 2 * bj] + sm.mask[bi * 128 + 2 * bj + 1] + 1) >> 1;
+                                    m = (__ldcg(gmask + (size_t)bi * L.mask_pitch + 2 * bj) + __ldcg(gmask + (size_t)bi * L.mask_pitch + 2 * bj + 1) + 1) >> 1;
                                 } else {
-                                    m = sm.mask[bi * 128 + bj];
+                                    m = __ldcg(gmask + (size_t)bi * L.mask_pitch + bj);
                                 }
                             } else {
                                 if (!sx && !sy) m = wedge_mask_d(r.bsize, r.wedge_sign, r.wedge_index, bi, bj);
@@ -215,6 +234,10 @@ __global__ void __launch_bounds__(INTER_THREADS) inter_pred_kernel(InterLaunch L
                 }
                 __syncthreads();
             }
+        if (plane == 0 && is_compound && r.comp_type == COMPOUND_DIFFWTD) {
+            __threadfence_block();
+            __syncthreads();
+        }
         // ---- overlapped motion compensation: blend with the neighbours' predictions, above pass then left pass
         const int n_nb = r.obmc_above + r.obmc_left;
         for (int k = 0; k < n_nb; k++) {
@@ -237,7 +260,7 @@ __global__ void __launch_bounds__(INTER_THREADS) inter_pred_kernel(InterLaunch L
                     const int tw = min(IT, ow - tx), th = min(IT, oh - ty);
                     const int posx = ((ox + tx) << 4) + ((2 * nb.mv[1]) >> sx), posy = ((oy + ty) << 4) + ((2 * nb.mv[0]) >> sy);
                     predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
-                                    filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm.mid, sm.pred[0]);
+                                    filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm, sm.pred[0]);
                     for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
                         const int i = idx / tw, j = idx - i * tw;
                         const int gx = ox + tx + j, gy = oy + ty + i;

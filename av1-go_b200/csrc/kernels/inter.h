@@ -13,6 +13,8 @@ struct InterLaunch {
     int n;
     DevPlanes refs[8];         // reference slots (same geometry as the current frame: scaled references are rejected by the host)
     DevPlanes cur;             // frame being reconstructed
+    uint8_t* mask;             // device, luma-sized byte plane: difference-weighted compound masks (COMPOUND_DIFFWTD blocks only)
+    uint32_t mask_pitch;
     DevFrameParams fp;
 };
 

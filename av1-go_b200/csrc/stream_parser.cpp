@@ -68,6 +68,10 @@ void cdf_clear_counters(CdfCtx& c) {
 
 static double g_prof[8];
 struct ProfPrinter { ~ProfPrinter() { if (getenv("AV1R_PROFILE")) fprintf(stderr, "[prof] tiles %.1f merge %.1f lf %.1f wrap %.1f begin %.1f ms\n", g_prof[0], g_prof[1], g_prof[2], g_prof[3], g_prof[4]); } } g_prof_printer;
+extern "C" void av1r_debug_parse_prof(double* out5, int reset) {
+    for (int i = 0; i < 5; i++) out5[i] = g_prof[i];
+    if (reset) memset(g_prof, 0, sizeof(g_prof));
+}
 #define PROF_T() std::chrono::steady_clock::now()
 #define PROF_ADD(i, a) g_prof[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()
 

@@ -16,6 +16,7 @@ struct ParsedFrame {
     int show_existing_slot = -1;     // show_existing_frame: output the frame stored in this slot
     FrameHdr fh;
     int64_t pts = 0;
+    std::shared_ptr<void> host;      // engine-side staging (pinned work-list arena), filled by the thread that parsed the frame
 };
 
 class StreamParser {
