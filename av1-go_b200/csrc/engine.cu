@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <future>
 #include <memory>
 #include <vector>
 
@@ -1084,31 +1085,46 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
             Segment& sg = *segs[s];
             StreamParser sp;
             sp.hp.seq = scan.seq;
-            for (size_t t = sg.tu0; t < sg.tu1 && !abort_flag.load(); t++) {
+            // parse TU t while the work-lists of TU t-1 are being laid out / copied into pinned memory on a helper thread
+            std::future<void> staging;
+            auto publish = [&](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
+                {
+                    std::lock_guard<std::mutex> lk(sg.m);
+                    sg.parsed[t - sg.tu0] = std::move(pfs);
+                    sg.rc[t - sg.tu0] = prc;
+                    if (prc) sg.errs[t - sg.tu0] = perr;
+                    sg.n_done++;
+                }
+                sg.cv.notify_all();
+            };
+            bool failed = false;
+            for (size_t t = sg.tu0; t < sg.tu1 && !abort_flag.load() && !failed; t++) {
                 {
                     std::unique_lock<std::mutex> lk(la_m);
                     la_cv.wait(lk, [&] { return la_outstanding < la_limit || abort_flag.load(); });
                     la_outstanding++;
                 }
-                std::vector<ParsedFrame> pfs;
-                int prc = sp.parse_tu(data + dm.tus[t].offset, dm.tus[t].size, dm.tus[t].pts, pfs);
-                std::string herr;
-                for (ParsedFrame& pf : pfs)
-                    if (pf.fw && !prc) {
-                        int hrc = 0;
-                        pf.host = E.make_host_arena(*pf.fw, sp.hp.seq, herr, hrc);
-                        if (hrc) { prc = hrc; sp.err = herr; }
-                    }
-                {
-                    std::lock_guard<std::mutex> lk(sg.m);
-                    sg.parsed[t - sg.tu0] = std::move(pfs);
-                    sg.rc[t - sg.tu0] = prc;
-                    if (prc) sg.errs[t - sg.tu0] = sp.err;
-                    sg.n_done++;
-                }
-                sg.cv.notify_all();
-                if (prc) break;
+                auto pfs = std::make_shared<std::vector<ParsedFrame>>();
+                const int prc = sp.parse_tu(data + dm.tus[t].offset, dm.tus[t].size, dm.tus[t].pts, *pfs);
+                if (staging.valid()) staging.get();      // TU t-1 is staged and published
+                const std::string perr = sp.err;
+                const SeqHdr seq = sp.hp.seq;
+                staging = std::async(std::launch::async, [&, t, pfs, prc, perr, seq]() {
+                    cudaSetDevice(E.cfg.device);
+                    int rc2 = prc;
+                    std::string e2 = perr;
+                    for (ParsedFrame& pf : *pfs)
+                        if (pf.fw && !rc2) {
+                            int hrc = 0;
+                            std::string herr;
+                            pf.host = E.make_host_arena(*pf.fw, seq, herr, hrc);
+                            if (hrc) { rc2 = hrc; e2 = herr; }
+                        }
+                    publish(t, std::move(*pfs), rc2, e2);
+                });
+                if (prc) failed = true;
             }
+            if (staging.valid()) staging.get();
             {   // mark the remaining TUs of a failed segment as done so the consumer never blocks
                 std::lock_guard<std::mutex> lk(sg.m);
                 sg.n_done = sg.tu1 - sg.tu0;

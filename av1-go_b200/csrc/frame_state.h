@@ -43,6 +43,7 @@ struct BlockInfo {
     uint8_t num_mv_found, is_global_or_default;
     uint8_t lossless;
     uint8_t warp_valid;        // LocalValid (motion_mode == WARPED_CAUSAL)
+    uint8_t lf_lvl[4];         // deblocking levels of this block: luma vertical edges, luma horizontal, U, V (spec 7.14.4)
     int32_t warp[6];           // LocalWarpParams
 };
 
@@ -147,17 +148,22 @@ struct FrameWork {
         sb128 = seq.use_128x128_superblock;
         mi_cols = h.mi_cols;
         mi_rows = h.mi_rows;
+        // A FrameWork is recycled (stream_parser.cpp): only what the parse *reads before writing* is cleared.  mi must be null
+        // ("not yet decoded in this frame"); every other per-mi map is fully written by the parse of the frame before anything
+        // reads it (each block writes its whole area), so resizing without a fill is enough.
         size_t n = (size_t)mi_cols * mi_rows;
         mi.assign(n, nullptr);
-        inter_tx.assign(n, 0);
-        tx_types.assign(n, 0);
-        seg_ids.assign(n, 0);
-        skip_mi.assign(n, 0);
+        inter_tx.resize(n);
+        tx_types.resize(n);
+        seg_ids.resize(n);
+        skip_mi.resize(n);
         for (int p = 0; p < 3; p++) {
             int sx = p ? subx : 0, sy = p ? suby : 0;
             size_t pn = (size_t)((mi_cols + sx) >> sx) * ((mi_rows + sy) >> sy);
-            lf_tx[p].assign(pn, 0);
-            lf[p].assign(pn, LfEdge{0, 0, 0, 0});
+            lf_tx[p].resize(pn);
+            lf[p].resize(pn);
+            lr[p].clear();
+            lr_rows[p] = lr_cols[p] = 0;
         }
         int c64 = (mi_cols + 15) >> 4, r64 = (mi_rows + 15) >> 4;
         cdef_idx.assign((size_t)c64 * r64, -1);
@@ -165,11 +171,38 @@ struct FrameWork {
         coefs.clear();
         sbs.clear();
         pal.clear();
-        tiles.clear();
         inter.clear();
         obmc.clear();
         warps.clear();
+        n_tiles_used = 0;
+        prev_seg_ids.clear();
+        mfmv.clear();
+        saved_mvs.clear();
+        memset(gm_warp_valid, 0, sizeof(gm_warp_valid));
+        memset(tool_hist, 0, sizeof(tool_hist));
+        coded_samples = coef_tokens = tx_blocks = inter_samples = inter_ref_samples = 0;
+        parse_ms = 0;
+        have_end_cdf = false;
     }
+    // per-tile outputs are recycled with the frame: hands out the next one, cleared but with its capacity kept
+    TileOut& next_tile() {
+        if (n_tiles_used == tiles.size()) tiles.push_back(std::make_unique<TileOut>());
+        TileOut& t = *tiles[n_tiles_used++];
+        t.tx.clear();
+        t.coefs.clear();
+        t.sbs.clear();
+        t.pal.clear();
+        t.inter.clear();
+        t.obmc.clear();
+        t.warps.clear();
+        t.blocks.clear();
+        t.coded_samples = t.coef_tokens = t.tx_blocks = t.inter_samples = t.inter_ref_samples = 0;
+        memset(t.tool_hist, 0, sizeof(t.tool_hist));
+        t.rc = 0;
+        t.err.clear();
+        return t;
+    }
+    size_t n_tiles_used = 0;
     int plane_w4(int p) const { int sx = p ? subx : 0; return (mi_cols + sx) >> sx; }
     int plane_h4(int p) const { int sy = p ? suby : 0; return (mi_rows + sy) >> sy; }
 };

@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <cstddef>
 
 #include "../../include/av1r.h"
@@ -75,6 +76,34 @@ extern "C" void av1r_debug_parse_prof(double* out5, int reset) {
 #define PROF_T() std::chrono::steady_clock::now()
 #define PROF_ADD(i, a) g_prof[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()
 
+// FrameWork objects are recycled process-wide: a 4K frame's maps and lists are ~20 MB of vectors whose allocation (page faults) and
+// growth would otherwise be paid on every frame.
+namespace {
+struct FrameWorkPool {
+    std::mutex m;
+    std::vector<FrameWork*> free_;
+    ~FrameWorkPool() { for (auto* f : free_) delete f; }
+};
+FrameWorkPool g_fw_pool;
+}  // namespace
+
+std::shared_ptr<FrameWork> acquire_framework() {
+    FrameWork* f = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_fw_pool.m);
+        if (!g_fw_pool.free_.empty()) {
+            f = g_fw_pool.free_.back();
+            g_fw_pool.free_.pop_back();
+        }
+    }
+    if (!f) f = new FrameWork();
+    return std::shared_ptr<FrameWork>(f, [](FrameWork* p) {
+        std::lock_guard<std::mutex> lk(g_fw_pool.m);
+        if (g_fw_pool.free_.size() < 96) g_fw_pool.free_.push_back(p);
+        else delete p;
+    });
+}
+
 StreamParser::StreamParser() {
     for (auto& c : slot_cdf_) cdf_load_defaults(c, 0);
 }
@@ -82,7 +111,7 @@ StreamParser::StreamParser() {
 int StreamParser::begin_frame(const FrameHdr& fh) {
     auto tb = std::chrono::steady_clock::now();
     struct Fin { std::chrono::steady_clock::time_point t; ~Fin() { g_prof[4] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } fin{tb};
-    cur_ = std::make_shared<FrameWork>();
+    cur_ = acquire_framework();
     cur_->init(hp.seq, fh);
     cur_fh_ = fh;
     tiles_done_ = 0;
@@ -223,8 +252,8 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
         pos += tile_size;
     }
     FrameWork& fw = *cur_;
-    const size_t first_out = fw.tiles.size();
-    for (size_t i = 0; i < tasks.size(); i++) fw.tiles.push_back(std::make_unique<TileOut>());
+    const size_t first_out = fw.n_tiles_used;
+    for (size_t i = 0; i < tasks.size(); i++) fw.next_tile();
     auto parse_one = [&](int i) {
         const Task& t = tasks[i];
         TileOut& to = *fw.tiles[first_out + i];
@@ -275,11 +304,6 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
         fw.inter_samples += to.inter_samples;
         fw.inter_ref_samples += to.inter_ref_samples;
         for (int k = 0; k < 24; k++) fw.tool_hist[k] += to.tool_hist[k];
-        // the lists now live in the frame; keep only the mode-info storage of the tile
-        std::vector<TxRec>().swap(to.tx);
-        std::vector<uint32_t>().swap(to.coefs);
-        std::vector<uint8_t>().swap(to.pal);
-        std::vector<InterBlk>().swap(to.inter);
         tiles_done_++;
     }
     PROF_ADD(1, tm);
@@ -424,66 +448,60 @@ void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
         if (plane > 0 && !fh.lf.level[1 + plane]) continue;
         const int sx = plane ? seq.subsampling_x : 0, sy = plane ? seq.subsampling_y : 0;
         const int pw4 = fw.plane_w4(plane), ph4 = fw.plane_h4(plane);
-        auto level_of = [&](const BlockInfo* b, int pass) -> int {
-            const int i = plane == 0 ? pass : plane + 1;
-            const int dlf = fh.delta_lf_multi ? b->delta_lf[i] : b->delta_lf[0];
-            int lvl = std::max(0, std::min(63, dlf + fh.lf.level[i]));
-            if (fh.seg.enabled && fh.seg.feature_enabled[b->segment_id][1 + i])
-                lvl = std::max(0, std::min(63, lvl + fh.seg.feature_data[b->segment_id][1 + i]));
-            if (fh.lf.delta_enabled) {
-                const int nshift = lvl >> 5;
-                const int ref = b->ref_frame[0];
-                if (ref == INTRA_FRAME) {
-                    lvl += fh.lf.ref_deltas[INTRA_FRAME] << nshift;
-                } else {
-                    const int mode = b->y_mode;
-                    const int mode_type = (mode >= NEARESTMV && mode != GLOBALMV && mode != GLOBAL_GLOBALMV) ? 1 : 0;
-                    lvl += (fh.lf.ref_deltas[ref] << nshift) + (fh.lf.mode_deltas[mode_type] << nshift);
-                }
-                lvl = std::max(0, std::min(63, lvl));
-            }
-            return lvl;
-        };
+        const int max_len = plane ? 8 : 16;
+        const int li[2] = {plane == 0 ? 0 : plane + 1, plane == 0 ? 1 : plane + 1};   // index into BlockInfo::lf_lvl per pass
+        const uint8_t* lf_tx = fw.lf_tx[plane].data();
+        LfEdge* edges = fw.lf[plane].data();
         const int rows_per_job = 16;
         const int n_jobs = (ph4 + rows_per_job - 1) / rows_per_job;
         WorkerPool::get().parallel_for(n_jobs, [&](int job) {
-        for (int r4 = job * rows_per_job; r4 < std::min(ph4, (job + 1) * rows_per_job); r4++)
-            for (int c4 = 0; c4 < pw4; c4++) {
-                // luma mi position visited by the spec's loop for this plane unit
-                const int row = r4 << sy, col = c4 << sx;
-                const int x = col * 4, y = row * 4;
-                if (row >= fw.mi_rows || col >= fw.mi_cols) continue;
-                LfEdge& e = fw.lf[plane][(size_t)r4 * pw4 + c4];
-                e = LfEdge{0, 0, 0, 0};
-                if (x >= fh.frame_width || y >= fh.frame_height) continue;
+            for (int r4 = job * rows_per_job; r4 < std::min(ph4, (job + 1) * rows_per_job); r4++) {
+                const int row = r4 << sy;
+                if (row >= fw.mi_rows) continue;
                 // for sub-sampled planes the spec addresses mode info at the odd (bottom-right) luma mi
-                const int mrow = std::min(fw.mi_rows - 1, row | sy), mcol = std::min(fw.mi_cols - 1, col | sx);
-                const BlockInfo* b = fw.mi[(size_t)mrow * fw.mi_cols + mcol];
-                if (!b) continue;
-                const int txsz = fw.lf_tx[plane][(size_t)r4 * pw4 + c4];
-                const int psz = plane_residual_size((BlockSize)b->bsize, sx, sy);
-                const int xp = c4 * 4, yp = r4 * 4;
-                const int is_intra = b->ref_frame[0] <= INTRA_FRAME;
-                for (int pass = 0; pass < 2; pass++) {
-                    if (pass == 0 && c4 == 0) continue;
-                    if (pass == 1 && r4 == 0) continue;
-                    const int is_block_edge = pass == 0 ? (xp % kBlockW[psz] == 0) : (yp % kBlockH[psz] == 0);
-                    const int is_tx_edge = pass == 0 ? (xp % kTxW[txsz] == 0) : (yp % kTxH[txsz] == 0);
-                    if (!is_tx_edge) continue;
-                    if (!(is_block_edge || !b->skip || is_intra)) continue;
-                    const int pr4 = pass == 0 ? r4 : r4 - 1, pc4 = pass == 0 ? c4 - 1 : c4;
-                    const int prev_tx = fw.lf_tx[plane][(size_t)pr4 * pw4 + pc4];
-                    const int base = pass == 0 ? std::min(kTxW[prev_tx], kTxW[txsz]) : std::min(kTxH[prev_tx], kTxH[txsz]);
-                    const int fsz = plane == 0 ? std::min(16, base) : std::min(8, base);
-                    int lvl = level_of(b, pass);
-                    if (lvl == 0) {
-                        const int prow = std::min(fw.mi_rows - 1, (pr4 << sy) | sy), pcol = std::min(fw.mi_cols - 1, (pc4 << sx) | sx);
-                        const BlockInfo* pb = fw.mi[(size_t)prow * fw.mi_cols + pcol];
-                        if (pb) lvl = level_of(pb, pass);
+                const int mrow = std::min(fw.mi_rows - 1, row | sy);
+                const int prow_v = mrow, prow_h = std::min(fw.mi_rows - 1, ((r4 - 1) << sy) | sy);
+                BlockInfo* const* mi_row = &fw.mi[(size_t)mrow * fw.mi_cols];
+                BlockInfo* const* mi_prev_row = r4 > 0 ? &fw.mi[(size_t)prow_h * fw.mi_cols] : nullptr;
+                (void)prow_v;
+                const bool row_visible = row * 4 < fh.frame_height;
+                for (int c4 = 0; c4 < pw4; c4++) {
+                    const int col = c4 << sx;
+                    if (col >= fw.mi_cols) continue;
+                    const size_t idx = (size_t)r4 * pw4 + c4;
+                    LfEdge e{0, 0, 0, 0};
+                    const int mcol = std::min(fw.mi_cols - 1, col | sx);
+                    const BlockInfo* b = mi_row[mcol];
+                    if (row_visible && col * 4 < fh.frame_width && b) {
+                        const int txsz = lf_tx[idx];
+                        const int txw = kTxW[txsz], txh = kTxH[txsz];
+                        const int bwp = std::max(4, kBlockW[b->bsize] >> sx), bhp = std::max(4, kBlockH[b->bsize] >> sy);
+                        const int xp = c4 * 4, yp = r4 * 4;
+                        const bool filt_inside = !b->skip || b->ref_frame[0] <= INTRA_FRAME;
+                        if (c4 > 0 && (xp & (txw - 1)) == 0 && (filt_inside || (xp & (bwp - 1)) == 0)) {
+                            int lvl = b->lf_lvl[li[0]];
+                            if (!lvl) {
+                                const BlockInfo* pb = mi_row[std::min(fw.mi_cols - 1, ((c4 - 1) << sx) | sx)];
+                                if (pb) lvl = pb->lf_lvl[li[0]];
+                            }
+                            if (lvl) {
+                                e.len_v = (uint8_t)std::min(max_len, std::min((int)kTxW[lf_tx[idx - 1]], txw));
+                                e.lvl_v = (uint8_t)lvl;
+                            }
+                        }
+                        if (r4 > 0 && (yp & (txh - 1)) == 0 && (filt_inside || (yp & (bhp - 1)) == 0)) {
+                            int lvl = b->lf_lvl[li[1]];
+                            if (!lvl) {
+                                const BlockInfo* pb = mi_prev_row[mcol];
+                                if (pb) lvl = pb->lf_lvl[li[1]];
+                            }
+                            if (lvl) {
+                                e.len_h = (uint8_t)std::min(max_len, std::min((int)kTxH[lf_tx[idx - pw4]], txh));
+                                e.lvl_h = (uint8_t)lvl;
+                            }
+                        }
                     }
-                    if (lvl == 0) continue;
-                    if (pass == 0) { e.len_v = (uint8_t)fsz; e.lvl_v = (uint8_t)lvl; }
-                    else { e.len_h = (uint8_t)fsz; e.lvl_h = (uint8_t)lvl; }
+                    edges[idx] = e;
                 }
             }
         });

@@ -45,6 +45,7 @@ private:
     int finish_frame(int64_t pts, std::vector<ParsedFrame>& out);
 };
 
+std::shared_ptr<FrameWork> acquire_framework();
 void cdf_clear_counters(CdfCtx& c);
 // host pre-pass of the deblocking filter: per-4x4 edge length + level (spec 7.14.2 - 7.14.5)
 void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw);

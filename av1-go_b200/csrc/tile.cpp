@@ -387,6 +387,28 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
     if (b->skip) reset_block_context();
     b->qidx = (uint8_t)get_qidx(fh, 0, b->segment_id, current_q_index);
     for (int i = 0; i < 4; i++) b->delta_lf[i] = (int8_t)delta_lf[i];
+    if (fh.lf.level[0] || fh.lf.level[1]) {
+        // filter level of the block per edge class (spec 7.14.4), computed once here instead of per 4x4 cell later
+        for (int i = 0; i < 4; i++) {
+            const int dlf = fh.delta_lf_multi ? b->delta_lf[i] : b->delta_lf[0];
+            int lvl = std::max(0, std::min(63, dlf + fh.lf.level[i]));
+            if (fh.seg.enabled && fh.seg.feature_enabled[b->segment_id][1 + i])
+                lvl = std::max(0, std::min(63, lvl + fh.seg.feature_data[b->segment_id][1 + i]));
+            if (fh.lf.delta_enabled) {
+                const int nshift = lvl >> 5;
+                const int ref = b->ref_frame[0];
+                if (ref == INTRA_FRAME) {
+                    lvl += fh.lf.ref_deltas[INTRA_FRAME] << nshift;
+                } else {
+                    const int mode = b->y_mode;
+                    const int mode_type = (mode >= NEARESTMV && mode != GLOBALMV && mode != GLOBAL_GLOBALMV) ? 1 : 0;
+                    lvl += (fh.lf.ref_deltas[ref] << nshift) + (fh.lf.mode_deltas[mode_type] << nshift);
+                }
+                lvl = std::max(0, std::min(63, lvl));
+            }
+            b->lf_lvl[i] = (uint8_t)lvl;
+        }
+    }
     // publish the block in the per-mi maps (clipped to the frame)
     const int rmax = std::min(r + bh4, fw.mi_rows), cmax = std::min(c + bw4, fw.mi_cols);
     for (int y = r; y < rmax; y++) {
@@ -1253,7 +1275,11 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             }
             *lp = (uint8_t)level;
         }
-        // signs + golomb, forward scan
+        // signs + golomb, forward scan (tokens are written through a raw pointer: at most eob of them)
+        const size_t tok_base = to.coefs.size();
+        to.coefs.resize(tok_base + eob);
+        uint32_t* tok_out = to.coefs.data() + tok_base;
+        int n_tok = 0;
         for (int c = 0; c < eob; c++) {
             const int pos = scan[c];
             uint8_t* lp = lv + (pos >> bwl) * ls + (pos & (width - 1));
@@ -1287,6 +1313,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                     bit = ms.literal(1);
                     if (length > 32) {
                         for (int cc = c; cc < eob; cc++) lv[(scan[cc] >> bwl) * ls + (scan[cc] & (width - 1))] = 0;
+                        to.coefs.resize(tok_base + n_tok);
                         fail(AV1R_EBITSTREAM, "golomb too long");
                         return 0;
                     }
@@ -1299,8 +1326,9 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             level &= 0xFFFFF;
             cul_level += level;
             if (cul_level > 63) cul_level = 63;
-            to.coefs.push_back(coef_token(pos, sign ? -level : level));
+            tok_out[n_tok++] = coef_token(pos, sign ? -level : level);
         }
+        to.coefs.resize(tok_base + n_tok);
         to.coef_tokens += eob;
     }
     for (int i = 0; i < w4; i++) {
