@@ -141,8 +141,8 @@ static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, k3order, total;
-    int n_recs, n_coefs, n_order, n_inter, n_obmc, n_warps, n_k3;
+    size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, k3order, k3units, total;
+    int n_recs, n_coefs, n_order, n_inter, n_obmc, n_warps, n_k3, n_k3units;
 };
 
 static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
@@ -224,10 +224,14 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     for (const TxRec& r : fw.tx) n_k3 += (r.mode != TXM_INTER) || (r.flags & TXF_II);
     L.n_k3 = n_k3;
     L.k3order = take(sizeof(uint32_t) * std::max(1, n_k3));
+    // unit table of the intra kernel: at most one entry per 64x64 luma unit (the exact count is known after the ordering pass)
+    const int units_cap = ((fw.fh.mi_cols + 15) >> 4) * ((fw.fh.mi_rows + 15) >> 4);
+    L.n_k3units = n_k3 > 0 ? units_cap : 0;
+    L.k3units = take(sizeof(K3Unit) * std::max(1, units_cap));
     L.total = o;
 }
 
-static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
+static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     const WorkLayout& L = dw.lay;
     if (L.n_recs) memcpy(h + L.recs, fw.tx.data(), sizeof(TxRec) * L.n_recs);
     if (L.n_coefs) memcpy(h + L.coefs, fw.coefs.data(), sizeof(uint32_t) * L.n_coefs);
@@ -245,33 +249,76 @@ static void fill_arena(const FrameWork& fw, const DevWork& dw, uint8_t* h) {
     if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
     if (L.n_warps) memcpy(h + L.warps, fw.warps.data(), sizeof(WarpRec) * L.n_warps);
     if (!fw.pal.empty()) memcpy(h + L.pal, fw.pal.data(), fw.pal.size());
-    {   // K3 order: records sorted (stably) by key = 4 * (sbx + 2 * sby) + z, (sbx, sby) = superblock coordinates and z = Z-index of
-        // the 64x64 unit inside a 128x128 superblock (0 for 64x64 superblocks); decode order inside a unit.  Every sample a record
-        // may read lies in a unit with a strictly smaller key or earlier in its own unit: the left superblock has base key - 4
-        // (this covers the below-left samples a 128x128 superblock may take from its left neighbour's bottom half), above-right
-        // base - 4, above base - 8.  "Wait only for lower positions" therefore stays deadlock-free while the ticket window
-        // advances along the superblock wavefront instead of along one superblock row.
+    {   // K3 order: records grouped by 64x64 luma unit, units in wavefront order.  Unit key = 4 * (sbx + 2 * sby) + seq with
+        // (sbx, sby) the superblock and seq the unit's rank in decode order inside its superblock (0 for 64x64 superblocks; a
+        // 128x128 superblock visits its four units in Z order, or 0,2,1,3 under a vertical split).  Every sample a record may
+        // read lies earlier in its own unit or in a unit with a smaller key: left superblock = base - 4 (this covers the
+        // below-left samples taken from the left neighbour's bottom half), above-right = base - 4, above = base - 8.  The intra
+        // kernel hands units to CTAs in table order and waits only for lower table indices, so it cannot deadlock.
         uint32_t* k3 = (uint32_t*)(h + L.k3order);
         TxRec* recs = (TxRec*)(h + L.recs);
+        K3Unit* units = (K3Unit*)(h + L.k3units);
         const int sx1 = dw.fp.subx, sy1 = dw.fp.suby;
-        const int sb128 = dw.fp.sb128;
-        auto key_of = [&](const TxRec& r) -> int {
+        const int sbs = dw.fp.sb128 ? 1 : 0;
+        const int UX = (dw.fp.mi_cols + 15) >> 4, UY = (dw.fp.mi_rows + 15) >> 4;
+        auto unit_of = [&](const TxRec& r) -> int {
             const int sx = r.plane ? sx1 : 0, sy = r.plane ? sy1 : 0;
             const int ux = ((r.x4 * 4) << sx) >> 6, uy = ((r.y4 * 4) << sy) >> 6;
-            if (sb128) return 4 * ((ux >> 1) + 2 * (uy >> 1)) + ((uy & 1) << 1 | (ux & 1));
-            return 4 * (ux + 2 * uy);
+            return std::min(uy, UY - 1) * UX + std::min(ux, UX - 1);
         };
-        std::vector<uint32_t> cnt(4096, 0);
-        for (int i = 0; i < L.n_recs; i++) {
+        auto in_k3 = [](const TxRec& r) { return r.mode != TXM_INTER || (r.flags & TXF_II); };
+        std::vector<int32_t> ukey((size_t)UX * UY, -1), upos((size_t)UX * UY, -1);
+        std::vector<uint32_t> cnt(4096 + 1, 0);
+        int last_sb = -1, seq = 0;
+        for (int i = 0; i < L.n_recs; i++) {   // decode order: first appearance of a unit fixes its rank inside the superblock
             const TxRec& r = fw.tx[i];
-            if (r.mode != TXM_INTER || (r.flags & TXF_II)) cnt[std::min(4095, key_of(r))]++;
+            if (!in_k3(r)) continue;
+            const int un = unit_of(r);
+            if (ukey[un] < 0) {
+                const int ux = un % UX, uy = un / UX;
+                const int sb = (uy >> sbs) * UX + (ux >> sbs);
+                seq = sb == last_sb ? std::min(seq + 1, 3) : 0;
+                last_sb = sb;
+                ukey[un] = std::min(4095, 4 * ((ux >> sbs) + 2 * (uy >> sbs)) + seq);
+            }
+            cnt[ukey[un]]++;
         }
         uint32_t acc = 0;
         for (auto& c : cnt) { const uint32_t t = c; c = acc; acc += t; }
         for (int i = 0; i < L.n_recs; i++) {
             const TxRec& r = fw.tx[i];
-            if (r.mode != TXM_INTER || (r.flags & TXF_II)) k3[cnt[std::min(4095, key_of(r))]++] = (uint32_t)i;
+            if (in_k3(r)) k3[cnt[ukey[unit_of(r)]]++] = (uint32_t)i;
         }
+        // unit table: runs of equal unit in K3 order
+        int nu = 0;
+        for (int n = 0; n < L.n_k3; n++) {
+            const int un = unit_of(recs[k3[n]]);
+            if (nu == 0 || upos[un] != nu - 1) {
+                K3Unit& u = units[nu];
+                u.first = (uint32_t)n;
+                u.count = 0;
+                u.ux = (uint16_t)(un % UX);
+                u.uy = (uint16_t)(un / UX);
+                upos[un] = nu++;
+            }
+            units[nu - 1].count++;
+        }
+        for (int k = 0; k < nu; k++) {
+            K3Unit& u = units[k];
+            static const int dxy[5][2] = {{-1, 0}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};   // left, below-left, above-left, above, above-right
+            for (int d = 0; d < 5; d++) {
+                const int nx = u.ux + dxy[d][0], ny = u.uy + dxy[d][1];
+                int dep = -1;
+                if (nx >= 0 && ny >= 0 && nx < UX && ny < UY) {
+                    const int pos = upos[(size_t)ny * UX + nx];
+                    if (pos >= 0 && pos < k) dep = pos;
+                }
+                u.dep[d] = dep;
+            }
+        }
+        dw.lay.n_k3units = nu;
+        for (int k = 0; k < nu; k++)
+            if (units[k].count > (uint32_t)K3_UNIT_MAX_RECS) dw.lay.n_k3units = -1;   // cannot happen at 4:2:0 (<= 576 records per unit)
         // explicit dependency of inter-intra residual records on their blend record (position in K3 order)
         uint32_t blend_pos[3] = {0, 0, 0};
         for (int n = 0; n < L.n_k3; n++) {
@@ -325,14 +372,12 @@ struct FrameSlot {
     DevBuf arena;        // submit path: the frame's work-lists
     DevBuf residual;
     DevBuf sync;         // K3 done flags + ticket
-    DevBuf wmap;         // K3 owner map (int32 per 4x4 cell, 3 planes)
     DevBuf diffmask;     // K2 difference-weighted compound masks (luma-sized byte plane)
     DevBuf grain_scratch;
     DevBuf cks_dev;
     PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
     PinBuf planes_host;
     bool busy = false;
-    bool k3_heavy = false;   // the frame queued on this slot has a large intra (K3) record list
     std::shared_ptr<void> host_arena;   // pinned staging the queued H2D copy reads from (returned to the pool when the slot is reused)
     // frame buffers touched by the work queued on this slot: kept alive (out of the recycling pool)
     // until the slot's completion event has been waited on
@@ -404,11 +449,13 @@ struct EngineImpl {
     RefState* rs = &main_refs;
     std::vector<std::shared_ptr<DevFrameBuf>> kept;   // keep_frames handles
     std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
+    DevBuf k3_prof;                                   // AV1R_K3_PROF: 16 cycle counters of the intra kernel
     DevBuf wedge_master;                              // 6 x 64 x 64 wedge master masks (inter-intra blends in K3)
     HostArenaPool host_pool;
     std::shared_ptr<void> make_host_arena(const FrameWork& fw, const SeqHdr& seq, std::string& e, int& rc);
-    size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_wmap = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
-    int k3_ctas = 0;                                  // ticket window of the K3 dataflow kernel in 2-warp CTAs; 0 = adaptive (AV1R_K3_CTAS)
+    size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
+    int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
+    int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
     int64_t frames_decoded = 0;
 
     int wait_slot(FrameSlot& s);
@@ -506,36 +553,37 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
     }
     if (L.n_k3 > 0) {
+        if (L.n_k3units < 0) { err = "a 64x64 unit holds more intra records than the intra kernel supports"; return AV1R_ENOSYS; }
         IntraLaunch il;
         il.recs = d_recs;
         il.order = (const uint32_t*)(d_arena + L.k3order);
         il.n = L.n_k3;
-        // ticket window: a lone intra-heavy frame gets (almost) the whole machine, several concurrent ones share it -- spinning
-        // warps of one frame must not crowd out the runnable records of the others
-        s.k3_heavy = L.n_k3 > 8192;
-        int heavy = 0;
-        for (auto& o : slots) heavy += (o->busy || o.get() == &s) && o->k3_heavy;
-        il.ctas = k3_ctas > 0 ? k3_ctas : std::max(148, std::min(1184, 2368 / std::max(1, heavy)));
-        size_t moff[3], mtotal = 0;
-        for (int p = 0; p < 3; p++) {
-            moff[p] = mtotal;
-            mtotal += align_up(sizeof(int32_t) * (size_t)fp.pw4[p] * fp.ph4[p], 256);
+        il.units = (const K3Unit*)(d_arena + L.k3units);
+        il.n_units = L.n_k3units;
+        // persistent CTAs of this frame = width of the unit wavefront (+2 so that the prologue of the next units overlaps): measured
+        // on c2 the frame latency does not improve beyond that, while every extra CTA is a spinning resident block that keeps the
+        // frames in flight on other streams off the SMs (16 -> 64 CTAs per 1080p frame costs 45 % of the clip throughput)
+        {
+            const int UX = (fp.mi_cols + 15) >> 4, UY = (fp.mi_rows + 15) >> 4;
+            il.ctas = k3_ctas > 0 ? k3_ctas : std::min(UY, (UX + 1) / 2) + 2;
+            // inter frames: the few units that hold intra / inter-intra blocks are mostly independent of each other -> one round
+            if (k3_ctas <= 0 && L.n_inter > 0) il.ctas = std::min(L.n_k3units, 6 * il.ctas);
         }
-        CK(s.wmap.ensure(mtotal, &hw_wmap));
-        CK(cudaMemsetAsync(s.wmap.p, 0xFF, mtotal, st));
-        for (int p = 0; p < 3; p++) il.wmap[p] = (int32_t*)(s.wmap.p + moff[p]);
-        CK(s.sync.ensure(sizeof(int) * (L.n_k3 + 4), &hw_sync));
-        CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_k3 + 4), st));
-        il.flags = (int*)s.sync.p;
-        il.ticket = (int*)s.sync.p + L.n_k3;
+        il.warps = k3_warps;
+        il.load_tile = L.n_inter > 0;
+        CK(s.sync.ensure(sizeof(int) * (L.n_k3units + 4), &hw_sync));
+        CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_k3units + 4), st));
+        il.uflags = (int*)s.sync.p;
+        il.ticket = (int*)s.sync.p + L.n_k3units;
         il.frame = recon->pl;
         il.res = res;
         il.fp = fp;
         il.wedge_master = wedge_master.p;
         il.pal = d_arena + L.pal;
+        il.prof = (unsigned long long*)k3_prof.p;
         CK(launch_intra(il, st));
     }
-    if (tm) tm->end(AV1R_ST_INTRA, L.n_k3 > 0 ? 2 : 0, st);
+    if (tm) tm->end(AV1R_ST_INTRA, L.n_k3 > 0 ? 1 : 0, st);
     std::shared_ptr<DevFrameBuf> cur = recon;
     if (dw.lf_on && (cfg.inloop_filters & 1)) {
         LfLaunch ll;
@@ -824,6 +872,16 @@ Engine::~Engine() {
     if (impl_->opened) {
         cudaSetDevice(impl_->cfg.device);
         cudaDeviceSynchronize();
+        if (impl_->k3_prof.p) {   // AV1R_K3_PROF: cycle totals of the intra kernel's phases
+            unsigned long long c[16];
+            cudaMemcpy(c, impl_->k3_prof.p, sizeof(c), cudaMemcpyDeviceToHost);
+            static const char* names[16] = {"ticket", "prologue", "unit_wait", "halo", "res_wait", "dataflow", "writeback", "", "rec_fetch", "rec_wait",
+                                            "rec_predict", "warp_idle", "records", "units", "", ""};
+            fprintf(stderr, "[av1r k3 prof]");
+            for (int i = 0; i < 14; i++)
+                if (names[i][0]) fprintf(stderr, " %s=%llu", names[i], c[i]);
+            fprintf(stderr, "\n");
+        }
         for (auto& s : impl_->slots) {
             if (s->ev0) cudaEventDestroy(s->ev0);
             if (s->ev1) cudaEventDestroy(s->ev1);
@@ -868,6 +926,11 @@ int Engine::open(const av1r_config& cfg) {
         E.slots.push_back(std::move(s));
     }
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));
+    if (const char* e = getenv("AV1R_K3_WARPS")) E.k3_warps = std::min(8, std::max(1, atoi(e)));
+    if (getenv("AV1R_K3_PROF")) {
+        CK(E.k3_prof.ensure(16 * sizeof(unsigned long long)));
+        CK(cudaMemset(E.k3_prof.p, 0, 16 * sizeof(unsigned long long)));
+    }
     CK(E.wedge_master.ensure(6 * 64 * 64));
     CK(inter_copy_wedge_master(E.wedge_master.p, E.streams[0]));
     CK(cudaStreamSynchronize(E.streams[0]));

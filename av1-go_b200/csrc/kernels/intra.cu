@@ -1,19 +1,20 @@
-// K3 -- intra prediction + residual add as a *record-level dataflow* kernel (AV1 spec 7.11.2, 7.11.4, 7.11.5, 7.12.3).
+// K3 -- intra prediction + residual add, *unit-resident dataflow* kernel (AV1 spec 7.11.2, 7.11.4, 7.11.5, 7.12.3).
 //
-// Intra prediction reads reconstructed neighbours, so transform blocks form a dependency DAG: a block needs the blocks that
-// own its above row (plus above-right when the mode looks there), its left column (plus below-left) and, for CfL, the luma
-// blocks under it.  Walking the blocks of a superblock row in decode order (v1-v4 of this kernel) serialises ~5000 blocks per
-// row although the DAG is only a few hundred blocks deep (a 2:1 wavefront at *block* granularity).  v5 therefore gives every
-// record to its own warp:
-//   1. `wmap_scatter_kernel` writes, for every 4x4 cell of every plane, the position (in K3 order) of the record that
-//      reconstructs it (atomicMax: for inter-intra blocks the residual record wins over the blend record).
-//   2. `intra_dataflow_kernel`: persistent warps claim records in decode order through an atomic ticket, look up the owners of
-//      the edge cells they are about to read, spin (with back-off) on those owners' done-flags, predict, add the residual,
-//      store, fence and raise their own flag.  A warp only ever waits for lower tickets, which are held by resident warps, so
-//      the lowest unfinished record can always run: no deadlock, no host-built dependency lists.
-// Edge samples come from L2 (ld.global.cg; the frame is being written by other SMs), the residual from K1's unit-major
-// buffer.  The critical path is the DAG depth (W/bw + 2H/bh blocks) times one L2 round trip, instead of the record count.
-// Algorithmic bytes: F_intra written + 2A residual read + 32 B/record (+ edge re-reads, all L2 hits).
+// Intra prediction reads reconstructed neighbours, so transform blocks form a dependency DAG; the stage is bound by the latency
+// of one link of that DAG times its depth, not by bytes.  v5 gave every record its own warp and handed samples over through
+// L2 (one link = flag poll + fence + L2 edge gather + fence: ~1.5 us).  v6 keeps the hand-over on chip:
+//   * one CTA owns one 64x64 luma unit (+ its two 32x32 chroma tiles) at a time.  The unit's samples live in a shared-memory
+//     canvas together with the halo they can read: the row above (corner .. above-right), the column to the left (.. below-left)
+//     and, for the bottom-left unit of a 128x128 superblock, the top-right unit's columns.
+//   * inside the CTA the unit's records are claimed in decode order by NW warps through a shared-memory ticket; a warp looks up
+//     the owners of the 4x4 cells its edges come from in a shared-memory owner map and spins on their done-flags (shared
+//     memory, ~30 cycles), predicts from the canvas into the canvas, adds the residual (brought in by one TMA bulk copy per
+//     unit: the residual is stored unit-major) and raises its flag.  One link costs a few hundred cycles.
+//   * units are listed by the host in wavefront order with the table indices of the (<= 5) neighbour units they read; a
+//     persistent grid claims units through a global ticket, waits for those neighbours' flags (acquire), loads the halo from
+//     L2, and after the last record writes the unit back with coalesced stores, fences and releases its own flag.
+//     A CTA only waits for lower tickets, which are held by CTAs that already run: no deadlock.
+// Algorithmic bytes: F_intra written + 2A residual read + 32 B/record (+ halo re-reads, L2 hits).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,6 +30,7 @@
 namespace av1r {
 
 __constant__ int16_t c_dr_deriv[90];
+__constant__ uint8_t c_mode_angle[9] = {0, 90, 180, 45, 135, 113, 157, 203, 67};
 __constant__ uint8_t c_sm_weights[124];
 __constant__ int8_t c_fi_taps[5][8][8];
 __constant__ uint8_t c_itxw_log2[TX_SIZES_ALL];
@@ -40,29 +42,102 @@ __constant__ uint8_t c_ii_blk_w[BLOCK_SIZES_ALL];
 __constant__ uint8_t c_ii_blk_h[BLOCK_SIZES_ALL];
 static bool g_intra_const_loaded[64] = {false};
 
-static constexpr int INTRA_WARPS = 2;
+typedef int16_t edge_t;                     // samples are <= 12 bits
+static constexpr int K3_MAX_WARPS = 8;
 static constexpr int EDGE_PAD = 16;
-static constexpr int EDGE_LEN = EDGE_PAD + 2 * 129 + 16;   // room for upsampled edges (index -2 .. 2*(w+h))
+static constexpr int EDGE_LEN = EDGE_PAD + 128 + 16;   // w + h <= 128 samples per edge; upsampled edges (w + h <= 16) need 2x + 2
+static constexpr int CV_LEFT = 16;          // canvas columns to the left of the unit (only column -1 is used; 16 keeps rows 16-byte aligned)
+static constexpr int CV_W0 = 64, CV_W1 = 32;            // unit tile sizes (4:2:0)
+static constexpr int CV_CS0 = CV_LEFT + 2 * CV_W0;      // canvas row stride, luma (covers the above-right samples)
+static constexpr int CV_CS1 = CV_LEFT + 2 * CV_W1;
+static constexpr int CV_ELEMS = (CV_W0 + 1) * CV_CS0 + 2 * (CV_W1 + 1) * CV_CS1;   // rows -1 .. H-1
+static constexpr int RES_ELEMS = CV_W0 * CV_W0 + 2 * CV_W1 * CV_W1;
+static constexpr int OWNER_CELLS = 16 * 16 + 2 * 8 * 8;
 
-struct IntraSmem {
-    int32_t above[2][EDGE_LEN];
-    int32_t left[2][EDGE_LEN];
-    int16_t tile[64 * 64 / 4];   // 32x32 int16: filter-intra predictions / CfL luma terms
-    int16_t res[256];            // residual of blocks up to 256 samples, fetched before the dependency wait
+struct WarpScratch {
+    edge_t above[2][EDGE_LEN];
+    edge_t left[2][EDGE_LEN];
+    int16_t tile[32 * 32];       // filter-intra predictions / CfL luma terms
 };
 
-// Samples of the frame under reconstruction, read through L2 (other SMs are writing it).
+// Where the unit's samples are: pure arithmetic on the plane index (the canvas geometry is fixed at 4:2:0), kept in registers.
 template <typename T>
-struct FrameView {
-    const uint8_t* p[3];
-    uint32_t pitch[3];
-    __device__ __forceinline__ int px(int plane, int x, int y) const { return (int)__ldcg((const T*)(p[plane] + (size_t)y * pitch[plane]) + x); }
+struct UnitCtx {
+    T* canvas;           // plane p: rows -1 .. H-1 of stride cs(p), columns -CV_LEFT .. 2W-1; planes back to back
+    T* lext;             // below-left columns: sample (x0 - 1, y0 + H + k) of plane p at lext[lext_off(p) + k]
+    const int16_t* res;  // residual of the unit (plane tiles of W x H int16)
+    int ux, uy;
+    __device__ __forceinline__ static int W(int p) { return p ? CV_W1 : CV_W0; }
+    __device__ __forceinline__ static int cs(int p) { return p ? CV_CS1 : CV_CS0; }
+    __device__ __forceinline__ static int cv_off(int p) {   // element offset of sample (x0, y0) of plane p
+        return (p == 0 ? 0 : (p == 1 ? (CV_W0 + 1) * CV_CS0 : (CV_W0 + 1) * CV_CS0 + (CV_W1 + 1) * CV_CS1)) + cs(p) + CV_LEFT;
+    }
+    __device__ __forceinline__ static int lext_off(int p) { return p == 0 ? 0 : (p == 1 ? CV_W0 : CV_W0 + CV_W1); }
+    __device__ __forceinline__ static int res_off(int p) { return p == 0 ? 0 : (p == 1 ? CV_W0 * CV_W0 : CV_W0 * CV_W0 + CV_W1 * CV_W1); }
+    __device__ __forceinline__ int x0(int p) const { return ux * W(p); }
+    __device__ __forceinline__ int y0(int p) const { return uy * W(p); }
+    __device__ __forceinline__ T* cv(int p) const { return canvas + cv_off(p); }
+    __device__ __forceinline__ int px(int plane, int x, int y) const {
+        const int dx = x - x0(plane), dy = y - y0(plane);
+        return dy < W(plane) ? (int)canvas[cv_off(plane) + dy * cs(plane) + dx] : (int)lext[lext_off(plane) + dy - W(plane)];
+    }
 };
 
-template <typename T>
-__device__ __forceinline__ int ldpx(const uint8_t* base, uint32_t pitch, int x, int y) {
-    return (int)__ldcg((const T*)(base + (size_t)y * pitch) + x);
+// log2 of the transform width / height minus 2, three bits per TxSize, as immediates (no table load on the record's critical path)
+__device__ __forceinline__ int tx_lw(int txsz) {
+    constexpr unsigned long long pk = 0ull | (0ull << 0) | (1ull << 3) | (2ull << 6) | (3ull << 9) | (4ull << 12) |   // 4x4 8x8 16x16 32x32 64x64
+                                      (0ull << 15) | (1ull << 18) | (1ull << 21) | (2ull << 24) | (2ull << 27) | (3ull << 30) |   // 4x8 8x4 8x16 16x8 16x32 32x16
+                                      (3ull << 33) | (4ull << 36) | (0ull << 39) | (2ull << 42) | (1ull << 45) | (3ull << 48) |   // 32x64 64x32 4x16 16x4 8x32 32x8
+                                      (2ull << 51) | (4ull << 54);                                                               // 16x64 64x16
+    return 2 + (int)((pk >> (3 * txsz)) & 7);
 }
+__device__ __forceinline__ int tx_lh(int txsz) {
+    constexpr unsigned long long pk = 0ull | (0ull << 0) | (1ull << 3) | (2ull << 6) | (3ull << 9) | (4ull << 12) |
+                                      (1ull << 15) | (0ull << 18) | (2ull << 21) | (1ull << 24) | (3ull << 27) | (2ull << 30) |
+                                      (4ull << 33) | (3ull << 36) | (2ull << 39) | (0ull << 42) | (3ull << 45) | (1ull << 48) |
+                                      (4ull << 51) | (2ull << 54);
+    return 2 + (int)((pk >> (3 * txsz)) & 7);
+}
+
+struct UnitSync {
+    unsigned long long bar;   // mbarrier of the residual bulk copy
+    int unit, next;
+};
+
+// ---- TMA bulk copy + mbarrier helpers (SASS UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
@@ -94,7 +169,7 @@ __device__ __forceinline__ int edge_upsample_d(int w, int h, int filter_type, in
 }
 
 // src/dst point at element 0 (index -1 is the corner).  sz counts the corner.
-__device__ __forceinline__ void edge_filter_d(const int32_t* src, int32_t* dst, int sz, int strength, int total, int lane) {
+__device__ __forceinline__ void edge_filter_d(const edge_t* src, edge_t* dst, int sz, int strength, int total, int lane) {
     const int k0 = strength == 3 ? 2 : 0, k1 = strength == 1 ? 4 : (strength == 2 ? 5 : 4), k2 = strength == 1 ? 8 : (strength == 2 ? 6 : 4);
     for (int i = lane; i < total + 2; i += 32) {
         // element index e = i - 1 over [-1, total]; filtered for 1 <= i < sz, copied otherwise
@@ -106,19 +181,19 @@ __device__ __forceinline__ void edge_filter_d(const int32_t* src, int32_t* dst, 
         } else {
             v = src[i - 1];
         }
-        dst[i - 1] = v;
+        dst[i - 1] = (edge_t)v;
     }
 }
 
 // upsample numPx samples: dst gets indices -2 .. 2*numPx-2
-__device__ __forceinline__ void edge_upsample_d(const int32_t* src, int32_t* dst, int num_px, int pixmax, int lane) {
+__device__ __forceinline__ void edge_upsample_d(const edge_t* src, edge_t* dst, int num_px, int pixmax, int lane) {
     for (int i = lane; i < num_px; i += 32) {
         // dup[k] = src[k-2] for k = 1..numPx+1, dup[0] = src[-1], dup[numPx+2] = src[numPx-1]
         const int d0 = src[max(i - 2, -1)], d1 = src[i - 1], d2 = src[i], d3 = src[min(i + 1, num_px - 1)];
         int s = -d0 + 9 * d1 + 9 * d2 - d3;
         s = min(max((s + 8) >> 4, 0), pixmax);
-        dst[2 * i - 1] = s;
-        dst[2 * i] = d2;
+        dst[2 * i - 1] = (edge_t)s;
+        dst[2 * i] = (edge_t)d2;
     }
     if (lane == 0) dst[-2] = src[-1];
 }
@@ -149,22 +224,20 @@ __device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int
 }
 
 template <typename T>
-__device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidual& res, const DevFrameParams& fp, IntraSmem& sm,
-                            const FrameView<T>& uv, int lane, const uint8_t* wedge_master, const uint8_t* pal) {
+__device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrameParams& fp, WarpScratch& sm, int lane,
+                            const uint8_t* wedge_master, const uint8_t* pal) {
     const int plane = r.plane;
-    const int lw = c_itxw_log2[r.txsz], lh = c_itxh_log2[r.txsz];
+    const int lw = tx_lw(r.txsz), lh = tx_lh(r.txsz);
     const int w = 1 << lw, h = 1 << lh;
     const int x = r.x4 * 4, y = r.y4 * 4;
     const int bd = fp.bd, pixmax = (1 << bd) - 1;
     const int max_x = fp.cw[plane] - 1, max_y = fp.ch[plane] - 1;
-    const uint32_t pitch = fr.pitch[plane];
     const int xe = min(w, fp.cw[plane] - x), ye = min(h, fp.ch[plane] - y);
-    T* out = (T*)(fr.p[plane] + (size_t)y * pitch) + x;
-    const int opitch = pitch / sizeof(T);
+    const int opitch = uv.cs(plane);
+    T* out = uv.cv(plane) + (y - uv.y0(plane)) * opitch + (x - uv.x0(plane));   // the unit's samples live in shared memory
     const bool has_res = r.eob > 0;
-    const bool res_pre = (w * h) <= 256;     // prefetched into sm.res (row-major w x h) by the caller
-    const int16_t* rp = res_pre ? sm.res : res_ptr(res, plane, x, y);
-    const int rpitch = res_pre ? w : (1 << res.tw_log2[plane]);
+    const int rpitch = uv.W(plane);            // residual unit: plane tiles of W x H int16, staged by the bulk copy
+    const int16_t* rp = uv.res + uv.res_off(plane) + (y - uv.y0(plane)) * rpitch + (x - uv.x0(plane));
     const bool ii = (r.flags & TXF_II) != 0;
     const int ii_pk = (uint16_t)r.cfl_alpha;
     const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
@@ -172,7 +245,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
         if (i < ye && j < xe) {
             if (ii) {   // blend the intra predictor over the inter predictor K2 left in the frame
                 const int m = ii_mask(ii_pk, wedge_master, i, j, w, h, psx, psy);
-                v = (m * v + (64 - m) * (int)__ldcg(out + i * opitch + j) + 32) >> 6;
+                v = (m * v + (64 - m) * (int)out[i * opitch + j] + 32) >> 6;
             }
             if (has_res) v = min(max(v + (int)rp[i * rpitch + j], 0), pixmax);
             out[i * opitch + j] = (T)v;
@@ -184,7 +257,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
             for (int idx = lane; idx < w * h; idx += 32) {
                 const int i = idx >> lw, j = idx & (w - 1);
                 if (i < ye && j < xe) {
-                    int v = (int)__ldcg(out + i * opitch + j) + (int)rp[i * rpitch + j];
+                    int v = (int)out[i * opitch + j] + (int)rp[i * rpitch + j];
                     out[i * opitch + j] = (T)min(max(v, 0), pixmax);
                 }
             }
@@ -203,8 +276,8 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
     }
     const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
     const int have_ar = r.flags & TXF_HAVE_ABOVE_RIGHT, have_bl = r.flags & TXF_HAVE_BELOW_LEFT;
-    int32_t* above = sm.above[0] + EDGE_PAD;
-    int32_t* left = sm.left[0] + EDGE_PAD;
+    edge_t* above = sm.above[0] + EDGE_PAD;
+    edge_t* left = sm.left[0] + EDGE_PAD;
     const int n = w + h;
     // ---- edges
     for (int i = lane; i < n; i += 32) {
@@ -225,8 +298,8 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
         } else {
             l = (1 << (bd - 1)) + 1;
         }
-        above[i] = a;
-        left[i] = l;
+        above[i] = (edge_t)a;
+        left[i] = (edge_t)l;
     }
     if (lane == 0) {
         int c;
@@ -234,8 +307,8 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
         else if (have_above) c = uv.px(plane, x, y - 1);
         else if (have_left) c = uv.px(plane, x - 1, y);
         else c = 1 << (bd - 1);
-        above[-1] = c;
-        left[-1] = c;
+        above[-1] = (edge_t)c;
+        left[-1] = (edge_t)c;
     }
     __syncwarp();
     int mode = r.mode;
@@ -276,8 +349,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
         return;
     }
     if (mode >= V_PRED && mode <= D67_PRED) {
-        const int kModeToAngle[9] = {0, 90, 180, 45, 135, 113, 157, 203, 67};
-        const int p_angle = kModeToAngle[mode] + r.angle_delta * 3;
+        const int p_angle = c_mode_angle[mode] + r.angle_delta * 3;
         int up_above = 0, up_left = 0;
         if (fp.enable_edge_filter) {
             const int filter_type = (r.flags & TXF_SMOOTH_EDGE) ? 1 : 0;
@@ -285,8 +357,8 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
                 if (p_angle > 90 && p_angle < 180 && (w + h) >= 24) {
                     if (lane == 0) {
                         const int v = (left[0] * 5 + above[-1] * 6 + above[0] * 5 + 8) >> 4;
-                        above[-1] = v;
-                        left[-1] = v;
+                        above[-1] = (edge_t)v;
+                        left[-1] = (edge_t)v;
                     }
                     __syncwarp();
                 }
@@ -294,7 +366,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
                     const int strength = edge_filter_strength_d(w, h, filter_type, p_angle - 90);
                     if (strength) {
                         const int num_px = min(w, max_x - x + 1) + (p_angle < 90 ? h : 0) + 1;
-                        int32_t* dst = (above == sm.above[0] + EDGE_PAD) ? sm.above[1] + EDGE_PAD : sm.above[0] + EDGE_PAD;
+                        edge_t* dst = (above == sm.above[0] + EDGE_PAD) ? sm.above[1] + EDGE_PAD : sm.above[0] + EDGE_PAD;
                         edge_filter_d(above, dst, num_px, strength, n - 1, lane);
                         above = dst;
                         __syncwarp();
@@ -304,7 +376,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
                     const int strength = edge_filter_strength_d(w, h, filter_type, p_angle - 180);
                     if (strength) {
                         const int num_px = min(h, max_y - y + 1) + (p_angle > 180 ? w : 0) + 1;
-                        int32_t* dst = (left == sm.left[0] + EDGE_PAD) ? sm.left[1] + EDGE_PAD : sm.left[0] + EDGE_PAD;
+                        edge_t* dst = (left == sm.left[0] + EDGE_PAD) ? sm.left[1] + EDGE_PAD : sm.left[0] + EDGE_PAD;
                         edge_filter_d(left, dst, num_px, strength, n - 1, lane);
                         left = dst;
                         __syncwarp();
@@ -313,14 +385,14 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
             }
             up_above = edge_upsample_d(w, h, filter_type, p_angle - 90);
             if (up_above) {
-                int32_t* dst = (above == sm.above[0] + EDGE_PAD) ? sm.above[1] + EDGE_PAD : sm.above[0] + EDGE_PAD;
+                edge_t* dst = (above == sm.above[0] + EDGE_PAD) ? sm.above[1] + EDGE_PAD : sm.above[0] + EDGE_PAD;
                 edge_upsample_d(above, dst, w + (p_angle < 90 ? h : 0), pixmax, lane);
                 above = dst;
                 __syncwarp();
             }
             up_left = edge_upsample_d(w, h, filter_type, p_angle - 180);
             if (up_left) {
-                int32_t* dst = (left == sm.left[0] + EDGE_PAD) ? sm.left[1] + EDGE_PAD : sm.left[0] + EDGE_PAD;
+                edge_t* dst = (left == sm.left[0] + EDGE_PAD) ? sm.left[1] + EDGE_PAD : sm.left[0] + EDGE_PAD;
                 edge_upsample_d(left, dst, h + (p_angle > 180 ? w : 0), pixmax, lane);
                 left = dst;
                 __syncwarp();
@@ -400,8 +472,12 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
             for (int k = lane; k < h; k += 32) s += left[k];
         if (have_above)
             for (int k = lane; k < w; k += 32) s += above[k];
-        s = warp_sum(s);
-        if (have_left && have_above) dc = (s + ((w + h) >> 1)) / (w + h);
+        s = __reduce_add_sync(0xffffffffu, s);
+        if (have_left && have_above) {   // (s + (w + h) / 2) / (w + h); w + h = {1, 3, 5} * 2^k: shift, then exact division by 3 or 5
+            const int lo = min(lw, lh), d = abs(lw - lh);
+            const unsigned q = (unsigned)(s + ((w + h) >> 1)) >> lo;      // divisor is now 2, 3 or 5 (square, 2:1, 4:1)
+            dc = d == 0 ? (int)(q >> 1) : (d == 1 ? (int)(__umulhi(q, 0xAAAAAAABu) >> 1) : (int)(__umulhi(q, 0xCCCCCCCDu) >> 2));
+        }
         else if (have_left) dc = (s + (h >> 1)) >> lh;
         else if (have_above) dc = (s + (w >> 1)) >> lw;
         else dc = 1 << (bd - 1);
@@ -425,7 +501,7 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
             L[idx] = (int16_t)v;
             s += v;
         }
-        s = warp_sum(s);
+        s = __reduce_add_sync(0xffffffffu, s);
         const int sh = lw + lh;
         const int avg = (s + (1 << (sh - 1))) >> sh;
         const int alpha = r.cfl_alpha;
@@ -438,139 +514,333 @@ __device__ void intra_block(const TxRec& r, const DevPlanes& fr, const DevResidu
     }
 }
 
-// 1. owner map: position (K3 order) of the record that reconstructs each 4x4 cell
-__global__ void __launch_bounds__(128) wmap_scatter_kernel(IntraLaunch L) {
-    const int pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (pos >= L.n) return;
-    const TxRec r = L.recs[L.order[pos]];
-    const int plane = r.plane;
-    const int w4 = 1 << (c_itxw_log2[r.txsz] - 2), h4 = 1 << (c_itxh_log2[r.txsz] - 2);
-    const int pw4 = L.fp.pw4[plane], ph4 = L.fp.ph4[plane];
-    int32_t* m = L.wmap[plane];
-    for (int c = lane; c < w4 * h4; c += 32) {
-        const int cy = r.y4 + c / w4, cx = r.x4 + c % w4;
-        if (cx < pw4 && cy < ph4) atomicMax(m + (size_t)cy * pw4 + cx, pos);
-    }
-}
 
-__device__ __forceinline__ void wait_flag(const int* flags, int id) {
-    const volatile int* f = flags + id;
-    int ns = 32;
-    while (*f == 0) {
-        __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
-    }
+// Warp-collective wait on the completion barriers of records of the same unit: every lane names one local record index (or
+// -1).  A record's barrier (one mbarrier, arrival count 1) completes one phase per unit the CTA processes -- when the record's
+// samples are in the canvas (barriers the unit does not use are stepped in the prologue, so all stay on the CTA's parity);
+// try_wait suspends the warp in hardware, so waiting warps do not steal issue slots or shared-memory bandwidth from the warps
+// that predict.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
 }
-
-// Warp-collective wait: every lane names one owner position (or -1).  All pending flags are sampled once per round with a
-// single warp-wide load; only lane 0 then spins, on the highest pending position (the one most likely to finish last), so a
-// waiting warp costs L2 one poll per back-off period instead of one per lane.
-__device__ __forceinline__ void wait_deps_warp(const int* flags, int id, int lane) {
-    while (true) {
-        const bool pend = id >= 0 && *(const volatile int*)(flags + id) == 0;
+// `stuck` (one int per frame) is raised instead of hanging if a wait makes no progress for seconds: a wrong work-list must
+// end in a digest mismatch, not in a wedged GPU.
+__device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parity, int* stuck) {
+    for (int spins = 0; spins < (1 << 22); spins++) {
+        const bool pend = id >= 0 && !mbar_test(rbar + 8u * (uint32_t)id, parity);
         if (!__any_sync(0xffffffffu, pend)) return;
         const int mx = __reduce_max_sync(0xffffffffu, pend ? id : -1);
-        if (lane == 0) wait_flag(flags, mx);
-        __syncwarp();
+        mbar_try(rbar + 8u * (uint32_t)mx, parity);
+    }
+    *stuck = 1;
+}
+
+__device__ __forceinline__ TxRec load_rec(const TxRec* p) {
+    union { TxRec r; uint4 q[2]; } u;
+    u.q[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    u.q[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    return u.r;
+}
+
+template <typename T, int NW>
+__global__ void __launch_bounds__(NW * 32) intra_unit_kernel(IntraLaunch L) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // ---- carve (mirrored by k3_smem_bytes)
+    int16_t* res_s = reinterpret_cast<int16_t*>(smem_raw);
+    T* canvas = reinterpret_cast<T*>(smem_raw + RES_ELEMS * sizeof(int16_t));
+    T* lext_s = canvas + CV_ELEMS;                                  // 64 + 32 + 32 samples
+    int32_t* owner = reinterpret_cast<int32_t*>(lext_s + 128);
+    unsigned long long* rbar_s = reinterpret_cast<unsigned long long*>(owner + OWNER_CELLS);   // one completion barrier per record
+    UnitSync* us = reinterpret_cast<UnitSync*>(rbar_s + K3_UNIT_MAX_RECS);
+    WarpScratch* wscr = reinterpret_cast<WarpScratch*>(reinterpret_cast<uint8_t*>(us) + 64);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nthr = NW * 32, nw = NW;
+    const DevFrameParams& fp = L.fp;
+    const uint32_t bar = smem_u32(&us->bar);
+    constexpr uint32_t unit_bytes = RES_ELEMS * sizeof(int16_t);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    int inited = 0;   // record barriers [0, inited) hold valid mbarrier objects
+    uint32_t rpar = 0;   // phase parity the record barriers complete during the current unit
+    const uint32_t rbar = smem_u32(rbar_s);
+    // optional phase timers (AV1R_K3_PROF): thread 0 of the CTA for the unit phases, lane 0 of every warp for the record phases
+    long long tp = 0;
+    auto lap = [&](int slot, bool who) {
+        if (L.prof && who) {
+            const long long t = clock64();
+            atomicAdd(L.prof + slot, (unsigned long long)(t - tp));
+            tp = t;
+        }
+    };
+    if (L.prof) tp = clock64();
+    while (true) {
+        if (tid == 0) us->unit = atomicAdd(L.ticket, 1);
+        __syncthreads();
+        const int u = us->unit;
+        if (u >= L.n_units) return;
+        lap(0, tid == 0);   // ticket
+        const K3Unit* up = L.units + u;
+        const int first = (int)__ldg(&up->first), count = (int)__ldg(&up->count);
+        const int ux = __ldg(&up->ux), uy = __ldg(&up->uy);
+        // ---- prologue (needs nothing from other units): residual bulk copy, context, owner map
+        if (tid == 0) {
+            us->next = 0;
+            mbar_expect_tx(bar, unit_bytes);
+            bulk_g2s(smem_u32(res_s), L.res.base + ((size_t)uy * L.res.units_x + ux) * L.res.unit_elems, unit_bytes, bar);
+        }
+        UnitCtx<T> uc;
+        uc.canvas = canvas;
+        uc.lext = lext_s;
+        uc.res = res_s;
+        uc.ux = ux;
+        uc.uy = uy;
+        for (int i = tid; i < OWNER_CELLS; i += nthr) owner[i] = -1;
+        for (int i = tid; i < max(count, inited); i += nthr) {
+            if (i >= inited) {   // first use: create the barrier and bring it to the CTA's current phase
+                mbar_init(rbar + 8u * i, 1);
+                if (rpar) mbar_arrive(rbar + 8u * i);
+            } else if (i >= count) {
+                mbar_arrive(rbar + 8u * i);   // not used by this unit: keep its phase in step
+            }
+        }
+        inited = max(inited, count);
+        __syncthreads();
+        for (int k0 = warp * 32; k0 < count; k0 += nw * 32) {   // owner map: local index of the record that reconstructs each 4x4 cell
+            uint2 hd = make_uint2(0, 0);
+            if (k0 + lane < count) hd = __ldg(reinterpret_cast<const uint2*>(L.recs + __ldg(L.order + first + k0 + lane)));
+            const int nb = min(32, count - k0);
+            for (int j = 0; j < nb; j++) {
+                const uint32_t hx = __shfl_sync(0xffffffffu, hd.x, j), hy = __shfl_sync(0xffffffffu, hd.y, j);
+                const int x4 = hx & 0xffff, y4 = hx >> 16, plane = hy & 0xff, txsz = (hy >> 8) & 0xff;
+                const int lw4 = tx_lw(txsz) - 2, w4 = 1 << lw4, h4 = 1 << (tx_lh(txsz) - 2);
+                const int uw4 = plane ? 8 : 16;
+                const int lx4 = x4 - ux * uw4, ly4 = y4 - uy * uw4;
+                int32_t* m = owner + (plane == 0 ? 0 : (plane == 1 ? 256 : 320));
+                for (int c = lane; c < w4 * h4; c += 32) {
+                    const int cy = ly4 + (c >> lw4), cx = lx4 + (c & (w4 - 1));
+                    if (cx >= 0 && cy >= 0 && cx < uw4 && cy < uw4) atomicMax(m + cy * uw4 + cx, k0 + j);
+                }
+            }
+        }
+        lap(1, tid == 0);   // prologue: context, owner map
+        // ---- wait for the neighbour units whose samples this unit reads
+        if (warp == 0) {
+            if (lane < 5) {
+                const int d = __ldg(&up->dep[lane]);
+                if (d >= 0) {
+                    int spins = 0;
+                    while (ld_acquire(L.uflags + d) == 0) {   // <= 5 polling lanes per CTA
+                        __nanosleep(40);
+                        if (++spins > (1 << 26)) { L.ticket[1] = 2; break; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        lap(2, tid == 0);   // neighbour units
+        // ---- halo (and, in inter frames, the unit's own inter-predicted samples) from L2
+        {   // row above (corner .. above-right) and column to the left (.. below-left) of the three planes: one flat index space, all
+            // loads of a thread issued before the first store, so the halo costs one L2 round trip
+            constexpr int SEG0 = 2 * (2 * CV_W0 + 1), SEG1 = 2 * (2 * CV_W1 + 1);   // per plane: [row: 2W + 1][col: 2W] (+1 pad)
+            constexpr int TOT = SEG0 + 2 * SEG1;
+            constexpr int PER = (TOT + nthr - 1) / nthr;
+            // decode element e -> global source (null: nothing to fetch) and canvas destination
+            auto halo = [&](int e, const T*& src, T*& dst) {
+                src = nullptr;
+                dst = nullptr;
+                if (e >= TOT) return;
+                const int p = e < SEG0 ? 0 : (e < SEG0 + SEG1 ? 1 : 2);
+                const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
+                const int i = e - (p == 0 ? 0 : (p == 1 ? SEG0 : SEG0 + SEG1));
+                const int x0 = ux * W, y0 = uy * W;
+                const uint8_t* fb = L.frame.p[p];
+                const uint32_t pitch = L.frame.pitch[p];
+                if (i < 2 * W + 1) {
+                    const int dx = i - 1;
+                    if (y0 > 0 && x0 + dx >= 0 && x0 + dx < fp.cw[p]) {
+                        src = reinterpret_cast<const T*>(fb + (size_t)(y0 - 1) * pitch) + x0 + dx;
+                        dst = uc.cv(p) - cs + dx;
+                    }
+                } else {
+                    const int dy = i - (2 * W + 1);
+                    if (x0 > 0 && dy < 2 * W && y0 + dy < fp.ch[p]) {
+                        src = reinterpret_cast<const T*>(fb + (size_t)(y0 + dy) * pitch) + x0 - 1;
+                        dst = dy < W ? uc.cv(p) + dy * cs - 1 : uc.lext + uc.lext_off(p) + (dy - W);
+                    }
+                }
+            };
+            T v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const T* src;
+                T* dst;
+                halo(tid + j * nthr, src, dst);
+                v[j] = src ? __ldcg(src) : (T)0;
+            }
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const T* src;
+                T* dst;
+                halo(tid + j * nthr, src, dst);
+                if (dst) *dst = v[j];
+            }
+        }
+        if (L.load_tile || (fp.sb128 && (uy & 1) && !(ux & 1))) {
+            for (int p = 0; p < 3; p++) {
+                const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
+                const int x0 = ux * W, y0 = uy * W;
+                const int cw = fp.cw[p], ch = fp.ch[p];
+                const uint8_t* fb = L.frame.p[p];
+                const uint32_t pitch = L.frame.pitch[p];
+                T* cv = uc.cv(p);
+                const int vw = min(W, cw - x0), vh = min(W, ch - y0);
+                if (L.load_tile) {   // inter frame: the unit's own inter-predicted samples
+                    const int wpr = vw * (int)sizeof(T) / 4;
+                    for (int i = tid; i < vh * wpr; i += nthr) {
+                        const int row = i / wpr, wi = i - row * wpr;
+                        reinterpret_cast<uint32_t*>(cv + row * cs)[wi] =
+                            __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T)) + wi);
+                    }
+                }
+                if (fp.sb128 && (uy & 1) && !(ux & 1)) {   // bottom-left unit of a 128x128 superblock: above-right samples inside the top-right unit
+                    const int rw = min(W, cw - x0 - W);
+                    const int wpr = rw > 0 ? rw * (int)sizeof(T) / 4 : 0;
+                    const int rows = min(W - 1, ch - y0);
+                    for (int i = tid; i < rows * wpr; i += nthr) {
+                        const int row = i / wpr, wi = i - row * wpr;
+                        reinterpret_cast<uint32_t*>(cv + row * cs + W)[wi] =
+                            __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)(x0 + W) * sizeof(T)) + wi);
+                    }
+                }
+            }
+        }
+        lap(3, tid == 0);   // halo loads
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        __syncthreads();
+        lap(4, tid == 0);   // residual bulk copy
+        if (L.prof && lane == 0 && tid != 0) tp = clock64();
+        // ---- record-level dataflow inside the unit
+        // Records are dealt round-robin to the warps (record k -> warp k mod NW; a warp walks its records in order, so the lowest
+        // unfinished record can always run) and the next record is fetched while the current one waits and predicts.
+        WarpScratch& sm = wscr[warp];
+        int k = warp;
+        TxRec r_next;
+        if (k < count) r_next = load_rec(L.recs + __ldg(L.order + first + k));
+        for (; k < count; k += nw) {
+            const TxRec r = r_next;
+            if (k + nw < count) r_next = load_rec(L.recs + __ldg(L.order + first + k + nw));
+            lap(8, lane == 0);   // record fetch
+            if (r.mode == TXM_INTER) {
+                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.ticket + 1);   // residual of an inter-intra block: after its blend
+            } else if (r.mode != TXM_PALETTE) {
+                const int plane = r.plane;
+                const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
+                const int pw4 = fp.pw4[plane], ph4 = fp.ph4[plane];
+                const int uw4 = plane ? 8 : 16;
+                const int bx4 = ux * uw4, by4 = uy * uw4;
+                const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
+                int need_ar = 0, need_bl = 0;
+                if (r.mode >= V_PRED && r.mode <= D67_PRED) {
+                    const int p_angle = c_mode_angle[r.mode] + r.angle_delta * 3;
+                    need_ar = p_angle < 90 && (r.flags & TXF_HAVE_ABOVE_RIGHT);
+                    need_bl = p_angle > 180 && (r.flags & TXF_HAVE_BELOW_LEFT);
+                }
+                // V_PRED reads only the row above, H_PRED only the left column (unless that edge is missing and the other one stands in)
+                const int want_above = have_above && !(r.mode == H_PRED && r.angle_delta == 0 && have_left);
+                const int want_left = have_left && !(r.mode == V_PRED && r.angle_delta == 0 && have_above);
+                const int na = want_above ? w4 * (need_ar ? 2 : 1) + 1 : 0;      // cells x4-1 .. on row y4-1 (the first is the corner)
+                const int nl = want_left ? h4 * (need_bl ? 2 : 1) : 0;            // cells y4 .. on column x4-1
+                const int32_t* m = owner + (plane == 0 ? 0 : (plane == 1 ? 256 : 320));
+                for (int c0 = 0; c0 < na + nl; c0 += 32) {       // warp-uniform trip count: the wait is collective
+                    const int c = c0 + lane;
+                    int id = -1;
+                    if (c < na + nl) {
+                        int cx, cy;
+                        if (c < na) {
+                            cx = r.x4 - 1 + c;
+                            cy = r.y4 - 1;
+                        } else {
+                            cx = r.x4 - 1;
+                            cy = r.y4 + (c - na);
+                        }
+                        cx = min(max(cx, 0), pw4 - 1) - bx4;
+                        cy = min(max(cy, 0), ph4 - 1) - by4;
+                        if (cx >= 0 && cy >= 0 && cx < uw4 && cy < uw4) {   // cells of other units were final before the unit started
+                            id = m[cy * uw4 + cx];
+                            if (id >= k) id = -1;
+                        }
+                    }
+                    wait_local(rbar, id, rpar, L.ticket + 1);
+                }
+                if (r.mode == TXM_CFL) {   // luma samples under this chroma block
+                    const int sx = fp.subx, sy = fp.suby;
+                    const int lx0 = (r.x4 << sx), ly0 = (r.y4 << sy);
+                    const int lx1 = min((r.x4 + w4) << sx, (int)r.cfl_max_w4), ly1 = min((r.y4 + h4) << sy, (int)r.cfl_max_h4);
+                    const int lw4 = max(lx1 - lx0, 0), lh4 = max(ly1 - ly0, 0);
+                    for (int c0 = 0; c0 < lw4 * lh4; c0 += 32) {
+                        const int c = c0 + lane;
+                        int id = -1;
+                        if (c < lw4 * lh4) {
+                            const int cx = lx0 + c % lw4 - ux * 16, cy = ly0 + c / lw4 - uy * 16;
+                            if (cx >= 0 && cy >= 0 && cx < 16 && cy < 16) {
+                                id = owner[cy * 16 + cx];
+                                if (id >= k) id = -1;
+                            }
+                        }
+                        wait_local(rbar, id, rpar, L.ticket + 1);
+                    }
+                }
+            }
+            // the waits acquire (mbarrier test/try_wait) what the owners released with their arrive; __syncwarp orders the lanes
+            __syncwarp();
+            lap(9, lane == 0);   // dependency wait
+            intra_block<T>(r, uc, fp, sm, lane, L.wedge_master, L.pal);
+            __syncwarp();        // all lanes' samples are in the canvas before lane 0 releases the record's barrier
+            if (lane == 0) mbar_arrive(rbar + 8u * (uint32_t)k);
+            lap(10, lane == 0);  // predict + reconstruct
+            if (L.prof && lane == 0) atomicAdd(L.prof + 12, 1ull);
+        }
+        lap(11, lane == 0 && tid != 0);   // warp idle at the end of the unit
+        __syncthreads();
+        lap(5, tid == 0);   // dataflow (CTA view)
+        // ---- write the unit back (coalesced 32-bit words; coded plane widths are multiples of 4 samples)
+        for (int p = 0; p < 3; p++) {
+            const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
+            const int x0 = ux * W, y0 = uy * W;
+            const int vw = min(W, fp.cw[p] - x0), vh = min(W, fp.ch[p] - y0);
+            uint8_t* fb = L.frame.p[p];
+            const uint32_t pitch = L.frame.pitch[p];
+            const T* cv = uc.cv(p);
+            const int wpr = vw * (int)sizeof(T) / 4;
+            for (int i = tid; i < vh * wpr; i += nthr) {
+                const int row = i / wpr, wi = i - row * wpr;
+                reinterpret_cast<uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T))[wi] =
+                    reinterpret_cast<const uint32_t*>(cv + row * cs)[wi];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(L.uflags + u, 1);
+        rpar ^= 1;
+        lap(6, tid == 0);   // write-back + release
+        if (L.prof && tid == 0) atomicAdd(L.prof + 13, 1ull);
     }
 }
 
-// 2. the dataflow kernel
-template <typename T>
-__global__ void __launch_bounds__(INTRA_WARPS * 32) intra_dataflow_kernel(IntraLaunch L) {
-    __shared__ IntraSmem s_sm[INTRA_WARPS];
-    const int warp_in = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    IntraSmem& sm = s_sm[warp_in];
-    const DevFrameParams& fp = L.fp;
-    FrameView<T> uv;
-    for (int pl = 0; pl < 3; pl++) {
-        uv.p[pl] = L.frame.p[pl];
-        uv.pitch[pl] = L.frame.pitch[pl];
-    }
-    while (true) {
-        // persistent warps claim records in K3 order; the grid (L.ctas) bounds the ticket window of one frame so that the frames
-        // in flight on other streams share the machine instead of one frame's spinning warps monopolising it
-        int pos = 0;
-        if (lane == 0) pos = atomicAdd(L.ticket, 1);
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (pos >= L.n) return;
-        __syncwarp();
-        const TxRec r = L.recs[L.order[pos]];
-        // residual of small blocks: fetch now (it has no dependency), so it is off the critical path after the wait
-        if (r.eob > 0) {
-            const int lw = c_itxw_log2[r.txsz], w = 1 << lw, n = w << c_itxh_log2[r.txsz];
-            if (n <= 256) {
-                const int16_t* rp = res_ptr(L.res, r.plane, r.x4 * 4, r.y4 * 4);
-                const int rpitch = 1 << L.res.tw_log2[r.plane];
-                for (int idx = lane; idx < n; idx += 32) sm.res[idx] = __ldg(rp + (idx >> lw) * rpitch + (idx & (w - 1)));
-            }
-        }
-        // ---- wait for the owners of everything this record reads
-        if (r.mode == TXM_INTER) {
-            if (r.flags & TXF_II) {   // residual of an inter-intra block: after its blend record
-                if (lane == 0) wait_flag(L.flags, (int)r.pal_off);
-            }
-        } else if (r.mode != TXM_PALETTE) {
-            const int plane = r.plane;
-            const int w4 = 1 << (c_itxw_log2[r.txsz] - 2), h4 = 1 << (c_itxh_log2[r.txsz] - 2);
-            const int pw4 = fp.pw4[plane], ph4 = fp.ph4[plane];
-            const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
-            int need_ar = 0, need_bl = 0;
-            if (r.mode >= V_PRED && r.mode <= D67_PRED) {
-                const int kModeToAngle[9] = {0, 90, 180, 45, 135, 113, 157, 203, 67};
-                const int p_angle = kModeToAngle[r.mode] + r.angle_delta * 3;
-                need_ar = p_angle < 90 && (r.flags & TXF_HAVE_ABOVE_RIGHT);
-                need_bl = p_angle > 180 && (r.flags & TXF_HAVE_BELOW_LEFT);
-            }
-            // V_PRED reads only the row above, H_PRED only the left column (unless that edge is missing and the other one stands in)
-            const int want_above = have_above && !(r.mode == H_PRED && r.angle_delta == 0 && have_left);
-            const int want_left = have_left && !(r.mode == V_PRED && r.angle_delta == 0 && have_above);
-            const int na = want_above ? w4 * (need_ar ? 2 : 1) + 1 : 0;      // cells x4-1 .. on row y4-1 (the first is the corner)
-            const int nl = want_left ? h4 * (need_bl ? 2 : 1) : 0;            // cells y4 .. on column x4-1
-            const int32_t* m = L.wmap[plane];
-            for (int c0 = 0; c0 < na + nl; c0 += 32) {       // warp-uniform trip count: the wait is collective
-                const int c = c0 + lane;
-                int id = -1;
-                if (c < na + nl) {
-                    int cx, cy;
-                    if (c < na) {
-                        cx = r.x4 - 1 + c;
-                        cy = r.y4 - 1;
-                    } else {
-                        cx = r.x4 - 1;
-                        cy = r.y4 + (c - na);
-                    }
-                    cx = min(max(cx, 0), pw4 - 1);
-                    cy = min(max(cy, 0), ph4 - 1);
-                    id = __ldg(m + (size_t)cy * pw4 + cx);
-                    if (id >= pos) id = -1;
-                }
-                wait_deps_warp(L.flags, id, lane);
-            }
-            if (r.mode == TXM_CFL) {   // luma samples under this chroma block
-                const int sx = fp.subx, sy = fp.suby;
-                const int lx0 = (r.x4 << sx), ly0 = (r.y4 << sy);
-                const int lx1 = min((r.x4 + w4) << sx, (int)r.cfl_max_w4), ly1 = min((r.y4 + h4) << sy, (int)r.cfl_max_h4);
-                const int lw4 = max(lx1 - lx0, 0), lh4 = max(ly1 - ly0, 0);
-                const int lpw4 = fp.pw4[0];
-                for (int c0 = 0; c0 < lw4 * lh4; c0 += 32) {
-                    const int c = c0 + lane;
-                    int id = -1;
-                    if (c < lw4 * lh4) {
-                        id = __ldg(L.wmap[0] + (size_t)(ly0 + c / lw4) * lpw4 + lx0 + c % lw4);
-                        if (id >= pos) id = -1;
-                    }
-                    wait_deps_warp(L.flags, id, lane);
-                }
-            }
-        }
-        __syncwarp();
-        __threadfence();   // acquire: the owners' samples are visible in L2
-        intra_block<T>(r, L.frame, L.res, fp, sm, uv, lane, L.wedge_master, L.pal);
-        __threadfence();   // release: this record's samples before its flag
-        __syncwarp();
-        if (lane == 0) *(volatile int*)(L.flags + pos) = 1;
-    }
+static size_t k3_smem_bytes(int bps, int warps) {
+    return RES_ELEMS * sizeof(int16_t) + (size_t)(CV_ELEMS + 128) * bps + OWNER_CELLS * 4 + K3_UNIT_MAX_RECS * 8 + 64 + (size_t)warps * sizeof(WarpScratch);
 }
 
 static cudaError_t intra_upload_constants() {
@@ -588,24 +858,29 @@ static cudaError_t intra_upload_constants() {
     if ((e = cudaMemcpyToSymbol(c_ii_signflip, av1t_wedge_signflip, sizeof(av1t_wedge_signflip))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_ii_blk_w, kBlockW, sizeof(kBlockW))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_ii_blk_h, kBlockH, sizeof(kBlockH))) != cudaSuccess) return e;
+    const size_t mx = k3_smem_bytes(2, K3_MAX_WARPS);
+    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint8_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint8_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint16_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
     if (dev < 64) g_intra_const_loaded[dev] = true;
     return cudaSuccess;
 }
 
 cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s) {
-    if (L.n <= 0) return cudaSuccess;
+    if (L.n_units <= 0) return cudaSuccess;
+    if (L.fp.subx != 1 || L.fp.suby != 1 || L.fp.mono) return cudaErrorInvalidValue;   // the canvas geometry is 4:2:0
     cudaError_t e = intra_upload_constants();
     if (e != cudaSuccess) return e;
-    wmap_scatter_kernel<<<(L.n + 3) / 4, 128, 0, s>>>(L);
-    const int blocks = std::min((L.n + INTRA_WARPS - 1) / INTRA_WARPS, std::max(1, L.ctas));
-    static bool attr_done = false;
-    if (!attr_done) {   // 14 KB of static shared memory per 2-warp CTA: ask for the large carve-out so 15 CTAs fit per SM
-        cudaFuncSetAttribute(intra_dataflow_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(intra_dataflow_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_done = true;
+    const int warps = L.warps <= 4 ? 4 : 8;
+    const int blocks = std::min(L.n_units, std::max(1, L.ctas));
+    if (L.fp.bd == 8) {
+        if (warps == 4) intra_unit_kernel<uint8_t, 4><<<blocks, 128, k3_smem_bytes(1, 4), s>>>(L);
+        else intra_unit_kernel<uint8_t, 8><<<blocks, 256, k3_smem_bytes(1, 8), s>>>(L);
+    } else {
+        if (warps == 4) intra_unit_kernel<uint16_t, 4><<<blocks, 128, k3_smem_bytes(2, 4), s>>>(L);
+        else intra_unit_kernel<uint16_t, 8><<<blocks, 256, k3_smem_bytes(2, 8), s>>>(L);
     }
-    if (L.fp.bd == 8) intra_dataflow_kernel<uint8_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
-    else intra_dataflow_kernel<uint16_t><<<blocks, INTRA_WARPS * 32, 0, s>>>(L);
     return cudaGetLastError();
 }
 

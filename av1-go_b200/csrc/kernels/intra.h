@@ -8,17 +8,21 @@ namespace av1r {
 
 struct IntraLaunch {            // passed by value
     const TxRec* recs;          // device, all records of the frame
-    const uint32_t* order;      // device, K3 order: indices of the records K3 owns (intra, palette, inter-intra blend + residual)
+    const uint32_t* order;      // device, K3 order: indices of the records K3 owns (intra, palette, inter-intra blend + residual), grouped by unit
     int n;                      // entries in order
-    int ctas;                   // persistent CTAs (2 warps each) this frame may occupy = its ticket window / 2
-    int32_t* wmap[3];           // device, per plane [ph4][pw4]: owner position of every 4x4 cell, pre-set to -1
-    int* flags;                 // device, n ints, zeroed before launch: done flag per position
+    const K3Unit* units;        // device, unit table in wavefront order
+    int n_units;
+    int ctas;                   // persistent CTAs this frame may occupy (one unit per CTA at a time)
+    int warps;                  // warps per CTA (records of a unit in flight)
+    int load_tile;              // 1: the frame already holds inter-predicted samples (inter frame) -> bring the unit in before predicting
+    int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
     int* ticket;                // device, one int, zeroed before launch
     DevPlanes frame;
     DevResidual res;
     DevFrameParams fp;
     const uint8_t* wedge_master;   // device, 6 x 64 x 64 (inter-intra wedge blends)
     const uint8_t* pal;            // device, palette entries (colours + colour index maps)
+    unsigned long long* prof;      // device, 16 cycle counters (AV1R_K3_PROF=1) or null
 };
 
 cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s);

@@ -107,6 +107,17 @@ struct SbRange {
 };
 static_assert(sizeof(SbRange) == 32, "SbRange must stay 32 bytes");
 
+// One 64x64 luma unit that holds K3 (intra / palette / inter-intra) records: the intra kernel keeps the unit on chip and
+// hands finished units to its neighbours.  Units are listed in wavefront order (superblock anti-diagonal, then decode order),
+// so every dependency has a lower table index.
+struct K3Unit {
+    uint32_t first, count;  // positions in the K3 order list
+    uint16_t ux, uy;        // unit position in 64-luma-sample units
+    int32_t dep[5];         // table indices of the left, below-left, above-left, above, above-right units to wait for (-1: none)
+};
+static_assert(sizeof(K3Unit) == 32, "K3Unit must stay 32 bytes");
+static constexpr int K3_UNIT_MAX_RECS = 640;    // per-record barrier capacity of the intra kernel per unit (4:2:0 worst case is 576)
+
 // Per-4x4 loop-filter description, one byte pair per plane 4x4 unit and direction:
 //   len: 0 = no edge here, else filter length 4 / 6 / 8 / 14 (13 for luma-wide is stored as 14)
 //   lvl: filter level 0..63 to use for this edge
