@@ -230,11 +230,11 @@ TOOL_NAMES = ["inter_blocks", "compound_avg", "compound_dist", "compound_wedge",
               "vartx_split", "switchable_filter", "palette", "intrabc"]
 
 
-STAGES = ["h2d", "itx", "intra", "inter", "deblock", "cdef", "lr", "grain", "digest"]
+STAGES = ["h2d", "itx", "intra", "inter", "deblock", "cdef", "lr", "grain", "digest", "superres"]
 
 
 class StageTimes(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("ms", C.c_float * 9), ("launches", C.c_int * 9)]
+    _fields_ = [("struct_size", C.c_uint32), ("ms", C.c_float * len(STAGES)), ("launches", C.c_int * len(STAGES))]
 
 
 class Clip:

@@ -149,7 +149,8 @@ static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
 
 struct DevWork {
     WorkLayout lay;
-    DevFrameParams fp;
+    DevFrameParams fp;       // geometry the frame is reconstructed at (coded width; downscaled when use_superres)
+    DevFrameParams fp_up;    // geometry of the frame that is output / kept as a reference (== fp without superres)
     FrameHdr fh;
     int lf_on = 0, lf_plane_on[3] = {0, 0, 0}, cdef_on = 0, lr_on = 0;
     uint64_t coded_samples = 0, coef_tokens = 0;
@@ -170,7 +171,7 @@ static void fill_params(const SeqHdr& seq, const FrameWork& fw, DevFrameParams& 
     fp.sb128 = seq.use_128x128_superblock;
     for (int p = 0; p < 3; p++) {
         const int sx = p ? fp.subx : 0, sy = p ? fp.suby : 0;
-        fp.w[p] = (fh.upscaled_width + sx) >> sx;
+        fp.w[p] = (fh.frame_width + sx) >> sx;
         fp.h[p] = (fh.frame_height + sy) >> sy;
         fp.cw[p] = (fh.mi_cols * 4) >> sx;
         fp.ch[p] = (fh.mi_rows * 4) >> sy;
@@ -610,13 +611,51 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         if (tm) tm->end(AV1R_ST_CDEF, 1, st);
         cur = dst;
     }
+    std::shared_ptr<DevFrameBuf> deblocked = recon;
+    const DevFrameParams& fpu = dw.fp_up;
+    if (dw.fh.use_superres) {   // K6: stretch the CDEF output (and, for the stripe boundaries of loop restoration, the deblocked frame)
+        SuperresLaunch sl;
+        sl.planes = fp.mono ? 1 : 3;
+        sl.bd = fp.bd;
+        for (int p = 0; p < 3; p++) {
+            const int sx = p ? fp.subx : 0;
+            const int down_w = (dw.fh.frame_width + sx) >> sx, up_w = (dw.fh.upscaled_width + sx) >> sx;
+            const int step = ((down_w << 14) + (up_w / 2)) / up_w;
+            const int e = up_w * step - (down_w << 14);
+            sl.step_x[p] = step;
+            sl.initial_subpel_x[p] = ((-((up_w - down_w) << 13) + up_w / 2) / up_w + (1 << 7) - e / 2) & ((1 << 14) - 1);
+            sl.up_w[p] = up_w;
+            sl.h[p] = fpu.h[p];
+            sl.src_cw[p] = fp.cw[p];
+        }
+        const bool need_db = dw.lr_on && (cfg.inloop_filters & 4) && cur != recon;
+        auto up = get_frame(fpu);
+        if (!up) return AV1R_ENOMEM;
+        s.hold.push_back(up);
+        sl.src = cur->pl;
+        sl.dst = up->pl;
+        CK(launch_superres(sl, st));
+        if (need_db) {
+            auto upd = get_frame(fpu);
+            if (!upd) return AV1R_ENOMEM;
+            s.hold.push_back(upd);
+            sl.src = recon->pl;
+            sl.dst = upd->pl;
+            CK(launch_superres(sl, st));
+            deblocked = upd;
+        } else {
+            deblocked = up;
+        }
+        if (tm) tm->end(AV1R_ST_SUPERRES, need_db ? 2 : 1, st);
+        cur = up;
+    }
     if (dw.lr_on && (cfg.inloop_filters & 4)) {
-        auto dst = get_frame(fp);
+        auto dst = get_frame(fpu);
         if (!dst) return AV1R_ENOMEM;
         s.hold.push_back(dst);
         LrLaunch ll;
         ll.cdef = cur->pl;
-        ll.deblocked = recon->pl;
+        ll.deblocked = deblocked->pl;
         ll.dst = dst->pl;
         for (int p = 0; p < 3; p++) {
             ll.units[p] = (const LrUnitDev*)(d_arena + L.lr[p]);
@@ -625,7 +664,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             ll.unit_rows[p] = dw.lr_rows[p];
             ll.unit_cols[p] = dw.lr_cols[p];
         }
-        ll.fp = fp;
+        ll.fp = fpu;
         CK(launch_lr(ll, st));
         if (tm) tm->end(AV1R_ST_LR, 1, st);
         cur = dst;
@@ -717,9 +756,22 @@ int EngineImpl::acquire_slot(int& slot_idx) {
     return 0;
 }
 
+static void upscaled_params(const FrameHdr& fh, const DevFrameParams& fp, DevFrameParams& up) {
+    up = fp;
+    if (!fh.use_superres) return;
+    up.mi_cols = 2 * ((fh.upscaled_width + 7) >> 3);
+    for (int p = 0; p < 3; p++) {
+        const int sx = p ? fp.subx : 0;
+        up.w[p] = (fh.upscaled_width + sx) >> sx;
+        up.cw[p] = (up.mi_cols * 4) >> sx;
+        up.pw4[p] = (up.mi_cols + sx) >> sx;
+    }
+}
+
 static int prepare_work_seq(const SeqHdr& seq, const FrameWork& fw, DevWork& dw, std::string& err) {
     if (fw.fh.using_qmatrix) { err = "quantiser matrices are not supported yet"; return AV1R_ENOSYS; }
     fill_params(seq, fw, dw.fp);
+    upscaled_params(fw.fh, dw.fp, dw.fp_up);
     dw.fh = fw.fh;
     dw.lf_on = fw.fh.lf.level[0] || fw.fh.lf.level[1];
     dw.lf_plane_on[0] = dw.lf_on;
@@ -763,6 +815,11 @@ int EngineImpl::exec_show_existing(int slot_idx, const FrameHdr& fh, int show_sl
     FrameWork dummy;
     dummy.fh = fh;
     fill_params(sp.hp.seq, dummy, fp);
+    {
+        DevFrameParams up;
+        upscaled_params(fh, fp, up);
+        fp = up;
+    }
     CK(cudaEventRecord(s.ev0, s.stream));
     int rc = emit_output(&s, slot_idx, f, fh, fh.fg, fp, pts, 0, true);
     if (rc) return rc;
@@ -782,7 +839,7 @@ int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_a
     for (int i = 0; i < 8; i++)
         if ((dw.fh.refresh_frame_flags >> i) & 1) rs->refs[i] = out;
     if (dw.fh.show_frame) {
-        rc = emit_output(&s, slot_idx, out, dw.fh, dw.fh.fg, dw.fp, pts, dw.parse_ms, false);
+        rc = emit_output(&s, slot_idx, out, dw.fh, dw.fh.fg, dw.fp_up, pts, dw.parse_ms, false);
         if (rc) return rc;
     }
     CK(cudaEventRecord(s.ev1, s.stream));

@@ -80,11 +80,34 @@ struct LrUnit {
     int8_t sgr_xqd[2];
 };
 
+// Growable array of coefficient tokens without value-initialisation: the coefficient reader appends up to eob tokens per
+// transform block through a raw pointer (std::vector::resize would zero-fill them first).
+struct TokenBuf {
+    uint32_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    TokenBuf() = default;
+    TokenBuf(const TokenBuf&) = delete;
+    TokenBuf& operator=(const TokenBuf&) = delete;
+    ~TokenBuf() { free(p); }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void clear() { n = 0; }
+    const uint32_t* begin() const { return p; }
+    const uint32_t* end() const { return p + n; }
+    uint32_t* tail(size_t extra) {   // room for `extra` more tokens; returns the write position (size is unchanged)
+        if (n + extra > cap) {
+            cap = std::max<size_t>(2 * cap, n + extra + 4096);
+            p = static_cast<uint32_t*>(realloc(p, cap * sizeof(uint32_t)));
+        }
+        return p + n;
+    }
+};
+
 // What one tile's parse produces.  Tiles are independent given the frame's initial CDFs, so they are parsed concurrently, each
 // into its own TileOut; StreamParser merges the lists in tile order (offsets inside the records are rebased there).
 struct TileOut {
     std::vector<TxRec> tx;
-    std::vector<uint32_t> coefs;
+    TokenBuf coefs;
     std::vector<SbRange> sbs;
     std::vector<uint8_t> pal;
     std::vector<InterBlk> inter;

@@ -59,6 +59,16 @@ struct LrLaunch {
 };
 cudaError_t launch_lr(const LrLaunch& L, cudaStream_t s);
 
+// K6 super-resolution: stretches `src` (coded width) to `dst` (upscaled width), spec 7.16
+struct SuperresLaunch {
+    DevPlanes src, dst;
+    int planes, bd;
+    int up_w[3], h[3];            // visible size of the upscaled planes
+    int src_cw[3];                // coded width of the source planes ((MiCols >> subX) * 4): the clamp range of the taps
+    int step_x[3], initial_subpel_x[3];
+};
+cudaError_t launch_superres(const SuperresLaunch& L, cudaStream_t s);
+
 cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s);
 
 }  // namespace av1r

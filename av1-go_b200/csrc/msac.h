@@ -4,6 +4,10 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#define AV1R_MSAC_SSE2 1
+#endif
 
 namespace av1r {
 
@@ -44,6 +48,9 @@ struct Msac {
     // all symbols) take a branch-free path: entropy-coded symbols are unpredictable by construction, so a
     // compare-and-count beats the data-dependent search loop.
     __attribute__((always_inline)) inline int symbol(uint16_t* c, int n) {
+#ifdef AV1R_MSAC_SSE2
+        if (n == 3 || n == 4) return symbol_v4(c, n);
+#endif
         const uint32_t r = rng;
         const uint32_t v16 = (uint32_t)(dif >> 48);
         const uint32_t r8 = r >> 8;
@@ -71,6 +78,41 @@ struct Msac {
         if (update) adapt(c, s, n);
         return s;
     }
+#ifdef AV1R_MSAC_SSE2
+    // 3- and 4-symbol alphabets (coefficient base levels, base-range increments, end-of-block base: ~90 % of all symbols):
+    // the three candidate split points, the comparison with the window and the probability adaptation run on four 16-bit lanes.
+    // The 64-bit load/store covers c[0..3]: probabilities, the zero sentinel c[n-1] and (n == 3) the adaptation counter, which
+    // the lane mask leaves untouched.
+    __attribute__((always_inline)) inline int symbol_v4(uint16_t* c, int n) {
+        const uint32_t r = rng;
+        const uint32_t v16 = (uint32_t)(dif >> 48);
+        const __m128i cv = _mm_loadl_epi64(reinterpret_cast<const __m128i*>(c));
+        const __m128i en = n == 4 ? _mm_set_epi16(0, 0, 0, 0, 0, -1, -1, -1) : _mm_set_epi16(0, 0, 0, 0, 0, 0, -1, -1);   // lanes < n - 1
+        const __m128i mp = n == 4 ? _mm_set_epi16(0, 0, 0, 0, 0, 4, 8, 12) : _mm_set_epi16(0, 0, 0, 0, 0, 0, 4, 8);        // 4 * (n - 1 - i)
+        // ((r >> 8) * (c >> 6)) >> 1 == mulhi(r & 0xff00, (c >> 6) << 7)
+        __m128i v = _mm_mulhi_epu16(_mm_set1_epi16((short)(r & 0xff00)), _mm_slli_epi16(_mm_srli_epi16(cv, 6), 7));
+        v = _mm_and_si128(_mm_add_epi16(v, mp), en);
+        // lanes with v <= window (unsigned): the first one is the symbol (lane n - 1 holds 0, so there always is one)
+        const __m128i le = _mm_cmpeq_epi16(_mm_subs_epu16(v, _mm_set1_epi16((short)v16)), _mm_setzero_si128());
+        const int s = __builtin_ctz((unsigned)_mm_movemask_epi8(le) | 0x100u) >> 1;
+        alignas(16) uint16_t t[8];
+        _mm_storel_epi64(reinterpret_cast<__m128i*>(t), v);
+        const uint32_t vv = t[s], u = s ? t[s - 1] : r;
+        normalize(dif - ((uint64_t)vv << 48), u - vv);
+        if (update) {
+            const int cnt_ = c[n];
+            const __m128i rate = _mm_cvtsi32_si128(3 + (cnt_ > 15) + (cnt_ > 31) + (n > 3 ? 2 : 1));
+            const __m128i up = _mm_add_epi16(cv, _mm_srl_epi16(_mm_sub_epi16(_mm_set1_epi16((short)0x8000), cv), rate));
+            const __m128i dn = _mm_sub_epi16(cv, _mm_srl_epi16(cv, rate));
+            const __m128i lt = _mm_andnot_si128(le, en);                       // lanes i < s
+            __m128i nv = _mm_or_si128(_mm_and_si128(lt, up), _mm_andnot_si128(lt, dn));
+            nv = _mm_or_si128(_mm_and_si128(en, nv), _mm_andnot_si128(en, cv));   // sentinel / counter lanes keep their value
+            _mm_storel_epi64(reinterpret_cast<__m128i*>(c), nv);
+            c[n] = (uint16_t)(cnt_ + (cnt_ < 32));
+        }
+        return s;
+    }
+#endif
     __attribute__((always_inline)) static inline void adapt(uint16_t* c, int val, int n) {
         const int cnt_ = c[n];
         const int rate = 3 + (cnt_ > 15) + (cnt_ > 31) + (n > 3 ? 2 : 1);   // + Min(FloorLog2(n), 2)

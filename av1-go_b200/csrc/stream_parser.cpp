@@ -137,12 +137,13 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
     cur_->warps.resize(8);
     memset(cur_->warps.data(), 0, sizeof(WarpRec) * 8);
     if (hp.seq.mono_chrome) return fail(AV1R_ENOSYS, "monochrome streams are not supported yet");
-    if (fh.use_superres) return fail(AV1R_ENOSYS, "super-resolution is not supported yet");
+    // super-resolution: intra frames are reconstructed at the coded (downscaled) width and upscaled before loop restoration (K6);
+    // an inter frame coded with superres predicts from references of a different width (scaled motion compensation, not built)
     if (!fh.frame_is_intra) {
         for (int i = 0; i < REFS_PER_FRAME; i++) {
             const RefHdrState& r = hp.refs[fh.ref_frame_idx[i]];
             if (!r.valid) return fail(AV1R_EBITSTREAM, "inter frame references an empty slot");
-            if (r.upscaled_width != fh.upscaled_width || r.frame_height != fh.frame_height)
+            if (r.upscaled_width != fh.frame_width || r.frame_height != fh.frame_height)
                 return fail(AV1R_ENOSYS, "scaled reference frames are not supported yet");
         }
         // global warp models of the 7 references (spec 7.11.3.6 validity)

@@ -79,6 +79,7 @@ TileDecoder::TileDecoder(const SeqHdr& s, const HeaderParser& h, FrameWork& f, T
     above_seg_pred.assign(fw.mi_cols + 64, 0);
     left_seg_pred.assign(fw.mi_rows + 64, 0);
     memset(levels, 0, sizeof(levels));
+    memset(levels3, 0, sizeof(levels3));
 }
 
 void TileDecoder::clear_block_decoded_flags(int r, int c, int sb4) {
@@ -1221,51 +1222,32 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             }
         }
         if (eob > width * height) { fail(AV1R_EBITSTREAM, "eob exceeds transform size"); return 0; }
-        // levels, reverse scan.  lv[] is a zero-padded (stride = width + 4) byte map of min(level, 15): the
-        // neighbour sums of the context derivation never need a bounds check; touched entries are cleared on exit.
+        // levels, reverse scan.  lv[] / lv3[] are zero-padded (stride = width + 4) byte maps of min(level, 15) and min(level, 3):
+        // the neighbour sums of the context derivation need neither bounds checks nor clamps; the positions of the non-zero
+        // levels are chained in nz[] so that the sign pass (forward scan) visits and clears only those.
         const int ls = width + 4;
         uint8_t* lv = levels;
-        static const int8_t sig_ref[3][5][2] = {{{0, 1}, {1, 0}, {1, 1}, {0, 2}, {2, 0}},
-                                                {{0, 1}, {1, 0}, {0, 2}, {0, 3}, {0, 4}},
-                                                {{0, 1}, {1, 0}, {2, 0}, {3, 0}, {4, 0}}};
-        int so[5], mo[3];
-        for (int i = 0; i < 5; i++) so[i] = sig_ref[cls][i][0] * ls + sig_ref[cls][i][1];
-        mo[0] = 1; mo[1] = ls; mo[2] = cls == TX_CLASS_2D ? ls + 1 : (cls == TX_CLASS_HORIZ ? 2 : 2 * ls);
+        uint8_t* lv3 = levels3;
+        uint16_t nz[1024];
+        int nnz = 0;
         uint16_t (*cb_cdf)[5] = cdf.coeff_base[tx_ctx][ptype];
         uint16_t (*br_cdf)[5] = cdf.coeff_br[std::min(tx_ctx, 3)][ptype];
-        for (int c = eob - 1; c >= 0; c--) {
+        {   // last coefficient of the scan: coeff_base_eob
+            const int c = eob - 1;
             const int pos = scan[c];
             const int row = pos >> bwl, col = pos - (row << bwl);
-            uint8_t* lp = lv + row * ls + col;
-            int level;
-            if (c == eob - 1) {
-                int ectx;
-                if (c == 0) ectx = 0;
-                else if (c <= (height << bwl) / 8) ectx = 1;
-                else if (c <= (height << bwl) / 4) ectx = 2;
-                else ectx = 3;
-                level = ms.symbol(cdf.coeff_base_eob[tx_ctx][ptype][ectx], 3) + 1;
-            } else {
-                int mag = std::min<int>(lp[so[0]], 3) + std::min<int>(lp[so[1]], 3) + std::min<int>(lp[so[2]], 3) + std::min<int>(lp[so[3]], 3) +
-                          std::min<int>(lp[so[4]], 3);
-                int bctx = std::min((mag + 1) >> 1, 4);
-                if (cls == TX_CLASS_2D) {
-                    if (pos == 0) bctx = 0;
-                    else bctx += av1t_coeff_base_ctx_offset[txsz][std::min(row, 4)][std::min(col, 4)];
-                } else {
-                    const int idx = cls == TX_CLASS_VERT ? row : col;
-                    bctx += 26 + 5 * std::min(idx, 2);
-                }
-                level = ms.symbol(cb_cdf[bctx], 4);
-            }
+            int ectx;
+            if (c == 0) ectx = 0;
+            else if (c <= (height << bwl) / 8) ectx = 1;
+            else if (c <= (height << bwl) / 4) ectx = 2;
+            else ectx = 3;
+            int level = ms.symbol(cdf.coeff_base_eob[tx_ctx][ptype][ectx], 3) + 1;
             if (level > 2) {
-                int mag = lp[mo[0]] + lp[mo[1]] + lp[mo[2]];
-                mag = std::min((mag + 1) >> 1, 6);
                 int rctx;
-                if (pos == 0) rctx = mag;
-                else if (cls == TX_CLASS_2D) rctx = (row < 2 && col < 2) ? mag + 7 : mag + 14;
-                else if (cls == TX_CLASS_HORIZ) rctx = col == 0 ? mag + 7 : mag + 14;
-                else rctx = row == 0 ? mag + 7 : mag + 14;
+                if (pos == 0) rctx = 0;
+                else if (cls == TX_CLASS_2D) rctx = (row < 2 && col < 2) ? 7 : 14;
+                else if (cls == TX_CLASS_HORIZ) rctx = col == 0 ? 7 : 14;
+                else rctx = row == 0 ? 7 : 14;
                 uint16_t* bc = br_cdf[rctx];
                 for (int idx = 0; idx < 4; idx++) {
                     const int br = ms.symbol(bc, 4);
@@ -1273,62 +1255,112 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                     if (br < 3) break;
                 }
             }
-            *lp = (uint8_t)level;
+            const int off = pos + (row << 2);
+            lv[off] = (uint8_t)level;
+            lv3[off] = (uint8_t)std::min(level, 3);
+            nz[nnz++] = (uint16_t)pos;
         }
-        // signs + golomb, forward scan (tokens are written through a raw pointer: at most eob of them)
-        const size_t tok_base = to.coefs.size();
-        to.coefs.resize(tok_base + eob);
-        uint32_t* tok_out = to.coefs.data() + tok_base;
+        auto pass1 = [&](auto cls_c) {
+            constexpr int CLS = decltype(cls_c)::value;
+            // neighbour offsets of the base context (5 positions) and of the base-range context (3 positions), spec 8.3.2
+            const int s2 = CLS == TX_CLASS_2D ? ls + 1 : (CLS == TX_CLASS_HORIZ ? 2 : 2 * ls);
+            const int s3 = CLS == TX_CLASS_2D ? 2 : (CLS == TX_CLASS_HORIZ ? 3 : 3 * ls);
+            const int s4 = CLS == TX_CLASS_2D ? 2 * ls : (CLS == TX_CLASS_HORIZ ? 4 : 4 * ls);
+            const int m2 = CLS == TX_CLASS_2D ? ls + 1 : (CLS == TX_CLASS_HORIZ ? 2 : 2 * ls);
+            for (int c = eob - 2; c >= 0; c--) {
+                const int pos = scan[c];
+                const int row = pos >> bwl, col = pos - (row << bwl);
+                const int off = pos + (row << 2);
+                const uint8_t* l3 = lv3 + off;
+                const int mag3 = l3[1] + l3[ls] + l3[s2] + l3[s3] + l3[s4];
+                int bctx = std::min((mag3 + 1) >> 1, 4);
+                if (CLS == TX_CLASS_2D) {
+                    if (pos == 0) bctx = 0;
+                    else bctx += av1t_coeff_base_ctx_offset[txsz][std::min(row, 4)][std::min(col, 4)];
+                } else {
+                    const int idx = CLS == TX_CLASS_VERT ? row : col;
+                    bctx += 26 + 5 * std::min(idx, 2);
+                }
+                int level = ms.symbol(cb_cdf[bctx], 4);
+                if (level == 0) continue;
+                if (level > 2) {
+                    const uint8_t* lp = lv + off;
+                    const int mag = std::min((lp[1] + lp[ls] + lp[m2] + 1) >> 1, 6);
+                    int rctx;
+                    if (pos == 0) rctx = mag;
+                    else if (CLS == TX_CLASS_2D) rctx = (row < 2 && col < 2) ? mag + 7 : mag + 14;
+                    else if (CLS == TX_CLASS_HORIZ) rctx = col == 0 ? mag + 7 : mag + 14;
+                    else rctx = row == 0 ? mag + 7 : mag + 14;
+                    uint16_t* bc = br_cdf[rctx];
+                    for (int idx = 0; idx < 4; idx++) {
+                        const int br = ms.symbol(bc, 4);
+                        level += br;
+                        if (br < 3) break;
+                    }
+                }
+                lv[off] = (uint8_t)level;
+                lv3[off] = (uint8_t)std::min(level, 3);
+                nz[nnz++] = (uint16_t)pos;
+            }
+        };
+        if (cls == TX_CLASS_2D) pass1(std::integral_constant<int, TX_CLASS_2D>());
+        else if (cls == TX_CLASS_HORIZ) pass1(std::integral_constant<int, TX_CLASS_HORIZ>());
+        else pass1(std::integral_constant<int, TX_CLASS_VERT>());
+        // signs + golomb, forward scan over the non-zero levels (tokens are written through a raw pointer: nnz of them)
+        uint32_t* tok_out = to.coefs.tail((size_t)nnz);
         int n_tok = 0;
-        for (int c = 0; c < eob; c++) {
-            const int pos = scan[c];
-            uint8_t* lp = lv + (pos >> bwl) * ls + (pos & (width - 1));
-            int level = *lp;
-            *lp = 0;
-            if (!level) continue;
+        for (int k = nnz - 1; k >= 0; k--) {
+            const int pos = nz[k];
+            const int off = pos + ((pos >> bwl) << 2);
+            int level = lv[off];
+            lv[off] = 0;
+            lv3[off] = 0;
             int sign;
-            if (c == 0) {
+            if (pos == 0) {
                 int dcs = 0;
-                for (int k = 0; k < w4; k++)
-                    if (x4 + k < max_x4) {
-                        const int s = above_dc[plane][x4 + k];
+                for (int i = 0; i < w4; i++)
+                    if (x4 + i < max_x4) {
+                        const int s = above_dc[plane][x4 + i];
                         if (s == 1) dcs--;
                         else if (s == 2) dcs++;
                     }
-                for (int k = 0; k < h4; k++)
-                    if (y4 + k < max_y4) {
-                        const int s = left_dc[plane][y4 + k];
+                for (int i = 0; i < h4; i++)
+                    if (y4 + i < max_y4) {
+                        const int s = left_dc[plane][y4 + i];
                         if (s == 1) dcs--;
                         else if (s == 2) dcs++;
                     }
                 const int dctx = dcs < 0 ? 1 : (dcs > 0 ? 2 : 0);
                 sign = ms.symbol(cdf.dc_sign[ptype][dctx], 2);
             } else {
-                sign = ms.literal(1);
+                sign = ms.bit();
             }
             if (level > 14) {
                 int length = 0, bit;
                 do {
                     length++;
-                    bit = ms.literal(1);
+                    bit = ms.bit();
                     if (length > 32) {
-                        for (int cc = c; cc < eob; cc++) lv[(scan[cc] >> bwl) * ls + (scan[cc] & (width - 1))] = 0;
-                        to.coefs.resize(tok_base + n_tok);
+                        for (int kk = k - 1; kk >= 0; kk--) {
+                            const int o2 = nz[kk] + ((nz[kk] >> bwl) << 2);
+                            lv[o2] = 0;
+                            lv3[o2] = 0;
+                        }
                         fail(AV1R_EBITSTREAM, "golomb too long");
                         return 0;
                     }
                 } while (!bit);
                 int x = 1;
-                for (int i = length - 2; i >= 0; i--) x = (x << 1) + ms.literal(1);
+                for (int i = length - 2; i >= 0; i--) x = (x << 1) + ms.bit();
                 level = x + 14;
             }
-            if (pos == 0 && level > 0) dc_category = sign ? 1 : 2;
+            if (pos == 0) dc_category = sign ? 1 : 2;
             level &= 0xFFFFF;
             cul_level += level;
             if (cul_level > 63) cul_level = 63;
             tok_out[n_tok++] = coef_token(pos, sign ? -level : level);
         }
-        to.coefs.resize(tok_base + n_tok);
+        to.coefs.n += (size_t)n_tok;
         to.coef_tokens += eob;
     }
     for (int i = 0; i < w4; i++) {

@@ -47,7 +47,8 @@ private:
     int max_luma_w = 0, max_luma_h = 0;
     SbRange cur_sb;
     int cur_unit = -1;
-    uint8_t levels[(32 + 4) * (32 + 5)];   // zero-padded level map of the transform block being parsed
+    uint8_t levels[(32 + 4) * (32 + 5)];   // zero-padded level map of the transform block being parsed: min(level, 15)
+    uint8_t levels3[(32 + 4) * (32 + 5)];  // same, min(level, 3)
     int ftype_cache[2] = {-1, -1};
 
     bool fail(int code, const char* msg) { if (!fail_code) { fail_code = code; err = msg; } return false; }

@@ -98,7 +98,7 @@ typedef struct av1r_clip_info {
 } av1r_clip_info;
 
 enum { AV1R_ST_H2D = 0, AV1R_ST_ITX, AV1R_ST_INTRA, AV1R_ST_INTER, AV1R_ST_DEBLOCK, AV1R_ST_CDEF, AV1R_ST_LR, AV1R_ST_GRAIN,
-       AV1R_ST_DIGEST, AV1R_ST_COUNT };
+       AV1R_ST_DIGEST, AV1R_ST_SUPERRES, AV1R_ST_COUNT };
 typedef struct av1r_stage_times {
     uint32_t struct_size;
     float ms[AV1R_ST_COUNT];       /* summed over the clip */

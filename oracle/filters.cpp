@@ -352,6 +352,32 @@ static void sgr_block(const LrCtx& c, const LrUnit& u, int bd, int x, int y, int
         }
 }
 
+// Upscaling process, AV1 spec 7.16: horizontal 8-tap filter with 1/16384-sample positions, per plane.
+void upscale_frame(const FrameHdr& fh, const Frame& in, Frame& out) {
+    const FrameGeom& g = in.g;
+    for (int plane = 0; plane < (g.mono ? 1 : 3); plane++) {
+        const int sx = plane ? g.subx : 0;
+        const int down_w = (fh.frame_width + sx) >> sx, up_w = (fh.upscaled_width + sx) >> sx;
+        const int plane_h = out.g.h[plane];
+        const int step_x = ((down_w << 14) + (up_w / 2)) / up_w;
+        const int err = up_w * step_x - (down_w << 14);
+        const int initial_subpel_x = ((-((up_w - down_w) << 13) + up_w / 2) / up_w + (1 << 7) - err / 2) & ((1 << 14) - 1);
+        const int max_x = g.cw[plane] - 1;     // (MiCols >> subX) * MI_SIZE - 1
+        const int pixmax = (1 << g.bd) - 1;
+        for (int y = 0; y < plane_h; y++)
+            for (int x = 0; x < up_w; x++) {
+                const int src_x = -(1 << 14) + initial_subpel_x + x * step_x;
+                const int src_px = src_x >> 14, sub = (src_x & ((1 << 14) - 1)) >> 8;
+                int sum = 0;
+                for (int k = 0; k < 8; k++) {
+                    const int sxp = std::min(std::max(src_px + k - 3, 0), max_x);
+                    sum += in.p[plane].at(sxp, y) * av1t_upscale_filter[sub][k];
+                }
+                out.p[plane].at(x, y) = (uint16_t)std::min(std::max((sum + 64) >> 7, 0), pixmax);
+            }
+    }
+}
+
 void lr_frame(const FrameWork& fw, const Frame& deblocked, const Frame& cdef, Frame& out) {
     const FrameGeom& g = cdef.g;
     out = cdef;

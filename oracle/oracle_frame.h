@@ -38,6 +38,8 @@ struct Frame {
 void reconstruct_frame(const av1r::FrameWork& fw, Frame& f, const Frame* const refs[8]);
 void deblock_frame(const av1r::FrameWork& fw, Frame& f);
 void cdef_frame(const av1r::FrameWork& fw, const Frame& in, Frame& out);
+// super-resolution (spec 7.16): `out` must be allocated at the upscaled geometry
+void upscale_frame(const av1r::FrameHdr& fh, const Frame& in, Frame& out);
 void lr_frame(const av1r::FrameWork& fw, const Frame& deblocked, const Frame& cdef, Frame& out);
 
 }  // namespace orc

@@ -35,7 +35,7 @@ struct Stream {
     uint64_t tool_hist[24] = {0};
 };
 
-static std::shared_ptr<Frame> make_frame(const SeqHdr& seq, const FrameHdr& fh) {
+static std::shared_ptr<Frame> make_frame(const SeqHdr& seq, const FrameHdr& fh, bool upscaled = false) {
     auto f = std::make_shared<Frame>();
     FrameGeom& g = f->g;
     g.bd = seq.bit_depth;
@@ -44,9 +44,9 @@ static std::shared_ptr<Frame> make_frame(const SeqHdr& seq, const FrameHdr& fh) 
     g.mono = seq.mono_chrome;
     for (int p = 0; p < 3; p++) {
         int sx = p ? g.subx : 0, sy = p ? g.suby : 0;
-        g.w[p] = (fh.upscaled_width + sx) >> sx;
+        g.w[p] = ((upscaled ? fh.upscaled_width : fh.frame_width) + sx) >> sx;
         g.h[p] = (fh.frame_height + sy) >> sy;
-        g.cw[p] = (fh.mi_cols * 4) >> sx;
+        g.cw[p] = ((upscaled ? 2 * ((fh.upscaled_width + 7) >> 3) : fh.mi_cols) * 4) >> sx;
         g.ch[p] = (fh.mi_rows * 4) >> sy;
         f->p[p].alloc(g.cw[p], g.ch[p]);
     }
@@ -136,6 +136,18 @@ extern "C" int orc_stream_decode(void* h, const uint8_t* tu, size_t len) {
             auto c = std::make_shared<Frame>(*cur);
             cdef_frame(fw, *cur, *c);
             cur = c;
+        }
+        if (pf.fh.use_superres) {   // spec 7.16: both the CDEF output and the deblocked frame (source of the LR stripe boundaries)
+            auto up = make_frame(s->sp.hp.seq, pf.fh, true);
+            upscale_frame(pf.fh, *cur, *up);
+            if (deblocked != cur) {
+                auto upd = make_frame(s->sp.hp.seq, pf.fh, true);
+                upscale_frame(pf.fh, *deblocked, *upd);
+                deblocked = upd;
+            } else {
+                deblocked = up;
+            }
+            cur = up;
         }
         if ((s->inloop_filters & 4) && pf.fh.uses_lr) {
             auto l = std::make_shared<Frame>(*cur);

@@ -25,6 +25,9 @@ CASES = {
     "intra_8b_lr_480x272": ("panzoom", 480, 272, 8, 2, {"cpu-used": "1", "cq-level": "40", "enable-restoration": "1"}, {14: 0, 48: 0}),
     "intra_8b_lr_tiles_616x376": ("panzoom", 616, 376, 8, 2, {"cpu-used": "3", "cq-level": "50", "enable-restoration": "1", "tile-columns": "1"}, {14: 0, 48: 0}),
     "intra_8b_grain_160x96": ("noise", 160, 96, 8, 2, {"cpu-used": "8", "cq-level": "30", "enable-restoration": "0", "film-grain-test": "7"}, {14: 0, 48: 0}),
+    # super-resolution (K6): cfg[19] = rc_superres_mode (1 = fixed), cfg[20] / cfg[21] = denominator for inter / key frames (9..16, 8 = off)
+    "intra_8b_superres_lr_328x200": ("panzoom", 328, 200, 8, 3, {"cpu-used": "4", "cq-level": "30", "enable-restoration": "1"}, {14: 0, 48: 0, 19: 1, 20: 12, 21: 12}),
+    "intra_10b_superres16_264x136": ("panzoom", 264, 136, 10, 2, {"cpu-used": "5", "cq-level": "40", "enable-restoration": "0"}, {14: 0, 48: 0, 19: 1, 20: 16, 21: 16}),
 }
 
 # inter streams (index_inter.json): cfg[14] = lag_in_frames, cfg[48] = kf_max_dist.  The low cpu-used cases make libaom use
@@ -38,21 +41,29 @@ INTER_CASES = {
     "inter_8b_sb128_tiles_640x360": ("panzoom", 640, 360, 8, 10, {"cpu-used": "5", "cq-level": "40", "sb-size": "128", "tile-columns": "1", "tile-rows": "1"},
                                      {14: 9, 48: 6}),
     "inter_10b_grain_208x144": ("noise", 208, 144, 10, 8, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "3"}, {14: 6, 48: 9999}),
+    # key frame coded at 8/11 of the width and upscaled; the inter frames (full width) predict from the upscaled reference
+    "inter_8b_kfsuperres_320x192": ("panzoom", 320, 192, 8, 6, {"cpu-used": "5", "cq-level": "32"}, {14: 0, 48: 9999, 19: 1, 20: 8, 21: 11}),
 }
 
 
 def main():
+    """all | inter | intra | only NAME...  (`only` adds / refreshes the named cases and keeps the rest of the index)"""
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("all", "inter"):
-        build(INTER_CASES, "index_inter.json")
-    if which in ("all", "intra"):
-        build(CASES, "index.json")
+    only = set(sys.argv[2:]) if which == "only" else None
+    if which in ("all", "inter", "only"):
+        build(INTER_CASES, "index_inter.json", only)
+    if which in ("all", "intra", "only"):
+        build(CASES, "index.json", only)
 
 
-def build(cases, index_name):
+def build(cases, index_name, only=None):
     index = {}
+    if only is not None:
+        index = json.load(open(os.path.join(OUT, index_name)))
     for name, (src, w, h, bpc, n, opts, cfg) in cases.items():
+        if only is not None and name not in only:
+            continue
         frames = list(sources.SOURCES[src](w, h, n, bpc=bpc, seed=7 if "lr" in name else len(name)))
         tus = aomenc.encode(frames, w, h, bpc=bpc, opts=opts, cfg=cfg, threads=1)
         ref = dav1d_ref.decode(tus)
