@@ -8,7 +8,7 @@ CSRC := av1-go_b200/csrc
 LIBDIR := av1-go_b200/lib
 OBJDIR := build/obj
 CXXFLAGS := -O2 -g -std=c++17 -fPIC -Wall -Wno-unused-function -Iinclude
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude --expt-relaxed-constexpr
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
 
 HOST_SRCS := $(wildcard $(CSRC)/*.cpp)
 CU_SRCS := $(wildcard $(CSRC)/kernels/*.cu) $(wildcard $(CSRC)/*.cu)

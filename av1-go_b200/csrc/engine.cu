@@ -142,7 +142,7 @@ static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::s
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
     size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, k3order, k3units, total;
-    int n_recs, n_coefs, n_order, n_inter, n_obmc, n_warps, n_k3, n_k3units;
+    int n_recs, n_coefs, n_order, n_order_small, n_inter, n_obmc, n_warps, n_k3, n_k3units;
 };
 
 static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
@@ -236,10 +236,16 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     const WorkLayout& L = dw.lay;
     if (L.n_recs) memcpy(h + L.recs, fw.tx.data(), sizeof(TxRec) * L.n_recs);
     if (L.n_coefs) memcpy(h + L.coefs, fw.coefs.data(), sizeof(uint32_t) * L.n_coefs);
-    uint32_t* ord = (uint32_t*)(h + L.order);
-    int k = 0;
-    for (int i = 0; i < L.n_recs; i++)
-        if (fw.tx[i].eob > 0) ord[k++] = (uint32_t)i;
+    {   // K1 order: coded transform blocks, those of at most 16x16 (itx_small_kernel) first, the 32- and 64-point ones after them
+        uint32_t* ord = (uint32_t*)(h + L.order);
+        int lo = 0, hi = L.n_order;
+        for (int i = 0; i < L.n_recs; i++)
+            if (fw.tx[i].eob > 0) {
+                if (kTxW[fw.tx[i].txsz] <= 16 && kTxH[fw.tx[i].txsz] <= 16) ord[lo++] = (uint32_t)i;
+                else ord[--hi] = (uint32_t)i;
+            }
+        dw.lay.n_order_small = lo;
+    }
     for (int p = 0; p < 3; p++)
         if (!fw.lf[p].empty()) memcpy(h + L.lf[p], fw.lf[p].data(), sizeof(LfEdge) * fw.lf[p].size());
     if (!fw.cdef_idx.empty()) memcpy(h + L.cdef_idx, fw.cdef_idx.data(), fw.cdef_idx.size());
@@ -304,13 +310,36 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
             }
             units[nu - 1].count++;
         }
+        // which neighbour units a unit really reads: a record on the unit's top row with an available row above reads the unit
+        // above (and above-left / above-right when it touches those corners), one on the left column reads the unit to the left
+        // (and below-left when the block reaches the unit's bottom).  In intra frames every neighbour is needed; in inter frames
+        // the few units that hold intra / inter-intra blocks would otherwise chain up for no reason.
+        std::vector<uint8_t> need((size_t)nu, 0);
+        for (int k = 0; k < nu; k++) {
+            const K3Unit& u = units[k];
+            uint8_t nd = 0;
+            for (uint32_t n = u.first; n < u.first + u.count; n++) {
+                const TxRec& r = recs[k3[n]];
+                if (r.mode == TXM_INTER || r.mode == TXM_PALETTE) continue;
+                const int sh = r.plane ? 3 : 4;                       // unit size in 4-sample cells: 16 luma, 8 chroma (4:2:0)
+                const int lx = r.x4 - (u.ux << sh), ly = r.y4 - (u.uy << sh);
+                const int w4 = kTxW[r.txsz] >> 2, h4 = kTxH[r.txsz] >> 2, uw = 1 << sh;
+                const bool top = ly == 0 && (r.flags & TXF_HAVE_ABOVE), lft = lx == 0 && (r.flags & TXF_HAVE_LEFT);
+                if (lft) nd |= 1;
+                if (lft && (r.flags & TXF_HAVE_BELOW_LEFT) && ly + 2 * h4 > uw) nd |= 2;
+                if ((top && lx == 0) || (lft && ly == 0)) nd |= 4;
+                if (top) nd |= 8;
+                if (top && (r.flags & TXF_HAVE_ABOVE_RIGHT) && lx + 2 * w4 > uw) nd |= 16;
+            }
+            need[k] = nd;
+        }
         for (int k = 0; k < nu; k++) {
             K3Unit& u = units[k];
             static const int dxy[5][2] = {{-1, 0}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};   // left, below-left, above-left, above, above-right
             for (int d = 0; d < 5; d++) {
                 const int nx = u.ux + dxy[d][0], ny = u.uy + dxy[d][1];
                 int dep = -1;
-                if (nx >= 0 && ny >= 0 && nx < UX && ny < UY) {
+                if (((need[k] >> d) & 1) && nx >= 0 && ny >= 0 && nx < UX && ny < UY) {
                     const int pos = upos[(size_t)ny * UX + nx];
                     if (pos >= 0 && pos < k) dep = pos;
                 }
@@ -520,7 +549,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     }
     const TxRec* d_recs = (const TxRec*)(d_arena + L.recs);
     if (tm) tm->begin(st);
-    CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
+    CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, L.n_order_small, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, L.n_order > 0, st);
     if (L.n_inter > 0) {
         InterLaunch xl;

@@ -7,6 +7,7 @@
 // 8x8 blocks are copied through.  Algorithmic bytes 2F; the halo re-reads are L2 hits.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "dev_common.cuh"
 #include "devframe.h"
@@ -19,6 +20,52 @@ __constant__ int8_t c_cdef_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}
 __constant__ uint8_t c_cdef_uv_dir[2][2][8] = {{{0, 1, 2, 3, 4, 5, 6, 7}, {1, 2, 2, 2, 3, 4, 6, 0}}, {{7, 0, 2, 4, 5, 6, 6, 6}, {0, 1, 2, 3, 4, 5, 6, 7}}};
 
 static constexpr int CDEF_LT = 68;   // luma tile edge (64 + 2*2)
+
+// Direction search (spec 7.15.2) as 90 line sums per 8x8 block: direction d partitions the block into lines (15 diagonals for d = 0, 4;
+// 8 rows / columns for d = 2, 6; 11 half-slope lines for the odd directions); cost[d] = sum over its lines of (line sum)^2 * 840 / (samples
+// on the line).  One warp searches one block: every lane owns three lines.  The table lists, per line, its samples (i * 8 + j, 0xff =
+// none), its direction and its weight; it is built once on the host.
+static constexpr int CDEF_LINES = 96;   // 90 used, padded to 3 per lane
+struct CdefLineTable {
+    uint8_t pix[CDEF_LINES][8];
+    uint16_t weight[CDEF_LINES];
+    uint8_t dir[CDEF_LINES];
+};
+__device__ CdefLineTable g_cdef_lines;
+static bool g_cdef_lines_loaded[64] = {false};
+
+static void cdef_build_lines(CdefLineTable& t) {
+    memset(&t, 0xff, sizeof(t));
+    int n = 0;
+    for (int d = 0; d < 8; d++) {
+        const int nl = (d == 0 || d == 4) ? 15 : ((d == 2 || d == 6) ? 8 : 11);
+        for (int k = 0; k < nl; k++) {
+            int cnt = 0;
+            for (int i = 0; i < 8; i++)
+                for (int j = 0; j < 8; j++) {
+                    int f;
+                    switch (d) {
+                        case 0: f = i + j; break;
+                        case 1: f = i + j / 2; break;
+                        case 2: f = i; break;
+                        case 3: f = 3 + i - j / 2; break;
+                        case 4: f = 7 + i - j; break;
+                        case 5: f = 3 - i / 2 + j; break;
+                        case 6: f = j; break;
+                        default: f = i / 2 + j; break;
+                    }
+                    if (f == k) t.pix[n][cnt++] = (uint8_t)(i * 8 + j);
+                }
+            t.weight[n] = (uint16_t)(840 / cnt);
+            t.dir[n] = (uint8_t)d;
+            n++;
+        }
+    }
+    for (; n < CDEF_LINES; n++) {
+        t.weight[n] = 0;
+        t.dir[n] = 0;
+    }
+}
 
 __device__ __forceinline__ int cdef_constrain(int diff, int threshold, int damping) {
     if (!threshold) return 0;
@@ -66,6 +113,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
     __shared__ int16_t s_chroma[2][CDEF_LT * CDEF_LT];   // sized for 4:4:4
     __shared__ uint8_t s_dir[64], s_skip[64];
     __shared__ int s_var[64];
+    __shared__ __align__(16) CdefLineTable s_lines;
     const DevFrameParams& fp = L.fp;
     const int tid = threadIdx.x;
     const int fbx = blockIdx.x, fby = blockIdx.y;
@@ -73,6 +121,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
     const int idx = L.cdef_idx[(size_t)fby * c64 + fbx];
     const int bd = fp.bd, cs = bd - 8;
     const int nplanes = fp.mono ? 1 : 3;
+    for (int i = tid; i < (int)(sizeof(CdefLineTable) / 4); i += 256) reinterpret_cast<uint32_t*>(&s_lines)[i] = reinterpret_cast<const uint32_t*>(&g_cdef_lines)[i];
     // ---- stage tiles
     for (int plane = 0; plane < nplanes; plane++) {
         const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
@@ -102,51 +151,48 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
         s_skip[tid] = (uint8_t)skip;
     }
     __syncthreads();
-    // ---- direction search, one thread per 8x8 block
-    if (tid < 64 && !s_skip[tid]) {
-        const int by = tid >> 3, bx = tid & 7;
-        int partial[8][15];
+    // ---- direction search: one warp per 8x8 block, three line sums per lane (skipped when no primary strength needs a direction)
+    const bool need_dir = idx >= 0 && (fp.cdef_y_pri[max(idx, 0)] | fp.cdef_uv_pri[max(idx, 0)]) != 0;
+    if (need_dir) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int blk = warp; blk < 64; blk += 8) {
+            if (s_skip[blk]) continue;   // warp-uniform
+            const int by = blk >> 3, bx = blk & 7;
+            const int16_t* base = s_luma + (by * 8 + 2) * CDEF_LT + bx * 8 + 2;
+            int c3[3], d3[3];
 #pragma unroll
-        for (int a = 0; a < 8; a++)
+            for (int q = 0; q < 3; q++) {
+                const int line = lane + 32 * q;
+                const uint2 pk = *reinterpret_cast<const uint2*>(s_lines.pix[line]);
+                int sum = 0;
 #pragma unroll
-            for (int b = 0; b < 15; b++) partial[a][b] = 0;
-        for (int i = 0; i < 8; i++)
-            for (int j = 0; j < 8; j++) {
-                const int x = (s_luma[(by * 8 + i + 2) * CDEF_LT + bx * 8 + j + 2] >> cs) - 128;
-                partial[0][i + j] += x;
-                partial[1][i + j / 2] += x;
-                partial[2][i] += x;
-                partial[3][3 + i - j / 2] += x;
-                partial[4][7 + i - j] += x;
-                partial[5][3 - i / 2 + j] += x;
-                partial[6][j] += x;
-                partial[7][i / 2 + j] += x;
+                for (int t = 0; t < 8; t++) {
+                    const uint32_t px = ((t < 4 ? pk.x : pk.y) >> (8 * (t & 3))) & 0xff;
+                    if (px != 0xff) sum += (base[(px >> 3) * CDEF_LT + (px & 7)] >> cs) - 128;
+                }
+                c3[q] = sum * sum * (int)s_lines.weight[line];
+                d3[q] = s_lines.dir[line];
             }
-        const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
-        int cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 8; i++) {
-            cost[2] += partial[2][i] * partial[2][i];
-            cost[6] += partial[6][i] * partial[6][i];
+            int cost[8];
+#pragma unroll
+            for (int d = 0; d < 8; d++)
+                cost[d] = __reduce_add_sync(0xffffffffu, (d3[0] == d ? c3[0] : 0) + (d3[1] == d ? c3[1] : 0) + (d3[2] == d ? c3[2] : 0));
+            if (lane == 0) {
+                int best = 0, dir = 0;
+#pragma unroll
+                for (int d = 0; d < 8; d++)
+                    if (cost[d] > best) { best = cost[d]; dir = d; }
+                int opp = cost[0];
+#pragma unroll
+                for (int d = 1; d < 8; d++)
+                    if (((dir + 4) & 7) == d) opp = cost[d];
+                s_dir[blk] = (uint8_t)dir;
+                s_var[blk] = (best - opp) >> 10;
+            }
         }
-        cost[2] *= 105;
-        cost[6] *= 105;
-        for (int i = 0; i < 7; i++) {
-            cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * div_table[i + 1];
-            cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * div_table[i + 1];
-        }
-        cost[0] += partial[0][7] * partial[0][7] * 105;
-        cost[4] += partial[4][7] * partial[4][7] * 105;
-        for (int i = 1; i < 8; i += 2) {
-            for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
-            cost[i] *= 105;
-            for (int j = 0; j < 3; j++)
-                cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * div_table[2 * j + 2];
-        }
-        int best = 0, dir = 0;
-        for (int d = 0; d < 8; d++)
-            if (cost[d] > best) { best = cost[d]; dir = d; }
-        s_dir[tid] = (uint8_t)dir;
-        s_var[tid] = (best - cost[(dir + 4) & 7]) >> 10;
+    } else if (tid < 64) {
+        s_dir[tid] = 0;
+        s_var[tid] = 0;
     }
     __syncthreads();
     // ---- filter
@@ -190,6 +236,17 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
 
 cudaError_t launch_cdef(const CdefLaunch& L, cudaStream_t s) {
     dim3 grid((L.fp.mi_cols + 15) >> 4, (L.fp.mi_rows + 15) >> 4);
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (!(dev < 64 && g_cdef_lines_loaded[dev])) {
+            static CdefLineTable host_tab;
+            cdef_build_lines(host_tab);
+            if ((e = cudaMemcpyToSymbol(g_cdef_lines, &host_tab, sizeof(host_tab))) != cudaSuccess) return e;
+            if (dev < 64) g_cdef_lines_loaded[dev] = true;
+        }
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(cdef_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

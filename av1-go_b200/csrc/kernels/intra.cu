@@ -4,8 +4,8 @@
 // of one link of that DAG times its depth, not by bytes.  v5 gave every record its own warp and handed samples over through
 // L2 (one link = flag poll + fence + L2 edge gather + fence: ~1.5 us).  v6 keeps the hand-over on chip:
 //   * one CTA owns one 64x64 luma unit (+ its two 32x32 chroma tiles) at a time.  The unit's samples live in a shared-memory
-//     canvas together with the halo they can read: the row above (corner .. above-right), the column to the left (.. below-left)
-//     and, for the bottom-left unit of a 128x128 superblock, the top-right unit's columns.
+//     canvas together with the halo they can read: the row above (corner .. above-right) and the column to the left
+//     (.. below-left; above-right samples beside the unit never exist: the unit to the right is decoded later).
 //   * inside the CTA the unit's records are claimed in decode order by NW warps through a shared-memory ticket; a warp looks up
 //     the owners of the 4x4 cells its edges come from in a shared-memory owner map and spins on their done-flags (shared
 //     memory, ~30 cycles), predicts from the canvas into the canvas, adds the residual (brought in by one TMA bulk copy per
@@ -548,7 +548,7 @@ __device__ __forceinline__ TxRec load_rec(const TxRec* p) {
 }
 
 template <typename T, int NW>
-__global__ void __launch_bounds__(NW * 32) intra_unit_kernel(IntraLaunch L) {
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(IntraLaunch L) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- carve (mirrored by k3_smem_bytes)
     int16_t* res_s = reinterpret_cast<int16_t*>(smem_raw);
@@ -632,6 +632,27 @@ __global__ void __launch_bounds__(NW * 32) intra_unit_kernel(IntraLaunch L) {
                 }
             }
         }
+        // inter frame: the unit's own inter-predicted samples (final since K2 ran: fetched before the neighbour wait, off the chain)
+        if (L.load_tile) {
+            for (int p = 0; p < 3; p++) {
+                const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
+                const int x0 = ux * W, y0 = uy * W;
+                const uint8_t* fb = L.frame.p[p];
+                const uint32_t pitch = L.frame.pitch[p];
+                T* cv = uc.cv(p);
+                const int vw = min(W, fp.cw[p] - x0), vh = min(W, fp.ch[p] - y0);
+                const int wpr = vw * (int)sizeof(T) / 4;
+                for (int i = tid; i < vh * wpr; i += nthr) {
+                    const int row = i / wpr, wi = i - row * wpr;
+                    reinterpret_cast<uint32_t*>(cv + row * cs)[wi] =
+                        __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T)) + wi);
+                }
+            }
+        }
+        // the first record of every warp does not depend on the neighbours either
+        int k = warp;
+        TxRec r_next;
+        if (k < count) r_next = load_rec(L.recs + __ldg(L.order + first + k));
         lap(1, tid == 0);   // prologue: context, owner map
         // ---- wait for the neighbour units whose samples this unit reads
         if (warp == 0) {
@@ -696,35 +717,6 @@ __global__ void __launch_bounds__(NW * 32) intra_unit_kernel(IntraLaunch L) {
                 if (dst) *dst = v[j];
             }
         }
-        if (L.load_tile || (fp.sb128 && (uy & 1) && !(ux & 1))) {
-            for (int p = 0; p < 3; p++) {
-                const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
-                const int x0 = ux * W, y0 = uy * W;
-                const int cw = fp.cw[p], ch = fp.ch[p];
-                const uint8_t* fb = L.frame.p[p];
-                const uint32_t pitch = L.frame.pitch[p];
-                T* cv = uc.cv(p);
-                const int vw = min(W, cw - x0), vh = min(W, ch - y0);
-                if (L.load_tile) {   // inter frame: the unit's own inter-predicted samples
-                    const int wpr = vw * (int)sizeof(T) / 4;
-                    for (int i = tid; i < vh * wpr; i += nthr) {
-                        const int row = i / wpr, wi = i - row * wpr;
-                        reinterpret_cast<uint32_t*>(cv + row * cs)[wi] =
-                            __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T)) + wi);
-                    }
-                }
-                if (fp.sb128 && (uy & 1) && !(ux & 1)) {   // bottom-left unit of a 128x128 superblock: above-right samples inside the top-right unit
-                    const int rw = min(W, cw - x0 - W);
-                    const int wpr = rw > 0 ? rw * (int)sizeof(T) / 4 : 0;
-                    const int rows = min(W - 1, ch - y0);
-                    for (int i = tid; i < rows * wpr; i += nthr) {
-                        const int row = i / wpr, wi = i - row * wpr;
-                        reinterpret_cast<uint32_t*>(cv + row * cs + W)[wi] =
-                            __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)(x0 + W) * sizeof(T)) + wi);
-                    }
-                }
-            }
-        }
         lap(3, tid == 0);   // halo loads
         mbar_wait(bar, parity);
         parity ^= 1;
@@ -735,9 +727,6 @@ __global__ void __launch_bounds__(NW * 32) intra_unit_kernel(IntraLaunch L) {
         // Records are dealt round-robin to the warps (record k -> warp k mod NW; a warp walks its records in order, so the lowest
         // unfinished record can always run) and the next record is fetched while the current one waits and predicts.
         WarpScratch& sm = wscr[warp];
-        int k = warp;
-        TxRec r_next;
-        if (k < count) r_next = load_rec(L.recs + __ldg(L.order + first + k));
         for (; k < count; k += nw) {
             const TxRec r = r_next;
             if (k + nw < count) r_next = load_rec(L.recs + __ldg(L.order + first + k + nw));

@@ -26,7 +26,7 @@ struct IntraLaunch {            // passed by value
 };
 
 cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s);
-cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, const uint32_t* coefs, const DevResidual& res,
+cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, int n_small, const uint32_t* coefs, const DevResidual& res,
                        const DevFrameParams& fp, cudaStream_t s);
 
 struct LfLaunch {

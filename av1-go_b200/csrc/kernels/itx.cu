@@ -174,6 +174,89 @@ __global__ void __launch_bounds__(ITX_WARPS * 32) itx_kernel(const TxRec* __rest
     }
 }
 
+// Transform blocks of at most 16x16 (the bulk of every stream) -- half a warp per block, t[16] registers: ~1/4 of the registers
+// of the general kernel, so that K1 no longer evicts the persistent K3 CTAs of the frames in flight on other streams.
+static constexpr int ITXS_HALF_WARPS = 8;
+__global__ void __launch_bounds__(ITXS_HALF_WARPS * 16) itx_small_kernel(const TxRec* __restrict__ recs, const uint32_t* __restrict__ order, int n,
+                                                                        const uint32_t* __restrict__ coefs, DevResidual res, DevFrameParams fp) {
+    __shared__ int32_t s_buf[ITXS_HALF_WARPS][16 * 17];
+    const int hw = threadIdx.x >> 4, lane = threadIdx.x & 15;
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);   // the two halves of a warp work on different blocks
+    const int bi = blockIdx.x * ITXS_HALF_WARPS + hw;
+    if (bi >= n) return;
+    const TxRec r = recs[order[bi]];
+    int32_t* buf = s_buf[hw];
+    const int txsz = r.txsz, plane = r.plane;
+    const int lw = c_txw_log2[txsz], lh = c_txh_log2[txsz];
+    const int w = 1 << lw, h = 1 << lh;
+    const int stride = w + 1;
+    const int bd = fp.bd;
+    for (int i = lane; i < h * stride; i += 16) buf[i] = 0;
+    __syncwarp(mask);
+    {
+        const int bdi = (bd - 8) >> 1;
+        const int dcq = c_dc_q[bdi][min(max(r.qidx + fp.dq_dc[plane], 0), 255)];
+        const int acq = c_ac_q[bdi][min(max(r.qidx + fp.dq_ac[plane], 0), 255)];
+        const int mx = (1 << (7 + bd)) - 1, mn = -(1 << (7 + bd));
+        const uint32_t* tk = coefs + r.coef_off;
+        for (int k = lane; k < r.ntok; k += 16) {
+            const uint32_t t = tk[k];
+            const int pos = (int)(t & 1023), level = (int32_t)t >> 10;
+            const int q = pos == 0 ? dcq : acq;
+            const uint32_t dq = ((uint32_t)abs(level) * (uint32_t)q) & 0xFFFFFFu;   // dqDenom is 1 up to 256 samples
+            int v = level < 0 ? -(int)dq : (int)dq;
+            v = min(max(v, mn), mx);
+            buf[(pos >> lw) * stride + (pos & (w - 1))] = v;
+        }
+    }
+    __syncwarp(mask);
+    int16_t* dst = res_ptr(res, plane, r.x4 * 4, r.y4 * 4);
+    const int dpe = 1 << res.tw_log2[plane];
+    const int cols_valid = min(w, fp.cw[plane] - r.x4 * 4), rows_valid = min(h, fp.ch[plane] - r.y4 * 4);
+    if (r.txtp == WHT_WHT) {
+        if (lane < 4) {
+            int32_t t[4];
+            for (int j = 0; j < 4; j++) t[j] = buf[lane * stride + j];
+            iwht4(t, 2);
+            for (int j = 0; j < 4; j++) buf[lane * stride + j] = t[j];
+        }
+        __syncwarp(mask);
+        if (lane < 4) {
+            int32_t t[4];
+            for (int i = 0; i < 4; i++) t[i] = buf[i * stride + lane];
+            iwht4(t, 0);
+            if (lane < cols_valid)
+                for (int i = 0; i < 4; i++)
+                    if (i < rows_valid) dst[i * dpe + lane] = (int16_t)t[i];
+        }
+        return;
+    }
+    int vk, hk, ud, lr;
+    txtp_decompose(r.txtp, vk, hk, ud, lr);
+    const int rect = (lw - lh == 1) || (lh - lw == 1);
+    static const int8_t kRowShiftS[TX_SIZES_ALL] = {0, 1, 2, 2, 2, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2};
+    const int rs = kRowShiftS[txsz];
+    if (lane < h) {
+        int32_t* row = buf + lane * stride;
+        switch (lw) {
+            case 2: row_pass<4>(row, w, hk, rect, bd, rs); break;
+            case 3: row_pass<8>(row, w, hk, rect, bd, rs); break;
+            default: row_pass<16>(row, w, hk, rect, bd, rs); break;
+        }
+    }
+    __syncwarp(mask);
+    const int mid_bits = max(bd + 6, 16);
+    if (lane < cols_valid) {
+        const int sj = lr ? w - 1 - lane : lane;
+        const int32_t* col = buf + sj;
+        switch (lh) {
+            case 2: col_pass<4>(col, stride, h, vk, mid_bits, ud, dst + lane, dpe, rows_valid); break;
+            case 3: col_pass<8>(col, stride, h, vk, mid_bits, ud, dst + lane, dpe, rows_valid); break;
+            default: col_pass<16>(col, stride, h, vk, mid_bits, ud, dst + lane, dpe, rows_valid); break;
+        }
+    }
+}
+
 cudaError_t itx_upload_constants() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -191,19 +274,23 @@ cudaError_t itx_upload_constants() {
     return cudaSuccess;
 }
 
-// order: indices of the records with eob > 0 (device array of n entries)
-cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, const uint32_t* coefs, const DevResidual& res,
+// order: indices of the records with eob > 0 (device array of n entries); the first n_small of them are at most 16x16
+cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, int n_small, const uint32_t* coefs, const DevResidual& res,
                        const DevFrameParams& fp, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     cudaError_t e = itx_upload_constants();
     if (e != cudaSuccess) return e;
-    const int blocks = (n + ITX_WARPS - 1) / ITX_WARPS;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(itx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_done = true;
     }
-    itx_kernel<<<blocks, ITX_WARPS * 32, 0, s>>>(recs, order, n, coefs, res, fp);
+    if (n_small > 0)
+        itx_small_kernel<<<(n_small + ITXS_HALF_WARPS - 1) / ITXS_HALF_WARPS, ITXS_HALF_WARPS * 16, 0, s>>>(recs, order, n_small, coefs, res, fp);
+    if (n > n_small) {
+        const int nl = n - n_small;
+        itx_kernel<<<(nl + ITX_WARPS - 1) / ITX_WARPS, ITX_WARPS * 32, 0, s>>>(recs, order + n_small, nl, coefs, res, fp);
+    }
     return cudaGetLastError();
 }
 
