@@ -71,6 +71,7 @@ extern "C" int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threa
     std::atomic<long long> frames{0};
     std::vector<double> parse_ms(nseg, 0.0);
     auto worker = [&]() {
+        WorkerPool::nested_enabled() = nseg < nthreads;
         while (true) {
             const int s = next.fetch_add(1);
             if (s >= nseg) return;

@@ -25,6 +25,7 @@
 #include "kernels/inter.h"
 #include "kernels/intra.h"
 #include "md5.h"
+#include "parallel.h"
 #include "stream_parser.h"
 
 struct av1r_clip;
@@ -1228,6 +1229,7 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     const int64_t la_limit = std::max<int64_t>(2 * nthreads, 8);
     auto worker = [&]() {
         cudaSetDevice(E.cfg.device);   // pinned staging is allocated from this thread
+        WorkerPool::nested_enabled() = nseg < (size_t)nthreads;   // enough segments to fill the cores: no tile / band helpers
         while (!abort_flag.load()) {
             const size_t s = next_seg.fetch_add(1);
             if (s >= nseg) return;

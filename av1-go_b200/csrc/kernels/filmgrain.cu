@@ -76,6 +76,68 @@ __device__ void build_lut256(int n, const int* val, const int* sc, int* lut, int
     }
 }
 
+// Auto-regressive grain filter (spec 7.18.3.3), row wavefront: row y may process column x once row y-1 has finished x + lag.
+// The lag is a template parameter so that the 2 * lag * (lag + 1) taps unroll into independent shared-memory loads with the
+// coefficients in registers: a step of the wavefront costs one load latency instead of a 24-iteration dependent loop.
+template <int LAG>
+__device__ __forceinline__ void fg_ar_filter(int16_t* g_luma, int16_t* g_cb, int16_t* g_cr, const int (*s_coef)[25], int ash, int gmin, int gmax,
+                                             int cw, int ch, int subx, int suby, int mono, bool luma_term, int tid) {
+    constexpr int NT = 2 * LAG * (LAG + 1);
+    {
+        constexpr int rows = 70, cols = 76, steps = cols + (LAG + 1) * (rows - 1);
+        int coef[NT > 0 ? NT : 1];
+#pragma unroll
+        for (int i = 0; i < NT; i++) coef[i] = s_coef[0][i];
+        const int y = tid + 3;
+        for (int t = 0; t < steps; t++) {
+            const int x = 3 + t - (LAG + 1) * tid;
+            if (tid < rows && x >= 3 && x < 3 + cols) {
+                int sum = 0;
+#pragma unroll
+                for (int dr = -LAG; dr <= 0; dr++)
+#pragma unroll
+                    for (int dc = -LAG; dc <= LAG; dc++)
+                        if (dr < 0 || dc < 0) sum += coef[(dr + LAG) * (2 * LAG + 1) + dc + LAG] * g_luma[(y + dr) * 82 + x + dc];
+                const int v = g_luma[y * 82 + x] + d_round2(sum, ash);
+                g_luma[y * 82 + x] = (int16_t)d_clip3(gmin, gmax, v);
+            }
+            __syncthreads();
+        }
+    }
+    if (!mono) {
+        const int rows = ch - 3, cols = cw - 6;
+        const int steps = cols + (LAG + 1) * (rows - 1);
+        const int pl = tid >> 7;          // 0: cb (threads 0..127)  1: cr (threads 128..255)
+        const int ry = tid & 127;
+        int16_t* gp = pl ? g_cr : g_cb;
+        int coef[NT + 1];
+#pragma unroll
+        for (int i = 0; i <= NT; i++) coef[i] = s_coef[1 + pl][i];
+        const int y = ry + 3;
+        for (int t = 0; t < steps; t++) {
+            const int x = 3 + t - (LAG + 1) * ry;
+            if (ry < rows && x >= 3 && x < 3 + cols) {
+                int sum = 0;
+#pragma unroll
+                for (int dr = -LAG; dr <= 0; dr++)
+#pragma unroll
+                    for (int dc = -LAG; dc <= LAG; dc++)
+                        if (dr < 0 || dc < 0) sum += coef[(dr + LAG) * (2 * LAG + 1) + dc + LAG] * gp[(y + dr) * cw + x + dc];
+                if (luma_term) {
+                    int luma = 0;
+                    const int lx = ((x - 3) << subx) + 3, ly = ((y - 3) << suby) + 3;
+                    for (int i = 0; i <= suby; i++)
+                        for (int j = 0; j <= subx; j++) luma += g_luma[(ly + i) * 82 + lx + j];
+                    sum += d_round2(luma, subx + suby) * coef[NT];
+                }
+                const int v = gp[y * cw + x] + d_round2(sum, ash);
+                gp[y * cw + x] = (int16_t)d_clip3(gmin, gmax, v);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fg_prepare_kernel(FgK k, FgDev* __restrict__ st) {
     __shared__ uint16_t jm[14][16];
     __shared__ int lut256[3][256];
@@ -140,62 +202,11 @@ __global__ void __launch_bounds__(256) fg_prepare_kernel(FgK k, FgDev* __restric
     const int ash = p.ar_coeff_shift;
     const int gcenter = 128 << (bd - 8);
     const int gmin = -gcenter, gmax = (256 << (bd - 8)) - 1 - gcenter;
-    {
-        const int rows = 70, cols = 76;
-        const int steps = cols + (lag + 1) * (rows - 1);
-        for (int t = 0; t < steps; t++) {
-            if (tid < rows) {
-                int y = tid + 3;
-                int x = 3 + t - (lag + 1) * tid;
-                if (x >= 3 && x < 3 + cols) {
-                    int sum = 0, pos = 0;
-                    for (int dr = -lag; dr <= 0; dr++)
-                        for (int dc = -lag; dc <= lag; dc++) {
-                            if (dr == 0 && dc == 0) break;
-                            sum += s_coef[0][pos++] * g_luma[(y + dr) * 82 + x + dc];
-                        }
-                    int v = g_luma[y * 82 + x] + d_round2(sum, ash);
-                    g_luma[y * 82 + x] = (int16_t)d_clip3(gmin, gmax, v);
-                }
-            }
-            __syncthreads();
-        }
-    }
-    if (!k.mono) {
-        const int rows = ch - 3, cols = cw - 6;
-        const int steps = cols + (lag + 1) * (rows - 1);
-        const int pl = tid >> 7;          // 0: cb (threads 0..127)  1: cr (threads 128..255)
-        const int ry = tid & 127;
-        int16_t* gp = pl ? g_cr : g_cb;
-        for (int t = 0; t < steps; t++) {
-            if (ry < rows) {
-                int y = ry + 3;
-                int x = 3 + t - (lag + 1) * ry;
-                if (x >= 3 && x < 3 + cols) {
-                    int sum = 0, pos = 0;
-                    for (int dr = -lag; dr <= 0; dr++)
-                        for (int dc = -lag; dc <= lag; dc++) {
-                            int c = s_coef[1 + pl][pos];
-                            if (dr == 0 && dc == 0) {
-                                if (p.num_y_points > 0) {
-                                    int luma = 0;
-                                    int lx = ((x - 3) << k.subx) + 3, ly = ((y - 3) << k.suby) + 3;
-                                    for (int i = 0; i <= k.suby; i++)
-                                        for (int j = 0; j <= k.subx; j++) luma += g_luma[(ly + i) * 82 + lx + j];
-                                    luma = d_round2(luma, k.subx + k.suby);
-                                    sum += luma * c;
-                                }
-                                break;
-                            }
-                            sum += c * gp[(y + dr) * cw + x + dc];
-                            pos++;
-                        }
-                    int v = gp[y * cw + x] + d_round2(sum, ash);
-                    gp[y * cw + x] = (int16_t)d_clip3(gmin, gmax, v);
-                }
-            }
-            __syncthreads();
-        }
+    switch (lag) {
+        case 0: fg_ar_filter<0>(g_luma, g_cb, g_cr, s_coef, ash, gmin, gmax, cw, ch, k.subx, k.suby, k.mono, p.num_y_points > 0, tid); break;
+        case 1: fg_ar_filter<1>(g_luma, g_cb, g_cr, s_coef, ash, gmin, gmax, cw, ch, k.subx, k.suby, k.mono, p.num_y_points > 0, tid); break;
+        case 2: fg_ar_filter<2>(g_luma, g_cb, g_cr, s_coef, ash, gmin, gmax, cw, ch, k.subx, k.suby, k.mono, p.num_y_points > 0, tid); break;
+        default: fg_ar_filter<3>(g_luma, g_cb, g_cr, s_coef, ash, gmin, gmax, cw, ch, k.subx, k.suby, k.mono, p.num_y_points > 0, tid); break;
     }
         for (int i = tid; i < 73 * 82; i += 256) {
         st->luma[i] = g_luma[i];

@@ -21,9 +21,16 @@ public:
     }
     int size() const { return (int)threads_.size(); }
 
+    // Per-thread switch: a caller that is itself one of >= #cores concurrent workers (a file with many GOP segments) runs its
+    // loops inline -- handing chunks to pool threads would only add waiting on time-sliced helpers.
+    static bool& nested_enabled() {
+        static thread_local bool v = true;
+        return v;
+    }
+
     void parallel_for(int n, const std::function<void(int)>& fn) {
         if (n <= 0) return;
-        if (n == 1 || threads_.empty()) {
+        if (n == 1 || threads_.empty() || !nested_enabled()) {
             for (int i = 0; i < n; i++) fn(i);
             return;
         }
