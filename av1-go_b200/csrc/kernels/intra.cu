@@ -30,7 +30,11 @@
 namespace av1r {
 
 __constant__ int16_t c_dr_deriv[90];
-__constant__ uint8_t c_mode_angle[9] = {0, 90, 180, 45, 135, 113, 157, 203, 67};
+// base angle of the directional modes V_PRED .. D67_PRED (index = PredMode 1..8), packed one byte each
+__device__ __forceinline__ int mode_angle(int mode) {
+    constexpr unsigned long long pk = (90ull << 8) | (180ull << 16) | (45ull << 24) | (135ull << 32) | (113ull << 40) | (157ull << 48) | (203ull << 56);
+    return mode == 8 ? 67 : (int)((pk >> (8 * mode)) & 0xff);
+}
 __constant__ uint8_t c_sm_weights[124];
 __constant__ int8_t c_fi_taps[5][8][8];
 __constant__ uint8_t c_itxw_log2[TX_SIZES_ALL];
@@ -231,8 +235,10 @@ __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrame
     const int w = 1 << lw, h = 1 << lh;
     const int x = r.x4 * 4, y = r.y4 * 4;
     const int bd = fp.bd, pixmax = (1 << bd) - 1;
-    const int max_x = fp.cw[plane] - 1, max_y = fp.ch[plane] - 1;
-    const int xe = min(w, fp.cw[plane] - x), ye = min(h, fp.ch[plane] - y);
+    // (two uniform parameter loads and a select instead of a register-indexed constant load: planes 1 and 2 have the same size)
+    const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
+    const int max_x = pcw - 1, max_y = pch - 1;
+    const int xe = min(w, pcw - x), ye = min(h, pch - y);
     const int opitch = uv.cs(plane);
     T* out = uv.cv(plane) + (y - uv.y0(plane)) * opitch + (x - uv.x0(plane));   // the unit's samples live in shared memory
     const bool has_res = r.eob > 0;
@@ -349,7 +355,7 @@ __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrame
         return;
     }
     if (mode >= V_PRED && mode <= D67_PRED) {
-        const int p_angle = c_mode_angle[mode] + r.angle_delta * 3;
+        const int p_angle = mode_angle(mode) + r.angle_delta * 3;
         int up_above = 0, up_left = 0;
         if (fp.enable_edge_filter) {
             const int filter_type = (r.flags & TXF_SMOOTH_EDGE) ? 1 : 0;
@@ -689,13 +695,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                 const uint32_t pitch = L.frame.pitch[p];
                 if (i < 2 * W + 1) {
                     const int dx = i - 1;
-                    if (y0 > 0 && x0 + dx >= 0 && x0 + dx < fp.cw[p]) {
+                    if (y0 > 0 && x0 + dx >= 0 && x0 + dx < (p ? fp.cw[1] : fp.cw[0])) {
                         src = reinterpret_cast<const T*>(fb + (size_t)(y0 - 1) * pitch) + x0 + dx;
                         dst = uc.cv(p) - cs + dx;
                     }
                 } else {
                     const int dy = i - (2 * W + 1);
-                    if (x0 > 0 && dy < 2 * W && y0 + dy < fp.ch[p]) {
+                    if (x0 > 0 && dy < 2 * W && y0 + dy < (p ? fp.ch[1] : fp.ch[0])) {
                         src = reinterpret_cast<const T*>(fb + (size_t)(y0 + dy) * pitch) + x0 - 1;
                         dst = dy < W ? uc.cv(p) + dy * cs - 1 : uc.lext + uc.lext_off(p) + (dy - W);
                     }
@@ -736,13 +742,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             } else if (r.mode != TXM_PALETTE) {
                 const int plane = r.plane;
                 const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
-                const int pw4 = fp.pw4[plane], ph4 = fp.ph4[plane];
+                const int pw4 = plane ? fp.pw4[1] : fp.pw4[0], ph4 = plane ? fp.ph4[1] : fp.ph4[0];
                 const int uw4 = plane ? 8 : 16;
                 const int bx4 = ux * uw4, by4 = uy * uw4;
                 const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
                 int need_ar = 0, need_bl = 0;
                 if (r.mode >= V_PRED && r.mode <= D67_PRED) {
-                    const int p_angle = c_mode_angle[r.mode] + r.angle_delta * 3;
+                    const int p_angle = mode_angle(r.mode) + r.angle_delta * 3;
                     need_ar = p_angle < 90 && (r.flags & TXF_HAVE_ABOVE_RIGHT);
                     need_bl = p_angle > 180 && (r.flags & TXF_HAVE_BELOW_LEFT);
                 }

@@ -328,6 +328,7 @@ def run_c2(args, torch, dist, rank, world, local, name="c2"):
         "grain": 2 * F * int(info.grain_frames),
         "digest": F * nfr,
     }
+    # (K6 super-resolution has no bench workload: the BASELINE configs do not use it; parity only, tests/golden/*superres*)
     stages = {}
     for k, (ms, launches) in prof.items():
         if launches:
@@ -374,6 +375,13 @@ def run_c2(args, torch, dist, rank, world, local, name="c2"):
         e2e_s = float(t.item())
     e2e_val = nfr * world / e2e_s
     launches_per_step = sum(v["launches"] for v in stages.values())
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload (or null)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(WORKLOAD_NAMES.get(name, name), {}).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        traffic = None
     out = {
         "metric": "AV1 decode-verify frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -384,7 +392,7 @@ def run_c2(args, torch, dist, rank, world, local, name="c2"):
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr,
                 "host_parse_ms_per_step": parse_ms, "host_threads": os.cpu_count(), "single_thread_submit_tu_fps": e2e_1t,
                 "note": "av1r_verify_buffer: key-frame-delimited GOP segments parsed on all host cores; host_parse_ms is the summed sequential symbol-parse time (north_star: reported separately)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": dom, "algorithmic_bytes_per_launch": dom_bytes,
                      "avg_launch_ms": dom_ms, "stages": stages,
                      "pipeline_algorithmic_gbs": sum(stage_bytes[k] for k in stages if k in stage_bytes) / (total_ms / args.steps / 1e3) / 1e9},
@@ -417,7 +425,8 @@ def cpu_baseline_c2(name="c2"):
     t0 = time.perf_counter()
     dav1d_ref.decode(tus[:20], n_threads=1, keep=False)
     dt1 = time.perf_counter() - t0
-    return {"value": len(out) / best, "unit": "frames/s", "cores": ncpu, "kind": "reference",
+    return {"value": len(out) / best, "unit": "frames/s", "cores": ncpu, "kind": "reference", "ms_per_step": best * 1e3,
+            "dtype": "u8" if name in ("c1", "c2", "c2_small") else "u16",
             "sample": f"libdav1d {dav1d_ref.version()} driven directly (no ffmpeg binary in the image), n_threads={ncpu}, whole {len(tus)}-TU clip "
                       f"preloaded in RAM, best of 3, no MD5; single-thread figure {20 / dt1:.1f} frames/s on 20 frames"}
 
@@ -547,6 +556,10 @@ def cpu_baseline_c5():
             "sample": f"libdav1d {dav1d_ref.version()} n_threads={ncpu}, files c5_00..c5_07 of the batch (8 x 16 frames 4K10) decoded back to back, preloaded in RAM, no MD5"}
 
 
+# clip key (tools/make_streams.py) -> bench workload name (profiles/ncu_traffic.json is keyed by the latter)
+WORKLOAD_NAMES = {"c2": "c2_intra_1080p8", "c1": "c1_1080p8", "c3": "c3_4k10_inter", "c4": "c4_4k10_grain"}
+
+
 def _clip_workload(name):
     return (lambda *a: run_c2(*a, name=name)), (lambda: cpu_baseline_c2(name))
 
@@ -577,6 +590,7 @@ def main():
         line = {"impl": "reference", "metric": "AV1 decode-verify frames/s", "value": cb["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": {"workload": args.workload},
+                "ms_per_step": cb.get("ms_per_step"), "dtype": cb.get("dtype"),
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
