@@ -596,6 +596,10 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # libraries (NCCL prints its version banner) must not write to stdout: the contract is ONE JSON line there
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     dist = None
     if world > 1:
@@ -603,13 +607,17 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
         return 2
     out = run(args, torch, dist, rank, world, local)
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_base()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_base()
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
