@@ -1227,6 +1227,9 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     std::condition_variable la_cv;
     int64_t la_outstanding = 0;
     const int64_t la_limit = std::max<int64_t>(2 * nthreads, 8);
+    // the segment the consumer is issuing is exempt from the look-ahead budget: otherwise the workers of later multi-TU segments
+    // can use the budget up while the worker the consumer waits for is the one blocked on it (deadlock seen on the C5 batch)
+    std::atomic<size_t> consumer_seg{0};
     auto worker = [&]() {
         cudaSetDevice(E.cfg.device);   // pinned staging is allocated from this thread
         WorkerPool::nested_enabled() = nseg < (size_t)nthreads;   // enough segments to fill the cores: no tile / band helpers
@@ -1252,7 +1255,7 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
             for (size_t t = sg.tu0; t < sg.tu1 && !abort_flag.load() && !failed; t++) {
                 {
                     std::unique_lock<std::mutex> lk(la_m);
-                    la_cv.wait(lk, [&] { return la_outstanding < la_limit || abort_flag.load(); });
+                    la_cv.wait(lk, [&] { return la_outstanding < la_limit || s == consumer_seg.load() || abort_flag.load(); });
                     la_outstanding++;
                 }
                 auto pfs = std::make_shared<std::vector<ParsedFrame>>();
@@ -1311,6 +1314,11 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     std::string msg;
     for (size_t s = 0; s < nseg && !rc; s++) {
         Segment& sg = *segs[s];
+        {
+            std::lock_guard<std::mutex> lk(la_m);
+            consumer_seg.store(s);
+        }
+        la_cv.notify_all();
         EngineImpl::RefState seg_refs;
         E.rs = &seg_refs;
         for (size_t t = 0; t < sg.tu1 - sg.tu0 && !rc; t++) {

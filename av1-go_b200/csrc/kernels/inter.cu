@@ -63,6 +63,11 @@ struct InterSmem {
     uint16_t refwin[(IT + 7) * RW];           // clamped reference samples of the tile's 8-tap support, loaded once
 };
 
+// idx / d for idx <= 39 * 39 and d <= 39 as a multiply and a shift (inv = ceil(65536 / d); exact in that range): the tile loops
+// below split a linear thread index into (row, column) for every sample
+__device__ __forceinline__ int recip16(int d) { return (65536 + d - 1) / d; }
+__device__ __forceinline__ int div16(int idx, int inv) { return (idx * inv) >> 16; }
+
 template <typename T>
 __device__ __forceinline__ int ld_ref(const uint8_t* base, uint32_t pitch, int x, int y) {
     return (int)__ldg((const T*)(base + (size_t)y * pitch) + x);
@@ -77,15 +82,16 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
     const int16_t* fh = c_subpel[fidx_h][fx];
     const int16_t* fv = c_subpel[fidx_v][fy];
     const int ww = tw + 7, wh = th + 7;
+    const int inv_ww = recip16(ww), inv_tw = recip16(tw);
     for (int idx = threadIdx.x; idx < ww * wh; idx += INTER_THREADS) {
-        const int r = idx / ww, c = idx - r * ww;
+        const int r = div16(idx, inv_ww), c = idx - r * ww;
         sm.refwin[r * RW + c] = (uint16_t)ld_ref<T>(ref, pitch, min(max(ix + c - 3, 0), lastx), min(max(iy + r - 3, 0), lasty));
     }
     __syncthreads();
     int32_t* mid = sm.mid;
     const int n1 = wh * tw;
     for (int idx = threadIdx.x; idx < n1; idx += INTER_THREADS) {
-        const int r = idx / tw, c = idx - r * tw;
+        const int r = div16(idx, inv_tw), c = idx - r * tw;
         const uint16_t* w = sm.refwin + r * RW + c;
         int s = 0;
 #pragma unroll
@@ -96,7 +102,7 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
     const int n2 = th * tw;
     const int rnd = 1 << (round1 - 1);
     for (int idx = threadIdx.x; idx < n2; idx += INTER_THREADS) {
-        const int r = idx / tw, c = idx - r * tw;
+        const int r = div16(idx, inv_tw), c = idx - r * tw;
         int s = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++) s += fv[t] * mid[(r + t) * IT + c];
@@ -184,8 +190,9 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                                         filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tw, th, round1, sm, sm.pred[l]);
                     }
                 }
+                const int inv_tw = recip16(tw);
                 for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
-                    const int i = idx / tw, j = idx - i * tw;
+                    const int i = div16(idx, inv_tw), j = idx - i * tw;
                     const int gx = px + tx + j, gy = py + ty + i;
                     const int a = sm.pred[0][i * IT + j];
                     int v;
@@ -261,8 +268,9 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                     const int posx = ((ox + tx) << 4) + ((2 * nb.mv[1]) >> sx), posy = ((oy + ty) << 4) + ((2 * nb.mv[0]) >> sy);
                     predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
                                     filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm, sm.pred[0]);
+                    const int inv_tw = recip16(tw);
                     for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
-                        const int i = idx / tw, j = idx - i * tw;
+                        const int i = div16(idx, inv_tw), j = idx - i * tw;
                         const int gx = ox + tx + j, gy = oy + ty + i;
                         if (gx >= fp.cw[plane] || gy >= fp.ch[plane]) continue;
                         const int o = min(max(sm.pred[0][i * IT + j], 0), pixmax);

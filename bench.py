@@ -458,7 +458,12 @@ def c5_items(nfiles=32):
 def run_c5(args, torch, dist, rank, world, local):
     import av1recon
     from av1recon import shard
-    items, tus_of, (w, h) = c5_items()
+    t_start = time.perf_counter()
+
+    def note(msg):   # progress on stderr: this workload holds 512 4K frames and takes minutes end to end
+        print(f"[c5 rank {rank} +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    items, tus_of, (w, h) = c5_items(int(os.environ.get("AV1R_C5_FILES", "32")))
+    note(f"{len(items)} GOP segments scanned")
     mine = shard.assign(items, world)[rank]
     my_tus = [t for k in mine for t in tus_of[k]]
     torch.cuda.set_device(local)
@@ -466,9 +471,12 @@ def run_c5(args, torch, dist, rank, world, local):
     clip = av1recon.Clip(dec, my_tus)
     info = clip.info
     nfr_local = int(info.frames_shown)
+    note(f"clip loaded: {nfr_local} frames")
     ms0, cks0 = clip.decode()
+    note(f"first decode {ms0:.1f} ms")
     for _ in range(args.warmup):
         clip.decode()
+    note("warm-up done")
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -492,7 +500,9 @@ def run_c5(args, torch, dist, rank, world, local):
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
         nfr = int(n.item())
     value = nfr * args.steps / (total_ms / 1e3)
+    note(f"timed steps done: {total_ms / args.steps:.1f} ms per step")
     prof = clip.profile()
+    note("stage profile done")
     stages = {k: {"ms_per_step": ms, "launches": n} for k, (ms, n) in prof.items() if n}
     # e2e: the rank's share of the batch as one container through av1r_ctx_verify_buffer (host parse of the segments on this
     # rank's share of the host cores, H2D, kernels, D2H of the digests)
@@ -500,6 +510,7 @@ def run_c5(args, torch, dist, rank, world, local):
     host_threads = max(1, (os.cpu_count() or 1) // world)
     vdec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32, host_threads=host_threads)
     vdec.verify_buffer(blob)
+    note("e2e warm-up done")
     best = None
     for _ in range(2):
         if world > 1:

@@ -125,6 +125,29 @@ def test_cuda_verify_buffer_inter(built):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(120)
+def test_cuda_verify_buffer_many_multi_tu_segments(built):
+    """A batch container with more multi-TU GOP segments than the parser look-ahead budget (the C5 shape: the workers of later
+    segments must not starve the segment the consumer is issuing -- this used to deadlock).  Digests equal the streaming path's."""
+    import av1recon
+    from av1recon import shard
+    from tools.obuio import read_ivf
+    name = "inter_8b_sb128_tiles_640x360"
+    tus = read_ivf(os.path.join(GOLD, name + ".ivf"))
+    copies = 6                                           # 12 segments of 6 / 4 temporal units; budget = max(2 * 4 threads, 8) = 8
+    blob = shard.ivf_bytes(tus * copies, INDEX[name]["w"], INDEX[name]["h"])
+    for _ in range(3):
+        rc, rep, digests = av1recon.verify_buffer(blob, host_threads=4)
+        assert rc == 0 and rep.status == 0, rep.message
+        assert rep.frames == INDEX[name]["frames"] * copies
+    dec = _gpu_decode(name)
+    want = [[int(x) for x in r.checksum] for r in dec.results]
+    dec.close()
+    for i in range(len(digests)):
+        assert [int(x) for x in digests[i]] == want[i % len(want)], f"frame {i}"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("clip", ["c1", "c3_small", "c3", "c4"])
 def test_cuda_full_size_clip_vs_dav1d(built, clip):
     """BASELINE-size clips (when present in streams_cache/): every plane digest of every frame from av1r_verify_buffer equals the
