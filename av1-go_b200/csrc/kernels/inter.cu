@@ -65,7 +65,8 @@ struct InterSmem {
 
 // idx / d for idx <= 39 * 39 and d <= 39 as a multiply and a shift (inv = ceil(65536 / d); exact in that range): the tile loops
 // below split a linear thread index into (row, column) for every sample
-__device__ __forceinline__ int recip16(int d) { return (65536 + d - 1) / d; }
+__constant__ uint32_t c_recip16[41];   // ceil(65536 / d), d = 1 .. 40
+__device__ __forceinline__ int recip16(int d) { return c_recip16[d]; }
 __device__ __forceinline__ int div16(int idx, int inv) { return (idx * inv) >> 16; }
 
 template <typename T>
@@ -83,9 +84,23 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
     const int16_t* fv = c_subpel[fidx_v][fy];
     const int ww = tw + 7, wh = th + 7;
     const int inv_ww = recip16(ww), inv_tw = recip16(tw);
-    for (int idx = threadIdx.x; idx < ww * wh; idx += INTER_THREADS) {
-        const int r = div16(idx, inv_ww), c = idx - r * ww;
-        sm.refwin[r * RW + c] = (uint16_t)ld_ref<T>(ref, pitch, min(max(ix + c - 3, 0), lastx), min(max(iy + r - 3, 0), lasty));
+    // four independent loads in flight per thread before the first store (the window fetch is pure L2 / L1 latency)
+    for (int base = threadIdx.x; base < ww * wh; base += 4 * INTER_THREADS) {
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * INTER_THREADS;
+            const int r = div16(min(idx, ww * wh - 1), inv_ww), c = min(idx, ww * wh - 1) - r * ww;
+            v[u] = ld_ref<T>(ref, pitch, min(max(ix + c - 3, 0), lastx), min(max(iy + r - 3, 0), lasty));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * INTER_THREADS;
+            if (idx < ww * wh) {
+                const int r = div16(idx, inv_ww), c = idx - r * ww;
+                sm.refwin[r * RW + c] = (uint16_t)v[u];
+            }
+        }
     }
     __syncthreads();
     int32_t* mid = sm.mid;
@@ -318,6 +333,11 @@ static cudaError_t inter_upload_constants() {
     if (e != cudaSuccess) return e;
     if (dev < 64 && g_inter_const_loaded[dev]) return cudaSuccess;
     if ((e = cudaMemcpyToSymbol(c_subpel, av1t_subpel_filters, sizeof(av1t_subpel_filters))) != cudaSuccess) return e;
+    {
+        uint32_t rc[41] = {0, 65536};
+        for (int d = 2; d <= 40; d++) rc[d] = (uint32_t)((65536 + d - 1) / d);
+        if ((e = cudaMemcpyToSymbol(c_recip16, rc, sizeof(rc))) != cudaSuccess) return e;
+    }
     if ((e = cudaMemcpyToSymbol(c_wedge_codebook, av1t_wedge_codebook, sizeof(av1t_wedge_codebook))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_wedge_signflip, av1t_wedge_signflip, sizeof(av1t_wedge_signflip))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_blk_w, kBlockW, sizeof(kBlockW))) != cudaSuccess) return e;
