@@ -49,6 +49,14 @@ __global__ void __launch_bounds__(256) checksum_kernel(const uint8_t* __restrict
 cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(out_dev, 0, sizeof(uint64_t), s);
     if (e != cudaSuccess) return e;
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(checksum_kernel<uint8_t>);
+            prefer_max_smem(checksum_kernel<uint16_t>);
+            carve_done = true;
+        }
+    }
     const int vec = bpc == 8 ? 16 : 8;
     long long items = (long long)((w + vec - 1) / vec) * h;
     int blocks = (int)((items + 256 * 4 - 1) / (256 * 4));

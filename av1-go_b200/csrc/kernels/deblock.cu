@@ -153,6 +153,16 @@ __global__ void __launch_bounds__(256) deblock_kernel(LfLaunch L) {
 }
 
 cudaError_t launch_deblock(const LfLaunch& L, cudaStream_t s) {
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(deblock_kernel<uint8_t, 0>);
+            prefer_max_smem(deblock_kernel<uint16_t, 0>);
+            prefer_max_smem(deblock_kernel<uint8_t, 1>);
+            prefer_max_smem(deblock_kernel<uint16_t, 1>);
+            carve_done = true;
+        }
+    }
     int nplanes = L.fp.mono ? 1 : 3;
     {
         dim3 grid((L.fp.pw4[0] + 7) / 8, (L.fp.ch[0] + 31) / 32, nplanes);

@@ -5,6 +5,14 @@
 
 namespace av1r {
 
+// Every kernel of the engine asks for the same (largest) shared-memory carve-out: the SMs then never have to drain to be
+// re-partitioned between L1 and shared memory when kernels of different frames (K3 needs 60-75 KB per CTA, the filters a few KB)
+// land on the same SM, which is what lets the stages of the frames in flight overlap.
+template <class F>
+static inline void prefer_max_smem(F f) {
+    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 __device__ __forceinline__ int d_round2(int x, int n) { return n == 0 ? x : (x + (1 << (n - 1))) >> n; }
 __device__ __forceinline__ int d_clip3(int lo, int hi, int x) { return min(max(x, lo), hi); }
 

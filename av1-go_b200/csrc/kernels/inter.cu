@@ -417,6 +417,16 @@ cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
     if (L.n <= 0) return cudaSuccess;
     cudaError_t e = inter_upload_constants();
     if (e != cudaSuccess) return e;
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(inter_pred_kernel<uint8_t>);
+            prefer_max_smem(inter_pred_kernel<uint16_t>);
+            prefer_max_smem(inter_residual_kernel<uint8_t>);
+            prefer_max_smem(inter_residual_kernel<uint16_t>);
+            carve_done = true;
+        }
+    }
     if (L.fp.bd == 8) inter_pred_kernel<uint8_t><<<L.n, INTER_THREADS, 0, s>>>(L);
     else inter_pred_kernel<uint16_t><<<L.n, INTER_THREADS, 0, s>>>(L);
     return cudaGetLastError();

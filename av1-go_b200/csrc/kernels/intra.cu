@@ -136,11 +136,14 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
                  : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
+// Polling a neighbour unit's flag uses a relaxed load (served by L2, no side effects); the acquire fence -- which invalidates the
+// SM's whole L1 (SASS CCTL.IVALL) -- is paid once, after the flag has been seen, not on every poll of every waiting CTA.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ int warp_sum(int v) {
@@ -666,10 +669,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                 const int d = __ldg(&up->dep[lane]);
                 if (d >= 0) {
                     int spins = 0;
-                    while (ld_acquire(L.uflags + d) == 0) {   // <= 5 polling lanes per CTA
-                        __nanosleep(40);
-                        if (++spins > (1 << 26)) { L.ticket[1] = 2; break; }
+                    while (ld_relaxed(L.uflags + d) == 0) {   // <= 5 polling lanes per CTA
+                        __nanosleep(100);
+                        if (++spins > (1 << 25)) { L.ticket[1] = 2; break; }
                     }
+                    fence_acquire_gpu();
                 }
             }
             __syncwarp();
@@ -867,6 +871,16 @@ cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s) {
     if (L.fp.subx != 1 || L.fp.suby != 1 || L.fp.mono) return cudaErrorInvalidValue;   // the canvas geometry is 4:2:0
     cudaError_t e = intra_upload_constants();
     if (e != cudaSuccess) return e;
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(intra_unit_kernel<uint8_t, 4>);
+            prefer_max_smem(intra_unit_kernel<uint16_t, 4>);
+            prefer_max_smem(intra_unit_kernel<uint8_t, 8>);
+            prefer_max_smem(intra_unit_kernel<uint16_t, 8>);
+            carve_done = true;
+        }
+    }
     const int warps = L.warps <= 4 ? 4 : 8;
     const int blocks = std::min(L.n_units, std::max(1, L.ctas));
     if (L.fp.bd == 8) {

@@ -285,6 +285,13 @@ cudaError_t launch_itx(const TxRec* recs, const uint32_t* order, int n, int n_sm
         cudaFuncSetAttribute(itx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_done = true;
     }
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(itx_small_kernel);
+            carve_done = true;
+        }
+    }
     if (n_small > 0)
         itx_small_kernel<<<(n_small + ITXS_HALF_WARPS - 1) / ITXS_HALF_WARPS, ITXS_HALF_WARPS * 16, 0, s>>>(recs, order, n_small, coefs, res, fp);
     if (n > n_small) {

@@ -193,6 +193,14 @@ cudaError_t launch_lr(const LrLaunch& L, cudaStream_t s) {
         if ((e = cudaMemcpyToSymbol(c_sgr_params, av1t_sgr_params, sizeof(av1t_sgr_params))) != cudaSuccess) return e;
         if (dev < 64) g_lr_const_loaded[dev] = true;
     }
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(lr_kernel<uint8_t>);
+            prefer_max_smem(lr_kernel<uint16_t>);
+            carve_done = true;
+        }
+    }
     const int nstripes = (L.fp.h[0] + 8 + 63) / 64;
     dim3 grid((L.fp.w[0] + LR_TW - 1) / LR_TW, nstripes, L.fp.mono ? 1 : 3);
     if (L.fp.bd == 8) lr_kernel<uint8_t><<<grid, 256, 0, s>>>(L);

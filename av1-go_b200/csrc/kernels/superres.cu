@@ -45,6 +45,14 @@ cudaError_t launch_superres(const SuperresLaunch& L, cudaStream_t s) {
         if (dev < 64) g_sr_const_loaded[dev] = true;
     }
     // chroma planes are at most as large as luma: the grid is sized for luma and chroma CTAs outside their plane exit at once
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            prefer_max_smem(superres_kernel<uint8_t>);
+            prefer_max_smem(superres_kernel<uint16_t>);
+            carve_done = true;
+        }
+    }
     dim3 grid((L.up_w[0] + 255) / 256, L.h[0], L.planes);
     if (L.bd == 8) superres_kernel<uint8_t><<<grid, 256, 0, s>>>(L);
     else superres_kernel<uint16_t><<<grid, 256, 0, s>>>(L);

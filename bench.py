@@ -282,7 +282,7 @@ def run_c2(args, torch, dist, rank, world, local, name="c2"):
     import av1recon
     tus = c2_clip(name)
     torch.cuda.set_device(local)
-    dec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
+    dec = av1recon.Decoder(device=local, streams=32, frames_in_flight=64)
     clip = av1recon.Clip(dec, tus)
     info = clip.info
     nfr = int(info.frames_shown)
@@ -387,7 +387,7 @@ def run_c2(args, torch, dist, rank, world, local, name="c2"):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if info.bit_depth == 8 else "u16", "data": "synthetic",
         "config": {"workload": C2_DESC if name == "c2" else CLIP_DESC[name] + STEP_NOTE, "frames_per_step": nfr, "parallelism": f"replicas{world} (independent clips per GPU, no collective)",
-                   "streams": 16, "frames_in_flight": 32},
+                   "streams": 32, "frames_in_flight": 64},
         "gpu_launches": launches_per_step * args.steps,
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr,
                 "host_parse_ms_per_step": parse_ms, "host_threads": os.cpu_count(), "single_thread_submit_tu_fps": e2e_1t,
@@ -467,7 +467,7 @@ def run_c5(args, torch, dist, rank, world, local):
     mine = shard.assign(items, world)[rank]
     my_tus = [t for k in mine for t in tus_of[k]]
     torch.cuda.set_device(local)
-    dec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
+    dec = av1recon.Decoder(device=local, streams=32, frames_in_flight=64)
     clip = av1recon.Clip(dec, my_tus)
     info = clip.info
     nfr_local = int(info.frames_shown)
@@ -537,7 +537,7 @@ def run_c5(args, torch, dist, rank, world, local):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
         "config": {"workload": C5_DESC, "frames_per_step": nfr, "items": len(items), "items_this_rank": len(mine),
-                   "parallelism": f"gop-segment sharding over {world} GPU(s), no collective", "streams": 16, "frames_in_flight": 32},
+                   "parallelism": f"gop-segment sharding over {world} GPU(s), no collective", "streams": 32, "frames_in_flight": 64},
         "gpu_launches": sum(v["launches"] for v in stages.values()) * args.steps,
         "e2e": {"value": nfr / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr_local,
                 "host_threads_per_rank": host_threads, "host_parse_ms_per_step_rank0": rep.host_parse_ms},
