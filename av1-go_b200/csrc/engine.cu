@@ -487,6 +487,8 @@ struct EngineImpl {
     size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
     int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
     int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
+    int k3_progressive = 1;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive (default), 2 always cell-level
+    int k3_intra_run = 0;                             // consecutive frames without inter prediction issued so far
     int64_t frames_decoded = 0;
 
     int wait_slot(FrameSlot& s);
@@ -602,10 +604,28 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         il.warps = k3_warps;
         il.load_tile = L.n_inter > 0;
-        CK(s.sync.ensure(sizeof(int) * (L.n_k3units + 4), &hw_sync));
-        CK(cudaMemsetAsync(s.sync.p, 0, sizeof(int) * (L.n_k3units + 4), st));
-        il.uflags = (int*)s.sync.p;
-        il.ticket = (int*)s.sync.p + L.n_k3units;
+        // sync block: [n_units x u64 progress words][n_units x int unit flags][ticket, stuck flag, pad]
+        const size_t sync_bytes = (sizeof(unsigned long long) + sizeof(int)) * (size_t)L.n_k3units + 4 * sizeof(int);
+        CK(s.sync.ensure(sync_bytes, &hw_sync));
+        CK(cudaMemsetAsync(s.sync.p, 0, sync_bytes, st));
+        il.uprog = (unsigned long long*)s.sync.p;
+        il.uflags = (int*)(s.sync.p + sizeof(unsigned long long) * (size_t)L.n_k3units);
+        il.ticket = il.uflags + L.n_k3units;
+        // Latency vs throughput.  Cell-level hand-over gives a 1.6x lower frame latency; whole-unit hand-over keeps fewer CTAs resident
+        // and polling per frame and gives the higher clip rate when many independent frames run side by side.  So: cell-level for
+        // every frame later frames predict from (it is on its GOP's critical path) and whenever the GPU is not saturated (the frame
+        // issued 8 frames ago has already completed); whole-unit only inside a run of independent key frames with >= 8 in flight.
+        k3_intra_run = L.n_inter == 0 ? k3_intra_run + 1 : 0;
+        bool saturated = false;
+        {
+            const int n = (int)slots.size();
+            if (n > 8) {
+                const FrameSlot& old = *slots[((next_slot - 1 - 8) % n + n) % n];
+                saturated = old.busy && cudaEventQuery(old.ev1) == cudaErrorNotReady;
+            }
+        }
+        il.progressive = k3_progressive == 1 ? !(k3_intra_run >= 4 && saturated) : (k3_progressive != 0);
+        if (il.progressive && k3_ctas <= 0 && L.n_inter == 0) il.ctas = std::min(L.n_k3units, (il.ctas * 7 + 4) / 5);
         il.frame = recon->pl;
         il.res = res;
         il.fp = fp;
@@ -1013,6 +1033,7 @@ int Engine::open(const av1r_config& cfg) {
         E.slots.push_back(std::move(s));
     }
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));
+    if (const char* e = getenv("AV1R_K3_PROGRESSIVE")) E.k3_progressive = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("AV1R_K3_WARPS")) E.k3_warps = std::min(8, std::max(1, atoi(e)));
     if (getenv("AV1R_K3_PROF")) {
         CK(E.k3_prof.ensure(16 * sizeof(unsigned long long)));

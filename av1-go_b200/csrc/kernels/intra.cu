@@ -143,6 +143,17 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Progressive hand-over: one 64-bit word per unit, a bit per 4-sample cell of the unit's bottom row and right column, per plane:
+//   luma bottom 0..15, luma right 16..31, U bottom 32..39, U right 40..47, V bottom 48..55, V right 56..63.
+// A record that writes such cells stores them to the frame, fences and ORs its bits in; records of neighbour units that read
+// them wait for the bits, then fetch the samples into their canvas halo.
+__device__ __forceinline__ int prog_boff(int p) { return p == 0 ? 0 : (p == 1 ? 32 : 48); }
+__device__ __forceinline__ int prog_roff(int p) { return p == 0 ? 16 : (p == 1 ? 40 : 56); }
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
@@ -663,8 +674,26 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         TxRec r_next;
         if (k < count) r_next = load_rec(L.recs + __ldg(L.order + first + k));
         lap(1, tid == 0);   // prologue: context, owner map
+        if (L.progressive) {
+            // border cells that no record of this unit reconstructs (inter-predicted samples, cells outside the frame) are final
+            __syncthreads();   // owner map complete
+            if (warp == 0) {
+                unsigned long long pre = 0;
+#pragma unroll
+                for (int p = 0; p < 3; p++) {
+                    const int uw4 = p ? 8 : 16;
+                    const int32_t* m = owner + (p == 0 ? 0 : (p == 1 ? 256 : 320));
+                    const bool inb = lane < uw4;
+                    const unsigned bb = __ballot_sync(0xffffffffu, inb && m[(uw4 - 1) * uw4 + lane] < 0);
+                    const unsigned rb = __ballot_sync(0xffffffffu, inb && m[lane * uw4 + uw4 - 1] < 0);
+                    pre |= (unsigned long long)bb << prog_boff(p);
+                    pre |= (unsigned long long)rb << prog_roff(p);
+                }
+                if (lane == 0 && pre) atomicOr(L.uprog + u, pre);
+            }
+        }
         // ---- wait for the neighbour units whose samples this unit reads
-        if (warp == 0) {
+        if (warp == 0 && !L.progressive) {
             if (lane < 5) {
                 const int d = __ldg(&up->dep[lane]);
                 if (d >= 0) {
@@ -681,7 +710,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         __syncthreads();
         lap(2, tid == 0);   // neighbour units
         // ---- halo (and, in inter frames, the unit's own inter-predicted samples) from L2
-        {   // row above (corner .. above-right) and column to the left (.. below-left) of the three planes: one flat index space, all
+        if (!L.progressive) {   // row above (corner .. above-right) and column to the left (.. below-left) of the three planes: one flat index space, all
             // loads of a thread issued before the first store, so the halo costs one L2 round trip
             constexpr int SEG0 = 2 * (2 * CV_W0 + 1), SEG1 = 2 * (2 * CV_W1 + 1);   // per plane: [row: 2W + 1][col: 2W] (+1 pad)
             constexpr int TOT = SEG0 + 2 * SEG1;
@@ -762,9 +791,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                 const int na = want_above ? w4 * (need_ar ? 2 : 1) + 1 : 0;      // cells x4-1 .. on row y4-1 (the first is the corner)
                 const int nl = want_left ? h4 * (need_bl ? 2 : 1) : 0;            // cells y4 .. on column x4-1
                 const int32_t* m = owner + (plane == 0 ? 0 : (plane == 1 ? 256 : 320));
+                const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
                 for (int c0 = 0; c0 < na + nl; c0 += 32) {       // warp-uniform trip count: the wait is collective
                     const int c = c0 + lane;
                     int id = -1;
+                    int nbr = -1, bit = 0, cxl = 0, cyl = 0;     // cell outside the unit: neighbour (index into K3Unit::dep) and its progress bit
                     if (c < na + nl) {
                         int cx, cy;
                         if (c < na) {
@@ -776,10 +807,71 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                         }
                         cx = min(max(cx, 0), pw4 - 1) - bx4;
                         cy = min(max(cy, 0), ph4 - 1) - by4;
-                        if (cx >= 0 && cy >= 0 && cx < uw4 && cy < uw4) {   // cells of other units were final before the unit started
+                        cxl = cx;
+                        cyl = cy;
+                        if (cx >= 0 && cy >= 0 && cx < uw4 && cy < uw4) {   // (whole-unit hand-over: cells of other units were final before the unit started)
                             id = m[cy * uw4 + cx];
                             if (id >= k) id = -1;
+                        } else if (L.progressive) {
+                            if (cy < 0) {            // row above the unit: above-left / above / above-right unit, bottom row of cells
+                                nbr = cx < 0 ? 2 : (cx < uw4 ? 3 : 4);
+                                bit = prog_boff(plane) + (cx < 0 ? uw4 - 1 : (cx < uw4 ? cx : cx - uw4));
+                            } else if (cx < 0) {     // column left of the unit: left / below-left unit, right column of cells
+                                nbr = cy < uw4 ? 0 : 1;
+                                bit = prog_roff(plane) + (cy < uw4 ? cy : cy - uw4);
+                            }
                         }
+                    }
+                    if (L.progressive && __any_sync(0xffffffffu, nbr >= 0)) {
+                        // lane n < 5 collects the cells wanted from neighbour n and polls that unit's progress word
+                        const unsigned long long mine = nbr >= 0 ? 1ull << bit : 0ull;
+                        unsigned long long want = 0;
+#pragma unroll
+                        for (int n = 0; n < 5; n++) {
+                            const unsigned lo = __reduce_or_sync(0xffffffffu, nbr == n ? (unsigned)mine : 0u);
+                            const unsigned hi = __reduce_or_sync(0xffffffffu, nbr == n ? (unsigned)(mine >> 32) : 0u);
+                            if (lane == n) want = ((unsigned long long)hi << 32) | lo;
+                        }
+                        if (lane < 5 && want) {
+                            const int d = __ldg(&up->dep[lane]);
+                            if (d >= 0) {
+                                int spins = 0;
+                                unsigned ns = 40;
+                                while ((ld_relaxed64(L.uprog + d) & want) != want) {
+                                    __nanosleep(ns);
+                                    if (ns < 320) ns <<= 1;
+                                    if (++spins > (1 << 24)) { L.ticket[1] = 3; break; }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        fence_acquire_gpu();
+                        if (nbr >= 0) {   // bring the cell's four samples next to the unit into the canvas halo
+                            T* cv = uc.cv(plane);
+                            const int cs = uc.cs(plane), W = uc.W(plane);
+                            const int x0 = ux * W, y0 = uy * W;
+                            const uint8_t* fb = L.frame.p[plane];
+                            const uint32_t pitch = L.frame.pitch[plane];
+                            if (cyl < 0) {
+                                const T* src = reinterpret_cast<const T*>(fb + (size_t)(y0 - 1) * pitch);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const int dx = cxl * 4 + j;
+                                    if (x0 + dx < pcw) cv[-cs + dx] = __ldcg(src + x0 + dx);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const int dy = cyl * 4 + j;
+                                    if (y0 + dy < pch) {
+                                        const T v = __ldcg(reinterpret_cast<const T*>(fb + (size_t)(y0 + dy) * pitch) + x0 - 1);
+                                        if (dy < W) cv[dy * cs - 1] = v;
+                                        else uc.lext[uc.lext_off(plane) + dy - W] = v;
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
                     wait_local(rbar, id, rpar, L.ticket + 1);
                 }
@@ -808,6 +900,44 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             intra_block<T>(r, uc, fp, sm, lane, L.wedge_master, L.pal);
             __syncwarp();        // all lanes' samples are in the canvas before lane 0 releases the record's barrier
             if (lane == 0) mbar_arrive(rbar + 8u * (uint32_t)k);
+            if (L.progressive) {
+                // cells of the unit's bottom row / right column this record is the last writer of: store them to the frame now and
+                // publish them, so that the units below and to the right can start on them while this unit is still busy
+                const int plane = r.plane;
+                const int uw4 = plane ? 8 : 16, W = uc.W(plane), cs = uc.cs(plane);
+                const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
+                const int lx4 = r.x4 - ux * uw4, ly4 = r.y4 - uy * uw4;
+                const int32_t* m = owner + (plane == 0 ? 0 : (plane == 1 ? 256 : 320));
+                const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
+                const int x0 = ux * W, y0 = uy * W;
+                const T* cv = uc.cv(plane);
+                uint8_t* fb = L.frame.p[plane];
+                const uint32_t pitch = L.frame.pitch[plane];
+                unsigned long long bits = 0;
+                if (ly4 + h4 == uw4) {
+                    const unsigned ob = __ballot_sync(0xffffffffu, lane < w4 && m[(uw4 - 1) * uw4 + lx4 + lane] == k);
+                    T* dst = reinterpret_cast<T*>(fb + (size_t)(y0 + W - 1) * pitch) + x0;
+                    for (int i = lane; i < 4 * w4; i += 32) {
+                        const int dx = lx4 * 4 + i;
+                        if (((ob >> (i >> 2)) & 1) && x0 + dx < pcw && y0 + W - 1 < pch) dst[dx] = cv[(W - 1) * cs + dx];
+                    }
+                    bits |= (unsigned long long)ob << (prog_boff(plane) + lx4);
+                }
+                if (lx4 + w4 == uw4) {
+                    const unsigned ob = __ballot_sync(0xffffffffu, lane < h4 && m[(ly4 + lane) * uw4 + uw4 - 1] == k);
+                    for (int i = lane; i < 4 * h4; i += 32) {
+                        const int dy = ly4 * 4 + i;
+                        if (((ob >> (i >> 2)) & 1) && y0 + dy < pch && x0 + W - 1 < pcw)
+                            reinterpret_cast<T*>(fb + (size_t)(y0 + dy) * pitch)[x0 + W - 1] = cv[dy * cs + W - 1];
+                    }
+                    bits |= (unsigned long long)ob << (prog_roff(plane) + ly4);
+                }
+                if (bits) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicOr(L.uprog + u, bits);
+                }
+            }
             lap(10, lane == 0);  // predict + reconstruct
             if (L.prof && lane == 0) atomicAdd(L.prof + 12, 1ull);
         }

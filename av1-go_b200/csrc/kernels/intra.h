@@ -15,6 +15,8 @@ struct IntraLaunch {            // passed by value
     int ctas;                   // persistent CTAs this frame may occupy (one unit per CTA at a time)
     int warps;                  // warps per CTA (records of a unit in flight)
     int load_tile;              // 1: the frame already holds inter-predicted samples (inter frame) -> bring the unit in before predicting
+    int progressive;            // 1: units hand their bottom row / right column over cell by cell (uprog), 0: whole units (uflags)
+    unsigned long long* uprog;  // device, n_units words, zeroed before launch: finished border cells of every unit (bit layout in intra.cu)
     int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
     int* ticket;                // device, one int, zeroed before launch
     DevPlanes frame;
