@@ -67,39 +67,46 @@ static void cdef_build_lines(CdefLineTable& t) {
     }
 }
 
-__device__ __forceinline__ int cdef_constrain(int diff, int threshold, int damping) {
-    if (!threshold) return 0;
-    const int adj = max(0, damping - (31 - __clz(threshold)));
+// constrain() of spec 7.15.3 with the damping shift (adj = max(0, damping - floor(log2(threshold)))) hoisted out of the tap loop
+__device__ __forceinline__ int cdef_constrain(int diff, int threshold, int adj) {
     const int mag = abs(diff);
     const int v = min(max(threshold - (mag >> adj), 0), mag);
     return diff < 0 ? -v : v;
 }
 
-__device__ __forceinline__ int cdef_pixel(const int16_t* tile, int ts, int tx, int ty, int pri, int sec, int damping, int dir, int cs) {
-    const int x = tile[ty * ts + tx];
+// dtab[d][k] = tile offset (dy * stride + dx) of tap k of direction d: read from shared memory, because the four 8x8 blocks a warp
+// covers have different directions and a register-indexed *constant* load would be replayed once per distinct direction
+__device__ __forceinline__ int cdef_pixel(const int16_t* tile, const int16_t (*dtab)[2], int pos, int pri, int sec, int damping, int dir, int cs) {
+    const int x = tile[pos];
     int sum = 0, mx = x, mn = x;
     const int pt0 = ((pri >> cs) & 1) ? 3 : 4, pt1 = ((pri >> cs) & 1) ? 3 : 2;
+    const int adj_p = pri ? max(0, damping - (31 - __clz(pri))) : 0, adj_s = sec ? max(0, damping - (31 - __clz(sec))) : 0;
+    const int d2a = (dir + 2) & 7, d2b = (dir - 2) & 7;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int ptap = k ? pt1 : pt0, stap = k ? 1 : 2;
+        const int op = dtab[dir][k], oa = dtab[d2a][k], ob = dtab[d2b][k];
 #pragma unroll
         for (int sg = -1; sg <= 1; sg += 2) {
-            {
-                const int p = tile[(ty + sg * c_cdef_dir[dir][k][0]) * ts + tx + sg * c_cdef_dir[dir][k][1]];
+            if (pri) {
+                const int p = tile[pos + sg * op];
                 if (p >= 0) {
-                    sum += ptap * cdef_constrain(p - x, pri, damping);
+                    sum += ptap * cdef_constrain(p - x, pri, adj_p);
                     mx = max(mx, p);
                     mn = min(mn, p);
                 }
             }
-#pragma unroll
-            for (int off = -2; off <= 2; off += 4) {
-                const int d2 = (dir + off) & 7;
-                const int s = tile[(ty + sg * c_cdef_dir[d2][k][0]) * ts + tx + sg * c_cdef_dir[d2][k][1]];
-                if (s >= 0) {
-                    sum += stap * cdef_constrain(s - x, sec, damping);
-                    mx = max(mx, s);
-                    mn = min(mn, s);
+            if (sec) {
+                const int s0 = tile[pos + sg * oa], s1 = tile[pos + sg * ob];
+                if (s0 >= 0) {
+                    sum += stap * cdef_constrain(s0 - x, sec, adj_s);
+                    mx = max(mx, s0);
+                    mn = min(mn, s0);
+                }
+                if (s1 >= 0) {
+                    sum += stap * cdef_constrain(s1 - x, sec, adj_s);
+                    mx = max(mx, s1);
+                    mn = min(mn, s1);
                 }
             }
         }
@@ -114,6 +121,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
     __shared__ uint8_t s_dir[64], s_skip[64];
     __shared__ int s_var[64];
     __shared__ __align__(16) CdefLineTable s_lines;
+    __shared__ int16_t s_dtab[8][2];
     const DevFrameParams& fp = L.fp;
     const int tid = threadIdx.x;
     const int fbx = blockIdx.x, fby = blockIdx.y;
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
     const int idx = L.cdef_idx[(size_t)fby * c64 + fbx];
     const int bd = fp.bd, cs = bd - 8;
     const int nplanes = fp.mono ? 1 : 3;
+    if (tid < 16) s_dtab[tid >> 1][tid & 1] = (int16_t)(c_cdef_dir[tid >> 1][tid & 1][0] * CDEF_LT + c_cdef_dir[tid >> 1][tid & 1][1]);
     for (int i = tid; i < (int)(sizeof(CdefLineTable) / 4); i += 256) reinterpret_cast<uint32_t*>(&s_lines)[i] = reinterpret_cast<const uint32_t*>(&g_cdef_lines)[i];
     // ---- stage tiles
     for (int plane = 0; plane < nplanes; plane++) {
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
                     dir = pri == 0 ? 0 : c_cdef_uv_dir[fp.subx][fp.suby][ydir];
                     damping = fp.cdef_damping + cs - 1;
                 }
-                if (pri | sec) v = cdef_pixel(tile, CDEF_LT, px + 2, py + 2, pri, sec, damping, dir, cs);
+                if (pri | sec) v = cdef_pixel(tile, s_dtab, (py + 2) * CDEF_LT + px + 2, pri, sec, damping, dir, cs);
             }
             dst[(size_t)y * pitch_e + x] = (T)v;
         }

@@ -6,13 +6,17 @@
 //   * one CTA owns one 64x64 luma unit (+ its two 32x32 chroma tiles) at a time.  The unit's samples live in a shared-memory
 //     canvas together with the halo they can read: the row above (corner .. above-right) and the column to the left
 //     (.. below-left; above-right samples beside the unit never exist: the unit to the right is decoded later).
-//   * inside the CTA the unit's records are claimed in decode order by NW warps through a shared-memory ticket; a warp looks up
-//     the owners of the 4x4 cells its edges come from in a shared-memory owner map and spins on their done-flags (shared
-//     memory, ~30 cycles), predicts from the canvas into the canvas, adds the residual (brought in by one TMA bulk copy per
-//     unit: the residual is stored unit-major) and raises its flag.  One link costs a few hundred cycles.
+//   * inside the CTA the unit's records are dealt round-robin to NW warps; a warp looks up the owners of the 4x4 cells its edges
+//     come from in a shared-memory owner map and waits on those records' completion barriers (one mbarrier per record:
+//     try_wait suspends the warp in hardware), predicts from the canvas into the canvas, adds the residual (brought in by one
+//     TMA bulk copy per unit: the residual is stored unit-major) and arrives on its own barrier.  One link = one predictor
+//     call (~3000 cycles of dependent instructions), no L2 round trip.
 //   * units are listed by the host in wavefront order with the table indices of the (<= 5) neighbour units they read; a
-//     persistent grid claims units through a global ticket, waits for those neighbours' flags (acquire), loads the halo from
-//     L2, and after the last record writes the unit back with coalesced stores, fences and releases its own flag.
+//     persistent grid claims units through a global ticket.  Hand-over between units is either whole-unit (wait for the
+//     neighbours' flags, load the halo, write the unit back, release the flag) or -- default -- cell-level: every unit has a
+//     64-bit progress word with a bit per 4-sample cell of its bottom row and right column; the record that last writes such
+//     cells stores them, fences and publishes the bits, and the border records of the neighbour units wait for exactly the bits
+//     they need and fetch those samples into their halo on demand, so a unit starts while its neighbours are still busy.
 //     A CTA only waits for lower tickets, which are held by CTAs that already run: no deadlock.
 // Algorithmic bytes: F_intra written + 2A residual read + 32 B/record (+ halo re-reads, L2 hits).
 #include <cuda_runtime.h>
