@@ -1284,7 +1284,10 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
                 if (staging.valid()) staging.get();      // TU t-1 is staged and published
                 const std::string perr = sp.err;
                 const SeqHdr seq = sp.hp.seq;
-                staging = std::async(std::launch::async, [&, t, pfs, prc, perr, seq]() {
+                // with fewer segments than threads the staging of TU t overlaps the parse of TU t+1 on a helper thread; when the
+                // segments alone fill the cores a helper would only add a thread creation per TU and time-slicing: stage inline
+                const auto policy = WorkerPool::nested_enabled() ? std::launch::async : std::launch::deferred;
+                staging = std::async(policy, [&, t, pfs, prc, perr, seq]() {
                     cudaSetDevice(E.cfg.device);
                     int rc2 = prc;
                     std::string e2 = perr;
@@ -1297,6 +1300,7 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
                         }
                     publish(t, std::move(*pfs), rc2, e2);
                 });
+                if (policy == std::launch::deferred) staging.get();
                 if (prc) failed = true;
             }
             if (staging.valid()) staging.get();

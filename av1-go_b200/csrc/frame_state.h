@@ -47,6 +47,15 @@ struct BlockInfo {
     int32_t warp[6];           // LocalWarpParams
 };
 
+// Per-mi digest of a block for the loop-filter edge pre-pass (8 bytes, read sequentially instead of chasing BlockInfo pointers)
+struct LfMi {
+    uint8_t lvl[4];            // BlockInfo::lf_lvl
+    uint8_t bsize;
+    uint8_t filt_inside;       // !skip || intra: transform edges inside the block are filtered too
+    uint8_t valid;             // 1 once a block of this frame covers the mi
+    uint8_t pad;
+};
+
 // Motion vector + reference saved per 8x8 for later frames (spec 7.19), and the projected field (7.9)
 struct SavedMv {
     Mv mv;
@@ -151,6 +160,7 @@ struct FrameWork {
     // mode info (host only)
     std::vector<std::unique_ptr<TileOut>> tiles;   // per-tile outputs (own the BlockInfo storage)
     std::vector<BlockInfo*> mi;         // per mi -> block
+    std::vector<LfMi> lf_mi;            // per mi: what the deblocking edge builder needs of the block (levels, size, skip && inter)
     std::vector<uint8_t> inter_tx;      // per mi: InterTxSizes
     std::vector<uint8_t> lf_tx[3];      // per plane 4x4: LoopfilterTxSizes
     std::vector<uint8_t> tx_types;      // per mi (luma)
@@ -176,6 +186,7 @@ struct FrameWork {
         // reads it (each block writes its whole area), so resizing without a fill is enough.
         size_t n = (size_t)mi_cols * mi_rows;
         mi.assign(n, nullptr);
+        lf_mi.resize(n);   // written for every mi a block covers; the edge builder only reads covered mi
         inter_tx.resize(n);
         tx_types.resize(n);
         seg_ids.resize(n);

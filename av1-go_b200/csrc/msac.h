@@ -30,6 +30,17 @@ struct Msac {
     }
     inline void refill() {
         int s = 64 - 9 - (cnt + 15);
+        if (s >= 0 && end - bptr >= 8) {
+            // whole bytes that fit below the window: one big-endian 64-bit load instead of a byte loop
+            uint64_t v;
+            __builtin_memcpy(&v, bptr, 8);
+            v = __builtin_bswap64(v);
+            const int n = (s >> 3) + 1;                 // 1 .. 7 bytes (s <= 55)
+            dif ^= (v >> (64 - 8 * n)) << (s - 8 * (n - 1));
+            cnt += 8 * n;
+            bptr += n;
+            return;
+        }
         for (; s >= 0 && bptr < end; s -= 8, bptr++) {
             dif ^= (uint64_t)bptr[0] << s;
             cnt += 8;

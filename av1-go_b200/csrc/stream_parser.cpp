@@ -462,8 +462,10 @@ void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
                 // for sub-sampled planes the spec addresses mode info at the odd (bottom-right) luma mi
                 const int mrow = std::min(fw.mi_rows - 1, row | sy);
                 const int prow_v = mrow, prow_h = std::min(fw.mi_rows - 1, ((r4 - 1) << sy) | sy);
-                BlockInfo* const* mi_row = &fw.mi[(size_t)mrow * fw.mi_cols];
-                BlockInfo* const* mi_prev_row = r4 > 0 ? &fw.mi[(size_t)prow_h * fw.mi_cols] : nullptr;
+                BlockInfo* const* mi_ptr_row = &fw.mi[(size_t)mrow * fw.mi_cols];   // coverage test only (null = no block here)
+                const LfMi* mi_row = &fw.lf_mi[(size_t)mrow * fw.mi_cols];
+                const LfMi* mi_prev_row = r4 > 0 ? &fw.lf_mi[(size_t)prow_h * fw.mi_cols] : nullptr;
+                BlockInfo* const* mi_prev_ptr_row = r4 > 0 ? &fw.mi[(size_t)prow_h * fw.mi_cols] : nullptr;
                 (void)prow_v;
                 const bool row_visible = row * 4 < fh.frame_height;
                 for (int c4 = 0; c4 < pw4; c4++) {
@@ -472,18 +474,18 @@ void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
                     const size_t idx = (size_t)r4 * pw4 + c4;
                     LfEdge e{0, 0, 0, 0};
                     const int mcol = std::min(fw.mi_cols - 1, col | sx);
-                    const BlockInfo* b = mi_row[mcol];
-                    if (row_visible && col * 4 < fh.frame_width && b) {
+                    if (row_visible && col * 4 < fh.frame_width && mi_ptr_row[mcol]) {
+                        const LfMi& b = mi_row[mcol];
                         const int txsz = lf_tx[idx];
                         const int txw = kTxW[txsz], txh = kTxH[txsz];
-                        const int bwp = std::max(4, kBlockW[b->bsize] >> sx), bhp = std::max(4, kBlockH[b->bsize] >> sy);
+                        const int bwp = std::max(4, kBlockW[b.bsize] >> sx), bhp = std::max(4, kBlockH[b.bsize] >> sy);
                         const int xp = c4 * 4, yp = r4 * 4;
-                        const bool filt_inside = !b->skip || b->ref_frame[0] <= INTRA_FRAME;
+                        const bool filt_inside = b.filt_inside;
                         if (c4 > 0 && (xp & (txw - 1)) == 0 && (filt_inside || (xp & (bwp - 1)) == 0)) {
-                            int lvl = b->lf_lvl[li[0]];
+                            int lvl = b.lvl[li[0]];
                             if (!lvl) {
-                                const BlockInfo* pb = mi_row[std::min(fw.mi_cols - 1, ((c4 - 1) << sx) | sx)];
-                                if (pb) lvl = pb->lf_lvl[li[0]];
+                                const int pcol = std::min(fw.mi_cols - 1, ((c4 - 1) << sx) | sx);
+                                if (mi_ptr_row[pcol]) lvl = mi_row[pcol].lvl[li[0]];
                             }
                             if (lvl) {
                                 e.len_v = (uint8_t)std::min(max_len, std::min((int)kTxW[lf_tx[idx - 1]], txw));
@@ -491,10 +493,9 @@ void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
                             }
                         }
                         if (r4 > 0 && (yp & (txh - 1)) == 0 && (filt_inside || (yp & (bhp - 1)) == 0)) {
-                            int lvl = b->lf_lvl[li[1]];
+                            int lvl = b.lvl[li[1]];
                             if (!lvl) {
-                                const BlockInfo* pb = mi_prev_row[mcol];
-                                if (pb) lvl = pb->lf_lvl[li[1]];
+                                if (mi_prev_ptr_row[mcol]) lvl = mi_prev_row[mcol].lvl[li[1]];
                             }
                             if (lvl) {
                                 e.len_h = (uint8_t)std::min(max_len, std::min((int)kTxH[lf_tx[idx - pw4]], txh));

@@ -412,14 +412,22 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
     }
     // publish the block in the per-mi maps (clipped to the frame)
     const int rmax = std::min(r + bh4, fw.mi_rows), cmax = std::min(c + bw4, fw.mi_cols);
+    LfMi lm;
+    memcpy(lm.lvl, b->lf_lvl, 4);
+    lm.bsize = b->bsize;
+    lm.filt_inside = (uint8_t)(!b->skip || b->ref_frame[0] <= INTRA_FRAME);
+    lm.valid = 1;
+    lm.pad = 0;
     for (int y = r; y < rmax; y++) {
         BlockInfo** row = &fw.mi[(size_t)y * fw.mi_cols];
         uint8_t* sk = &fw.skip_mi[(size_t)y * fw.mi_cols];
         uint8_t* sg = &fw.seg_ids[(size_t)y * fw.mi_cols];
+        LfMi* lf = &fw.lf_mi[(size_t)y * fw.mi_cols];
         for (int x = c; x < cmax; x++) {
             row[x] = b;
             sk[x] = b->skip;
             sg[x] = b->segment_id;
+            lf[x] = lm;
         }
     }
     if (b->is_inter) emit_inter_block();
