@@ -32,7 +32,7 @@ __constant__ uint8_t c_wedge_codebook[3][16][3];
 __constant__ uint8_t c_wedge_signflip[BLOCK_SIZES_ALL][16];
 __constant__ uint8_t c_blk_w[BLOCK_SIZES_ALL];
 __constant__ uint8_t c_blk_h[BLOCK_SIZES_ALL];
-__device__ int16_t d_warped_filter[193][8];
+__device__ __align__(16) int16_t d_warped_filter[193][8];
 __device__ uint8_t d_obmc_mask[7][64];
 __device__ uint8_t d_wedge_master[6][64][64];
 static bool g_inter_const_loaded[64] = {false};
@@ -178,9 +178,22 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
         const long long dst_y = (long long)wr.mat[4] * src_x + (long long)wr.mat[5] * src_y + wr.mat[1];
         const long long x4 = dst_x >> sx, y4 = dst_y >> sy;
         const int ix4 = (int)(x4 >> 16), sx4 = (int)(x4 & 0xFFFF), iy4 = (int)(y4 >> 16), sy4 = (int)(y4 & 0xFFFF);
-        for (int idx = lane; idx < 15 * 15; idx += 32) {
-            const int wr_ = idx / 15, wc = idx - wr_ * 15;
-            win[wr_ * 16 + wc] = (uint16_t)ld_ref<T>(ref, pitch, min(max(ix4 + wc - 7, 0), lastx), min(max(iy4 + wr_ - 7, 0), lasty));
+        {   // 15 x 15 support: eight loads in flight per lane before the stores
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int idx = min(lane + 32 * u, 15 * 15 - 1);
+                const int wr_ = (idx * 4370) >> 16, wc = idx - wr_ * 15;   // idx / 15 for idx < 225
+                v[u] = ld_ref<T>(ref, pitch, min(max(ix4 + wc - 7, 0), lastx), min(max(iy4 + wr_ - 7, 0), lasty));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int idx = lane + 32 * u;
+                if (idx < 15 * 15) {
+                    const int wr_ = (idx * 4370) >> 16, wc = idx - wr_ * 15;
+                    win[wr_ * 16 + wc] = (uint16_t)v[u];
+                }
+            }
         }
         __syncwarp();
         for (int idx = lane; idx < 15 * 8; idx += 32) {
@@ -188,9 +201,13 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
             const int sxx = sx4 + wr.alpha * i2 + wr.beta * i1;
             const int offs = ((sxx + 512) >> 10) + 64;
             const uint16_t* w = win + (i1 + 7) * 16 + (i2 - 3 + 7);
+            // the eight taps of one filter phase are one 16-byte row of the table: a single vector load instead of eight
+            const uint4 fq = __ldg(reinterpret_cast<const uint4*>(d_warped_filter[offs]));
+            const int f[8] = {(int16_t)(fq.x & 0xffff), (int16_t)(fq.x >> 16), (int16_t)(fq.y & 0xffff), (int16_t)(fq.y >> 16),
+                              (int16_t)(fq.z & 0xffff), (int16_t)(fq.z >> 16), (int16_t)(fq.w & 0xffff), (int16_t)(fq.w >> 16)};
             int s = 0;
 #pragma unroll
-            for (int i3 = 0; i3 < 8; i3++) s += d_warped_filter[offs][i3] * (int)w[i3];
+            for (int i3 = 0; i3 < 8; i3++) s += f[i3] * (int)w[i3];
             wm[idx] = (s + 4) >> 3;
         }
         __syncwarp();
@@ -198,9 +215,12 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
             const int i1 = (idx >> 3) - 4, i2 = (idx & 7) - 4;
             const int syy = sy4 + wr.gamma * i2 + wr.delta * i1;
             const int offs = ((syy + 512) >> 10) + 64;
+            const uint4 fq = __ldg(reinterpret_cast<const uint4*>(d_warped_filter[offs]));
+            const int f[8] = {(int16_t)(fq.x & 0xffff), (int16_t)(fq.x >> 16), (int16_t)(fq.y & 0xffff), (int16_t)(fq.y >> 16),
+                              (int16_t)(fq.z & 0xffff), (int16_t)(fq.z >> 16), (int16_t)(fq.w & 0xffff), (int16_t)(fq.w >> 16)};
             int s = 0;
 #pragma unroll
-            for (int i3 = 0; i3 < 8; i3++) s += d_warped_filter[offs][i3] * wm[(i1 + i3 + 4) * 8 + i2 + 4];
+            for (int i3 = 0; i3 < 8; i3++) s += f[i3] * wm[(i1 + i3 + 4) * 8 + i2 + 4];
             out[(i8 * 8 + i1 + 4) * IT + j8 * 8 + i2 + 4] = (s + rnd) >> round1;
         }
         __syncwarp();

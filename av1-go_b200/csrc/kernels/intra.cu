@@ -555,11 +555,15 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // `stuck` (one int per frame) is raised instead of hanging if a wait makes no progress for seconds: a wrong work-list must
 // end in a digest mismatch, not in a wedged GPU.
 __device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parity, int* stuck) {
-    for (int spins = 0; spins < (1 << 22); spins++) {
+    for (int rounds = 0; rounds < 64; rounds++) {
         const bool pend = id >= 0 && !mbar_test(rbar + 8u * (uint32_t)id, parity);
         if (!__any_sync(0xffffffffu, pend)) return;
-        const int mx = __reduce_max_sync(0xffffffffu, pend ? id : -1);
-        mbar_try(rbar + 8u * (uint32_t)mx, parity);
+        // sleep on the youngest pending record (the one most likely to finish last); only the try_wait itself is re-issued while
+        // it times out, not the whole test / vote / reduce sequence
+        const uint32_t b = rbar + 8u * (uint32_t)__reduce_max_sync(0xffffffffu, pend ? id : -1);
+        int spins = 0;
+        while (!mbar_try(b, parity))
+            if (++spins > (1 << 22)) { *stuck = 1; return; }
     }
     *stuck = 1;
 }
