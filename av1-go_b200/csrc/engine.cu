@@ -487,7 +487,7 @@ struct EngineImpl {
     size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
     int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
     int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
-    int k3_progressive = 1;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive (default), 2 always cell-level
+    int k3_progressive = 2;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive, 2 always cell-level (default)
     int k3_intra_run = 0;                             // consecutive frames without inter prediction issued so far
     int64_t frames_decoded = 0;
 
@@ -611,10 +611,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         il.uprog = (unsigned long long*)s.sync.p;
         il.uflags = (int*)(s.sync.p + sizeof(unsigned long long) * (size_t)L.n_k3units);
         il.ticket = il.uflags + L.n_k3units;
-        // Latency vs throughput.  Cell-level hand-over gives a 1.6x lower frame latency; whole-unit hand-over keeps fewer CTAs resident
-        // and polling per frame and gives the higher clip rate when many independent frames run side by side.  So: cell-level for
-        // every frame later frames predict from (it is on its GOP's critical path) and whenever the GPU is not saturated (the frame
-        // issued 8 frames ago has already completed); whole-unit only inside a run of independent key frames with >= 8 in flight.
+        // Cell-level hand-over is the default: 1.6x lower frame latency and (since the wait loop got leaner) also the higher clip
+        // rate with 16+ frames side by side (c2: 3220 vs 2960 frames/s).  AV1R_K3_PROGRESSIVE=1 selects the earlier adaptive policy
+        // (whole-unit hand-over inside saturated runs of frames nothing predicts from), =0 whole-unit always.
         k3_intra_run = L.n_inter == 0 ? k3_intra_run + 1 : 0;
         bool saturated = false;
         {
