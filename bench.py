@@ -350,7 +350,7 @@ def run_c2(args, torch, dist, rank, world, local, name="c2"):
                             host_threads=max(1, (os.cpu_count() or 1) // world))
     vdec.verify_buffer(blob)                                                  # warm-up (allocations, first-touch)
     best = None
-    for _ in range(3):
+    for _ in range(5):   # wall-clock of a host-bound path on a shared box: best of 5
         t0 = time.perf_counter()
         rc, rep, digs = vdec.verify_buffer(blob)
         dt = time.perf_counter() - t0
