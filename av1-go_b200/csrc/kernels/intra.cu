@@ -844,11 +844,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                             const int d = __ldg(&up->dep[lane]);
                             if (d >= 0) {
                                 int spins = 0;
-                                unsigned ns = 40;
+                                // back-off 100 ns .. 0.8 us: a frame's chain crosses ~100 unit borders, so even the longest sleep adds a few
+                                // per cent to its latency, while the polls were a fifth of the kernel's issued instructions
+                                unsigned ns = 100;
                                 while ((ld_relaxed64(L.uprog + d) & want) != want) {
                                     __nanosleep(ns);
-                                    if (ns < 320) ns <<= 1;
-                                    if (++spins > (1 << 24)) { L.ticket[1] = 3; break; }
+                                    if (ns < 800) ns <<= 1;
+                                    if (++spins > (1 << 23)) { L.ticket[1] = 3; break; }
                                 }
                             }
                         }
