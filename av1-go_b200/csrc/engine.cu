@@ -409,6 +409,7 @@ struct FrameSlot {
     PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
     PinBuf planes_host;
     bool busy = false;
+    const int* k3_stuck_dev = nullptr;   // device word the intra kernel raises when one of its waits made no progress (watchdog)
     std::shared_ptr<void> host_arena;   // pinned staging the queued H2D copy reads from (returned to the pool when the slot is reused)
     // frame buffers touched by the work queued on this slot: kept alive (out of the recycling pool)
     // until the slot's completion event has been waited on
@@ -551,6 +552,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         res.base = (int16_t*)s.residual.p;
     }
     const TxRec* d_recs = (const TxRec*)(d_arena + L.recs);
+    s.k3_stuck_dev = nullptr;
     if (tm) tm->begin(st);
     CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, L.n_order_small, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, L.n_order > 0, st);
@@ -611,6 +613,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         il.uprog = (unsigned long long*)s.sync.p;
         il.uflags = (int*)(s.sync.p + sizeof(unsigned long long) * (size_t)L.n_k3units);
         il.ticket = il.uflags + L.n_k3units;
+        s.k3_stuck_dev = il.ticket + 1;
         // Cell-level hand-over is the default: 1.6x lower frame latency and (since the wait loop got leaner) also the higher clip
         // rate with 16+ frames side by side (c2: 3220 vs 2960 frames/s).  AV1R_K3_PROGRESSIVE=1 selects the earlier adaptive policy
         // (whole-unit hand-over inside saturated runs of frames nothing predicts from), =0 whole-unit always.
@@ -755,6 +758,8 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
         CK(launch_plane_checksum(shown->pl.p[p], shown->pl.pitch[p], fp.w[p], fp.h[p], fp.bd, (uint64_t*)s->cks_dev.p + p, st));
     if (tm) tm->end(AV1R_ST_DIGEST, np, st);
     CK(cudaMemcpyAsync(s->cks_host.p, s->cks_dev.p, 24, cudaMemcpyDeviceToHost, st));
+    memset(s->cks_host.p + 24, 0, 4);
+    if (s->k3_stuck_dev && !existing) CK(cudaMemcpyAsync(s->cks_host.p + 24, s->k3_stuck_dev, 4, cudaMemcpyDeviceToHost, st));
     Pending pd;
     memset(&pd.res, 0, sizeof(pd.res));
     pd.res.struct_size = sizeof(pd.res);
@@ -958,6 +963,14 @@ int EngineImpl::finish_pending(Pending& p) {
     cudaEventElapsedTime(&ms, s.ev0, s.ev1);
     p.res.device_ms = ms;
     memcpy(p.res.checksum, s.cks_host.p, 24);
+    {   // the intra kernel's watchdog fired: a wait on a work-list dependency never completed -- report it, do not trust the digest
+        int stuck = 0;
+        memcpy(&stuck, s.cks_host.p + 24, 4);
+        if (stuck) {
+            p.res.status = AV1R_EIO;
+            err = "intra kernel watchdog: a dependency wait made no progress (inconsistent work-list)";
+        }
+    }
     if (p.need_md5) {
         const int np = p.res.layout == 0 ? 1 : 3;
         for (int pl = 0; pl < np; pl++) {
@@ -1325,6 +1338,10 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
             int r = eng.collect(res.data(), (int)res.size(), &n);
             if (r) return r;
             for (int i = 0; i < n; i++) {
+                if (res[i].status) {   // a frame the device could not reconstruct consistently (intra kernel watchdog)
+                    out->first_bad_frame = shown;
+                    return res[i].status;
+                }
                 if (digests && shown < cap_frames) memcpy(digests + 3 * shown, res[i].checksum, 24);
                 shown++;
                 out->device_ms += res[i].device_ms;
