@@ -823,7 +823,6 @@ static void upscaled_params(const FrameHdr& fh, const DevFrameParams& fp, DevFra
 }
 
 static int prepare_work_seq(const SeqHdr& seq, const FrameWork& fw, DevWork& dw, std::string& err) {
-    if (fw.fh.using_qmatrix) { err = "quantiser matrices are not supported yet"; return AV1R_ENOSYS; }
     fill_params(seq, fw, dw.fp);
     upscaled_params(fw.fh, dw.fp, dw.fp_up);
     dw.fh = fw.fh;

@@ -15,6 +15,7 @@
 #include "devframe.h"
 #include "itx1d.h"
 #include "../tables/tables_quant.inc"
+#include "../tables/tables_qm.inc"
 
 namespace av1r {
 
@@ -22,6 +23,8 @@ __constant__ int16_t c_dc_q[3][256];
 __constant__ int16_t c_ac_q[3][256];
 __constant__ uint8_t c_txw_log2[TX_SIZES_ALL];
 __constant__ uint8_t c_txh_log2[TX_SIZES_ALL];
+__constant__ uint16_t c_qm_offset[TX_SIZES_ALL];
+__device__ uint8_t d_iqmatrix[15][2][3344];   // Quantizer_Matrix (spec 7.12.3), row-major per transform size; 100 KB, read through L1/L2
 static bool g_itx_const_loaded[64] = {false};
 
 static constexpr int ITX_WARPS = 4;
@@ -108,10 +111,13 @@ __global__ void __launch_bounds__(ITX_WARPS * 32) itx_kernel(const TxRec* __rest
         const int dq_denom = (pels > 256) + (pels > 1024);
         const int mx = (1 << (7 + bd)) - 1, mn = -(1 << (7 + bd));
         const uint32_t* tk = coefs + r.coef_off;
+        // quantiser matrix: 2-D transform types only, level 15 = flat
+        const uint8_t* qm = (r.qm_level < 15 && r.txtp < IDTX) ? d_iqmatrix[r.qm_level][plane > 0] + c_qm_offset[txsz] : nullptr;
         for (int k = lane; k < r.ntok; k += 32) {
             const uint32_t t = tk[k];
             const int pos = (int)(t & 1023), level = (int32_t)t >> 10;
-            const int q = pos == 0 ? dcq : acq;
+            int q = pos == 0 ? dcq : acq;
+            if (qm) q = (q * (int)__ldg(qm + pos) + 16) >> 5;
             uint32_t dq = ((uint32_t)abs(level) * (uint32_t)q) & 0xFFFFFFu;
             dq >>= dq_denom;
             int v = level < 0 ? -(int)dq : (int)dq;
@@ -199,10 +205,12 @@ __global__ void __launch_bounds__(ITXS_HALF_WARPS * 16) itx_small_kernel(const T
         const int acq = c_ac_q[bdi][min(max(r.qidx + fp.dq_ac[plane], 0), 255)];
         const int mx = (1 << (7 + bd)) - 1, mn = -(1 << (7 + bd));
         const uint32_t* tk = coefs + r.coef_off;
+        const uint8_t* qm = (r.qm_level < 15 && r.txtp < IDTX) ? d_iqmatrix[r.qm_level][plane > 0] + c_qm_offset[txsz] : nullptr;
         for (int k = lane; k < r.ntok; k += 16) {
             const uint32_t t = tk[k];
             const int pos = (int)(t & 1023), level = (int32_t)t >> 10;
-            const int q = pos == 0 ? dcq : acq;
+            int q = pos == 0 ? dcq : acq;
+            if (qm) q = (q * (int)__ldg(qm + pos) + 16) >> 5;
             const uint32_t dq = ((uint32_t)abs(level) * (uint32_t)q) & 0xFFFFFFu;   // dqDenom is 1 up to 256 samples
             int v = level < 0 ? -(int)dq : (int)dq;
             v = min(max(v, mn), mx);
@@ -269,6 +277,10 @@ cudaError_t itx_upload_constants() {
     e = cudaMemcpyToSymbol(c_txw_log2, kTxWLog2, sizeof(kTxWLog2));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_txh_log2, kTxHLog2, sizeof(kTxHLog2));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_qm_offset, av1t_qm_offset, sizeof(av1t_qm_offset));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(d_iqmatrix, av1t_iqmatrix, sizeof(av1t_iqmatrix));
     if (e != cudaSuccess) return e;
     if (dev < 64) g_itx_const_loaded[dev] = true;
     return cudaSuccess;

@@ -16,6 +16,7 @@
 
 #include "../av1-go_b200/csrc/tables/tables_pred.inc"
 #include "../av1-go_b200/csrc/tables/tables_quant.inc"
+#include "../av1-go_b200/csrc/tables/tables_qm.inc"
 
 extern "C" void orc_inverse_transform_2d(const int32_t* coef, int txsz, int txtp, int bd, int32_t* res);
 
@@ -311,10 +312,13 @@ static void dequant_block(const FrameWork& fw, const FrameGeom& g, const TxRec& 
     const int pels = w * h;
     const int dq_denom = (pels > 256) + (pels > 1024);
     const int mx = (1 << (7 + g.bd)) - 1, mn = -(1 << (7 + g.bd));
+    // quantiser matrix (spec 7.12.3): 2-D transform types only, level 15 = flat
+    const uint8_t* qm = (r.qm_level < 15 && r.txtp < IDTX) ? av1t_iqmatrix[r.qm_level][r.plane > 0] + av1t_qm_offset[r.txsz] : nullptr;
     for (int k = 0; k < r.ntok; k++) {
         uint32_t t = fw.coefs[r.coef_off + k];
         int pos = coef_token_pos(t), level = coef_token_level(t);
         int q = pos == 0 ? dcq : acq;
+        if (qm) q = (q * qm[pos] + 16) >> 5;
         int64_t dq = (int64_t)abs(level) * q;
         dq &= 0xFFFFFF;
         dq >>= dq_denom;
