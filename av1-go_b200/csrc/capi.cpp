@@ -28,6 +28,7 @@ extern "C" void av1r_default_config(av1r_config* cfg) {
 #include <thread>
 
 #include "demux.h"
+#include "k3_plan.h"
 #include "parallel.h"
 #include "stream_parser.h"
 
@@ -102,4 +103,56 @@ extern "C" int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threa
     snprintf(out->message, sizeof(out->message), "parse only: %lld frames, %d GOP segments, %d segment threads, tile threads %s", (long long)out->frames, nseg,
              nthreads, tile_threads ? "on" : "off");
     return rc_all;
+}
+
+// Debug / test entry point (host only, no GPU): parses every frame of a container, builds the intra kernel's plan (K3 order, unit
+// table, neighbour dependencies -- k3_plan.h) and checks the invariants the kernel's freedom from deadlock rests on.
+// Returns 0 and the number of frames / units checked, or AV1R_EINVAL with the first violation in msg.
+extern "C" int av1r_debug_k3_check(const uint8_t* data, size_t len, long long* frames, long long* units_total, char* msg, size_t cap) {
+    using namespace av1r;
+    if (!data || !msg || cap == 0) return AV1R_EINVAL;
+    msg[0] = 0;
+    DemuxResult dm;
+    std::string derr;
+    if (!demux_buffer(data, len, dm, derr)) {
+        snprintf(msg, cap, "%s", derr.c_str());
+        return AV1R_EBITSTREAM;
+    }
+    StreamParser sp;
+    if (!dm.config_obus.empty()) {
+        std::vector<ObuUnit> obus;
+        if (sp.hp.split_obus(dm.config_obus.data(), dm.config_obus.size(), obus))
+            for (auto& u : obus)
+                if (u.type == OBU_SEQUENCE_HEADER) sp.hp.parse_sequence_header(u.data, u.size);
+    }
+    long long nf = 0, nu_total = 0;
+    for (const TemporalUnit& tu : dm.tus) {
+        std::vector<ParsedFrame> pfs;
+        const int rc = sp.parse_tu(data + tu.offset, tu.size, tu.pts, pfs);
+        if (rc) {
+            snprintf(msg, cap, "%s", sp.err.c_str());
+            return rc;
+        }
+        for (ParsedFrame& pf : pfs) {
+            if (!pf.fw) continue;
+            const FrameWork& fw = *pf.fw;
+            const int n_recs = (int)fw.tx.size();
+            int n_k3 = 0;
+            for (const TxRec& r : fw.tx) n_k3 += k3_owns(r);
+            std::vector<TxRec> recs(fw.tx);
+            std::vector<uint32_t> k3((size_t)std::max(1, n_k3));
+            std::vector<K3Unit> units((size_t)((fw.mi_cols + 15) >> 4) * ((fw.mi_rows + 15) >> 4) + 1);
+            const int nu = k3_plan_build(fw.tx.data(), n_recs, n_k3, fw.subx, fw.suby, fw.sb128, fw.mi_cols, fw.mi_rows, recs.data(), k3.data(), units.data());
+            const std::string bad = k3_plan_check(fw.tx.data(), n_recs, n_k3, fw.subx, fw.suby, fw.mi_cols, fw.mi_rows, recs.data(), k3.data(), units.data(), nu);
+            if (!bad.empty()) {
+                snprintf(msg, cap, "frame %lld: %s", nf, bad.c_str());
+                return AV1R_EINVAL;
+            }
+            nf++;
+            nu_total += nu;
+        }
+    }
+    if (frames) *frames = nf;
+    if (units_total) *units_total = nu_total;
+    return 0;
 }

@@ -24,6 +24,7 @@
 #include "engine.h"
 #include "kernels/inter.h"
 #include "kernels/intra.h"
+#include "k3_plan.h"
 #include "md5.h"
 #include "parallel.h"
 #include "stream_parser.h"
@@ -257,108 +258,9 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
     if (L.n_warps) memcpy(h + L.warps, fw.warps.data(), sizeof(WarpRec) * L.n_warps);
     if (!fw.pal.empty()) memcpy(h + L.pal, fw.pal.data(), fw.pal.size());
-    {   // K3 order: records grouped by 64x64 luma unit, units in wavefront order.  Unit key = 4 * (sbx + 2 * sby) + seq with
-        // (sbx, sby) the superblock and seq the unit's rank in decode order inside its superblock (0 for 64x64 superblocks; a
-        // 128x128 superblock visits its four units in Z order, or 0,2,1,3 under a vertical split).  Every sample a record may
-        // read lies earlier in its own unit or in a unit with a smaller key: left superblock = base - 4 (this covers the
-        // below-left samples taken from the left neighbour's bottom half), above-right = base - 4, above = base - 8.  The intra
-        // kernel hands units to CTAs in table order and waits only for lower table indices, so it cannot deadlock.
-        uint32_t* k3 = (uint32_t*)(h + L.k3order);
-        TxRec* recs = (TxRec*)(h + L.recs);
-        K3Unit* units = (K3Unit*)(h + L.k3units);
-        const int sx1 = dw.fp.subx, sy1 = dw.fp.suby;
-        const int sbs = dw.fp.sb128 ? 1 : 0;
-        const int UX = (dw.fp.mi_cols + 15) >> 4, UY = (dw.fp.mi_rows + 15) >> 4;
-        auto unit_of = [&](const TxRec& r) -> int {
-            const int sx = r.plane ? sx1 : 0, sy = r.plane ? sy1 : 0;
-            const int ux = ((r.x4 * 4) << sx) >> 6, uy = ((r.y4 * 4) << sy) >> 6;
-            return std::min(uy, UY - 1) * UX + std::min(ux, UX - 1);
-        };
-        auto in_k3 = [](const TxRec& r) { return r.mode != TXM_INTER || (r.flags & TXF_II); };
-        std::vector<int32_t> ukey((size_t)UX * UY, -1), upos((size_t)UX * UY, -1);
-        std::vector<uint32_t> cnt(4096 + 1, 0);
-        int last_sb = -1, seq = 0;
-        for (int i = 0; i < L.n_recs; i++) {   // decode order: first appearance of a unit fixes its rank inside the superblock
-            const TxRec& r = fw.tx[i];
-            if (!in_k3(r)) continue;
-            const int un = unit_of(r);
-            if (ukey[un] < 0) {
-                const int ux = un % UX, uy = un / UX;
-                const int sb = (uy >> sbs) * UX + (ux >> sbs);
-                seq = sb == last_sb ? std::min(seq + 1, 3) : 0;
-                last_sb = sb;
-                ukey[un] = std::min(4095, 4 * ((ux >> sbs) + 2 * (uy >> sbs)) + seq);
-            }
-            cnt[ukey[un]]++;
-        }
-        uint32_t acc = 0;
-        for (auto& c : cnt) { const uint32_t t = c; c = acc; acc += t; }
-        for (int i = 0; i < L.n_recs; i++) {
-            const TxRec& r = fw.tx[i];
-            if (in_k3(r)) k3[cnt[ukey[unit_of(r)]]++] = (uint32_t)i;
-        }
-        // unit table: runs of equal unit in K3 order
-        int nu = 0;
-        for (int n = 0; n < L.n_k3; n++) {
-            const int un = unit_of(recs[k3[n]]);
-            if (nu == 0 || upos[un] != nu - 1) {
-                K3Unit& u = units[nu];
-                u.first = (uint32_t)n;
-                u.count = 0;
-                u.ux = (uint16_t)(un % UX);
-                u.uy = (uint16_t)(un / UX);
-                upos[un] = nu++;
-            }
-            units[nu - 1].count++;
-        }
-        // which neighbour units a unit really reads: a record on the unit's top row with an available row above reads the unit
-        // above (and above-left / above-right when it touches those corners), one on the left column reads the unit to the left
-        // (and below-left when the block reaches the unit's bottom).  In intra frames every neighbour is needed; in inter frames
-        // the few units that hold intra / inter-intra blocks would otherwise chain up for no reason.
-        std::vector<uint8_t> need((size_t)nu, 0);
-        for (int k = 0; k < nu; k++) {
-            const K3Unit& u = units[k];
-            uint8_t nd = 0;
-            for (uint32_t n = u.first; n < u.first + u.count; n++) {
-                const TxRec& r = recs[k3[n]];
-                if (r.mode == TXM_INTER || r.mode == TXM_PALETTE) continue;
-                const int sh = r.plane ? 3 : 4;                       // unit size in 4-sample cells: 16 luma, 8 chroma (4:2:0)
-                const int lx = r.x4 - (u.ux << sh), ly = r.y4 - (u.uy << sh);
-                const int w4 = kTxW[r.txsz] >> 2, h4 = kTxH[r.txsz] >> 2, uw = 1 << sh;
-                const bool top = ly == 0 && (r.flags & TXF_HAVE_ABOVE), lft = lx == 0 && (r.flags & TXF_HAVE_LEFT);
-                if (lft) nd |= 1;
-                if (lft && (r.flags & TXF_HAVE_BELOW_LEFT) && ly + 2 * h4 > uw) nd |= 2;
-                if ((top && lx == 0) || (lft && ly == 0)) nd |= 4;
-                if (top) nd |= 8;
-                if (top && (r.flags & TXF_HAVE_ABOVE_RIGHT) && lx + 2 * w4 > uw) nd |= 16;
-            }
-            need[k] = nd;
-        }
-        for (int k = 0; k < nu; k++) {
-            K3Unit& u = units[k];
-            static const int dxy[5][2] = {{-1, 0}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};   // left, below-left, above-left, above, above-right
-            for (int d = 0; d < 5; d++) {
-                const int nx = u.ux + dxy[d][0], ny = u.uy + dxy[d][1];
-                int dep = -1;
-                if (((need[k] >> d) & 1) && nx >= 0 && ny >= 0 && nx < UX && ny < UY) {
-                    const int pos = upos[(size_t)ny * UX + nx];
-                    if (pos >= 0 && pos < k) dep = pos;
-                }
-                u.dep[d] = dep;
-            }
-        }
-        dw.lay.n_k3units = nu;
-        for (int k = 0; k < nu; k++)
-            if (units[k].count > (uint32_t)K3_UNIT_MAX_RECS) dw.lay.n_k3units = -1;   // cannot happen at 4:2:0 (<= 576 records per unit)
-        // explicit dependency of inter-intra residual records on their blend record (position in K3 order)
-        uint32_t blend_pos[3] = {0, 0, 0};
-        for (int n = 0; n < L.n_k3; n++) {
-            TxRec& r = recs[k3[n]];
-            if (!(r.flags & TXF_II)) continue;
-            if (r.mode != TXM_INTER) blend_pos[r.plane] = (uint32_t)n;
-            else r.pal_off = blend_pos[r.plane];
-        }
-    }
+    // K3 plan (k3_plan.h): record order, unit table with neighbour dependencies, inter-intra blend links
+    dw.lay.n_k3units = k3_plan_build(fw.tx.data(), L.n_recs, L.n_k3, dw.fp.subx, dw.fp.suby, dw.fp.sb128, dw.fp.mi_cols, dw.fp.mi_rows,
+                                     (TxRec*)(h + L.recs), (uint32_t*)(h + L.k3order), (K3Unit*)(h + L.k3units));
 }
 
 // Pinned staging of one frame's work-lists, filled by the thread that parsed the frame (so the copy into pinned memory and the K3

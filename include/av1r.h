@@ -121,6 +121,9 @@ int av1r_ctx_verify_buffer(av1r_ctx* ctx, const uint8_t* data, size_t len, av1r_
  * tiles of a frame on the process-wide worker pool when tile_threads != 0.  Fills frames, host_parse_ms (summed over frames),
  * wall_ms and frames_per_sec: the "sequential parse, timed and reported separately" of the hot path. */
 int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threads, int tile_threads, av1r_report* out);
+/* Host-only check of the intra kernel's plan (record order, 64x64 unit table, neighbour dependencies) for every frame of a
+ * container: 0 or AV1R_EINVAL with the first violated invariant in msg.  Test / diagnosis entry point; touches no GPU. */
+int av1r_debug_k3_check(const uint8_t* data, size_t len, long long* frames, long long* units_total, char* msg, size_t cap);
 int av1r_probe_file(const char* path, av1r_stream_info* out);
 int av1r_probe_buffer(const uint8_t* data, size_t len, av1r_stream_info* out);
 
