@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         }
         // inter frame: the unit's own inter-predicted samples (final since K2 ran: fetched before the neighbour wait, off the chain)
         if (L.load_tile) {
-            for (int p = 0; p < 3; p++) {
+            for (int p = 0; p < (fp.mono ? 1 : 3); p++) {
                 const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
                 const int x0 = ux * W, y0 = uy * W;
                 const uint8_t* fb = L.frame.p[p];
@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         __syncthreads();
         lap(5, tid == 0);   // dataflow (CTA view)
         // ---- write the unit back (coalesced 32-bit words; coded plane widths are multiples of 4 samples)
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < (fp.mono ? 1 : 3); p++) {
             const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
             const int x0 = ux * W, y0 = uy * W;
             const int vw = min(W, fp.cw[p] - x0), vh = min(W, fp.ch[p] - y0);
@@ -1008,7 +1008,7 @@ static cudaError_t intra_upload_constants() {
 
 cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s) {
     if (L.n_units <= 0) return cudaSuccess;
-    if (L.fp.subx != 1 || L.fp.suby != 1 || L.fp.mono) return cudaErrorInvalidValue;   // the canvas geometry is 4:2:0
+    if (!L.fp.mono && (L.fp.subx != 1 || L.fp.suby != 1)) return cudaErrorInvalidValue;   // the canvas geometry is 4:2:0 (or luma only)
     cudaError_t e = intra_upload_constants();
     if (e != cudaSuccess) return e;
     {

@@ -136,7 +136,6 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
         }
     cur_->warps.resize(8);
     memset(cur_->warps.data(), 0, sizeof(WarpRec) * 8);
-    if (hp.seq.mono_chrome) return fail(AV1R_ENOSYS, "monochrome streams are not supported yet");
     // super-resolution: intra frames are reconstructed at the coded (downscaled) width and upscaled before loop restoration (K6);
     // an inter frame coded with superres predicts from references of a different width (scaled motion compensation, not built)
     if (!fh.frame_is_intra) {

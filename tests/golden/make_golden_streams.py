@@ -29,6 +29,8 @@ CASES = {
     "intra_8b_superres_lr_328x200": ("panzoom", 328, 200, 8, 3, {"cpu-used": "4", "cq-level": "30", "enable-restoration": "1"}, {14: 0, 48: 0, 19: 1, 20: 12, 21: 12}),
     "intra_10b_superres16_264x136": ("panzoom", 264, 136, 10, 2, {"cpu-used": "5", "cq-level": "40", "enable-restoration": "0"}, {14: 0, 48: 0, 19: 1, 20: 16, 21: 16}),
     # quantiser matrices (K1): per-frame qm levels between qm-min and qm-max
+    # monochrome (cfg[52] = monochrome): luma only, one MD5 per frame
+    "intra_8b_mono_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 0, 52: 1}),
     "intra_8b_qm_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30", "enable-qm": "1", "qm-min": "2", "qm-max": "10"}, {14: 0, 48: 0}),
 }
 
@@ -45,6 +47,7 @@ INTER_CASES = {
     "inter_10b_grain_208x144": ("noise", 208, 144, 10, 8, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "3"}, {14: 6, 48: 9999}),
     # key frame coded at 8/11 of the width and upscaled; the inter frames (full width) predict from the upscaled reference
     "inter_8b_kfsuperres_320x192": ("panzoom", 320, 192, 8, 6, {"cpu-used": "5", "cq-level": "32"}, {14: 0, 48: 9999, 19: 1, 20: 8, 21: 11}),
+    "inter_10b_mono_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36"}, {14: 4, 48: 9999, 52: 1}),
     "inter_10b_qm_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36", "enable-qm": "1", "qm-min": "0", "qm-max": "15"}, {14: 4, 48: 9999}),
 }
 
@@ -74,7 +77,7 @@ def build(cases, index_name, only=None):
         assert len(ref) == len(aom) == n
         md5 = []
         for i in range(n):
-            for p in range(3):
+            for p in range(len(ref[i][4])):   # one plane for monochrome
                 assert np.array_equal(ref[i][4][p], aom[i][p]), "dav1d and libaom disagree"
             md5.append(dav1d_ref.plane_md5(ref[i][4]))
         obuio.write_ivf(os.path.join(OUT, name + ".ivf"), tus, w, h)

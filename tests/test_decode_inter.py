@@ -30,7 +30,7 @@ def test_oracle_matches_golden_md5(built, name):
     frames, _ = oracle_lib.decode_stream(_tus(name))
     assert len(frames) == meta["frames"]
     for i, planes in enumerate(frames):
-        assert _md5(planes, meta["bpc"]) == meta["md5"][i], f"{name} frame {i}"
+        assert _md5(planes, meta["bpc"])[:len(meta["md5"][i])] == meta["md5"][i], f"{name} frame {i}"
 
 
 def test_golden_streams_exercise_the_inter_tools(built):
@@ -76,7 +76,7 @@ def test_cuda_matches_golden_md5(built, name):
     assert len(dec.results) == meta["frames"], dec.error()
     for i, r in enumerate(dec.results):
         assert r.status == 0 and r.w == meta["w"] and r.h == meta["h"] and r.bpc == meta["bpc"]
-        got = [bytes(r.md5[p]).hex() for p in range(3)]
+        got = [bytes(r.md5[p]).hex() for p in range(len(meta["md5"][i]))]
         if got != meta["md5"][i]:
             from oracle import oracle_lib
             ref, _ = oracle_lib.decode_stream(_tus(name))
