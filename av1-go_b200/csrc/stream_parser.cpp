@@ -136,6 +136,10 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
         }
     cur_->warps.resize(8);
     memset(cur_->warps.data(), 0, sizeof(WarpRec) * 8);
+    // chroma formats / bit depths the device path is not built for are refused up front (soft outcome for the caller)
+    if (!hp.seq.mono_chrome && !(hp.seq.subsampling_x == 1 && hp.seq.subsampling_y == 1))
+        return fail(AV1R_ENOSYS, "4:4:4 / 4:2:2 streams are not supported yet");
+    if (hp.seq.bit_depth > 10) return fail(AV1R_ENOSYS, "12-bit streams are not supported yet");
     // super-resolution: intra frames are reconstructed at the coded (downscaled) width and upscaled before loop restoration (K6);
     // an inter frame coded with superres predicts from references of a different width (scaled motion compensation, not built)
     if (!fh.frame_is_intra) {
