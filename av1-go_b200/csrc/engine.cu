@@ -391,6 +391,7 @@ struct EngineImpl {
     int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
     int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
     int k3_progressive = 2;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive, 2 always cell-level (default)
+    int k3_inter_mult = 6;                            // inter frames: CTAs = this x the unit wavefront (AV1R_K3_INTER_MULT)
     int k3_intra_run = 0;                             // consecutive frames without inter prediction issued so far
     int64_t frames_decoded = 0;
 
@@ -504,7 +505,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             const int UX = (fp.mi_cols + 15) >> 4, UY = (fp.mi_rows + 15) >> 4;
             il.ctas = k3_ctas > 0 ? k3_ctas : std::min(UY, (UX + 1) / 2) + 2;
             // inter frames: the few units that hold intra / inter-intra blocks are mostly independent of each other -> one round
-            if (k3_ctas <= 0 && L.n_inter > 0) il.ctas = std::min(L.n_k3units, 6 * il.ctas);
+            if (k3_ctas <= 0 && L.n_inter > 0) il.ctas = std::min(L.n_k3units, k3_inter_mult * il.ctas);
         }
         il.warps = k3_warps;
         il.load_tile = L.n_inter > 0;
@@ -946,6 +947,7 @@ int Engine::open(const av1r_config& cfg) {
         E.slots.push_back(std::move(s));
     }
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));
+    if (const char* e = getenv("AV1R_K3_INTER_MULT")) E.k3_inter_mult = std::max(1, atoi(e));
     if (const char* e = getenv("AV1R_K3_PROGRESSIVE")) E.k3_progressive = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("AV1R_K3_WARPS")) E.k3_warps = std::min(8, std::max(1, atoi(e)));
     if (getenv("AV1R_K3_PROF")) {
