@@ -31,14 +31,6 @@ HeaderParser::HeaderParser() {
     default_gm(prev_gm_params);
 }
 
-int HeaderParser::get_relative_dist(int a, int b) const {
-    if (!seq.enable_order_hint) return 0;
-    int diff = a - b;
-    int m = 1 << (seq.order_hint_bits - 1);
-    diff = (diff & (m - 1)) - (diff & m);
-    return diff;
-}
-
 bool HeaderParser::split_obus(const uint8_t* data, size_t len, std::vector<ObuUnit>& out) {
     size_t pos = 0;
     while (pos < len) {

@@ -48,7 +48,12 @@ public:
     bool parse_tile_group_header(BitReader& br, const FrameHdr& fh, TileGroupInfo& tg);
     // spec 7.20: store header-level state of the just-decoded frame into refreshed slots.
     void reference_update(const FrameHdr& fh);
-    int get_relative_dist(int a, int b) const;
+    // spec 7.9.3 get_relative_dist (inline: the tile parser calls it for every temporal / reference MV candidate)
+    int get_relative_dist(int a, int b) const {
+        if (!seq.enable_order_hint) return 0;
+        const int diff = a - b, m = 1 << (seq.order_hint_bits - 1);
+        return (diff & (m - 1)) - (diff & m);
+    }
 
 private:
     bool fail(const char* msg) { error = msg; return false; }

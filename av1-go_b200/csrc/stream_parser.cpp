@@ -185,21 +185,28 @@ void StreamParser::motion_field_estimation() {
             sfw->saved_mvs.empty())
             return 0;
         const int ref_to_cur = hp.get_relative_dist(fh.order_hints[src], fh.order_hint);
+        // per reference of the source frame: offset, validity and the projection factor num * Div_Mult[den] (spec 7.9.3)
+        int roff[8];
+        int64_t rfac[8];
+        bool rok[8];
+        for (int rf = 0; rf < 8; rf++) {
+            roff[rf] = rf > INTRA_FRAME ? hp.get_relative_dist(fh.order_hints[src], r.saved_order_hints[rf]) : 0;
+            rok[rf] = rf > INTRA_FRAME && std::abs(ref_to_cur) <= 31 && std::abs(roff[rf]) <= 31 && roff[rf] > 0;
+            rfac[rf] = rok[rf] ? (int64_t)std::max(-31, std::min(31, ref_to_cur * dst_sign)) * kDivMult[std::min(31, roff[rf])] : 0;
+        }
         // a projected position never leaves the 8-row band of its source (MAX_OFFSET_HEIGHT = 0): bands are independent and each
         // is walked in raster order, so "the later source wins" stays deterministic
         WorkerPool::get().parallel_for((h8 + 7) >> 3, [&](int band) {
         for (int row8 = band * 8; row8 < std::min(h8, band * 8 + 8); row8++)
             for (int col8 = 0; col8 < w8; col8++) {
                 const SavedMv& sm = sfw->saved_mvs[(size_t)row8 * w8 + col8];
-                if (sm.ref <= INTRA_FRAME) continue;
-                const int ref_offset = hp.get_relative_dist(fh.order_hints[src], r.saved_order_hints[sm.ref]);
-                if (!(std::abs(ref_to_cur) <= 31 && std::abs(ref_offset) <= 31 && ref_offset > 0)) continue;
-                const int num = std::max(-31, std::min(31, ref_to_cur * dst_sign));
-                const int den = std::min(31, ref_offset);
+                if (sm.ref <= INTRA_FRAME || !rok[sm.ref]) continue;
+                const int ref_offset = roff[sm.ref];
+                const int64_t fac = rfac[sm.ref];
                 int proj[2];
                 const int mvc[2] = {sm.mv.row, sm.mv.col};
                 for (int i = 0; i < 2; i++) {
-                    const int64_t v = (int64_t)mvc[i] * num * kDivMult[den];
+                    const int64_t v = (int64_t)mvc[i] * fac;
                     const int64_t sc = v >= 0 ? (v + 8192) >> 14 : -((-v + 8192) >> 14);
                     proj[i] = (int)std::max<int64_t>(-(1 << 14) + 1, std::min<int64_t>((1 << 14) - 1, sc));
                 }
