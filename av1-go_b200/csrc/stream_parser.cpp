@@ -111,6 +111,10 @@ StreamParser::StreamParser() {
 int StreamParser::begin_frame(const FrameHdr& fh) {
     auto tb = std::chrono::steady_clock::now();
     struct Fin { std::chrono::steady_clock::time_point t; ~Fin() { g_prof[4] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } fin{tb};
+    // AV1 level 6.3 caps a picture at 16384 x 8704 and 35,651,584 samples: anything beyond is a corrupt header, not a frame to allocate
+    if (fh.upscaled_width > 16384 || fh.frame_height > 8704 || (int64_t)fh.upscaled_width * fh.frame_height > 35651584 || fh.frame_width < 1 ||
+        fh.frame_height < 1)
+        return fail(AV1R_EBITSTREAM, "frame size outside the AV1 level limits");
     cur_ = acquire_framework();
     cur_->init(hp.seq, fh);
     cur_fh_ = fh;
