@@ -458,7 +458,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     s.k3_stuck_dev = nullptr;
     if (tm) tm->begin(st);
     CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, L.n_order_small, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
-    if (tm) tm->end(AV1R_ST_ITX, L.n_order > 0, st);
+    if (tm) tm->end(AV1R_ST_ITX, (L.n_order_small > 0) + (L.n_order > L.n_order_small), st);
     if (L.n_inter > 0) {
         InterLaunch xl;
         xl.blks = (const InterBlk*)(d_arena + L.inter);
