@@ -295,3 +295,63 @@ def verify_buffer(data, device=0, host_threads=0, apply_grain=1, inloop_filters=
     rc = l.av1r_verify_buffer(data, len(data), C.byref(cfg), C.byref(rep), dig, max_frames if want_digests else 0)
     digs = [tuple(dig[3 * i:3 * i + 3]) for i in range(int(rep.frames))] if want_digests else []
     return rc, rep, digs
+
+
+# ---- mirror of the Go surface the daemon would use (av1-go_b200/go/internal/av1recon/av1recon.go) --------------
+# Same names, argument meaning and error behaviour as the cgo package: Open(device) -> Engine, Engine.VerifyFile(path) -> Report or
+# VerifyError with the text that would land in job.Reason, Engine.Close(); ProbeFile / VerifyOutput follow
+# /root/reference/internal/metadata/probe.go:125 and the VerifyOutput helper of INTEGRATION.md section 3.
+class VerifyError(RuntimeError):
+    def __init__(self, code, message, report=None):
+        super().__init__(f"av1 verify failed (code {code}): {message}")
+        self.code = code
+        self.report = report
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._dec = Decoder(device=device, streams=16, frames_in_flight=32)
+
+    def VerifyFile(self, path):
+        """Decodes every frame of an AV1 file (Matroska / IVF / raw OBU) on the GPU -> Report; raises VerifyError on failure."""
+        try:
+            data = open(path, "rb").read()
+        except OSError as e:
+            raise VerifyError(-5, f"failed to read {path}: {e}")
+        rc, rep, _ = self._dec.verify_buffer(data, want_digests=False)
+        if rc != 0:
+            raise VerifyError(rc, rep.message.decode(errors="replace"), rep)
+        return rep
+
+    def Close(self):
+        self._dec.close()
+
+
+def Open(device=0):
+    """av1recon.Open: one engine = one GPU.  Raises RuntimeError when no CUDA device is present (the daemon then skips verification,
+    like it tolerates a failed QSV self-test: /root/reference/cmd/av1d/main.go:41-52)."""
+    return Engine(device)
+
+
+def ProbeFile(path):
+    """Width / Height / BitDepth / is-AV1 of a file from its sequence header (metadata.ProbeFile without the ffprobe child)."""
+    info = StreamInfo()
+    info.struct_size = C.sizeof(StreamInfo)
+    l = lib()
+    l.av1r_probe_file.argtypes = [C.c_char_p, C.POINTER(StreamInfo)]
+    rc = l.av1r_probe_file(os.fsencode(path), C.byref(info))
+    if rc:
+        raise RuntimeError(f"av1r_probe_file({path}) -> {rc}")
+    return info
+
+
+def VerifyOutput(eng, output_path, src_width, src_height):
+    """ffmpeg.VerifyOutput of INTEGRATION.md: decode the transcoded file and check it against what the probe said about the source
+    (odd dimensions are rounded up to even by the transcode: /root/reference/internal/ffmpeg/transcode.go:98,107)."""
+    rep = eng.VerifyFile(output_path)
+    want_w, want_h = (src_width + 1) // 2 * 2, (src_height + 1) // 2 * 2
+    if (rep.width, rep.height) != (want_w, want_h):
+        raise VerifyError(-22, f"decoded size {rep.width}x{rep.height} does not match source {src_width}x{src_height}", rep)
+    if rep.frames == 0:
+        raise VerifyError(-22, "no frames decoded", rep)
+    return rep
