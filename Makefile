@@ -39,7 +39,15 @@ oracle/_build/liboracle.so: $(ORACLE_C) $(ORACLE_CPP) $(PARSER_OBJS) $(wildcard 
 	$(CC) -O2 -g -fPIC -c oracle/filmgrain.c -o oracle/_build/filmgrain.o
 	$(CXX) -O2 -g -std=c++17 -fPIC -shared -Iinclude $(ORACLE_CPP) oracle/_build/filmgrain.o $(PARSER_OBJS) -o $@ -ldl
 
+# sanitizer build of the host half (demux + parser + C entry points that need no GPU), driven by tests/test_robustness.py
+ASAN_CXX ?= /usr/bin/g++
+ASAN_SRCS := $(HOST_SRCS) tests/native/parse_fuzz_main.cpp
+build/asan/parse_fuzz: $(ASAN_SRCS) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p build/asan
+	$(ASAN_CXX) -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize=shift-base -fno-sanitize-recover=undefined -fno-omit-frame-pointer -Iinclude -I/usr/local/cuda/include $(ASAN_SRCS) -o $@ -lpthread
+
 clean:
 	rm -rf build $(LIBDIR) oracle/_build
 
-.PHONY: all clean
+.PHONY: all clean asan
+asan: build/asan/parse_fuzz

@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "../../include/av1r.h"
+#include "../../include/av1r_stages.h"
 
 extern "C" uint32_t av1r_abi_version(void) { return AV1R_ABI_VERSION; }
 
@@ -103,6 +104,59 @@ extern "C" int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threa
     snprintf(out->message, sizeof(out->message), "parse only: %lld frames, %d GOP segments, %d segment threads, tile threads %s", (long long)out->frames, nseg,
              nthreads, tile_threads ? "on" : "off");
     return rc_all;
+}
+
+// Host-only clip statistics (no GPU): the counts the roofline model and the bench's "does this clip really contain its config's
+// tools" gate are computed from -- same fields av1r_clip_load fills, minus the device-side ones (worklist_bytes stays 0).
+extern "C" int av1r_parse_stats(const uint8_t* data, size_t len, av1r_clip_info* out) {
+    using namespace av1r;
+    if (!data || !out) return AV1R_EINVAL;
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    DemuxResult dm;
+    std::string derr;
+    if (!demux_buffer(data, len, dm, derr)) return AV1R_EBITSTREAM;
+    StreamParser sp;
+    if (!dm.config_obus.empty()) {
+        std::vector<ObuUnit> obus;
+        if (sp.hp.split_obus(dm.config_obus.data(), dm.config_obus.size(), obus))
+            for (auto& u : obus)
+                if (u.type == OBU_SEQUENCE_HEADER) sp.hp.parse_sequence_header(u.data, u.size);
+    }
+    for (const TemporalUnit& tu : dm.tus) {
+        std::vector<ParsedFrame> pfs;
+        const int rc = sp.parse_tu(data + tu.offset, tu.size, tu.pts, pfs);
+        if (rc) return rc;
+        for (ParsedFrame& pf : pfs) {
+            if (pf.show_existing_slot >= 0) { out->frames_shown++; continue; }
+            const FrameWork& fw = *pf.fw;
+            out->frames_decoded++;
+            out->frames_shown += fw.fh.show_frame;
+            out->host_parse_ms += fw.parse_ms;
+            out->coded_samples += fw.coded_samples;
+            out->coef_tokens += fw.coefs.size();
+            out->tx_blocks += fw.tx.size();
+            out->inter_samples += fw.inter_samples;
+            out->inter_ref_samples += fw.inter_ref_samples;
+            out->inter_blocks += fw.inter.size();
+            out->obmc_neighbours += fw.obmc.size();
+            out->lr_frames += fw.fh.uses_lr != 0;
+            out->cdef_frames += fw.fh.enable_cdef_frame != 0;
+            out->deblock_frames += (fw.fh.lf.level[0] || fw.fh.lf.level[1]);
+            out->grain_frames += fw.fh.show_frame && fw.fh.fg.apply_grain;
+            for (int i = 0; i < 24; i++) out->tool_hist[i] += fw.tool_hist[i];
+            for (const TxRec& r : fw.tx)
+                if (r.mode != TXM_INTER) out->intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+            out->width = fw.fh.upscaled_width;
+            out->height = fw.fh.frame_height;
+            out->bit_depth = sp.hp.seq.bit_depth;
+            const int bps = sp.hp.seq.bit_depth == 8 ? 1 : 2;
+            const int sx = sp.hp.seq.subsampling_x, sy = sp.hp.seq.subsampling_y;
+            out->frame_bytes = (uint64_t)fw.fh.upscaled_width * fw.fh.frame_height * bps;
+            if (!sp.hp.seq.mono_chrome) out->frame_bytes += 2ull * ((fw.fh.upscaled_width + sx) >> sx) * ((fw.fh.frame_height + sy) >> sy) * bps;
+        }
+    }
+    return 0;
 }
 
 // Debug / test entry point (host only, no GPU): parses every frame of a container, builds the intra kernel's plan (K3 order, unit

@@ -11,13 +11,14 @@ static uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)r
 static bool demux_ivf(const uint8_t* d, size_t n, DemuxResult& out, std::string& err) {
     if (n < 32) { err = "ivf: truncated header"; return false; }
     size_t hl = d[6] | (d[7] << 8);
+    if (hl < 32 || hl > n) { err = "ivf: bad header length"; return false; }
     if (memcmp(d + 8, "AV01", 4) != 0) { err = "ivf: fourcc is not AV01"; return false; }
     size_t pos = hl;
     while (pos + 12 <= n) {
         uint32_t sz = rd32(d + pos);
         int64_t pts = (int64_t)rd64(d + pos + 4);
         pos += 12;
-        if (pos + sz > n) { err = "ivf: truncated frame"; return false; }
+        if (sz > n - pos) { err = "ivf: truncated frame"; return false; }
         out.tus.push_back({pos, sz, pts});
         pos += sz;
     }
@@ -43,7 +44,7 @@ static bool demux_obu(const uint8_t* d, size_t n, DemuxResult& out, std::string&
             sz |= (uint64_t)(b & 0x7f) << (7 * i);
             if (!(b & 0x80)) break;
         }
-        if (p + sz > n) { err = "obu: truncated"; return false; }
+        if (p > n || sz > n - p) { err = "obu: truncated"; return false; }
         if (type == 2 && any) {
             out.tus.push_back({tu_start, pos - tu_start, pts++});
             tu_start = pos;
@@ -57,125 +58,204 @@ static bool demux_obu(const uint8_t* d, size_t n, DemuxResult& out, std::string&
 }
 
 // ---- Matroska (EBML) ------------------------------------------------------------------------
+// The file is untrusted (it is the possibly-broken output the verifier exists to catch): every element end is clamped to its
+// parent's end and to the buffer, sizes are checked before they are added to a position, and a block is only recorded when its
+// payload lies inside the buffer.
+namespace {
+
 struct Ebml {
     const uint8_t* d;
     size_t n;
-    bool read_id(size_t& pos, uint32_t& id) const {
-        if (pos >= n) return false;
-        uint8_t b = d[pos];
-        int len = b & 0x80 ? 1 : b & 0x40 ? 2 : b & 0x20 ? 3 : b & 0x10 ? 4 : 0;
-        if (!len || pos + len > n) return false;
+    // element id at pos (1..4 bytes), pos advances; false at end / malformed
+    bool read_id(size_t& pos, size_t end, uint32_t& id) const {
+        if (pos >= end) return false;
+        const uint8_t b = d[pos];
+        const int len = b & 0x80 ? 1 : b & 0x40 ? 2 : b & 0x20 ? 3 : b & 0x10 ? 4 : 0;
+        if (!len || end - pos < (size_t)len) return false;
         id = 0;
         for (int i = 0; i < len; i++) id = (id << 8) | d[pos + i];
         pos += len;
         return true;
     }
-    bool read_size(size_t& pos, uint64_t& sz, bool& unknown) const {
-        if (pos >= n) return false;
-        uint8_t b = d[pos];
+    // EBML variable-length integer (element size, track number, lace size); `unknown` = all value bits set
+    bool read_vint(size_t& pos, size_t end, uint64_t& v, bool& unknown, int* nbytes = nullptr) const {
+        if (pos >= end) return false;
+        const uint8_t b = d[pos];
         int len = 0;
         for (int i = 0; i < 8; i++)
             if (b & (0x80 >> i)) { len = i + 1; break; }
-        if (!len || pos + len > n) return false;
-        uint64_t v = b & (0xff >> len);
-        bool all1 = v == (uint64_t)(0xff >> len);
+        if (!len || end - pos < (size_t)len) return false;
+        uint64_t x = b & (0xff >> len);
+        bool all1 = x == (uint64_t)(0xff >> len);
         for (int i = 1; i < len; i++) {
-            v = (v << 8) | d[pos + i];
+            x = (x << 8) | d[pos + i];
             if (d[pos + i] != 0xff) all1 = false;
         }
         pos += len;
-        sz = v;
+        v = x;
         unknown = all1;
+        if (nbytes) *nbytes = len;
         return true;
     }
-    uint64_t read_uint(size_t pos, uint64_t sz) const {
+    // header of the child element at pos inside [pos, parent_end): id, payload range [pos, el_end).  An unknown-size child
+    // extends to the parent's end.  false = no further well-formed child.
+    bool child(size_t& pos, size_t parent_end, uint32_t& id, size_t& el_end, bool& unknown) const {
+        uint64_t sz;
+        if (!read_id(pos, parent_end, id) || !read_vint(pos, parent_end, sz, unknown)) return false;
+        if (unknown) el_end = parent_end;
+        else if (sz > (uint64_t)(parent_end - pos)) return false;   // child sticks out of its parent (or of the buffer)
+        else el_end = pos + (size_t)sz;
+        return true;
+    }
+    uint64_t read_uint(size_t pos, size_t end) const {   // big-endian unsigned of up to 8 bytes
         uint64_t v = 0;
-        for (uint64_t i = 0; i < sz && i < 8; i++) v = (v << 8) | d[pos + i];
+        for (size_t i = pos; i < end && i < pos + 8; i++) v = (v << 8) | d[i];
         return v;
     }
 };
 
+enum : uint32_t {
+    ID_EBML = 0x1A45DFA3, ID_SEGMENT = 0x18538067, ID_TRACKS = 0x1654AE6B, ID_TRACK_ENTRY = 0xAE, ID_TRACK_NUMBER = 0xD7,
+    ID_CODEC_ID = 0x86, ID_CODEC_PRIVATE = 0x63A2, ID_CLUSTER = 0x1F43B675, ID_TIMESTAMP = 0xE7, ID_SIMPLE_BLOCK = 0xA3,
+    ID_BLOCK_GROUP = 0xA0, ID_BLOCK = 0xA1, ID_CUES = 0x1C53BB6B, ID_TAGS = 0x1254C367, ID_SEEK_HEAD = 0x114D9B74,
+    ID_INFO = 0x1549A966, ID_CHAPTERS = 0x1043A770, ID_ATTACHMENTS = 0x1941A469,
+};
+
+static bool is_top_level(uint32_t id) {
+    return id == ID_CLUSTER || id == ID_CUES || id == ID_TAGS || id == ID_SEEK_HEAD || id == ID_INFO || id == ID_TRACKS ||
+           id == ID_CHAPTERS || id == ID_ATTACHMENTS;
+}
+
+// (Simple)Block payload [bp, bend): track number, 16-bit relative time, flags, then one frame or a lace of frames.
+static bool take_block(const Ebml& e, size_t bp, size_t bend, int64_t av1_track, int64_t cluster_ts, DemuxResult& out, std::string& err) {
+    uint64_t tn;
+    bool tunk;
+    size_t q = bp;
+    if (!e.read_vint(q, bend, tn, tunk) || bend - q < 3) { err = "mkv: truncated block header"; return false; }
+    const int16_t rel = (int16_t)((e.d[q] << 8) | e.d[q + 1]);
+    const uint8_t flags = e.d[q + 2];
+    q += 3;
+    if ((int64_t)tn != av1_track) return true;
+    const int lacing = (flags >> 1) & 3;
+    const int64_t pts = cluster_ts + rel;
+    if (!lacing) {
+        if (bend > q) out.tus.push_back({q, bend - q, pts});
+        return true;
+    }
+    // laced block: frame count - 1, then the sizes of all frames but the last (Xiph 1, fixed 2, EBML 3)
+    if (q >= bend) { err = "mkv: truncated lace header"; return false; }
+    const int nfr = e.d[q++] + 1;
+    std::vector<uint64_t> sizes((size_t)nfr, 0);
+    if (lacing == 1) {
+        for (int i = 0; i < nfr - 1; i++) {
+            uint64_t s = 0;
+            while (true) {
+                if (q >= bend) { err = "mkv: truncated Xiph lace"; return false; }
+                const uint8_t b = e.d[q++];
+                s += b;
+                if (b != 255) break;
+            }
+            sizes[i] = s;
+        }
+    } else if (lacing == 3) {
+        int64_t prev = 0;
+        for (int i = 0; i < nfr - 1; i++) {
+            uint64_t v;
+            bool u;
+            int nb = 0;
+            if (!e.read_vint(q, bend, v, u, &nb)) { err = "mkv: truncated EBML lace"; return false; }
+            int64_t s;
+            if (i == 0) s = (int64_t)v;
+            else s = prev + ((int64_t)v - (((int64_t)1 << (7 * nb - 1)) - 1));   // signed difference to the previous size
+            if (s < 0) { err = "mkv: negative EBML lace size"; return false; }
+            sizes[i] = (uint64_t)s;
+            prev = s;
+        }
+    }
+    const size_t payload = bend - q;
+    if (lacing == 2) {
+        if (payload % (size_t)nfr) { err = "mkv: fixed lace does not divide the block"; return false; }
+        for (auto& s : sizes) s = payload / (size_t)nfr;
+    } else {
+        uint64_t sum = 0;
+        for (int i = 0; i < nfr - 1; i++) {
+            if (sizes[i] > payload - sum) { err = "mkv: lace sizes exceed the block"; return false; }
+            sum += sizes[i];
+        }
+        sizes[nfr - 1] = payload - sum;
+    }
+    for (int i = 0; i < nfr; i++) {
+        if (sizes[i]) out.tus.push_back({q, (size_t)sizes[i], pts + i});
+        q += (size_t)sizes[i];
+    }
+    return true;
+}
+
+}  // namespace
+
 static bool demux_mkv(const uint8_t* d, size_t n, DemuxResult& out, std::string& err) {
-    Ebml e{d, n};
-    size_t pos = 0;
+    const Ebml e{d, n};
+    size_t pos = 0, end;
     uint32_t id;
-    uint64_t sz;
     bool unk;
-    if (!e.read_id(pos, id) || id != 0x1A45DFA3 || !e.read_size(pos, sz, unk)) { err = "mkv: no EBML header"; return false; }
-    pos += sz;
-    if (!e.read_id(pos, id) || id != 0x18538067 || !e.read_size(pos, sz, unk)) { err = "mkv: no Segment"; return false; }
-    size_t seg_end = unk ? n : (pos + sz > n ? n : pos + (size_t)sz);
+    if (!e.child(pos, n, id, end, unk) || id != ID_EBML || unk) { err = "mkv: no EBML header"; return false; }
+    pos = end;
+    if (!e.child(pos, n, id, end, unk) || id != ID_SEGMENT) { err = "mkv: no Segment"; return false; }
+    const size_t seg_end = end;
     int64_t av1_track = -1;
-    int64_t pts_fallback = 0;
     while (pos < seg_end) {
-        size_t el = pos;
-        if (!e.read_id(pos, id) || !e.read_size(pos, sz, unk)) break;
-        size_t end = unk ? seg_end : pos + (size_t)sz;
-        if (end > seg_end) end = seg_end;
-        if (id == 0x1654AE6B) {  // Tracks
-            size_t p = pos;
-            while (p < end) {
-                uint32_t tid; uint64_t tsz; bool tu;
-                if (!e.read_id(p, tid) || !e.read_size(p, tsz, tu)) break;
-                size_t tend = p + (size_t)tsz;
-                if (tid == 0xAE) {  // TrackEntry
+        if (!e.child(pos, seg_end, id, end, unk)) break;    // trailing garbage / truncated element: keep what was found
+        if (id == ID_TRACKS) {
+            size_t p = pos, tend;
+            uint32_t tid;
+            bool tu;
+            while (p < end && e.child(p, end, tid, tend, tu)) {
+                if (tid == ID_TRACK_ENTRY) {
                     int64_t num = -1;
                     bool is_av1 = false;
-                    size_t cp_off = 0, cp_sz = 0;
-                    size_t q = p;
-                    while (q < tend) {
-                        uint32_t fid; uint64_t fsz; bool fu;
-                        if (!e.read_id(q, fid) || !e.read_size(q, fsz, fu)) break;
-                        if (fid == 0xD7) num = (int64_t)e.read_uint(q, fsz);
-                        else if (fid == 0x86) is_av1 = fsz == 5 && memcmp(d + q, "V_AV1", 5) == 0;
-                        else if (fid == 0x63A2) { cp_off = q; cp_sz = (size_t)fsz; }
-                        q += (size_t)fsz;
+                    size_t cp_off = 0, cp_end = 0, q = p, fend;
+                    uint32_t fid;
+                    bool fu;
+                    while (q < tend && e.child(q, tend, fid, fend, fu)) {
+                        if (fid == ID_TRACK_NUMBER) num = (int64_t)e.read_uint(q, fend);
+                        else if (fid == ID_CODEC_ID) is_av1 = fend - q == 5 && memcmp(d + q, "V_AV1", 5) == 0;
+                        else if (fid == ID_CODEC_PRIVATE) { cp_off = q; cp_end = fend; }
+                        q = fend;
                     }
-                    if (is_av1 && av1_track < 0) {
+                    if (is_av1 && av1_track < 0 && num >= 0) {
                         av1_track = num;
-                        if (cp_sz > 4) out.config_obus.assign(d + cp_off + 4, d + cp_off + cp_sz);  // skip av1C 4-byte header
+                        if (cp_end - cp_off > 4) out.config_obus.assign(d + cp_off + 4, d + cp_end);   // skip the 4-byte av1C header
                     }
                 }
                 p = tend;
             }
-        } else if (id == 0x1F43B675) {  // Cluster
+        } else if (id == ID_CLUSTER) {
             int64_t cluster_ts = 0;
-            size_t p = pos;
+            size_t p = pos, cend;
+            uint32_t cid;
+            bool cu;
             while (p < end) {
-                size_t save = p;
-                uint32_t cid; uint64_t csz; bool cu;
-                if (!e.read_id(p, cid) || !e.read_size(p, csz, cu)) break;
-                if (unk && (cid == 0x1F43B675 || cid == 0x1C53BB6B || cid == 0x1254C367)) { end = save; break; }
-                size_t cend = p + (size_t)csz;
-                if (cend > n) { err = "mkv: truncated cluster"; return false; }
-                auto take_block = [&](size_t bp, size_t bend) -> bool {
-                    uint64_t tn; bool tunk; size_t q = bp;
-                    if (!e.read_size(q, tn, tunk) || q + 3 > bend) return false;
-                    int16_t rel = (int16_t)((d[q] << 8) | d[q + 1]);
-                    uint8_t flags = d[q + 2];
-                    q += 3;
-                    if ((int64_t)tn != av1_track) return true;
-                    if (flags & 0x06) { err = "mkv: laced blocks unsupported"; return false; }
-                    out.tus.push_back({q, bend - q, cluster_ts + rel});
-                    return true;
-                };
-                if (cid == 0xE7) cluster_ts = (int64_t)e.read_uint(p, csz);
-                else if (cid == 0xA3) { if (!take_block(p, cend)) { if (err.empty()) err = "mkv: bad SimpleBlock"; return false; } }
-                else if (cid == 0xA0) {
-                    size_t q = p;
-                    while (q < cend) {
-                        uint32_t gid; uint64_t gsz; bool gu;
-                        if (!e.read_id(q, gid) || !e.read_size(q, gsz, gu)) break;
-                        if (gid == 0xA1) { if (!take_block(q, q + (size_t)gsz)) { if (err.empty()) err = "mkv: bad Block"; return false; } }
-                        q += (size_t)gsz;
+                const size_t save = p;
+                if (!e.child(p, end, cid, cend, cu)) {
+                    if (!unk) { err = "mkv: truncated cluster"; return false; }
+                    end = save;
+                    break;
+                }
+                if (unk && is_top_level(cid)) { end = save; break; }   // an unknown-size cluster ends at the next top-level element
+                if (cid == ID_TIMESTAMP) cluster_ts = (int64_t)e.read_uint(p, cend);
+                else if (cid == ID_SIMPLE_BLOCK) { if (!take_block(e, p, cend, av1_track, cluster_ts, out, err)) return false; }
+                else if (cid == ID_BLOCK_GROUP) {
+                    size_t q = p, gend;
+                    uint32_t gid;
+                    bool gu;
+                    while (q < cend && e.child(q, cend, gid, gend, gu)) {
+                        if (gid == ID_BLOCK && !take_block(e, q, gend, av1_track, cluster_ts, out, err)) return false;
+                        q = gend;
                     }
                 }
                 p = cend;
             }
-            if (unk) { pos = end; continue; }
         }
-        (void)el;
-        (void)pts_fallback;
         pos = end;
     }
     if (av1_track < 0) { err = "mkv: no V_AV1 track"; return false; }

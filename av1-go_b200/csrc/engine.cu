@@ -311,7 +311,6 @@ struct FrameSlot {
     PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
     PinBuf planes_host;
     bool busy = false;
-    const int* k3_stuck_dev = nullptr;   // device word the intra kernel raises when one of its waits made no progress (watchdog)
     std::shared_ptr<void> host_arena;   // pinned staging the queued H2D copy reads from (returned to the pool when the slot is reused)
     // frame buffers touched by the work queued on this slot: kept alive (out of the recycling pool)
     // until the slot's completion event has been waited on
@@ -385,6 +384,7 @@ struct EngineImpl {
     std::vector<std::shared_ptr<DevFrameBuf>> pool;   // recycled frame buffers
     DevBuf k3_prof;                                   // AV1R_K3_PROF: 16 cycle counters of the intra kernel
     DevBuf wedge_master;                              // 6 x 64 x 64 wedge master masks (inter-intra blends in K3)
+    DevBuf k3_stuck;                                  // one int: watchdog word of the intra kernel (sticky until the next verify / replay)
     HostArenaPool host_pool;
     std::shared_ptr<void> make_host_arena(const FrameWork& fw, const SeqHdr& seq, std::string& e, int& rc);
     size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
@@ -455,7 +455,6 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         res.base = (int16_t*)s.residual.p;
     }
     const TxRec* d_recs = (const TxRec*)(d_arena + L.recs);
-    s.k3_stuck_dev = nullptr;
     if (tm) tm->begin(st);
     CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, L.n_order_small, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, (L.n_order_small > 0) + (L.n_order > L.n_order_small), st);
@@ -516,7 +515,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         il.uprog = (unsigned long long*)s.sync.p;
         il.uflags = (int*)(s.sync.p + sizeof(unsigned long long) * (size_t)L.n_k3units);
         il.ticket = il.uflags + L.n_k3units;
-        s.k3_stuck_dev = il.ticket + 1;
+        il.stuck = (int*)k3_stuck.p;
         // Cell-level hand-over is the default: 1.6x lower frame latency and (since the wait loop got leaner) also the higher clip
         // rate with 16+ frames side by side (c2: 3220 vs 2960 frames/s).  AV1R_K3_PROGRESSIVE=1 selects the earlier adaptive policy
         // (whole-unit hand-over inside saturated runs of frames nothing predicts from), =0 whole-unit always.
@@ -661,8 +660,9 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
         CK(launch_plane_checksum(shown->pl.p[p], shown->pl.pitch[p], fp.w[p], fp.h[p], fp.bd, (uint64_t*)s->cks_dev.p + p, st));
     if (tm) tm->end(AV1R_ST_DIGEST, np, st);
     CK(cudaMemcpyAsync(s->cks_host.p, s->cks_dev.p, 24, cudaMemcpyDeviceToHost, st));
-    memset(s->cks_host.p + 24, 0, 4);
-    if (s->k3_stuck_dev && !existing) CK(cudaMemcpyAsync(s->cks_host.p + 24, s->k3_stuck_dev, 4, cudaMemcpyDeviceToHost, st));
+    // watchdog word of the intra kernel: engine-wide and sticky, so a stuck *hidden* frame (ALTREF, or one shown later through
+    // show_existing_frame) is reported with the next output instead of being lost
+    CK(cudaMemcpyAsync(s->cks_host.p + 24, k3_stuck.p, 4, cudaMemcpyDeviceToHost, st));
     Pending pd;
     memset(&pd.res, 0, sizeof(pd.res));
     pd.res.struct_size = sizeof(pd.res);
@@ -804,20 +804,21 @@ int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_a
     return 0;
 }
 
-static double g_eprof[8];
+static std::atomic<long long> g_eprof_ns[8];   // written from the consumer and the parser threads
 struct EProfPrinter {
     ~EProfPrinter() {
         if (getenv("AV1R_PROFILE"))
-            fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f ms\n", g_eprof[0], g_eprof[1],
-                    g_eprof[2], g_eprof[3], g_eprof[4], g_eprof[5]);
+            fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f ms\n", g_eprof_ns[0] * 1e-6,
+                    g_eprof_ns[1] * 1e-6, g_eprof_ns[2] * 1e-6, g_eprof_ns[3] * 1e-6, g_eprof_ns[4] * 1e-6, g_eprof_ns[5] * 1e-6);
     }
 } g_eprof_printer;
 extern "C" void av1r_debug_engine_prof(double* out6, int reset) {
-    for (int i = 0; i < 6; i++) out6[i] = g_eprof[i];
-    if (reset) memset(g_eprof, 0, sizeof(g_eprof));
+    for (int i = 0; i < 6; i++) out6[i] = g_eprof_ns[i] * 1e-6;
+    if (reset)
+        for (auto& v : g_eprof_ns) v = 0;
 }
 #define EP_T() std::chrono::steady_clock::now()
-#define EP_ADD(i, a) g_eprof[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()
+#define EP_ADD(i, a) g_eprof_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count()
 
 int EngineImpl::decode_parsed(ParsedFrame& pf) {
     int slot_idx;
@@ -954,6 +955,8 @@ int Engine::open(const av1r_config& cfg) {
         CK(E.k3_prof.ensure(16 * sizeof(unsigned long long)));
         CK(cudaMemset(E.k3_prof.p, 0, 16 * sizeof(unsigned long long)));
     }
+    CK(E.k3_stuck.ensure(256));
+    CK(cudaMemset(E.k3_stuck.p, 0, 256));
     CK(E.wedge_master.ensure(6 * 64 * 64));
     CK(inter_copy_wedge_master(E.wedge_master.p, E.streams[0]));
     CK(cudaStreamSynchronize(E.streams[0]));
@@ -1110,6 +1113,7 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     int rc = eng.flush();
     if (rc) return fail(rc, eng.error());
     impl_->pending.clear();
+    cudaMemset(impl_->k3_stuck.p, 0, 4);
     auto t0 = std::chrono::steady_clock::now();
     // ---- pre-scan: sequence header + segment boundaries (TUs that start with a shown key frame)
     HeaderParser scan;
@@ -1302,7 +1306,10 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
         }
         E.rs = &E.main_refs;
     }
-    abort_flag.store(true);
+    {   // under la_m: a worker between its predicate test and its block must not miss the wake-up
+        std::lock_guard<std::mutex> lk(la_m);
+        abort_flag.store(true);
+    }
     la_cv.notify_all();
     for (auto& th : pool) th.join();
     int r = drain(true);
@@ -1411,6 +1418,7 @@ int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, 
     int rc = flush();
     if (rc) return rc;
     E.pending.clear();
+    cudaMemset(E.k3_stuck.p, 0, 4);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -1451,6 +1459,7 @@ int Engine::clip_profile(av1r_clip* clip, av1r_stage_times* out) {
     int rc = flush();
     if (rc) return rc;
     E.pending.clear();
+    cudaMemset(E.k3_stuck.p, 0, 4);
     memset(out, 0, sizeof(*out));
     out->struct_size = sizeof(*out);
     // serialise on one stream so that the spans do not overlap

@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                     int spins = 0;
                     while (ld_relaxed(L.uflags + d) == 0) {   // <= 5 polling lanes per CTA
                         __nanosleep(100);
-                        if (++spins > (1 << 25)) { L.ticket[1] = 2; break; }
+                        if (++spins > (1 << 25)) { *L.stuck = 2; break; }
                     }
                     fence_acquire_gpu();
                 }
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             if (k + nw < count) r_next = load_rec(L.recs + __ldg(L.order + first + k + nw));
             lap(8, lane == 0);   // record fetch
             if (r.mode == TXM_INTER) {
-                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.ticket + 1);   // residual of an inter-intra block: after its blend
+                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck);   // residual of an inter-intra block: after its blend
             } else if (r.mode != TXM_PALETTE) {
                 const int plane = r.plane;
                 const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 while ((ld_relaxed64(L.uprog + d) & want) != want) {
                                     __nanosleep(ns);
                                     if (ns < 800) ns <<= 1;
-                                    if (++spins > (1 << 23)) { L.ticket[1] = 3; break; }
+                                    if (++spins > (1 << 23)) { *L.stuck = 3; break; }
                                 }
                             }
                         }
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                         }
                         __syncwarp();
                     }
-                    wait_local(rbar, id, rpar, L.ticket + 1);
+                    wait_local(rbar, id, rpar, L.stuck);
                 }
                 if (r.mode == TXM_CFL) {   // luma samples under this chroma block
                     const int sx = fp.subx, sy = fp.suby;
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 if (id >= k) id = -1;
                             }
                         }
-                        wait_local(rbar, id, rpar, L.ticket + 1);
+                        wait_local(rbar, id, rpar, L.stuck);
                     }
                 }
             }

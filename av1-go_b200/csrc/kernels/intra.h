@@ -19,6 +19,7 @@ struct IntraLaunch {            // passed by value
     unsigned long long* uprog;  // device, n_units words, zeroed before launch: finished border cells of every unit (bit layout in intra.cu)
     int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
     int* ticket;                // device, one int, zeroed before launch
+    int* stuck;                 // device, one int shared by every frame of the engine: raised (never cleared by the kernel) when a wait made no progress
     DevPlanes frame;
     DevResidual res;
     DevFrameParams fp;

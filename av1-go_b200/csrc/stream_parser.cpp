@@ -1,6 +1,7 @@
 #include "stream_parser.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -67,14 +68,15 @@ void cdf_clear_counters(CdfCtx& c) {
 #undef CLR
 }
 
-static double g_prof[8];
-struct ProfPrinter { ~ProfPrinter() { if (getenv("AV1R_PROFILE")) fprintf(stderr, "[prof] tiles %.1f merge %.1f lf %.1f wrap %.1f begin %.1f ms\n", g_prof[0], g_prof[1], g_prof[2], g_prof[3], g_prof[4]); } } g_prof_printer;
+static std::atomic<long long> g_prof_ns[8];   // several parser threads add to these
+struct ProfPrinter { ~ProfPrinter() { if (getenv("AV1R_PROFILE")) fprintf(stderr, "[prof] tiles %.1f merge %.1f lf %.1f wrap %.1f begin %.1f ms\n", g_prof_ns[0] * 1e-6, g_prof_ns[1] * 1e-6, g_prof_ns[2] * 1e-6, g_prof_ns[3] * 1e-6, g_prof_ns[4] * 1e-6); } } g_prof_printer;
 extern "C" void av1r_debug_parse_prof(double* out5, int reset) {
-    for (int i = 0; i < 5; i++) out5[i] = g_prof[i];
-    if (reset) memset(g_prof, 0, sizeof(g_prof));
+    for (int i = 0; i < 5; i++) out5[i] = g_prof_ns[i] * 1e-6;
+    if (reset)
+        for (auto& v : g_prof_ns) v = 0;
 }
 #define PROF_T() std::chrono::steady_clock::now()
-#define PROF_ADD(i, a) g_prof[i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()
+#define PROF_ADD(i, a) g_prof_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count()
 
 // FrameWork objects are recycled process-wide: a 4K frame's maps and lists are ~20 MB of vectors whose allocation (page faults) and
 // growth would otherwise be paid on every frame.
@@ -110,7 +112,7 @@ StreamParser::StreamParser() {
 
 int StreamParser::begin_frame(const FrameHdr& fh) {
     auto tb = std::chrono::steady_clock::now();
-    struct Fin { std::chrono::steady_clock::time_point t; ~Fin() { g_prof[4] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } fin{tb};
+    struct Fin { std::chrono::steady_clock::time_point t; ~Fin() { g_prof_ns[4] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } fin{tb};
     // AV1 level 6.3 caps a picture at 16384 x 8704 and 35,651,584 samples: anything beyond is a corrupt header, not a frame to allocate
     if (fh.upscaled_width > 16384 || fh.frame_height > 8704 || (int64_t)fh.upscaled_width * fh.frame_height > 35651584 || fh.frame_width < 1 ||
         fh.frame_height < 1)
@@ -246,6 +248,9 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
     BitReader br(payload + offset, size - offset);
     TileGroupInfo tg;
     if (!hp.parse_tile_group_header(br, cur_fh_, tg)) return fail(AV1R_EBITSTREAM, hp.error);
+    // tile groups cover the tiles of a frame in order, each tile exactly once (spec 5.11.1: tg_start == TileNum of the next tile)
+    if (tg.tg_start != tiles_done_ || tg.tg_end < tg.tg_start || tg.tg_end >= cur_fh_.tile_cols * cur_fh_.tile_rows)
+        return fail(AV1R_EBITSTREAM, "tile group does not continue at the next tile of the frame");
     size_t pos = offset + tg.data_offset;
     auto t0 = std::chrono::steady_clock::now();
     // ---- locate the tiles of this group, then parse them concurrently (each tile is an independent symbol stream)
@@ -385,6 +390,15 @@ int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
 }
 
 int StreamParser::parse_tu(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out) {
+    const int rc = parse_tu_inner(data, len, pts, out);
+    if (rc) {   // a failed temporal unit never leaves a half-assembled frame behind: the next unit starts clean
+        have_frame_ = false;
+        cur_.reset();
+    }
+    return rc;
+}
+
+int StreamParser::parse_tu_inner(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out) {
     std::vector<ObuUnit> obus;
     if (!hp.split_obus(data, len, obus)) return fail(AV1R_EBITSTREAM, hp.error);
     for (const ObuUnit& u : obus) {
@@ -393,14 +407,20 @@ int StreamParser::parse_tu(const uint8_t* data, size_t len, int64_t pts, std::ve
                 if (!hp.parse_sequence_header(u.data, u.size)) return fail(AV1R_EBITSTREAM, hp.error);
                 break;
             case OBU_TEMPORAL_DELIMITER:
+                if (have_frame_) return fail(AV1R_EBITSTREAM, "temporal delimiter inside a frame: tile data of the previous frame is missing");
                 break;
             case OBU_FRAME_HEADER:
             case OBU_REDUNDANT_FRAME_HEADER:
             case OBU_FRAME: {
                 if (have_frame_) {
+                    // only a copy of the active header may appear while tile groups are outstanding (spec 5.9.1 frame_header_copy)
                     if (u.type == OBU_FRAME) return fail(AV1R_EBITSTREAM, "frame OBU while another frame is open");
+                    const size_t nb = cur_hdr_bytes_.size() > 1 ? cur_hdr_bytes_.size() - 1 : 0;   // last byte may differ in trailing bits
+                    if (u.size < nb || memcmp(u.data, cur_hdr_bytes_.data(), nb) != 0)
+                        return fail(AV1R_EBITSTREAM, "new frame header while tile data of the previous frame is missing");
                     break;   // redundant copy of the active header
                 }
+                if (u.type == OBU_REDUNDANT_FRAME_HEADER) return fail(AV1R_EBITSTREAM, "redundant frame header without an active frame");
                 BitReader br(u.data, u.size);
                 FrameHdr fh;
                 if (!hp.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) return fail(AV1R_EBITSTREAM, hp.error);
@@ -426,6 +446,11 @@ int StreamParser::parse_tu(const uint8_t* data, size_t len, int64_t pts, std::ve
                 }
                 int rc = begin_frame(fh);
                 if (rc) return rc;
+                {
+                    BitReader tmp = br;
+                    tmp.byte_align();
+                    cur_hdr_bytes_.assign(u.data, u.data + std::min(u.size, (size_t)tmp.byte_pos()));
+                }
                 if (u.type == OBU_FRAME) {
                     br.byte_align();
                     rc = tile_group(u.data, u.size, br.byte_pos());
@@ -453,6 +478,9 @@ int StreamParser::parse_tu(const uint8_t* data, size_t len, int64_t pts, std::ve
                 break;   // metadata, padding
         }
     }
+    // a temporal unit holds whole frames: a frame header whose tile groups did not all arrive is a truncated / corrupt stream
+    // (without this check the frame would silently vanish and the verifier would report one frame fewer as "ok")
+    if (have_frame_) return fail(AV1R_EBITSTREAM, "temporal unit ends inside a frame: tile data missing");
     return 0;
 }
 

@@ -38,7 +38,9 @@ private:
     CdfCtx cur_init_cdf_;
     int tiles_done_ = 0;
     bool have_frame_ = false;
+    std::vector<uint8_t> cur_hdr_bytes_;   // bytes of the active frame header (to recognise its redundant copies)
     int fail(int code, const std::string& m) { err = m; return code; }
+    int parse_tu_inner(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out);
     int begin_frame(const FrameHdr& fh);
     void motion_field_estimation();
     int tile_group(const uint8_t* payload, size_t size, size_t offset);

@@ -111,6 +111,10 @@ int av1r_clip_info_get(const av1r_clip* clip, av1r_clip_info* out);
 int av1r_clip_decode(struct av1r_ctx* ctx, av1r_clip* clip, uint64_t* checksums, int cap_frames, int* n_frames, float* device_ms);
 int av1r_clip_profile(struct av1r_ctx* ctx, av1r_clip* clip, av1r_stage_times* out);
 void av1r_clip_free(av1r_clip* clip);
+/* Host-only statistics of a container (IVF / raw OBU / Matroska bytes): the parser-side fields of av1r_clip_info (tool histogram,
+ * coded samples, frames per post-filter stage ...) without touching a GPU.  bench.py uses it to refuse a clip that lacks the tools
+ * of the BASELINE config it stands for. */
+int av1r_parse_stats(const uint8_t* data, size_t len, av1r_clip_info* out);
 
 #ifdef __cplusplus
 }

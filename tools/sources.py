@@ -115,3 +115,77 @@ def pan_zoom(w, h, n, bpc=8, seed=3):
 
 
 SOURCES = {"testsrc2": testsrc2_like, "noise": noise_gradient, "panzoom": pan_zoom}
+
+
+def occluders(w, h, n, bpc=8, seed=3, n_obj=14):
+    """Fine-textured background under a global pan / slow zoom, with textured foreground objects that move independently, cross
+    each other (occlusion edges -> wedge / difference-weighted compound, OBMC, inter-intra at uncovered borders), two of which fade
+    in brightness (distance-weighted compound), plus mild sensor-like noise (keeps loop restoration worthwhile)."""
+    rng = np.random.default_rng(seed)
+    big = 1 << int(np.ceil(np.log2(max(w, h) * 1.5)))
+    coarse = np.kron(rng.normal(0, 1, size=(big // 32, big // 32)).astype(np.float32), np.ones((32, 32), np.float32))
+    mid = np.kron(rng.normal(0, 1, size=(big // 8, big // 8)).astype(np.float32), np.ones((8, 8), np.float32))
+    fine = np.kron(rng.normal(0, 1, size=(big // 2, big // 2)).astype(np.float32), np.ones((2, 2), np.float32))
+    tex = coarse * 28 + mid * 14 + fine * 7 + 120
+    for _ in range(2):
+        tex = (tex + np.roll(tex, 1, 0) + np.roll(tex, 1, 1) + np.roll(np.roll(tex, 1, 0), 1, 1)) / 4
+    cu = np.kron(rng.normal(128, 25, size=(big // 64, big // 64)).astype(np.float32), np.ones((64, 64), np.float32))
+    cv = np.roll(cu, 177, axis=1)[::-1]
+    xx, yy = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    cx, cy = w / 2, h / 2
+    objs = []
+    for i in range(n_obj):
+        ow = int(rng.integers(w // 14, w // 5))
+        oh = int(rng.integers(h // 10, h // 4))
+        objs.append(dict(x=float(rng.integers(0, w - ow)), y=float(rng.integers(0, h - oh)), w=ow, h=oh,
+                         vx=float(rng.uniform(-9, 9)), vy=float(rng.uniform(-6, 6)), tx=int(rng.integers(0, big - ow)), ty=int(rng.integers(0, big - oh)),
+                         gain=float(rng.uniform(0.6, 1.2)), off=float(rng.uniform(-30, 50)), fade=(i % 5 == 0), round=(i % 3 == 0),
+                         cu=float(rng.uniform(70, 190)), cv=float(rng.uniform(70, 190))))
+    for t in range(n):
+        zoom = 1.0 + 0.002 * t
+        sx = (xx - cx) / zoom + cx + 1.75 * t + big / 4
+        sy = (yy - cy) / zoom + cy + 0.75 * t + big / 4
+        x0 = np.floor(sx).astype(np.int32)
+        y0 = np.floor(sy).astype(np.int32)
+        fx = sx - x0
+        fy = sy - y0
+        x0 %= big
+        y0 %= big
+        x1 = (x0 + 1) % big
+        y1 = (y0 + 1) % big
+
+        def samp(img):
+            return (img[y0, x0] * (1 - fx) * (1 - fy) + img[y0, x1] * fx * (1 - fy) + img[y1, x0] * (1 - fx) * fy + img[y1, x1] * fx * fy)
+
+        y = samp(tex)
+        u = samp(cu)
+        v = samp(cv)
+        for o in objs:
+            px = o["x"] + o["vx"] * t
+            py = o["y"] + o["vy"] * t
+            # bounce inside the frame
+            rx, ry = w - o["w"], h - o["h"]
+            px = abs((px % (2 * rx)) - rx) if rx > 0 else 0
+            py = abs((py % (2 * ry)) - ry) if ry > 0 else 0
+            qx, qy = int(px), int(py)
+            patch = tex[o["ty"]:o["ty"] + o["h"], o["tx"]:o["tx"] + o["w"]] * o["gain"] + o["off"]
+            if o["fade"]:
+                patch = patch + 40.0 * np.sin(t / 5.0)
+            if o["round"]:
+                ey, ex = np.ogrid[0:o["h"], 0:o["w"]]
+                m = (((ex - o["w"] / 2) / (o["w"] / 2)) ** 2 + ((ey - o["h"] / 2) / (o["h"] / 2)) ** 2) <= 1.0
+                ys = y[qy:qy + o["h"], qx:qx + o["w"]]
+                ys[m] = patch[m]
+                us = u[qy:qy + o["h"], qx:qx + o["w"]]
+                us[m] = o["cu"]
+                vs = v[qy:qy + o["h"], qx:qx + o["w"]]
+                vs[m] = o["cv"]
+            else:
+                y[qy:qy + o["h"], qx:qx + o["w"]] = patch
+                u[qy:qy + o["h"], qx:qx + o["w"]] = o["cu"]
+                v[qy:qy + o["h"], qx:qx + o["w"]] = o["cv"]
+        y = y + rng.normal(0, 2.0, size=y.shape).astype(np.float32)
+        yield _to420(y, u, v, bpc)
+
+
+SOURCES["occluders"] = occluders
