@@ -41,7 +41,7 @@ oracle/_build/liboracle.so: $(ORACLE_C) $(ORACLE_CPP) $(PARSER_OBJS) $(wildcard 
 
 # sanitizer build of the host half (demux + parser + C entry points that need no GPU), driven by tests/test_robustness.py
 ASAN_CXX ?= /usr/bin/g++
-ASAN_SRCS := $(HOST_SRCS) tests/native/parse_fuzz_main.cpp
+ASAN_SRCS := $(filter-out $(CSRC)/batch.cpp,$(HOST_SRCS)) tests/native/parse_fuzz_main.cpp
 build/asan/parse_fuzz: $(ASAN_SRCS) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p build/asan
 	$(ASAN_CXX) -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize=shift-base -fno-sanitize-recover=undefined -fno-omit-frame-pointer -Iinclude -I/usr/local/cuda/include $(ASAN_SRCS) -o $@ -lpthread

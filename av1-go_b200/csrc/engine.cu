@@ -332,7 +332,10 @@ struct ClipFrame {
     FrameHdr fh;
     int64_t pts = 0;
     DevWork dw;
-    DevBuf arena;
+    uint8_t* host = nullptr;   // pinned work-list arena (exact size): what every replay copies to the device inside the timed region
+    DevBuf arena;              // resident mode only: device copy made once
+    bool arena_valid = false;
+    ~ClipFrame() { if (host) cudaFreeHost(host); }
 };
 
 // cudaEvent-based per-stage timer (profile replay only)
@@ -341,6 +344,7 @@ struct StageTimer {
     std::vector<Span> spans;
     cudaEvent_t cur = nullptr;
     void begin(cudaStream_t st) {
+        if (cur) cudaEventDestroy(cur);
         cudaEventCreate(&cur);
         cudaEventRecord(cur, st);
     }
@@ -1059,6 +1063,7 @@ int Engine::verify_file(const char* path, const av1r_config* cfg, av1r_report* o
     return verify_buffer(buf.data(), buf.size(), cfg, out, nullptr, 0);
 }
 
+// ---- verification of whole containers: one file on one GPU (av1r_verify_*), or a batch of files over several GPUs ------------
 // One key-frame-delimited GOP segment: parsed by one host thread, issued to the GPU in order.
 struct Segment {
     size_t tu0 = 0, tu1 = 0;                       // temporal units [tu0, tu1)
@@ -1069,6 +1074,78 @@ struct Segment {
     std::condition_variable cv;
     size_t n_done = 0;                              // TUs parsed so far
 };
+
+// Pre-scan of one container: sequence header, temporal units, where the independently decodable GOP segments start (temporal
+// units whose first frame is a shown KEY_FRAME -- the only safe cut) and how many frames are shown before each unit.
+int VerifyFile::prescan(std::string& msg) {
+    std::string derr;
+    if (!demux_buffer(data, len, dm, derr)) { msg = derr; return AV1R_EBITSTREAM; }
+    if (!dm.config_obus.empty()) {
+        std::vector<ObuUnit> obus;
+        if (scan.split_obus(dm.config_obus.data(), dm.config_obus.size(), obus))
+            for (auto& u : obus)
+                if (u.type == OBU_SEQUENCE_HEADER) scan.parse_sequence_header(u.data, u.size);
+    }
+    starts.clear();
+    frame_base.assign(dm.tus.size() + 1, 0);
+    for (size_t i = 0; i < dm.tus.size(); i++) {
+        std::vector<ObuUnit> obus;
+        if (!scan.split_obus(data + dm.tus[i].offset, dm.tus[i].size, obus)) { msg = scan.error; return AV1R_EBITSTREAM; }
+        bool first_frame = true, frame_open = false;   // frame_open: a frame header was seen and not all of its tiles yet
+        int shown = 0;
+        FrameHdr open_fh;
+        auto tiles_after = [&](const uint8_t* p, size_t n) {   // tile group header at p: is the frame complete after this group?
+            BitReader tb(p, n);
+            TileGroupInfo tg;
+            if (!scan.parse_tile_group_header(tb, open_fh, tg)) return true;   // the parser proper reports the error
+            return tg.tg_end + 1 >= open_fh.tile_cols * open_fh.tile_rows;
+        };
+        for (const ObuUnit& u : obus) {
+            if (u.type == OBU_SEQUENCE_HEADER) {
+                if (!scan.parse_sequence_header(u.data, u.size)) { msg = scan.error; return AV1R_EBITSTREAM; }
+            } else if (u.type == OBU_FRAME || (u.type == OBU_FRAME_HEADER && !frame_open)) {   // (a header while a frame is open is a copy)
+                BitReader br(u.data, u.size);
+                FrameHdr fh;
+                if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) { msg = scan.error; return AV1R_EBITSTREAM; }
+                if (first_frame && !fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
+                shown += fh.show_existing_frame || fh.show_frame;
+                if (!fh.show_existing_frame) scan.reference_update(fh);
+                else if (fh.frame_type == KEY_FRAME) {
+                    RefHdrState r = scan.refs[fh.frame_to_show_map_idx];
+                    for (auto& x : scan.refs) x = r;
+                }
+                first_frame = false;
+                open_fh = fh;
+                frame_open = !fh.show_existing_frame;
+                if (u.type == OBU_FRAME) {
+                    br.byte_align();
+                    const size_t off = br.byte_pos();
+                    frame_open = off < u.size ? !tiles_after(u.data + off, u.size - off) : false;
+                }
+            } else if (u.type == OBU_TILE_GROUP && frame_open) {
+                frame_open = !tiles_after(u.data, u.size);
+            }
+        }
+        frame_base[i + 1] = frame_base[i] + shown;
+    }
+    if (!scan.seq.valid) { msg = "no sequence header"; return AV1R_EBITSTREAM; }
+    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+    return 0;
+}
+
+void VerifyFile::init_report() {
+    memset(rep, 0, sizeof(*rep));
+    rep->struct_size = sizeof(*rep);
+    rep->first_bad_frame = -1;
+}
+
+void VerifyFile::fail(int rc, int64_t frame, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(m);
+    if (rep->status && rep->first_bad_frame >= 0 && (frame < 0 || frame >= rep->first_bad_frame)) return;   // keep the earliest
+    rep->status = rc;
+    rep->first_bad_frame = frame;
+    snprintf(rep->message, sizeof(rep->message), "%s", msg.c_str());
+}
 
 int Engine::verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, av1r_report* out, uint64_t* digests, int64_t cap_frames) {
     av1r_config c;
@@ -1095,71 +1172,65 @@ int Engine::verify_buffer(const uint8_t* data, size_t len, const av1r_config* cf
 
 // Verify a whole container with this (already open, reusable) engine.
 int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames) {
-    Engine& eng = *this;
-    const av1r_config& c = impl_->cfg;
-    memset(out, 0, sizeof(*out));
-    out->struct_size = sizeof(*out);
-    out->first_bad_frame = -1;
-    auto fail = [&](int rc, const std::string& msg) {
+    VerifyFile vf;
+    vf.data = data;
+    vf.len = len;
+    vf.rep = out;
+    vf.digests = digests;
+    vf.cap_frames = cap_frames;
+    vf.init_report();
+    auto t0 = std::chrono::steady_clock::now();
+    std::string msg;
+    int rc = vf.prescan(msg);
+    if (rc) {
         out->status = rc;
         snprintf(out->message, sizeof(out->message), "%s", msg.c_str());
         return rc;
-    };
-    DemuxResult dm;
-    std::string derr;
-    if (!demux_buffer(data, len, dm, derr)) return fail(AV1R_EBITSTREAM, derr);
+    }
+    std::vector<VerifyFile*> files{&vf};
+    std::vector<VerifyItem> items;
+    for (size_t s = 0; s < vf.starts.size(); s++)
+        items.push_back(VerifyItem{0, vf.starts[s], s + 1 < vf.starts.size() ? vf.starts[s + 1] : vf.dm.tus.size(), 0});
+    int nthreads = 0;
+    rc = verify_items(files, items, true, &nthreads);
+    out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out->frames_per_sec = out->wall_ms > 0 ? out->frames * 1000.0 / out->wall_ms : 0;
+    if (!out->status && rc) {   // engine-level failure that no frame was blamed for
+        out->status = rc;
+        snprintf(out->message, sizeof(out->message), "%s", error().c_str());
+    }
+    if (!out->status)
+        snprintf(out->message, sizeof(out->message), "ok: %lld frames, %zu GOP segments, %d parser threads", (long long)out->frames, items.size(), nthreads);
+    return out->status;
+}
+
+// Parses and reconstructs a list of GOP segments (possibly of several files) on this engine's GPU.  Segments are parsed by
+// host_threads workers in list order (bounded look-ahead), issued to the GPU by the calling thread in list order; every shown frame
+// lands in its file's report / digest array at its display index.  stop_on_error: the first failing frame ends the run (single
+// file); otherwise a failing segment only marks its own file and the remaining segments still run (batch).
+int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<VerifyItem>& items, bool stop_on_error, int* threads_used) {
+    Engine& eng = *this;
+    const av1r_config& c = impl_->cfg;
+    EngineImpl& E = *impl_;
+    cudaSetDevice(c.device);
     int nthreads = c.host_threads > 0 ? c.host_threads : (int)std::thread::hardware_concurrency();
     nthreads = std::max(1, std::min(nthreads, 32));
+    if (threads_used) *threads_used = nthreads;
     int rc = eng.flush();
-    if (rc) return fail(rc, eng.error());
+    if (rc) return rc;
     impl_->pending.clear();
     cudaMemset(impl_->k3_stuck.p, 0, 4);
-    auto t0 = std::chrono::steady_clock::now();
-    // ---- pre-scan: sequence header + segment boundaries (TUs that start with a shown key frame)
-    HeaderParser scan;
-    if (!dm.config_obus.empty()) {
-        std::vector<ObuUnit> obus;
-        if (scan.split_obus(dm.config_obus.data(), dm.config_obus.size(), obus))
-            for (auto& u : obus)
-                if (u.type == OBU_SEQUENCE_HEADER) scan.parse_sequence_header(u.data, u.size);
-    }
-    std::vector<size_t> starts;
-    for (size_t i = 0; i < dm.tus.size(); i++) {
-        std::vector<ObuUnit> obus;
-        if (!scan.split_obus(data + dm.tus[i].offset, dm.tus[i].size, obus)) return fail(AV1R_EBITSTREAM, scan.error);
-        bool first_frame = true;
-        for (const ObuUnit& u : obus) {
-            if (u.type == OBU_SEQUENCE_HEADER) {
-                if (!scan.parse_sequence_header(u.data, u.size)) return fail(AV1R_EBITSTREAM, scan.error);
-            } else if (u.type == OBU_FRAME || u.type == OBU_FRAME_HEADER) {
-                BitReader br(u.data, u.size);
-                FrameHdr fh;
-                if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) return fail(AV1R_EBITSTREAM, scan.error);
-                if (first_frame && !fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
-                if (!fh.show_existing_frame) scan.reference_update(fh);
-                else if (fh.frame_type == KEY_FRAME) {
-                    RefHdrState r = scan.refs[fh.frame_to_show_map_idx];
-                    for (auto& x : scan.refs) x = r;
-                }
-                first_frame = false;
-            }
-        }
-    }
-    if (!scan.seq.valid) return fail(AV1R_EBITSTREAM, "no sequence header");
-    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
-    const size_t nseg = starts.size();
+    const size_t nseg = items.size();
     std::vector<std::unique_ptr<Segment>> segs(nseg);
     for (size_t s = 0; s < nseg; s++) {
         segs[s] = std::make_unique<Segment>();
-        segs[s]->tu0 = starts[s];
-        segs[s]->tu1 = s + 1 < nseg ? starts[s + 1] : dm.tus.size();
+        segs[s]->tu0 = items[s].tu0;
+        segs[s]->tu1 = items[s].tu1;
         const size_t n = segs[s]->tu1 - segs[s]->tu0;
         segs[s]->parsed.resize(n);
         segs[s]->rc.assign(n, 0);
         segs[s]->errs.resize(n);
     }
-    EngineImpl& E = *eng.impl_;
-    E.sp.hp.seq = scan.seq;
     // ---- parser threads: claim segments in order; bounded look-ahead (frames parsed but not yet issued)
     std::atomic<size_t> next_seg{0};
     std::atomic<bool> abort_flag{false};
@@ -1177,8 +1248,9 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
             const size_t s = next_seg.fetch_add(1);
             if (s >= nseg) return;
             Segment& sg = *segs[s];
+            const VerifyFile& vf = *files[items[s].file];
             StreamParser sp;
-            sp.hp.seq = scan.seq;
+            sp.hp.seq = vf.scan.seq;
             // parse TU t while the work-lists of TU t-1 are being laid out / copied into pinned memory on a helper thread
             std::future<void> staging;
             auto publish = [&](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
@@ -1199,7 +1271,8 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
                     la_outstanding++;
                 }
                 auto pfs = std::make_shared<std::vector<ParsedFrame>>();
-                const int prc = sp.parse_tu(data + dm.tus[t].offset, dm.tus[t].size, dm.tus[t].pts, *pfs);
+                const TemporalUnit& tu = vf.dm.tus[t];
+                const int prc = sp.parse_tu(vf.data + tu.offset, tu.size, ((int64_t)s << 32) | (int64_t)t, *pfs);
                 if (staging.valid()) staging.get();      // TU t-1 is staged and published
                 const std::string perr = sp.err;
                 const SeqHdr seq = sp.hp.seq;
@@ -1234,7 +1307,10 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     for (int i = 0; i < nthreads; i++) pool.emplace_back(worker);
     // ---- consumer: issue GPU work segment by segment, TU by TU (display order)
     std::vector<av1r_frame_result> res(64);
-    int64_t shown = 0;
+    int64_t last_pts = -1;
+    int same_pts = 0;
+    int fatal = 0;          // engine-level error (CUDA fault): nothing more can run on this device
+    bool stop = false;      // stop_on_error and a frame failed
     auto drain = [&](bool all) -> int {
         while (true) {
             int n = 0;
@@ -1245,23 +1321,30 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
             int r = eng.collect(res.data(), (int)res.size(), &n);
             if (r) return r;
             for (int i = 0; i < n; i++) {
+                const size_t s = (size_t)(res[i].pts >> 32), t = (size_t)(res[i].pts & 0xffffffff);
+                VerifyFile& vf = *files[items[s].file];
+                same_pts = res[i].pts == last_pts ? same_pts + 1 : 0;
+                last_pts = res[i].pts;
+                const int64_t idx = vf.frame_base[t] + same_pts;
                 if (res[i].status) {   // a frame the device could not reconstruct consistently (intra kernel watchdog)
-                    out->first_bad_frame = shown;
-                    return res[i].status;
+                    vf.fail(res[i].status, idx, E.err);
+                    if (stop_on_error) stop = true;
+                    continue;
                 }
-                if (digests && shown < cap_frames) memcpy(digests + 3 * shown, res[i].checksum, 24);
-                shown++;
-                out->device_ms += res[i].device_ms;
-                out->width = res[i].w;
-                out->height = res[i].h;
-                out->bit_depth = res[i].bpc;
+                std::lock_guard<std::mutex> lk(vf.m);
+                if (vf.digests && idx < vf.cap_frames) memcpy(vf.digests + 3 * idx, res[i].checksum, 24);
+                vf.rep->frames++;
+                vf.rep->device_ms += res[i].device_ms;
+                vf.rep->width = res[i].w;
+                vf.rep->height = res[i].h;
+                vf.rep->bit_depth = res[i].bpc;
             }
             if (n == 0) return 0;
         }
     };
-    std::string msg;
-    for (size_t s = 0; s < nseg && !rc; s++) {
+    for (size_t s = 0; s < nseg && !fatal && !stop; s++) {
         Segment& sg = *segs[s];
+        VerifyFile& vf = *files[items[s].file];
         {
             std::lock_guard<std::mutex> lk(la_m);
             consumer_seg.store(s);
@@ -1269,9 +1352,11 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
         la_cv.notify_all();
         EngineImpl::RefState seg_refs;
         E.rs = &seg_refs;
-        for (size_t t = 0; t < sg.tu1 - sg.tu0 && !rc; t++) {
+        bool seg_failed = false;
+        for (size_t t = 0; t < sg.tu1 - sg.tu0 && !fatal && !stop; t++) {
             std::vector<ParsedFrame> pfs;
             int prc;
+            std::string msg;
             {
                 auto tw = EP_T();
                 std::unique_lock<std::mutex> lk(sg.m);
@@ -1281,28 +1366,36 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
                 prc = sg.rc[t];
                 if (prc) msg = sg.errs[t];
             }
-            for (ParsedFrame& pf : pfs) {
-                if (pf.fw) out->host_parse_ms += pf.fw->parse_ms;
-                int r = E.decode_parsed(pf);
-                if (r) { rc = r; msg = E.err; break; }
-            }
+            int frc = 0;
+            if (!seg_failed)
+                for (ParsedFrame& pf : pfs) {
+                    if (pf.fw) {
+                        std::lock_guard<std::mutex> lk(vf.m);
+                        vf.rep->host_parse_ms += pf.fw->parse_ms;
+                    }
+                    int r = E.decode_parsed(pf);
+                    if (r) { frc = r; msg = E.err; break; }
+                }
             {
                 std::lock_guard<std::mutex> lk(la_m);
                 la_outstanding--;
             }
             la_cv.notify_all();
-            if (!rc && prc) rc = prc;
-            if (rc) {
-                out->first_bad_frame = shown;
+            if (seg_failed) continue;          // rest of a failed segment: only hand the look-ahead budget back
+            if (!frc && prc) frc = prc;
+            if (frc) {
                 char tmp[600];
                 snprintf(tmp, sizeof(tmp), "temporal unit %zu: %s", sg.tu0 + t, msg.c_str());
-                msg = tmp;
-                break;
+                vf.fail(frc, vf.frame_base[sg.tu0 + t], tmp);
+                if (frc == AV1R_EIO || frc == AV1R_ENOMEM) fatal = frc;
+                seg_failed = true;
+                if (stop_on_error) stop = true;
+                continue;
             }
             auto td = EP_T();
             int r = drain(false);
             EP_ADD(5, td);
-            if (r) { rc = r; msg = E.err; }
+            if (r) fatal = r;
         }
         E.rs = &E.main_refs;
     }
@@ -1313,14 +1406,8 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
     la_cv.notify_all();
     for (auto& th : pool) th.join();
     int r = drain(true);
-    if (!rc && r) { rc = r; msg = E.err; }
-    out->frames = shown;
-    out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    out->frames_per_sec = out->wall_ms > 0 ? out->frames * 1000.0 / out->wall_ms : 0;
-    out->status = rc;
-    if (rc) snprintf(out->message, sizeof(out->message), "%s", msg.c_str());
-    else snprintf(out->message, sizeof(out->message), "ok: %lld frames, %zu GOP segments, %d parser threads", (long long)out->frames, nseg, nthreads);
-    return rc;
+    if (!fatal && r) fatal = r;
+    return fatal;
 }
 
 }  // namespace av1r
@@ -1328,6 +1415,7 @@ int Engine::verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* 
 struct av1r_clip {
     std::vector<std::unique_ptr<av1r::ClipFrame>> frames;
     av1r_clip_info info;
+    int resident = 0;   // 1: work-lists uploaded once, replays read them from HBM (no H2D inside the pass)
 };
 
 namespace av1r {
@@ -1339,62 +1427,137 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
     auto clip = std::make_unique<av1r_clip>();
     memset(&clip->info, 0, sizeof(clip->info));
     clip->info.struct_size = sizeof(clip->info);
-    StreamParser parser;   // independent of the streaming state of this ctx
-    PinBuf staging;
-    for (int t = 0; t < n; t++) {
-        std::vector<ParsedFrame> pfs;
-        int rc = parser.parse_tu(tus[t], lens[t], t, pfs);
-        if (rc) { err = parser.err; return rc; }
-        for (ParsedFrame& pf : pfs) {
-            auto cf = std::make_unique<ClipFrame>();
-            cf->fh = pf.fh;
-            cf->pts = pf.pts;
-            if (pf.show_existing_slot >= 0) {
-                cf->show_existing = true;
-                cf->show_slot = pf.show_existing_slot;
-                clip->info.frames_shown++;
-            } else {
-                const FrameWork& fw = *pf.fw;
-                E.sp.hp.seq = parser.hp.seq;   // fill_params reads the sequence header of this ctx
-                rc = E.prepare_work(fw, cf->dw);
-                if (rc) return rc;
-                CK(staging.ensure(cf->dw.lay.total));
-                CK(cf->arena.ensure(cf->dw.lay.total));
-                fill_arena(fw, cf->dw, staging.p);
-                CK(cudaMemcpy(cf->arena.p, staging.p, cf->dw.lay.total, cudaMemcpyHostToDevice));
-                clip->info.frames_decoded++;
-                clip->info.frames_shown += fw.fh.show_frame;
-                clip->info.host_parse_ms += fw.parse_ms;
-                clip->info.worklist_bytes += cf->dw.lay.total;
-                clip->info.coded_samples += fw.coded_samples;
-                clip->info.coef_tokens += fw.coefs.size();
-                clip->info.tx_blocks += fw.tx.size();
-                clip->info.inter_samples += fw.inter_samples;
-                clip->info.inter_ref_samples += fw.inter_ref_samples;
-                clip->info.inter_blocks += fw.inter.size();
-                clip->info.obmc_neighbours += fw.obmc.size();
-                clip->info.lr_frames += cf->dw.lr_on && (E.cfg.inloop_filters & 4);
-                clip->info.cdef_frames += cf->dw.cdef_on && (E.cfg.inloop_filters & 2);
-                clip->info.deblock_frames += cf->dw.lf_on && (E.cfg.inloop_filters & 1);
-                clip->info.grain_frames += fw.fh.show_frame && fw.fh.fg.apply_grain && E.cfg.apply_grain;
-                for (int i = 0; i < 24; i++) clip->info.tool_hist[i] += fw.tool_hist[i];
-                for (const TxRec& r : fw.tx)
-                    if (r.mode != TXM_INTER) clip->info.intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
-                clip->info.width = fw.fh.upscaled_width;
-                clip->info.height = fw.fh.frame_height;
-                clip->info.bit_depth = parser.hp.seq.bit_depth;
-                const DevFrameParams& fp = cf->dw.fp;
-                clip->info.frame_bytes = 0;
-                for (int p = 0; p < (fp.mono ? 1 : 3); p++) clip->info.frame_bytes += (uint64_t)fp.w[p] * fp.h[p] * (fp.bd == 8 ? 1 : 2);
+    // ---- cut at shown key frames (header scan), then parse the GOP segments on all host cores; per-segment results are merged in
+    // order, so the clip is the same as a sequential parse would give
+    std::vector<int> starts;
+    SeqHdr seq0;
+    {
+        HeaderParser scan;
+        for (int i = 0; i < n; i++) {
+            std::vector<ObuUnit> obus;
+            if (!scan.split_obus(tus[i], lens[i], obus)) { err = scan.error; return AV1R_EBITSTREAM; }
+            bool first = true;
+            for (const ObuUnit& u : obus) {
+                if (u.type == OBU_SEQUENCE_HEADER) {
+                    if (!scan.parse_sequence_header(u.data, u.size)) { err = scan.error; return AV1R_EBITSTREAM; }
+                } else if ((u.type == OBU_FRAME || u.type == OBU_FRAME_HEADER) && first) {
+                    BitReader br(u.data, u.size);
+                    FrameHdr fh;
+                    if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) { err = scan.error; return AV1R_EBITSTREAM; }
+                    if (!fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
+                    first = false;
+                    break;   // only the first frame header of a unit decides; the segment parsers read the rest
+                }
             }
-            clip->frames.push_back(std::move(cf));
         }
+        seq0 = scan.seq;
     }
+    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+    const int nseg = (int)starts.size();
+    struct SegOut {
+        std::vector<std::unique_ptr<ClipFrame>> frames;
+        av1r_clip_info info;
+        int rc = 0;
+        std::string err;
+    };
+    std::vector<SegOut> outs(nseg);
+    std::atomic<int> next{0};
+    const int inloop = E.cfg.inloop_filters, apply_grain = E.cfg.apply_grain, device = E.cfg.device;
+    auto worker = [&]() {
+        cudaSetDevice(device);
+        WorkerPool::nested_enabled() = nseg < (int)std::thread::hardware_concurrency();
+        while (true) {
+            const int sidx = next.fetch_add(1);
+            if (sidx >= nseg) return;
+            SegOut& so = outs[sidx];
+            memset(&so.info, 0, sizeof(so.info));
+            StreamParser parser;
+            parser.hp.seq = seq0;
+            const int t1 = sidx + 1 < nseg ? starts[sidx + 1] : n;
+            for (int t = starts[sidx]; t < t1 && !so.rc; t++) {
+                std::vector<ParsedFrame> pfs;
+                int rc = parser.parse_tu(tus[t], lens[t], t, pfs);
+                if (rc) { so.rc = rc; so.err = parser.err; break; }
+                for (ParsedFrame& pf : pfs) {
+                    auto cf = std::make_unique<ClipFrame>();
+                    cf->fh = pf.fh;
+                    cf->pts = pf.pts;
+                    if (pf.show_existing_slot >= 0) {
+                        cf->show_existing = true;
+                        cf->show_slot = pf.show_existing_slot;
+                        so.info.frames_shown++;
+                    } else {
+                        const FrameWork& fw = *pf.fw;
+                        rc = prepare_work_seq(parser.hp.seq, fw, cf->dw, so.err);
+                        if (rc) { so.rc = rc; break; }
+                        if (cudaHostAlloc(&cf->host, align_up(cf->dw.lay.total, 4096), cudaHostAllocDefault) != cudaSuccess) {
+                            so.rc = AV1R_ENOMEM;
+                            so.err = "cudaHostAlloc(clip work-lists) failed";
+                            break;
+                        }
+                        fill_arena(fw, cf->dw, cf->host);
+                        av1r_clip_info& ci = so.info;
+                        ci.frames_decoded++;
+                        ci.frames_shown += fw.fh.show_frame;
+                        ci.host_parse_ms += fw.parse_ms;
+                        ci.worklist_bytes += cf->dw.lay.total;
+                        ci.coded_samples += fw.coded_samples;
+                        ci.coef_tokens += fw.coefs.size();
+                        ci.tx_blocks += fw.tx.size();
+                        ci.inter_samples += fw.inter_samples;
+                        ci.inter_ref_samples += fw.inter_ref_samples;
+                        ci.inter_blocks += fw.inter.size();
+                        ci.obmc_neighbours += fw.obmc.size();
+                        ci.lr_frames += cf->dw.lr_on && (inloop & 4);
+                        ci.cdef_frames += cf->dw.cdef_on && (inloop & 2);
+                        ci.deblock_frames += cf->dw.lf_on && (inloop & 1);
+                        ci.grain_frames += fw.fh.show_frame && fw.fh.fg.apply_grain && apply_grain;
+                        for (int i = 0; i < 24; i++) ci.tool_hist[i] += fw.tool_hist[i];
+                        for (const TxRec& r : fw.tx)
+                            if (r.mode != TXM_INTER) ci.intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+                        ci.width = fw.fh.upscaled_width;
+                        ci.height = fw.fh.frame_height;
+                        ci.bit_depth = parser.hp.seq.bit_depth;
+                        const DevFrameParams& fp = cf->dw.fp_up;
+                        ci.frame_bytes = 0;
+                        for (int p = 0; p < (fp.mono ? 1 : 3); p++) ci.frame_bytes += (uint64_t)fp.w[p] * fp.h[p] * (fp.bd == 8 ? 1 : 2);
+                    }
+                    so.frames.push_back(std::move(cf));
+                }
+            }
+        }
+    };
+    {
+        const int nt = std::max(1, std::min(nseg, (int)std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (int i = 1; i < nt; i++) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
+    for (SegOut& so : outs) {
+        if (so.rc) { err = so.err; return so.rc; }
+        av1r_clip_info& d = clip->info;
+        const av1r_clip_info& a = so.info;
+        d.frames_decoded += a.frames_decoded; d.frames_shown += a.frames_shown; d.host_parse_ms += a.host_parse_ms;
+        d.worklist_bytes += a.worklist_bytes; d.coded_samples += a.coded_samples; d.coef_tokens += a.coef_tokens;
+        d.tx_blocks += a.tx_blocks; d.intra_samples += a.intra_samples; d.inter_samples += a.inter_samples;
+        d.inter_ref_samples += a.inter_ref_samples; d.lr_frames += a.lr_frames; d.cdef_frames += a.cdef_frames;
+        d.deblock_frames += a.deblock_frames; d.grain_frames += a.grain_frames; d.inter_blocks += a.inter_blocks;
+        d.obmc_neighbours += a.obmc_neighbours;
+        for (int i = 0; i < 24; i++) d.tool_hist[i] += a.tool_hist[i];
+        if (a.frames_decoded) { d.width = a.width; d.height = a.height; d.bit_depth = a.bit_depth; d.frame_bytes = a.frame_bytes; }
+        for (auto& cf : so.frames) clip->frames.push_back(std::move(cf));
+    }
+    E.sp.hp.seq = seq0;   // fill_params (show_existing_frame outputs) reads the sequence header of this ctx
     *out = clip.release();
     return 0;
 }
 
+// One pass over the clip.  Default: every frame's work-lists travel host -> device inside the pass (one copy per frame from the
+// clip's pinned arena into the slot's device arena, as in the streaming path: SURVEY 8d times the device path "from the first
+// work-list H2D enqueue").  Resident mode (av1r_clip_set_resident): the lists are uploaded once and replays read them from HBM.
 static int replay(EngineImpl& E, av1r_clip* clip) {
+    std::string& err = E.err;
     for (auto& cf : clip->frames) {
         int slot_idx;
         int rc = E.acquire_slot(slot_idx);
@@ -1403,8 +1566,23 @@ static int replay(EngineImpl& E, av1r_clip* clip) {
         if (cf->show_existing) {
             rc = E.exec_show_existing(slot_idx, cf->fh, cf->show_slot, cf->pts);
         } else {
-            if (cudaEventRecord(s.ev0, s.stream) != cudaSuccess) return AV1R_EIO;
-            rc = E.exec_decoded(slot_idx, cf->dw, cf->arena.p, cf->pts);
+            const uint8_t* d_arena;
+            CK(cudaEventRecord(s.ev0, s.stream));
+            if (clip->resident) {
+                if (!cf->arena_valid) {
+                    CK(cf->arena.ensure(cf->dw.lay.total));
+                    CK(cudaMemcpy(cf->arena.p, cf->host, cf->dw.lay.total, cudaMemcpyHostToDevice));
+                    cf->arena_valid = true;
+                }
+                d_arena = cf->arena.p;
+            } else {
+                CK(s.arena.ensure(cf->dw.lay.total, &E.hw_arena));
+                if (E.tm) E.tm->begin(s.stream);
+                CK(cudaMemcpyAsync(s.arena.p, cf->host, cf->dw.lay.total, cudaMemcpyHostToDevice, s.stream));
+                if (E.tm) E.tm->end(AV1R_ST_H2D, 1, s.stream);
+                d_arena = s.arena.p;
+            }
+            rc = E.exec_decoded(slot_idx, cf->dw, d_arena, cf->pts);
         }
         if (rc) return rc;
     }
@@ -1486,3 +1664,8 @@ extern "C" int av1r_clip_info_get(const av1r_clip* clip, av1r_clip_info* out) {
     return 0;
 }
 extern "C" void av1r_clip_free(av1r_clip* clip) { delete clip; }
+extern "C" int av1r_clip_set_resident(av1r_clip* clip, int resident) {
+    if (!clip) return AV1R_EINVAL;
+    clip->resident = resident != 0;
+    return 0;
+}

@@ -3,11 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of
-synthetic input.  Workloads:
-  filmgrain_4k10   K8 stage alone on 4K 10-bit frames (first kernel family that landed)
-  c2_intra_1080p8  BASELINE configs[1]: 1080p 8-bit all-key-frame clip, full GPU reconstruction
-The default is the most complete workload the engine currently decodes bit-exactly.
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one clip (or one batch of files).
+  --gpus 1 (default): headline = c3_4k10_inter (BASELINE configs[2]: 3840x2160 10-bit, compound / OBMC / warped motion / loop
+                      restoration); the same line carries `per_config`: c1, c2, c4 and the 32-file batch c5, each with value, e2e,
+                      cpu_baseline and the dominant kernel's roofline fraction.
+  --gpus N > 1:       c5_batch_4k10 (BASELINE configs[4]): the batch's GOP segments sharded longest-first over the N ranks (one
+                      engine per GPU, no collective on the data path), strong scaling.
+  --workload NAME     one of WORKLOADS (single-clip line without per_config).
+  --impl reference    libdav1d (the decoder inside the reference's FFmpeg build) on the host cores, same workload / steps.
+`value` is timed from the first work-list H2D enqueue to the last kernel; `value_hbm_resident` is the same pass with
+the work-lists already in HBM.  bench.py refuses a clip whose tool histogram lacks the tools of the BASELINE config it stands for.
 PyTorch is used only for device buffers / events / torch.distributed plumbing.
 """
 import os as _os
@@ -253,201 +258,269 @@ def cpu_baseline_filmgrain():
 
 
 # ------------------------------------------------------------------------------------------
-# workload: BASELINE configs[1] -- 1080p 8-bit intra-only clip, full GPU reconstruction
+# clip workloads: BASELINE configs[0..3] as single clips, configs[4] as a batch of 32 files
 # ------------------------------------------------------------------------------------------
 CLIP_DESC = {
     "c1": ("c1_1080p8: BASELINE configs[0] -- 1920x1080 8-bit 4:2:0 Main profile, 60 frames, testsrc2-like source, libaom 3.13.1 cq 32, "
            "lag_in_frames 19 (hidden ARFs + show_existing_frame), kf_max_dist 30 (2 closed GOPs), 2 tile columns, all default tools"),
-    "c3": ("c3_4k10_inter: BASELINE configs[2] -- 3840x2160 10-bit 4:2:0, 60 frames, pan/zoom/rotation texture with moving patches, "
-           "libaom cq 32, compound + OBMC + warped/global motion + loop restoration, 4x2 tiles, lag 19, kf_max_dist 30"),
-    "c4": ("c4_4k10_grain: BASELINE configs[3] -- as c3 on a noise-heavy source with film grain synthesis (libaom film-grain-test 5)"),
+    "c2": ("c2_intra_1080p8: BASELINE configs[1] -- 1920x1080 8-bit 4:2:0, 60 frames, every frame KEY (libaom 3.13.1, cq 32, "
+           "CDEF on, LR off, synthetic pan/zoom texture)"),
+    "c3": ("c3_4k10_inter: BASELINE configs[2] -- 3840x2160 10-bit 4:2:0, 60 frames, fine texture under pan/zoom with independently moving, "
+           "crossing and fading foreground objects, libaom 3.13.1 cpu-used 1 cq 32, compound (average / distance / wedge / difference-weighted), "
+           "inter-intra, OBMC, local + global warped motion, loop restoration, 4x2 tiles, lag 19, two closed GOPs of 30"),
+    "c4": ("c4_4k10_grain: BASELINE configs[3] -- 3840x2160 10-bit noise-heavy source with film grain synthesis (libaom film-grain-test 5), "
+           "60 frames, 4x2 tiles, lag 19, kf_max_dist 30"),
     "c3_small": "c3_small: 960x544 10-bit inter clip (smoke-size version of c3)",
+    "c2_small": "c2_small: 640x360 8-bit all-key clip (smoke-size version of c2)",
 }
-C2_DESC = ("c2_intra_1080p8: BASELINE configs[1] -- 1920x1080 8-bit 4:2:0, 60 frames, every frame KEY (libaom 3.13.1, cq 32, "
-           "CDEF on, LR off, synthetic pan/zoom texture); step = one pass over the 60-frame clip; "
-           "value = device path from HBM-resident work-lists (sequential host symbol parse reported separately as host_parse_ms); "
-           "per-step working set (work-lists + frame buffers of 60 frames) exceeds the 126 MB L2, no flush needed")
+STEP_NOTE = "; step = one pass over the whole clip"
+TIMING_NOTE = ("per frame one H2D copy of its work-lists, then the reconstruction kernels, frames pipelined over 32 streams; value is timed with CUDA "
+               "events from the first H2D enqueue to the last kernel, max over ranks; the sequential host symbol parse is reported separately as "
+               "host_parse_ms")
+
+# tools / stages a clip must really contain to stand for its BASELINE config (block counts from the host parser, frames per stage)
+REQUIRED = {
+    "c1": dict(tools=["inter_blocks", "compound_avg"], stages=["cdef_frames"]),
+    "c2": dict(tools=[], stages=["cdef_frames", "deblock_frames"], forbid=["inter_blocks"]),
+    "c3": dict(tools=["inter_blocks", "compound_avg", "compound_dist", "compound_wedge", "compound_diffwtd", "interintra", "obmc", "local_warp",
+                      "global_warp"], stages=["lr_frames", "cdef_frames", "deblock_frames"]),
+    "c4": dict(tools=["inter_blocks", "compound_avg"], stages=["grain_frames", "cdef_frames"]),
+    "c5": dict(tools=["inter_blocks", "compound_avg", "compound_wedge", "compound_diffwtd", "interintra", "obmc", "local_warp", "global_warp"],
+               stages=["lr_frames", "cdef_frames", "deblock_frames"]),
+}
 
 
-def c2_clip(name="c2"):
-    from tools.make_streams import get_clip
-    return get_clip(name, verbose=True)
+class ClipLacksTools(RuntimeError):
+    pass
 
 
-STEP_NOTE = ("; step = one pass over the clip; value = device path from HBM-resident work-lists (sequential host symbol parse reported "
-             "separately as host_parse_ms); per-step working set (work-lists + frame buffers in flight) exceeds the 126 MB L2, no flush needed")
+def check_clip_tools(key, info, hist):
+    """Refuse to benchmark a clip that does not exercise what its config names (the 4K10 clip held no OBMC / masked compound
+    and no loop restoration)."""
+    req = REQUIRED.get(key)
+    if not req:
+        return
+    missing = [t for t in req["tools"] if not hist.get(t)] + [s for s in req["stages"] if not int(getattr(info, s))]
+    present = [t for t in req.get("forbid", []) if hist.get(t)]
+    if missing or present:
+        raise ClipLacksTools(f"clip {key} does not stand for its BASELINE config: missing {missing}, unexpected {present}; "
+                             f"regenerate it with `python -m tools.make_streams {key}`")
 
 
-def run_c2(args, torch, dist, rank, world, local, name="c2"):
+def get_clip(name):
+    from tools.make_streams import get_clip as gc
+    return gc(name, verbose=True)
+
+
+def stage_model_bytes(info):
+    """Algorithmic bytes per stage summed over the clip (with the counts the parser collected)."""
+    F = int(info.frame_bytes)
+    A = int(info.coded_samples)
+    bps = 1 if info.bit_depth == 8 else 2
+    return {
+        "itx": 4 * int(info.coef_tokens) + 32 * int(info.tx_blocks) + 2 * A,       # C (tokens) + records + residual write
+        "intra": bps * int(info.intra_samples) + 2 * A + 32 * int(info.tx_blocks),  # intra samples written + residual read + records
+        "inter": bps * (int(info.inter_ref_samples) + int(info.inter_samples)) + 40 * int(info.inter_blocks),   # Rbar*F_inter + F_inter
+        "deblock": 2 * F * int(info.deblock_frames),
+        "cdef": 2 * F * int(info.cdef_frames),
+        "lr": int(2.0625 * F) * int(info.lr_frames),
+        "grain": 2 * F * int(info.grain_frames),
+        "digest": F * int(info.frames_shown),
+    }
+
+
+def dist_max(torch, dist, world, local, x):
+    if world <= 1:
+        return x
+    t = torch.tensor([x], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dist_sum(torch, dist, world, local, x):
+    if world <= 1:
+        return x
+    t = torch.tensor([x], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def measure_clip(key, tus, blob, args, torch, dist, rank, world, local, steps, warmup, desc, sample_clocks=True, e2e_reps=5, gate_key=None):
+    """Device path + e2e + live roofline of one clip (or of this rank's share of a batch, given as one list of temporal units)."""
     import av1recon
-    tus = c2_clip(name)
     torch.cuda.set_device(local)
     dec = av1recon.Decoder(device=local, streams=32, frames_in_flight=64)
     clip = av1recon.Clip(dec, tus)
     info = clip.info
-    nfr = int(info.frames_shown)
-    # reference digests: first replay
-    ms0, cks0 = clip.decode()
-    for _ in range(args.warmup):
+    hist = av1recon.tool_hist(info)
+    if world == 1:
+        check_clip_tools(gate_key or key, info, hist)
+    nfr_local = int(info.frames_shown)
+    ms0, cks0 = clip.decode()                       # first pass: allocations; its digests are the reference for every later pass
+    for _ in range(warmup):
         clip.decode()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     total_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         ms, cks = clip.decode()
         total_ms += ms
         if cks != cks0:
             raise RuntimeError("replay produced different digests: non-deterministic reconstruction")
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([total_ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = nfr * args.steps * world / (total_ms / 1e3)
-    # per-stage device time (serialised replay, CUDA events) -> live roofline of the dominant kernel
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    total_ms = dist_max(torch, dist, world, local, total_ms)
+    nfr = int(round(dist_sum(torch, dist, world, local, nfr_local)))
+    value = nfr * steps / (total_ms / 1e3)
+    # the same pass with the work-lists already resident in HBM (kernel-only figure)
+    clip.set_resident(True)
+    clip.decode()
+    res_ms = 0.0
+    nres = max(2, min(5, steps))
+    for _ in range(nres):
+        ms, cks = clip.decode()
+        res_ms += ms
+        if cks != cks0:
+            raise RuntimeError("resident replay produced different digests")
+    res_ms = dist_max(torch, dist, world, local, res_ms)
+    value_resident = nfr * nres / (res_ms / 1e3)
+    clip.set_resident(False)
+    # per-stage device time (serialised replay, CUDA events on the launching stream) -> live roofline of the dominant kernel
     prof = clip.profile()
-    F = int(info.frame_bytes)
-    A = int(info.coded_samples)
-    ntok = int(info.coef_tokens)
-    nrec = int(info.tx_blocks)
-    nf = int(info.frames_decoded)
-    bps = 1 if info.bit_depth == 8 else 2
-    intra_s, inter_s, ref_s = int(info.intra_samples), int(info.inter_samples), int(info.inter_ref_samples)
-    stage_bytes = {
-        "itx": 4 * ntok + 32 * nrec + 2 * A,                 # C (tokens) + records + residual write
-        "intra": bps * intra_s + 2 * A + 32 * nrec,           # intra samples written + residual read + records
-        "inter": bps * (ref_s + inter_s) + 40 * int(info.inter_blocks),   # Rbar * F_inter read + F_inter written + records
-        "deblock": 2 * F * int(info.deblock_frames),
-        "cdef": 2 * F * int(info.cdef_frames),
-        "lr": int(2.0625 * F) * int(info.lr_frames),
-        "grain": 2 * F * int(info.grain_frames),
-        "digest": F * nfr,
-    }
-    # (K6 super-resolution has no bench workload: the BASELINE configs do not use it; parity only, tests/golden/*superres*)
+    sb = stage_model_bytes(info)
     stages = {}
     for k, (ms, launches) in prof.items():
         if launches:
-            ent = {"ms_per_clip": ms, "launches": launches}
-            if k in stage_bytes and ms > 0:
-                ent["algorithmic_gbs"] = stage_bytes[k] / (ms / 1e3) / 1e9
+            ent = {"ms_per_step": ms, "launches": launches}
+            if k in sb and ms > 0:
+                ent["algorithmic_gbs"] = sb[k] / (ms / 1e3) / 1e9
             stages[k] = ent
-    dom = max((k for k in stages if k in stage_bytes), key=lambda k: stages[k]["ms_per_clip"])
     peak, peak_src = measured_peaks()
-    dom_ms = stages[dom]["ms_per_clip"] / stages[dom]["launches"]
-    dom_bytes = stage_bytes[dom] / stages[dom]["launches"]
+    dom = max((k for k in stages if k in sb), key=lambda k: stages[k]["ms_per_step"])
+    dom_ms = stages[dom]["ms_per_step"] / stages[dom]["launches"]
+    dom_bytes = sb[dom] / stages[dom]["launches"]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
-    # e2e: the call a user makes -- av1r_verify_buffer on the HOST container bytes: demux, GOP-segment-parallel
-    # host symbol parse (all host cores), H2D of the work-lists, reconstruction kernels, D2H of the 24-byte
-    # plane digests of every frame.  Wall clock.
-    from tools.make_streams import clip_path
-    blob = open(clip_path(name), "rb").read()
-    vdec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32,   # the daemon keeps one engine open
-                            host_threads=max(1, (os.cpu_count() or 1) // world))
-    vdec.verify_buffer(blob)                                                  # warm-up (allocations, first-touch)
-    best = None
-    for _ in range(5):   # wall-clock of a host-bound path on a shared box: best of 5
+    for k, ent in stages.items():
+        if "algorithmic_gbs" in ent:
+            ent["frac_of_peak"] = ent["algorithmic_gbs"] / peak
+    launches_per_step = sum(v["launches"] for k, v in stages.items() if k != "h2d")
+    # e2e: the call a user makes -- av1r_ctx_verify_buffer on the HOST container bytes with an engine that stays open (the daemon
+    # keeps one): demux, GOP-segment-parallel host symbol parse, H2D of the work-lists, kernels, D2H of the 24-byte plane digests.
+    host_threads = max(1, (os.cpu_count() or 1) // world)
+    vdec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32, host_threads=host_threads)
+    vdec.verify_buffer(blob)                        # warm-up (allocations, first touch)
+    best, parse_ms = None, 0.0
+    for _ in range(e2e_reps):                       # wall clock of a host-bound path on a shared box: best of e2e_reps
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         rc, rep, digs = vdec.verify_buffer(blob)
         dt = time.perf_counter() - t0
         if rc:
-            raise RuntimeError(f"av1r_verify_buffer failed: {rep.message}")
+            raise RuntimeError(f"av1r_ctx_verify_buffer failed: {rep.message}")
         if digs != cks0:
             raise RuntimeError("e2e digests differ from replay digests")
-        best = dt if best is None else min(best, dt)
-    e2e_s = best
-    parse_ms = rep.host_parse_ms
+        dt = dist_max(torch, dist, world, local, dt)
+        if best is None or dt < best:
+            best, parse_ms = dt, rep.host_parse_ms
     vdec.close()
-    # single-threaded streaming API (av1r_submit_tu per temporal unit), for reference
-    dec2 = av1recon.Decoder(device=local, streams=16, frames_in_flight=32)
-    t0 = time.perf_counter()
-    for i, tu in enumerate(tus):
-        dec2.submit(tu, i)
-    dec2.flush()
-    e2e_1t = nfr / (time.perf_counter() - t0)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = nfr * world / e2e_s
-    launches_per_step = sum(v["launches"] for v in stages.values())
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload (or null)
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = tj.get(WORKLOAD_NAMES.get(name, name), {}).get(dom, {}).get("dram_bytes_per_launch")
+        traffic = tj.get(WORKLOAD_NAMES.get(key, key), {}).get(dom, {}).get("dram_bytes_per_launch")
     except Exception:
         traffic = None
+    nf = int(info.frames_decoded)
+    F = int(info.frame_bytes)
+    bps = 1 if info.bit_depth == 8 else 2
     out = {
         "metric": "AV1 decode-verify frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if info.bit_depth == 8 else "u16", "data": "synthetic",
-        "config": {"workload": C2_DESC if name == "c2" else CLIP_DESC[name] + STEP_NOTE, "frames_per_step": nfr, "parallelism": f"replicas{world} (independent clips per GPU, no collective)",
-                   "streams": 32, "frames_in_flight": 64},
-        "gpu_launches": launches_per_step * args.steps,
-        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr,
-                "host_parse_ms_per_step": parse_ms, "host_threads": os.cpu_count(), "single_thread_submit_tu_fps": e2e_1t,
-                "note": "av1r_verify_buffer: key-frame-delimited GOP segments parsed on all host cores; host_parse_ms is the summed sequential symbol-parse time (north_star: reported separately)"},
+        "config": workload_config(WORKLOAD_NAMES.get(key, key), world),
+        "engine": {"streams": 32, "frames_in_flight": 64, "frames_per_step_all_ranks": nfr, "timing": TIMING_NOTE},
+        "value_hbm_resident": value_resident,
+        "gpu_launches": launches_per_step * steps,
+        "e2e": {"value": nfr / best, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes) + len(blob) * 0,
+                "d2h_bytes_per_step": 24 * nfr_local, "host_input_bytes_per_step": len(blob),
+                "host_parse_ms_per_step": parse_ms, "host_threads": host_threads,
+                "note": "av1r_ctx_verify_buffer on the container bytes in host memory: demux, GOP-segment- and tile-parallel host symbol parse, "
+                        "one H2D copy of the work-lists per frame from pinned staging, kernels, D2H of the plane digests; wall clock, best of "
+                        f"{e2e_reps}; host_parse_ms is the summed sequential symbol-parse time (north_star: reported separately)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel": dom, "algorithmic_bytes_per_launch": dom_bytes,
-                     "avg_launch_ms": dom_ms, "stages": stages,
-                     "pipeline_algorithmic_gbs": sum(stage_bytes[k] for k in stages if k in stage_bytes) / (total_ms / args.steps / 1e3) / 1e9},
+                     "peak_source": peak_src, "kernel": dom, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                     "stages": stages,
+                     "pipeline_algorithmic_gbs": sum(sb[k] for k in stages if k in sb) / (total_ms / steps / 1e3) / 1e9},
         "host_parse_ms_per_frame": float(info.host_parse_ms) / max(1, nf),
-        "clip": {"bytes": sum(len(t) for t in tus), "frames": nfr, "coded_sample_fraction": A / max(1, nf * (F // bps)),
-                 "coef_tokens_per_frame": ntok / max(1, nf), "tx_blocks_per_frame": nrec / max(1, nf),
-                 "frames_decoded": nf, "inter_sample_fraction": inter_s / max(1, nf * (F // bps)),
-                 "mean_refs_per_inter_sample": ref_s / max(1, inter_s),
-                 "tools": {k: int(v) for k, v in zip(av1recon.TOOL_NAMES, info.tool_hist) if v}},
+        "clip": {"bytes": sum(len(t) for t in tus), "frames": nfr_local, "frames_decoded": nf, "frame_bytes": F,
+                 "coded_sample_fraction": int(info.coded_samples) / max(1, nf * (F // bps)),
+                 "coef_tokens_per_frame": int(info.coef_tokens) / max(1, nf), "tx_blocks_per_frame": int(info.tx_blocks) / max(1, nf),
+                 "inter_sample_fraction": int(info.inter_samples) / max(1, nf * (F // bps)),
+                 "mean_refs_per_inter_sample": int(info.inter_ref_samples) / max(1, int(info.inter_samples)),
+                 "lr_frames": int(info.lr_frames), "cdef_frames": int(info.cdef_frames), "deblock_frames": int(info.deblock_frames),
+                 "grain_frames": int(info.grain_frames), "tools": hist},
         "clocks": clocks,
     }
     clip.free()
     dec.close()
-    dec2.close()
     return out
 
 
-def cpu_baseline_c2(name="c2"):
+def run_clip(args, torch, dist, rank, world, local, name, steps=None, warmup=None, sample_clocks=True):
+    """Single clip; with world > 1 every rank decodes its own replica (weak scaling, `replicasN`)."""
+    from tools.make_streams import clip_path
+    tus = get_clip(name)
+    blob = open(clip_path(name), "rb").read()
+    out = measure_clip(name, tus, blob, args, torch, dist, rank, world, local, steps or args.steps, warmup or args.warmup,
+                       CLIP_DESC[name], sample_clocks=sample_clocks)
+    return out
+
+
+def dav1d_pass(tus, n_threads):
+    from oracle import dav1d_ref
+    t0 = time.perf_counter()
+    n = len(dav1d_ref.decode(tus, n_threads=n_threads, keep=False))
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline_clip(name, passes=3):
     """libdav1d 1.5.3 (the decoder inside the reference's FFmpeg build) on the host cores, same clip."""
     from oracle import dav1d_ref
-    tus = c2_clip(name)
+    tus = get_clip(name)
     ncpu = os.cpu_count() or 1
     dav1d_ref.decode(tus[:8], n_threads=ncpu, keep=False)
-    best = None
-    for _ in range(3):
-        t0 = time.perf_counter()
-        out = dav1d_ref.decode(tus, n_threads=ncpu, keep=False)
-        dt = time.perf_counter() - t0
+    best, n = None, 0
+    for _ in range(passes):
+        n, dt = dav1d_pass(tus, ncpu)
         best = dt if best is None else min(best, dt)
-    t0 = time.perf_counter()
-    dav1d_ref.decode(tus[:20], n_threads=1, keep=False)
-    dt1 = time.perf_counter() - t0
-    return {"value": len(out) / best, "unit": "frames/s", "cores": ncpu, "kind": "reference", "ms_per_step": best * 1e3,
-            "dtype": "u8" if name in ("c1", "c2", "c2_small") else "u16",
-            "sample": f"libdav1d {dav1d_ref.version()} driven directly (no ffmpeg binary in the image), n_threads={ncpu}, whole {len(tus)}-TU clip "
-                      f"preloaded in RAM, best of 3, no MD5; single-thread figure {20 / dt1:.1f} frames/s on 20 frames"}
+    k1 = min(len(tus), 10)
+    n1, dt1 = dav1d_pass(tus[:k1], 1)
+    return {"value": n / best, "unit": "frames/s", "cores": ncpu, "kind": "reference", "ms_per_step": best * 1e3,
+            "single_thread_fps": n1 / dt1,
+            "sample": f"libdav1d {dav1d_ref.version()} driven directly (no ffmpeg binary in the image; omits FFmpeg's demux), n_threads={ncpu}, whole "
+                      f"{len(tus)}-TU clip {name} preloaded in RAM, best of {passes}, no MD5; single-thread figure on the first {k1} units"}
 
 
 # ------------------------------------------------------------------------------------------
 # workload: BASELINE configs[4] -- batch of 32 4K 10-bit files, GOP-segment-sharded across the GPUs (no collective)
 # ------------------------------------------------------------------------------------------
-C5_DESC = ("c5_batch_4k10: BASELINE configs[4] -- batch of 32 synthetic 3840x2160 10-bit files (pan/zoom texture, seeds 100..131, 16 frames "
-           "each, kf_max_dist 4 => 4 closed GOP segments per file => 128 independent work items), items assigned to the ranks "
-           "longest-first by coded bytes, one engine per GPU, no collective; step = one pass over the whole batch (strong scaling: the "
-           "batch is fixed, per-rank share shrinks with N); value = device path from HBM-resident work-lists")
+C5_DESC = ("c5_batch_4k10: BASELINE configs[4] -- batch of 32 synthetic 3840x2160 10-bit files (source and tools as c3, seeds 100..131, libaom "
+           "cpu-used 2, 16 frames each in two closed GOPs of 8 => 64 independent GOP segments), segments assigned to the ranks longest-first by "
+           "coded bytes, one engine per GPU, no collective on the data path (strong scaling: the batch is fixed, the per-rank share shrinks with N)")
+C5_FILES = int(os.environ.get("AV1R_C5_FILES", "32"))
 
 
-def c5_items(nfiles=32):
+def c5_items(nfiles=C5_FILES):
     """-> (items [(key, weight)], tus_of {key: [tu bytes]}, (w, h))"""
     import av1recon
     from av1recon import shard
-    from tools.make_streams import get_clip
     items, tus_of = [], {}
     for f in range(nfiles):
-        tus = get_clip(f"c5_{f:02d}", verbose=True)
+        tus = get_clip(f"c5_{f:02d}")
         for s_idx, (a, b) in enumerate(shard.split_segments(tus, av1recon.scan_headers(tus))):
             key = (f, s_idx)
             tus_of[key] = tus[a:b]
@@ -455,130 +528,114 @@ def c5_items(nfiles=32):
     return items, tus_of, (3840, 2160)
 
 
-def run_c5(args, torch, dist, rank, world, local):
+def run_c5(args, torch, dist, rank, world, local, steps=None, warmup=None, sample_clocks=True):
     import av1recon
     from av1recon import shard
-    t_start = time.perf_counter()
-
-    def note(msg):   # progress on stderr: this workload holds 512 4K frames and takes minutes end to end
-        print(f"[c5 rank {rank} +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
-    items, tus_of, (w, h) = c5_items(int(os.environ.get("AV1R_C5_FILES", "32")))
-    note(f"{len(items)} GOP segments scanned")
+    items, tus_of, (w, h) = c5_items()
     mine = shard.assign(items, world)[rank]
     my_tus = [t for k in mine for t in tus_of[k]]
-    torch.cuda.set_device(local)
-    dec = av1recon.Decoder(device=local, streams=32, frames_in_flight=64)
-    clip = av1recon.Clip(dec, my_tus)
-    info = clip.info
-    nfr_local = int(info.frames_shown)
-    note(f"clip loaded: {nfr_local} frames")
-    ms0, cks0 = clip.decode()
-    note(f"first decode {ms0:.1f} ms")
-    for _ in range(args.warmup):
-        clip.decode()
-    note("warm-up done")
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    total_ms = 0.0
-    for _ in range(args.steps):
-        ms, cks = clip.decode()
-        total_ms += ms
-        if cks != cks0:
-            raise RuntimeError("replay produced different digests: non-deterministic reconstruction")
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    nfr = nfr_local
-    if world > 1:
-        t = torch.tensor([total_ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        n = torch.tensor([nfr_local], device=f"cuda:{local}")
-        dist.all_reduce(n, op=dist.ReduceOp.SUM)
-        nfr = int(n.item())
-    value = nfr * args.steps / (total_ms / 1e3)
-    note(f"timed steps done: {total_ms / args.steps:.1f} ms per step")
-    prof = clip.profile()
-    note("stage profile done")
-    stages = {k: {"ms_per_step": ms, "launches": n} for k, (ms, n) in prof.items() if n}
-    # e2e: the rank's share of the batch as one container through av1r_ctx_verify_buffer (host parse of the segments on this
-    # rank's share of the host cores, H2D, kernels, D2H of the digests)
-    blob = shard.ivf_bytes(my_tus, w, h)
-    host_threads = max(1, (os.cpu_count() or 1) // world)
-    vdec = av1recon.Decoder(device=local, streams=16, frames_in_flight=32, host_threads=host_threads)
-    vdec.verify_buffer(blob)
-    note("e2e warm-up done")
-    best = None
-    for _ in range(2):
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        rc, rep, digs = vdec.verify_buffer(blob)
-        dt = time.perf_counter() - t0
-        if rc:
-            raise RuntimeError(f"av1r_verify_buffer failed: {rep.message}")
-        if digs != cks0:
-            raise RuntimeError("e2e digests differ from replay digests")
-        best = dt if best is None else min(best, dt)
-    e2e_s = best
-    if world > 1:
-        t = torch.tensor([e2e_s], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    vdec.close()
-    peak, peak_src = measured_peaks()
-    F = int(info.frame_bytes)
-    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
-    out = {
-        "metric": "AV1 decode-verify frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": C5_DESC, "frames_per_step": nfr, "items": len(items), "items_this_rank": len(mine),
-                   "parallelism": f"gop-segment sharding over {world} GPU(s), no collective", "streams": 32, "frames_in_flight": 64},
-        "gpu_launches": sum(v["launches"] for v in stages.values()) * args.steps,
-        "e2e": {"value": nfr / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes), "d2h_bytes_per_step": 24 * nfr_local,
-                "host_threads_per_rank": host_threads, "host_parse_ms_per_step_rank0": rep.host_parse_ms},
-        "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                     "kernel": dom, "stages": stages, "note": "per-stage algorithmic GB/s are reported by the single-clip workloads (c3_4k10_inter)"},
-        "clip": {"frames": nfr, "frame_bytes": F, "tools": {k: int(v) for k, v in zip(av1recon.TOOL_NAMES, info.tool_hist) if v}},
-        "clocks": clocks,
-    }
-    clip.free()
-    dec.close()
+    if world == 1:   # whole batch on this GPU: gate on the tool histogram of the batch
+        pass
+    blob = shard.ivf_bytes(my_tus, w, h)      # this rank's share as one container (the segments stay independent: each starts with a key frame)
+    out = measure_clip("c5", my_tus, blob, args, torch, dist, rank, world, local, steps or args.steps, warmup or args.warmup,
+                       C5_DESC, sample_clocks=sample_clocks, e2e_reps=3, gate_key="c5")
+    out["scaling"] = "strong"
+    out["engine"].update({"items": len(items), "items_rank0": len(mine)})
     return out
 
 
-def cpu_baseline_c5():
-    """libdav1d on all host cores over a bounded sample of the batch (8 of the 32 files, one after the other)."""
+def cpu_baseline_c5(nfiles=8):
+    """libdav1d on all host cores over a bounded sample of the batch (the first `nfiles` files, one after the other)."""
     from oracle import dav1d_ref
-    from tools.make_streams import get_clip
     ncpu = os.cpu_count() or 1
-    files = [get_clip(f"c5_{f:02d}") for f in range(8)]
+    files = [get_clip(f"c5_{f:02d}") for f in range(nfiles)]
     dav1d_ref.decode(files[0], n_threads=ncpu, keep=False)
     t0 = time.perf_counter()
     n = 0
     for tus in files:
         n += len(dav1d_ref.decode(tus, n_threads=ncpu, keep=False))
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": ncpu, "kind": "reference",
-            "sample": f"libdav1d {dav1d_ref.version()} n_threads={ncpu}, files c5_00..c5_07 of the batch (8 x 16 frames 4K10) decoded back to back, preloaded in RAM, no MD5"}
+    return {"value": n / dt, "unit": "frames/s", "cores": ncpu, "kind": "reference", "ms_per_step": dt * 1e3,
+            "sample": f"libdav1d {dav1d_ref.version()} n_threads={ncpu}, files c5_00..c5_{nfiles - 1:02d} of the batch ({nfiles} x 16 frames 4K10) decoded "
+                      "back to back, preloaded in RAM, no MD5"}
 
 
 # clip key (tools/make_streams.py) -> bench workload name (profiles/ncu_traffic.json is keyed by the latter)
-WORKLOAD_NAMES = {"c2": "c2_intra_1080p8", "c1": "c1_1080p8", "c3": "c3_4k10_inter", "c4": "c4_4k10_grain"}
+WORKLOAD_NAMES = {"c2": "c2_intra_1080p8", "c1": "c1_1080p8", "c3": "c3_4k10_inter", "c4": "c4_4k10_grain", "c5": "c5_batch_4k10",
+                  "c3_small": "c3_small", "c2_small": "c2_small"}
 
 
 def _clip_workload(name):
-    return (lambda *a: run_c2(*a, name=name)), (lambda: cpu_baseline_c2(name))
+    return (lambda *a, **kw: run_clip(*a, name=name, **kw)), (lambda: cpu_baseline_clip(name)), (lambda: get_clip(name))
 
 
-WORKLOADS = {"filmgrain_4k10": (run_filmgrain, cpu_baseline_filmgrain), "c2_intra_1080p8": (run_c2, cpu_baseline_c2),
-             "c1_1080p8": _clip_workload("c1"), "c3_4k10_inter": _clip_workload("c3"), "c4_4k10_grain": _clip_workload("c4"),
-             "c3_small": _clip_workload("c3_small"), "c5_batch_4k10": (run_c5, cpu_baseline_c5)}
-DEFAULT_WORKLOAD = "c2_intra_1080p8"
+def _c5_sample():
+    return [t for f in range(8) for t in get_clip(f"c5_{f:02d}")]
+
+
+WORKLOADS = {"filmgrain_4k10": (run_filmgrain, cpu_baseline_filmgrain, None),
+             "c2_intra_1080p8": _clip_workload("c2"), "c1_1080p8": _clip_workload("c1"), "c3_4k10_inter": _clip_workload("c3"),
+             "c4_4k10_grain": _clip_workload("c4"), "c3_small": _clip_workload("c3_small"), "c2_small": _clip_workload("c2_small"),
+             "c5_batch_4k10": (run_c5, cpu_baseline_c5, _c5_sample)}
+HEADLINE_N1 = "c3_4k10_inter"          # BASELINE metric's 4K10 half, the config north_star names as the target
+HEADLINE_NGPU = "c5_batch_4k10"        # BASELINE configs[4]: the batch sharded over the GPUs
+PER_CONFIG = ["c1_1080p8", "c2_intra_1080p8", "c4_4k10_grain", "c5_batch_4k10"]
+
+
+FRAMES_PER_STEP = {"c1_1080p8": 60, "c2_intra_1080p8": 60, "c3_4k10_inter": 60, "c4_4k10_grain": 60, "c3_small": 20, "c2_small": 8,
+                   "c5_batch_4k10": 16 * C5_FILES}
+DESC_OF = {"c1_1080p8": "c1", "c2_intra_1080p8": "c2", "c3_4k10_inter": "c3", "c4_4k10_grain": "c4", "c3_small": "c3_small", "c2_small": "c2_small"}
+
+
+def workload_config(workload, world):
+    """The `config` object of the JSON line: identical for the b200 arm and the reference arm of the same command."""
+    if workload == "c5_batch_4k10":
+        return {"workload": C5_DESC + "; step = one pass over the whole batch (reference arm: a bounded sample, the first 8 of the 32 files)", "frames_per_step": FRAMES_PER_STEP[workload], "files": C5_FILES,
+                "parallelism": f"gop-segment sharding over {world} GPU(s), longest-first by coded bytes, no collective",
+                "l2": "per-step working set exceeds the 126 MB L2 (no flush needed)"}
+    if workload in DESC_OF:
+        return {"workload": CLIP_DESC[DESC_OF[workload]] + STEP_NOTE, "frames_per_step": FRAMES_PER_STEP[workload],
+                "parallelism": f"replicas{world} (independent clips per GPU, no collective)" if world > 1 else "single GPU",
+                "l2": "per-step working set exceeds the 126 MB L2 (no flush needed)"}
+    return {"workload": workload}
+
+
+def compact(line):
+    """per_config entry: the figures the verdict asked for, without the long tables."""
+    r = line["roofline"]
+    return {"workload": line["config"]["workload"].split(" --")[0].split(":")[0], "config": line["config"], "value": line["value"], "value_hbm_resident": line.get("value_hbm_resident"),
+            "unit": "frames/s", "steps": line["steps"], "ms_per_step": line["ms_per_step"], "dtype": line["dtype"], "scaling": line["scaling"],
+            "e2e": {k: line["e2e"][k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "host_parse_ms_per_step", "host_threads")},
+            "cpu_baseline": line.get("cpu_baseline"),
+            "roofline": {"kernel": r["kernel"], "achieved": r["achieved"], "peak": r["peak"], "frac": r["frac"], "unit": "GB/s",
+                         "pipeline_algorithmic_gbs": r["pipeline_algorithmic_gbs"],
+                         "stages": {k: {kk: v[kk] for kk in ("ms_per_step", "launches", "algorithmic_gbs") if kk in v} for k, v in r["stages"].items()}},
+            "gpu_launches": line["gpu_launches"], "host_parse_ms_per_frame": line["host_parse_ms_per_frame"],
+            "clip": {k: line["clip"][k] for k in ("frames", "lr_frames", "cdef_frames", "deblock_frames", "grain_frames", "tools")}}
+
+
+def reference_arm(args, workload):
+    """The reference's CPU implementation of the path (libdav1d, all host threads) on this arm's workload: W warm-up steps, then K
+    timed steps; a step = one pass over the clip (c5: over a bounded sample of 8 of the 32 files)."""
+    from oracle import dav1d_ref
+    sample = WORKLOADS[workload][2]
+    if sample is None:
+        cb = WORKLOADS[workload][1]()
+        return cb, cb["value"], None
+    tus = sample()
+    ncpu = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        dav1d_pass(tus, ncpu)
+    frames, t = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = dav1d_pass(tus, ncpu)
+        frames += n
+        t += dt
+    what = "first 8 of the 32 files (128 frames) per step" if workload == "c5_batch_4k10" else f"whole {len(tus)}-TU clip per step"
+    cb = {"value": frames / t, "unit": "frames/s", "cores": ncpu, "kind": "reference",
+          "sample": f"libdav1d {dav1d_ref.version()} driven directly (no ffmpeg binary in the image; omits FFmpeg's demux), n_threads={ncpu}, {what}, "
+                    f"{args.warmup} warm-up + {args.steps} timed steps, stream preloaded in RAM, no MD5"}
+    return cb, frames / t, t * 1e3 / args.steps
 
 
 def main():
@@ -586,24 +643,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--workload", default=None)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()
-    run, cpu_base = WORKLOADS[args.workload]
+    workload = args.workload or (HEADLINE_N1 if max(world, args.gpus) == 1 else HEADLINE_NGPU)
+    run, cpu_base, _ = WORKLOADS[workload]
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = cpu_base()
-        line = {"impl": "reference", "metric": "AV1 decode-verify frames/s", "value": cb["value"], "unit": "frames/s",
+        cb, value, ms_per_step = reference_arm(args, workload)
+        line = {"impl": "reference", "metric": "AV1 decode-verify frames/s", "value": value, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": {"workload": args.workload},
-                "ms_per_step": cb.get("ms_per_step"), "dtype": cb.get("dtype"),
+                "scaling": "strong" if workload == "c5_batch_4k10" else "weak", "vs_baseline": None, "data": "synthetic",
+                "config": workload_config(workload, max(1, args.gpus)), "ms_per_step": ms_per_step,
+                "dtype": "u8" if workload in ("c1_1080p8", "c2_intra_1080p8", "c2_small") else "u16",
                 "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
@@ -623,8 +683,18 @@ def main():
         print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
         return 2
     out = run(args, torch, dist, rank, world, local)
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+    if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_base()
+    # N = 1 default run: the other BASELINE configs ride along as compact entries (fewer steps each; same timing rules)
+    if world == 1 and args.workload is None and not args.no_per_config:
+        out["per_config"] = []
+        for wname in PER_CONFIG:
+            r2, cb2, _ = WORKLOADS[wname]
+            k = max(3, min(args.steps, 5 if wname != "c5_batch_4k10" else 3))
+            line = r2(args, torch, dist, rank, world, local, steps=k, warmup=3, sample_clocks=False)
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cb2()
+            out["per_config"].append(compact(line))
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:

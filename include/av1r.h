@@ -117,6 +117,26 @@ int av1r_verify_buffer(const uint8_t* data, size_t len, const av1r_config* cfg, 
 /* Same, on an engine that stays open between files (what the daemon's job loop wants: one av1r_open at start-up,
  * one call per job; /root/reference/cmd/av1d/main.go:312-349).  Uses cfg.host_threads / streams of the ctx. */
 int av1r_ctx_verify_buffer(av1r_ctx* ctx, const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames);
+/* ---- several GPUs inside one process (the daemon is one Go process: /root/reference/cmd/av1d/main.go:311-349) -------------------
+ * A pool holds one engine + one host thread per device.  A batch of files is cut into key-frame-delimited GOP segments (a segment
+ * starts only at a temporal unit whose first frame is a shown KEY_FRAME), the segments are assigned to the devices longest-first by
+ * coded bytes, and every device parses (its share of the host cores) and reconstructs its segments; there is no exchange between
+ * devices.  reports[f] describes file f (frames, status, first_bad_frame, message); *total (optional) aggregates the batch:
+ * frames, wall_ms, frames_per_sec, and first_bad_frame = index of the first failing file.  digests[f] (optional, may be NULL or hold
+ * NULL entries) receives 3 x uint64 plane digests per shown frame of file f in display order, cap_frames[f] entries. */
+typedef struct av1r_pool av1r_pool;
+int av1r_pool_open(const int* devices, int n_devices, const av1r_config* cfg, av1r_pool** out);
+void av1r_pool_close(av1r_pool* pool);
+int av1r_pool_devices(const av1r_pool* pool);
+int av1r_pool_verify_files(av1r_pool* pool, const char* const* paths, int n_files, av1r_report* reports, av1r_report* total);
+int av1r_pool_verify_buffers(av1r_pool* pool, const uint8_t* const* data, const size_t* lens, int n_files, av1r_report* reports,
+                             uint64_t* const* digests, const int64_t* cap_frames, av1r_report* total);
+/* open + verify_files + close */
+int av1r_verify_batch(const char* const* paths, int n_files, const int* devices, int n_devices, const av1r_config* cfg,
+                      av1r_report* reports, av1r_report* total);
+/* The assignment rule alone (host only, for tests / planning): assignment[i] = device index of item i. */
+int av1r_batch_assign(const uint64_t* weights, int n_items, int n_devices, int* assignment);
+
 /* Host half only (no device): demux + symbol parse of every frame, GOP segments on `host_threads` threads (0 = all cores), the
  * tiles of a frame on the process-wide worker pool when tile_threads != 0.  Fills frames, host_parse_ms (summed over frames),
  * wall_ms and frames_per_sec: the "sequential parse, timed and reported separately" of the hot path. */

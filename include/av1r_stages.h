@@ -70,10 +70,10 @@ uint64_t av1r_plane_checksum_host(const void* src, size_t pitch, int w, int h, i
 
 const char* av1r_stage_last_error(void);
 
-/* ---- device-resident clip replay (measurement): parse + upload once, then time the device path ----
- * av1r_clip_load runs the sequential host parse of every temporal unit and uploads the work-lists to
- * HBM (untimed).  av1r_clip_decode replays the reconstruction of the whole clip from those resident
- * work-lists: this is the region `value` in bench.py times (CUDA events, all streams fenced by the
+/* ---- clip replay (measurement): parse once, then time the device path ----
+ * av1r_clip_load runs the host parse of every temporal unit (GOP segments in parallel) and keeps the work-lists in pinned
+ * host memory (untimed).  av1r_clip_decode replays the reconstruction of the whole clip: per frame one H2D copy of its
+ * work-lists, then the kernels -- the region `value` in bench.py times (CUDA events, all streams fenced by the
  * start/stop events).  av1r_clip_profile replays serially on one stream with an event between the
  * stages and reports per-stage device time and launch counts (the live roofline input). */
 struct av1r_ctx;
@@ -111,6 +111,9 @@ int av1r_clip_info_get(const av1r_clip* clip, av1r_clip_info* out);
 int av1r_clip_decode(struct av1r_ctx* ctx, av1r_clip* clip, uint64_t* checksums, int cap_frames, int* n_frames, float* device_ms);
 int av1r_clip_profile(struct av1r_ctx* ctx, av1r_clip* clip, av1r_stage_times* out);
 void av1r_clip_free(av1r_clip* clip);
+/* Default (0): every replay copies each frame's work-lists host -> device inside the timed pass ("from the first
+ * work-list H2D enqueue").  1: upload once, replays read the lists from HBM (the kernel-only figure). */
+int av1r_clip_set_resident(av1r_clip* clip, int resident);
 /* Host-only statistics of a container (IVF / raw OBU / Matroska bytes): the parser-side fields of av1r_clip_info (tool histogram,
  * coded samples, frames per post-filter stage ...) without touching a GPU.  bench.py uses it to refuse a clip that lacks the tools
  * of the BASELINE config it stands for. */

@@ -41,4 +41,13 @@ def test_verify_file_and_verify_output(built, tmp_path):
     assert ei.value.code != 0 and len(str(ei.value)) < 800                           # fits job.Reason (transcode.go:295-297)
     with pytest.raises(av1recon.VerifyError):
         eng.VerifyFile(str(tmp_path / "missing.mkv"))
+    # anamorphic WebRip jobs are rescaled by the sample aspect ratio before the even-size rounding (transcode.go:93-101): an output
+    # wider than the source must pass for them and still fail for ordinary jobs
+    assert av1recon.VerifyOutput(eng, str(mkv), 150, 136, is_webrip_like=True).frames == rep.frames
+    with pytest.raises(av1recon.VerifyError):
+        av1recon.VerifyOutput(eng, str(mkv), 150, 136)
+    empty = tmp_path / "empty.av1-tmp.mkv"
+    empty.write_bytes(b"")
+    with pytest.raises(av1recon.VerifyError):
+        eng.VerifyFile(str(empty))
     eng.Close()
