@@ -19,6 +19,7 @@ static bool demux_ivf(const uint8_t* d, size_t n, DemuxResult& out, std::string&
         int64_t pts = (int64_t)rd64(d + pos + 4);
         pos += 12;
         if (sz > n - pos) { err = "ivf: truncated frame"; return false; }
+        if (sz == 0) { err = "ivf: empty frame"; return false; }   // a temporal unit holds at least a temporal delimiter
         out.tus.push_back({pos, sz, pts});
         pos += sz;
     }

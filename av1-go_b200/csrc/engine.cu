@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <future>
 #include <memory>
 #include <vector>
@@ -330,6 +331,7 @@ struct ClipFrame {
     bool show_existing = false;
     int show_slot = -1;
     FrameHdr fh;
+    SeqHdr seq;
     int64_t pts = 0;
     DevWork dw;
     uint8_t* host = nullptr;   // pinned work-list arena (exact size): what every replay copies to the device inside the timed region
@@ -413,6 +415,26 @@ struct EngineImpl {
     int exec_show_existing(int slot_idx, const FrameHdr& fh, int show_slot, int64_t pts);
 };
 
+static std::atomic<long long> g_eprof_ns[20];   // written from the consumer and the parser threads
+struct EProfPrinter {
+    ~EProfPrinter() {
+        if (getenv("AV1R_PROFILE"))
+            fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f replay_h2d %.1f replay_exec %.1f ms\n",
+                    g_eprof_ns[0] * 1e-6, g_eprof_ns[1] * 1e-6, g_eprof_ns[2] * 1e-6, g_eprof_ns[3] * 1e-6, g_eprof_ns[4] * 1e-6, g_eprof_ns[5] * 1e-6,
+                    g_eprof_ns[6] * 1e-6, g_eprof_ns[7] * 1e-6);
+            fprintf(stderr, "[engine prof] host issue per stage: getframe %.1f itx %.1f inter %.1f intra %.1f deblock %.1f cdef %.1f lr %.1f emit %.1f ms\n",
+                    g_eprof_ns[8] * 1e-6, g_eprof_ns[9] * 1e-6, g_eprof_ns[10] * 1e-6, g_eprof_ns[11] * 1e-6, g_eprof_ns[12] * 1e-6, g_eprof_ns[13] * 1e-6,
+                    g_eprof_ns[14] * 1e-6, g_eprof_ns[15] * 1e-6);
+    }
+} g_eprof_printer;
+extern "C" void av1r_debug_engine_prof(double* out20, int reset) {
+    for (int i = 0; i < 20; i++) out20[i] = g_eprof_ns[i] * 1e-6;
+    if (reset)
+        for (auto& v : g_eprof_ns) v = 0;
+}
+#define EP_T() std::chrono::steady_clock::now()
+#define EP_ADD(i, a) g_eprof_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count()
+
 std::shared_ptr<DevFrameBuf> EngineImpl::get_frame(const DevFrameParams& fp) {
     for (size_t i = 0; i < pool.size(); i++) {
         auto& f = pool[i];
@@ -438,9 +460,12 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     const WorkLayout& L = dw.lay;
     const DevFrameParams& fp = dw.fp;
     cudaStream_t st = s.stream;
+    auto t_h = EP_T();
     auto recon = get_frame(fp);
     if (!recon) return AV1R_ENOMEM;
     s.hold.push_back(recon);
+    EP_ADD(8, t_h);
+    t_h = EP_T();
     // residual: unit-major tiles (devframe.h)
     DevResidual res;
     {
@@ -462,6 +487,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     if (tm) tm->begin(st);
     CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, L.n_order_small, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, (L.n_order_small > 0) + (L.n_order > L.n_order_small), st);
+    EP_ADD(9, t_h);
+    t_h = EP_T();
     if (L.n_inter > 0) {
         InterLaunch xl;
         xl.blks = (const InterBlk*)(d_arena + L.inter);
@@ -493,6 +520,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         CK(launch_inter_residual(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
         if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
     }
+    EP_ADD(10, t_h);
+    t_h = EP_T();
     if (L.n_k3 > 0) {
         if (L.n_k3units < 0) { err = "a 64x64 unit holds more intra records than the intra kernel supports"; return AV1R_ENOSYS; }
         IntraLaunch il;
@@ -543,6 +572,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         CK(launch_intra(il, st));
     }
     if (tm) tm->end(AV1R_ST_INTRA, L.n_k3 > 0 ? 1 : 0, st);
+    EP_ADD(11, t_h);
+    t_h = EP_T();
     std::shared_ptr<DevFrameBuf> cur = recon;
     if (dw.lf_on && (cfg.inloop_filters & 1)) {
         LfLaunch ll;
@@ -555,6 +586,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         CK(launch_deblock(ll, st));
         if (tm) tm->end(AV1R_ST_DEBLOCK, 2, st);
     }
+    EP_ADD(12, t_h);
+    t_h = EP_T();
     if (dw.cdef_on && (cfg.inloop_filters & 2)) {
         auto dst = get_frame(fp);
         if (!dst) return AV1R_ENOMEM;
@@ -569,6 +602,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         if (tm) tm->end(AV1R_ST_CDEF, 1, st);
         cur = dst;
     }
+    EP_ADD(13, t_h);
+    t_h = EP_T();
     std::shared_ptr<DevFrameBuf> deblocked = recon;
     const DevFrameParams& fpu = dw.fp_up;
     if (dw.fh.use_superres) {   // K6: stretch the CDEF output (and, for the stripe boundaries of loop restoration, the deblocked frame)
@@ -629,6 +664,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     }
     CK(cudaEventRecord(cur->ready, st));
     out_ref = cur;
+    EP_ADD(14, t_h);
     return 0;
 }
 
@@ -799,7 +835,9 @@ int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_a
     for (int i = 0; i < 8; i++)
         if ((dw.fh.refresh_frame_flags >> i) & 1) rs->refs[i] = out;
     if (dw.fh.show_frame) {
+        auto t_e = EP_T();
         rc = emit_output(&s, slot_idx, out, dw.fh, dw.fh.fg, dw.fp_up, pts, dw.parse_ms, false);
+        EP_ADD(15, t_e);
         if (rc) return rc;
     }
     CK(cudaEventRecord(s.ev1, s.stream));
@@ -808,21 +846,6 @@ int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_a
     return 0;
 }
 
-static std::atomic<long long> g_eprof_ns[8];   // written from the consumer and the parser threads
-struct EProfPrinter {
-    ~EProfPrinter() {
-        if (getenv("AV1R_PROFILE"))
-            fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f ms\n", g_eprof_ns[0] * 1e-6,
-                    g_eprof_ns[1] * 1e-6, g_eprof_ns[2] * 1e-6, g_eprof_ns[3] * 1e-6, g_eprof_ns[4] * 1e-6, g_eprof_ns[5] * 1e-6);
-    }
-} g_eprof_printer;
-extern "C" void av1r_debug_engine_prof(double* out6, int reset) {
-    for (int i = 0; i < 6; i++) out6[i] = g_eprof_ns[i] * 1e-6;
-    if (reset)
-        for (auto& v : g_eprof_ns) v = 0;
-}
-#define EP_T() std::chrono::steady_clock::now()
-#define EP_ADD(i, a) g_eprof_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count()
 
 int EngineImpl::decode_parsed(ParsedFrame& pf) {
     int slot_idx;
@@ -831,15 +854,20 @@ int EngineImpl::decode_parsed(ParsedFrame& pf) {
     EP_ADD(0, ta);
     if (rc) return rc;
     FrameSlot& s = *slots[slot_idx];
+    sp.hp.seq = pf.seq;   // the frame's own sequence header (segments of different files alternate on one engine)
     if (pf.show_existing_slot >= 0) return exec_show_existing(slot_idx, pf.fh, pf.show_existing_slot, pf.pts);
     const FrameWork& fw = *pf.fw;
     if (pf.host) {   // staged by the parser thread
         HostArena& ha = *(HostArena*)pf.host.get();
         auto ti = EP_T();
+        auto t1 = EP_T();
         CK(s.arena.ensure(ha.dw.lay.total, &hw_arena));
+        EP_ADD(16, t1);
         s.host_arena = pf.host;
+        t1 = EP_T();
         CK(cudaEventRecord(s.ev0, s.stream));
         CK(cudaMemcpyAsync(s.arena.p, ha.pin.p, ha.dw.lay.total, cudaMemcpyHostToDevice, s.stream));
+        EP_ADD(17, t1);
         rc = exec_decoded(slot_idx, ha.dw, s.arena.p, pf.pts);
         EP_ADD(3, ti);
         return rc;
@@ -1063,6 +1091,57 @@ int Engine::verify_file(const char* path, const av1r_config* cfg, av1r_report* o
     return verify_buffer(buf.data(), buf.size(), cfg, out, nullptr, 0);
 }
 
+// One helper thread with a FIFO of closures: the staging lane of a segment parser (merge of the tile lists, deblocking edges, copy
+// into pinned memory run here while the parser thread is already in the next frame).  Persistent for the life of the worker: a
+// std::async per temporal unit cost a thread creation plus a first CUDA call on a fresh thread per frame.
+class SerialWorker {
+public:
+    explicit SerialWorker(int device) {
+        th_ = std::thread([this, device] {
+            cudaSetDevice(device);
+            std::unique_lock<std::mutex> lk(m_);
+            while (true) {
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;   // stop requested and nothing left
+                auto f = std::move(q_.front());
+                q_.pop_front();
+                busy_ = true;
+                lk.unlock();
+                f();
+                lk.lock();
+                busy_ = false;
+                if (q_.empty()) idle_.notify_all();
+            }
+        });
+    }
+    ~SerialWorker() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    void post(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_all();
+    }
+    void drain() {
+        std::unique_lock<std::mutex> lk(m_);
+        idle_.wait(lk, [&] { return q_.empty() && !busy_; });
+    }
+
+private:
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_, idle_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false, busy_ = false;
+};
+
 // ---- verification of whole containers: one file on one GPU (av1r_verify_*), or a batch of files over several GPUs ------------
 // One key-frame-delimited GOP segment: parsed by one host thread, issued to the GPU in order.
 struct Segment {
@@ -1077,6 +1156,54 @@ struct Segment {
 
 // Pre-scan of one container: sequence header, temporal units, where the independently decodable GOP segments start (temporal
 // units whose first frame is a shown KEY_FRAME -- the only safe cut) and how many frames are shown before each unit.
+// Header scan of one temporal unit (no tile data is read): keeps `scan`'s reference state current, reports whether the unit starts
+// an independently decodable GOP segment (its first frame is a shown KEY_FRAME -- the only safe cut) and how many
+// frames it shows.
+static int scan_temporal_unit(HeaderParser& scan, const uint8_t* p, size_t n, bool* seg_start, int* shown_out, std::string& msg) {
+    std::vector<ObuUnit> obus;
+    if (!scan.split_obus(p, n, obus)) { msg = scan.error; return AV1R_EBITSTREAM; }
+    bool first_frame = true, frame_open = false;   // frame_open: a frame header was seen and not all of its tiles yet
+    int shown = 0;
+    *seg_start = false;
+    FrameHdr open_fh;
+    auto tiles_after = [&](const uint8_t* q, size_t m) {   // tile group header at q: is the frame complete after this group?
+        BitReader tb(q, m);
+        TileGroupInfo tg;
+        if (!scan.parse_tile_group_header(tb, open_fh, tg)) return true;   // the parser proper reports the error
+        return tg.tg_end + 1 >= open_fh.tile_cols * open_fh.tile_rows;
+    };
+    for (const ObuUnit& u : obus) {
+        if (u.type == OBU_SEQUENCE_HEADER) {
+            if (!scan.parse_sequence_header(u.data, u.size)) { msg = scan.error; return AV1R_EBITSTREAM; }
+        } else if (u.type == OBU_FRAME || (u.type == OBU_FRAME_HEADER && !frame_open)) {   // (a header while a frame is open is a copy)
+            BitReader br(u.data, u.size);
+            FrameHdr fh;
+            if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) { msg = scan.error; return AV1R_EBITSTREAM; }
+            if (first_frame && !fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) *seg_start = true;
+            shown += fh.show_existing_frame || fh.show_frame;
+            if (!fh.show_existing_frame) scan.reference_update(fh);
+            else if (fh.frame_type == KEY_FRAME) {
+                RefHdrState r = scan.refs[fh.frame_to_show_map_idx];
+                for (auto& x : scan.refs) x = r;
+            }
+            first_frame = false;
+            open_fh = fh;
+            frame_open = !fh.show_existing_frame;
+            if (u.type == OBU_FRAME) {
+                br.byte_align();
+                const size_t off = br.byte_pos();
+                frame_open = off < u.size ? !tiles_after(u.data + off, u.size - off) : false;
+            }
+        } else if (u.type == OBU_TILE_GROUP && frame_open) {
+            frame_open = !tiles_after(u.data, u.size);
+        }
+    }
+    *shown_out = shown;
+    return 0;
+}
+
+// Pre-scan of one container: sequence header, temporal units, where the GOP segments start and how many frames are shown before
+// each unit.
 int VerifyFile::prescan(std::string& msg) {
     std::string derr;
     if (!demux_buffer(data, len, dm, derr)) { msg = derr; return AV1R_EBITSTREAM; }
@@ -1087,49 +1214,21 @@ int VerifyFile::prescan(std::string& msg) {
                 if (u.type == OBU_SEQUENCE_HEADER) scan.parse_sequence_header(u.data, u.size);
     }
     starts.clear();
+    start_seq.clear();
     frame_base.assign(dm.tus.size() + 1, 0);
     for (size_t i = 0; i < dm.tus.size(); i++) {
-        std::vector<ObuUnit> obus;
-        if (!scan.split_obus(data + dm.tus[i].offset, dm.tus[i].size, obus)) { msg = scan.error; return AV1R_EBITSTREAM; }
-        bool first_frame = true, frame_open = false;   // frame_open: a frame header was seen and not all of its tiles yet
+        bool seg = false;
         int shown = 0;
-        FrameHdr open_fh;
-        auto tiles_after = [&](const uint8_t* p, size_t n) {   // tile group header at p: is the frame complete after this group?
-            BitReader tb(p, n);
-            TileGroupInfo tg;
-            if (!scan.parse_tile_group_header(tb, open_fh, tg)) return true;   // the parser proper reports the error
-            return tg.tg_end + 1 >= open_fh.tile_cols * open_fh.tile_rows;
-        };
-        for (const ObuUnit& u : obus) {
-            if (u.type == OBU_SEQUENCE_HEADER) {
-                if (!scan.parse_sequence_header(u.data, u.size)) { msg = scan.error; return AV1R_EBITSTREAM; }
-            } else if (u.type == OBU_FRAME || (u.type == OBU_FRAME_HEADER && !frame_open)) {   // (a header while a frame is open is a copy)
-                BitReader br(u.data, u.size);
-                FrameHdr fh;
-                if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) { msg = scan.error; return AV1R_EBITSTREAM; }
-                if (first_frame && !fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
-                shown += fh.show_existing_frame || fh.show_frame;
-                if (!fh.show_existing_frame) scan.reference_update(fh);
-                else if (fh.frame_type == KEY_FRAME) {
-                    RefHdrState r = scan.refs[fh.frame_to_show_map_idx];
-                    for (auto& x : scan.refs) x = r;
-                }
-                first_frame = false;
-                open_fh = fh;
-                frame_open = !fh.show_existing_frame;
-                if (u.type == OBU_FRAME) {
-                    br.byte_align();
-                    const size_t off = br.byte_pos();
-                    frame_open = off < u.size ? !tiles_after(u.data + off, u.size - off) : false;
-                }
-            } else if (u.type == OBU_TILE_GROUP && frame_open) {
-                frame_open = !tiles_after(u.data, u.size);
-            }
+        const int rc = scan_temporal_unit(scan, data + dm.tus[i].offset, dm.tus[i].size, &seg, &shown, msg);
+        if (rc) return rc;
+        if (seg || i == 0) {
+            starts.push_back(i);
+            start_seq.push_back(scan.seq);
         }
         frame_base[i + 1] = frame_base[i] + shown;
     }
     if (!scan.seq.valid) { msg = "no sequence header"; return AV1R_EBITSTREAM; }
-    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+    if (starts.empty()) { msg = "no temporal units"; return AV1R_EBITSTREAM; }
     return 0;
 }
 
@@ -1244,16 +1343,19 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
     auto worker = [&]() {
         cudaSetDevice(E.cfg.device);   // pinned staging is allocated from this thread
         WorkerPool::nested_enabled() = nseg < (size_t)nthreads;   // enough segments to fill the cores: no tile / band helpers
+        // with fewer segments than threads the staging of TU t overlaps the parse of TU t+1 on this worker's helper thread; when the
+        // segments alone fill the cores a helper would only add time-slicing: stage inline
+        std::unique_ptr<SerialWorker> helper;
+        if (WorkerPool::nested_enabled()) helper = std::make_unique<SerialWorker>(E.cfg.device);
         while (!abort_flag.load()) {
             const size_t s = next_seg.fetch_add(1);
             if (s >= nseg) return;
             Segment& sg = *segs[s];
             const VerifyFile& vf = *files[items[s].file];
             StreamParser sp;
-            sp.hp.seq = vf.scan.seq;
-            // parse TU t while the work-lists of TU t-1 are being laid out / copied into pinned memory on a helper thread
-            std::future<void> staging;
-            auto publish = [&](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
+            sp.hp.seq = vf.seq_for(sg.tu0);
+            sp.defer_finalize = true;   // merge of the tile lists + deblocking edges run in the staging step below, off the parse chain
+            auto publish = [&sg](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
                 {
                     std::lock_guard<std::mutex> lk(sg.m);
                     sg.parsed[t - sg.tu0] = std::move(pfs);
@@ -1273,29 +1375,25 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
                 auto pfs = std::make_shared<std::vector<ParsedFrame>>();
                 const TemporalUnit& tu = vf.dm.tus[t];
                 const int prc = sp.parse_tu(vf.data + tu.offset, tu.size, ((int64_t)s << 32) | (int64_t)t, *pfs);
-                if (staging.valid()) staging.get();      // TU t-1 is staged and published
                 const std::string perr = sp.err;
-                const SeqHdr seq = sp.hp.seq;
-                // with fewer segments than threads the staging of TU t overlaps the parse of TU t+1 on a helper thread; when the
-                // segments alone fill the cores a helper would only add a thread creation per TU and time-slicing: stage inline
-                const auto policy = WorkerPool::nested_enabled() ? std::launch::async : std::launch::deferred;
-                staging = std::async(policy, [&, t, pfs, prc, perr, seq]() {
-                    cudaSetDevice(E.cfg.device);
+                auto stage = [&E, publish, t, pfs, prc, perr]() {
                     int rc2 = prc;
                     std::string e2 = perr;
                     for (ParsedFrame& pf : *pfs)
                         if (pf.fw && !rc2) {
+                            finalize_framework(*pf.fw);
                             int hrc = 0;
                             std::string herr;
-                            pf.host = E.make_host_arena(*pf.fw, seq, herr, hrc);
+                            pf.host = E.make_host_arena(*pf.fw, pf.seq, herr, hrc);
                             if (hrc) { rc2 = hrc; e2 = herr; }
                         }
                     publish(t, std::move(*pfs), rc2, e2);
-                });
-                if (policy == std::launch::deferred) staging.get();
+                };
+                if (helper) helper->post(stage);
+                else stage();
                 if (prc) failed = true;
             }
-            if (staging.valid()) staging.get();
+            if (helper) helper->drain();
             {   // mark the remaining TUs of a failed segment as done so the consumer never blocks
                 std::lock_guard<std::mutex> lk(sg.m);
                 sg.n_done = sg.tu1 - sg.tu0;
@@ -1430,29 +1528,20 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
     // ---- cut at shown key frames (header scan), then parse the GOP segments on all host cores; per-segment results are merged in
     // order, so the clip is the same as a sequential parse would give
     std::vector<int> starts;
-    SeqHdr seq0;
+    std::vector<SeqHdr> seg_seq;        // sequence header in force where each segment starts
     {
         HeaderParser scan;
         for (int i = 0; i < n; i++) {
-            std::vector<ObuUnit> obus;
-            if (!scan.split_obus(tus[i], lens[i], obus)) { err = scan.error; return AV1R_EBITSTREAM; }
-            bool first = true;
-            for (const ObuUnit& u : obus) {
-                if (u.type == OBU_SEQUENCE_HEADER) {
-                    if (!scan.parse_sequence_header(u.data, u.size)) { err = scan.error; return AV1R_EBITSTREAM; }
-                } else if ((u.type == OBU_FRAME || u.type == OBU_FRAME_HEADER) && first) {
-                    BitReader br(u.data, u.size);
-                    FrameHdr fh;
-                    if (!scan.parse_frame_header(br, fh, u.temporal_id, u.spatial_id)) { err = scan.error; return AV1R_EBITSTREAM; }
-                    if (!fh.show_existing_frame && fh.frame_type == KEY_FRAME && fh.show_frame) starts.push_back(i);
-                    first = false;
-                    break;   // only the first frame header of a unit decides; the segment parsers read the rest
-                }
+            bool seg = false;
+            int shown = 0;
+            const int rc = scan_temporal_unit(scan, tus[i], lens[i], &seg, &shown, err);
+            if (rc) return rc;
+            if (seg || i == 0) {
+                starts.push_back(i);
+                seg_seq.push_back(scan.seq);
             }
         }
-        seq0 = scan.seq;
     }
-    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
     const int nseg = (int)starts.size();
     struct SegOut {
         std::vector<std::unique_ptr<ClipFrame>> frames;
@@ -1472,7 +1561,7 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
             SegOut& so = outs[sidx];
             memset(&so.info, 0, sizeof(so.info));
             StreamParser parser;
-            parser.hp.seq = seq0;
+            parser.hp.seq = seg_seq[sidx];
             const int t1 = sidx + 1 < nseg ? starts[sidx + 1] : n;
             for (int t = starts[sidx]; t < t1 && !so.rc; t++) {
                 std::vector<ParsedFrame> pfs;
@@ -1481,6 +1570,7 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
                 for (ParsedFrame& pf : pfs) {
                     auto cf = std::make_unique<ClipFrame>();
                     cf->fh = pf.fh;
+                    cf->seq = pf.seq;
                     cf->pts = pf.pts;
                     if (pf.show_existing_slot >= 0) {
                         cf->show_existing = true;
@@ -1548,7 +1638,6 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
         if (a.frames_decoded) { d.width = a.width; d.height = a.height; d.bit_depth = a.bit_depth; d.frame_bytes = a.frame_bytes; }
         for (auto& cf : so.frames) clip->frames.push_back(std::move(cf));
     }
-    E.sp.hp.seq = seq0;   // fill_params (show_existing_frame outputs) reads the sequence header of this ctx
     *out = clip.release();
     return 0;
 }
@@ -1560,9 +1649,12 @@ static int replay(EngineImpl& E, av1r_clip* clip) {
     std::string& err = E.err;
     for (auto& cf : clip->frames) {
         int slot_idx;
+        auto t_q = EP_T();
         int rc = E.acquire_slot(slot_idx);
+        EP_ADD(0, t_q);
         if (rc) return rc;
         FrameSlot& s = *E.slots[slot_idx];
+        E.sp.hp.seq = cf->seq;
         if (cf->show_existing) {
             rc = E.exec_show_existing(slot_idx, cf->fh, cf->show_slot, cf->pts);
         } else {
@@ -1576,13 +1668,17 @@ static int replay(EngineImpl& E, av1r_clip* clip) {
                 }
                 d_arena = cf->arena.p;
             } else {
+                auto t_a = EP_T();
                 CK(s.arena.ensure(cf->dw.lay.total, &E.hw_arena));
                 if (E.tm) E.tm->begin(s.stream);
                 CK(cudaMemcpyAsync(s.arena.p, cf->host, cf->dw.lay.total, cudaMemcpyHostToDevice, s.stream));
                 if (E.tm) E.tm->end(AV1R_ST_H2D, 1, s.stream);
                 d_arena = s.arena.p;
+                EP_ADD(6, t_a);
             }
+            auto t_x = EP_T();
             rc = E.exec_decoded(slot_idx, cf->dw, d_arena, cf->pts);
+            EP_ADD(7, t_x);
         }
         if (rc) return rc;
     }
@@ -1597,6 +1693,12 @@ int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, 
     if (rc) return rc;
     E.pending.clear();
     cudaMemset(E.k3_stuck.p, 0, 4);
+    if (!clip->resident) {   // no slot arena may have to grow (cudaFree + cudaMalloc) inside the timed pass
+        size_t mx = 0;
+        for (auto& cf : clip->frames)
+            if (!cf->show_existing) mx = std::max(mx, cf->dw.lay.total);
+        for (auto& sl : E.slots) CK(sl->arena.ensure(mx, &E.hw_arena));
+    }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));

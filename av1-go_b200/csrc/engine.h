@@ -26,12 +26,18 @@ struct VerifyFile {
     DemuxResult dm;
     HeaderParser scan;                  // carries the sequence header after prescan()
     std::vector<size_t> starts;         // temporal units at which an independently decodable GOP segment starts
+    std::vector<SeqHdr> start_seq;      // sequence header in force at each of them
     std::vector<int64_t> frame_base;    // shown frames before each temporal unit (display index of its first shown frame)
     av1r_report* rep = nullptr;
     uint64_t* digests = nullptr;        // 3 x uint64 per shown frame, display order (may be null)
     int64_t cap_frames = 0;
     std::mutex m;
     int prescan(std::string& msg);
+    const SeqHdr& seq_for(size_t tu) const {   // sequence header in force for the segment that holds temporal unit `tu`
+        size_t k = 0;
+        while (k + 1 < starts.size() && starts[k + 1] <= tu) k++;
+        return start_seq.empty() ? scan.seq : start_seq[k];
+    }
     void init_report();
     void fail(int rc, int64_t frame, const std::string& msg);
 };

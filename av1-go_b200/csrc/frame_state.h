@@ -171,6 +171,7 @@ struct FrameWork {
     // CDFs at the end of the context-update tile (saved into refreshed slots)
     CdfCtx end_cdf;
     bool have_end_cdf = false;
+    bool finalized = true;              // false between the tile parse and finalize_framework() (stream_parser.h)
 
     void init(const SeqHdr& seq, const FrameHdr& h) {
         fh = h;
@@ -217,6 +218,7 @@ struct FrameWork {
         coded_samples = coef_tokens = tx_blocks = inter_samples = inter_ref_samples = 0;
         parse_ms = 0;
         have_end_cdf = false;
+        finalized = true;
     }
     // per-tile outputs are recycled with the frame: hands out the next one, cleared but with its capacity kept
     TileOut& next_tile() {

@@ -56,11 +56,13 @@ __device__ __forceinline__ int filter_index_d(int type, int len) {
     return type;
 }
 
-static constexpr int RW = IT + 8;             // reference window row stride (tw + 7 samples used)
+static constexpr int RW = IT + 16;            // reference window row stride in samples (tw + 7 used; 96 B rows: 16-byte aligned)
+static constexpr int MW = IT + 8;             // row stride of the packed 16-bit intermediate (80 B rows: 16-byte aligned)
 struct InterSmem {
     int32_t pred[2][IT * IT];
-    int32_t mid[(IT + 7) * IT];
-    uint16_t refwin[(IT + 7) * RW];           // clamped reference samples of the tile's 8-tap support, loaded once
+    // intermediate of the separable filter: int32 [39][32] on the generic / warped paths, int16 [39][MW] on the fast path
+    __align__(16) int32_t mid[(IT + 7) * IT];
+    __align__(16) uint16_t refwin[(IT + 7) * RW];   // clamped reference samples of the tile's 8-tap support, loaded once
 };
 
 // idx / d for idx <= 39 * 39 and d <= 39 as a multiply and a shift (inv = ceil(65536 / d); exact in that range): the tile loops
@@ -74,6 +76,126 @@ __device__ __forceinline__ int ld_ref(const uint8_t* base, uint32_t pitch, int x
     return (int)__ldg((const T*)(base + (size_t)y * pitch) + x);
 }
 
+// ---- fast path of the translational predictor: tiles 8 / 16 / 32 samples wide, a multiple of 4 high -------------------------
+// Written for instruction count (the stage is issue-bound, not bandwidth-bound: profiles/r1d_c3_ncu_summary.md):
+//   fetch : the (tw + 7) x (th + 7) support comes in with one 32-bit load per lane and row (a warp per row, ten rows in flight per
+//           warp); a funnel shift with the neighbour lane's word removes the sub-word start offset, so that the window in shared
+//           memory starts at sample ix - 3 as packed 16-bit pairs.  Windows that leave the reference frame take a clamped
+//           per-sample path.
+//   H pass: a thread turns 16 window samples (two 128-bit shared loads) into 8 outputs and stores them as one 128-bit row of
+//           packed int16 (the intermediate fits 16 bits: spec 7.11.3.4).
+//   V pass: a thread owns two columns x four rows: eleven 32-bit loads of packed pairs feed 64 multiply-adds.
+template <typename T>
+__device__ __forceinline__ void fetch_window_fast(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, int ww, int wh,
+                                                  uint16_t* win) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = ix - 3, y0 = iy - 3;
+    const bool interior = x0 >= 0 && y0 >= 0 && x0 + ww - 1 <= lastx && y0 + wh - 1 <= lasty;
+    if (interior) {
+        constexpr int SPW = 4 / (int)sizeof(T);              // samples per 32-bit word: 2 (uint16) or 4 (uint8)
+        const int xs = x0 & ~(SPW - 1), sh = (x0 - xs) * 8 * (int)sizeof(T);
+        const int nwords = ((x0 + ww - 1 - xs) / SPW) + 1;   // <= 21 (uint16) / 11 (uint8)
+        const uint8_t* base = ref + (size_t)y0 * pitch + (size_t)xs * sizeof(T);
+        uint32_t w[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const int r = warp + 4 * k;
+            w[k] = (r < wh && lane < nwords) ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * pitch) + lane) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const int r = warp + 4 * k;
+            const uint32_t nxt = __shfl_down_sync(0xffffffffu, w[k], 1);
+            const uint32_t v = __funnelshift_r(w[k], nxt, sh);
+            if (r < wh && lane < nwords) {
+                if (sizeof(T) == 2) {
+                    reinterpret_cast<uint32_t*>(win + r * RW)[lane] = v;
+                } else {
+                    uint2 e;
+                    e.x = __byte_perm(v, 0, 0x4140);
+                    e.y = __byte_perm(v, 0, 0x4342);
+                    reinterpret_cast<uint2*>(win + r * RW)[lane] = e;
+                }
+            }
+        }
+    } else {
+        for (int r = warp; r < wh; r += INTER_THREADS / 32) {
+            const int y = min(max(y0 + r, 0), lasty);
+            const T* row = (const T*)(ref + (size_t)y * pitch);
+            for (int c = lane; c < ww; c += 32) win[r * RW + c] = (uint16_t)__ldg(row + min(max(x0 + c, 0), lastx));
+        }
+    }
+}
+
+template <typename T>
+__device__ void predict_tile_fast(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, const int16_t* fh, const int16_t* fv,
+                                  int tw, int th, int round1, InterSmem& sm, int32_t* out) {
+    const int ww = tw + 7, wh = th + 7;
+    fetch_window_fast<T>(ref, pitch, lastx, lasty, ix, iy, ww, wh, sm.refwin);
+    __syncthreads();
+    int16_t* mid = reinterpret_cast<int16_t*>(sm.mid);
+    {   // horizontal pass: (row, group of 8 columns) per thread
+        const int lg = tw == 32 ? 2 : (tw == 16 ? 1 : 0), ng = 1 << lg;
+        int f[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) f[t] = fh[t];
+        for (int idx = threadIdx.x; idx < (wh << lg); idx += INTER_THREADS) {
+            const int r = idx >> lg, c0 = (idx & (ng - 1)) << 3;
+            const uint4* wp = reinterpret_cast<const uint4*>(sm.refwin + r * RW + c0);
+            const uint4 a = wp[0], b = wp[1];
+            const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            int x[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                x[2 * k] = (int)(wv[k] & 0xffffu);
+                x[2 * k + 1] = (int)(wv[k] >> 16);
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int s0 = 4, s1 = 4;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    s0 += f[t] * x[2 * k + t];
+                    s1 += f[t] * x[2 * k + 1 + t];
+                }
+                o[k] = ((uint32_t)(s0 >> 3) & 0xffffu) | ((uint32_t)(s1 >> 3) << 16);
+            }
+            *reinterpret_cast<uint4*>(mid + r * MW + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    {   // vertical pass: (column pair, group of 4 rows) per thread
+        const int lp = tw == 32 ? 4 : (tw == 16 ? 3 : 2), np = 1 << lp;
+        const int rnd = 1 << (round1 - 1);
+        int f[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) f[t] = fv[t];
+        for (int idx = threadIdx.x; idx < ((th >> 2) << lp); idx += INTER_THREADS) {
+            const int cp = idx & (np - 1), r0 = (idx >> lp) << 2;
+            const uint32_t* mp = reinterpret_cast<const uint32_t*>(mid + r0 * MW) + cp;
+            int lo[11], hi[11];
+#pragma unroll
+            for (int t = 0; t < 11; t++) {
+                const uint32_t v = mp[t * (MW / 2)];
+                lo[t] = (int)(short)(v & 0xffffu);
+                hi[t] = (int)v >> 16;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int s0 = rnd, s1 = rnd;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    s0 += f[t] * lo[k + t];
+                    s1 += f[t] * hi[k + t];
+                }
+                *reinterpret_cast<int2*>(out + (r0 + k) * IT + 2 * cp) = make_int2(s0 >> round1, s1 >> round1);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // translational prediction of a tw x th tile; (fx, fy) = 1/16 phases, (ix, iy) = integer reference position of the tile's
 // top-left sample.  The (tw + 7) x (th + 7) support is fetched once (coordinates clamped to the visible reference frame, spec
 // 7.11.3.4) into shared memory; both filter passes then run out of shared memory.
@@ -83,6 +205,10 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
     const int16_t* fh = c_subpel[fidx_h][fx];
     const int16_t* fv = c_subpel[fidx_v][fy];
     const int ww = tw + 7, wh = th + 7;
+    if ((tw == 8 || tw == 16 || tw == 32) && (th & 3) == 0) {
+        predict_tile_fast<T>(ref, pitch, lastx, lasty, ix, iy, fh, fv, tw, th, round1, sm, out);
+        return;
+    }
     const int inv_ww = recip16(ww), inv_tw = recip16(tw);
     // four independent loads in flight per thread before the first store (the window fetch is pure L2 / L1 latency)
     for (int base = threadIdx.x; base < ww * wh; base += 4 * INTER_THREADS) {
@@ -260,6 +386,62 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                         predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
                                         filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tw, th, round1, sm, sm.pred[l]);
                     }
+                }
+                const bool masked = is_compound && (r.comp_type == COMPOUND_WEDGE || r.comp_type == COMPOUND_DIFFWTD);
+                if (!masked && (tw == 8 || tw == 16 || tw == 32)) {
+                    // unmasked predictions (single, average, distance weights): a thread finishes 8 neighbouring samples of a row
+                    // and stores them with one 128-bit (64-bit at 8 bits per sample) store where the row position allows it
+                    const int lg = tw == 32 ? 2 : (tw == 16 ? 1 : 0);
+                    const int wa = !is_compound ? 1 : (r.comp_type == COMPOUND_DISTANCE ? r.fwd_w : 1);
+                    const int wb = !is_compound ? 0 : (r.comp_type == COMPOUND_DISTANCE ? r.bck_w : 1);
+                    const int sh = !is_compound ? 0 : (r.comp_type == COMPOUND_DISTANCE ? 4 + post : 1 + post);
+                    const int rnd = sh ? 1 << (sh - 1) : 0;
+                    const int cwp = fp.cw[plane], chp = fp.ch[plane];
+                    for (int idx = threadIdx.x; idx < (th << lg); idx += INTER_THREADS) {
+                        const int i = idx >> lg, j0 = (idx & ((1 << lg) - 1)) << 3;
+                        const int gx = px + tx + j0, gy = py + ty + i;
+                        if (gy >= chp || gx >= cwp) continue;
+                        const int4* pa = reinterpret_cast<const int4*>(sm.pred[0] + i * IT + j0);
+                        const int4 a0 = pa[0], a1 = pa[1];
+                        int v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        if (is_compound) {
+                            const int4* pb = reinterpret_cast<const int4*>(sm.pred[1] + i * IT + j0);
+                            const int4 b0 = pb[0], b1 = pb[1];
+                            const int b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int k = 0; k < 8; k++) v[k] = (v[k] * wa + b[k] * wb + rnd) >> sh;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) v[k] = min(max(v[k], 0), pixmax);
+                        T* dp = cur + (size_t)gy * cpe + gx;
+                        if (sizeof(T) == 2) {
+                            const uint32_t w0 = (uint32_t)v[0] | ((uint32_t)v[1] << 16), w1 = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+                            const uint32_t w2 = (uint32_t)v[4] | ((uint32_t)v[5] << 16), w3 = (uint32_t)v[6] | ((uint32_t)v[7] << 16);
+                            if (gx + 8 <= cwp && (gx & 7) == 0) {
+                                *reinterpret_cast<uint4*>(dp) = make_uint4(w0, w1, w2, w3);
+                            } else {   // rows of chroma blocks start at even samples only: 32-bit stores, pair by pair
+                                uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);
+                                d32[0] = w0;
+                                if (gx + 2 < cwp) d32[1] = w1;
+                                if (gx + 4 < cwp) d32[2] = w2;
+                                if (gx + 6 < cwp) d32[3] = w3;
+                            }
+                        } else {
+                            const uint32_t w0 = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+                            const uint32_t w1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
+                            if (gx + 8 <= cwp && (gx & 7) == 0) {
+                                *reinterpret_cast<uint2*>(dp) = make_uint2(w0, w1);
+                            } else {
+                                uint16_t* d16 = reinterpret_cast<uint16_t*>(dp);
+                                d16[0] = (uint16_t)w0;
+                                if (gx + 2 < cwp) d16[1] = (uint16_t)(w0 >> 16);
+                                if (gx + 4 < cwp) d16[2] = (uint16_t)w1;
+                                if (gx + 6 < cwp) d16[3] = (uint16_t)(w1 >> 16);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    continue;
                 }
                 const int inv_tw = recip16(tw);
                 for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {

@@ -285,8 +285,8 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
     if (tile_threads && tasks.size() > 1) WorkerPool::get().parallel_for((int)tasks.size(), parse_one);
     else for (size_t i = 0; i < tasks.size(); i++) parse_one((int)i);
     PROF_ADD(0, t0);
-    auto tm = PROF_T();
-    // ---- merge in tile order: rebase the offsets the records carry
+    // ---- what the *next* frame's parse needs is ready now (CDFs of the context-update tile); the merge of the per-tile work-lists
+    // into the frame's lists is deferred to finalize_framework(), off the frame-to-frame critical path
     for (size_t i = 0; i < tasks.size(); i++) {
         TileOut& to = *fw.tiles[first_out + i];
         if (to.rc) return fail(to.rc, to.err);
@@ -294,6 +294,22 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
             fw.end_cdf = to.end_cdf;
             fw.have_end_cdf = true;
         }
+        tiles_done_++;
+    }
+    fw.finalized = false;
+    cur_->parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+// Second half of a frame's host work: concatenates the per-tile work-lists in tile order (rebasing the offsets the records carry)
+// and classifies the deblocking edges.  Nothing later frames' *parse* reads is touched here (that is mode info, saved motion
+// vectors, segment ids and CDFs, all complete when parse_tu returns), so the verify path runs it on the staging thread while the
+// next frame of the GOP is already being parsed.
+void finalize_framework(FrameWork& fw) {
+    if (fw.finalized) return;
+    auto tm = PROF_T();
+    for (size_t i = 0; i < fw.n_tiles_used; i++) {
+        TileOut& to = *fw.tiles[i];
         const uint32_t coef_base = (uint32_t)fw.coefs.size(), pal_base = (uint32_t)fw.pal.size();
         const uint32_t tx_base = (uint32_t)fw.tx.size(), obmc_base = (uint32_t)fw.obmc.size();
         const int warp_base = (int)fw.warps.size() - 8;   // slots 0..7 hold the global models
@@ -324,17 +340,17 @@ int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset)
         fw.inter_samples += to.inter_samples;
         fw.inter_ref_samples += to.inter_ref_samples;
         for (int k = 0; k < 24; k++) fw.tool_hist[k] += to.tool_hist[k];
-        tiles_done_++;
     }
     PROF_ADD(1, tm);
-    cur_->parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return 0;
+    auto tl = PROF_T();
+    build_loopfilter_edges(fw);
+    PROF_ADD(2, tl);
+    fw.parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm).count();
+    fw.finalized = true;
 }
 
 int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
     auto t0 = std::chrono::steady_clock::now();
-    build_loopfilter_edges(hp.seq, *cur_);
-    PROF_ADD(2, t0);
     auto tw = PROF_T();
     {
         FrameWork& fw = *cur_;
@@ -382,7 +398,9 @@ int StreamParser::finish_frame(int64_t pts, std::vector<ParsedFrame>& out) {
     ParsedFrame pf;
     pf.fw = cur_;
     pf.fh = cur_fh_;
+    pf.seq = hp.seq;
     pf.pts = pts;
+    if (!defer_finalize) finalize_framework(*cur_);
     out.push_back(pf);
     cur_.reset();
     have_frame_ = false;
@@ -428,6 +446,7 @@ int StreamParser::parse_tu_inner(const uint8_t* data, size_t len, int64_t pts, s
                     ParsedFrame pf;
                     pf.show_existing_slot = fh.frame_to_show_map_idx;
                     pf.fh = fh;
+                    pf.seq = hp.seq;
                     pf.pts = pts;
                     if (fh.frame_type == KEY_FRAME) {
                         // frame loading process (7.21): the shown key frame refreshes every slot
@@ -484,12 +503,12 @@ int StreamParser::parse_tu_inner(const uint8_t* data, size_t len, int64_t pts, s
     return 0;
 }
 
-void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw) {
+void build_loopfilter_edges(FrameWork& fw) {
     const FrameHdr& fh = fw.fh;
     if (!fh.lf.level[0] && !fh.lf.level[1]) return;
-    for (int plane = 0; plane < seq.num_planes; plane++) {
+    for (int plane = 0; plane < (fw.mono ? 1 : 3); plane++) {
         if (plane > 0 && !fh.lf.level[1 + plane]) continue;
-        const int sx = plane ? seq.subsampling_x : 0, sy = plane ? seq.subsampling_y : 0;
+        const int sx = plane ? fw.subx : 0, sy = plane ? fw.suby : 0;
         const int pw4 = fw.plane_w4(plane), ph4 = fw.plane_h4(plane);
         const int max_len = plane ? 8 : 16;
         const int li[2] = {plane == 0 ? 0 : plane + 1, plane == 0 ? 1 : plane + 1};   // index into BlockInfo::lf_lvl per pass

@@ -15,6 +15,7 @@ struct ParsedFrame {
     std::shared_ptr<FrameWork> fw;   // null when show_existing_slot >= 0
     int show_existing_slot = -1;     // show_existing_frame: output the frame stored in this slot
     FrameHdr fh;
+    SeqHdr seq;                      // sequence header in force for this frame (geometry / bit depth of show_existing outputs, grain matrix)
     int64_t pts = 0;
     std::shared_ptr<void> host;      // engine-side staging (pinned work-list arena), filled by the thread that parsed the frame
 };
@@ -25,6 +26,9 @@ public:
     HeaderParser hp;
     std::string err;
     bool tile_threads = true;   // parse the tiles of a tile group concurrently on the process-wide worker pool
+    // true: parse_tu returns frames whose work-lists are still per tile; the caller runs finalize_framework(*pf.fw) (on another
+    // thread, typically) before it reads fw.tx / coefs / inter / lf.  Everything the parse of later frames needs is complete.
+    bool defer_finalize = false;
     // Parses one temporal unit; appends one ParsedFrame per frame (shown or not) in decode order.
     // Returns 0 or AV1R_E*.
     int parse_tu(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out);
@@ -50,6 +54,8 @@ private:
 std::shared_ptr<FrameWork> acquire_framework();
 void cdf_clear_counters(CdfCtx& c);
 // host pre-pass of the deblocking filter: per-4x4 edge length + level (spec 7.14.2 - 7.14.5)
-void build_loopfilter_edges(const SeqHdr& seq, FrameWork& fw);
+void build_loopfilter_edges(FrameWork& fw);
+// merge of the per-tile work-lists + deblocking edge classification (idempotent); see StreamParser::defer_finalize
+void finalize_framework(FrameWork& fw);
 
 }  // namespace av1r

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "../../include/av1r.h"
 #include "tables/tables_scan.inc"
@@ -83,18 +84,22 @@ TileDecoder::TileDecoder(const SeqHdr& s, const HeaderParser& h, FrameWork& f, T
 }
 
 void TileDecoder::clear_block_decoded_flags(int r, int c, int sb4) {
+    // spec 5.11.3: the row above and the column left of the superblock count as decoded where they lie inside the tile, everything
+    // else starts undecoded.  Row-wise fills instead of a branch per cell (this runs once per superblock and plane).
     for (int plane = 0; plane < seq.num_planes; plane++) {
-        int sx = plane ? seq.subsampling_x : 0, sy = plane ? seq.subsampling_y : 0;
-        int sbw4 = (mi_col_end - c) >> sx, sbh4 = (mi_row_end - r) >> sy;
-        for (int y = -1; y <= (sb4 >> sy); y++)
-            for (int x = -1; x <= (sb4 >> sx); x++) {
-                uint8_t v;
-                if (y < 0 && x < sbw4) v = 1;
-                else if (x < 0 && y < sbh4) v = 1;
-                else v = 0;
-                block_decoded[plane][y + 1][x + 1] = v;
-            }
-        block_decoded[plane][(sb4 >> sy) + 1][0] = 0;
+        const int sx = plane ? seq.subsampling_x : 0, sy = plane ? seq.subsampling_y : 0;
+        const int sbw4 = (mi_col_end - c) >> sx, sbh4 = (mi_row_end - r) >> sy;
+        const int nx = (sb4 >> sx) + 2, ny = (sb4 >> sy) + 2;          // cells x, y = -1 .. sb4 >> s?
+        uint8_t (*bd)[35] = block_decoded[plane];
+        // y = -1: decoded for x < sbw4 (x = -1 included)
+        const int n1 = std::min(nx, std::max(0, sbw4 + 1));
+        memset(bd[0], 1, (size_t)n1);
+        memset(bd[0] + n1, 0, (size_t)(nx - n1));
+        for (int y = 0; y < ny - 1; y++) {
+            memset(bd[y + 1], 0, (size_t)nx);
+            bd[y + 1][0] = y < sbh4;                                   // x = -1
+        }
+        bd[(sb4 >> sy) + 1][0] = 0;
     }
 }
 

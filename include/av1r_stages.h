@@ -1,10 +1,13 @@
-/* av1r stage-level entry points: one per reconstruction stage of SURVEY.md section 8(a2).
+/* av1r stage-level and measurement entry points.
  *
- * These exist so that every CUDA kernel family can be parity-tested and timed in isolation
- * against the oracle (libdav1d with apply_grain / inloop_filters toggled), exactly the way
- * the whole path is: plain pointers and sizes, no torch types.  All image pointers are DEVICE
- * pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream).  Pitches are in
- * bytes.  Samples are uint8 when bpc == 8, else uint16.
+ * Callable in isolation on caller-owned device planes: K8 film grain (av1r_stage_film_grain) and the K9 plane digest
+ * (av1r_stage_plane_checksum) -- the two stages whose whole input is a frame.  K1-K7 consume the parser's work-lists, which only
+ * exist inside the engine; they are isolated for parity the way libdav1d isolates them: av1r_config.inloop_filters (bit mask
+ * 1 = deblock, 2 = CDEF, 4 = loop restoration) and av1r_config.apply_grain switch stages off so that the output after each stage
+ * can be compared with the oracle run with the same switches (tests/test_decode_intra.py, tests/test_decode_inter.py), and
+ * av1r_clip_profile times every stage separately (CUDA events between the stages of a serialised replay).
+ * Plain pointers and sizes, no torch types.  All image pointers are DEVICE pointers; `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream).  Pitches are in bytes.  Samples are uint8 when bpc == 8, else uint16.
  */
 #ifndef AV1R_STAGES_H
 #define AV1R_STAGES_H

@@ -163,6 +163,51 @@ def decode(tus, n_threads=1, apply_grain=1, inloop_filters=7, keep=True, max_fra
     return out
 
 
+def decode_md5(tus, n_threads=1, apply_grain=1, inloop_filters=7):
+    """Per-frame per-plane MD5 (framemd5 domain: visible rows tightly packed, >8-bit as LE uint16) of libdav1d's output, computed
+    picture by picture so that BASELINE-size clips need not be held in memory.  -> list of [md5(Y), md5(U), md5(V)] hex strings."""
+    l = lib()
+    s = Dav1dSettings()
+    l.dav1d_default_settings(C.byref(s))
+    s.n_threads = n_threads
+    s.max_frame_delay = 0
+    s.apply_grain = apply_grain
+    s.inloop_filters = inloop_filters
+    ctx = C.c_void_p()
+    rc = l.dav1d_open(C.byref(ctx), C.byref(s))
+    if rc:
+        raise RuntimeError(f"dav1d_open {rc}")
+    out = []
+    pic = Dav1dPicture()
+
+    def pull():
+        got = False
+        while True:
+            C.memset(C.byref(pic), 0, C.sizeof(pic))
+            if l.dav1d_get_picture(ctx, C.byref(pic)) != 0:
+                return got
+            out.append(plane_md5(_grab(pic, True)[4]))
+            l.dav1d_picture_unref(C.byref(pic))
+            got = True
+
+    try:
+        for tu in tus:
+            d = Dav1dData()
+            p = l.dav1d_data_create(C.byref(d), len(tu))
+            C.memmove(p, tu, len(tu))
+            while d.sz > 0:
+                r = l.dav1d_send_data(ctx, C.byref(d))
+                if r not in (0, -11):
+                    l.dav1d_data_unref(C.byref(d))
+                    raise RuntimeError(f"dav1d_send_data {r}")
+                pull()
+        while pull():
+            pass
+    finally:
+        l.dav1d_close(C.byref(ctx))
+    return out
+
+
 def plane_md5(planes):
     """md5 over tightly packed visible rows; >8-bit as LE uint16 (framemd5 domain)."""
     return [hashlib.md5(np.ascontiguousarray(p).tobytes()).hexdigest() for p in planes]

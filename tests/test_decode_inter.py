@@ -147,11 +147,43 @@ def test_cuda_verify_buffer_many_multi_tu_segments(built):
         assert [int(x) for x in digests[i]] == want[i % len(want)], f"frame {i}"
 
 
+FULL_SIZE = ["c1", "c2", "c3_small", "c3", "c4"] + [f"c5_{i:02d}" for i in range(0, 32, 4)]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("clip", ["c1", "c3_small", "c3", "c4"])
-def test_cuda_full_size_clip_vs_dav1d(built, clip):
-    """BASELINE-size clips (when present in streams_cache/): every plane digest of every frame from av1r_verify_buffer equals the
-    digest of libdav1d's output for the same frame (the digest is a position-salted 64-bit hash; host restatement in the library)."""
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("clip", FULL_SIZE)
+def test_cuda_full_size_clip_md5_vs_dav1d(built, clip):
+    """All five BASELINE configs at full size (c5: every fourth file of the batch): per-frame **MD5 of the Y, U and V planes** from
+    the CUDA engine in parity mode (av1r_submit_tu / av1r_collect, parity_md5 = 1) equals the MD5 of libdav1d's output planes for the
+    same frame -- north_star's bit-exactness criterion.  The clips must be in streams_cache/ (they travel with the repo snapshot)."""
+    import av1recon
+    from oracle import dav1d_ref
+    from tools.make_streams import clip_path
+    from tools.obuio import read_ivf
+    path = clip_path(clip)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    tus = read_ivf(path)
+    want = dav1d_ref.decode_md5(tus, n_threads=os.cpu_count() or 4)
+    dec = av1recon.Decoder(parity_md5=1, streams=8, frames_in_flight=16)
+    for i, tu in enumerate(tus):
+        dec.submit(tu, i)
+    dec.flush()
+    got = [[bytes(r.md5[p]).hex() for p in range(3)] for r in dec.results]
+    dec.close()
+    assert len(got) == len(want) > 0
+    for i in range(len(want)):
+        assert got[i] == want[i], f"{clip} frame {i}: plane MD5 differs from libdav1d"
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("clip", ["c1", "c2", "c3", "c4", "c5_00"])
+def test_cuda_full_size_verify_digests_vs_dav1d(built, clip):
+    """The segment-parallel verify path (what bench.py's e2e times) on the full-size clips: every plane digest of every frame from
+    av1r_verify_buffer equals the digest of libdav1d's output for the same frame (position-salted 64-bit hash; host restatement in
+    the library)."""
     import ctypes as C
     import av1recon
     from oracle import dav1d_ref
@@ -175,3 +207,48 @@ def test_cuda_full_size_clip_vs_dav1d(built, clip):
             a = np.ascontiguousarray(fr[4][p].astype(np.uint8 if bpc == 8 else "<u2"))
             want = l.av1r_plane_checksum_host(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], bpc)
             assert int(digests[i][p]) == int(want), f"{clip} frame {i} plane {p}: digest differs from libdav1d"
+
+
+def test_baseline_clips_exercise_their_configs_tools(built):
+    """The clips in streams_cache/ really contain what their BASELINE config names (the 4K10 clip held no OBMC, no
+    masked compound and no loop restoration).  Same gate bench.py applies before it times a clip.  Host parser only."""
+    import av1recon
+    import importlib.util
+    from tools.make_streams import clip_path
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    checked = 0
+    for key in ("c1", "c2", "c3", "c4"):
+        path = clip_path(key)
+        if not os.path.exists(path):
+            continue
+        info = av1recon.parse_stats(open(path, "rb").read())
+        bench.check_clip_tools(key, info, av1recon.tool_hist(info))
+        checked += 1
+    # c5: gate on the sum over the files that exist
+    tot, n = None, 0
+    for i in range(32):
+        path = clip_path(f"c5_{i:02d}")
+        if not os.path.exists(path):
+            continue
+        info = av1recon.parse_stats(open(path, "rb").read())
+        n += 1
+        if tot is None:
+            tot = info
+        else:
+            for f in ("lr_frames", "cdef_frames", "deblock_frames", "grain_frames"):
+                setattr(tot, f, getattr(tot, f) + getattr(info, f))
+            for k in range(24):
+                tot.tool_hist[k] += info.tool_hist[k]
+    if n:
+        bench.check_clip_tools("c5", tot, av1recon.tool_hist(tot))
+        checked += 1
+    if not checked:
+        pytest.skip("no BASELINE-size clips in streams_cache/")
+    # and the gate does refuse: the all-intra clip cannot stand for the inter config
+    path = clip_path("c2")
+    if os.path.exists(path):
+        info = av1recon.parse_stats(open(path, "rb").read())
+        with pytest.raises(bench.ClipLacksTools):
+            bench.check_clip_tools("c3", info, av1recon.tool_hist(info))
