@@ -144,8 +144,8 @@ static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, obmc, warps, pal, k3order, k3units, total;
-    int n_recs, n_coefs, n_order, n_order_small, n_inter, n_obmc, n_warps, n_k3, n_k3units;
+    size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, itiles, obmc, warps, pal, k3order, k3units, total;
+    int n_recs, n_coefs, n_order, n_order_small, n_inter, n_itiles, n_obmc, n_warps, n_k3, n_k3units;
 };
 
 static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
@@ -221,6 +221,10 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     L.n_obmc = (int)fw.obmc.size();
     L.n_warps = (int)fw.warps.size();
     L.inter = take(sizeof(InterBlk) * std::max(1, L.n_inter));
+    // K2 work items: one per 64x64 luma quadrant of a prediction rectangle (a 128x128 block is four CTAs' worth of work, not one)
+    L.n_itiles = 0;
+    for (const InterBlk& b : fw.inter) L.n_itiles += ((b.w + 63) >> 6) * ((b.h + 63) >> 6);
+    L.itiles = take(sizeof(uint32_t) * std::max(1, L.n_itiles));
     L.obmc = take(sizeof(ObmcNb) * std::max(1, L.n_obmc));
     L.warps = take(sizeof(WarpRec) * std::max(1, L.n_warps));
     L.pal = take(std::max<size_t>(4, fw.pal.size()));
@@ -256,6 +260,16 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     for (int p = 0; p < 3; p++)
         if (!fw.lr[p].empty()) memcpy(h + L.lr[p], fw.lr[p].data(), sizeof(LrUnit) * fw.lr[p].size());
     if (L.n_inter) memcpy(h + L.inter, fw.inter.data(), sizeof(InterBlk) * L.n_inter);
+    {   // quadrant list: record index | quadrant << 28 (bit 0 of the quadrant = right half, bit 1 = bottom half)
+        uint32_t* it = (uint32_t*)(h + L.itiles);
+        int k = 0;
+        for (int i = 0; i < L.n_inter; i++) {
+            const InterBlk& b = fw.inter[i];
+            const int qx = (b.w + 63) >> 6, qy = (b.h + 63) >> 6;
+            for (int y = 0; y < qy; y++)
+                for (int x = 0; x < qx; x++) it[k++] = (uint32_t)i | ((uint32_t)(y * 2 + x) << 28);
+        }
+    }
     if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
     if (L.n_warps) memcpy(h + L.warps, fw.warps.data(), sizeof(WarpRec) * L.n_warps);
     if (!fw.pal.empty()) memcpy(h + L.pal, fw.pal.data(), fw.pal.size());
@@ -402,6 +416,10 @@ struct EngineImpl {
     int64_t frames_decoded = 0;
 
     int wait_slot(FrameSlot& s);
+    // Slot buffers of one kind grow together: a cudaFree / cudaMalloc pair drains the device, so when one slot needs a bigger buffer
+    // every slot gets the new size in that one stall instead of each slot stalling the pipeline later when it meets its first big
+    // frame (seen as 2x swings of the clip rate between otherwise identical runs).
+    int ensure_slots(DevBuf FrameSlot::*member, FrameSlot& s, size_t n, size_t& hw);
     int finish_pending(Pending& p);
     std::shared_ptr<DevFrameBuf> get_frame(const DevFrameParams& fp);
     StageTimer* tm = nullptr;             // set during av1r_clip_profile
@@ -447,6 +465,23 @@ std::shared_ptr<DevFrameBuf> EngineImpl::get_frame(const DevFrameParams& fp) {
     return pool[first_new];
 }
 
+int EngineImpl::ensure_slots(DevBuf FrameSlot::*member, FrameSlot& s, size_t n, size_t& hw) {
+    if (n <= (s.*member).cap) return 0;
+    const size_t want = std::max(align_up(n + n / 2, 1 << 20), hw);
+    hw = want;
+    CK(cudaDeviceSynchronize());
+    for (auto& sl : slots) {
+        DevBuf& b = (*sl).*member;
+        if (b.cap >= want) continue;
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        CK(cudaMalloc(&b.p, want));
+        b.cap = want;
+    }
+    return 0;
+}
+
 int EngineImpl::wait_slot(FrameSlot& s) {
     if (s.busy) CK(cudaEventSynchronize(s.ev1));
     s.busy = false;
@@ -480,7 +515,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         res.units_x = units_x;
         res.unit_elems = off;
-        CK(s.residual.ensure((size_t)units_x * units_y * off * sizeof(int16_t), &hw_residual));
+        { int e_ = ensure_slots(&FrameSlot::residual, s, (size_t)units_x * units_y * off * sizeof(int16_t), hw_residual); if (e_) return e_; }
         res.base = (int16_t*)s.residual.p;
     }
     const TxRec* d_recs = (const TxRec*)(d_arena + L.recs);
@@ -495,6 +530,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.obmc = (const ObmcNb*)(d_arena + L.obmc);
         xl.warps = (const WarpRec*)(d_arena + L.warps);
         xl.n = L.n_inter;
+        xl.tiles = (const uint32_t*)(d_arena + L.itiles);
+        xl.n_tiles = L.n_itiles;
         memset(xl.refs, 0, sizeof(xl.refs));
         for (int i = 0; i < REFS_PER_FRAME; i++) {
             const int slot = dw.fh.ref_frame_idx[i];
@@ -513,7 +550,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.cur = recon->pl;
         xl.fp = fp;
         xl.mask_pitch = (uint32_t)align_up((size_t)fp.cw[0], 256);
-        CK(s.diffmask.ensure((size_t)xl.mask_pitch * fp.ch[0], &hw_mask));
+        { int e_ = ensure_slots(&FrameSlot::diffmask, s, (size_t)xl.mask_pitch * fp.ch[0], hw_mask); if (e_) return e_; }
         xl.mask = s.diffmask.p;
         CK(launch_inter(xl, st));
         if (tm) tm->end(AV1R_ST_INTER, 1, st);
@@ -543,7 +580,11 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         il.load_tile = L.n_inter > 0;
         // sync block: [n_units x u64 progress words][n_units x int unit flags][ticket, stuck flag, pad]
         const size_t sync_bytes = (sizeof(unsigned long long) + sizeof(int)) * (size_t)L.n_k3units + 4 * sizeof(int);
-        CK(s.sync.ensure(sync_bytes, &hw_sync));
+        {   // sized for the frame geometry (one entry per 64x64 unit), not for this frame's unit count
+            const size_t cap_bytes = (sizeof(unsigned long long) + sizeof(int)) * (size_t)(((fp.mi_cols + 15) >> 4) * ((fp.mi_rows + 15) >> 4)) + 4 * sizeof(int);
+            int e_ = ensure_slots(&FrameSlot::sync, s, std::max(sync_bytes, cap_bytes), hw_sync);
+            if (e_) return e_;
+        }
         CK(cudaMemsetAsync(s.sync.p, 0, sync_bytes, st));
         il.uprog = (unsigned long long*)s.sync.p;
         il.uflags = (int*)(s.sync.p + sizeof(unsigned long long) * (size_t)L.n_k3units);
@@ -861,7 +902,7 @@ int EngineImpl::decode_parsed(ParsedFrame& pf) {
         HostArena& ha = *(HostArena*)pf.host.get();
         auto ti = EP_T();
         auto t1 = EP_T();
-        CK(s.arena.ensure(ha.dw.lay.total, &hw_arena));
+        { int e_ = ensure_slots(&FrameSlot::arena, s, ha.dw.lay.total, hw_arena); if (e_) return e_; }
         EP_ADD(16, t1);
         s.host_arena = pf.host;
         t1 = EP_T();
@@ -879,7 +920,7 @@ int EngineImpl::decode_parsed(ParsedFrame& pf) {
     if (rc) return rc;
     auto tf = EP_T();
     CK(s.staging.ensure(dw.lay.total, &hw_staging));
-    CK(s.arena.ensure(dw.lay.total, &hw_arena));
+    { int e_ = ensure_slots(&FrameSlot::arena, s, dw.lay.total, hw_arena); if (e_) return e_; }
     fill_arena(fw, dw, s.staging.p);
     EP_ADD(2, tf);
     auto ti = EP_T();
@@ -1669,7 +1710,7 @@ static int replay(EngineImpl& E, av1r_clip* clip) {
                 d_arena = cf->arena.p;
             } else {
                 auto t_a = EP_T();
-                CK(s.arena.ensure(cf->dw.lay.total, &E.hw_arena));
+                { int e_ = E.ensure_slots(&FrameSlot::arena, s, cf->dw.lay.total, E.hw_arena); if (e_) return e_; }
                 if (E.tm) E.tm->begin(s.stream);
                 CK(cudaMemcpyAsync(s.arena.p, cf->host, cf->dw.lay.total, cudaMemcpyHostToDevice, s.stream));
                 if (E.tm) E.tm->end(AV1R_ST_H2D, 1, s.stream);
@@ -1697,7 +1738,7 @@ int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, 
         size_t mx = 0;
         for (auto& cf : clip->frames)
             if (!cf->show_existing) mx = std::max(mx, cf->dw.lay.total);
-        for (auto& sl : E.slots) CK(sl->arena.ensure(mx, &E.hw_arena));
+        if (!E.slots.empty()) { int e_ = E.ensure_slots(&FrameSlot::arena, *E.slots[0], mx, E.hw_arena); if (e_) return e_; }
     }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));

@@ -90,9 +90,10 @@ __device__ __forceinline__ void fetch_window_fast(const uint8_t* ref, uint32_t p
                                                   uint16_t* win) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x0 = ix - 3, y0 = iy - 3;
-    const bool interior = x0 >= 0 && y0 >= 0 && x0 + ww - 1 <= lastx && y0 + wh - 1 <= lasty;
+    constexpr int SPW = 4 / (int)sizeof(T);                  // samples per 32-bit word: 2 (uint16) or 4 (uint8)
+    // interior: every 32-bit word the rows are fetched with lies inside the visible reference frame
+    const bool interior = x0 >= 0 && y0 >= 0 && ((x0 + ww - 1) | (SPW - 1)) <= lastx && y0 + wh - 1 <= lasty;
     if (interior) {
-        constexpr int SPW = 4 / (int)sizeof(T);              // samples per 32-bit word: 2 (uint16) or 4 (uint8)
         const int xs = x0 & ~(SPW - 1), sh = (x0 - xs) * 8 * (int)sizeof(T);
         const int nwords = ((x0 + ww - 1 - xs) / SPW) + 1;   // <= 21 (uint16) / 11 (uint8)
         const uint8_t* base = ref + (size_t)y0 * pitch + (size_t)xs * sizeof(T);
@@ -288,6 +289,100 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
     __syncthreads();
 }
 
+// ---- warped prediction, 16-bit samples: packed dot products ---------------------------------------------------------------------
+// The warp filter has a different 8-tap phase for every sample, so the work per sample is fixed: what can shrink is the number of
+// instructions around the 8 + 8 multiply-adds.  All 193 x 8 taps fit a signed byte, samples and the horizontal intermediate fit a
+// signed 16-bit lane, so a pair of taps times a pair of samples is one IDP.2A (same issue rate as IMAD on sm_100a:
+// tools/micro/idp_bench.cu): 5 per output instead of 8 IMAD + 8 unpacks, with the odd start positions handled by shifting the
+// 64-bit tap vector by one byte instead of re-packing samples.  The 15 x 15 support is fetched as 32-bit words (no clamps) when it
+// lies inside the reference; the horizontal intermediate is stored transposed so that the vertical pass reads packed row pairs.
+__device__ __align__(8) int8_t d_warped_filter8[193][8];
+
+__device__ __forceinline__ int dot8_packed(const uint32_t* w, int start, uint2 taps) {
+    // sum over t < 8 of taps[t] * sample[start + t], samples packed two per word in w[]
+    const int sh = (start & 1) << 3;
+    const uint32_t* q = w + (start >> 1);
+    const int t0 = (int)(taps.x << sh), t1 = (int)__funnelshift_l(taps.x, taps.y, sh), t2 = (int)__funnelshift_l(taps.y, 0u, sh);
+    int s = __dp2a_lo((int)q[0], t0, 0);
+    s = __dp2a_hi((int)q[1], t0, s);
+    s = __dp2a_lo((int)q[2], t1, s);
+    s = __dp2a_hi((int)q[3], t1, s);
+    s = __dp2a_lo((int)q[4], t2, s);
+    return s;
+}
+
+__device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw,
+                            int th, int round1, InterSmem& sm, int32_t* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* win = reinterpret_cast<uint32_t*>(sm.refwin) + warp * 132;   // 15 rows x 8 words (+ slack for the fifth word of the last row)
+    uint32_t* wmt = reinterpret_cast<uint32_t*>(sm.mid) + warp * 80;       // transposed intermediate: 8 columns x 9 words (15 int16 + pad)
+    const int nbx = tw >> 3, lnbx = 31 - __clz(nbx), nb = nbx * (th >> 3);
+    const int rnd = 1 << (round1 - 1);
+    for (int b = warp; b < nb; b += INTER_THREADS / 32) {
+        const int i8 = b >> lnbx, j8 = b & (nbx - 1);
+        const int src_x = (x0 + j8 * 8 + 4) << sx, src_y = (y0 + i8 * 8 + 4) << sy;
+        const long long dst_x = (long long)wr.mat[2] * src_x + (long long)wr.mat[3] * src_y + wr.mat[0];
+        const long long dst_y = (long long)wr.mat[4] * src_x + (long long)wr.mat[5] * src_y + wr.mat[1];
+        const long long x4 = dst_x >> sx, y4 = dst_y >> sy;
+        const int ix4 = (int)(x4 >> 16), sx4 = (int)(x4 & 0xFFFF), iy4 = (int)(y4 >> 16), sy4 = (int)(y4 & 0xFFFF);
+        const int xl = ix4 - 7, yt = iy4 - 7;
+        int off;                                                     // window column 0 sits at sample `off` of a row's first word
+        if (xl >= 0 && yt >= 0 && (xl & ~1) + 15 <= lastx && yt + 14 <= lasty) {   // all eight words of every row inside the frame
+            const int xs = xl & ~1;
+            off = xl - xs;
+            const uint8_t* base = ref + (size_t)yt * pitch + (size_t)xs * 2;
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = lane + 32 * u, r = idx >> 3, c = idx & 7;
+                v[u] = r < 15 ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * pitch) + c) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = lane + 32 * u;
+                if (idx < 15 * 8) win[idx] = v[u];
+            }
+        } else {                                                     // leaves the reference frame: clamped samples, packed by pairs
+            off = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = lane + 32 * u, r = idx >> 3, c = idx & 7;
+                if (r < 15) {
+                    const uint16_t* row = (const uint16_t*)(ref + (size_t)min(max(yt + r, 0), lasty) * pitch);
+                    const uint32_t a = __ldg(row + min(max(xl + 2 * c, 0), lastx)), bb = __ldg(row + min(max(xl + 2 * c + 1, 0), lastx));
+                    win[idx] = a | (bb << 16);
+                }
+            }
+        }
+        __syncwarp();
+        int16_t* wmt16 = reinterpret_cast<int16_t*>(wmt);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {                                // horizontal: 15 rows x 8 columns
+            const int idx = lane + 32 * u;
+            if (idx < 15 * 8) {
+                const int r = idx >> 3, c = idx & 7;                 // i1 = r - 7, i2 = c - 4
+                const int sxx = sx4 + wr.alpha * (c - 4) + wr.beta * (r - 7);
+                const int offs = ((sxx + 512) >> 10) + 64;
+                const uint2 taps = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[offs]));
+                const int s = dot8_packed(win + r * 8, off + c, taps);
+                wmt16[c * 18 + r] = (int16_t)((s + 4) >> 3);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 2; u++) {                                // vertical: 8 x 8 outputs
+            const int idx = lane + 32 * u, orow = idx >> 3, c = idx & 7;   // i1 = orow - 4, i2 = c - 4
+            const int syy = sy4 + wr.gamma * (c - 4) + wr.delta * (orow - 4);
+            const int offs = ((syy + 512) >> 10) + 64;
+            const uint2 taps = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[offs]));
+            const int s = dot8_packed(wmt + c * 9, orow, taps);
+            out[(i8 * 8 + orow) * IT + j8 * 8 + c] = (s + rnd) >> round1;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
 // warped prediction of a tile (multiples of 8): one warp per 8x8 sub-block
 template <typename T>
 __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw, int th,
@@ -357,7 +452,9 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
 template <typename T>
 __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunch L) {
     __shared__ InterSmem sm;
-    const InterBlk r = L.blks[blockIdx.x];
+    const uint32_t item = L.tiles[blockIdx.x];
+    const InterBlk r = L.blks[item & 0x0fffffffu];
+    const int qx0 = ((item >> 28) & 1) << 6, qy0 = ((item >> 29) & 1) << 6;   // luma origin of this CTA's 64x64 quadrant inside the block
     const DevFrameParams& fp = L.fp;
     const int pixmax = (1 << fp.bd) - 1;
     const int is_compound = r.ref[1] >= 0;
@@ -373,14 +470,19 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
         const int lastx = fp.w[plane] - 1, lasty = fp.h[plane] - 1;
         T* cur = (T*)L.cur.p[plane];
         const int cpe = L.cur.pitch[plane] / sizeof(T);
-        for (int ty = 0; ty < ph; ty += IT)
-            for (int tx = 0; tx < pw; tx += IT) {
+        const int rx0 = qx0 >> sx, ry0 = qy0 >> sy, rx1 = min(pw, (qx0 + 64) >> sx), ry1 = min(ph, (qy0 + 64) >> sy);
+        for (int ty = ry0; ty < ry1; ty += IT)
+            for (int tx = rx0; tx < rx1; tx += IT) {
                 const int tw = min(IT, pw - tx), th = min(IT, ph - ty);
                 for (int l = 0; l < 1 + is_compound; l++) {
                     const DevPlanes& rf = L.refs[r.ref[l]];
                     if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) {
-                        warp_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
-                                     sm.pred[l]);
+                        if (sizeof(T) == 2)
+                            warp_tile16(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
+                                        sm.pred[l]);
+                        else
+                            warp_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
+                                         sm.pred[l]);
                     } else {
                         const int posx = ((px + tx) << 4) + ((2 * r.mv[l][1]) >> sx), posy = ((py + ty) << 4) + ((2 * r.mv[l][0]) >> sy);
                         predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
@@ -515,9 +617,12 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
             const int ox = (nb.x4 * 4) >> sx, oy = (nb.y4 * 4) >> sy;
             const DevPlanes& rf = L.refs[nb.ref];
             const uint8_t* m = d_obmc_mask[31 - __clz(above ? oh : ow)];
+            // absolute plane rectangle of this CTA's quadrant: only overlap samples inside it are blended here
+            const int ax0 = px + rx0, ay0 = py + ry0, ax1 = px + rx1, ay1 = py + ry1;
             for (int ty = 0; ty < oh; ty += IT)
                 for (int tx = 0; tx < ow; tx += IT) {
                     const int tw = min(IT, ow - tx), th = min(IT, oh - ty);
+                    if (ox + tx >= ax1 || ox + tx + tw <= ax0 || oy + ty >= ay1 || oy + ty + th <= ay0) continue;   // CTA-uniform
                     const int posx = ((ox + tx) << 4) + ((2 * nb.mv[1]) >> sx), posy = ((oy + ty) << 4) + ((2 * nb.mv[0]) >> sy);
                     predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
                                     filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm, sm.pred[0]);
@@ -525,7 +630,7 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                     for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
                         const int i = div16(idx, inv_tw), j = idx - i * tw;
                         const int gx = ox + tx + j, gy = oy + ty + i;
-                        if (gx >= fp.cw[plane] || gy >= fp.ch[plane]) continue;
+                        if (gx >= fp.cw[plane] || gy >= fp.ch[plane] || gx < ax0 || gx >= ax1 || gy < ay0 || gy >= ay1) continue;
                         const int o = min(max(sm.pred[0][i * IT + j], 0), pixmax);
                         const int mm = above ? m[ty + i] : m[tx + j];
                         T* p = cur + (size_t)gy * cpe + gx;
@@ -581,6 +686,12 @@ static cudaError_t inter_upload_constants() {
     if ((e = cudaMemcpyToSymbol(c_blk_w, kBlockW, sizeof(kBlockW))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_blk_h, kBlockH, sizeof(kBlockH))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(d_warped_filter, av1t_warped_filter, sizeof(av1t_warped_filter))) != cudaSuccess) return e;
+    {
+        static int8_t f8[193][8];
+        for (int i = 0; i < 193; i++)
+            for (int t = 0; t < 8; t++) f8[i][t] = (int8_t)av1t_warped_filter[i][t];   // all taps lie in -22 .. 127
+        if ((e = cudaMemcpyToSymbol(d_warped_filter8, f8, sizeof(f8))) != cudaSuccess) return e;
+    }
     if ((e = cudaMemcpyToSymbol(d_obmc_mask, av1t_obmc_mask, sizeof(av1t_obmc_mask))) != cudaSuccess) return e;
     // wedge master masks (spec 7.11.3.11)
     static uint8_t master[6][64][64];
@@ -616,7 +727,7 @@ cudaError_t inter_copy_wedge_master(uint8_t* dst_dev, cudaStream_t s) {
 }
 
 cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
-    if (L.n <= 0) return cudaSuccess;
+    if (L.n <= 0 || L.n_tiles <= 0) return cudaSuccess;
     cudaError_t e = inter_upload_constants();
     if (e != cudaSuccess) return e;
     {
@@ -629,8 +740,8 @@ cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
             carve_done = true;
         }
     }
-    if (L.fp.bd == 8) inter_pred_kernel<uint8_t><<<L.n, INTER_THREADS, 0, s>>>(L);
-    else inter_pred_kernel<uint16_t><<<L.n, INTER_THREADS, 0, s>>>(L);
+    if (L.fp.bd == 8) inter_pred_kernel<uint8_t><<<L.n_tiles, INTER_THREADS, 0, s>>>(L);
+    else inter_pred_kernel<uint16_t><<<L.n_tiles, INTER_THREADS, 0, s>>>(L);
     return cudaGetLastError();
 }
 

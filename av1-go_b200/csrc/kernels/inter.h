@@ -11,6 +11,8 @@ struct InterLaunch {
     const ObmcNb* obmc;        // device
     const WarpRec* warps;      // device
     int n;
+    const uint32_t* tiles;     // device, n_tiles work items: record index | quadrant << 28 (one CTA per 64x64 luma quadrant of a record)
+    int n_tiles;
     DevPlanes refs[8];         // reference slots (same geometry as the current frame: scaled references are rejected by the host)
     DevPlanes cur;             // frame being reconstructed
     uint8_t* mask;             // device, luma-sized byte plane: difference-weighted compound masks (COMPOUND_DIFFWTD blocks only)

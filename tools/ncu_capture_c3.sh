@@ -1,7 +1,8 @@
-# ncu evidence for the 4K10 inter clip (c3): launch list + --set full of K2 (run on the GPU box through gpurun)
+# ncu evidence for the 4K10 inter clip (c3): launch list + --set full of one kernel family (run on the GPU box through gpurun)
+# usage: bash tools/ncu_capture_c3.sh TAG KERNEL_REGEX [SKIP] [COUNT]
+TAG=${1:-r2}; KREGEX=${2:-inter_pred}; SKIP=${3:-12}; COUNT=${4:-2}
 set -x
-B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload c3_4k10_inter"
-timeout 300 $B > gpurun_out/plain_r1d_c3.log 2>&1 || exit 1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 800 --csv --log-file gpurun_out/launches_r1d_c3.csv $B > gpurun_out/ncu_r1d_c3_a.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:inter_pred -s 12 -c 2 -f -o gpurun_out/prof_k2_r1d $B > gpurun_out/ncu_r1d_c3_b.log 2>&1
-ls -la gpurun_out/prof_k2_r1d.ncu-rep gpurun_out/launches_r1d_c3.csv
+B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-per-config --workload c3_4k10_inter"
+timeout 300 $B > gpurun_out/plain_${TAG}_c3.log 2>&1 || exit 1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s $SKIP -c $COUNT -f -o gpurun_out/prof_${TAG}_$KREGEX $B > gpurun_out/ncu_${TAG}_c3_b.log 2>&1
+ls -la gpurun_out/prof_${TAG}_$KREGEX.ncu-rep
