@@ -4,7 +4,8 @@
 // is staged in shared memory once, with the normative stripe rule applied while loading (rows outside
 // the stripe come from the deblocked, pre-CDEF frame and only the 2 nearest are used; columns/rows clamp
 // at the plane edges) -- after that both filters run purely out of shared memory.  Out of place; units
-// whose type is NONE are copied through.  Algorithmic bytes ~2.06 F (4 boundary rows per 64-row stripe).
+// whose type is NONE are copied through with 128-bit streaming loads / stores.  Algorithmic bytes ~2.06 F
+// (4 boundary rows per 64-row stripe).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -16,16 +17,19 @@
 namespace av1r {
 
 static constexpr int LR_TW = 64, LR_TH = 64, LR_H = 3;
-static constexpr int LR_SW = LR_TW + 2 * LR_H;      // staged tile width
-static constexpr int LR_SH = LR_TH + 2 * LR_H;
+static constexpr int LR_SH = LR_TH + 2 * LR_H;      // staged rows
+// Staged tile: row stride 80 samples (160 B, 16-byte aligned); tile column c (sample x0 - 3 + c) lives at row offset c + 1, so that
+// offset 0 is sample x0 - 4 -- an 8-byte aligned address in the frame (x0 is a multiple of 64) and rows come in as 64-bit loads.
+static constexpr int LR_SW = 80;
+static constexpr int LR_IW = LR_TW + 8;             // row stride of the Wiener intermediate (144 B, 16-byte aligned)
 
 __constant__ int16_t c_sgr_params[16][4];
 static bool g_lr_const_loaded[64] = {false};
 
 struct LrSmem {
-    uint16_t tile[LR_SH * LR_SW];
+    __align__(16) uint16_t tile[LR_SH * LR_SW];
     union {
-        int16_t inter[LR_SH * LR_TW];                          // Wiener horizontal pass
+        __align__(16) int16_t inter[LR_SH * LR_IW];            // Wiener horizontal pass
         struct {
             uint16_t A[(LR_TH + 2) * (LR_TW + 2)];
             int32_t B[(LR_TH + 2) * (LR_TW + 2)];
@@ -33,14 +37,21 @@ struct LrSmem {
     } u;
 };
 
+// K7: one CTA per (64-column tile, 64-luma-row stripe, plane).
+//   staging : a warp per row; rows of interior tiles arrive as 64-bit loads (four 16-bit samples), edge tiles sample by sample with
+//             the column clamp.  The stripe rule picks the source row: CDEF output inside the stripe, the deblocked frame for the
+//             (at most two) rows used above / below it.
+//   Wiener  : horizontal pass 8 outputs per thread from two 128-bit shared loads (symmetric taps: 4 multiplies per output), packed
+//             int16 intermediate; vertical pass two columns x four rows per thread, 32-bit stores.
+//   SGR     : box sums from shared memory, projection, stores.
 template <typename T>
 __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
     __shared__ LrSmem sm;
     const int plane = blockIdx.z;
     const DevFrameParams& fp = L.fp;
-    const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
+    const int sy = plane ? fp.suby : 0;
     const int pw = fp.w[plane], ph = fp.h[plane];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stripe = blockIdx.y;
     const int ls = -8 + stripe * 64;
     const int ys = ls >> sy, ye = ys + (64 >> sy) - 1;          // StripeStartY / StripeEndY in plane rows
@@ -65,53 +76,110 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
         type = u.type;
     }
     if (type == RESTORE_NONE_D) {
+        if (sizeof(T) == 2 && (w & 7) == 0) {   // rows of 16-byte pieces (x0 is a multiple of 64 samples)
+            const int lg = 31 - __clz(w >> 3);
+            if ((w >> 3) == (1 << lg)) {
+                for (int i = tid; i < (h << lg); i += 256) {
+                    const int r = i >> lg, c = (i & ((1 << lg) - 1)) << 3;
+                    st_stream128(dst + (size_t)(y0 + r) * ope + x0 + c, ld_stream128(cdef + (size_t)(y0 + r) * cpe + x0 + c));
+                }
+                return;
+            }
+        }
         for (int i = tid; i < w * h; i += 256) {
             const int r = i / w, c = i - r * w;
             dst[(size_t)(y0 + r) * ope + x0 + c] = cdef[(size_t)(y0 + r) * cpe + x0 + c];
         }
         return;
     }
-    // ---- stage the tile: sample(x0 - 3 + c, y0 - 3 + r) with the stripe rule
-    for (int i = tid; i < (h + 6) * (w + 6); i += 256) {
-        const int r = i / (w + 6), c = i - r * (w + 6);
-        int x = min(max(x0 - 3 + c, 0), pw - 1);
-        int y = min(max(y0 - 3 + r, 0), ph - 1);
-        int v;
-        if (y < ys) v = dbl[(size_t)max(ys - 2, y) * dpe + x];
-        else if (y > ye) v = dbl[(size_t)min(ye + 2, y) * dpe + x];
-        else v = cdef[(size_t)y * cpe + x];
-        sm.tile[r * LR_SW + c] = (uint16_t)v;
+    // ---- stage the tile: sample(x0 - 3 + c, y0 - 3 + r) with the stripe rule, at tile[r * LR_SW + c + 1]
+    {
+        const bool fast = sizeof(T) == 2 && x0 >= 4 && x0 + w + 3 <= pw - 1 && (size_t)(x0 + 72) * sizeof(T) <= L.cdef.pitch[plane] &&
+                          (size_t)(x0 + 72) * sizeof(T) <= L.deblocked.pitch[plane];
+        for (int r = warp; r < h + 6; r += 8) {
+            const int y = min(max(y0 - 3 + r, 0), ph - 1);
+            const T* row;
+            if (y < ys) row = dbl + (size_t)max(ys - 2, y) * dpe;
+            else if (y > ye) row = dbl + (size_t)min(ye + 2, y) * dpe;
+            else row = cdef + (size_t)y * cpe;
+            if (fast) {
+                if (lane < 19) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + x0 - 4) + lane);
+                    reinterpret_cast<uint2*>(sm.tile + r * LR_SW)[lane] = v;
+                }
+            } else {
+                for (int c = lane; c < w + 6; c += 32) sm.tile[r * LR_SW + c + 1] = (uint16_t)row[min(max(x0 - 3 + c, 0), pw - 1)];
+            }
+        }
     }
     __syncthreads();
     if (type == RESTORE_WIENER_D) {
         const int round0 = bd == 12 ? 5 : 3, round1 = bd == 12 ? 9 : 11;
-        int vf[7], hf[7];
+        int vf[4], hf[4];                                        // taps 0..2 and the centre tap (symmetric filters)
         vf[3] = hf[3] = 128;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            vf[i] = vf[6 - i] = u.wiener[0][i];
+            vf[i] = u.wiener[0][i];
             vf[3] -= 2 * u.wiener[0][i];
-            hf[i] = hf[6 - i] = u.wiener[1][i];
+            hf[i] = u.wiener[1][i];
             hf[3] -= 2 * u.wiener[1][i];
         }
         const int offset = 1 << (bd + 7 - round0 - 1);
         const int limit = (1 << (bd + 1 + 7 - round0)) - 1;
-        for (int i = tid; i < (h + 6) * w; i += 256) {
-            const int r = i / w, c = i - r * w;
-            int s = 0;
+        const int rnd0 = 1 << (round0 - 1), lo = -offset, hi = limit - offset;
+        for (int idx = tid; idx < (h + 6) * 8; idx += 256) {   // horizontal: (row, group of 8 columns)
+            const int r = idx >> 3, c0 = (idx & 7) << 3;
+            if (c0 >= w) continue;
+            const uint4* wp = reinterpret_cast<const uint4*>(sm.tile + r * LR_SW + c0);
+            const uint4 a = wp[0], b = wp[1];
+            const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            int x[16];
 #pragma unroll
-            for (int t = 0; t < 7; t++) s += hf[t] * sm.tile[r * LR_SW + c + t];
-            const int v = (s + (1 << (round0 - 1))) >> round0;
-            sm.u.inter[r * LR_TW + c] = (int16_t)min(max(v, -offset), limit - offset);
+            for (int k = 0; k < 8; k++) {
+                x[2 * k] = (int)(wv[k] & 0xffffu);
+                x[2 * k + 1] = (int)(wv[k] >> 16);
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {                       // output column c0 + k reads tile columns c0 + k .. c0 + k + 6 = x[k + 1 .. k + 7]
+                int s = rnd0 + hf[3] * x[k + 4];
+                s += hf[0] * (x[k + 1] + x[k + 7]);
+                s += hf[1] * (x[k + 2] + x[k + 6]);
+                s += hf[2] * (x[k + 3] + x[k + 5]);
+                const int v = min(max(s >> round0, lo), hi);
+                if (k & 1) o[k >> 1] |= (uint32_t)v << 16;
+                else o[k >> 1] = (uint32_t)v & 0xffffu;
+            }
+            *reinterpret_cast<uint4*>(sm.u.inter + r * LR_IW + c0) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
-        for (int i = tid; i < h * w; i += 256) {
-            const int r = i / w, c = i - r * w;
-            int s = 0;
+        const int rnd1 = 1 << (round1 - 1);
+        for (int idx = tid; idx < ((h + 3) >> 2) * 32; idx += 256) {   // vertical: (column pair, group of 4 rows)
+            const int cp = idx & 31, r0 = (idx >> 5) << 2;
+            if (2 * cp >= w) continue;
+            const uint32_t* mp = reinterpret_cast<const uint32_t*>(sm.u.inter + r0 * LR_IW) + cp;
+            int lo_[10], hi_[10];
 #pragma unroll
-            for (int t = 0; t < 7; t++) s += vf[t] * sm.u.inter[(r + t) * LR_TW + c];
-            const int v = (s + (1 << (round1 - 1))) >> round1;
-            dst[(size_t)(y0 + r) * ope + x0 + c] = (T)min(max(v, 0), pixmax);
+            for (int t = 0; t < 10; t++) {
+                const uint32_t v = (r0 + t < h + 6) ? mp[t * (LR_IW / 2)] : 0u;
+                lo_[t] = (int)(short)(v & 0xffffu);
+                hi_[t] = (int)v >> 16;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (r0 + k >= h) break;
+                int s0 = rnd1 + vf[3] * lo_[k + 3], s1 = rnd1 + vf[3] * hi_[k + 3];
+                s0 += vf[0] * (lo_[k] + lo_[k + 6]) + vf[1] * (lo_[k + 1] + lo_[k + 5]) + vf[2] * (lo_[k + 2] + lo_[k + 4]);
+                s1 += vf[0] * (hi_[k] + hi_[k + 6]) + vf[1] * (hi_[k + 1] + hi_[k + 5]) + vf[2] * (hi_[k + 2] + hi_[k + 4]);
+                const int v0 = min(max(s0 >> round1, 0), pixmax), v1 = min(max(s1 >> round1, 0), pixmax);
+                T* dp = dst + (size_t)(y0 + r0 + k) * ope + x0 + 2 * cp;
+                if (2 * cp + 1 < w) {
+                    if (sizeof(T) == 2) *reinterpret_cast<uint32_t*>(dp) = (uint32_t)v0 | ((uint32_t)v1 << 16);
+                    else *reinterpret_cast<uint16_t*>(dp) = (uint16_t)(v0 | (v1 << 8));
+                } else {
+                    dp[0] = (T)v0;
+                }
+            }
         }
         return;
     }
@@ -121,17 +189,20 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
     constexpr int PPT = LR_TW * LR_TH / 256;      // pixels per thread
     int f0[PPT];
     const int gw = w + 2;
+    const uint16_t* tile = sm.tile + 1;           // tile column c at tile[r * LR_SW + c]
     for (int pass = 0; pass < 2; pass++) {
         const int r = pass ? r1 : r0, sp = pass ? s1 : s0;
         if (r) {
             const int n = (2 * r + 1) * (2 * r + 1);
             const uint32_t one_by_n = ((1u << 12) + n / 2) / n;
+            // pass 0 (r = 2) only ever reads the odd grid rows (weights of the even ones are zero): skip the others
             for (int i = tid; i < (h + 2) * gw; i += 256) {
                 const int gi = i / gw, gj = i - gi * gw;     // grid point (gi - 1, gj - 1) -> tile centre (gi + 2, gj + 2)
+                if (pass == 0 && !((gi - 1) & 1)) continue;
                 uint32_t a = 0, b = 0;
                 for (int dy = -r; dy <= r; dy++)
                     for (int dx = -r; dx <= r; dx++) {
-                        const uint32_t v = sm.tile[(gi + 2 + dy) * LR_SW + gj + 2 + dx];
+                        const uint32_t v = tile[(gi + 2 + dy) * LR_SW + gj + 2 + dx];
                         a += v * v;
                         b += v;
                     }
@@ -153,20 +224,38 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
         int k = 0;
         for (int i = tid; i < h * w; i += 256, k++) {
             const int pr = i / w, pc = i - pr * w;
-            const int uu = (int)sm.tile[(pr + 3) * LR_SW + pc + 3];
+            const int uu = (int)tile[(pr + 3) * LR_SW + pc + 3];
             int f = uu << 4;
             if (r) {
                 int a = 0, b = 0;
+                if (pass == 0) {
+                    if (pr & 1) {     // odd row: the grid row itself, weights 5 6 5
 #pragma unroll
-                for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            const int wgt = dx == 0 ? 6 : 5;
+                            a += wgt * (int)sm.u.sg.A[(pr + 1) * (LR_TW + 2) + pc + 1 + dx];
+                            b += wgt * sm.u.sg.B[(pr + 1) * (LR_TW + 2) + pc + 1 + dx];
+                        }
+                    } else {          // even row: the odd grid rows above and below, weights 5 6 5 each
 #pragma unroll
-                    for (int dx = -1; dx <= 1; dx++) {
-                        int wgt;
-                        if (pass == 0) wgt = ((pr + dy) & 1) ? (dx == 0 ? 6 : 5) : 0;
-                        else wgt = (dx == 0 || dy == 0) ? 4 : 3;
-                        a += wgt * (int)sm.u.sg.A[(pr + 1 + dy) * (LR_TW + 2) + pc + 1 + dx];
-                        b += wgt * sm.u.sg.B[(pr + 1 + dy) * (LR_TW + 2) + pc + 1 + dx];
+                        for (int dy = -1; dy <= 1; dy += 2)
+#pragma unroll
+                            for (int dx = -1; dx <= 1; dx++) {
+                                const int wgt = dx == 0 ? 6 : 5;
+                                a += wgt * (int)sm.u.sg.A[(pr + 1 + dy) * (LR_TW + 2) + pc + 1 + dx];
+                                b += wgt * sm.u.sg.B[(pr + 1 + dy) * (LR_TW + 2) + pc + 1 + dx];
+                            }
                     }
+                } else {
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) {
+                            const int wgt = (dx == 0 || dy == 0) ? 4 : 3;
+                            a += wgt * (int)sm.u.sg.A[(pr + 1 + dy) * (LR_TW + 2) + pc + 1 + dx];
+                            b += wgt * sm.u.sg.B[(pr + 1 + dy) * (LR_TW + 2) + pc + 1 + dx];
+                        }
+                }
                 int shift = 5;
                 if (pass == 0 && (pr & 1)) shift = 4;
                 const int v = a * uu + b;
