@@ -737,9 +737,13 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
     CK(s->cks_dev.ensure(64));
     CK(s->cks_host.ensure(64));
     const int np = fp.mono ? 1 : 3;
-    for (int p = 0; p < np; p++)
-        CK(launch_plane_checksum(shown->pl.p[p], shown->pl.pitch[p], fp.w[p], fp.h[p], fp.bd, (uint64_t*)s->cks_dev.p + p, st));
-    if (tm) tm->end(AV1R_ST_DIGEST, np, st);
+    {
+        const void* src3[3] = {shown->pl.p[0], shown->pl.p[1], shown->pl.p[2]};
+        const size_t pitch3[3] = {shown->pl.pitch[0], shown->pl.pitch[1], shown->pl.pitch[2]};
+        const int w3[3] = {fp.w[0], fp.w[1], fp.w[2]}, h3[3] = {fp.h[0], fp.h[1], fp.h[2]};
+        CK(launch_frame_checksum(src3, pitch3, w3, h3, np, fp.bd, (uint64_t*)s->cks_dev.p, st));
+    }
+    if (tm) tm->end(AV1R_ST_DIGEST, 1, st);
     CK(cudaMemcpyAsync(s->cks_host.p, s->cks_dev.p, 24, cudaMemcpyDeviceToHost, st));
     // watchdog word of the intra kernel: engine-wide and sticky, so a stuck *hidden* frame (ALTREF, or one shown later through
     // show_existing_frame) is reported with the next output instead of being lost

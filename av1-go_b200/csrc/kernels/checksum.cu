@@ -15,9 +15,19 @@ __host__ __device__ __forceinline__ uint64_t cks_term(uint32_t v, uint32_t x, ui
     return (uint64_t)(v + 1) * wgt;
 }
 
+struct CksPlanes {
+    const uint8_t* src[3];
+    size_t pitch[3];
+    int w[3], h[3];
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256) checksum_kernel(const uint8_t* __restrict__ src, size_t pitch, int w, int h,
-                                                       unsigned long long* __restrict__ out) {
+__global__ void __launch_bounds__(256) checksum_kernel(CksPlanes P, unsigned long long* __restrict__ out3) {
+    // blockIdx.y = plane: the three planes of a frame in one launch
+    const uint8_t* __restrict__ src = P.src[blockIdx.y];
+    const size_t pitch = P.pitch[blockIdx.y];
+    const int w = P.w[blockIdx.y], h = P.h[blockIdx.y];
+    unsigned long long* out = out3 + blockIdx.y;
     constexpr int VEC = PixTraits<T>::VEC;
     const int ipr = (w + VEC - 1) / VEC;
     const long long total = (long long)ipr * h;
@@ -46,8 +56,10 @@ __global__ void __launch_bounds__(256) checksum_kernel(const uint8_t* __restrict
     }
 }
 
-cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(out_dev, 0, sizeof(uint64_t), s);
+// all planes of a frame: one memset of the accumulators + one launch (grid.y = plane)
+cudaError_t launch_frame_checksum(const void* const src[3], const size_t pitch[3], const int w[3], const int h[3], int nplanes, int bpc,
+                                  uint64_t* out_dev, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, 3 * sizeof(uint64_t), s);
     if (e != cudaSuccess) return e;
     {
         static bool carve_done = false;
@@ -57,13 +69,38 @@ cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, i
             carve_done = true;
         }
     }
+    CksPlanes P;
+    for (int p = 0; p < 3; p++) {
+        const int q = p < nplanes ? p : 0;
+        P.src[p] = (const uint8_t*)src[q];
+        P.pitch[p] = pitch[q];
+        P.w[p] = p < nplanes ? w[q] : 0;
+        P.h[p] = p < nplanes ? h[q] : 0;
+    }
+    const int vec = bpc == 8 ? 16 : 8;
+    long long items = (long long)((w[0] + vec - 1) / vec) * h[0];
+    int blocks = (int)((items + 256 * 4 - 1) / (256 * 4));
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    dim3 grid(blocks, nplanes);
+    if (bpc == 8) checksum_kernel<uint8_t><<<grid, 256, 0, s>>>(P, (unsigned long long*)out_dev);
+    else checksum_kernel<uint16_t><<<grid, 256, 0, s>>>(P, (unsigned long long*)out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s) {
+    // single plane (stage API): same kernel with one plane; only out_dev[0] is touched
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, sizeof(uint64_t), s);
+    if (e != cudaSuccess) return e;
+    CksPlanes P;
+    for (int p = 0; p < 3; p++) { P.src[p] = (const uint8_t*)src; P.pitch[p] = pitch; P.w[p] = w; P.h[p] = h; }
     const int vec = bpc == 8 ? 16 : 8;
     long long items = (long long)((w + vec - 1) / vec) * h;
     int blocks = (int)((items + 256 * 4 - 1) / (256 * 4));
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (bpc == 8) checksum_kernel<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)src, pitch, w, h, (unsigned long long*)out_dev);
-    else checksum_kernel<uint16_t><<<blocks, 256, 0, s>>>((const uint8_t*)src, pitch, w, h, (unsigned long long*)out_dev);
+    if (bpc == 8) checksum_kernel<uint8_t><<<dim3(blocks, 1), 256, 0, s>>>(P, (unsigned long long*)out_dev);
+    else checksum_kernel<uint16_t><<<dim3(blocks, 1), 256, 0, s>>>(P, (unsigned long long*)out_dev);
     return cudaGetLastError();
 }
 

@@ -661,6 +661,46 @@ __global__ void __launch_bounds__(128) inter_residual_kernel(const TxRec* recs, 
     const int ope = cur.pitch[plane] / sizeof(T);
     const int16_t* rp = res_ptr(res, plane, x, y);
     const int rpe = 1 << res.tw_log2[plane];
+    if (w >= 8 && xe == w) {
+        // transform blocks are aligned to their width: rows of 8-sample groups move as 128-bit residual / pixel vectors
+        const int lg = lw - 3;
+        for (int idx = lane; idx < (ye << lg); idx += 32) {
+            const int i = idx >> lg, j = (idx & ((1 << lg) - 1)) << 3;
+            const uint4 rv = *reinterpret_cast<const uint4*>(rp + i * rpe + j);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            T* op = out + i * ope + j;
+            int px[8];
+            if (sizeof(T) == 2) {
+                const uint4 pv = *reinterpret_cast<const uint4*>(op);
+                const uint32_t pw_[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    px[2 * k] = (int)(pw_[k] & 0xffffu);
+                    px[2 * k + 1] = (int)(pw_[k] >> 16);
+                }
+            } else {
+                const uint2 pv = *reinterpret_cast<const uint2*>(op);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    px[k] = (int)((pv.x >> (8 * k)) & 0xffu);
+                    px[4 + k] = (int)((pv.y >> (8 * k)) & 0xffu);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                px[2 * k] = min(max(px[2 * k] + (int)(short)(rw[k] & 0xffffu), 0), pixmax);
+                px[2 * k + 1] = min(max(px[2 * k + 1] + ((int)rw[k] >> 16), 0), pixmax);
+            }
+            if (sizeof(T) == 2) {
+                *reinterpret_cast<uint4*>(op) = make_uint4((uint32_t)px[0] | ((uint32_t)px[1] << 16), (uint32_t)px[2] | ((uint32_t)px[3] << 16),
+                                                           (uint32_t)px[4] | ((uint32_t)px[5] << 16), (uint32_t)px[6] | ((uint32_t)px[7] << 16));
+            } else {
+                *reinterpret_cast<uint2*>(op) = make_uint2((uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24),
+                                                           (uint32_t)px[4] | ((uint32_t)px[5] << 8) | ((uint32_t)px[6] << 16) | ((uint32_t)px[7] << 24));
+            }
+        }
+        return;
+    }
     for (int idx = lane; idx < w * h; idx += 32) {
         const int i = idx >> lw, j = idx & (w - 1);
         if (i < ye && j < xe) {

@@ -73,5 +73,7 @@ struct SuperresLaunch {
 cudaError_t launch_superres(const SuperresLaunch& L, cudaStream_t s);
 
 cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s);
+cudaError_t launch_frame_checksum(const void* const src[3], const size_t pitch[3], const int w[3], const int h[3], int nplanes, int bpc,
+                                  uint64_t* out_dev, cudaStream_t s);
 
 }  // namespace av1r

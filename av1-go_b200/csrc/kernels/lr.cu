@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
         return;
     }
     // ---- self-guided
+    __shared__ uint16_t s_xbx[256];               // x / (x + 1) in 8-bit fixed point (spec 7.17.3), instead of a division per grid point
+    s_xbx[tid] = (uint16_t)(tid == 255 ? 256 : (tid == 0 ? 1 : ((tid << 8) + tid / 2) / (tid + 1)));
+    __syncthreads();
     const int r0 = c_sgr_params[u.sgr_set][0], r1 = c_sgr_params[u.sgr_set][1];
     const int s0 = c_sgr_params[u.sgr_set][2], s1 = c_sgr_params[u.sgr_set][3];
     constexpr int PPT = LR_TW * LR_TH / 256;      // pixels per thread
@@ -200,21 +203,32 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
                 const int gi = i / gw, gj = i - gi * gw;     // grid point (gi - 1, gj - 1) -> tile centre (gi + 2, gj + 2)
                 if (pass == 0 && !((gi - 1) & 1)) continue;
                 uint32_t a = 0, b = 0;
-                for (int dy = -r; dy <= r; dy++)
-                    for (int dx = -r; dx <= r; dx++) {
-                        const uint32_t v = tile[(gi + 2 + dy) * LR_SW + gj + 2 + dx];
-                        a += v * v;
-                        b += v;
-                    }
+                const uint16_t* tc = tile + (gi + 2) * LR_SW + gj + 2;
+                if (r == 2) {
+#pragma unroll
+                    for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+                        for (int dx = -2; dx <= 2; dx++) {
+                            const uint32_t v = tc[dy * LR_SW + dx];
+                            a += v * v;
+                            b += v;
+                        }
+                } else {
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) {
+                            const uint32_t v = tc[dy * LR_SW + dx];
+                            a += v * v;
+                            b += v;
+                        }
+                }
                 const int sh = bd - 8;
                 a = sh ? (a + (1u << (2 * sh - 1))) >> (2 * sh) : a;
                 const uint32_t d = sh ? (b + (1u << (sh - 1))) >> sh : b;
                 const uint32_t p = a * n < d * d ? 0 : a * n - d * d;
                 const uint32_t z = (uint32_t)(((uint64_t)p * (uint32_t)sp + (1u << 19)) >> 20);
-                uint32_t a2;
-                if (z >= 255) a2 = 256;
-                else if (z == 0) a2 = 1;
-                else a2 = ((z << 8) + z / 2) / (z + 1);
+                const uint32_t a2 = s_xbx[min(z, 255u)];
                 const uint32_t b2 = (256 - a2) * b * one_by_n;
                 sm.u.sg.A[gi * (LR_TW + 2) + gj] = (uint16_t)a2;
                 sm.u.sg.B[gi * (LR_TW + 2) + gj] = (int32_t)((b2 + (1u << 11)) >> 12);
