@@ -436,8 +436,8 @@ struct EngineImpl {
 static std::atomic<long long> g_eprof_ns[20];   // written from the consumer and the parser threads
 struct EProfPrinter {
     ~EProfPrinter() {
-        if (getenv("AV1R_PROFILE"))
-            fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f replay_h2d %.1f replay_exec %.1f ms\n",
+        if (!getenv("AV1R_PROFILE")) return;
+        fprintf(stderr, "[engine prof] acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f replay_h2d %.1f replay_exec %.1f ms\n",
                     g_eprof_ns[0] * 1e-6, g_eprof_ns[1] * 1e-6, g_eprof_ns[2] * 1e-6, g_eprof_ns[3] * 1e-6, g_eprof_ns[4] * 1e-6, g_eprof_ns[5] * 1e-6,
                     g_eprof_ns[6] * 1e-6, g_eprof_ns[7] * 1e-6);
             fprintf(stderr, "[engine prof] host issue per stage: getframe %.1f itx %.1f inter %.1f intra %.1f deblock %.1f cdef %.1f lr %.1f emit %.1f ms\n",

@@ -20,6 +20,10 @@ __constant__ int8_t c_cdef_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}
 __constant__ uint8_t c_cdef_uv_dir[2][2][8] = {{{0, 1, 2, 3, 4, 5, 6, 7}, {1, 2, 2, 2, 3, 4, 6, 0}}, {{7, 0, 2, 4, 5, 6, 6, 6}, {0, 1, 2, 3, 4, 5, 6, 7}}};
 
 static constexpr int CDEF_LT = 68;   // luma tile edge (64 + 2*2)
+// Row stride of the staged tiles.  Tile column tx (sample x0 - 2 + tx) lives at row offset tx + 2, so that offset 0 is sample
+// x0 - 4: an 8-byte aligned address in the frame, and the rows of interior tiles arrive as 64-bit loads.
+static constexpr int CDEF_LS = 72;
+#define CDEF_TIDX(ty, tx) ((ty) * CDEF_LS + (tx) + 2)
 
 // Direction search (spec 7.15.2) as 90 line sums per 8x8 block: direction d partitions the block into lines (15 diagonals for d = 0, 4;
 // 8 rows / columns for d = 2, 6; 11 half-slope lines for the odd directions); cost[d] = sum over its lines of (line sum)^2 * 840 / (samples
@@ -74,41 +78,33 @@ __device__ __forceinline__ int cdef_constrain(int diff, int threshold, int adj) 
     return diff < 0 ? -v : v;
 }
 
-// dtab[d][k] = tile offset (dy * stride + dx) of tap k of direction d: read from shared memory, because the four 8x8 blocks a warp
-// covers have different directions and a register-indexed *constant* load would be replayed once per distinct direction
-__device__ __forceinline__ int cdef_pixel(const int16_t* tile, const int16_t (*dtab)[2], int pos, int pri, int sec, int damping, int dir, int cs) {
+// One filtered sample (spec 7.15.3), branch free: a tap that is unavailable (marked -1 in the tile) or whose strength class is off is
+// replaced by the centre sample, which makes its difference 0 and leaves the min / max unchanged -- exactly the effect of skipping it.
+// offsets: op[k] primary, oa[k] / ob[k] the two secondary directions (tile offsets dy * stride + dx), k = tap distance 1 / 2.
+struct CdefBlk {
+    int pri, sec, adj_p, adj_s, pt0, pt1;
+    int op[2], oa[2], ob[2];
+};
+__device__ __forceinline__ int cdef_tap(int p, int x, bool on, int thr, int adj, int wgt, int& mx, int& mn) {
+    p = (on && p >= 0) ? p : x;
+    const int d = p - x;
+    const int v = cdef_constrain(d, thr, adj);
+    mx = max(mx, p);
+    mn = min(mn, p);
+    return wgt * v;
+}
+__device__ __forceinline__ int cdef_pixel(const int16_t* tile, int pos, const CdefBlk& B) {
     const int x = tile[pos];
     int sum = 0, mx = x, mn = x;
-    const int pt0 = ((pri >> cs) & 1) ? 3 : 4, pt1 = ((pri >> cs) & 1) ? 3 : 2;
-    const int adj_p = pri ? max(0, damping - (31 - __clz(pri))) : 0, adj_s = sec ? max(0, damping - (31 - __clz(sec))) : 0;
-    const int d2a = (dir + 2) & 7, d2b = (dir - 2) & 7;
+    const bool pon = B.pri != 0, son = B.sec != 0;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const int ptap = k ? pt1 : pt0, stap = k ? 1 : 2;
-        const int op = dtab[dir][k], oa = dtab[d2a][k], ob = dtab[d2b][k];
+        const int ptap = k ? B.pt1 : B.pt0, stap = k ? 1 : 2;
 #pragma unroll
         for (int sg = -1; sg <= 1; sg += 2) {
-            if (pri) {
-                const int p = tile[pos + sg * op];
-                if (p >= 0) {
-                    sum += ptap * cdef_constrain(p - x, pri, adj_p);
-                    mx = max(mx, p);
-                    mn = min(mn, p);
-                }
-            }
-            if (sec) {
-                const int s0 = tile[pos + sg * oa], s1 = tile[pos + sg * ob];
-                if (s0 >= 0) {
-                    sum += stap * cdef_constrain(s0 - x, sec, adj_s);
-                    mx = max(mx, s0);
-                    mn = min(mn, s0);
-                }
-                if (s1 >= 0) {
-                    sum += stap * cdef_constrain(s1 - x, sec, adj_s);
-                    mx = max(mx, s1);
-                    mn = min(mn, s1);
-                }
-            }
+            sum += cdef_tap(tile[pos + sg * B.op[k]], x, pon, B.pri, B.adj_p, ptap, mx, mn);
+            sum += cdef_tap(tile[pos + sg * B.oa[k]], x, son, B.sec, B.adj_s, stap, mx, mn);
+            sum += cdef_tap(tile[pos + sg * B.ob[k]], x, son, B.sec, B.adj_s, stap, mx, mn);
         }
     }
     return min(max(x + ((8 + sum - (sum < 0)) >> 4), mn), mx);
@@ -116,8 +112,8 @@ __device__ __forceinline__ int cdef_pixel(const int16_t* tile, const int16_t (*d
 
 template <typename T>
 __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
-    __shared__ int16_t s_luma[CDEF_LT * CDEF_LT];
-    __shared__ int16_t s_chroma[2][CDEF_LT * CDEF_LT];   // sized for 4:4:4
+    __shared__ __align__(16) int16_t s_luma[CDEF_LT * CDEF_LS];
+    __shared__ __align__(16) int16_t s_chroma[2][CDEF_LT * CDEF_LS];   // sized for 4:4:4
     __shared__ uint8_t s_dir[64], s_skip[64];
     __shared__ int s_var[64];
     __shared__ __align__(16) CdefLineTable s_lines;
@@ -129,22 +125,38 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
     const int idx = L.cdef_idx[(size_t)fby * c64 + fbx];
     const int bd = fp.bd, cs = bd - 8;
     const int nplanes = fp.mono ? 1 : 3;
-    if (tid < 16) s_dtab[tid >> 1][tid & 1] = (int16_t)(c_cdef_dir[tid >> 1][tid & 1][0] * CDEF_LT + c_cdef_dir[tid >> 1][tid & 1][1]);
+    if (tid < 16) s_dtab[tid >> 1][tid & 1] = (int16_t)(c_cdef_dir[tid >> 1][tid & 1][0] * CDEF_LS + c_cdef_dir[tid >> 1][tid & 1][1]);
     for (int i = tid; i < (int)(sizeof(CdefLineTable) / 4); i += 256) reinterpret_cast<uint32_t*>(&s_lines)[i] = reinterpret_cast<const uint32_t*>(&g_cdef_lines)[i];
-    // ---- stage tiles
-    for (int plane = 0; plane < nplanes; plane++) {
-        const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
-        const int tw = (64 >> sx) + 4, th = (64 >> sy) + 4;
-        const int x0 = (fbx * 64 >> sx) - 2, y0 = (fby * 64 >> sy) - 2;
-        int16_t* tile = plane == 0 ? s_luma : s_chroma[plane - 1];
-        const T* src = (const T*)L.src.p[plane];
-        const int pitch_e = L.src.pitch[plane] / sizeof(T);
-        for (int i = tid; i < tw * th; i += 256) {
-            const int ty = i / tw, tx = i - ty * tw;
-            const int x = x0 + tx, y = y0 + ty;
-            int v = -1;
-            if (x >= 0 && y >= 0 && x < fp.cw[plane] && y < fp.ch[plane]) v = src[(size_t)y * pitch_e + x];
-            tile[ty * CDEF_LT + tx] = (int16_t)v;
+    // ---- stage tiles (a warp per row; samples outside the coded frame are marked -1 = unavailable)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int plane = 0; plane < nplanes; plane++) {
+            const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
+            const int tw = (64 >> sx) + 4, th = (64 >> sy) + 4;
+            const int x0 = (fbx * 64 >> sx) - 2, y0 = (fby * 64 >> sy) - 2;
+            int16_t* tile = plane == 0 ? s_luma : s_chroma[plane - 1];
+            const T* src = (const T*)L.src.p[plane];
+            const int pitch_e = L.src.pitch[plane] / sizeof(T);
+            // interior in x: all of x0 .. x0 + tw - 1 inside the coded width and the 64-bit pieces starting at x0 - 2 inside the row
+            const int nq = (tw + 2 + 3) >> 2;                     // 64-bit pieces from sample x0 - 2: 18 (luma) / 10 (4:2:0 chroma)
+            const bool fast = sizeof(T) == 2 && x0 >= 2 && x0 + tw <= fp.cw[plane] && (size_t)(x0 - 2 + 4 * nq) * sizeof(T) <= L.src.pitch[plane];
+            for (int ty = warp; ty < th; ty += 8) {
+                const int y = y0 + ty;
+                const bool row_ok = y >= 0 && y < fp.ch[plane];
+                if (fast && row_ok) {
+                    if (lane < nq) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(src + (size_t)y * pitch_e + x0 - 2) + lane);
+                        reinterpret_cast<uint2*>(tile + ty * CDEF_LS)[lane] = v;
+                    }
+                } else {
+                    for (int tx = lane; tx < tw; tx += 32) {
+                        const int x = x0 + tx;
+                        int v = -1;
+                        if (row_ok && x >= 0 && x < fp.cw[plane]) v = src[(size_t)y * pitch_e + x];
+                        tile[CDEF_TIDX(ty, tx)] = (int16_t)v;
+                    }
+                }
+            }
         }
     }
     // ---- per 8x8: skip flag
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
         for (int blk = warp; blk < 64; blk += 8) {
             if (s_skip[blk]) continue;   // warp-uniform
             const int by = blk >> 3, bx = blk & 7;
-            const int16_t* base = s_luma + (by * 8 + 2) * CDEF_LT + bx * 8 + 2;
+            const int16_t* base = s_luma + CDEF_TIDX(by * 8 + 2, bx * 8 + 2);
             int c3[3], d3[3];
 #pragma unroll
             for (int q = 0; q < 3; q++) {
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
                     const uint32_t px = ((t < 4 ? pk.x : pk.y) >> (8 * (t & 3))) & 0xff;
-                    if (px != 0xff) sum += (base[(px >> 3) * CDEF_LT + (px & 7)] >> cs) - 128;
+                    if (px != 0xff) sum += (base[(px >> 3) * CDEF_LS + (px & 7)] >> cs) - 128;
                 }
                 c3[q] = sum * sum * (int)s_lines.weight[line];
                 d3[q] = s_lines.dir[line];
@@ -204,21 +216,24 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
         s_var[tid] = 0;
     }
     __syncthreads();
-    // ---- filter
+    // ---- filter: a thread finishes one row of a block -- 8 luma / 4 (4:2:0) chroma samples that share strengths, direction and
+    // damping -- and stores it as one 128-bit (64-bit) vector
     for (int plane = 0; plane < nplanes; plane++) {
         const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
-        const int bw = 64 >> sx, bh = 64 >> sy;           // plane samples in this filter block
         const int x0 = fbx * 64 >> sx, y0 = fby * 64 >> sy;
         const int16_t* tile = plane == 0 ? s_luma : s_chroma[plane - 1];
         T* dst = (T*)L.dst.p[plane];
         const int pitch_e = L.dst.pitch[plane] / sizeof(T);
-        const int lbw = 6 - sx;
-        for (int i = tid; i < bw * bh; i += 256) {
-            const int py = i >> lbw, px = i & (bw - 1);
+        const int G = 8 >> sx, bh = 64 >> sy;                // samples per block row, plane rows in this filter block
+        for (int it = tid; it < bh * 8; it += 256) {
+            const int bx = it & 7, py = it >> 3, px = bx * G;
             const int x = x0 + px, y = y0 + py;
             if (x >= fp.cw[plane] || y >= fp.ch[plane]) continue;
-            const int blk = ((py << sy) >> 3) * 8 + ((px << sx) >> 3);
-            int v = tile[(py + 2) * CDEF_LT + px + 2];
+            const int blk = ((py << sy) >> 3) * 8 + bx;
+            const int pos = CDEF_TIDX(py + 2, px + 2);
+            int v[8];
+            bool filt = false;
+            CdefBlk B;
             if (!s_skip[blk]) {
                 const int ydir = s_dir[blk];
                 int pri, sec, dir, damping;
@@ -236,9 +251,42 @@ __global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
                     dir = pri == 0 ? 0 : c_cdef_uv_dir[fp.subx][fp.suby][ydir];
                     damping = fp.cdef_damping + cs - 1;
                 }
-                if (pri | sec) v = cdef_pixel(tile, s_dtab, (py + 2) * CDEF_LT + px + 2, pri, sec, damping, dir, cs);
+                if (pri | sec) {
+                    filt = true;
+                    B.pri = pri;
+                    B.sec = sec;
+                    B.pt0 = ((pri >> cs) & 1) ? 3 : 4;
+                    B.pt1 = ((pri >> cs) & 1) ? 3 : 2;
+                    B.adj_p = pri ? max(0, damping - (31 - __clz(pri))) : 0;
+                    B.adj_s = sec ? max(0, damping - (31 - __clz(sec))) : 0;
+                    const int d2a = (dir + 2) & 7, d2b = (dir - 2) & 7;
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        B.op[k] = s_dtab[dir][k];
+                        B.oa[k] = s_dtab[d2a][k];
+                        B.ob[k] = s_dtab[d2b][k];
+                    }
+                }
             }
-            dst[(size_t)y * pitch_e + x] = (T)v;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (k < G) v[k] = filt ? cdef_pixel(tile, pos + k, B) : (int)tile[pos + k];
+            T* dp = dst + (size_t)y * pitch_e + x;
+            if (x + G <= fp.cw[plane]) {
+                if (sizeof(T) == 2) {
+                    if (G == 8) *reinterpret_cast<uint4*>(dp) = make_uint4((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16),
+                                                                             (uint32_t)v[4] | ((uint32_t)v[5] << 16), (uint32_t)v[6] | ((uint32_t)v[7] << 16));
+                    else *reinterpret_cast<uint2*>(dp) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+                } else {
+                    if (G == 8) *reinterpret_cast<uint2*>(dp) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24),
+                                                                             (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24));
+                    else *reinterpret_cast<uint32_t*>(dp) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (k < G && x + k < fp.cw[plane]) dp[k] = (T)v[k];
+            }
         }
     }
 }

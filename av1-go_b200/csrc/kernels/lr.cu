@@ -199,8 +199,10 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
             const int n = (2 * r + 1) * (2 * r + 1);
             const uint32_t one_by_n = ((1u << 12) + n / 2) / n;
             // pass 0 (r = 2) only ever reads the odd grid rows (weights of the even ones are zero): skip the others
-            for (int i = tid; i < (h + 2) * gw; i += 256) {
-                const int gi = i / gw, gj = i - gi * gw;     // grid point (gi - 1, gj - 1) -> tile centre (gi + 2, gj + 2)
+            // (grid rows are walked 66 columns at a time whatever the tile width: a multiply-shift instead of a division by gw)
+            for (int i = tid; i < (h + 2) * (LR_TW + 2); i += 256) {
+                const int gi = (i * 993) >> 16, gj = i - gi * (LR_TW + 2);     // i / 66 for i < 66 * 66; grid point (gi - 1, gj - 1)
+                if (gj >= gw) continue;
                 if (pass == 0 && !((gi - 1) & 1)) continue;
                 uint32_t a = 0, b = 0;
                 const uint16_t* tc = tile + (gi + 2) * LR_SW + gj + 2;
@@ -236,8 +238,9 @@ __global__ void __launch_bounds__(256) lr_kernel(LrLaunch L) {
         }
         __syncthreads();
         int k = 0;
-        for (int i = tid; i < h * w; i += 256, k++) {
-            const int pr = i / w, pc = i - pr * w;
+        for (int i = tid; i < h * LR_TW; i += 256, k++) {   // 64 columns per row whatever the tile width: shifts instead of a division
+            const int pr = i >> 6, pc = i & (LR_TW - 1);
+            if (pc >= w) continue;
             const int uu = (int)tile[(pr + 3) * LR_SW + pc + 3];
             int f = uu << 4;
             if (r) {
