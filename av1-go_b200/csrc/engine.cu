@@ -145,7 +145,7 @@ static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::s
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
     size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, itiles, obmc, warps, pal, k3order, k3units, total;
-    int n_recs, n_coefs, n_order, n_order_small, n_inter, n_itiles, n_obmc, n_warps, n_k3, n_k3units;
+    int n_recs, n_coefs, n_order, n_order_small, n_inter, n_itiles, n_itiles_small, n_obmc, n_warps, n_k3, n_k3units;
 };
 
 static_assert(sizeof(LrUnit) == sizeof(LrUnitDev), "LrUnit layouts must match");
@@ -260,11 +260,18 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     for (int p = 0; p < 3; p++)
         if (!fw.lr[p].empty()) memcpy(h + L.lr[p], fw.lr[p].data(), sizeof(LrUnit) * fw.lr[p].size());
     if (L.n_inter) memcpy(h + L.inter, fw.inter.data(), sizeof(InterBlk) * L.n_inter);
-    {   // quadrant list: record index | quadrant << 28 (bit 0 of the quadrant = right half, bit 1 = bottom half)
+    {   // quadrant list: record index | quadrant << 28 (bit 0 of the quadrant = right half, bit 1 = bottom half); the items of
+        // small blocks (at most 16x16 luma samples) come first: K2 runs them as two-warp CTAs
         uint32_t* it = (uint32_t*)(h + L.itiles);
         int k = 0;
         for (int i = 0; i < L.n_inter; i++) {
             const InterBlk& b = fw.inter[i];
+            if (b.w <= 16 && b.h <= 16) it[k++] = (uint32_t)i;
+        }
+        dw.lay.n_itiles_small = k;
+        for (int i = 0; i < L.n_inter; i++) {
+            const InterBlk& b = fw.inter[i];
+            if (b.w <= 16 && b.h <= 16) continue;
             const int qx = (b.w + 63) >> 6, qy = (b.h + 63) >> 6;
             for (int y = 0; y < qy; y++)
                 for (int x = 0; x < qx; x++) it[k++] = (uint32_t)i | ((uint32_t)(y * 2 + x) << 28);
@@ -532,6 +539,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.n = L.n_inter;
         xl.tiles = (const uint32_t*)(d_arena + L.itiles);
         xl.n_tiles = L.n_itiles;
+        xl.n_tiles_small = L.n_itiles_small;
         memset(xl.refs, 0, sizeof(xl.refs));
         for (int i = 0; i < REFS_PER_FRAME; i++) {
             const int slot = dw.fh.ref_frame_idx[i];
@@ -553,7 +561,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         { int e_ = ensure_slots(&FrameSlot::diffmask, s, (size_t)xl.mask_pitch * fp.ch[0], hw_mask); if (e_) return e_; }
         xl.mask = s.diffmask.p;
         CK(launch_inter(xl, st));
-        if (tm) tm->end(AV1R_ST_INTER, 1, st);
+        if (tm) tm->end(AV1R_ST_INTER, (L.n_itiles_small > 0) + (L.n_itiles > L.n_itiles_small), st);
         CK(launch_inter_residual(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
         if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
     }
@@ -1385,6 +1393,8 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
     // the segment the consumer is issuing is exempt from the look-ahead budget: otherwise the workers of later multi-TU segments
     // can use the budget up while the worker the consumer waits for is the one blocked on it (deadlock seen on the C5 batch)
     std::atomic<size_t> consumer_seg{0};
+    std::mutex ready_m;                  // the consumer sleeps on ready_cv when no segment has a parsed unit for it
+    std::condition_variable ready_cv;
     auto worker = [&]() {
         cudaSetDevice(E.cfg.device);   // pinned staging is allocated from this thread
         WorkerPool::nested_enabled() = nseg < (size_t)nthreads;   // enough segments to fill the cores: no tile / band helpers
@@ -1400,7 +1410,7 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
             StreamParser sp;
             sp.hp.seq = vf.seq_for(sg.tu0);
             sp.defer_finalize = true;   // merge of the tile lists + deblocking edges run in the staging step below, off the parse chain
-            auto publish = [&sg](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
+            auto publish = [&sg, &ready_cv](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
                 {
                     std::lock_guard<std::mutex> lk(sg.m);
                     sg.parsed[t - sg.tu0] = std::move(pfs);
@@ -1409,17 +1419,22 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
                     sg.n_done++;
                 }
                 sg.cv.notify_all();
+                ready_cv.notify_one();
             };
             bool failed = false;
             for (size_t t = sg.tu0; t < sg.tu1 && !abort_flag.load() && !failed; t++) {
                 {
+                    auto t_w = EP_T();
                     std::unique_lock<std::mutex> lk(la_m);
-                    la_cv.wait(lk, [&] { return la_outstanding < la_limit || s == consumer_seg.load() || abort_flag.load(); });
+                    la_cv.wait(lk, [&] { return la_outstanding < la_limit || s <= consumer_seg.load() || abort_flag.load(); });
                     la_outstanding++;
+                    EP_ADD(18, t_w);
                 }
                 auto pfs = std::make_shared<std::vector<ParsedFrame>>();
                 const TemporalUnit& tu = vf.dm.tus[t];
+                auto t_p = EP_T();
                 const int prc = sp.parse_tu(vf.data + tu.offset, tu.size, ((int64_t)s << 32) | (int64_t)t, *pfs);
+                EP_ADD(19, t_p);
                 const std::string perr = sp.err;
                 auto stage = [&E, publish, t, pfs, prc, perr]() {
                     int rc2 = prc;
@@ -1444,6 +1459,7 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
                 sg.n_done = sg.tu1 - sg.tu0;
             }
             sg.cv.notify_all();
+            ready_cv.notify_one();
         }
     };
     std::vector<std::thread> pool;
@@ -1485,63 +1501,94 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
             if (n == 0) return 0;
         }
     };
-    for (size_t s = 0; s < nseg && !fatal && !stop; s++) {
-        Segment& sg = *segs[s];
-        VerifyFile& vf = *files[items[s].file];
+    // Frames are issued as soon as they are parsed, from whichever active segment has one ready (every shown frame finds its place
+    // through its pts, so the order between segments is free): a slow segment at the head of the list does not hold back the
+    // frames other workers have already parsed, and a small look-ahead budget is enough however many segments there are.
+    struct SegIssue {
+        size_t next_t = 0;
+        bool failed = false, done = false;
+        std::unique_ptr<EngineImpl::RefState> refs;
+    };
+    std::vector<SegIssue> st(nseg);
+    size_t lo = 0;   // first segment not yet fully issued
+    while (lo < nseg && !fatal && !stop) {
+        bool progressed = false;
+        const size_t hi = std::min(nseg, next_seg.load());   // segments claimed by a worker so far
+        for (size_t s = lo; s < hi && !fatal && !stop; s++) {
+            SegIssue& si = st[s];
+            if (si.done) continue;
+            Segment& sg = *segs[s];
+            VerifyFile& vf = *files[items[s].file];
+            const size_t ntu = sg.tu1 - sg.tu0;
+            while (si.next_t < ntu && !fatal && !stop) {
+                const size_t t = si.next_t;
+                std::vector<ParsedFrame> pfs;
+                int prc;
+                std::string msg;
+                {
+                    std::lock_guard<std::mutex> lk(sg.m);
+                    if (sg.n_done <= t) break;          // not parsed yet: look at the other segments
+                    pfs = std::move(sg.parsed[t]);
+                    prc = sg.rc[t];
+                    if (prc) msg = sg.errs[t];
+                }
+                si.next_t++;
+                progressed = true;
+                if (!si.refs) si.refs = std::make_unique<EngineImpl::RefState>();
+                E.rs = si.refs.get();
+                int frc = 0;
+                if (!si.failed)
+                    for (ParsedFrame& pf : pfs) {
+                        if (pf.fw) {
+                            std::lock_guard<std::mutex> lk(vf.m);
+                            vf.rep->host_parse_ms += pf.fw->parse_ms;
+                        }
+                        int r = E.decode_parsed(pf);
+                        if (r) { frc = r; msg = E.err; break; }
+                    }
+                E.rs = &E.main_refs;
+                {
+                    std::lock_guard<std::mutex> lk(la_m);
+                    la_outstanding--;
+                }
+                la_cv.notify_all();
+                if (si.failed) continue;          // rest of a failed segment: only hand the look-ahead budget back
+                if (!frc && prc) frc = prc;
+                if (frc) {
+                    char tmp[600];
+                    snprintf(tmp, sizeof(tmp), "temporal unit %zu: %s", sg.tu0 + t, msg.c_str());
+                    vf.fail(frc, vf.frame_base[sg.tu0 + t], tmp);
+                    if (frc == AV1R_EIO || frc == AV1R_ENOMEM) fatal = frc;
+                    si.failed = true;
+                    if (stop_on_error) stop = true;
+                    continue;
+                }
+                auto td = EP_T();
+                int r = drain(false);
+                EP_ADD(5, td);
+                if (r) fatal = r;
+            }
+            if (si.next_t == ntu) {
+                si.done = true;
+                si.refs.reset();                   // the segment's reference frames go back to the pool (slots still hold what is queued)
+            }
+        }
+        while (lo < nseg && st[lo].done) lo++;
         {
             std::lock_guard<std::mutex> lk(la_m);
-            consumer_seg.store(s);
+            consumer_seg.store(lo);
         }
         la_cv.notify_all();
-        EngineImpl::RefState seg_refs;
-        E.rs = &seg_refs;
-        bool seg_failed = false;
-        for (size_t t = 0; t < sg.tu1 - sg.tu0 && !fatal && !stop; t++) {
-            std::vector<ParsedFrame> pfs;
-            int prc;
-            std::string msg;
-            {
-                auto tw = EP_T();
-                std::unique_lock<std::mutex> lk(sg.m);
-                sg.cv.wait(lk, [&] { return sg.n_done > t; });
-                EP_ADD(4, tw);
-                pfs = std::move(sg.parsed[t]);
-                prc = sg.rc[t];
-                if (prc) msg = sg.errs[t];
-            }
-            int frc = 0;
-            if (!seg_failed)
-                for (ParsedFrame& pf : pfs) {
-                    if (pf.fw) {
-                        std::lock_guard<std::mutex> lk(vf.m);
-                        vf.rep->host_parse_ms += pf.fw->parse_ms;
-                    }
-                    int r = E.decode_parsed(pf);
-                    if (r) { frc = r; msg = E.err; break; }
-                }
-            {
-                std::lock_guard<std::mutex> lk(la_m);
-                la_outstanding--;
-            }
-            la_cv.notify_all();
-            if (seg_failed) continue;          // rest of a failed segment: only hand the look-ahead budget back
-            if (!frc && prc) frc = prc;
-            if (frc) {
-                char tmp[600];
-                snprintf(tmp, sizeof(tmp), "temporal unit %zu: %s", sg.tu0 + t, msg.c_str());
-                vf.fail(frc, vf.frame_base[sg.tu0 + t], tmp);
-                if (frc == AV1R_EIO || frc == AV1R_ENOMEM) fatal = frc;
-                seg_failed = true;
-                if (stop_on_error) stop = true;
-                continue;
-            }
-            auto td = EP_T();
-            int r = drain(false);
-            EP_ADD(5, td);
-            if (r) fatal = r;
+        if (!progressed && lo < nseg) {
+            // nothing ready anywhere: sleep until a worker publishes a temporal unit (or for a short while: the claim of a new
+            // segment is not signalled)
+            auto tw = EP_T();
+            std::unique_lock<std::mutex> lk(ready_m);
+            ready_cv.wait_for(lk, std::chrono::microseconds(200));
+            EP_ADD(4, tw);
         }
-        E.rs = &E.main_refs;
     }
+    E.rs = &E.main_refs;
     {   // under la_m: a worker between its predicate test and its block must not miss the wake-up
         std::lock_guard<std::mutex> lk(la_m);
         abort_flag.store(true);

@@ -38,7 +38,8 @@ __device__ uint8_t d_wedge_master[6][64][64];
 static bool g_inter_const_loaded[64] = {false};
 
 static constexpr int IT = 32;                 // tile edge
-static constexpr int INTER_THREADS = 128;
+static constexpr int INTER_THREADS = 128;       // CTA size of the general kernel
+static constexpr int INTER_THREADS_SMALL = 64;  // blocks of at most 16x16 luma samples: two warps (half the idle lanes per barrier)
 
 __device__ __forceinline__ int wedge_mask_d(int bsize, int flip, int wedge, int i, int j) {
     const int w = c_blk_w[bsize], h = c_blk_h[bsize];
@@ -85,7 +86,7 @@ __device__ __forceinline__ int ld_ref(const uint8_t* base, uint32_t pitch, int x
 //   H pass: a thread turns 16 window samples (two 128-bit shared loads) into 8 outputs and stores them as one 128-bit row of
 //           packed int16 (the intermediate fits 16 bits: spec 7.11.3.4).
 //   V pass: a thread owns two columns x four rows: eleven 32-bit loads of packed pairs feed 64 multiply-adds.
-template <typename T>
+template <typename T, int NT>
 __device__ __forceinline__ void fetch_window_fast(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, int ww, int wh,
                                                   uint16_t* win) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,15 +98,16 @@ __device__ __forceinline__ void fetch_window_fast(const uint8_t* ref, uint32_t p
         const int xs = x0 & ~(SPW - 1), sh = (x0 - xs) * 8 * (int)sizeof(T);
         const int nwords = ((x0 + ww - 1 - xs) / SPW) + 1;   // <= 21 (uint16) / 11 (uint8)
         const uint8_t* base = ref + (size_t)y0 * pitch + (size_t)xs * sizeof(T);
-        uint32_t w[10];
+        constexpr int NW = NT / 32, KMAX = NT == 128 ? 10 : 12;   // 4 warps x 10 rows >= 39; 2 warps x 12 rows >= 23 (small blocks)
+        uint32_t w[KMAX];
 #pragma unroll
-        for (int k = 0; k < 10; k++) {
-            const int r = warp + 4 * k;
+        for (int k = 0; k < KMAX; k++) {
+            const int r = warp + NW * k;
             w[k] = (r < wh && lane < nwords) ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * pitch) + lane) : 0u;
         }
 #pragma unroll
-        for (int k = 0; k < 10; k++) {
-            const int r = warp + 4 * k;
+        for (int k = 0; k < KMAX; k++) {
+            const int r = warp + NW * k;
             const uint32_t nxt = __shfl_down_sync(0xffffffffu, w[k], 1);
             const uint32_t v = __funnelshift_r(w[k], nxt, sh);
             if (r < wh && lane < nwords) {
@@ -120,7 +122,7 @@ __device__ __forceinline__ void fetch_window_fast(const uint8_t* ref, uint32_t p
             }
         }
     } else {
-        for (int r = warp; r < wh; r += INTER_THREADS / 32) {
+        for (int r = warp; r < wh; r += NT / 32) {
             const int y = min(max(y0 + r, 0), lasty);
             const T* row = (const T*)(ref + (size_t)y * pitch);
             for (int c = lane; c < ww; c += 32) win[r * RW + c] = (uint16_t)__ldg(row + min(max(x0 + c, 0), lastx));
@@ -128,11 +130,11 @@ __device__ __forceinline__ void fetch_window_fast(const uint8_t* ref, uint32_t p
     }
 }
 
-template <typename T>
+template <typename T, int NT>
 __device__ void predict_tile_fast(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, const int16_t* fh, const int16_t* fv,
                                   int tw, int th, int round1, InterSmem& sm, int32_t* out) {
     const int ww = tw + 7, wh = th + 7;
-    fetch_window_fast<T>(ref, pitch, lastx, lasty, ix, iy, ww, wh, sm.refwin);
+    fetch_window_fast<T, NT>(ref, pitch, lastx, lasty, ix, iy, ww, wh, sm.refwin);
     __syncthreads();
     int16_t* mid = reinterpret_cast<int16_t*>(sm.mid);
     {   // horizontal pass: (row, group of 8 columns) per thread
@@ -140,7 +142,7 @@ __device__ void predict_tile_fast(const uint8_t* ref, uint32_t pitch, int lastx,
         int f[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) f[t] = fh[t];
-        for (int idx = threadIdx.x; idx < (wh << lg); idx += INTER_THREADS) {
+        for (int idx = threadIdx.x; idx < (wh << lg); idx += NT) {
             const int r = idx >> lg, c0 = (idx & (ng - 1)) << 3;
             const uint4* wp = reinterpret_cast<const uint4*>(sm.refwin + r * RW + c0);
             const uint4 a = wp[0], b = wp[1];
@@ -172,7 +174,7 @@ __device__ void predict_tile_fast(const uint8_t* ref, uint32_t pitch, int lastx,
         int f[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) f[t] = fv[t];
-        for (int idx = threadIdx.x; idx < ((th >> 2) << lp); idx += INTER_THREADS) {
+        for (int idx = threadIdx.x; idx < ((th >> 2) << lp); idx += NT) {
             const int cp = idx & (np - 1), r0 = (idx >> lp) << 2;
             const uint32_t* mp = reinterpret_cast<const uint32_t*>(mid + r0 * MW) + cp;
             int lo[11], hi[11];
@@ -200,29 +202,29 @@ __device__ void predict_tile_fast(const uint8_t* ref, uint32_t pitch, int lastx,
 // translational prediction of a tw x th tile; (fx, fy) = 1/16 phases, (ix, iy) = integer reference position of the tile's
 // top-left sample.  The (tw + 7) x (th + 7) support is fetched once (coordinates clamped to the visible reference frame, spec
 // 7.11.3.4) into shared memory; both filter passes then run out of shared memory.
-template <typename T>
+template <typename T, int NT>
 __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int ix, int iy, int fx, int fy, int fidx_h, int fidx_v,
                              int tw, int th, int round1, InterSmem& sm, int32_t* out) {
     const int16_t* fh = c_subpel[fidx_h][fx];
     const int16_t* fv = c_subpel[fidx_v][fy];
     const int ww = tw + 7, wh = th + 7;
     if ((tw == 8 || tw == 16 || tw == 32) && (th & 3) == 0) {
-        predict_tile_fast<T>(ref, pitch, lastx, lasty, ix, iy, fh, fv, tw, th, round1, sm, out);
+        predict_tile_fast<T, NT>(ref, pitch, lastx, lasty, ix, iy, fh, fv, tw, th, round1, sm, out);
         return;
     }
     const int inv_ww = recip16(ww), inv_tw = recip16(tw);
     // four independent loads in flight per thread before the first store (the window fetch is pure L2 / L1 latency)
-    for (int base = threadIdx.x; base < ww * wh; base += 4 * INTER_THREADS) {
+    for (int base = threadIdx.x; base < ww * wh; base += 4 * NT) {
         int v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int idx = base + u * INTER_THREADS;
+            const int idx = base + u * NT;
             const int r = div16(min(idx, ww * wh - 1), inv_ww), c = min(idx, ww * wh - 1) - r * ww;
             v[u] = ld_ref<T>(ref, pitch, min(max(ix + c - 3, 0), lastx), min(max(iy + r - 3, 0), lasty));
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int idx = base + u * INTER_THREADS;
+            const int idx = base + u * NT;
             if (idx < ww * wh) {
                 const int r = div16(idx, inv_ww), c = idx - r * ww;
                 sm.refwin[r * RW + c] = (uint16_t)v[u];
@@ -236,7 +238,7 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
         // register sliding window: a thread produces 4 neighbouring outputs from 11 inputs (32 MACs per 11 shared-memory loads
         // instead of 8 loads per output), horizontally then vertically
         const int gw = tw >> 2, inv_gw = recip16(gw);
-        for (int idx = threadIdx.x; idx < wh * gw; idx += INTER_THREADS) {
+        for (int idx = threadIdx.x; idx < wh * gw; idx += NT) {
             const int r = div16(idx, inv_gw), c = (idx - r * gw) << 2;
             const uint16_t* w = sm.refwin + r * RW + c;
             int x[11];
@@ -252,7 +254,7 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
         }
         __syncthreads();
         const int gh = th >> 2;
-        for (int idx = threadIdx.x; idx < gh * tw; idx += INTER_THREADS) {
+        for (int idx = threadIdx.x; idx < gh * tw; idx += NT) {
             const int g = div16(idx, inv_tw), c = idx - g * tw, r = g << 2;
             int x[11];
 #pragma unroll
@@ -269,7 +271,7 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
         return;
     }
     const int n1 = wh * tw;
-    for (int idx = threadIdx.x; idx < n1; idx += INTER_THREADS) {
+    for (int idx = threadIdx.x; idx < n1; idx += NT) {
         const int r = div16(idx, inv_tw), c = idx - r * tw;
         const uint16_t* w = sm.refwin + r * RW + c;
         int s = 0;
@@ -279,7 +281,7 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
     }
     __syncthreads();
     const int n2 = th * tw;
-    for (int idx = threadIdx.x; idx < n2; idx += INTER_THREADS) {
+    for (int idx = threadIdx.x; idx < n2; idx += NT) {
         const int r = div16(idx, inv_tw), c = idx - r * tw;
         int s = 0;
 #pragma unroll
@@ -311,6 +313,7 @@ __device__ __forceinline__ int dot8_packed(const uint32_t* w, int start, uint2 t
     return s;
 }
 
+template <int NT>
 __device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw,
                             int th, int round1, InterSmem& sm, int32_t* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -318,7 +321,7 @@ __device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int l
     uint32_t* wmt = reinterpret_cast<uint32_t*>(sm.mid) + warp * 80;       // transposed intermediate: 8 columns x 9 words (15 int16 + pad)
     const int nbx = tw >> 3, lnbx = 31 - __clz(nbx), nb = nbx * (th >> 3);
     const int rnd = 1 << (round1 - 1);
-    for (int b = warp; b < nb; b += INTER_THREADS / 32) {
+    for (int b = warp; b < nb; b += NT / 32) {
         const int i8 = b >> lnbx, j8 = b & (nbx - 1);
         const int src_x = (x0 + j8 * 8 + 4) << sx, src_y = (y0 + i8 * 8 + 4) << sy;
         const long long dst_x = (long long)wr.mat[2] * src_x + (long long)wr.mat[3] * src_y + wr.mat[0];
@@ -384,7 +387,7 @@ __device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int l
 }
 
 // warped prediction of a tile (multiples of 8): one warp per 8x8 sub-block
-template <typename T>
+template <typename T, int NT>
 __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw, int th,
                           int round1, InterSmem& sm, int32_t* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -392,7 +395,7 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
     uint16_t* win = sm.refwin + warp * 240;   // 15 x 15 support of one 8x8 block (16-sample rows)
     const int nbx = tw >> 3, nb = nbx * (th >> 3);
     const int rnd = 1 << (round1 - 1);
-    for (int b = warp; b < nb; b += INTER_THREADS / 32) {
+    for (int b = warp; b < nb; b += NT / 32) {
         const int i8 = b / nbx, j8 = b - i8 * nbx;
         const int src_x = (x0 + j8 * 8 + 4) << sx, src_y = (y0 + i8 * 8 + 4) << sy;
         const long long dst_x = (long long)wr.mat[2] * src_x + (long long)wr.mat[3] * src_y + wr.mat[0];
@@ -449,10 +452,10 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
     __syncthreads();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunch L) {
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : 12) inter_pred_kernel(InterLaunch L, int first_item) {
     __shared__ InterSmem sm;
-    const uint32_t item = L.tiles[blockIdx.x];
+    const uint32_t item = L.tiles[first_item + blockIdx.x];
     const InterBlk r = L.blks[item & 0x0fffffffu];
     const int qx0 = ((item >> 28) & 1) << 6, qy0 = ((item >> 29) & 1) << 6;   // luma origin of this CTA's 64x64 quadrant inside the block
     const DevFrameParams& fp = L.fp;
@@ -478,14 +481,14 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                     const DevPlanes& rf = L.refs[r.ref[l]];
                     if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) {
                         if (sizeof(T) == 2)
-                            warp_tile16(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
+                            warp_tile16<NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
                                         sm.pred[l]);
                         else
-                            warp_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
+                            warp_tile<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
                                          sm.pred[l]);
                     } else {
                         const int posx = ((px + tx) << 4) + ((2 * r.mv[l][1]) >> sx), posy = ((py + ty) << 4) + ((2 * r.mv[l][0]) >> sy);
-                        predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
+                        predict_tile<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
                                         filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tw, th, round1, sm, sm.pred[l]);
                     }
                 }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                     const int sh = !is_compound ? 0 : (r.comp_type == COMPOUND_DISTANCE ? 4 + post : 1 + post);
                     const int rnd = sh ? 1 << (sh - 1) : 0;
                     const int cwp = fp.cw[plane], chp = fp.ch[plane];
-                    for (int idx = threadIdx.x; idx < (th << lg); idx += INTER_THREADS) {
+                    for (int idx = threadIdx.x; idx < (th << lg); idx += NT) {
                         const int i = idx >> lg, j0 = (idx & ((1 << lg) - 1)) << 3;
                         const int gx = px + tx + j0, gy = py + ty + i;
                         if (gy >= chp || gx >= cwp) continue;
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                     continue;
                 }
                 const int inv_tw = recip16(tw);
-                for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
+                for (int idx = threadIdx.x; idx < tw * th; idx += NT) {
                     const int i = div16(idx, inv_tw), j = idx - i * tw;
                     const int gx = px + tx + j, gy = py + ty + i;
                     const int a = sm.pred[0][i * IT + j];
@@ -624,10 +627,10 @@ __global__ void __launch_bounds__(INTER_THREADS, 8) inter_pred_kernel(InterLaunc
                     const int tw = min(IT, ow - tx), th = min(IT, oh - ty);
                     if (ox + tx >= ax1 || ox + tx + tw <= ax0 || oy + ty >= ay1 || oy + ty + th <= ay0) continue;   // CTA-uniform
                     const int posx = ((ox + tx) << 4) + ((2 * nb.mv[1]) >> sx), posy = ((oy + ty) << 4) + ((2 * nb.mv[0]) >> sy);
-                    predict_tile<T>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
+                    predict_tile<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
                                     filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm, sm.pred[0]);
                     const int inv_tw = recip16(tw);
-                    for (int idx = threadIdx.x; idx < tw * th; idx += INTER_THREADS) {
+                    for (int idx = threadIdx.x; idx < tw * th; idx += NT) {
                         const int i = div16(idx, inv_tw), j = idx - i * tw;
                         const int gx = ox + tx + j, gy = oy + ty + i;
                         if (gx >= fp.cw[plane] || gy >= fp.ch[plane] || gx < ax0 || gx >= ax1 || gy < ay0 || gy >= ay1) continue;
@@ -773,15 +776,25 @@ cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
     {
         static bool carve_done = false;
         if (!carve_done) {
-            prefer_max_smem(inter_pred_kernel<uint8_t>);
-            prefer_max_smem(inter_pred_kernel<uint16_t>);
+            prefer_max_smem(inter_pred_kernel<uint8_t, INTER_THREADS>);
+            prefer_max_smem(inter_pred_kernel<uint16_t, INTER_THREADS>);
+            prefer_max_smem(inter_pred_kernel<uint8_t, INTER_THREADS_SMALL>);
+            prefer_max_smem(inter_pred_kernel<uint16_t, INTER_THREADS_SMALL>);
             prefer_max_smem(inter_residual_kernel<uint8_t>);
             prefer_max_smem(inter_residual_kernel<uint16_t>);
             carve_done = true;
         }
     }
-    if (L.fp.bd == 8) inter_pred_kernel<uint8_t><<<L.n_tiles, INTER_THREADS, 0, s>>>(L);
-    else inter_pred_kernel<uint16_t><<<L.n_tiles, INTER_THREADS, 0, s>>>(L);
+    // the host lists the work items of small blocks (at most 16x16 luma samples) first: they run as two-warp CTAs
+    const int n_small = L.n_tiles_small, n_large = L.n_tiles - L.n_tiles_small;
+    if (n_small > 0) {
+        if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, s>>>(L, 0);
+        else inter_pred_kernel<uint16_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, s>>>(L, 0);
+    }
+    if (n_large > 0) {
+        if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS><<<n_large, INTER_THREADS, 0, s>>>(L, n_small);
+        else inter_pred_kernel<uint16_t, INTER_THREADS><<<n_large, INTER_THREADS, 0, s>>>(L, n_small);
+    }
     return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@ struct InterLaunch {
     int n;
     const uint32_t* tiles;     // device, n_tiles work items: record index | quadrant << 28 (one CTA per 64x64 luma quadrant of a record)
     int n_tiles;
+    int n_tiles_small;         // the first n_tiles_small items belong to blocks of at most 16x16 luma samples
     DevPlanes refs[8];         // reference slots (same geometry as the current frame: scaled references are rejected by the host)
     DevPlanes cur;             // frame being reconstructed
     uint8_t* mask;             // device, luma-sized byte plane: difference-weighted compound masks (COMPOUND_DIFFWTD blocks only)

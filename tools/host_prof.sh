@@ -29,6 +29,7 @@ for _ in range(3):
 l.av1r_debug_engine_prof(out6, 0); l.av1r_debug_parse_prof(out5, 0)
 print(f"e2e {rep.frames / best:.1f} fps ({best * 1e3:.1f} ms), summed host parse {rep.host_parse_ms:.1f} ms, device_ms sum {rep.device_ms:.1f}")
 print("engine prof (3 runs, ms): acquire %.1f prepare %.1f fill %.1f issue %.1f wait_parse %.1f drain %.1f" % tuple(out6[:6]))
+print("  workers (3 runs, summed over segment threads, ms): wait_budget %.1f parse_tu %.1f" % (out6[18], out6[19]))
 print("  issue detail (3 runs, ms): getframe %.1f itx %.1f inter %.1f intra %.1f deblock %.1f cdef %.1f lr+sr %.1f emit %.1f | arena_ensure %.1f h2d_enqueue %.1f" % tuple(list(out6[8:16]) + [out6[16], out6[17]]))
 print("parse prof (3 runs, ms): tiles %.1f merge %.1f lf %.1f wrap %.1f begin %.1f" % tuple(out5))
 PY
