@@ -97,6 +97,7 @@ struct DevFrameBuf {
     std::shared_ptr<FrameSlab> slab;   // owner of `base` when set
     DevPlanes pl;
     int cw[3], ch[3], bps;
+    int w[3] = {0, 0, 0}, h[3] = {0, 0, 0};   // visible size of the frame currently held (the reference geometry scaled prediction reads)
     size_t bytes = 0;
     cudaEvent_t ready = nullptr;   // recorded when the frame's last kernel has been queued; readers on other streams wait on it
     ~DevFrameBuf() {
@@ -323,6 +324,8 @@ struct HostArenaPool {
 struct FrameSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t fg_ev = nullptr;   // film-grain templates of this slot's frame are ready (prepared on the side stream)
+    bool fg_prepared = false;
     PinBuf staging;
     DevBuf arena;        // submit path: the frame's work-lists
     DevBuf residual;
@@ -400,6 +403,7 @@ struct EngineImpl {
     StreamParser sp;
     bool opened = false;
     std::vector<cudaStream_t> streams;
+    cudaStream_t side = nullptr;          // film-grain template preparation runs here, ahead of the frame it belongs to
     std::vector<std::unique_ptr<FrameSlot>> slots;
     int next_slot = 0, next_stream = 0;
     std::deque<Pending> pending;          // outputs in display order
@@ -461,15 +465,20 @@ extern "C" void av1r_debug_engine_prof(double* out20, int reset) {
 #define EP_ADD(i, a) g_eprof_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count()
 
 std::shared_ptr<DevFrameBuf> EngineImpl::get_frame(const DevFrameParams& fp) {
-    for (size_t i = 0; i < pool.size(); i++) {
+    std::shared_ptr<DevFrameBuf> got;
+    for (size_t i = 0; i < pool.size() && !got; i++) {
         auto& f = pool[i];
         if (f.use_count() == 1 && f->cw[0] == fp.cw[0] && f->ch[0] == fp.ch[0] && f->cw[1] == fp.cw[1] && f->ch[1] == fp.ch[1] &&
             f->bps == (fp.bd == 8 ? 1 : 2))
-            return f;
+            got = f;
     }
-    const size_t first_new = pool.size();
-    if (!alloc_frames(fp, 8, pool, err)) return nullptr;
-    return pool[first_new];
+    if (!got) {
+        const size_t first_new = pool.size();
+        if (!alloc_frames(fp, 8, pool, err)) return nullptr;
+        got = pool[first_new];
+    }
+    for (int p = 0; p < 3; p++) { got->w[p] = fp.w[p]; got->h[p] = fp.h[p]; }
+    return got;
 }
 
 int EngineImpl::ensure_slots(DevBuf FrameSlot::*member, FrameSlot& s, size_t n, size_t& hw) {
@@ -541,16 +550,23 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.n_tiles = L.n_itiles;
         xl.n_tiles_small = L.n_itiles_small;
         memset(xl.refs, 0, sizeof(xl.refs));
+        memset(xl.ref_w, 0, sizeof(xl.ref_w));
+        memset(xl.ref_h, 0, sizeof(xl.ref_h));
+        for (int i = 0; i < 8; i++) xl.xscale[i] = xl.yscale[i] = 1 << 14;
         for (int i = 0; i < REFS_PER_FRAME; i++) {
             const int slot = dw.fh.ref_frame_idx[i];
             auto& rf = rs->refs[slot];
             if (!rf) { err = "inter frame references an empty slot"; return AV1R_EBITSTREAM; }
-            if (rf->cw[0] != fp.cw[0] || rf->ch[0] != fp.ch[0] || rf->bps != (fp.bd == 8 ? 1 : 2)) {
-                err = "reference frame geometry differs from the current frame";
-                return AV1R_ENOSYS;
+            if (rf->bps != (fp.bd == 8 ? 1 : 2)) {
+                err = "reference frame bit depth differs from the current frame";
+                return AV1R_EBITSTREAM;
             }
             if (!xl.refs[slot].p[0]) {
                 xl.refs[slot] = rf->pl;
+                // reference geometry + scale factors (spec 7.11.3.3): 1 << 14 = same size
+                for (int p = 0; p < 3; p++) { xl.ref_w[slot][p] = rf->w[p]; xl.ref_h[slot][p] = rf->h[p]; }
+                xl.xscale[slot] = (int)((((long long)rf->w[0] << 14) + fp.w[0] / 2) / fp.w[0]);
+                xl.yscale[slot] = (int)((((long long)rf->h[0] << 14) + fp.h[0] / 2) / fp.h[0]);
                 s.hold.push_back(rf);
                 CK(cudaStreamWaitEvent(st, rf->ready, 0));   // produced on another stream
             }
@@ -733,8 +749,17 @@ int EngineImpl::emit_output(FrameSlot* s, int slot_idx, const std::shared_ptr<De
         void* dst[3] = {disp->pl.p[0], disp->pl.p[1], disp->pl.p[2]};
         size_t sp_[3] = {frame->pl.pitch[0], frame->pl.pitch[1], frame->pl.pitch[2]};
         size_t dp_[3] = {disp->pl.pitch[0], disp->pl.pitch[1], disp->pl.pitch[2]};
-        int rc = av1r_stage_film_grain((const av1r_film_grain_params*)&fg, fp.bd, fp.w[0], fp.h[0], fp.subx, fp.suby, fp.mono,
-                                       sp.hp.seq.matrix_coefficients == 0, src, sp_, dst, dp_, s->grain_scratch.p, st);
+        const int mc_id = sp.hp.seq.matrix_coefficients == 0;
+        int rc;
+        if (s->fg_prepared) {   // templates were prepared on the side stream while the frame was being reconstructed
+            CK(cudaStreamWaitEvent(st, s->fg_ev, 0));
+            s->fg_prepared = false;
+        } else {
+            rc = fg_launch_prepare((const av1r_film_grain_params*)&fg, fp.bd, fp.w[0], fp.h[0], fp.subx, fp.suby, fp.mono, mc_id, s->grain_scratch.p, st);
+            if (rc) { err = av1r_stage_last_error(); return rc; }
+        }
+        rc = fg_launch_apply((const av1r_film_grain_params*)&fg, fp.bd, fp.w[0], fp.h[0], fp.subx, fp.suby, fp.mono, mc_id, src, sp_, dst, dp_,
+                             s->grain_scratch.p, st);
         if (rc) {
             err = av1r_stage_last_error();
             return rc;
@@ -883,6 +908,18 @@ int EngineImpl::exec_show_existing(int slot_idx, const FrameHdr& fh, int show_sl
 int EngineImpl::exec_decoded(int slot_idx, const DevWork& dw, const uint8_t* d_arena, int64_t pts) {
     FrameSlot& s = *slots[slot_idx];
     std::shared_ptr<DevFrameBuf> out;
+    s.fg_prepared = false;
+    if (!tm && dw.fh.show_frame && cfg.apply_grain && dw.fh.fg.apply_grain) {
+        // grain templates depend on the header only: prepare them now on the side stream (a single-CTA, ~170 us latency-bound kernel)
+        // instead of at the end of the frame's own chain.  (The stage profile keeps it inline so that its time is attributed.)
+        CK(s.grain_scratch.ensure(av1r_film_grain_scratch_bytes()));
+        const DevFrameParams& fpu = dw.fp_up;
+        int grc = fg_launch_prepare((const av1r_film_grain_params*)&dw.fh.fg, fpu.bd, fpu.w[0], fpu.h[0], fpu.subx, fpu.suby, fpu.mono,
+                                    sp.hp.seq.matrix_coefficients == 0, s.grain_scratch.p, side);
+        if (grc) { err = av1r_stage_last_error(); return grc; }
+        CK(cudaEventRecord(s.fg_ev, side));
+        s.fg_prepared = true;
+    }
     int rc = run_frame(s, dw, d_arena, out);
     if (rc) return rc;
     for (int i = 0; i < 8; i++)
@@ -992,6 +1029,7 @@ Engine::~Engine() {
         for (auto& s : impl_->slots) {
             if (s->ev0) cudaEventDestroy(s->ev0);
             if (s->ev1) cudaEventDestroy(s->ev1);
+            if (s->fg_ev) cudaEventDestroy(s->fg_ev);
         }
         impl_->slots.clear();
         impl_->pending.clear();
@@ -999,6 +1037,7 @@ Engine::~Engine() {
         impl_->pool.clear();
         for (auto& r : impl_->main_refs.refs) r.reset();
         for (auto st : impl_->streams) cudaStreamDestroy(st);
+        if (impl_->side) cudaStreamDestroy(impl_->side);
     }
     delete impl_;
 }
@@ -1026,10 +1065,12 @@ int Engine::open(const av1r_config& cfg) {
     CK(cudaSetDevice(cfg.device));
     E.streams.resize(E.cfg.streams);
     for (auto& st : E.streams) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&E.side, cudaStreamNonBlocking));
     for (int i = 0; i < E.cfg.frames_in_flight; i++) {
         auto s = std::make_unique<FrameSlot>();
         CK(cudaEventCreate(&s->ev0));
         CK(cudaEventCreate(&s->ev1));
+        CK(cudaEventCreateWithFlags(&s->fg_ev, cudaEventDisableTiming));
         E.slots.push_back(std::move(s));
     }
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));

@@ -149,6 +149,7 @@ struct FrameWork {
     std::vector<ObmcNb> obmc;
     std::vector<WarpRec> warps;         // [0..7] global models per reference frame (slot 0 unused), then local ones
     uint8_t gm_warp_valid[8] = {0};
+    uint8_t ref_scaled[8] = {0};        // per reference frame (LAST .. ALTREF): its size differs from this frame's (spec 7.11.3.3 is_scaled)
     // motion state: what this frame's parse reads from earlier frames and what it leaves for later ones
     std::vector<uint8_t> prev_seg_ids;  // PrevSegmentIds (empty = all zero)
     std::vector<MfMv> mfmv;             // projected motion field per 8x8 (empty = no temporal candidates)
@@ -214,6 +215,7 @@ struct FrameWork {
         mfmv.clear();
         saved_mvs.clear();
         memset(gm_warp_valid, 0, sizeof(gm_warp_valid));
+        memset(ref_scaled, 0, sizeof(ref_scaled));
         memset(tool_hist, 0, sizeof(tool_hist));
         coded_samples = coef_tokens = tx_blocks = inter_samples = inter_ref_samples = 0;
         parse_ms = 0;

@@ -479,14 +479,13 @@ extern "C" size_t av1r_film_grain_scratch_bytes(void) { return sizeof(FgDev); }
 
 extern "C" const char* av1r_stage_last_error(void) { return g_stage_err; }
 
-extern "C" int av1r_stage_film_grain(const av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby,
-                                     int mono, int mc_identity, const void* const src[3], const size_t src_pitch[3],
-                                     void* const dst[3], const size_t dst_pitch[3], void* scratch, void* stream) {
+// Two halves of the stage, so that the engine can start the (single-CTA, latency-bound) template preparation on a side stream as
+// soon as the frame is issued -- it depends on the header's grain parameters only -- and apply it when the frame's pixels exist.
+static int fg_setup(const av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby, int mono, int mc_identity, void* scratch, FgK& k) {
     if (!p || !scratch || w <= 0 || h <= 0 || (bpc != 8 && bpc != 10 && bpc != 12)) {
         g_stage_err = "film_grain: bad arguments";
         return -22;
     }
-    cudaStream_t s = (cudaStream_t)stream;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         g_stage_err = "film_grain: no CUDA device";
@@ -499,7 +498,6 @@ extern "C" int av1r_stage_film_grain(const av1r_film_grain_params* p, int bpc, i
         }
         g_gauss_loaded[dev] = true;
     }
-    FgK k;
     k.p = *p;
     k.bd = bpc; k.w = w; k.h = h; k.subx = subx; k.suby = suby; k.mono = mono; k.mc_identity = mc_identity;
     k.nstripes = (h + 31) / 32;
@@ -508,10 +506,27 @@ extern "C" int av1r_stage_film_grain(const av1r_film_grain_params* p, int bpc, i
         g_stage_err = "film_grain: frame too large";
         return -38;
     }
-    FgDev* st = (FgDev*)scratch;
-    fg_prepare_kernel<<<1, 256, 0, s>>>(k, st);
+    return 0;
+}
+
+namespace av1r {
+int fg_launch_prepare(const av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby, int mono, int mc_identity, void* scratch,
+                      cudaStream_t s) {
+    FgK k;
+    const int rc = fg_setup(p, bpc, w, h, subx, suby, mono, mc_identity, scratch, k);
+    if (rc) return rc;
+    fg_prepare_kernel<<<1, 256, 0, s>>>(k, (FgDev*)scratch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_stage_err = cudaGetErrorString(e); return -5; }
+    return 0;
+}
+
+int fg_launch_apply(const av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby, int mono, int mc_identity, const void* const src[3],
+                    const size_t src_pitch[3], void* const dst[3], const size_t dst_pitch[3], void* scratch, cudaStream_t s) {
+    FgK k;
+    const int rc = fg_setup(p, bpc, w, h, subx, suby, mono, mc_identity, scratch, k);
+    if (rc) return rc;
+    FgDev* st = (FgDev*)scratch;
     FgPlanes pp;
     for (int i = 0; i < 3; i++) {
         pp.src[i] = (const uint8_t*)src[mono ? 0 : i];
@@ -519,6 +534,7 @@ extern "C" int av1r_stage_film_grain(const av1r_film_grain_params* p, int bpc, i
         pp.spitch[i] = src_pitch[mono ? 0 : i];
         pp.dpitch[i] = dst_pitch[mono ? 0 : i];
     }
+    cudaError_t e;
     if (bpc == 8) {
         if (subx && suby) e = launch_apply<uint8_t, 1, 1>(k, st, pp, s);
         else if (subx) e = launch_apply<uint8_t, 1, 0>(k, st, pp, s);
@@ -530,4 +546,14 @@ extern "C" int av1r_stage_film_grain(const av1r_film_grain_params* p, int bpc, i
     }
     if (e != cudaSuccess) { g_stage_err = cudaGetErrorString(e); return -5; }
     return 0;
+}
+}  // namespace av1r
+
+extern "C" int av1r_stage_film_grain(const av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby,
+                                     int mono, int mc_identity, const void* const src[3], const size_t src_pitch[3],
+                                     void* const dst[3], const size_t dst_pitch[3], void* scratch, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = av1r::fg_launch_prepare(p, bpc, w, h, subx, suby, mono, mc_identity, scratch, s);
+    if (rc) return rc;
+    return av1r::fg_launch_apply(p, bpc, w, h, subx, suby, mono, mc_identity, src, src_pitch, dst, dst_pitch, scratch, s);
 }

@@ -386,6 +386,55 @@ __device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int l
     __syncthreads();
 }
 
+// ---- scaled references (spec 7.11.3.3 motion vector scaling + 7.11.3.4 block inter prediction) --------------------------------
+// The reference has another size than the frame (spatial resize, or super-resolution on an inter frame): sample positions advance
+// in 1/1024 steps of xStep / yStep from a start position computed once per *block* (the rounding of the start position and of the
+// steps is part of the normative result, so tiles of a block derive their positions from the block origin, not from their own).
+// Rare in practice (the daemon's encoder never resizes): a plain per-sample implementation, reference samples straight from L2.
+__device__ __forceinline__ long long round2s64_d(long long x, int n) {
+    return x >= 0 ? (x + (1ll << (n - 1))) >> n : -((-x + (1ll << (n - 1))) >> n);
+}
+template <typename T, int NT>
+__device__ void predict_tile_scaled(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int bx, int by, int mv_row, int mv_col, int sx, int sy,
+                                    int xscale, int yscale, int fidx_h, int fidx_v, int tx, int ty, int tw, int th, int round1, InterSmem& sm,
+                                    int32_t* out) {
+    const long long origx = ((long long)bx << 4) + ((2 * mv_col) >> sx) + 8, origy = ((long long)by << 4) + ((2 * mv_row) >> sy) + 8;
+    const int startx = (int)(round2s64_d(origx * xscale - (8ll << 14), 8) + 32), starty = (int)(round2s64_d(origy * yscale - (8ll << 14), 8) + 32);
+    const int stepx = (int)round2s64_d(xscale, 4), stepy = (int)round2s64_d(yscale, 4);
+    const int fy0 = starty & 1023;
+    const int rnd = 1 << (round1 - 1);
+    int32_t* mid = sm.mid;
+    // 16 output rows at a time: at most ((15 * 2048 + 1023) >> 10) + 8 = 38 intermediate rows, which fit the 39-row scratch
+    for (int sub = 0; sub < th; sub += 16) {
+        const int sh = min(16, th - sub);
+        const int row0 = (fy0 + stepy * (ty + sub)) >> 10;
+        const int nrows = ((fy0 + stepy * (ty + sub + sh - 1)) >> 10) + 8 - row0;
+        for (int idx = threadIdx.x; idx < nrows * tw; idx += NT) {
+            const int r = idx / tw, c = idx - r * tw;
+            const int p = startx + stepx * (tx + c);
+            const int16_t* f = c_subpel[fidx_h][(p >> 6) & 15];
+            const T* row = (const T*)(ref + (size_t)min(max((starty >> 10) + row0 + r - 3, 0), lasty) * pitch);
+            const int x0 = (p >> 10) - 3;
+            int s = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) s += f[t] * (int)__ldg(row + min(max(x0 + t, 0), lastx));
+            mid[r * IT + c] = (s + 4) >> 3;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < sh * tw; idx += NT) {
+            const int r = idx / tw, c = idx - r * tw;
+            const int p = fy0 + stepy * (ty + sub + r);
+            const int16_t* f = c_subpel[fidx_v][(p >> 6) & 15];
+            const int base = (p >> 10) - row0;
+            int s = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) s += f[t] * mid[(base + t) * IT + c];
+            out[(sub + r) * IT + c] = (s + rnd) >> round1;
+        }
+        __syncthreads();
+    }
+}
+
 // warped prediction of a tile (multiples of 8): one warp per 8x8 sub-block
 template <typename T, int NT>
 __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw, int th,
@@ -470,7 +519,6 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 12) inter_pred_kernel(Inte
         if (plane > 0 && !(r.planes & 2)) continue;
         const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
         const int px = r.x >> sx, py = r.y >> sy, pw = r.w >> sx, ph = r.h >> sy;
-        const int lastx = fp.w[plane] - 1, lasty = fp.h[plane] - 1;
         T* cur = (T*)L.cur.p[plane];
         const int cpe = L.cur.pitch[plane] / sizeof(T);
         const int rx0 = qx0 >> sx, ry0 = qy0 >> sy, rx1 = min(pw, (qx0 + 64) >> sx), ry1 = min(ph, (qy0 + 64) >> sy);
@@ -479,7 +527,12 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 12) inter_pred_kernel(Inte
                 const int tw = min(IT, pw - tx), th = min(IT, ph - ty);
                 for (int l = 0; l < 1 + is_compound; l++) {
                     const DevPlanes& rf = L.refs[r.ref[l]];
-                    if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) {
+                    const int lastx = L.ref_w[r.ref[l]][plane] - 1, lasty = L.ref_h[r.ref[l]][plane] - 1;
+                    if (L.xscale[r.ref[l]] != (1 << 14) || L.yscale[r.ref[l]] != (1 << 14)) {
+                        predict_tile_scaled<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, px, py, r.mv[l][0], r.mv[l][1], sx, sy, L.xscale[r.ref[l]],
+                                                   L.yscale[r.ref[l]], filter_index_d(r.filt[1], pw), filter_index_d(r.filt[0], ph), tx, ty, tw, th, round1,
+                                                   sm, sm.pred[l]);
+                    } else if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) {
                         if (sizeof(T) == 2)
                             warp_tile16<NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, px + tx, py + ty, sx, sy, L.warps[r.warp[l]], tw, th, round1, sm,
                                         sm.pred[l]);
@@ -619,6 +672,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 12) inter_pred_kernel(Inte
             }
             const int ox = (nb.x4 * 4) >> sx, oy = (nb.y4 * 4) >> sy;
             const DevPlanes& rf = L.refs[nb.ref];
+            const int lastx = L.ref_w[nb.ref][plane] - 1, lasty = L.ref_h[nb.ref][plane] - 1;
+            const bool nb_scaled = L.xscale[nb.ref] != (1 << 14) || L.yscale[nb.ref] != (1 << 14);
             const uint8_t* m = d_obmc_mask[31 - __clz(above ? oh : ow)];
             // absolute plane rectangle of this CTA's quadrant: only overlap samples inside it are blended here
             const int ax0 = px + rx0, ay0 = py + ry0, ax1 = px + rx1, ay1 = py + ry1;
@@ -627,8 +682,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 12) inter_pred_kernel(Inte
                     const int tw = min(IT, ow - tx), th = min(IT, oh - ty);
                     if (ox + tx >= ax1 || ox + tx + tw <= ax0 || oy + ty >= ay1 || oy + ty + th <= ay0) continue;   // CTA-uniform
                     const int posx = ((ox + tx) << 4) + ((2 * nb.mv[1]) >> sx), posy = ((oy + ty) << 4) + ((2 * nb.mv[0]) >> sy);
-                    predict_tile<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
-                                    filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm, sm.pred[0]);
+                    if (nb_scaled)
+                        predict_tile_scaled<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, ox, oy, nb.mv[0], nb.mv[1], sx, sy, L.xscale[nb.ref],
+                                                   L.yscale[nb.ref], filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tx, ty, tw, th, 11, sm,
+                                                   sm.pred[0]);
+                    else
+                        predict_tile<T, NT>(rf.p[plane], rf.pitch[plane], lastx, lasty, posx >> 4, posy >> 4, posx & 15, posy & 15,
+                                            filter_index_d(nb.filt[1], ow), filter_index_d(nb.filt[0], oh), tw, th, 11, sm, sm.pred[0]);
                     const int inv_tw = recip16(tw);
                     for (int idx = threadIdx.x; idx < tw * th; idx += NT) {
                         const int i = div16(idx, inv_tw), j = idx - i * tw;

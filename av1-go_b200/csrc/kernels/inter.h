@@ -14,7 +14,9 @@ struct InterLaunch {
     const uint32_t* tiles;     // device, n_tiles work items: record index | quadrant << 28 (one CTA per 64x64 luma quadrant of a record)
     int n_tiles;
     int n_tiles_small;         // the first n_tiles_small items belong to blocks of at most 16x16 luma samples
-    DevPlanes refs[8];         // reference slots (same geometry as the current frame: scaled references are rejected by the host)
+    DevPlanes refs[8];         // reference slots
+    int ref_w[8][3], ref_h[8][3];   // visible size of each reference plane (clamp range of the taps)
+    int xscale[8], yscale[8];  // spec 7.11.3.3 scale factors of each slot against this frame (1 << 14: same size)
     DevPlanes cur;             // frame being reconstructed
     uint8_t* mask;             // device, luma-sized byte plane: difference-weighted compound masks (COMPOUND_DIFFWTD blocks only)
     uint32_t mask_pitch;

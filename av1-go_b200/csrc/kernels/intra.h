@@ -4,6 +4,7 @@
 
 #include "devframe.h"
 
+struct av1r_film_grain_params;
 namespace av1r {
 
 struct IntraLaunch {            // passed by value
@@ -73,6 +74,11 @@ struct SuperresLaunch {
 cudaError_t launch_superres(const SuperresLaunch& L, cudaStream_t s);
 
 cudaError_t launch_plane_checksum(const void* src, size_t pitch, int w, int h, int bpc, uint64_t* out_dev, cudaStream_t s);
+// K8 film grain in two halves (filmgrain.cu): template preparation (depends on the header only) and application
+int fg_launch_prepare(const struct ::av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby, int mono, int mc_identity, void* scratch,
+                      cudaStream_t s);
+int fg_launch_apply(const struct ::av1r_film_grain_params* p, int bpc, int w, int h, int subx, int suby, int mono, int mc_identity,
+                    const void* const src[3], const size_t src_pitch[3], void* const dst[3], const size_t dst_pitch[3], void* scratch, cudaStream_t s);
 cudaError_t launch_frame_checksum(const void* const src[3], const size_t pitch[3], const int w[3], const int h[3], int nplanes, int bpc,
                                   uint64_t* out_dev, cudaStream_t s);
 

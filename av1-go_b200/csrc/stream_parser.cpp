@@ -147,13 +147,18 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
         return fail(AV1R_ENOSYS, "4:4:4 / 4:2:2 streams are not supported yet");
     if (hp.seq.bit_depth > 10) return fail(AV1R_ENOSYS, "12-bit streams are not supported yet");
     // super-resolution: intra frames are reconstructed at the coded (downscaled) width and upscaled before loop restoration (K6);
-    // an inter frame coded with superres predicts from references of a different width (scaled motion compensation, not built)
+    // an inter frame coded with superres predicts from references of a different width: scaled motion compensation (K2)
     if (!fh.frame_is_intra) {
         for (int i = 0; i < REFS_PER_FRAME; i++) {
             const RefHdrState& r = hp.refs[fh.ref_frame_idx[i]];
             if (!r.valid) return fail(AV1R_EBITSTREAM, "inter frame references an empty slot");
-            if (r.upscaled_width != fh.frame_width || r.frame_height != fh.frame_height)
-                return fail(AV1R_ENOSYS, "scaled reference frames are not supported yet");
+            // reference scaling (spec 7.11.3.3 / 5.9.7): a reference may be up to twice as large and down to 1/16 of the frame
+            if (2 * fh.frame_width < r.upscaled_width || 2 * fh.frame_height < r.frame_height || fh.frame_width > 16 * r.upscaled_width ||
+                fh.frame_height > 16 * r.frame_height)
+                return fail(AV1R_EBITSTREAM, "reference frame size outside the allowed scaling range");
+            const int xscale = (int)((((int64_t)r.upscaled_width << 14) + fh.frame_width / 2) / fh.frame_width);
+            const int yscale = (int)((((int64_t)r.frame_height << 14) + fh.frame_height / 2) / fh.frame_height);
+            cur_->ref_scaled[LAST_FRAME + i] = xscale != (1 << 14) || yscale != (1 << 14);
         }
         // global warp models of the 7 references (spec 7.11.3.6 validity)
         cur_->warps.resize(8);

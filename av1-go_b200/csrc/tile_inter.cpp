@@ -540,7 +540,7 @@ void TileDecoder::read_motion_mode(int is_compound) {
     if (!fh.force_integer_mv && (b->y_mode == GLOBALMV || b->y_mode == GLOBAL_GLOBALMV) && fh.gm_type[b->ref_frame[0]] > GM_TRANSLATION) return;
     if (is_compound || b->ref_frame[1] == INTRA_FRAME || !has_overlappable_candidates()) return;
     find_warp_samples();
-    if (fh.force_integer_mv || num_samples == 0 || !fh.allow_warped_motion) {
+    if (fh.force_integer_mv || num_samples == 0 || !fh.allow_warped_motion || fw.ref_scaled[b->ref_frame[0]]) {
         b->motion_mode = ms.symbol(cdf.obmc[b->bsize], 2) ? OBMC_CAUSAL : SIMPLE_TRANSLATION;
     } else {
         b->motion_mode = (uint8_t)ms.symbol(cdf.motion_mode[b->bsize], 3);
@@ -1074,7 +1074,7 @@ void TileDecoder::emit_inter_block() {
     } else if ((b->y_mode == GLOBALMV || b->y_mode == GLOBAL_GLOBALMV) && std::min(bw, bh) >= 8) {
         for (int l = 0; l < 1 + is_compound; l++) {
             const int ref = b->ref_frame[l];
-            if (fh.gm_type[ref] > GM_TRANSLATION && fw.gm_warp_valid[ref]) r.warp[l] = (int16_t)ref;
+            if (fh.gm_type[ref] > GM_TRANSLATION && fw.gm_warp_valid[ref] && !fw.ref_scaled[ref]) r.warp[l] = (int16_t)ref;
         }
     }
     if (is_compound && b->compound_type == COMPOUND_DISTANCE) {

@@ -67,9 +67,52 @@ static int filter_index(int type, int len) {
     return type;
 }
 
+static inline int64_t round2s64(int64_t x, int n) { return x >= 0 ? (x + ((int64_t)1 << (n - 1))) >> n : -((-x + ((int64_t)1 << (n - 1))) >> n); }
+
+// 7.11.3.3 (motion vector scaling) + 7.11.3.4 (block inter prediction) for a reference whose size differs from the frame's
+// (cur_w x cur_h = luma size of the frame being predicted): positions advance in 1/1024 sample steps of xStep / yStep.
+static void block_pred_scaled(const Frame& ref, int cur_w, int cur_h, int plane, int px, int py, int w, int h, int mv_row, int mv_col,
+                              const uint8_t filt[2], int round0, int round1, int* out) {
+    const int sx = plane ? ref.g.subx : 0, sy = plane ? ref.g.suby : 0;
+    const Plane& rp = ref.p[plane];
+    const int lastx = ref.g.w[plane] - 1, lasty = ref.g.h[plane] - 1;
+    const int xscale = (int)((((int64_t)ref.g.w[0] << 14) + cur_w / 2) / cur_w), yscale = (int)((((int64_t)ref.g.h[0] << 14) + cur_h / 2) / cur_h);
+    const int half = 8;
+    const int64_t origx = ((int64_t)px << 4) + ((2 * mv_col) >> sx) + half, origy = ((int64_t)py << 4) + ((2 * mv_row) >> sy) + half;
+    const int64_t basex = origx * xscale - ((int64_t)half << 14), basey = origy * yscale - ((int64_t)half << 14);
+    const int startx = (int)(round2s64(basex, 14 + 4 - 10) + 32), starty = (int)(round2s64(basey, 14 + 4 - 10) + 32);
+    const int stepx = (int)round2s64(xscale, 4), stepy = (int)round2s64(yscale, 4);
+    const int ih = (((h - 1) * stepy + (1 << 10) - 1) >> 10) + 8;
+    const int fih = filter_index(filt[1], w), fiv = filter_index(filt[0], h);
+    std::vector<int> inter((size_t)ih * w);
+    for (int r = 0; r < ih; r++) {
+        const int yy = clip3(0, lasty, (starty >> 10) + r - 3);
+        for (int c = 0; c < w; c++) {
+            const int p = startx + stepx * c;
+            const int16_t* f = av1t_subpel_filters[fih][(p >> 6) & 15];
+            int s = 0;
+            for (int t = 0; t < 8; t++) s += f[t] * rp.at(clip3(0, lastx, (p >> 10) + t - 3), yy);
+            inter[(size_t)r * w + c] = round2(s, round0);
+        }
+    }
+    for (int r = 0; r < h; r++) {
+        const int p = (starty & 1023) + stepy * r;
+        const int16_t* f = av1t_subpel_filters[fiv][(p >> 6) & 15];
+        for (int c = 0; c < w; c++) {
+            int s = 0;
+            for (int t = 0; t < 8; t++) s += f[t] * inter[(size_t)((p >> 10) + t) * w + c];
+            out[r * w + c] = round2(s, round1);
+        }
+    }
+}
+
 // 7.11.3.3 + 7.11.3.4 (unscaled references): out[h][w] at intermediate precision
-static void block_pred(const Frame& ref, int plane, int px, int py, int w, int h, int mv_row, int mv_col, const uint8_t filt[2], int round0,
-                       int round1, int* out) {
+static void block_pred(const Frame& ref, int cur_w, int cur_h, int plane, int px, int py, int w, int h, int mv_row, int mv_col, const uint8_t filt[2],
+                       int round0, int round1, int* out) {
+    if (ref.g.w[0] != cur_w || ref.g.h[0] != cur_h) {
+        block_pred_scaled(ref, cur_w, cur_h, plane, px, py, w, h, mv_row, mv_col, filt, round0, round1, out);
+        return;
+    }
     const int sx = plane ? ref.g.subx : 0, sy = plane ? ref.g.suby : 0;
     const Plane& rp = ref.p[plane];
     const int lastx = ref.g.w[plane] - 1, lasty = ref.g.h[plane] - 1;
@@ -146,7 +189,7 @@ void predict_inter_frame(const FrameWork& fw, Frame& f, const Frame* const refs[
             for (int l = 0; l < 1 + is_compound; l++) {
                 const Frame& ref = *refs[r.ref[l]];
                 if (r.warp[l] >= 0 && pw >= 8 && ph >= 8) warp_pred(ref, plane, px, py, pw, ph, fw.warps[r.warp[l]], round0, round1, preds[l]);
-                else block_pred(ref, plane, px, py, pw, ph, r.mv[l][0], r.mv[l][1], r.filt, round0, round1, preds[l]);
+                else block_pred(ref, g.w[0], g.h[0], plane, px, py, pw, ph, r.mv[l][0], r.mv[l][1], r.filt, round0, round1, preds[l]);
             }
             const int xe = std::min(pw, g.cw[plane] - px), ye = std::min(ph, g.ch[plane] - py);
             if (!is_compound) {
@@ -200,7 +243,7 @@ void predict_inter_frame(const FrameWork& fw, Frame& f, const Frame* const refs[
                         oh = std::min(ph, (nb.step4 * 4) >> sy);
                     }
                     const int ox = (nb.x4 * 4) >> sx, oy = (nb.y4 * 4) >> sy;
-                    block_pred(*refs[nb.ref], plane, ox, oy, ow, oh, nb.mv[0], nb.mv[1], nb.filt, 3, 11, ob.data());
+                    block_pred(*refs[nb.ref], g.w[0], g.h[0], plane, ox, oy, ow, oh, nb.mv[0], nb.mv[1], nb.filt, 3, 11, ob.data());
                     int lg = 0;
                     while ((1 << lg) < (above ? oh : ow)) lg++;
                     const uint8_t* m = av1t_obmc_mask[lg];

@@ -47,6 +47,12 @@ INTER_CASES = {
     "inter_10b_grain_208x144": ("noise", 208, 144, 10, 8, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "3"}, {14: 6, 48: 9999}),
     # key frame coded at 8/11 of the width and upscaled; the inter frames (full width) predict from the upscaled reference
     "inter_8b_kfsuperres_320x192": ("panzoom", 320, 192, 8, 6, {"cpu-used": "5", "cq-level": "32"}, {14: 0, 48: 9999, 19: 1, 20: 8, 21: 11}),
+    # scaled references (spec 7.11.3.3): fixed spatial resize with different denominators for key and inter frames (cfg[16..18] =
+    # rc_resize_mode, rc_resize_denominator, rc_resize_kf_denominator), and super-resolution on inter frames (references have the
+    # upscaled width, the frame is predicted at the coded width: horizontal scaling only)
+    "inter_8b_refscale_352x288": ("panzoom", 352, 288, 8, 10, {"cpu-used": "3", "cq-level": "34"}, {14: 4, 48: 9999, 16: 1, 17: 12, 18: 10}),
+    "inter_10b_refscale_208x144": ("panzoom", 208, 144, 10, 8, {"cpu-used": "2", "cq-level": "30"}, {14: 4, 48: 9999, 16: 1, 17: 14, 18: 9}),
+    "inter_8b_superres_inter_352x288": ("panzoom", 352, 288, 8, 10, {"cpu-used": "3", "cq-level": "34"}, {14: 4, 48: 9999, 19: 1, 20: 12, 21: 9}),
     "inter_10b_mono_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36"}, {14: 4, 48: 9999, 52: 1}),
     "inter_10b_qm_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36", "enable-qm": "1", "qm-min": "0", "qm-max": "15"}, {14: 4, 48: 9999}),
 }
