@@ -159,6 +159,26 @@ __device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long l
     return v;
 }
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Release of border cells without touching L1: `fence.acq_rel.gpu` / __threadfence() compile to MEMBAR.ALL.GPU + CCTL.IVALL, and the
+// CCTL invalidates the whole L1 of the SM -- the records, order lists and halo lines of *every* K3 CTA resident there (co-resident
+// frames slowed each other by 1.6x at two CTAs per SM).  A release RED orders the warp's earlier stores (cumulative over the
+// __syncwarp before it) with a MEMBAR only; the consumers read the cells with L1-bypassing loads after they have seen the bits,
+// so nothing stale can be hit.
+__device__ __forceinline__ void red_release_or64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ T ld_cell(const T* p) {   // coherent at L2, never served by L1
+    if (sizeof(T) == 1) {
+        unsigned short v;   // (no 8-bit register class in inline PTX: load into a 16-bit one)
+        asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+        return (T)v;
+    } else {
+        unsigned short v;
+        asm volatile("ld.relaxed.gpu.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+        return (T)v;
+    }
+}
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ int warp_sum(int v) {
@@ -854,8 +874,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 }
                             }
                         }
-                        __syncwarp();
-                        fence_acquire_gpu();
+                        __syncwarp();   // every lane is past the polls that saw the bits: the cells are in L2 (released before the bits)
                         if (nbr >= 0) {   // bring the cell's four samples next to the unit into the canvas halo
                             T* cv = uc.cv(plane);
                             const int cs = uc.cs(plane), W = uc.W(plane);
@@ -867,14 +886,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
                                     const int dx = cxl * 4 + j;
-                                    if (x0 + dx < pcw) cv[-cs + dx] = __ldcg(src + x0 + dx);
+                                    if (x0 + dx < pcw) cv[-cs + dx] = ld_cell<T>(src + x0 + dx);
                                 }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
                                     const int dy = cyl * 4 + j;
                                     if (y0 + dy < pch) {
-                                        const T v = __ldcg(reinterpret_cast<const T*>(fb + (size_t)(y0 + dy) * pitch) + x0 - 1);
+                                        const T v = ld_cell<T>(reinterpret_cast<const T*>(fb + (size_t)(y0 + dy) * pitch) + x0 - 1);
                                         if (dy < W) cv[dy * cs - 1] = v;
                                         else uc.lext[uc.lext_off(plane) + dy - W] = v;
                                     }
@@ -943,9 +962,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                     bits |= (unsigned long long)ob << (prog_roff(plane) + ly4);
                 }
                 if (bits) {
-                    __threadfence();
                     __syncwarp();
-                    if (lane == 0) atomicOr(L.uprog + u, bits);
+                    if (lane == 0) red_release_or64(L.uprog + u, bits);
                 }
             }
             lap(10, lane == 0);  // predict + reconstruct
@@ -969,9 +987,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                     reinterpret_cast<const uint32_t*>(cv + row * cs)[wi];
             }
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(L.uflags + u, 1);
+        if (tid == 0) st_release(L.uflags + u, 1);   // release after the CTA barrier: cumulative over every thread's write-back stores
         rpar ^= 1;
         lap(6, tid == 0);   // write-back + release
         if (L.prof && tid == 0) atomicAdd(L.prof + 13, 1ull);
