@@ -145,7 +145,8 @@ static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, lf[3], cdef_idx, skip_mi, lr[3], inter, itiles, obmc, warps, pal, k3order, k3units, total;
+    size_t recs, coefs, order, lf[3], lfblk, lftx[3], cdef_idx, skip_mi, lr[3], inter, itiles, obmc, warps, pal, k3order, k3units, total;
+    int n_lfblk, lf_device;
     int n_recs, n_coefs, n_order, n_order_small, n_inter, n_itiles, n_itiles_small, n_obmc, n_warps, n_k3, n_k3units;
 };
 
@@ -209,7 +210,19 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     L.recs = take(sizeof(TxRec) * std::max(1, L.n_recs));
     L.coefs = take(sizeof(uint32_t) * std::max(1, L.n_coefs));
     L.order = take(sizeof(uint32_t) * std::max(1, L.n_order));
-    for (int p = 0; p < 3; p++) L.lf[p] = take(sizeof(LfEdge) * std::max<size_t>(1, fw.lf[p].size()));
+    // deblocking: host-classified edges (4 B per 4x4 cell and plane), or -- the engine's own parsers -- the block list and the
+    // per-4x4 transform-size maps from which the device classifies the edges itself (a quarter of the bytes, none of the host time)
+    L.lf_device = !fw.host_lf;
+    L.n_lfblk = (int)fw.lf_blocks.size();
+    if (L.lf_device) {
+        for (int p = 0; p < 3; p++) L.lf[p] = 0;
+        L.lfblk = take(sizeof(LfBlk) * std::max(1, L.n_lfblk));
+        for (int p = 0; p < 3; p++) L.lftx[p] = take(std::max<size_t>(1, (size_t)fw.plane_w4(p) * fw.plane_h4(p)));
+    } else {
+        for (int p = 0; p < 3; p++) L.lf[p] = take(sizeof(LfEdge) * std::max<size_t>(1, fw.lf[p].size()));
+        L.lfblk = 0;
+        for (int p = 0; p < 3; p++) L.lftx[p] = 0;
+    }
     L.cdef_idx = take(std::max<size_t>(1, fw.cdef_idx.size()));
     L.skip_mi = take(std::max<size_t>(1, fw.skip_mi.size()));
     for (int p = 0; p < 3; p++) {
@@ -254,8 +267,15 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
             }
         dw.lay.n_order_small = lo;
     }
-    for (int p = 0; p < 3; p++)
-        if (!fw.lf[p].empty()) memcpy(h + L.lf[p], fw.lf[p].data(), sizeof(LfEdge) * fw.lf[p].size());
+    if (L.lf_device) {
+        if (L.n_lfblk) memcpy(h + L.lfblk, fw.lf_blocks.data(), sizeof(LfBlk) * L.n_lfblk);
+        const bool lf_frame = fw.fh.lf.level[0] || fw.fh.lf.level[1];
+        for (int p = 0; p < (fw.mono ? 1 : 3) && lf_frame; p++)
+            memcpy(h + L.lftx[p], fw.lf_tx[p].data(), (size_t)fw.plane_w4(p) * fw.plane_h4(p));
+    } else {
+        for (int p = 0; p < 3; p++)
+            if (!fw.lf[p].empty()) memcpy(h + L.lf[p], fw.lf[p].data(), sizeof(LfEdge) * fw.lf[p].size());
+    }
     if (!fw.cdef_idx.empty()) memcpy(h + L.cdef_idx, fw.cdef_idx.data(), fw.cdef_idx.size());
     if (!fw.skip_mi.empty()) memcpy(h + L.skip_mi, fw.skip_mi.data(), fw.skip_mi.size());
     for (int p = 0; p < 3; p++)
@@ -331,6 +351,7 @@ struct FrameSlot {
     DevBuf residual;
     DevBuf sync;         // K3 done flags + ticket
     DevBuf diffmask;     // K2 difference-weighted compound masks (luma-sized byte plane)
+    DevBuf lfscratch;    // device-side deblocking edge classification: per-mi block index + the three LfEdge planes
     DevBuf grain_scratch;
     DevBuf cks_dev;
     PinBuf cks_host;     // 3 x uint64 (+ planes in parity mode)
@@ -418,7 +439,7 @@ struct EngineImpl {
     DevBuf k3_stuck;                                  // one int: watchdog word of the intra kernel (sticky until the next verify / replay)
     HostArenaPool host_pool;
     std::shared_ptr<void> make_host_arena(const FrameWork& fw, const SeqHdr& seq, std::string& e, int& rc);
-    size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0;   // high-water marks of the slot buffers
+    size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0, hw_lf = 0;   // high-water marks of the slot buffers
     int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
     int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
     int k3_progressive = 2;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive, 2 always cell-level (default)
@@ -643,13 +664,30 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     if (dw.lf_on && (cfg.inloop_filters & 1)) {
         LfLaunch ll;
         ll.frame = cur->pl;
-        for (int p = 0; p < 3; p++) {
-            ll.edges[p] = (const LfEdge*)(d_arena + L.lf[p]);
-            ll.plane_on[p] = dw.lf_plane_on[p];
-        }
         ll.fp = fp;
+        if (L.lf_device) {
+            // classify the edges on the device: block list -> per-mi block index -> LfEdge planes (slot scratch)
+            size_t off[4], o = align_up((size_t)fp.mi_cols * fp.mi_rows * sizeof(uint32_t), 256);
+            for (int p = 0; p < 3; p++) { off[p] = o; o += align_up((size_t)fp.pw4[p] * fp.ph4[p] * sizeof(LfEdge), 256); }
+            { int e_ = ensure_slots(&FrameSlot::lfscratch, s, o, hw_lf); if (e_) return e_; }
+            LfClassify lc;
+            lc.blks = (const LfBlk*)(d_arena + L.lfblk);
+            lc.n_blks = L.n_lfblk;
+            lc.mi_blk = (uint32_t*)s.lfscratch.p;
+            for (int p = 0; p < 3; p++) {
+                lc.lf_tx[p] = d_arena + L.lftx[p];
+                lc.edges[p] = (LfEdge*)(s.lfscratch.p + off[p]);
+                lc.plane_on[p] = dw.lf_plane_on[p];
+                ll.edges[p] = lc.edges[p];
+            }
+            lc.fp = fp;
+            CK(launch_lf_classify(lc, st));
+        } else {
+            for (int p = 0; p < 3; p++) ll.edges[p] = (const LfEdge*)(d_arena + L.lf[p]);
+        }
+        for (int p = 0; p < 3; p++) ll.plane_on[p] = dw.lf_plane_on[p];
         CK(launch_deblock(ll, st));
-        if (tm) tm->end(AV1R_ST_DEBLOCK, 2, st);
+        if (tm) tm->end(AV1R_ST_DEBLOCK, L.lf_device ? 4 : 2, st);
     }
     EP_ADD(12, t_h);
     t_h = EP_T();
@@ -1083,6 +1121,7 @@ int Engine::open(const av1r_config& cfg) {
     }
     CK(E.k3_stuck.ensure(256));
     CK(cudaMemset(E.k3_stuck.p, 0, 256));
+    E.sp.host_lf_edges = false;   // (streaming API parser) deblocking edges are classified on the device
     CK(E.wedge_master.ensure(6 * 64 * 64));
     CK(inter_copy_wedge_master(E.wedge_master.p, E.streams[0]));
     CK(cudaStreamSynchronize(E.streams[0]));
@@ -1450,7 +1489,8 @@ int Engine::verify_items(std::vector<VerifyFile*>& files, const std::vector<Veri
             const VerifyFile& vf = *files[items[s].file];
             StreamParser sp;
             sp.hp.seq = vf.seq_for(sg.tu0);
-            sp.defer_finalize = true;   // merge of the tile lists + deblocking edges run in the staging step below, off the parse chain
+            sp.defer_finalize = true;   // merge of the tile lists runs in the staging step below, off the parse chain
+            sp.host_lf_edges = false;   // deblocking edges are classified on the device
             auto publish = [&sg, &ready_cv](size_t t, std::vector<ParsedFrame>&& pfs, int prc, const std::string& perr) {
                 {
                     std::lock_guard<std::mutex> lk(sg.m);
@@ -1695,6 +1735,7 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
             memset(&so.info, 0, sizeof(so.info));
             StreamParser parser;
             parser.hp.seq = seg_seq[sidx];
+            parser.host_lf_edges = false;
             const int t1 = sidx + 1 < nseg ? starts[sidx + 1] : n;
             for (int t = starts[sidx]; t < t1 && !so.rc; t++) {
                 std::vector<ParsedFrame> pfs;

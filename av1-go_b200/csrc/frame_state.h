@@ -122,6 +122,7 @@ struct TileOut {
     std::vector<InterBlk> inter;
     std::vector<ObmcNb> obmc;
     std::vector<WarpRec> warps;         // local warp models of this tile (InterBlk::warp = 8 + index until merged)
+    std::vector<LfBlk> lf_blocks;       // device-side deblocking edge classification: one record per block
     std::deque<BlockInfo> blocks;       // mode info storage; FrameWork::mi points into it
     uint64_t coded_samples = 0, coef_tokens = 0, tx_blocks = 0, inter_samples = 0, inter_ref_samples = 0;
     uint32_t tool_hist[24] = {0};
@@ -140,7 +141,9 @@ struct FrameWork {
     std::vector<uint32_t> coefs;
     std::vector<SbRange> sbs;
     std::vector<uint8_t> pal;
-    std::vector<LfEdge> lf[3];          // per plane, (plane_h4 x plane_w4)
+    std::vector<LfEdge> lf[3];          // per plane, (plane_h4 x plane_w4): host-side edge classification (oracle / tests)
+    std::vector<LfBlk> lf_blocks;       // device-side edge classification: block list (see host_lf)
+    bool host_lf = true;                // true: build_loopfilter_edges fills lf[] on the host; false: the engine ships lf_blocks + lf_tx
     std::vector<int8_t> cdef_idx;       // per 64x64 luma block, -1 = skip
     std::vector<uint8_t> skip_mi;       // per mi: block skip flag (CDEF 8x8 skip condition)
     std::vector<LrUnit> lr[3];
@@ -210,6 +213,7 @@ struct FrameWork {
         inter.clear();
         obmc.clear();
         warps.clear();
+        lf_blocks.clear();
         n_tiles_used = 0;
         prev_seg_ids.clear();
         mfmv.clear();
@@ -233,6 +237,7 @@ struct FrameWork {
         t.inter.clear();
         t.obmc.clear();
         t.warps.clear();
+        t.lf_blocks.clear();
         t.blocks.clear();
         t.coded_samples = t.coef_tokens = t.tx_blocks = t.inter_samples = t.inter_ref_samples = 0;
         memset(t.tool_hist, 0, sizeof(t.tool_hist));

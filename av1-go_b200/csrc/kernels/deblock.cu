@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../av1_consts.h"
 #include "dev_common.cuh"
 #include "devframe.h"
 #include "intra.h"
@@ -150,6 +151,83 @@ __global__ void __launch_bounds__(256) deblock_kernel(LfLaunch L) {
     const int pitch_e = L.frame.pitch[plane] / sizeof(T);
     T* q0 = (T*)L.frame.p[plane] + (size_t)y * pitch_e + x;
     lf_line<T>(q0, PASS ? pitch_e : 1, plane, len, lvl, L.fp.lf_sharpness, L.fp.bd);
+}
+
+// ---- edge classification on the device (what the host pre-pass build_loopfilter_edges computes, stream_parser.cpp) -----------
+__constant__ uint8_t c_lf_txw[TX_SIZES_ALL] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
+__constant__ uint8_t c_lf_txh[TX_SIZES_ALL] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
+__constant__ uint8_t c_lf_bw[BLOCK_SIZES_ALL] = {4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64, 128, 128, 4, 16, 8, 32, 16, 64};
+__constant__ uint8_t c_lf_bh[BLOCK_SIZES_ALL] = {4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 64, 32, 64, 128, 64, 128, 16, 4, 32, 8, 64, 16};
+
+// one warp per block: its mi cells (clipped to the frame) get the block's index
+__global__ void __launch_bounds__(256) lf_scatter_kernel(const LfBlk* __restrict__ blks, int n, uint32_t* __restrict__ mi_blk, int mi_cols, int mi_rows) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n) return;
+    const LfBlk b = blks[wid];
+    const int w4 = c_lf_bw[b.bsize] >> 2, h4 = c_lf_bh[b.bsize] >> 2;
+    const int cw = min(w4, mi_cols - b.mi_col), ch = min(h4, mi_rows - b.mi_row);
+    const int lw = 31 - __clz(w4);
+    for (int i = lane; i < (h4 << lw); i += 32) {
+        const int y = i >> lw, x = i & (w4 - 1);
+        if (x < cw && y < ch) mi_blk[(size_t)(b.mi_row + y) * mi_cols + b.mi_col + x] = (uint32_t)wid;
+    }
+}
+
+__global__ void __launch_bounds__(256) lf_classify_kernel(LfClassify L) {
+    const int plane = blockIdx.z;
+    if (!L.plane_on[plane]) return;
+    const DevFrameParams& fp = L.fp;
+    const int sx = plane ? fp.subx : 0, sy = plane ? fp.suby : 0;
+    const int pw4 = fp.pw4[plane], ph4 = fp.ph4[plane];
+    const int c4 = blockIdx.x * 64 + (threadIdx.x & 63), r4 = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (c4 >= pw4 || r4 >= ph4) return;
+    const int mi_cols = fp.mi_cols, mi_rows = fp.mi_rows;
+    const size_t idx = (size_t)r4 * pw4 + c4;
+    const int row = r4 << sy, col = c4 << sx;
+    LfEdge e = {0, 0, 0, 0};
+    // for sub-sampled planes the spec addresses mode info at the odd (bottom-right) luma mi
+    const int mrow = min(mi_rows - 1, row | sy), mcol = min(mi_cols - 1, col | sx);
+    if (row * 4 < fp.h[0] && col * 4 < fp.w[0]) {
+        const uint8_t* lf_tx = L.lf_tx[plane];
+        const LfBlk b = L.blks[L.mi_blk[(size_t)mrow * mi_cols + mcol]];
+        const int max_len = plane ? 8 : 16;
+        const int li0 = plane == 0 ? 0 : plane + 1, li1 = plane == 0 ? 1 : plane + 1;
+        const int txsz = lf_tx[idx];
+        const int txw = c_lf_txw[txsz], txh = c_lf_txh[txsz];
+        const int bwp = max(4, c_lf_bw[b.bsize] >> sx), bhp = max(4, c_lf_bh[b.bsize] >> sy);
+        const int xp = c4 * 4, yp = r4 * 4;
+        if (c4 > 0 && (xp & (txw - 1)) == 0 && (b.filt_inside || (xp & (bwp - 1)) == 0)) {
+            int lvl = b.lvl[li0];
+            if (!lvl) {
+                const int pcol = min(mi_cols - 1, ((c4 - 1) << sx) | sx);
+                lvl = L.blks[L.mi_blk[(size_t)mrow * mi_cols + pcol]].lvl[li0];
+            }
+            if (lvl) {
+                e.len_v = (uint8_t)min(max_len, min((int)c_lf_txw[lf_tx[idx - 1]], txw));
+                e.lvl_v = (uint8_t)lvl;
+            }
+        }
+        if (r4 > 0 && (yp & (txh - 1)) == 0 && (b.filt_inside || (yp & (bhp - 1)) == 0)) {
+            int lvl = b.lvl[li1];
+            if (!lvl) {
+                const int prow = min(mi_rows - 1, ((r4 - 1) << sy) | sy);
+                lvl = L.blks[L.mi_blk[(size_t)prow * mi_cols + mcol]].lvl[li1];
+            }
+            if (lvl) {
+                e.len_h = (uint8_t)min(max_len, min((int)c_lf_txh[lf_tx[idx - pw4]], txh));
+                e.lvl_h = (uint8_t)lvl;
+            }
+        }
+    }
+    L.edges[plane][idx] = e;
+}
+
+cudaError_t launch_lf_classify(const LfClassify& L, cudaStream_t s) {
+    if (L.n_blks <= 0) return cudaErrorInvalidValue;
+    lf_scatter_kernel<<<(L.n_blks * 32 + 255) / 256, 256, 0, s>>>(L.blks, L.n_blks, L.mi_blk, L.fp.mi_cols, L.fp.mi_rows);
+    dim3 grid((L.fp.pw4[0] + 63) / 64, (L.fp.ph4[0] + 3) / 4, L.fp.mono ? 1 : 3);
+    lf_classify_kernel<<<grid, 256, 0, s>>>(L);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_deblock(const LfLaunch& L, cudaStream_t s) {

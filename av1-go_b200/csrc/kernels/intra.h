@@ -40,6 +40,18 @@ struct LfLaunch {
     int plane_on[3];
 };
 cudaError_t launch_deblock(const LfLaunch& L, cudaStream_t s);
+// Device-side edge classification (spec 7.14.2 - 7.14.5): scatter the block list into a per-mi block index, then one thread per
+// 4x4 cell and plane derives filter length and level of its left / top edge.  Same result as the host's build_loopfilter_edges.
+struct LfClassify {
+    const LfBlk* blks;         // device
+    int n_blks;
+    uint32_t* mi_blk;          // device scratch, [mi_rows][mi_cols]: index into blks
+    const uint8_t* lf_tx[3];   // device, per plane [ph4][pw4]: transform size of the cell
+    LfEdge* edges[3];          // device, out
+    int plane_on[3];
+    DevFrameParams fp;
+};
+cudaError_t launch_lf_classify(const LfClassify& L, cudaStream_t s);
 
 struct CdefLaunch {
     DevPlanes src, dst;

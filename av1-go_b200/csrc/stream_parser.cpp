@@ -119,6 +119,7 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
         return fail(AV1R_EBITSTREAM, "frame size outside the AV1 level limits");
     cur_ = acquire_framework();
     cur_->init(hp.seq, fh);
+    cur_->host_lf = host_lf_edges;
     cur_fh_ = fh;
     tiles_done_ = 0;
     have_frame_ = true;
@@ -339,6 +340,7 @@ void finalize_framework(FrameWork& fw) {
         }
         fw.obmc.insert(fw.obmc.end(), to.obmc.begin(), to.obmc.end());
         fw.warps.insert(fw.warps.end(), to.warps.begin(), to.warps.end());
+        fw.lf_blocks.insert(fw.lf_blocks.end(), to.lf_blocks.begin(), to.lf_blocks.end());
         fw.coded_samples += to.coded_samples;
         fw.coef_tokens += to.coef_tokens;
         fw.tx_blocks += to.tx_blocks;
@@ -348,7 +350,7 @@ void finalize_framework(FrameWork& fw) {
     }
     PROF_ADD(1, tm);
     auto tl = PROF_T();
-    build_loopfilter_edges(fw);
+    if (fw.host_lf) build_loopfilter_edges(fw);
     PROF_ADD(2, tl);
     fw.parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm).count();
     fw.finalized = true;

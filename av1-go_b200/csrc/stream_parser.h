@@ -29,6 +29,8 @@ public:
     // true: parse_tu returns frames whose work-lists are still per tile; the caller runs finalize_framework(*pf.fw) (on another
     // thread, typically) before it reads fw.tx / coefs / inter / lf.  Everything the parse of later frames needs is complete.
     bool defer_finalize = false;
+    // false: the deblocking edges are classified on the device; frames carry FrameWork::lf_blocks (+ lf_tx) instead of lf[]
+    bool host_lf_edges = true;
     // Parses one temporal unit; appends one ParsedFrame per frame (shown or not) in decode order.
     // Returns 0 or AV1R_E*.
     int parse_tu(const uint8_t* data, size_t len, int64_t pts, std::vector<ParsedFrame>& out);

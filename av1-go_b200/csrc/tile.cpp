@@ -417,13 +417,15 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
     }
     // publish the block in the per-mi maps (clipped to the frame)
     const int rmax = std::min(r + bh4, fw.mi_rows), cmax = std::min(c + bw4, fw.mi_cols);
-    LfMi lm;
-    memcpy(lm.lvl, b->lf_lvl, 4);
-    lm.bsize = b->bsize;
-    lm.filt_inside = (uint8_t)(!b->skip || b->ref_frame[0] <= INTRA_FRAME);
-    lm.valid = 1;
-    lm.pad = 0;
-    {   // four per-mi maps, one contiguous run per row each: library fills (vectorised) instead of a four-stream scalar loop
+    const bool lf_frame = fh.lf.level[0] || fh.lf.level[1];
+    if (fw.host_lf) {
+        LfMi lm;
+        memcpy(lm.lvl, b->lf_lvl, 4);
+        lm.bsize = b->bsize;
+        lm.filt_inside = (uint8_t)(!b->skip || b->ref_frame[0] <= INTRA_FRAME);
+        lm.valid = 1;
+        lm.pad = 0;
+        // four per-mi maps, one contiguous run per row each: library fills (vectorised) instead of a four-stream scalar loop
         const size_t n = (size_t)(cmax - c);
         for (int y = r; y < rmax; y++) {
             const size_t o = (size_t)y * fw.mi_cols + c;
@@ -431,6 +433,25 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
             memset(&fw.skip_mi[o], b->skip, n);
             memset(&fw.seg_ids[o], b->segment_id, n);
             std::fill_n(&fw.lf_mi[o], n, lm);
+        }
+    } else {
+        // device-side edge classification: the block goes into a 12-byte list, the per-mi level map is not needed on the host
+        if (lf_frame) {
+            LfBlk lb;
+            lb.mi_row = (uint16_t)r;
+            lb.mi_col = (uint16_t)c;
+            lb.bsize = b->bsize;
+            lb.filt_inside = (uint8_t)(!b->skip || b->ref_frame[0] <= INTRA_FRAME);
+            memcpy(lb.lvl, b->lf_lvl, 4);
+            lb.pad = 0;
+            to.lf_blocks.push_back(lb);
+        }
+        const size_t n = (size_t)(cmax - c);
+        for (int y = r; y < rmax; y++) {
+            const size_t o = (size_t)y * fw.mi_cols + c;
+            std::fill_n(&fw.mi[o], n, b);
+            memset(&fw.skip_mi[o], b->skip, n);
+            memset(&fw.seg_ids[o], b->segment_id, n);
         }
     }
     if (b->is_inter) emit_inter_block();

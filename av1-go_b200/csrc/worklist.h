@@ -124,6 +124,16 @@ static constexpr int K3_UNIT_MAX_RECS = 640;    // per-record barrier capacity o
 struct LfEdge {
     uint8_t len_v, lvl_v, len_h, lvl_h;
 };
+// What the deblocking edge classification needs of one block (spec 7.14.2 - 7.14.5).  With device-side classification the host ships
+// this list (12 B per block) plus the per-4x4 transform-size maps instead of one LfEdge per 4x4 cell of every plane.
+struct LfBlk {
+    uint16_t mi_row, mi_col;
+    uint8_t bsize;
+    uint8_t filt_inside;       // !skip || intra: transform edges inside the block are filtered too
+    uint8_t lvl[4];            // filter level per edge class: Y vertical, Y horizontal, U, V
+    uint16_t pad;
+};
+static_assert(sizeof(LfBlk) == 12, "LfBlk must stay 12 bytes");
 
 // Frame-level parameters every kernel needs (kept small; passed by value or via constant memory).
 struct FrameParams {
