@@ -78,6 +78,7 @@ extern "C" int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threa
             const int s = next.fetch_add(1);
             if (s >= nseg) return;
             StreamParser sp;
+            sp.host_lf_edges = false;   // as on the verify path: deblocking edges are classified on the device
             sp.hp.seq = scan.seq;
             sp.tile_threads = tile_threads != 0;
             const size_t t1 = s + 1 < nseg ? starts[s + 1] : dm.tus.size();

@@ -443,6 +443,8 @@ struct EngineImpl {
     int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
     int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
     int k3_progressive = 2;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive, 2 always cell-level (default)
+    int k3_wait_ns = 0;                               // AV1R_K3_WAIT_NS: sleep between attempts of a record-level wait
+    int k3_poll_ns_max = 800;                         // AV1R_K3_POLL_NS: back-off cap of the neighbour-unit polls
     int k3_inter_mult = 6;                            // inter frames: CTAs = this x the unit wavefront (AV1R_K3_INTER_MULT)
     int k3_intra_run = 0;                             // consecutive frames without inter prediction issued so far
     int64_t frames_decoded = 0;
@@ -622,6 +624,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             if (k3_ctas <= 0 && L.n_inter > 0) il.ctas = std::min(L.n_k3units, k3_inter_mult * il.ctas);
         }
         il.warps = k3_warps;
+        il.wait_ns = k3_wait_ns;
+        il.poll_ns_max = k3_poll_ns_max;
         il.load_tile = L.n_inter > 0;
         // sync block: [n_units x u64 progress words][n_units x int unit flags][ticket, stuck flag, pad]
         const size_t sync_bytes = (sizeof(unsigned long long) + sizeof(int)) * (size_t)L.n_k3units + 4 * sizeof(int);
@@ -1115,6 +1119,8 @@ int Engine::open(const av1r_config& cfg) {
     if (const char* e = getenv("AV1R_K3_INTER_MULT")) E.k3_inter_mult = std::max(1, atoi(e));
     if (const char* e = getenv("AV1R_K3_PROGRESSIVE")) E.k3_progressive = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("AV1R_K3_WARPS")) E.k3_warps = std::min(8, std::max(1, atoi(e)));
+    if (const char* e = getenv("AV1R_K3_WAIT_NS")) E.k3_wait_ns = std::min(100000, std::max(0, atoi(e)));
+    if (const char* e = getenv("AV1R_K3_POLL_NS")) E.k3_poll_ns_max = std::min(100000, std::max(100, atoi(e)));
     if (getenv("AV1R_K3_PROF")) {
         CK(E.k3_prof.ensure(16 * sizeof(unsigned long long)));
         CK(cudaMemset(E.k3_prof.p, 0, 16 * sizeof(unsigned long long)));

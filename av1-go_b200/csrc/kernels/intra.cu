@@ -574,7 +574,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // `stuck` (one int per frame) is raised instead of hanging if a wait makes no progress for seconds: a wrong work-list must
 // end in a digest mismatch, not in a wedged GPU.
-__device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parity, int* stuck) {
+__device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parity, int* stuck, int wait_ns) {
     for (int rounds = 0; rounds < 64; rounds++) {
         const bool pend = id >= 0 && !mbar_test(rbar + 8u * (uint32_t)id, parity);
         if (!__any_sync(0xffffffffu, pend)) return;
@@ -582,8 +582,10 @@ __device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parit
         // it times out, not the whole test / vote / reduce sequence
         const uint32_t b = rbar + 8u * (uint32_t)__reduce_max_sync(0xffffffffu, pend ? id : -1);
         int spins = 0;
-        while (!mbar_try(b, parity))
+        while (!mbar_try(b, parity)) {
+            if (wait_ns) __nanosleep(wait_ns);   // waiting warps of co-resident frames must not eat the working warps' issue slots
             if (++spins > (1 << 22)) { *stuck = 1; return; }
+        }
     }
     *stuck = 1;
 }
@@ -799,7 +801,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             if (k + nw < count) r_next = load_rec(L.recs + __ldg(L.order + first + k + nw));
             lap(8, lane == 0);   // record fetch
             if (r.mode == TXM_INTER) {
-                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck);   // residual of an inter-intra block: after its blend
+                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck, L.wait_ns);   // residual of an inter-intra block: after its blend
             } else if (r.mode != TXM_PALETTE) {
                 const int plane = r.plane;
                 const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
@@ -869,7 +871,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 unsigned ns = 100;
                                 while ((ld_relaxed64(L.uprog + d) & want) != want) {
                                     __nanosleep(ns);
-                                    if (ns < 800) ns <<= 1;
+                                    if (ns < (unsigned)L.poll_ns_max) ns <<= 1;
                                     if (++spins > (1 << 23)) { *L.stuck = 3; break; }
                                 }
                             }
@@ -902,7 +904,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                         }
                         __syncwarp();
                     }
-                    wait_local(rbar, id, rpar, L.stuck);
+                    wait_local(rbar, id, rpar, L.stuck, L.wait_ns);
                 }
                 if (r.mode == TXM_CFL) {   // luma samples under this chroma block
                     const int sx = fp.subx, sy = fp.suby;
@@ -919,7 +921,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 if (id >= k) id = -1;
                             }
                         }
-                        wait_local(rbar, id, rpar, L.stuck);
+                        wait_local(rbar, id, rpar, L.stuck, L.wait_ns);
                     }
                 }
             }

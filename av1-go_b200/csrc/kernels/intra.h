@@ -17,6 +17,8 @@ struct IntraLaunch {            // passed by value
     int warps;                  // warps per CTA (records of a unit in flight)
     int load_tile;              // 1: the frame already holds inter-predicted samples (inter frame) -> bring the unit in before predicting
     int progressive;            // 1: units hand their bottom row / right column over cell by cell (uprog), 0: whole units (uflags)
+    int wait_ns;                // sleep between two attempts of a record-level wait (0: re-issue try_wait immediately)
+    int poll_ns_max;            // cap of the back-off between polls of a neighbour unit's progress word
     unsigned long long* uprog;  // device, n_units words, zeroed before launch: finished border cells of every unit (bit layout in intra.cu)
     int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
     int* ticket;                // device, one int, zeroed before launch
