@@ -197,7 +197,7 @@ extern "C" int av1r_debug_k3_check(const uint8_t* data, size_t len, long long* f
             std::vector<TxRec> recs(fw.tx);
             std::vector<uint32_t> k3((size_t)std::max(1, n_k3));
             std::vector<K3Unit> units((size_t)((fw.mi_cols + 15) >> 4) * ((fw.mi_rows + 15) >> 4) + 1);
-            const int nu = k3_plan_build(fw.tx.data(), n_recs, n_k3, fw.subx, fw.suby, fw.sb128, fw.mi_cols, fw.mi_rows, recs.data(), k3.data(), units.data());
+            const int nu = k3_plan_build(fw.tx.data(), n_recs, n_k3, fw.subx, fw.suby, fw.sb128, fw.mi_cols, fw.mi_rows, recs.data(), k3.data(), units.data(), fw.fh.allow_intrabc ? 1 : 0);
             const std::string bad = k3_plan_check(fw.tx.data(), n_recs, n_k3, fw.subx, fw.suby, fw.mi_cols, fw.mi_rows, recs.data(), k3.data(), units.data(), nu);
             if (!bad.empty()) {
                 snprintf(msg, cap, "frame %lld: %s", nf, bad.c_str());
@@ -211,3 +211,23 @@ extern "C" int av1r_debug_k3_check(const uint8_t* data, size_t len, long long* f
     if (units_total) *units_total = nu_total;
     return 0;
 }
+
+// Plan-level self test of the block-copy rule (CPU tests): two 64x64 units in one row, each one luma 64x64 block-copy record; the
+// vector points 64 samples to the left (forward == 0: the second unit copies from the first) or to the right (forward != 0: the
+// first unit would copy from the second, which does not exist yet).  Returns k3_plan_build's result.
+extern "C" int av1r_debug_k3_ibc_selftest(int forward) {
+    using namespace av1r;
+    TxRec tx[2];
+    memset(tx, 0, sizeof(tx));
+    for (int i = 0; i < 2; i++) {
+        tx[i].x4 = (uint16_t)(16 * i);
+        tx[i].txsz = TX_64X64;
+        tx[i].mode = (uint8_t)(i == (forward ? 0 : 1) ? (int)TXM_INTRABC : (int)DC_PRED);
+        tx[i].cfl_max_w4 = (uint16_t)(int16_t)(forward ? 64 * 8 : -64 * 8);
+    }
+    TxRec recs[2] = {tx[0], tx[1]};
+    uint32_t k3[2];
+    K3Unit units[4];
+    return k3_plan_build(tx, 2, 2, 1, 1, 0, 32, 16, recs, k3, units, 1);
+}
+

@@ -145,8 +145,8 @@ static bool alloc_frames(const DevFrameParams& fp, int count, std::vector<std::s
 
 // Layout of the per-frame work-list arena (same offsets on host staging and device).
 struct WorkLayout {
-    size_t recs, coefs, order, lf[3], lfblk, lftx[3], cdef_idx, skip_mi, lr[3], inter, itiles, obmc, warps, pal, k3order, k3units, total;
-    int n_lfblk, lf_device;
+    size_t recs, coefs, order, lf[3], lfblk, lftx[3], cdef_idx, skip_mi, lr[3], inter, itiles, obmc, warps, pal, k3order, k3units, k3upos, total;
+    int n_lfblk, lf_device, k3upos_on;
     int n_recs, n_coefs, n_order, n_order_small, n_inter, n_itiles, n_itiles_small, n_obmc, n_warps, n_k3, n_k3units;
 };
 
@@ -250,6 +250,9 @@ static void plan_layout(const FrameWork& fw, DevWork& dw) {
     const int units_cap = ((fw.fh.mi_cols + 15) >> 4) * ((fw.fh.mi_rows + 15) >> 4);
     L.n_k3units = n_k3 > 0 ? units_cap : 0;
     L.k3units = take(sizeof(K3Unit) * std::max(1, units_cap));
+    // frames with intra block copy: unit position -> table index, so that the kernel finds the units a block vector points into
+    L.k3upos_on = fw.fh.allow_intrabc && n_k3 > 0;
+    L.k3upos = L.k3upos_on ? take(sizeof(int32_t) * std::max(1, units_cap)) : 0;
     L.total = o;
 }
 
@@ -303,7 +306,8 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     if (!fw.pal.empty()) memcpy(h + L.pal, fw.pal.data(), fw.pal.size());
     // K3 plan (k3_plan.h): record order, unit table with neighbour dependencies, inter-intra blend links
     dw.lay.n_k3units = k3_plan_build(fw.tx.data(), L.n_recs, L.n_k3, dw.fp.subx, dw.fp.suby, dw.fp.sb128, dw.fp.mi_cols, dw.fp.mi_rows,
-                                     (TxRec*)(h + L.recs), (uint32_t*)(h + L.k3order), (K3Unit*)(h + L.k3units));
+                                     (TxRec*)(h + L.recs), (uint32_t*)(h + L.k3order), (K3Unit*)(h + L.k3units), L.k3upos_on ? 1 : 0,
+                                     L.k3upos_on ? (int32_t*)(h + L.k3upos) : nullptr);
 }
 
 // Pinned staging of one frame's work-lists, filled by the thread that parsed the frame (so the copy into pinned memory and the K3
@@ -607,6 +611,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     EP_ADD(10, t_h);
     t_h = EP_T();
     if (L.n_k3 > 0) {
+        if (L.n_k3units == -2) { err = "intra block copy vector points at samples that are not reconstructed yet"; return AV1R_EBITSTREAM; }
         if (L.n_k3units < 0) { err = "a 64x64 unit holds more intra records than the intra kernel supports"; return AV1R_ENOSYS; }
         IntraLaunch il;
         il.recs = d_recs;
@@ -638,6 +643,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         il.uprog = (unsigned long long*)s.sync.p;
         il.uflags = (int*)(s.sync.p + sizeof(unsigned long long) * (size_t)L.n_k3units);
         il.ticket = il.uflags + L.n_k3units;
+        il.upos = L.k3upos_on ? (const int32_t*)(d_arena + L.k3upos) : nullptr;
         il.stuck = (int*)k3_stuck.p;
         // Cell-level hand-over is the default: 1.6x lower frame latency and (since the wait loop got leaner) also the higher clip
         // rate with 16+ frames side by side (c2: 3220 vs 2960 frames/s).  AV1R_K3_PROGRESSIVE=1 selects the earlier adaptive policy
@@ -653,6 +659,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         il.progressive = k3_progressive == 1 ? !(k3_intra_run >= 4 && saturated) : (k3_progressive != 0);
         if (il.progressive && k3_ctas <= 0 && L.n_inter == 0) il.ctas = std::min(L.n_k3units, (il.ctas * 7 + 4) / 5);
+        // block-copy frames list their units in decode order: rows overlap only as far as the CTAs reach ahead in that order
+        if (L.k3upos_on && k3_ctas <= 0) il.ctas = std::min(L.n_k3units, std::max(il.ctas, 2 * ((fp.mi_cols + 15) >> 4)));
         il.frame = recon->pl;
         il.res = res;
         il.fp = fp;

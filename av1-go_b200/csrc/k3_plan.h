@@ -16,6 +16,21 @@ namespace av1r {
 
 inline bool k3_owns(const TxRec& r) { return r.mode != TXM_INTER || (r.flags & TXF_II); }
 
+// 64x64 luma units [ux0, ux1] x [uy0, uy1] the predictor of an intra-block-copy record reads (same arithmetic on the device)
+inline void k3_ibc_source_units(const TxRec& r, int subx, int suby, int mi_cols, int mi_rows, int& ux0, int& uy0, int& ux1, int& uy1) {
+    const int sx = r.plane ? subx : 0, sy = r.plane ? suby : 0;
+    const int dvx = (int16_t)r.cfl_max_w4, dvy = (int16_t)r.cfl_max_h4;       // 1/8 luma sample = 1/16 chroma sample at 4:2:0
+    const int x = r.x4 * 4, y = r.y4 * 4;
+    const int w = std::max(1, std::min((int)kTxW[r.txsz], ((mi_cols * 4) >> sx) - x)), h = std::max(1, std::min((int)kTxH[r.txsz], ((mi_rows * 4) >> sy) - y));
+    const int posx = (x << 4) + ((2 * dvx) >> sx), posy = (y << 4) + ((2 * dvy) >> sy);   // 1/16 sample, plane units
+    const int px0 = posx >> 4, py0 = posy >> 4;
+    const int us = r.plane ? 6 - sx : 6, vs = r.plane ? 6 - sy : 6;
+    ux0 = px0 >> us;
+    uy0 = py0 >> vs;
+    ux1 = (px0 + w - 1 + ((posx & 15) != 0)) >> us;     // a fractional position reads one more sample (second bilinear tap)
+    uy1 = (py0 + h - 1 + ((posy & 15) != 0)) >> vs;
+}
+
 // K3 order: records grouped by 64x64 luma unit, units in wavefront order.  Unit key = 4 * (sbx + 2 * sby) + seq with (sbx, sby)
 // the superblock and seq the unit's rank in decode order inside its superblock (0 for 64x64 superblocks; a 128x128 superblock
 // visits its four units in Z order, or 0,2,1,3 under a vertical split).  Every sample a record may read lies earlier in its own
@@ -26,8 +41,14 @@ inline bool k3_owns(const TxRec& r) { return r.mode != TXM_INTER || (r.flags & T
 //   recs[n_recs] : the staged copy (inter-intra residual records get the K3 position of their blend record in pal_off)
 //   k3[n_k3]     : out, record indices in K3 order;  units[]: out (capacity: one entry per 64x64 unit of the frame)
 // Returns the number of units, or -1 if a unit holds more records than the kernel's barrier array.
+// Frames that allow intra block copy (`raster` != 0) list their units in decode order instead: a block vector may point at any
+// unit decoded earlier (spec 6.10.25 allows sources up to five unit columns ahead per superblock row above, which the 2:1
+// wavefront order has not visited yet), and decode order is a topological order of those reads as well as of the neighbour
+// reads (prediction never crosses a tile).  `upos_out` (one entry per 64x64 unit of the frame, may be null) receives the table
+// index of every unit: the kernel finds the source units of a block vector through it.  Returns -2 if a block-copy record reads
+// a unit that is not listed before its own.
 inline int k3_plan_build(const TxRec* tx, int n_recs, int n_k3, int subx, int suby, int sb128, int mi_cols, int mi_rows, TxRec* recs,
-                         uint32_t* k3, K3Unit* units) {
+                         uint32_t* k3, K3Unit* units, int raster = 0, int32_t* upos_out = nullptr) {
     const int sx1 = subx, sy1 = suby;
     const int sbs = sb128 ? 1 : 0;
     const int UX = (mi_cols + 15) >> 4, UY = (mi_rows + 15) >> 4;
@@ -37,8 +58,8 @@ inline int k3_plan_build(const TxRec* tx, int n_recs, int n_k3, int subx, int su
         return std::min(uy, UY - 1) * UX + std::min(ux, UX - 1);
     };
     std::vector<int32_t> ukey((size_t)UX * UY, -1), upos((size_t)UX * UY, -1);
-    std::vector<uint32_t> cnt(4096 + 1, 0);
-    int last_sb = -1, seq = 0;
+    std::vector<uint32_t> cnt((size_t)std::max(4096, UX * UY) + 1, 0);
+    int last_sb = -1, seq = 0, rank = 0;
     for (int i = 0; i < n_recs; i++) {   // decode order: first appearance of a unit fixes its rank inside the superblock
         const TxRec& r = tx[i];
         if (!k3_owns(r)) continue;
@@ -48,7 +69,7 @@ inline int k3_plan_build(const TxRec* tx, int n_recs, int n_k3, int subx, int su
             const int sb = (uy >> sbs) * UX + (ux >> sbs);
             seq = sb == last_sb ? std::min(seq + 1, 3) : 0;
             last_sb = sb;
-            ukey[un] = std::min(4095, 4 * ((ux >> sbs) + 2 * (uy >> sbs)) + seq);
+            ukey[un] = raster ? rank++ : std::min(4095, 4 * ((ux >> sbs) + 2 * (uy >> sbs)) + seq);
         }
         cnt[ukey[un]]++;
     }
@@ -82,7 +103,7 @@ inline int k3_plan_build(const TxRec* tx, int n_recs, int n_k3, int subx, int su
         uint8_t nd = 0;
         for (uint32_t n = u.first; n < u.first + u.count; n++) {
             const TxRec& r = recs[k3[n]];
-            if (r.mode == TXM_INTER || r.mode == TXM_PALETTE) continue;
+            if (r.mode == TXM_INTER || r.mode == TXM_PALETTE || r.mode == TXM_INTRABC) continue;
             const int sh = r.plane ? 3 : 4;                       // unit size in 4-sample cells: 16 luma, 8 chroma (4:2:0)
             const int lx = r.x4 - (u.ux << sh), ly = r.y4 - (u.uy << sh);
             const int w4 = kTxW[r.txsz] >> 2, h4 = kTxH[r.txsz] >> 2, uw = 1 << sh;
@@ -111,6 +132,24 @@ inline int k3_plan_build(const TxRec* tx, int n_recs, int n_k3, int subx, int su
     int n_units = nu;
     for (int k = 0; k < nu; k++)
         if (units[k].count > (uint32_t)K3_UNIT_MAX_RECS) n_units = -1;   // cannot happen at 4:2:0 (<= 576 records per unit)
+    // intra block copy: every unit the source rectangle touches (one sample of margin for the chroma half-sample taps) must be
+    // listed before the record's own unit
+    for (int k = 0; k < nu && n_units >= 0; k++) {
+        const K3Unit& u = units[k];
+        for (uint32_t n = u.first; n < u.first + u.count; n++) {
+            const TxRec& r = recs[k3[n]];
+            if (r.mode != TXM_INTRABC) continue;
+            int ux0, uy0, ux1, uy1;
+            k3_ibc_source_units(r, subx, suby, mi_cols, mi_rows, ux0, uy0, ux1, uy1);
+            for (int yy = uy0; yy <= uy1; yy++)
+                for (int xx = ux0; xx <= ux1; xx++) {
+                    if (xx < 0 || yy < 0 || xx >= UX || yy >= UY) continue;   // (outside the frame: the fetch clamps)
+                    const int pos = upos[(size_t)yy * UX + xx];
+                    if (pos < 0 || pos >= k) n_units = -2;
+                }
+        }
+    }
+    if (upos_out) memcpy(upos_out, upos.data(), sizeof(int32_t) * (size_t)UX * UY);
     // explicit dependency of inter-intra residual records on their blend record (position in K3 order)
     uint32_t blend_pos[3] = {0, 0, 0};
     for (int n = 0; n < n_k3; n++) {
@@ -148,6 +187,16 @@ inline std::string k3_plan_check(const TxRec* tx, int n_recs, int n_k3, int subx
             prev = idx;
             const int sx = r.plane ? subx : 0, sy = r.plane ? suby : 0;
             if ((((r.x4 * 4) << sx) >> 6) != U.ux || (((r.y4 * 4) << sy) >> 6) != U.uy) return fail("record outside its unit", u, (int)idx);
+            if (r.mode == TXM_INTRABC) {   // every source unit of a block vector comes earlier in the table
+                int ux0, uy0, ux1, uy1;
+                k3_ibc_source_units(r, subx, suby, mi_cols, mi_rows, ux0, uy0, ux1, uy1);
+                for (int yy = uy0; yy <= uy1; yy++)
+                    for (int xx = ux0; xx <= ux1; xx++) {
+                        if (xx < 0 || yy < 0 || xx >= UX || yy >= UY) continue;
+                        const int pos = upos[(size_t)yy * UX + xx];
+                        if (pos < 0 || pos >= u) return fail("block copy reads a unit that is not finished before its own", u, (int)idx);
+                    }
+            }
             if ((r.flags & TXF_II) && r.mode == TXM_INTER) {   // residual of an inter-intra block: its blend record is earlier in the same unit
                 if (r.pal_off < U.first || r.pal_off >= n) return fail("inter-intra residual does not follow its blend record", u, (int)idx);
                 const TxRec& b = recs[k3[r.pal_off]];
@@ -169,7 +218,7 @@ inline std::string k3_plan_check(const TxRec* tx, int n_recs, int n_k3, int subx
         // every neighbour a record of the unit can read (edge-availability flags) that is listed earlier must be a dependency
         for (uint32_t n = U.first; n < U.first + U.count; n++) {
             const TxRec& r = recs[k3[n]];
-            if (r.mode == TXM_INTER || r.mode == TXM_PALETTE) continue;
+            if (r.mode == TXM_INTER || r.mode == TXM_PALETTE || r.mode == TXM_INTRABC) continue;
             const int sh = r.plane ? 3 : 4, uw = 1 << sh;
             const int lx = r.x4 - (U.ux << sh), ly = r.y4 - (U.uy << sh);
             const int w4 = kTxW[r.txsz] >> 2, h4 = kTxH[r.txsz] >> 2;

@@ -267,7 +267,7 @@ __device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int
 
 template <typename T>
 __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrameParams& fp, WarpScratch& sm, int lane,
-                            const uint8_t* wedge_master, const uint8_t* pal) {
+                            const uint8_t* wedge_master, const uint8_t* pal, const DevPlanes& frame) {
     const int plane = r.plane;
     const int lw = tx_lw(r.txsz), lh = tx_lh(r.txsz);
     const int w = 1 << lw, h = 1 << lh;
@@ -285,8 +285,11 @@ __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrame
     const bool ii = (r.flags & TXF_II) != 0;
     const int ii_pk = (uint16_t)r.cfl_alpha;
     const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
+    // luma is reconstructed in full also beyond the coded frame edge (the canvas holds the whole unit; the write-back clips):
+    // chroma-from-luma of a block that straddles the edge reads those samples (spec MaxLumaW / MaxLumaH)
+    const int xw = plane ? xe : w, yw = plane ? ye : h;
     auto emit = [&](int i, int j, int v) {
-        if (i < ye && j < xe) {
+        if (i < yw && j < xw) {
             if (ii) {   // blend the intra predictor over the inter predictor K2 left in the frame
                 const int m = ii_mask(ii_pk, wedge_master, i, j, w, h, psx, psy);
                 v = (m * v + (64 - m) * (int)out[i * opitch + j] + 32) >> 6;
@@ -305,6 +308,28 @@ __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrame
                     out[i * opitch + j] = (T)min(max(v, 0), pixmax);
                 }
             }
+        return;
+    }
+    if (r.mode == TXM_INTRABC) {
+        // spec 7.11.3.2 - 7.11.3.4 with use_intrabc: the reference is this frame (no filter runs on such frames), displaced by the
+        // block vector; bilinear taps at 1/16 sample (the chroma of an odd luma vector sits on a half sample), rounding 3 then 11,
+        // positions clamped to the coded plane.  The source units are complete and released (the caller waited for their flags);
+        // the loads bypass L1.
+        const int dvx = (int16_t)r.cfl_max_w4, dvy = (int16_t)r.cfl_max_h4;
+        const int posx = (x << 4) + ((2 * dvx) >> psx), posy = (y << 4) + ((2 * dvy) >> psy);
+        const int ix = posx >> 4, fx = posx & 15, iy = posy >> 4, fy = posy & 15;
+        const uint8_t* fb = frame.p[plane];
+        const uint32_t pitch = frame.pitch[plane];
+        for (int idx = lane; idx < w * h; idx += 32) {
+            const int i = idx >> lw, j = idx & (w - 1);
+            const int xa = min(max(ix + j, 0), max_x), xb = min(max(ix + j + 1, 0), max_x);
+            const int ya = min(max(iy + i, 0), max_y), yb = min(max(iy + i + 1, 0), max_y);
+            const T* r0 = reinterpret_cast<const T*>(fb + (size_t)ya * pitch);
+            const T* r1 = reinterpret_cast<const T*>(fb + (size_t)yb * pitch);
+            const int t0 = ((128 - 8 * fx) * (int)ld_cell<T>(r0 + xa) + 8 * fx * (int)ld_cell<T>(r0 + xb) + 4) >> 3;
+            const int t1 = ((128 - 8 * fx) * (int)ld_cell<T>(r1 + xa) + 8 * fx * (int)ld_cell<T>(r1 + xb) + 4) >> 3;
+            emit(i, j, min(max(((128 - 8 * fy) * t0 + 8 * fy * t1 + 1024) >> 11, 0), pixmax));
+        }
         return;
     }
     if (r.mode == TXM_PALETTE) {   // spec 7.11.4; entry layout documented at TileDecoder::palette_tokens
@@ -802,6 +827,37 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             lap(8, lane == 0);   // record fetch
             if (r.mode == TXM_INTER) {
                 if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck, L.wait_ns);   // residual of an inter-intra block: after its blend
+            } else if (r.mode == TXM_INTRABC) {
+                // block copy: wait until every unit the source rectangle touches is complete in the frame (whole-unit flags; the
+                // plan guarantees they come earlier in the table, so this cannot wait on a unit that waits on us)
+                if (L.upos) {
+                    const int plane = r.plane;
+                    const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
+                    const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
+                    const int bx = r.x4 * 4, by = r.y4 * 4;
+                    const int bw = max(1, min(1 << tx_lw(r.txsz), pcw - bx)), bh = max(1, min(1 << tx_lh(r.txsz), pch - by));
+                    const int posx = (bx << 4) + ((2 * (int)(int16_t)r.cfl_max_w4) >> psx), posy = (by << 4) + ((2 * (int)(int16_t)r.cfl_max_h4) >> psy);
+                    const int us = 6 - psx, vs = 6 - psy;
+                    const int sx0 = (posx >> 4) >> us, sy0 = (posy >> 4) >> vs;
+                    const int sx1 = ((posx >> 4) + bw - 1 + ((posx & 15) != 0)) >> us, sy1 = ((posy >> 4) + bh - 1 + ((posy & 15) != 0)) >> vs;
+                    const int nx = sx1 - sx0 + 1, ny = sy1 - sy0 + 1;
+                    const int UX = (fp.mi_cols + 15) >> 4, UY = (fp.mi_rows + 15) >> 4;
+                    if (lane < nx * ny && lane < 32) {
+                        const int xx = sx0 + lane % nx, yy = sy0 + lane / nx;
+                        if (xx >= 0 && yy >= 0 && xx < UX && yy < UY) {
+                            const int d = __ldg(L.upos + yy * UX + xx);
+                            if (d >= 0 && d < u) {
+                                int spins = 0;
+                                while (ld_relaxed(L.uflags + d) == 0) {
+                                    __nanosleep(200);
+                                    if (++spins > (1 << 24)) { *L.stuck = 4; break; }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    fence_acquire_gpu();
+                }
             } else if (r.mode != TXM_PALETTE) {
                 const int plane = r.plane;
                 const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
@@ -928,7 +984,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             // the waits acquire (mbarrier test/try_wait) what the owners released with their arrive; __syncwarp orders the lanes
             __syncwarp();
             lap(9, lane == 0);   // dependency wait
-            intra_block<T>(r, uc, fp, sm, lane, L.wedge_master, L.pal);
+            intra_block<T>(r, uc, fp, sm, lane, L.wedge_master, L.pal, L.frame);
             __syncwarp();        // all lanes' samples are in the canvas before lane 0 releases the record's barrier
             if (lane == 0) mbar_arrive(rbar + 8u * (uint32_t)k);
             if (L.progressive) {

@@ -21,6 +21,7 @@ struct IntraLaunch {            // passed by value
     int poll_ns_max;            // cap of the back-off between polls of a neighbour unit's progress word
     unsigned long long* uprog;  // device, n_units words, zeroed before launch: finished border cells of every unit (bit layout in intra.cu)
     int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
+    const int32_t* upos;        // device, one entry per 64x64 unit of the frame: its table index (frames with intra block copy; else null)
     int* ticket;                // device, one int, zeroed before launch
     int* stuck;                 // device, one int shared by every frame of the engine: raised (never cleared by the kernel) when a wait made no progress
     DevPlanes frame;

@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(ITX_WARPS * 32) itx_kernel(const TxRec* __rest
     __syncwarp();
     int16_t* dst = res_ptr(res, plane, r.x4 * 4, r.y4 * 4);   // a transform block never straddles a unit
     const int dpe = 1 << res.tw_log2[plane];
-    const int cols_valid = min(w, fp.cw[plane] - r.x4 * 4), rows_valid = min(h, fp.ch[plane] - r.y4 * 4);
+    // luma blocks are written in full also where they straddle the coded frame edge: chroma-from-luma averages the reconstructed
+    // luma of the whole transform block (spec MaxLumaW / MaxLumaH), and the residual tile of the unit has room for it
+    const int cols_valid = plane ? min(w, fp.cw[plane] - r.x4 * 4) : w, rows_valid = plane ? min(h, fp.ch[plane] - r.y4 * 4) : h;
     if (r.txtp == WHT_WHT) {
         if (lane < 4) {
             int32_t t[4];
@@ -220,7 +222,9 @@ __global__ void __launch_bounds__(ITXS_HALF_WARPS * 16) itx_small_kernel(const T
     __syncwarp(mask);
     int16_t* dst = res_ptr(res, plane, r.x4 * 4, r.y4 * 4);
     const int dpe = 1 << res.tw_log2[plane];
-    const int cols_valid = min(w, fp.cw[plane] - r.x4 * 4), rows_valid = min(h, fp.ch[plane] - r.y4 * 4);
+    // luma blocks are written in full also where they straddle the coded frame edge: chroma-from-luma averages the reconstructed
+    // luma of the whole transform block (spec MaxLumaW / MaxLumaH), and the residual tile of the unit has room for it
+    const int cols_valid = plane ? min(w, fp.cw[plane] - r.x4 * 4) : w, rows_valid = plane ? min(h, fp.ch[plane] - r.y4 * 4) : h;
     if (r.txtp == WHT_WHT) {
         if (lane < 4) {
             int32_t t[4];

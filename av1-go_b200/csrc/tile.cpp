@@ -454,7 +454,7 @@ bool TileDecoder::decode_block(int r, int c, int bsize) {
             memset(&fw.seg_ids[o], b->segment_id, n);
         }
     }
-    if (b->is_inter) emit_inter_block();
+    if (b->is_inter && !b->use_intrabc) emit_inter_block();   // (intra block copy is predicted by the wavefront kernel, record by record)
     residual();
     return fail_code == 0;
 }
@@ -475,7 +475,17 @@ void TileDecoder::intra_frame_mode_info() {
         b->use_intrabc = (uint8_t)ms.symbol(cdf.intrabc, 2);
     }
     if (b->use_intrabc) {
-        fail(AV1R_ENOSYS, "intra block copy is not supported yet");
+        // spec 5.11.7: the block is coded like a single-reference NEWMV inter block whose reference is the frame being
+        // decoded (before any filter); bilinear interpolation, no palette, DC_PRED for the neighbours' contexts
+        b->is_inter = 1;
+        b->y_mode = DC_PRED;
+        b->uv_mode = DC_PRED;
+        b->motion_mode = 0;
+        b->compound_type = COMPOUND_AVERAGE;
+        b->interp_filter[0] = b->interp_filter[1] = INTERP_BILINEAR;
+        to.tool_hist[TOOL_INTRABC]++;
+        find_mv_stack(0);
+        assign_dv();
         return;
     }
     b->is_inter = 0;
@@ -1038,6 +1048,13 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
             rec.mode = b->uv_mode;
             rec.angle_delta = b->angle_uv;
         }
+    } else if (b->use_intrabc) {
+        // every transform block of an intra-block-copy block is its own predict + reconstruct record of the wavefront kernel:
+        // the predictor is a pure function of the sample position and the block vector (chroma uses the block's own vector,
+        // also for sub-8x8 groups: spec 7.11.3.1 finds RefFrame[0] == INTRA_FRAME there)
+        rec.mode = TXM_INTRABC;
+        rec.cfl_max_w4 = (uint16_t)b->mv[0].col;
+        rec.cfl_max_h4 = (uint16_t)b->mv[0].row;
     } else {
         rec.mode = TXM_INTER;
     }
@@ -1049,7 +1066,7 @@ void TileDecoder::transform_block(int plane, int base_x, int base_y, int txsz, i
     rec.eob = (uint16_t)eob;
     rec.ntok = (uint16_t)(to.coefs.size() - rec.coef_off);
     if (b->is_inter && b->interintra) rec.flags |= TXF_II;
-    if (!b->is_inter || eob > 0) push_record(rec, (start_x << sx) >> 6, (start_y << sy) >> 6);
+    if (!b->is_inter || eob > 0 || b->use_intrabc) push_record(rec, (start_x << sx) >> 6, (start_y << sy) >> 6);
     if (eob > 0) to.coded_samples += (uint64_t)kTxW[txsz] * kTxH[txsz];
     // LoopfilterTxSizes + BlockDecoded
     const int pw4 = fw.plane_w4(plane), ph4 = fw.plane_h4(plane);

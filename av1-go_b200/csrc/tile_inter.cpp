@@ -407,6 +407,52 @@ void TileDecoder::assign_mv(int is_compound) {
     if (!is_compound) b->mv[1] = Mv{0, 0};
 }
 
+// Block vector of an intra-block-copy block (spec 5.11.26 assign_mv with use_intrabc, MvCtx = MV_CONTEXTS_INTRABC): predicted from
+// the first non-zero entry of the stack, else from a default one superblock up (or a superblock + 256 samples to the left on the
+// tile's first superblock row); the difference is coded like a NEWMV at integer precision (force_integer_mv is 1 in intra frames).
+void TileDecoder::assign_dv() {
+    Mv pred = ref_stack[0][0];
+    if (pred.row == 0 && pred.col == 0) pred = ref_stack[1][0];
+    if (pred.row == 0 && pred.col == 0) {
+        const int sb4 = seq.use_128x128_superblock ? 32 : 16;
+        if (mi_row - sb4 < mi_row_start) {
+            pred.row = 0;
+            pred.col = (int16_t)(-(sb4 * 4 + 256) * 8);
+        } else {
+            pred.row = (int16_t)(-(sb4 * 4 * 8));
+            pred.col = 0;
+        }
+    }
+    int diff[2] = {0, 0};
+    const int joint = ms.symbol(cdf.dv_joints, 4);
+    auto comp = [&](int c) {
+        const int sign = ms.symbol(c ? cdf.dv_c1_sign : cdf.dv_c0_sign, 2);
+        const int mv_class = ms.symbol(c ? cdf.dv_c1_classes : cdf.dv_c0_classes, 11);
+        int mag;
+        if (mv_class == 0) {
+            const int class0_bit = ms.symbol(c ? cdf.dv_c1_class0 : cdf.dv_c0_class0, 2);
+            mag = ((class0_bit << 3) | (3 << 1) | 1) + 1;
+        } else {
+            int d = 0;
+            for (int i = 0; i < mv_class; i++) d |= ms.symbol(c ? cdf.dv_c1_bits[i] : cdf.dv_c0_bits[i], 2) << i;
+            mag = (2 << (mv_class + 2)) + ((d << 3) | (3 << 1) | 1) + 1;
+        }
+        return sign ? -mag : mag;
+    };
+    if (joint == MV_JOINT_HZVNZ || joint == MV_JOINT_HNZVNZ) diff[0] = comp(0);
+    if (joint == MV_JOINT_HNZVZ || joint == MV_JOINT_HNZVNZ) diff[1] = comp(1);
+    b->mv[0].row = (int16_t)(pred.row + diff[0]);
+    b->mv[0].col = (int16_t)(pred.col + diff[1]);
+    b->mv[1] = Mv{0, 0};
+    // conformance (spec 6.10.25 / 7.11.3.2): whole-sample vector, source rectangle inside the tile.  That the source has been
+    // reconstructed already is checked where the wavefront kernel's plan is built (k3_plan.h): a vector into the future must be
+    // an error, not a wait that never ends.
+    const int sx0 = mi_col * 4 + (b->mv[0].col >> 3), sy0 = mi_row * 4 + (b->mv[0].row >> 3);
+    if ((b->mv[0].row & 7) || (b->mv[0].col & 7) || sx0 < mi_col_start * 4 || sy0 < mi_row_start * 4 ||
+        sx0 + bw4 * 4 > mi_col_end * 4 || sy0 + bh4 * 4 > mi_row_end * 4)
+        fail(AV1R_EBITSTREAM, "intra block copy vector points outside the tile");
+}
+
 int TileDecoder::read_mv_component(int comp) {
     uint16_t* sign_c = comp ? cdf.mv_c1_sign : cdf.mv_c0_sign;
     uint16_t* classes_c = comp ? cdf.mv_c1_classes : cdf.mv_c0_classes;

@@ -73,6 +73,8 @@ enum : uint8_t {
     TXM_CFL = 13,           // DC_PRED followed by chroma-from-luma
     TXM_PALETTE = 14,
     TXM_FILTER_INTRA = 15,
+    TXM_INTRABC = 16,       // intra block copy: predictor = the frame being decoded displaced by the block vector, which
+                            // cfl_max_w4 / cfl_max_h4 hold (column, row as int16, 1/8 luma sample; spec 7.11.3.2 with use_intrabc)
     TXM_INTER = 255,        // no intra prediction: residual is added to the inter predictor
 };
 enum : uint8_t {

@@ -144,6 +144,9 @@ int av1r_parse_buffer(const uint8_t* data, size_t len, int host_threads, int til
 /* Host-only check of the intra kernel's plan (record order, 64x64 unit table, neighbour dependencies) for every frame of a
  * container: 0 or AV1R_EINVAL with the first violated invariant in msg.  Test / diagnosis entry point; touches no GPU. */
 int av1r_debug_k3_check(const uint8_t* data, size_t len, long long* frames, long long* units_total, char* msg, size_t cap);
+/* Host-only self test of the intra-block-copy rule of that plan: a block vector into a unit that is decoded earlier (forward = 0)
+ * is accepted (returns the unit count), one into a unit that comes later (forward != 0) is rejected with -2. */
+int av1r_debug_k3_ibc_selftest(int forward);
 int av1r_probe_file(const char* path, av1r_stream_info* out);
 int av1r_probe_buffer(const uint8_t* data, size_t len, av1r_stream_info* out);
 

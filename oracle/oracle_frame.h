@@ -12,11 +12,13 @@ namespace orc {
 struct Plane {
     std::vector<uint16_t> d;
     int w = 0, h = 0, stride = 0;   // coded size (multiple of 8 luma samples)
+    // 64 samples of margin to the right and below: a transform block that straddles the coded frame edge is reconstructed in
+    // full (spec 7.11.2 / 7.13.3 write the whole block), and chroma-from-luma reads those luma samples (MaxLumaW / MaxLumaH)
     void alloc(int w_, int h_) {
         w = w_;
         h = h_;
-        stride = w_;
-        d.assign((size_t)w_ * h_, 0);
+        stride = w_ + 64;
+        d.assign((size_t)stride * (h_ + 64), 0);
     }
     uint16_t& at(int x, int y) { return d[(size_t)y * stride + x]; }
     const uint16_t& at(int x, int y) const { return d[(size_t)y * stride + x]; }

@@ -341,7 +341,9 @@ void reconstruct_frame(const FrameWork& fw, Frame& f, const Frame* const refs[8]
         Plane& pl = f.p[r.plane];
         const int w = kTxW[r.txsz], h = kTxH[r.txsz];
         const int x = r.x4 * 4, y = r.y4 * 4;
-        const int xe = std::min(x + w, g.cw[r.plane]), ye = std::min(y + h, g.ch[r.plane]);
+        // the whole transform block is reconstructed, also the part beyond the coded frame edge (it lands in the planes' margin):
+        // chroma-from-luma of a block that straddles the edge averages those luma samples
+        const int xe = x + w, ye = y + h;
         if (r.mode != TXM_INTER && (r.flags & TXF_II)) {
             predict_intra_block(pl, g, r, r.plane, pred);
             interintra_blend(f, r, pred);
@@ -355,6 +357,28 @@ void reconstruct_frame(const FrameWork& fw, Frame& f, const Frame* const refs[8]
             const int ox = hdr[8], oy = hdr[9], stride = hdr[10];
             for (int i = 0; i < h; i++)
                 for (int j = 0; j < w; j++) pred[i * w + j] = hdr[map[(size_t)(y - oy + i) * stride + (x - ox + j)]];
+            for (int yy = y; yy < ye; yy++)
+                for (int xx = x; xx < xe; xx++) pl.at(xx, yy) = (uint16_t)pred[(yy - y) * w + (xx - x)];
+        } else if (r.mode == TXM_INTRABC) {
+            // spec 7.11.3.2 - 7.11.3.4 with use_intrabc: the reference is the frame being decoded (no filter has run), bilinear
+            // taps at 1/16 sample (chroma of an odd luma vector is a half-sample position), rounding 3 then 11, positions clamped
+            // to the coded plane.  Decode order guarantees the source samples are final.
+            const int sx = r.plane ? g.subx : 0, sy = r.plane ? g.suby : 0;
+            const int dvx = (int16_t)r.cfl_max_w4, dvy = (int16_t)r.cfl_max_h4;
+            const int posx = (x << 4) + ((2 * dvx) >> sx), posy = (y << 4) + ((2 * dvy) >> sy);
+            const int ix = posx >> 4, fx = posx & 15, iy = posy >> 4, fy = posy & 15;
+            const int lastx = g.cw[r.plane] - 1, lasty = g.ch[r.plane] - 1;
+            const int round0 = g.bd == 12 ? 5 : 3, round1 = g.bd == 12 ? 9 : 11;
+            for (int i = 0; i < ye - y; i++)
+                for (int j = 0; j < xe - x; j++) {
+                    int t[2];
+                    for (int k = 0; k < 2; k++) {
+                        const int yy = clip3(0, lasty, iy + i + k);
+                        const int a = pl.at(clip3(0, lastx, ix + j), yy), b = pl.at(clip3(0, lastx, ix + j + 1), yy);
+                        t[k] = round2((128 - 8 * fx) * a + 8 * fx * b, round0);
+                    }
+                    pred[i * w + j] = clip3(0, pixmax, round2((128 - 8 * fy) * t[0] + 8 * fy * t[1], round1));
+                }
             for (int yy = y; yy < ye; yy++)
                 for (int xx = x; xx < xe; xx++) pl.at(xx, yy) = (uint16_t)pred[(yy - y) * w + (xx - x)];
         } else if (r.mode != TXM_INTER) {

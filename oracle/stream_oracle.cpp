@@ -78,7 +78,8 @@ static std::shared_ptr<Frame> grain(const Stream& s, const std::shared_ptr<Frame
         for (int p = 0; p < 3; p++) {
             i8[p].resize((size_t)g.cw[p] * g.ch[p]);
             o8[p].resize(i8[p].size());
-            for (size_t k = 0; k < i8[p].size(); k++) i8[p][k] = (uint8_t)in->p[p].d[k];
+            for (int y = 0; y < g.ch[p]; y++)
+                for (int x = 0; x < g.cw[p]; x++) i8[p][(size_t)y * g.cw[p] + x] = (uint8_t)in->p[p].at(x, y);
             ip[p] = i8[p].data();
             op[p] = o8[p].data();
             is[p] = os[p] = g.cw[p];

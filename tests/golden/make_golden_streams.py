@@ -32,6 +32,14 @@ CASES = {
     # monochrome (cfg[52] = monochrome): luma only, one MD5 per frame
     "intra_8b_mono_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 0, 52: 1}),
     "intra_8b_qm_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30", "enable-qm": "1", "qm-min": "2", "qm-max": "10"}, {14: 0, 48: 0}),
+    # screen content (tune-content=screen on a source of flat colours and recurring glyphs): palette mode, and intra block copy (K3:
+    # the predictor is the frame being decoded displaced by a block vector; libaom only picks it with CDEF off or at low cpu-used).
+    # The 322x182 case also has chroma-from-luma blocks whose luma transform block straddles the coded frame edge.
+    "intra_8b_palette_320x192": ("screen", 320, 192, 8, 2, {"cpu-used": "3", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "0", "enable-restoration": "0"}, {14: 0, 48: 0}),
+    "intra_8b_intrabc_320x192": ("screen", 320, 192, 8, 2, {"cpu-used": "2", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0", "enable-cdef": "0"}, {14: 0, 48: 0}),
+    "intra_10b_intrabc_328x200": ("screen", 328, 200, 10, 2, {"cpu-used": "1", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0", "enable-cdef": "0"}, {14: 0, 48: 0}),
+    "intra_8b_intrabc_sb128_456x264": ("screen", 456, 264, 8, 2, {"cpu-used": "2", "cq-level": "20", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0", "enable-cdef": "0", "sb-size": "128"}, {14: 0, 48: 0}),
+    "intra_8b_intrabc_edge_322x182": ("screen", 322, 182, 8, 2, {"cpu-used": "2", "cq-level": "50", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0", "enable-cdef": "0"}, {14: 0, 48: 0}),
 }
 
 # inter streams (index_inter.json): cfg[14] = lag_in_frames, cfg[48] = kf_max_dist.  The low cpu-used cases make libaom use
@@ -53,6 +61,9 @@ INTER_CASES = {
     "inter_8b_refscale_352x288": ("panzoom", 352, 288, 8, 10, {"cpu-used": "3", "cq-level": "34"}, {14: 4, 48: 9999, 16: 1, 17: 12, 18: 10}),
     "inter_10b_refscale_208x144": ("panzoom", 208, 144, 10, 8, {"cpu-used": "2", "cq-level": "30"}, {14: 4, 48: 9999, 16: 1, 17: 14, 18: 9}),
     "inter_8b_superres_inter_352x288": ("panzoom", 352, 288, 8, 10, {"cpu-used": "3", "cq-level": "34"}, {14: 4, 48: 9999, 19: 1, 20: 12, 21: 9}),
+    # screen content with inter frames: block-copy + palette key frame, then integer motion vectors (force_integer_mv) and palette
+    # blocks inside inter frames
+    "inter_8b_screen_352x288": ("screen", 352, 288, 8, 6, {"cpu-used": "2", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0", "enable-cdef": "0"}, {14: 4, 48: 9999}),
     "inter_10b_mono_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36"}, {14: 4, 48: 9999, 52: 1}),
     "inter_10b_qm_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36", "enable-qm": "1", "qm-min": "0", "qm-max": "15"}, {14: 4, 48: 9999}),
 }

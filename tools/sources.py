@@ -189,3 +189,43 @@ def occluders(w, h, n, bpc=8, seed=3, n_obj=14):
 
 
 SOURCES["occluders"] = occluders
+
+
+def screen_text(w, h, n, bpc=8, seed=5):
+    """Screen content: a few flat colours, rows of small glyphs drawn from a fixed font of random 5x7 bitmaps (so the same shapes
+    recur all over the frame: what palette mode and intra block copy are made for), window frames, a scrolling text pane."""
+    rng = np.random.default_rng(seed)
+    font = rng.integers(0, 2, size=(26, 7, 5)).astype(np.uint8)
+    font[:, :, 0] |= font[:, :, 4] & font[:, :, 2]
+    cols = np.array([[235, 128, 128], [16, 128, 128], [81, 90, 240], [145, 54, 34], [41, 240, 110], [180, 100, 160]], np.float32)
+    lines = [rng.integers(0, 26, size=w // 6 + 2) for _ in range(h // 9 + n + 4)]
+    for k in range(3, len(lines), 3):
+        lines[k] = lines[k - 3].copy()      # repeated lines: long exact matches for block copy
+    for t in range(n):
+        idx = np.zeros((h, w), np.int32)    # colour index per sample
+        pane_x0 = w // 3
+        idx[:, :pane_x0] = 5
+        idx[:, pane_x0:pane_x0 + 2] = 1
+        idx[:12, :] = 2                      # title bar
+        for li in range((h - 14) // 9):
+            y0 = 14 + li * 9
+            txt = lines[li + t]              # the pane scrolls one text line per frame
+            for ci in range((w - pane_x0 - 6) // 6):
+                g = font[txt[ci]]
+                x0 = pane_x0 + 4 + ci * 6
+                blk = idx[y0:y0 + 7, x0:x0 + 5]
+                blk[g[:blk.shape[0], :blk.shape[1]] > 0] = 1 if (li + t) % 5 else 3
+            # static side bar with icons
+            if li % 3 == 0:
+                g = np.kron(font[(li // 3) % 26], np.ones((1, 1), np.uint8))
+                for rep in range(max(1, (pane_x0 - 8) // 12)):
+                    x0 = 4 + rep * 12
+                    blk = idx[y0:y0 + 7, x0:x0 + 5]
+                    blk[g[:blk.shape[0], :blk.shape[1]] > 0] = 4
+        y = cols[idx, 0]
+        u = cols[idx, 1]
+        v = cols[idx, 2]
+        yield _to420(y, u, v, bpc)
+
+
+SOURCES["screen"] = screen_text
