@@ -704,16 +704,20 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     EP_ADD(12, t_h);
     t_h = EP_T();
     if (dw.cdef_on && (cfg.inloop_filters & 2)) {
+        auto t_g = EP_T();
         auto dst = get_frame(fp);
         if (!dst) return AV1R_ENOMEM;
         s.hold.push_back(dst);
+        if (getenv("AV1R_SLOWDBG")) { double us = std::chrono::duration<double, std::micro>(EP_T() - t_g).count(); if (us > 100) fprintf(stderr, "slow get_frame(cdef) %.0f us pool %zu\n", us, pool.size()); }
         CdefLaunch cl;
         cl.src = cur->pl;
         cl.dst = dst->pl;
         cl.cdef_idx = (const int8_t*)(d_arena + L.cdef_idx);
         cl.skip_mi = d_arena + L.skip_mi;
         cl.fp = fp;
+        t_g = EP_T();
         CK(launch_cdef(cl, st));
+        if (getenv("AV1R_SLOWDBG")) { double us = std::chrono::duration<double, std::micro>(EP_T() - t_g).count(); if (us > 100) fprintf(stderr, "slow launch_cdef %.0f us\n", us); }
         if (tm) tm->end(AV1R_ST_CDEF, 1, st);
         cur = dst;
     }
@@ -758,9 +762,11 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         cur = up;
     }
     if (dw.lr_on && (cfg.inloop_filters & 4)) {
+        auto t_g = EP_T();
         auto dst = get_frame(fpu);
         if (!dst) return AV1R_ENOMEM;
         s.hold.push_back(dst);
+        if (getenv("AV1R_SLOWDBG")) { double us = std::chrono::duration<double, std::micro>(EP_T() - t_g).count(); if (us > 100) fprintf(stderr, "slow get_frame(lr) %.0f us pool %zu\n", us, pool.size()); }
         LrLaunch ll;
         ll.cdef = cur->pl;
         ll.deblocked = deblocked->pl;
@@ -773,7 +779,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             ll.unit_cols[p] = dw.lr_cols[p];
         }
         ll.fp = fpu;
+        t_g = EP_T();
         CK(launch_lr(ll, st));
+        if (getenv("AV1R_SLOWDBG")) { double us = std::chrono::duration<double, std::micro>(EP_T() - t_g).count(); if (us > 100) fprintf(stderr, "slow launch_lr %.0f us\n", us); }
         if (tm) tm->end(AV1R_ST_LR, 1, st);
         cur = dst;
     }

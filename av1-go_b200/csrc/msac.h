@@ -28,9 +28,11 @@ struct Msac {
         update = !disable_cdf_update;
         refill();
     }
-    inline void refill() {
+    // (forced inline, and the rare tail path works on a copy: a decoder held in a local variable never has its address taken, so
+    // its window / range / count stay in registers across the byte and vector stores of the coefficient loop)
+    __attribute__((always_inline)) inline void refill() {
         int s = 64 - 9 - (cnt + 15);
-        if (s >= 0 && end - bptr >= 8) {
+        if (__builtin_expect(s >= 0 && end - bptr >= 8, 1)) {
             // whole bytes that fit below the window: one big-endian 64-bit load instead of a byte loop
             uint64_t v;
             __builtin_memcpy(&v, bptr, 8);
@@ -41,6 +43,11 @@ struct Msac {
             bptr += n;
             return;
         }
+        Msac t = *this;
+        t.refill_tail(s);
+        *this = t;
+    }
+    __attribute__((noinline)) void refill_tail(int s) {
         for (; s >= 0 && bptr < end; s -= 8, bptr++) {
             dif ^= (uint64_t)bptr[0] << s;
             cnt += 8;
@@ -106,9 +113,10 @@ struct Msac {
         // lanes with v <= window (unsigned): the first one is the symbol (lane n - 1 holds 0, so there always is one)
         const __m128i le = _mm_cmpeq_epi16(_mm_subs_epu16(v, _mm_set1_epi16((short)v16)), _mm_setzero_si128());
         const int s = __builtin_ctz((unsigned)_mm_movemask_epi8(le) | 0x100u) >> 1;
-        alignas(16) uint16_t t[8];
-        _mm_storel_epi64(reinterpret_cast<__m128i*>(t), v);
-        const uint32_t vv = t[s], u = s ? t[s - 1] : r;
+        // lanes s and s - 1 (lane -1 = the current range) by shifts of the 64-bit lane image: no store-to-load round trip
+        const uint64_t vq = (uint64_t)_mm_cvtsi128_si64(v);
+        const uint32_t vv = (uint32_t)(vq >> (16 * s)) & 0xffffu;
+        const uint32_t u = (uint32_t)((((vq << 16) | r) >> (16 * s)) & 0xffffu);
         normalize(dif - ((uint64_t)vv << 48), u - vv);
         if (update) {
             const int cnt_ = c[n];

@@ -123,6 +123,18 @@ int StreamParser::begin_frame(const FrameHdr& fh) {
     cur_fh_ = fh;
     tiles_done_ = 0;
     have_frame_ = true;
+    if (getenv("AV1R_DEP_TRACE")) {   // decode-order dependency trace (tools/dep_trace.py): which earlier frames this one needs
+        static thread_local int slot_no[8], frame_no = 0;
+        if (fh.frame_type == 0 && fh.show_frame) frame_no = 0;
+        fprintf(stderr, "dep frame %d type %d show %d tiles %dx%d primary %d refs", frame_no, fh.frame_type, fh.show_frame, fh.tile_cols, fh.tile_rows,
+                fh.primary_ref_frame == PRIMARY_REF_NONE ? -1 : slot_no[fh.ref_frame_idx[fh.primary_ref_frame]]);
+        if (!fh.frame_is_intra)
+            for (int i = 0; i < 7; i++) fprintf(stderr, " %d", slot_no[fh.ref_frame_idx[i]]);
+        fprintf(stderr, " mfmv %d endcdf %d\n", fh.use_ref_frame_mvs, !fh.disable_frame_end_update_cdf);
+        for (int i = 0; i < 8; i++)
+            if ((fh.refresh_frame_flags >> i) & 1) slot_no[i] = frame_no;
+        frame_no++;
+    }
     if (fh.primary_ref_frame == PRIMARY_REF_NONE) {
         cdf_load_defaults(cur_init_cdf_, fh.base_q_idx);
     } else {

@@ -928,9 +928,38 @@ static int uv_tx_size(int bsize, int sx, int sy) {
     return uv;
 }
 
+// A skipped inter block codes no coefficient and emits no record: all its walk over the transform blocks leaves behind is the
+// transform size in the deblocking maps and the "decoded" flags the intra edge availability of later blocks looks at.  Both are
+// rectangles (the transform size of a skipped inter block is uniform), written here with row fills instead of one
+// transform_block() call per transform block (a million calls per 4K clip of 60 frames).
+void TileDecoder::mark_skipped_inter_block() {
+    const int sb_mask = seq.use_128x128_superblock ? 31 : 15;
+    for (int plane = 0; plane < 1 + b->has_chroma * 2; plane++) {
+        const int sx = plane ? seq.subsampling_x : 0, sy = plane ? seq.subsampling_y : 0;
+        const int txsz = plane ? uv_tx_size(b->bsize, sx, sy) : b->tx_size;
+        const int step_x = kTxW[txsz] >> 2, step_y = kTxH[txsz] >> 2;
+        const int plane_sz = plane_residual_size((BlockSize)b->bsize, sx, sy);
+        const int x0 = mi_col >> sx, y0 = mi_row >> sy;
+        const int pw4 = fw.plane_w4(plane), ph4 = fw.plane_h4(plane);
+        // transform blocks that start inside the frame (the others are not visited)
+        const int cw = std::min((int)kBlockW4[plane_sz], pw4 - x0), chh = std::min((int)kBlockH4[plane_sz], ph4 - y0);
+        if (cw <= 0 || chh <= 0) continue;
+        const int cw_tx = (cw + step_x - 1) / step_x * step_x, ch_tx = (chh + step_y - 1) / step_y * step_y;
+        const int wv = std::min(cw_tx, pw4 - x0), hv = std::min(ch_tx, ph4 - y0);
+        for (int i = 0; i < hv; i++) memset(&fw.lf_tx[plane][(size_t)(y0 + i) * pw4 + x0], txsz, (size_t)wv);
+        const int bx0 = (((x0 << sx) & sb_mask) >> sx) + 1, by0 = (((y0 << sy) & sb_mask) >> sy) + 1;
+        const int n = std::min(cw_tx, 35 - bx0);
+        for (int i = 0; i < ch_tx && by0 + i < 35 && n > 0; i++) memset(&block_decoded[plane][by0 + i][bx0], 1, (size_t)n);
+    }
+}
+
 void TileDecoder::residual() {
     const int sb_mask = seq.use_128x128_superblock ? 31 : 15;
     (void)sb_mask;
+    if (b->skip && b->is_inter && !b->use_intrabc && !b->lossless) {
+        mark_skipped_inter_block();
+        return;
+    }
     const int width_chunks = std::max(1, kBlockW[b->bsize] >> 6), height_chunks = std::max(1, kBlockH[b->bsize] >> 6);
     const int mi_size_chunk = (width_chunks > 1 || height_chunks > 1) ? BLOCK_64X64 : b->bsize;
     for (int chunk_y = 0; chunk_y < height_chunks; chunk_y++)
@@ -1231,7 +1260,10 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             if (bw * bh > w * h) ctx += 3;
         }
     }
-    const int all_zero = ms.symbol(cdf.txb_skip[tx_ctx][ctx], 2);
+    // the arithmetic decoder runs from a local copy inside this function: the byte stores of the level maps (and the vector stores
+    // of the CDF adaptation) may alias anything behind `this`, and would force its window / range / count through memory per symbol
+    Msac m = ms;
+    const int all_zero = m.symbol(cdf.txb_skip[tx_ctx][ctx], 2);
     int eob = 0, cul_level = 0, dc_category = 0;
     if (all_zero) {
         if (plane == 0) {
@@ -1241,7 +1273,11 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
         }
         rec.txtp = b->lossless ? WHT_WHT : DCT_DCT;
     } else {
-        if (plane == 0) read_transform_type(x4, y4, txsz);
+        if (plane == 0) {
+            ms = m;
+            read_transform_type(x4, y4, txsz);
+            m = ms;
+        }
         const int txtp = compute_tx_type(plane, txsz, x4, y4);
         rec.txtp = (uint8_t)txtp;
         const int cls = tx_class_of(txtp);
@@ -1253,24 +1289,24 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
         const int eob_ctx = cls == TX_CLASS_2D ? 0 : 1;
         int eob_pt;
         switch (eob_multi) {
-            case 0: eob_pt = ms.symbol(cdf.eob_pt_16[ptype][eob_ctx], 5) + 1; break;
-            case 1: eob_pt = ms.symbol(cdf.eob_pt_32[ptype][eob_ctx], 6) + 1; break;
-            case 2: eob_pt = ms.symbol(cdf.eob_pt_64[ptype][eob_ctx], 7) + 1; break;
-            case 3: eob_pt = ms.symbol(cdf.eob_pt_128[ptype][eob_ctx], 8) + 1; break;
-            case 4: eob_pt = ms.symbol(cdf.eob_pt_256[ptype][eob_ctx], 9) + 1; break;
-            case 5: eob_pt = ms.symbol(cdf.eob_pt_512[ptype][eob_ctx], 10) + 1; break;
-            default: eob_pt = ms.symbol(cdf.eob_pt_1024[ptype][eob_ctx], 11) + 1; break;
+            case 0: eob_pt = m.symbol(cdf.eob_pt_16[ptype][eob_ctx], 5) + 1; break;
+            case 1: eob_pt = m.symbol(cdf.eob_pt_32[ptype][eob_ctx], 6) + 1; break;
+            case 2: eob_pt = m.symbol(cdf.eob_pt_64[ptype][eob_ctx], 7) + 1; break;
+            case 3: eob_pt = m.symbol(cdf.eob_pt_128[ptype][eob_ctx], 8) + 1; break;
+            case 4: eob_pt = m.symbol(cdf.eob_pt_256[ptype][eob_ctx], 9) + 1; break;
+            case 5: eob_pt = m.symbol(cdf.eob_pt_512[ptype][eob_ctx], 10) + 1; break;
+            default: eob_pt = m.symbol(cdf.eob_pt_1024[ptype][eob_ctx], 11) + 1; break;
         }
         eob = eob_pt < 2 ? eob_pt : ((1 << (eob_pt - 2)) + 1);
         int eob_shift = eob_pt >= 3 ? eob_pt - 3 : -1;
         if (eob_shift >= 0) {
-            if (ms.symbol(cdf.eob_extra[tx_ctx][ptype][eob_pt - 3], 2)) eob += 1 << eob_shift;
+            if (m.symbol(cdf.eob_extra[tx_ctx][ptype][eob_pt - 3], 2)) eob += 1 << eob_shift;
             for (int i = 1; i < std::max(0, eob_pt - 2); i++) {
                 eob_shift = std::max(0, eob_pt - 2) - 1 - i;
-                if (ms.literal(1)) eob += 1 << eob_shift;
+                if (m.literal(1)) eob += 1 << eob_shift;
             }
         }
-        if (eob > width * height) { fail(AV1R_EBITSTREAM, "eob exceeds transform size"); return 0; }
+        if (eob > width * height) { ms = m; fail(AV1R_EBITSTREAM, "eob exceeds transform size"); return 0; }
         // levels, reverse scan.  lv[] / lv3[] are zero-padded (stride = width + 4) byte maps of min(level, 15) and min(level, 3):
         // the neighbour sums of the context derivation need neither bounds checks nor clamps; the positions of the non-zero
         // levels are chained in nz[] so that the sign pass (forward scan) visits and clears only those.
@@ -1290,7 +1326,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
             else if (c <= (height << bwl) / 8) ectx = 1;
             else if (c <= (height << bwl) / 4) ectx = 2;
             else ectx = 3;
-            int level = ms.symbol(cdf.coeff_base_eob[tx_ctx][ptype][ectx], 3) + 1;
+            int level = m.symbol(cdf.coeff_base_eob[tx_ctx][ptype][ectx], 3) + 1;
             if (level > 2) {
                 int rctx;
                 if (pos == 0) rctx = 0;
@@ -1299,7 +1335,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                 else rctx = row == 0 ? 7 : 14;
                 uint16_t* bc = br_cdf[rctx];
                 for (int idx = 0; idx < 4; idx++) {
-                    const int br = ms.symbol(bc, 4);
+                    const int br = m.symbol(bc, 4);
                     level += br;
                     if (br < 3) break;
                 }
@@ -1330,7 +1366,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                     const int idx = CLS == TX_CLASS_VERT ? row : col;
                     bctx += 26 + 5 * std::min(idx, 2);
                 }
-                int level = ms.symbol(cb_cdf[bctx], 4);
+                int level = m.symbol(cb_cdf[bctx], 4);
                 if (level == 0) continue;
                 if (level > 2) {
                     const uint8_t* lp = lv + off;
@@ -1342,7 +1378,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                     else rctx = row == 0 ? mag + 7 : mag + 14;
                     uint16_t* bc = br_cdf[rctx];
                     for (int idx = 0; idx < 4; idx++) {
-                        const int br = ms.symbol(bc, 4);
+                        const int br = m.symbol(bc, 4);
                         level += br;
                         if (br < 3) break;
                     }
@@ -1380,27 +1416,28 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
                         else if (s == 2) dcs++;
                     }
                 const int dctx = dcs < 0 ? 1 : (dcs > 0 ? 2 : 0);
-                sign = ms.symbol(cdf.dc_sign[ptype][dctx], 2);
+                sign = m.symbol(cdf.dc_sign[ptype][dctx], 2);
             } else {
-                sign = ms.bit();
+                sign = m.bit();
             }
             if (level > 14) {
                 int length = 0, bit;
                 do {
                     length++;
-                    bit = ms.bit();
+                    bit = m.bit();
                     if (length > 32) {
                         for (int kk = k - 1; kk >= 0; kk--) {
                             const int o2 = nz[kk] + ((nz[kk] >> bwl) << 2);
                             lv[o2] = 0;
                             lv3[o2] = 0;
                         }
+                        ms = m;
                         fail(AV1R_EBITSTREAM, "golomb too long");
                         return 0;
                     }
                 } while (!bit);
                 int x = 1;
-                for (int i = length - 2; i >= 0; i--) x = (x << 1) + ms.bit();
+                for (int i = length - 2; i >= 0; i--) x = (x << 1) + m.bit();
                 level = x + 14;
             }
             if (pos == 0) dc_category = sign ? 1 : 2;
@@ -1420,6 +1457,7 @@ int TileDecoder::coeffs(int plane, int start_x, int start_y, int txsz, TxRec& re
         left_level[plane][y4 + i] = (uint8_t)cul_level;
         left_dc[plane][y4 + i] = (uint8_t)dc_category;
     }
+    ms = m;
     return eob;
 }
 

@@ -103,6 +103,7 @@ private:
     int seg_feature_active(int f) const { return fh.seg.enabled && fh.seg.feature_enabled[b->segment_id][f]; }
     void assign_mv(int is_compound);
     void assign_dv();
+    void mark_skipped_inter_block();
     void read_mv(int list);
     int read_mv_component(int comp);
     void read_interintra_mode(int is_compound);

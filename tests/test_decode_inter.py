@@ -149,7 +149,7 @@ def test_cuda_verify_buffer_many_multi_tu_segments(built):
         assert [int(x) for x in digests[i]] == want[i % len(want)], f"frame {i}"
 
 
-FULL_SIZE = ["c1", "c2", "c3_small", "c3", "c4"] + [f"c5_{i:02d}" for i in range(0, 32, 4)]
+FULL_SIZE = ["c1", "c2", "c3_small", "c3", "c4", "screen1080"] + [f"c5_{i:02d}" for i in range(0, 32, 4)]
 
 
 @pytest.mark.gpu
@@ -181,7 +181,7 @@ def test_cuda_full_size_clip_md5_vs_dav1d(built, clip):
 
 @pytest.mark.gpu
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("clip", ["c1", "c2", "c3", "c4", "c5_00"])
+@pytest.mark.parametrize("clip", ["c1", "c2", "c3", "c4", "c5_00", "screen1080"])
 def test_cuda_full_size_verify_digests_vs_dav1d(built, clip):
     """The segment-parallel verify path (what bench.py's e2e times) on the full-size clips: every plane digest of every frame from
     av1r_verify_buffer equals the digest of libdav1d's output for the same frame (position-salted 64-bit hash; host restatement in

@@ -31,6 +31,10 @@ CONFIGS = {
     **{f"c5_{i:02d}": ("occluders", 3840, 2160, 10, 16, {"cpu-used": "2", "cq-level": "32", "tile-columns": "2", "tile-rows": "1", "enable-obmc": "1",
                                                             "enable-warped-motion": "1", "enable-global-motion": "1", "enable-restoration": "1"},
                        {14: 7, 48: 8}, 100 + i) for i in range(32)},
+    # screen content at 1080p, every frame a key frame with palette + intra block copy (not a BASELINE config: the full-size parity
+    # case for the decode-order unit table of block-copy frames, 30 x 17 units and ~60 CTAs in flight per frame)
+    "screen1080": ("screen", 1920, 1080, 8, 6, {"cpu-used": "2", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0",
+                                             "enable-cdef": "0"}, {14: 0, 48: 0}),
     "c2_small": ("panzoom", 640, 360, 8, 8, {"cpu-used": "8", "cq-level": "32", "enable-restoration": "0", "enable-cdef": "1"}, {14: 0, 48: 0}),
 }
 
