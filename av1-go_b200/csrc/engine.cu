@@ -445,10 +445,7 @@ struct EngineImpl {
     std::shared_ptr<void> make_host_arena(const FrameWork& fw, const SeqHdr& seq, std::string& e, int& rc);
     size_t hw_staging = 0, hw_arena = 0, hw_residual = 0, hw_sync = 0, hw_mask = 0, hw_lf = 0;   // high-water marks of the slot buffers
     int k3_ctas = 0;                                  // persistent CTAs per frame of the K3 unit kernel; 0 = default (AV1R_K3_CTAS)
-    int k3_warps = 8;                                 // warps per K3 CTA (AV1R_K3_WARPS)
     int k3_progressive = 2;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive, 2 always cell-level (default)
-    int k3_wait_ns = 0;                               // AV1R_K3_WAIT_NS: sleep between attempts of a record-level wait
-    int k3_poll_ns_max = 800;                         // AV1R_K3_POLL_NS: back-off cap of the neighbour-unit polls
     int k3_inter_mult = 6;                            // inter frames: CTAs = this x the unit wavefront (AV1R_K3_INTER_MULT)
     int k3_intra_run = 0;                             // consecutive frames without inter prediction issued so far
     int64_t frames_decoded = 0;
@@ -628,9 +625,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             // inter frames: the few units that hold intra / inter-intra blocks are mostly independent of each other -> one round
             if (k3_ctas <= 0 && L.n_inter > 0) il.ctas = std::min(L.n_k3units, k3_inter_mult * il.ctas);
         }
-        il.warps = k3_warps;
-        il.wait_ns = k3_wait_ns;
-        il.poll_ns_max = k3_poll_ns_max;
+        il.general = (L.n_inter > 0 || dw.fh.allow_screen_content_tools) ? 1 : 0;
         il.load_tile = L.n_inter > 0;
         // sync block: [n_units x u64 progress words][n_units x int unit flags][ticket, stuck flag, pad]
         const size_t sync_bytes = (sizeof(unsigned long long) + sizeof(int)) * (size_t)L.n_k3units + 4 * sizeof(int);
@@ -1134,9 +1129,6 @@ int Engine::open(const av1r_config& cfg) {
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));
     if (const char* e = getenv("AV1R_K3_INTER_MULT")) E.k3_inter_mult = std::max(1, atoi(e));
     if (const char* e = getenv("AV1R_K3_PROGRESSIVE")) E.k3_progressive = std::min(2, std::max(0, atoi(e)));
-    if (const char* e = getenv("AV1R_K3_WARPS")) E.k3_warps = std::min(8, std::max(1, atoi(e)));
-    if (const char* e = getenv("AV1R_K3_WAIT_NS")) E.k3_wait_ns = std::min(100000, std::max(0, atoi(e)));
-    if (const char* e = getenv("AV1R_K3_POLL_NS")) E.k3_poll_ns_max = std::min(100000, std::max(100, atoi(e)));
     if (getenv("AV1R_K3_PROF")) {
         CK(E.k3_prof.ensure(16 * sizeof(unsigned long long)));
         CK(cudaMemset(E.k3_prof.p, 0, 16 * sizeof(unsigned long long)));

@@ -187,10 +187,12 @@ struct FrameWork {
         mi_cols = h.mi_cols;
         mi_rows = h.mi_rows;
         // A FrameWork is recycled (stream_parser.cpp): only what the parse *reads before writing* is cleared.  mi must be null
-        // ("not yet decoded in this frame"); every other per-mi map is fully written by the parse of the frame before anything
-        // reads it (each block writes its whole area), so resizing without a fill is enough.
+        // ("not yet decoded in this frame"): every tile clears its own rectangle when it starts (TileDecoder::decode_tile; a tile
+        // only ever looks at its own rectangle, and the 4 MB fill of a 4K frame leaves the frame-to-frame chain for the tile
+        // threads); every other per-mi map is fully written by the parse of the frame before anything reads it (each block
+        // writes its whole area), so resizing without a fill is enough.
         size_t n = (size_t)mi_cols * mi_rows;
-        mi.assign(n, nullptr);
+        mi.resize(n);
         lf_mi.resize(n);   // written for every mi a block covers; the edge builder only reads covered mi
         inter_tx.resize(n);
         tx_types.resize(n);

@@ -265,47 +265,65 @@ __device__ __forceinline__ int ii_mask(int pk, const uint8_t* master, int i, int
     return 32;
 }
 
+#ifndef K3_RARE_ATTR
+#define K3_RARE_ATTR __forceinline__
+#endif
+// Geometry of a record inside its unit (shared by the hot predictor and the out-of-line rare paths).
 template <typename T>
-__device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrameParams& fp, WarpScratch& sm, int lane,
-                            const uint8_t* wedge_master, const uint8_t* pal, const DevPlanes& frame) {
-    const int plane = r.plane;
-    const int lw = tx_lw(r.txsz), lh = tx_lh(r.txsz);
-    const int w = 1 << lw, h = 1 << lh;
-    const int x = r.x4 * 4, y = r.y4 * 4;
-    const int bd = fp.bd, pixmax = (1 << bd) - 1;
-    // (two uniform parameter loads and a select instead of a register-indexed constant load: planes 1 and 2 have the same size)
-    const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
-    const int max_x = pcw - 1, max_y = pch - 1;
-    const int xe = min(w, pcw - x), ye = min(h, pch - y);
-    const int opitch = uv.cs(plane);
-    T* out = uv.cv(plane) + (y - uv.y0(plane)) * opitch + (x - uv.x0(plane));   // the unit's samples live in shared memory
-    const bool has_res = r.eob > 0;
-    const int rpitch = uv.W(plane);            // residual unit: plane tiles of W x H int16, staged by the bulk copy
-    const int16_t* rp = uv.res + uv.res_off(plane) + (y - uv.y0(plane)) * rpitch + (x - uv.x0(plane));
-    const bool ii = (r.flags & TXF_II) != 0;
-    const int ii_pk = (uint16_t)r.cfl_alpha;
-    const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
-    // luma is reconstructed in full also beyond the coded frame edge (the canvas holds the whole unit; the write-back clips):
-    // chroma-from-luma of a block that straddles the edge reads those samples (spec MaxLumaW / MaxLumaH)
-    const int xw = plane ? xe : w, yw = plane ? ye : h;
-    auto emit = [&](int i, int j, int v) {
+struct BlkCtx {
+    int plane, lw, lh, w, h, x, y, pixmax, max_x, max_y, xe, ye, xw, yw, opitch, rpitch;
+    T* out;
+    const int16_t* rp;
+    bool has_res;
+    __device__ __forceinline__ BlkCtx(const TxRec& r, const UnitCtx<T>& uv, int bd, int pcw, int pch) {
+        plane = r.plane;
+        lw = tx_lw(r.txsz);
+        lh = tx_lh(r.txsz);
+        w = 1 << lw;
+        h = 1 << lh;
+        x = r.x4 * 4;
+        y = r.y4 * 4;
+        pixmax = (1 << bd) - 1;
+        max_x = pcw - 1;
+        max_y = pch - 1;
+        xe = min(w, pcw - x);
+        ye = min(h, pch - y);
+        // luma is reconstructed in full also beyond the coded frame edge (the canvas holds the whole unit; the write-back clips):
+        // chroma-from-luma of a block that straddles the edge reads those samples (spec MaxLumaW / MaxLumaH)
+        xw = plane ? xe : w;
+        yw = plane ? ye : h;
+        opitch = uv.cs(plane);
+        out = uv.cv(plane) + (y - uv.y0(plane)) * opitch + (x - uv.x0(plane));   // the unit's samples live in shared memory
+        has_res = r.eob > 0;
+        rpitch = uv.W(plane);            // residual unit: plane tiles of W x H int16, staged by the bulk copy
+        rp = uv.res + uv.res_off(plane) + (y - uv.y0(plane)) * rpitch + (x - uv.x0(plane));
+    }
+    __device__ __forceinline__ void emit(int i, int j, int v) const {
         if (i < yw && j < xw) {
-            if (ii) {   // blend the intra predictor over the inter predictor K2 left in the frame
-                const int m = ii_mask(ii_pk, wedge_master, i, j, w, h, psx, psy);
-                v = (m * v + (64 - m) * (int)out[i * opitch + j] + 32) >> 6;
-            }
             if (has_res) v = min(max(v + (int)rp[i * rpitch + j], 0), pixmax);
             out[i * opitch + j] = (T)v;
         }
-    };
+    }
+};
+
+// Record kinds that read no neighbour edge and are rare in camera content: residual of an inter-intra block, intra block copy,
+// palette.  Out of line on purpose: the wavefront kernel is bound by the latency of its dependency chain, its instruction cache hit
+// rate is ~91 % (ncu sm__icc_request_hit_rate), and every kilobyte of cold code inlined into the record loop showed up as lost
+// throughput when several frames share an SM (profiles/r2_k3_sweep.md).  Scalars are passed by value: taking the address of the
+// kernel's parameter struct would copy it to local memory.
+template <typename T>
+__device__ K3_RARE_ATTR void rare_block(const TxRec r, const UnitCtx<T> uv, int bd, int pcw, int pch, int psx, int psy, int lane,
+                                        const uint8_t* pal, const uint8_t* fb, uint32_t pitch) {
+    const BlkCtx<T> c(r, uv, bd, pcw, pch);
+    const int w = c.w, h = c.h, lw = c.lw, x = c.x, y = c.y;
     if (r.mode == TXM_INTER) {
         // plain inter residuals were added by the K2 residual kernel; only inter-intra blocks wait for their blend
-        if (has_res && ii)
+        if (c.has_res && (r.flags & TXF_II))
             for (int idx = lane; idx < w * h; idx += 32) {
                 const int i = idx >> lw, j = idx & (w - 1);
-                if (i < ye && j < xe) {
-                    int v = (int)out[i * opitch + j] + (int)rp[i * rpitch + j];
-                    out[i * opitch + j] = (T)min(max(v, 0), pixmax);
+                if (i < c.ye && j < c.xe) {
+                    int v = (int)c.out[i * c.opitch + j] + (int)c.rp[i * c.rpitch + j];
+                    c.out[i * c.opitch + j] = (T)min(max(v, 0), c.pixmax);
                 }
             }
         return;
@@ -318,31 +336,102 @@ __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrame
         const int dvx = (int16_t)r.cfl_max_w4, dvy = (int16_t)r.cfl_max_h4;
         const int posx = (x << 4) + ((2 * dvx) >> psx), posy = (y << 4) + ((2 * dvy) >> psy);
         const int ix = posx >> 4, fx = posx & 15, iy = posy >> 4, fy = posy & 15;
-        const uint8_t* fb = frame.p[plane];
-        const uint32_t pitch = frame.pitch[plane];
         for (int idx = lane; idx < w * h; idx += 32) {
             const int i = idx >> lw, j = idx & (w - 1);
-            const int xa = min(max(ix + j, 0), max_x), xb = min(max(ix + j + 1, 0), max_x);
-            const int ya = min(max(iy + i, 0), max_y), yb = min(max(iy + i + 1, 0), max_y);
+            const int xa = min(max(ix + j, 0), c.max_x), xb = min(max(ix + j + 1, 0), c.max_x);
+            const int ya = min(max(iy + i, 0), c.max_y), yb = min(max(iy + i + 1, 0), c.max_y);
             const T* r0 = reinterpret_cast<const T*>(fb + (size_t)ya * pitch);
             const T* r1 = reinterpret_cast<const T*>(fb + (size_t)yb * pitch);
             const int t0 = ((128 - 8 * fx) * (int)ld_cell<T>(r0 + xa) + 8 * fx * (int)ld_cell<T>(r0 + xb) + 4) >> 3;
             const int t1 = ((128 - 8 * fx) * (int)ld_cell<T>(r1 + xa) + 8 * fx * (int)ld_cell<T>(r1 + xb) + 4) >> 3;
-            emit(i, j, min(max(((128 - 8 * fy) * t0 + 8 * fy * t1 + 1024) >> 11, 0), pixmax));
+            c.emit(i, j, min(max(((128 - 8 * fy) * t0 + 8 * fy * t1 + 1024) >> 11, 0), c.pixmax));
         }
         return;
     }
-    if (r.mode == TXM_PALETTE) {   // spec 7.11.4; entry layout documented at TileDecoder::palette_tokens
+    {   // TXM_PALETTE, spec 7.11.4; entry layout documented at TileDecoder::palette_tokens
         const uint8_t* e = pal + r.pal_off;
         const uint16_t* hdr = reinterpret_cast<const uint16_t*>(e);
         const uint8_t* map = e + 24;
         const int ox = hdr[8], oy = hdr[9], stride = hdr[10];
         for (int idx = lane; idx < w * h; idx += 32) {
             const int i = idx >> lw, j = idx & (w - 1);
-            emit(i, j, (int)hdr[map[(size_t)(y - oy + i) * stride + (x - ox + j)]]);
+            c.emit(i, j, (int)hdr[map[(size_t)(y - oy + i) * stride + (x - ox + j)]]);
         }
-        return;
     }
+}
+
+// Inter-intra (inter frames only): the intra predictor of the whole block is blended over the inter predictor K2 left in the
+// frame.  ii_save parks the inter predictor in the warp's scratch tile (blocks are at most 32x32), the ordinary predictor then
+// writes the intra predictor into the canvas, ii_blend mixes the two (spec 7.11.3.13).  Both out of line: see rare_block.
+template <typename T>
+__device__ K3_RARE_ATTR void ii_save(const TxRec r, const UnitCtx<T> uv, int bd, int pcw, int pch, int16_t* tile, int lane) {
+    const BlkCtx<T> c(r, uv, bd, pcw, pch);
+    for (int idx = lane; idx < c.w * c.h; idx += 32) {
+        const int i = idx >> c.lw, j = idx & (c.w - 1);
+        if (i < c.yw && j < c.xw) tile[idx] = (int16_t)c.out[i * c.opitch + j];
+    }
+}
+template <typename T>
+__device__ K3_RARE_ATTR void ii_blend(const TxRec r, const UnitCtx<T> uv, int bd, int pcw, int pch, int psx, int psy, const int16_t* tile,
+                                      const uint8_t* wedge_master, int lane) {
+    const BlkCtx<T> c(r, uv, bd, pcw, pch);
+    const int ii_pk = (uint16_t)r.cfl_alpha;
+    for (int idx = lane; idx < c.w * c.h; idx += 32) {
+        const int i = idx >> c.lw, j = idx & (c.w - 1);
+        if (i < c.yw && j < c.xw) {
+            const int m = ii_mask(ii_pk, wedge_master, i, j, c.w, c.h, psx, psy);
+            c.out[i * c.opitch + j] = (T)((m * (int)c.out[i * c.opitch + j] + (64 - m) * (int)tile[idx] + 32) >> 6);
+        }
+    }
+}
+
+// Filter-intra (spec 7.11.2.3): 4x2 sub-blocks along anti-diagonals, each from seven neighbours.  Rare -> out of line (see rare_block).
+template <typename T>
+__device__ K3_RARE_ATTR void filter_intra_block(const TxRec r, const UnitCtx<T> uv, int bd, int pcw, int pch, const edge_t* above, const edge_t* left,
+                                                int16_t* pt, int lane) {
+    const BlkCtx<T> c(r, uv, bd, pcw, pch);
+    const int w = c.w, h = c.h, lw = c.lw, pixmax = c.pixmax;
+    {
+        const int w4 = w >> 2, h2 = h >> 1;
+        const int fm = r.fi_mode;
+        for (int d = 0; d < h2 + w4 - 1; d++) {
+            const int i2_lo = max(0, d - (w4 - 1)), i2_hi = min(h2 - 1, d);
+            const int nblk = i2_hi - i2_lo + 1;
+            for (int t = lane; t < nblk * 8; t += 32) {
+                const int i2 = i2_lo + (t >> 3), j4 = d - i2, o = t & 7;
+                int p[7];
+#pragma unroll
+                for (int i = 0; i < 7; i++) {
+                    int v;
+                    if (i < 5) {
+                        if (i2 == 0) v = above[(j4 << 2) + i - 1];
+                        else if (j4 == 0 && i == 0) v = left[(i2 << 1) - 1];
+                        else v = pt[((i2 << 1) - 1) * w + (j4 << 2) + i - 1];
+                    } else {
+                        if (j4 == 0) v = left[(i2 << 1) + i - 5];
+                        else v = pt[((i2 << 1) + i - 5) * w + (j4 << 2) - 1];
+                    }
+                    p[i] = v;
+                }
+                int pr = 0;
+#pragma unroll
+                for (int i = 0; i < 7; i++) pr += c_fi_taps[fm][o][i] * p[i];
+                const int v = pr >= 0 ? (pr + 8) >> 4 : -((-pr + 8) >> 4);
+                pt[((i2 << 1) + (o >> 2)) * w + (j4 << 2) + (o & 3)] = (int16_t)min(max(v, 0), pixmax);
+            }
+            __syncwarp();
+        }
+        for (int idx = lane; idx < w * h; idx += 32) c.emit(idx >> lw, idx & (w - 1), pt[idx]);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void intra_pred(const TxRec& r, const UnitCtx<T>& uv, const DevFrameParams& fp, WarpScratch& sm, int lane) {
+    const int bd = fp.bd;
+    // (two uniform parameter loads and a select instead of a register-indexed constant load: planes 1 and 2 have the same size)
+    const BlkCtx<T> c(r, uv, bd, r.plane ? fp.cw[1] : fp.cw[0], r.plane ? fp.ch[1] : fp.ch[0]);
+    const int plane = c.plane, lw = c.lw, lh = c.lh, w = c.w, h = c.h, x = c.x, y = c.y, pixmax = c.pixmax, max_x = c.max_x, max_y = c.max_y;
+    auto emit = [&](int i, int j, int v) { c.emit(i, j, v); };
     const int have_left = r.flags & TXF_HAVE_LEFT, have_above = r.flags & TXF_HAVE_ABOVE;
     const int have_ar = r.flags & TXF_HAVE_ABOVE_RIGHT, have_bl = r.flags & TXF_HAVE_BELOW_LEFT;
     edge_t* above = sm.above[0] + EDGE_PAD;
@@ -384,37 +473,7 @@ __device__ void intra_block(const TxRec& r, const UnitCtx<T>& uv, const DevFrame
     if (mode == TXM_CFL) mode = DC_PRED;
 
     if (mode == TXM_FILTER_INTRA) {
-        const int w4 = w >> 2, h2 = h >> 1;
-        int16_t* pt = sm.tile;   // w x h predictions
-        const int fm = r.fi_mode;
-        for (int d = 0; d < h2 + w4 - 1; d++) {
-            const int i2_lo = max(0, d - (w4 - 1)), i2_hi = min(h2 - 1, d);
-            const int nblk = i2_hi - i2_lo + 1;
-            for (int t = lane; t < nblk * 8; t += 32) {
-                const int i2 = i2_lo + (t >> 3), j4 = d - i2, o = t & 7;
-                int p[7];
-#pragma unroll
-                for (int i = 0; i < 7; i++) {
-                    int v;
-                    if (i < 5) {
-                        if (i2 == 0) v = above[(j4 << 2) + i - 1];
-                        else if (j4 == 0 && i == 0) v = left[(i2 << 1) - 1];
-                        else v = pt[((i2 << 1) - 1) * w + (j4 << 2) + i - 1];
-                    } else {
-                        if (j4 == 0) v = left[(i2 << 1) + i - 5];
-                        else v = pt[((i2 << 1) + i - 5) * w + (j4 << 2) - 1];
-                    }
-                    p[i] = v;
-                }
-                int pr = 0;
-#pragma unroll
-                for (int i = 0; i < 7; i++) pr += c_fi_taps[fm][o][i] * p[i];
-                const int v = pr >= 0 ? (pr + 8) >> 4 : -((-pr + 8) >> 4);
-                pt[((i2 << 1) + (o >> 2)) * w + (j4 << 2) + (o & 3)] = (int16_t)min(max(v, 0), pixmax);
-            }
-            __syncwarp();
-        }
-        for (int idx = lane; idx < w * h; idx += 32) emit(idx >> lw, idx & (w - 1), pt[idx]);
+        filter_intra_block<T>(r, uv, bd, plane ? fp.cw[1] : fp.cw[0], plane ? fp.ch[1] : fp.ch[0], above, left, sm.tile, lane);
         return;
     }
     if (mode >= V_PRED && mode <= D67_PRED) {
@@ -599,7 +658,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // `stuck` (one int per frame) is raised instead of hanging if a wait makes no progress for seconds: a wrong work-list must
 // end in a digest mismatch, not in a wedged GPU.
-__device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parity, int* stuck, int wait_ns) {
+__device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parity, int* stuck) {
     for (int rounds = 0; rounds < 64; rounds++) {
         const bool pend = id >= 0 && !mbar_test(rbar + 8u * (uint32_t)id, parity);
         if (!__any_sync(0xffffffffu, pend)) return;
@@ -607,10 +666,8 @@ __device__ __forceinline__ void wait_local(uint32_t rbar, int id, uint32_t parit
         // it times out, not the whole test / vote / reduce sequence
         const uint32_t b = rbar + 8u * (uint32_t)__reduce_max_sync(0xffffffffu, pend ? id : -1);
         int spins = 0;
-        while (!mbar_try(b, parity)) {
-            if (wait_ns) __nanosleep(wait_ns);   // waiting warps of co-resident frames must not eat the working warps' issue slots
+        while (!mbar_try(b, parity))   // (sleeping between attempts was measured: no effect on throughput, profiles/r2_k3_sweep.md)
             if (++spins > (1 << 22)) { *stuck = 1; return; }
-        }
     }
     *stuck = 1;
 }
@@ -622,7 +679,11 @@ __device__ __forceinline__ TxRec load_rec(const TxRec* p) {
     return u.r;
 }
 
-template <typename T, int NW>
+// PROG (cell-by-cell hand-over between units or whole units) and PROF (phase timers) are compile-time: the record loop is bound by
+// the latency of its dependency chain, and every runtime test or dead branch in it costs throughput (profiles/r2_k3_sweep.md).
+// GEN = false is the camera-content build: the frame holds no inter-intra, inter-residual, block-copy or palette record (an intra
+// frame without screen-content tools), and those paths are compiled out of the record loop.
+template <typename T, int NW, bool PROG, bool PROF, bool GEN>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(IntraLaunch L) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- carve (mirrored by k3_smem_bytes)
@@ -651,13 +712,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
     // optional phase timers (AV1R_K3_PROF): thread 0 of the CTA for the unit phases, lane 0 of every warp for the record phases
     long long tp = 0;
     auto lap = [&](int slot, bool who) {
-        if (L.prof && who) {
+        if (PROF && who) {
             const long long t = clock64();
             atomicAdd(L.prof + slot, (unsigned long long)(t - tp));
             tp = t;
         }
     };
-    if (L.prof) tp = clock64();
+    if (PROF) tp = clock64();
     while (true) {
         if (tid == 0) us->unit = atomicAdd(L.ticket, 1);
         __syncthreads();
@@ -729,7 +790,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         TxRec r_next;
         if (k < count) r_next = load_rec(L.recs + __ldg(L.order + first + k));
         lap(1, tid == 0);   // prologue: context, owner map
-        if (L.progressive) {
+        if (PROG) {
             // border cells that no record of this unit reconstructs (inter-predicted samples, cells outside the frame) are final
             __syncthreads();   // owner map complete
             if (warp == 0) {
@@ -748,7 +809,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             }
         }
         // ---- wait for the neighbour units whose samples this unit reads
-        if (warp == 0 && !L.progressive) {
+        if (warp == 0 && !PROG) {
             if (lane < 5) {
                 const int d = __ldg(&up->dep[lane]);
                 if (d >= 0) {
@@ -765,7 +826,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         __syncthreads();
         lap(2, tid == 0);   // neighbour units
         // ---- halo (and, in inter frames, the unit's own inter-predicted samples) from L2
-        if (!L.progressive) {   // row above (corner .. above-right) and column to the left (.. below-left) of the three planes: one flat index space, all
+        if (!PROG) {   // row above (corner .. above-right) and column to the left (.. below-left) of the three planes: one flat index space, all
             // loads of a thread issued before the first store, so the halo costs one L2 round trip
             constexpr int SEG0 = 2 * (2 * CV_W0 + 1), SEG1 = 2 * (2 * CV_W1 + 1);   // per plane: [row: 2W + 1][col: 2W] (+1 pad)
             constexpr int TOT = SEG0 + 2 * SEG1;
@@ -816,7 +877,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         parity ^= 1;
         __syncthreads();
         lap(4, tid == 0);   // residual bulk copy
-        if (L.prof && lane == 0 && tid != 0) tp = clock64();
+        if (PROF && lane == 0 && tid != 0) tp = clock64();
         // ---- record-level dataflow inside the unit
         // Records are dealt round-robin to the warps (record k -> warp k mod NW; a warp walks its records in order, so the lowest
         // unfinished record can always run) and the next record is fetched while the current one waits and predicts.
@@ -825,11 +886,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             const TxRec r = r_next;
             if (k + nw < count) r_next = load_rec(L.recs + __ldg(L.order + first + k + nw));
             lap(8, lane == 0);   // record fetch
-            if (r.mode == TXM_INTER) {
-                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck, L.wait_ns);   // residual of an inter-intra block: after its blend
-            } else if (r.mode == TXM_INTRABC) {
+            if (GEN && r.mode == TXM_INTER) {
+                if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck);   // residual of an inter-intra block: after its blend
+            } else if (GEN && r.mode == TXM_INTRABC) {
                 // block copy: wait until every unit the source rectangle touches is complete in the frame (whole-unit flags; the
                 // plan guarantees they come earlier in the table, so this cannot wait on a unit that waits on us)
+#ifndef K3_NO_IBC_WAIT
                 if (L.upos) {
                     const int plane = r.plane;
                     const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
@@ -858,7 +920,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                     __syncwarp();
                     fence_acquire_gpu();
                 }
-            } else if (r.mode != TXM_PALETTE) {
+#endif
+            } else if (!GEN || r.mode != TXM_PALETTE) {
                 const int plane = r.plane;
                 const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
                 const int pw4 = plane ? fp.pw4[1] : fp.pw4[0], ph4 = plane ? fp.ph4[1] : fp.ph4[0];
@@ -898,7 +961,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                         if (cx >= 0 && cy >= 0 && cx < uw4 && cy < uw4) {   // (whole-unit hand-over: cells of other units were final before the unit started)
                             id = m[cy * uw4 + cx];
                             if (id >= k) id = -1;
-                        } else if (L.progressive) {
+                        } else if (PROG) {
                             if (cy < 0) {            // row above the unit: above-left / above / above-right unit, bottom row of cells
                                 nbr = cx < 0 ? 2 : (cx < uw4 ? 3 : 4);
                                 bit = prog_boff(plane) + (cx < 0 ? uw4 - 1 : (cx < uw4 ? cx : cx - uw4));
@@ -908,7 +971,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                             }
                         }
                     }
-                    if (L.progressive && __any_sync(0xffffffffu, nbr >= 0)) {
+                    if (PROG && __any_sync(0xffffffffu, nbr >= 0)) {
                         // lane n < 5 collects the cells wanted from neighbour n and polls that unit's progress word
                         const unsigned long long mine = nbr >= 0 ? 1ull << bit : 0ull;
                         unsigned long long want = 0;
@@ -927,7 +990,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 unsigned ns = 100;
                                 while ((ld_relaxed64(L.uprog + d) & want) != want) {
                                     __nanosleep(ns);
-                                    if (ns < (unsigned)L.poll_ns_max) ns <<= 1;
+                                    if (ns < 800) ns <<= 1;
                                     if (++spins > (1 << 23)) { *L.stuck = 3; break; }
                                 }
                             }
@@ -960,7 +1023,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                         }
                         __syncwarp();
                     }
-                    wait_local(rbar, id, rpar, L.stuck, L.wait_ns);
+                    wait_local(rbar, id, rpar, L.stuck);
                 }
                 if (r.mode == TXM_CFL) {   // luma samples under this chroma block
                     const int sx = fp.subx, sy = fp.suby;
@@ -977,17 +1040,36 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                                 if (id >= k) id = -1;
                             }
                         }
-                        wait_local(rbar, id, rpar, L.stuck, L.wait_ns);
+                        wait_local(rbar, id, rpar, L.stuck);
                     }
                 }
             }
             // the waits acquire (mbarrier test/try_wait) what the owners released with their arrive; __syncwarp orders the lanes
             __syncwarp();
             lap(9, lane == 0);   // dependency wait
-            intra_block<T>(r, uc, fp, sm, lane, L.wedge_master, L.pal, L.frame);
+            {
+                const int plane = r.plane;
+                const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
+                const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
+                if (GEN && (r.mode == TXM_INTER || r.mode == TXM_INTRABC || r.mode == TXM_PALETTE)) {
+                    rare_block<T>(r, uc, fp.bd, pcw, pch, psx, psy, lane, L.pal, plane == 0 ? L.frame.p[0] : (plane == 1 ? L.frame.p[1] : L.frame.p[2]),
+                                  plane == 0 ? L.frame.pitch[0] : L.frame.pitch[1]);
+                } else {
+                    const bool ii = GEN && (r.flags & TXF_II) != 0;
+                    if (ii) {
+                        ii_save<T>(r, uc, fp.bd, pcw, pch, sm.tile, lane);
+                        __syncwarp();
+                    }
+                    intra_pred<T>(r, uc, fp, sm, lane);
+                    if (ii) {
+                        __syncwarp();
+                        ii_blend<T>(r, uc, fp.bd, pcw, pch, psx, psy, sm.tile, L.wedge_master, lane);
+                    }
+                }
+            }
             __syncwarp();        // all lanes' samples are in the canvas before lane 0 releases the record's barrier
             if (lane == 0) mbar_arrive(rbar + 8u * (uint32_t)k);
-            if (L.progressive) {
+            if (PROG) {
                 // cells of the unit's bottom row / right column this record is the last writer of: store them to the frame now and
                 // publish them, so that the units below and to the right can start on them while this unit is still busy
                 const int plane = r.plane;
@@ -1025,7 +1107,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                 }
             }
             lap(10, lane == 0);  // predict + reconstruct
-            if (L.prof && lane == 0) atomicAdd(L.prof + 12, 1ull);
+            if (PROF && lane == 0) atomicAdd(L.prof + 12, 1ull);
         }
         lap(11, lane == 0 && tid != 0);   // warp idle at the end of the unit
         __syncthreads();
@@ -1049,12 +1131,20 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         if (tid == 0) st_release(L.uflags + u, 1);   // release after the CTA barrier: cumulative over every thread's write-back stores
         rpar ^= 1;
         lap(6, tid == 0);   // write-back + release
-        if (L.prof && tid == 0) atomicAdd(L.prof + 13, 1ull);
+        if (PROF && tid == 0) atomicAdd(L.prof + 13, 1ull);
     }
 }
 
 static size_t k3_smem_bytes(int bps, int warps) {
     return RES_ELEMS * sizeof(int16_t) + (size_t)(CV_ELEMS + 128) * bps + OWNER_CELLS * 4 + K3_UNIT_MAX_RECS * 8 + 64 + (size_t)warps * sizeof(WarpScratch);
+}
+
+template <typename F>
+static void k3_for_each_kernel(F f) {   // T x PROG x {camera, general, general + timers}
+    f(intra_unit_kernel<uint8_t, 8, false, false, false>); f(intra_unit_kernel<uint8_t, 8, false, false, true>); f(intra_unit_kernel<uint8_t, 8, false, true, true>);
+    f(intra_unit_kernel<uint8_t, 8, true, false, false>); f(intra_unit_kernel<uint8_t, 8, true, false, true>); f(intra_unit_kernel<uint8_t, 8, true, true, true>);
+    f(intra_unit_kernel<uint16_t, 8, false, false, false>); f(intra_unit_kernel<uint16_t, 8, false, false, true>); f(intra_unit_kernel<uint16_t, 8, false, true, true>);
+    f(intra_unit_kernel<uint16_t, 8, true, false, false>); f(intra_unit_kernel<uint16_t, 8, true, false, true>); f(intra_unit_kernel<uint16_t, 8, true, true, true>);
 }
 
 static cudaError_t intra_upload_constants() {
@@ -1073,10 +1163,12 @@ static cudaError_t intra_upload_constants() {
     if ((e = cudaMemcpyToSymbol(c_ii_blk_w, kBlockW, sizeof(kBlockW))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_ii_blk_h, kBlockH, sizeof(kBlockH))) != cudaSuccess) return e;
     const size_t mx = k3_smem_bytes(2, K3_MAX_WARPS);
-    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint8_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint8_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(intra_unit_kernel<uint16_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx)) != cudaSuccess) return e;
+    {
+        cudaError_t ea = cudaSuccess;
+        auto set = [&](auto k) { if (ea == cudaSuccess) ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx); };
+        k3_for_each_kernel(set);
+        if (ea != cudaSuccess) return ea;
+    }
     if (dev < 64) g_intra_const_loaded[dev] = true;
     return cudaSuccess;
 }
@@ -1089,22 +1181,27 @@ cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s) {
     {
         static bool carve_done = false;
         if (!carve_done) {
-            prefer_max_smem(intra_unit_kernel<uint8_t, 4>);
-            prefer_max_smem(intra_unit_kernel<uint16_t, 4>);
-            prefer_max_smem(intra_unit_kernel<uint8_t, 8>);
-            prefer_max_smem(intra_unit_kernel<uint16_t, 8>);
+            k3_for_each_kernel([](auto k) { prefer_max_smem(k); });
             carve_done = true;
         }
     }
-    const int warps = L.warps <= 4 ? 4 : 8;
     const int blocks = std::min(L.n_units, std::max(1, L.ctas));
-    if (L.fp.bd == 8) {
-        if (warps == 4) intra_unit_kernel<uint8_t, 4><<<blocks, 128, k3_smem_bytes(1, 4), s>>>(L);
-        else intra_unit_kernel<uint8_t, 8><<<blocks, 256, k3_smem_bytes(1, 8), s>>>(L);
-    } else {
-        if (warps == 4) intra_unit_kernel<uint16_t, 4><<<blocks, 128, k3_smem_bytes(2, 4), s>>>(L);
-        else intra_unit_kernel<uint16_t, 8><<<blocks, 256, k3_smem_bytes(2, 8), s>>>(L);
-    }
+    const bool prof = L.prof != nullptr, prog = L.progressive != 0, gen = L.general != 0 || prof;
+    auto go = [&](auto tag_t) {
+        using TT = decltype(tag_t);
+        const size_t sm = k3_smem_bytes((int)sizeof(TT), 8);
+        if (prog) {
+            if (prof) intra_unit_kernel<TT, 8, true, true, true><<<blocks, 256, sm, s>>>(L);
+            else if (gen) intra_unit_kernel<TT, 8, true, false, true><<<blocks, 256, sm, s>>>(L);
+            else intra_unit_kernel<TT, 8, true, false, false><<<blocks, 256, sm, s>>>(L);
+        } else {
+            if (prof) intra_unit_kernel<TT, 8, false, true, true><<<blocks, 256, sm, s>>>(L);
+            else if (gen) intra_unit_kernel<TT, 8, false, false, true><<<blocks, 256, sm, s>>>(L);
+            else intra_unit_kernel<TT, 8, false, false, false><<<blocks, 256, sm, s>>>(L);
+        }
+    };
+    if (L.fp.bd == 8) go(uint8_t());
+    else go(uint16_t());
     return cudaGetLastError();
 }
 

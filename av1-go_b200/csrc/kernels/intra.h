@@ -14,11 +14,9 @@ struct IntraLaunch {            // passed by value
     const K3Unit* units;        // device, unit table in wavefront order
     int n_units;
     int ctas;                   // persistent CTAs this frame may occupy (one unit per CTA at a time)
-    int warps;                  // warps per CTA (records of a unit in flight)
     int load_tile;              // 1: the frame already holds inter-predicted samples (inter frame) -> bring the unit in before predicting
     int progressive;            // 1: units hand their bottom row / right column over cell by cell (uprog), 0: whole units (uflags)
-    int wait_ns;                // sleep between two attempts of a record-level wait (0: re-issue try_wait immediately)
-    int poll_ns_max;            // cap of the back-off between polls of a neighbour unit's progress word
+    int general;                // 1: the frame may hold inter-intra / inter-residual / block-copy / palette records (0: camera-content intra frame)
     unsigned long long* uprog;  // device, n_units words, zeroed before launch: finished border cells of every unit (bit layout in intra.cu)
     int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
     const int32_t* upos;        // device, one entry per 64x64 unit of the frame: its table index (frames with intra block copy; else null)

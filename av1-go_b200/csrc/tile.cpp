@@ -109,6 +109,8 @@ int TileDecoder::decode_tile(const uint8_t* data, size_t sz, int tile_row, int t
     mi_col_start = fh.mi_col_starts[tile_col];
     mi_col_end = fh.mi_col_starts[tile_col + 1];
     current_q_index = fh.base_q_idx;
+    for (int r = mi_row_start; r < mi_row_end; r++)   // "not yet decoded in this frame" for the tile's rectangle (see FrameWork::init)
+        memset(&fw.mi[(size_t)r * fw.mi_cols + mi_col_start], 0, sizeof(fw.mi[0]) * (size_t)(mi_col_end - mi_col_start));
     ms.init(data, sz, fh.disable_cdf_update != 0);
     // clear_above_context
     for (int p = 0; p < 3; p++) {
