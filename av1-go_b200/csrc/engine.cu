@@ -625,7 +625,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
             // inter frames: the few units that hold intra / inter-intra blocks are mostly independent of each other -> one round
             if (k3_ctas <= 0 && L.n_inter > 0) il.ctas = std::min(L.n_k3units, k3_inter_mult * il.ctas);
         }
-        il.general = (L.n_inter > 0 || dw.fh.allow_screen_content_tools) ? 1 : 0;
+        il.kind = dw.fh.allow_screen_content_tools ? 2 : (L.n_inter > 0 ? 1 : 0);
         il.load_tile = L.n_inter > 0;
         // sync block: [n_units x u64 progress words][n_units x int unit flags][ticket, stuck flag, pad]
         const size_t sync_bytes = (sizeof(unsigned long long) + sizeof(int)) * (size_t)L.n_k3units + 4 * sizeof(int);

@@ -311,7 +311,7 @@ struct BlkCtx {
 // rate is ~91 % (ncu sm__icc_request_hit_rate), and every kilobyte of cold code inlined into the record loop showed up as lost
 // throughput when several frames share an SM (profiles/r2_k3_sweep.md).  Scalars are passed by value: taking the address of the
 // kernel's parameter struct would copy it to local memory.
-template <typename T>
+template <typename T, int KIND>
 __device__ K3_RARE_ATTR void rare_block(const TxRec r, const UnitCtx<T> uv, int bd, int pcw, int pch, int psx, int psy, int lane,
                                         const uint8_t* pal, const uint8_t* fb, uint32_t pitch) {
     const BlkCtx<T> c(r, uv, bd, pcw, pch);
@@ -328,6 +328,7 @@ __device__ K3_RARE_ATTR void rare_block(const TxRec r, const UnitCtx<T> uv, int 
             }
         return;
     }
+    if (KIND < 2) return;
     if (r.mode == TXM_INTRABC) {
         // spec 7.11.3.2 - 7.11.3.4 with use_intrabc: the reference is this frame (no filter runs on such frames), displaced by the
         // block vector; bilinear taps at 1/16 sample (the chroma of an odd luma vector sits on a half sample), rounding 3 then 11,
@@ -681,9 +682,10 @@ __device__ __forceinline__ TxRec load_rec(const TxRec* p) {
 
 // PROG (cell-by-cell hand-over between units or whole units) and PROF (phase timers) are compile-time: the record loop is bound by
 // the latency of its dependency chain, and every runtime test or dead branch in it costs throughput (profiles/r2_k3_sweep.md).
-// GEN = false is the camera-content build: the frame holds no inter-intra, inter-residual, block-copy or palette record (an intra
-// frame without screen-content tools), and those paths are compiled out of the record loop.
-template <typename T, int NW, bool PROG, bool PROF, bool GEN>
+// KIND selects which record kinds the build knows: 0 = camera-content intra frame (no inter-intra, inter-residual, block-copy or
+// palette record can occur: those paths are compiled out of the record loop), 1 = inter frame without screen-content tools
+// (adds inter-intra blends and their residuals), 2 = everything (adds palette and intra block copy).
+template <typename T, int NW, bool PROG, bool PROF, int KIND>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(IntraLaunch L) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- carve (mirrored by k3_smem_bytes)
@@ -886,9 +888,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             const TxRec r = r_next;
             if (k + nw < count) r_next = load_rec(L.recs + __ldg(L.order + first + k + nw));
             lap(8, lane == 0);   // record fetch
-            if (GEN && r.mode == TXM_INTER) {
+            if (KIND >= 1 && r.mode == TXM_INTER) {
                 if (r.flags & TXF_II) wait_local(rbar, lane == 0 ? (int)r.pal_off - first : -1, rpar, L.stuck);   // residual of an inter-intra block: after its blend
-            } else if (GEN && r.mode == TXM_INTRABC) {
+            } else if (KIND == 2 && r.mode == TXM_INTRABC) {
                 // block copy: wait until every unit the source rectangle touches is complete in the frame (whole-unit flags; the
                 // plan guarantees they come earlier in the table, so this cannot wait on a unit that waits on us)
 #ifndef K3_NO_IBC_WAIT
@@ -921,7 +923,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                     fence_acquire_gpu();
                 }
 #endif
-            } else if (!GEN || r.mode != TXM_PALETTE) {
+            } else if (KIND < 2 || r.mode != TXM_PALETTE) {
                 const int plane = r.plane;
                 const int w4 = 1 << (tx_lw(r.txsz) - 2), h4 = 1 << (tx_lh(r.txsz) - 2);
                 const int pw4 = plane ? fp.pw4[1] : fp.pw4[0], ph4 = plane ? fp.ph4[1] : fp.ph4[0];
@@ -1051,11 +1053,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                 const int plane = r.plane;
                 const int pcw = plane ? fp.cw[1] : fp.cw[0], pch = plane ? fp.ch[1] : fp.ch[0];
                 const int psx = plane ? fp.subx : 0, psy = plane ? fp.suby : 0;
-                if (GEN && (r.mode == TXM_INTER || r.mode == TXM_INTRABC || r.mode == TXM_PALETTE)) {
-                    rare_block<T>(r, uc, fp.bd, pcw, pch, psx, psy, lane, L.pal, plane == 0 ? L.frame.p[0] : (plane == 1 ? L.frame.p[1] : L.frame.p[2]),
+                if (KIND >= 1 && (r.mode == TXM_INTER || (KIND == 2 && (r.mode == TXM_INTRABC || r.mode == TXM_PALETTE)))) {
+                    rare_block<T, KIND>(r, uc, fp.bd, pcw, pch, psx, psy, lane, L.pal, plane == 0 ? L.frame.p[0] : (plane == 1 ? L.frame.p[1] : L.frame.p[2]),
                                   plane == 0 ? L.frame.pitch[0] : L.frame.pitch[1]);
                 } else {
-                    const bool ii = GEN && (r.flags & TXF_II) != 0;
+                    const bool ii = KIND >= 1 && (r.flags & TXF_II) != 0;
                     if (ii) {
                         ii_save<T>(r, uc, fp.bd, pcw, pch, sm.tile, lane);
                         __syncwarp();
@@ -1140,11 +1142,11 @@ static size_t k3_smem_bytes(int bps, int warps) {
 }
 
 template <typename F>
-static void k3_for_each_kernel(F f) {   // T x PROG x {camera, general, general + timers}
-    f(intra_unit_kernel<uint8_t, 8, false, false, false>); f(intra_unit_kernel<uint8_t, 8, false, false, true>); f(intra_unit_kernel<uint8_t, 8, false, true, true>);
-    f(intra_unit_kernel<uint8_t, 8, true, false, false>); f(intra_unit_kernel<uint8_t, 8, true, false, true>); f(intra_unit_kernel<uint8_t, 8, true, true, true>);
-    f(intra_unit_kernel<uint16_t, 8, false, false, false>); f(intra_unit_kernel<uint16_t, 8, false, false, true>); f(intra_unit_kernel<uint16_t, 8, false, true, true>);
-    f(intra_unit_kernel<uint16_t, 8, true, false, false>); f(intra_unit_kernel<uint16_t, 8, true, false, true>); f(intra_unit_kernel<uint16_t, 8, true, true, true>);
+static void k3_for_each_kernel(F f) {   // T x PROG x {camera intra, inter, everything, everything + timers}
+    f(intra_unit_kernel<uint8_t, 8, false, false, 0>); f(intra_unit_kernel<uint8_t, 8, false, false, 1>); f(intra_unit_kernel<uint8_t, 8, false, false, 2>); f(intra_unit_kernel<uint8_t, 8, false, true, 2>);
+    f(intra_unit_kernel<uint8_t, 8, true, false, 0>); f(intra_unit_kernel<uint8_t, 8, true, false, 1>); f(intra_unit_kernel<uint8_t, 8, true, false, 2>); f(intra_unit_kernel<uint8_t, 8, true, true, 2>);
+    f(intra_unit_kernel<uint16_t, 8, false, false, 0>); f(intra_unit_kernel<uint16_t, 8, false, false, 1>); f(intra_unit_kernel<uint16_t, 8, false, false, 2>); f(intra_unit_kernel<uint16_t, 8, false, true, 2>);
+    f(intra_unit_kernel<uint16_t, 8, true, false, 0>); f(intra_unit_kernel<uint16_t, 8, true, false, 1>); f(intra_unit_kernel<uint16_t, 8, true, false, 2>); f(intra_unit_kernel<uint16_t, 8, true, true, 2>);
 }
 
 static cudaError_t intra_upload_constants() {
@@ -1186,22 +1188,24 @@ cudaError_t launch_intra(const IntraLaunch& L, cudaStream_t s) {
         }
     }
     const int blocks = std::min(L.n_units, std::max(1, L.ctas));
-    const bool prof = L.prof != nullptr, prog = L.progressive != 0, gen = L.general != 0 || prof;
-    auto go = [&](auto tag_t) {
+    const bool prof = L.prof != nullptr, prog = L.progressive != 0;
+    const int kind = prof ? 2 : L.kind;
+    auto go = [&](auto tag_t, auto tag_prog) {
         using TT = decltype(tag_t);
+        constexpr bool PG = decltype(tag_prog)::value;
         const size_t sm = k3_smem_bytes((int)sizeof(TT), 8);
-        if (prog) {
-            if (prof) intra_unit_kernel<TT, 8, true, true, true><<<blocks, 256, sm, s>>>(L);
-            else if (gen) intra_unit_kernel<TT, 8, true, false, true><<<blocks, 256, sm, s>>>(L);
-            else intra_unit_kernel<TT, 8, true, false, false><<<blocks, 256, sm, s>>>(L);
-        } else {
-            if (prof) intra_unit_kernel<TT, 8, false, true, true><<<blocks, 256, sm, s>>>(L);
-            else if (gen) intra_unit_kernel<TT, 8, false, false, true><<<blocks, 256, sm, s>>>(L);
-            else intra_unit_kernel<TT, 8, false, false, false><<<blocks, 256, sm, s>>>(L);
-        }
+        if (prof) intra_unit_kernel<TT, 8, PG, true, 2><<<blocks, 256, sm, s>>>(L);
+        else if (kind == 0) intra_unit_kernel<TT, 8, PG, false, 0><<<blocks, 256, sm, s>>>(L);
+        else if (kind == 1) intra_unit_kernel<TT, 8, PG, false, 1><<<blocks, 256, sm, s>>>(L);
+        else intra_unit_kernel<TT, 8, PG, false, 2><<<blocks, 256, sm, s>>>(L);
     };
-    if (L.fp.bd == 8) go(uint8_t());
-    else go(uint16_t());
+    if (L.fp.bd == 8) {
+        if (prog) go(uint8_t(), std::true_type());
+        else go(uint8_t(), std::false_type());
+    } else {
+        if (prog) go(uint16_t(), std::true_type());
+        else go(uint16_t(), std::false_type());
+    }
     return cudaGetLastError();
 }
 

@@ -16,7 +16,8 @@ struct IntraLaunch {            // passed by value
     int ctas;                   // persistent CTAs this frame may occupy (one unit per CTA at a time)
     int load_tile;              // 1: the frame already holds inter-predicted samples (inter frame) -> bring the unit in before predicting
     int progressive;            // 1: units hand their bottom row / right column over cell by cell (uprog), 0: whole units (uflags)
-    int general;                // 1: the frame may hold inter-intra / inter-residual / block-copy / palette records (0: camera-content intra frame)
+    int kind;                   // record kinds the frame may hold: 0 camera-content intra frame, 1 inter frame without screen-content tools
+                                // (adds inter-intra blends + their residuals), 2 anything (adds palette and intra block copy)
     unsigned long long* uprog;  // device, n_units words, zeroed before launch: finished border cells of every unit (bit layout in intra.cu)
     int* uflags;                // device, n_units ints, zeroed before launch: unit done flags
     const int32_t* upos;        // device, one entry per 64x64 unit of the frame: its table index (frames with intra block copy; else null)
