@@ -87,7 +87,8 @@ struct UnitCtx {
     __device__ __forceinline__ T* cv(int p) const { return canvas + cv_off(p); }
     __device__ __forceinline__ int px(int plane, int x, int y) const {
         const int dx = x - x0(plane), dy = y - y0(plane);
-        return dy < W(plane) ? (int)canvas[cv_off(plane) + dy * cs(plane) + dx] : (int)lext[lext_off(plane) + dy - W(plane)];
+        const T* p = dy < W(plane) ? canvas + (cv_off(plane) + dy * cs(plane) + dx) : lext + (lext_off(plane) + dy - W(plane));   // one load, selected address
+        return (int)*p;
     }
 };
 
@@ -771,20 +772,20 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
             }
         }
         // inter frame: the unit's own inter-predicted samples (final since K2 ran: fetched before the neighbour wait, off the chain)
-        if (L.load_tile) {
+        if (KIND >= 1 && L.load_tile) {   // (a row per warp, a 32-bit word per lane: a row of the unit is at most 32 words)
+#pragma unroll 1
             for (int p = 0; p < (fp.mono ? 1 : 3); p++) {
                 const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
                 const int x0 = ux * W, y0 = uy * W;
-                const uint8_t* fb = L.frame.p[p];
-                const uint32_t pitch = L.frame.pitch[p];
+                const uint8_t* fb = p == 0 ? L.frame.p[0] : (p == 1 ? L.frame.p[1] : L.frame.p[2]);
+                const uint32_t pitch = p == 0 ? L.frame.pitch[0] : L.frame.pitch[1];
                 T* cv = uc.cv(p);
-                const int vw = min(W, fp.cw[p] - x0), vh = min(W, fp.ch[p] - y0);
+                const int vw = min(W, (p ? fp.cw[1] : fp.cw[0]) - x0), vh = min(W, (p ? fp.ch[1] : fp.ch[0]) - y0);
                 const int wpr = vw * (int)sizeof(T) / 4;
-                for (int i = tid; i < vh * wpr; i += nthr) {
-                    const int row = i / wpr, wi = i - row * wpr;
-                    reinterpret_cast<uint32_t*>(cv + row * cs)[wi] =
-                        __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T)) + wi);
-                }
+                if (lane < wpr)
+                    for (int row = warp; row < vh; row += nw)
+                        reinterpret_cast<uint32_t*>(cv + row * cs)[lane] =
+                            __ldcg(reinterpret_cast<const uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T)) + lane);
             }
         }
         // the first record of every warp does not depend on the neighbours either
@@ -1115,19 +1116,19 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
         __syncthreads();
         lap(5, tid == 0);   // dataflow (CTA view)
         // ---- write the unit back (coalesced 32-bit words; coded plane widths are multiples of 4 samples)
-        for (int p = 0; p < (fp.mono ? 1 : 3); p++) {
+#pragma unroll 1
+        for (int p = 0; p < (fp.mono ? 1 : 3); p++) {   // (a row per warp, a 32-bit word per lane)
             const int W = p ? CV_W1 : CV_W0, cs = p ? CV_CS1 : CV_CS0;
             const int x0 = ux * W, y0 = uy * W;
-            const int vw = min(W, fp.cw[p] - x0), vh = min(W, fp.ch[p] - y0);
-            uint8_t* fb = L.frame.p[p];
-            const uint32_t pitch = L.frame.pitch[p];
+            const int vw = min(W, (p ? fp.cw[1] : fp.cw[0]) - x0), vh = min(W, (p ? fp.ch[1] : fp.ch[0]) - y0);
+            uint8_t* fb = p == 0 ? L.frame.p[0] : (p == 1 ? L.frame.p[1] : L.frame.p[2]);
+            const uint32_t pitch = p == 0 ? L.frame.pitch[0] : L.frame.pitch[1];
             const T* cv = uc.cv(p);
             const int wpr = vw * (int)sizeof(T) / 4;
-            for (int i = tid; i < vh * wpr; i += nthr) {
-                const int row = i / wpr, wi = i - row * wpr;
-                reinterpret_cast<uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T))[wi] =
-                    reinterpret_cast<const uint32_t*>(cv + row * cs)[wi];
-            }
+            if (lane < wpr)
+                for (int row = warp; row < vh; row += nw)
+                    reinterpret_cast<uint32_t*>(fb + (size_t)(y0 + row) * pitch + (size_t)x0 * sizeof(T))[lane] =
+                        reinterpret_cast<const uint32_t*>(cv + row * cs)[lane];
         }
         __syncthreads();
         if (tid == 0) st_release(L.uflags + u, 1);   // release after the CTA barrier: cumulative over every thread's write-back stores
