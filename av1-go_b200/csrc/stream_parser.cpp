@@ -201,6 +201,19 @@ void StreamParser::motion_field_estimation() {
     fw.mfmv.assign((size_t)w8 * h8, MfMv{{0, 0}, 0});
     static const int kDivMult[32] = {0,    16384, 8192, 5461, 4096, 3276, 2730, 2340, 2048, 1820, 1638, 1489, 1365, 1260, 1170, 1092,
                                      1024, 963,   910,  862,  819,  780,  744,  712,  682,  655,  630,  606,  585,  564,  546,  528};
+    // One source = one earlier frame whose saved motion vectors are projected.  The sources are chosen first (header data only),
+    // then all of them are walked band by band in ONE parallel loop: a projected position never leaves the 8-row band of its
+    // source (MAX_OFFSET_HEIGHT = 0), so bands are independent, and inside a band the sources are applied in the order of the
+    // specification and each in raster order, so "the later projection wins" stays deterministic.
+    struct Source {
+        const FrameWork* sfw;
+        int dst_sign;
+        int roff[8];
+        int64_t rfac[8];
+        bool rok[8];
+    };
+    Source srcs[4];
+    int n_srcs = 0;
     auto project = [&](int src, int dst_sign) -> int {
         const int src_idx = fh.ref_frame_idx[src - LAST_FRAME];
         const RefHdrState& r = hp.refs[src_idx];
@@ -210,46 +223,14 @@ void StreamParser::motion_field_estimation() {
             return 0;
         const int ref_to_cur = hp.get_relative_dist(fh.order_hints[src], fh.order_hint);
         // per reference of the source frame: offset, validity and the projection factor num * Div_Mult[den] (spec 7.9.3)
-        int roff[8];
-        int64_t rfac[8];
-        bool rok[8];
+        Source& S = srcs[n_srcs++];
+        S.sfw = sfw.get();
+        S.dst_sign = dst_sign;
         for (int rf = 0; rf < 8; rf++) {
-            roff[rf] = rf > INTRA_FRAME ? hp.get_relative_dist(fh.order_hints[src], r.saved_order_hints[rf]) : 0;
-            rok[rf] = rf > INTRA_FRAME && std::abs(ref_to_cur) <= 31 && std::abs(roff[rf]) <= 31 && roff[rf] > 0;
-            rfac[rf] = rok[rf] ? (int64_t)std::max(-31, std::min(31, ref_to_cur * dst_sign)) * kDivMult[std::min(31, roff[rf])] : 0;
+            S.roff[rf] = rf > INTRA_FRAME ? hp.get_relative_dist(fh.order_hints[src], r.saved_order_hints[rf]) : 0;
+            S.rok[rf] = rf > INTRA_FRAME && std::abs(ref_to_cur) <= 31 && std::abs(S.roff[rf]) <= 31 && S.roff[rf] > 0;
+            S.rfac[rf] = S.rok[rf] ? (int64_t)std::max(-31, std::min(31, ref_to_cur * dst_sign)) * kDivMult[std::min(31, S.roff[rf])] : 0;
         }
-        // a projected position never leaves the 8-row band of its source (MAX_OFFSET_HEIGHT = 0): bands are independent and each
-        // is walked in raster order, so "the later source wins" stays deterministic
-        WorkerPool::get().parallel_for((h8 + 7) >> 3, [&](int band) {
-        for (int row8 = band * 8; row8 < std::min(h8, band * 8 + 8); row8++)
-            for (int col8 = 0; col8 < w8; col8++) {
-                const SavedMv& sm = sfw->saved_mvs[(size_t)row8 * w8 + col8];
-                if (sm.ref <= INTRA_FRAME || !rok[sm.ref]) continue;
-                const int ref_offset = roff[sm.ref];
-                const int64_t fac = rfac[sm.ref];
-                int proj[2];
-                const int mvc[2] = {sm.mv.row, sm.mv.col};
-                for (int i = 0; i < 2; i++) {
-                    const int64_t v = (int64_t)mvc[i] * fac;
-                    const int64_t sc = v >= 0 ? (v + 8192) >> 14 : -((-v + 8192) >> 14);
-                    proj[i] = (int)std::max<int64_t>(-(1 << 14) + 1, std::min<int64_t>((1 << 14) - 1, sc));
-                }
-                auto pos = [&](int v8, int delta, int max8, int max_off8, bool& ok) {
-                    const int base8 = (v8 >> 3) << 3;
-                    const int off8 = delta >= 0 ? (delta >> 6) : -((-delta) >> 6);
-                    v8 += dst_sign * off8;
-                    if (v8 < 0 || v8 >= max8 || v8 < base8 - max_off8 || v8 >= base8 + 8 + max_off8) ok = false;
-                    return v8;
-                };
-                bool ok = true;
-                const int py = pos(row8, proj[0], h8, 0, ok);
-                const int px = pos(col8, proj[1], w8, 8, ok);
-                if (!ok) continue;
-                MfMv& m = fw.mfmv[(size_t)py * w8 + px];
-                m.mv = sm.mv;
-                m.ref_offset = (int8_t)ref_offset;
-            }
-        });
         return 1;
     };
     const int last_idx = fh.ref_frame_idx[0];
@@ -260,6 +241,41 @@ void StreamParser::motion_field_estimation() {
     if (hp.get_relative_dist(fh.order_hints[ALTREF2_FRAME], fh.order_hint) > 0 && project(ALTREF2_FRAME, 1)) ref_stamp--;
     if (hp.get_relative_dist(fh.order_hints[ALTREF_FRAME], fh.order_hint) > 0 && ref_stamp >= 0 && project(ALTREF_FRAME, 1)) ref_stamp--;
     if (ref_stamp >= 0) project(LAST2_FRAME, -1);
+    if (!n_srcs) return;
+    WorkerPool::get().parallel_for((h8 + 7) >> 3, [&](int band) {
+        for (int si = 0; si < n_srcs; si++) {
+            const Source& S = srcs[si];
+            const int dst_sign = S.dst_sign;
+            for (int row8 = band * 8; row8 < std::min(h8, band * 8 + 8); row8++)
+                for (int col8 = 0; col8 < w8; col8++) {
+                    const SavedMv& sm = S.sfw->saved_mvs[(size_t)row8 * w8 + col8];
+                    if (sm.ref <= INTRA_FRAME || !S.rok[sm.ref]) continue;
+                    const int ref_offset = S.roff[sm.ref];
+                    const int64_t fac = S.rfac[sm.ref];
+                    int proj[2];
+                    const int mvc[2] = {sm.mv.row, sm.mv.col};
+                    for (int i = 0; i < 2; i++) {
+                        const int64_t v = (int64_t)mvc[i] * fac;
+                        const int64_t sc = v >= 0 ? (v + 8192) >> 14 : -((-v + 8192) >> 14);
+                        proj[i] = (int)std::max<int64_t>(-(1 << 14) + 1, std::min<int64_t>((1 << 14) - 1, sc));
+                    }
+                    auto pos = [&](int v8, int delta, int max8, int max_off8, bool& ok) {
+                        const int base8 = (v8 >> 3) << 3;
+                        const int off8 = delta >= 0 ? (delta >> 6) : -((-delta) >> 6);
+                        v8 += dst_sign * off8;
+                        if (v8 < 0 || v8 >= max8 || v8 < base8 - max_off8 || v8 >= base8 + 8 + max_off8) ok = false;
+                        return v8;
+                    };
+                    bool ok = true;
+                    const int py = pos(row8, proj[0], h8, 0, ok);
+                    const int px = pos(col8, proj[1], w8, 8, ok);
+                    if (!ok) continue;
+                    MfMv& m = fw.mfmv[(size_t)py * w8 + px];
+                    m.mv = sm.mv;
+                    m.ref_offset = (int8_t)ref_offset;
+                }
+        }
+    });
 }
 
 int StreamParser::tile_group(const uint8_t* payload, size_t size, size_t offset) {
