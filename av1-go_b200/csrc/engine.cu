@@ -261,14 +261,27 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     if (L.n_recs) memcpy(h + L.recs, fw.tx.data(), sizeof(TxRec) * L.n_recs);
     if (L.n_coefs) memcpy(h + L.coefs, fw.coefs.data(), sizeof(uint32_t) * L.n_coefs);
     {   // K1 order: coded transform blocks, those of at most 16x16 (itx_small_kernel) first, the 32- and 64-point ones after them
+        // Inside each group the blocks are ordered by (transform size, transform type), stable in decode order: every size / type pair
+        // is its own unrolled butterfly network, and warps that run side by side on an SM should be fetching the same one (ncu on
+        // the 32/64-point kernel in decode order: instruction cache hit rate 65 %, 6.4 warp-cycles of fetch stall per instruction).
         uint32_t* ord = (uint32_t*)(h + L.order);
-        int lo = 0, hi = L.n_order;
+        static const bool nosort = getenv("AV1R_K1_NOSORT") != nullptr;   // (A/B switch of the experiment)
+        constexpr int NKEY = TX_SIZES_ALL * 17;
+        uint32_t cnt[2][NKEY + 1];
+        memset(cnt, 0, sizeof(cnt));
+        auto grp = [&](const TxRec& r) { return (kTxW[r.txsz] <= 16 && kTxH[r.txsz] <= 16) ? 0 : 1; };
+        auto key = [&](const TxRec& r) { return nosort ? 0 : (int)r.txsz * 17 + std::min<int>(r.txtp, 16); };
+        for (int i = 0; i < L.n_recs; i++)
+            if (fw.tx[i].eob > 0) cnt[grp(fw.tx[i])][key(fw.tx[i]) + 1]++;
+        for (int g = 0; g < 2; g++)
+            for (int q = 0; q < NKEY; q++) cnt[g][q + 1] += cnt[g][q];
+        const int n_small = (int)cnt[0][NKEY];
         for (int i = 0; i < L.n_recs; i++)
             if (fw.tx[i].eob > 0) {
-                if (kTxW[fw.tx[i].txsz] <= 16 && kTxH[fw.tx[i].txsz] <= 16) ord[lo++] = (uint32_t)i;
-                else ord[--hi] = (uint32_t)i;
+                const int g = grp(fw.tx[i]);
+                ord[(g ? n_small : 0) + cnt[g][key(fw.tx[i])]++] = (uint32_t)i;
             }
-        dw.lay.n_order_small = lo;
+        dw.lay.n_order_small = n_small;
     }
     if (L.lf_device) {
         if (L.n_lfblk) memcpy(h + L.lfblk, fw.lf_blocks.data(), sizeof(LfBlk) * L.n_lfblk);
@@ -286,19 +299,49 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
     if (L.n_inter) memcpy(h + L.inter, fw.inter.data(), sizeof(InterBlk) * L.n_inter);
     {   // quadrant list: record index | quadrant << 28 (bit 0 of the quadrant = right half, bit 1 = bottom half); the items of
         // small blocks (at most 16x16 luma samples) come first: K2 runs them as two-warp CTAs
+        // Inside each of the two groups the items are ordered by *code path* (block shape, warped, compound, masked, OBMC), stable
+        // in decode order: K2 is ~100 KB of straight-line filter code, a CTA walks ~40 KB of it, and the small-block kernel spent 5
+        // warp-cycles per issued instruction waiting for instruction fetch (ncu stalled_no_instruction) when neighbouring CTAs --
+        // resident on an SM together -- each took a different path through it.  Blocks are independent, any order is valid.
         uint32_t* it = (uint32_t*)(h + L.itiles);
+        auto path_key = [](const InterBlk& b) -> int {
+            const int lw = 31 - __builtin_clz((unsigned)b.w), lh = 31 - __builtin_clz((unsigned)b.h);    // 2 .. 7
+            const int warped = b.warp[0] >= 0 || b.warp[1] >= 0;
+            const int comp = b.ref[1] >= 0;
+            const int masked = comp && (b.comp_type == COMPOUND_WEDGE || b.comp_type == COMPOUND_DIFFWTD);
+            const int obmc = (b.obmc_above + b.obmc_left) > 0;
+            static const bool off = getenv("AV1R_K2_NOSORT") != nullptr;   // (A/B switch of the experiment)
+            if (off) return 0;
+            return ((((lw - 2) * 6 + (lh - 2)) * 2 + warped) * 2 + comp) * 2 * 2 + masked * 2 + obmc;   // < 36 * 16
+        };
+        constexpr int NKEY = 36 * 16;
         int k = 0;
-        for (int i = 0; i < L.n_inter; i++) {
-            const InterBlk& b = fw.inter[i];
-            if (b.w <= 16 && b.h <= 16) it[k++] = (uint32_t)i;
-        }
-        dw.lay.n_itiles_small = k;
-        for (int i = 0; i < L.n_inter; i++) {
-            const InterBlk& b = fw.inter[i];
-            if (b.w <= 16 && b.h <= 16) continue;
-            const int qx = (b.w + 63) >> 6, qy = (b.h + 63) >> 6;
-            for (int y = 0; y < qy; y++)
-                for (int x = 0; x < qx; x++) it[k++] = (uint32_t)i | ((uint32_t)(y * 2 + x) << 28);
+        for (int pass = 0; pass < 2; pass++) {   // small blocks (at most 16x16), then the rest
+            uint32_t cnt[NKEY + 1] = {0};
+            for (int i = 0; i < L.n_inter; i++) {
+                const InterBlk& b = fw.inter[i];
+                if ((b.w <= 16 && b.h <= 16) != (pass == 0)) continue;
+                cnt[path_key(b) + 1] += pass == 0 ? 1 : ((b.w + 63) >> 6) * ((b.h + 63) >> 6);
+            }
+            for (int q = 0; q < NKEY; q++) cnt[q + 1] += cnt[q];
+            const int base = k;
+            for (int i = 0; i < L.n_inter; i++) {
+                const InterBlk& b = fw.inter[i];
+                if ((b.w <= 16 && b.h <= 16) != (pass == 0)) continue;
+                uint32_t& pos = cnt[path_key(b)];
+                if (pass == 0) {
+                    it[base + pos++] = (uint32_t)i;
+                    k++;
+                } else {
+                    const int qx = (b.w + 63) >> 6, qy = (b.h + 63) >> 6;
+                    for (int y = 0; y < qy; y++)
+                        for (int x = 0; x < qx; x++) {
+                            it[base + pos++] = (uint32_t)i | ((uint32_t)(y * 2 + x) << 28);
+                            k++;
+                        }
+                }
+            }
+            if (pass == 0) dw.lay.n_itiles_small = k;
         }
     }
     if (L.n_obmc) memcpy(h + L.obmc, fw.obmc.data(), sizeof(ObmcNb) * L.n_obmc);
