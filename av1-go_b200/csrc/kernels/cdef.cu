@@ -111,7 +111,9 @@ __device__ __forceinline__ int cdef_pixel(const int16_t* tile, int pos, const Cd
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) cdef_kernel(CdefLaunch L) {
+// (six CTAs per SM: 40 registers with a few bytes of spill beat 60 registers at four CTAs by 5 % -- the kernel waits on its tile
+// loads, profiles/r2_work_order.md)
+__global__ void __launch_bounds__(256, 6) cdef_kernel(CdefLaunch L) {
     __shared__ __align__(16) int16_t s_luma[CDEF_LT * CDEF_LS];
     __shared__ __align__(16) int16_t s_chroma[2][CDEF_LT * CDEF_LS];   // sized for 4:4:4
     __shared__ uint8_t s_dir[64], s_skip[64];
