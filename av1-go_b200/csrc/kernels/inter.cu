@@ -502,6 +502,7 @@ __device__ void warp_tile(const uint8_t* ref, uint32_t pitch, int lastx, int las
 }
 
 template <typename T, int NT>
+// (8 / 12 CTAs per SM; 10 and 12 / 8 and 16 were measured and change nothing: the kernel is not occupancy-limited, profiles/r2_work_order.md)
 __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 12) inter_pred_kernel(InterLaunch L, int first_item) {
     __shared__ InterSmem sm;
     const uint32_t item = L.tiles[first_item + blockIdx.x];
