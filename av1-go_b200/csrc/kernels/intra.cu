@@ -396,6 +396,11 @@ __device__ K3_RARE_ATTR void filter_intra_block(const TxRec r, const UnitCtx<T> 
     {
         const int w4 = w >> 2, h2 = h >> 1;
         const int fm = r.fi_mode;
+        // a lane always computes the same sample of a 4x2 sub-block (t strides by 32, o = t & 7): its seven taps are loaded once;
+        // indexed by o inside the loop they were an 8-way divergent constant-memory access per tap and iteration
+        int tap[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) tap[i] = c_fi_taps[fm][lane & 7][i];
         for (int d = 0; d < h2 + w4 - 1; d++) {
             const int i2_lo = max(0, d - (w4 - 1)), i2_hi = min(h2 - 1, d);
             const int nblk = i2_hi - i2_lo + 1;
@@ -417,7 +422,7 @@ __device__ K3_RARE_ATTR void filter_intra_block(const TxRec r, const UnitCtx<T> 
                 }
                 int pr = 0;
 #pragma unroll
-                for (int i = 0; i < 7; i++) pr += c_fi_taps[fm][o][i] * p[i];
+                for (int i = 0; i < 7; i++) pr += tap[i] * p[i];
                 const int v = pr >= 0 ? (pr + 8) >> 4 : -((-pr + 8) >> 4);
                 pt[((i2 << 1) + (o >> 2)) * w + (j4 << 2) + (o & 3)] = (int16_t)min(max(v, 0), pixmax);
             }
@@ -428,7 +433,8 @@ __device__ K3_RARE_ATTR void filter_intra_block(const TxRec r, const UnitCtx<T> 
 }
 
 template <typename T>
-__device__ __forceinline__ void intra_pred(const TxRec& r, const UnitCtx<T>& uv, const DevFrameParams& fp, WarpScratch& sm, int lane) {
+__device__ __forceinline__ void intra_pred(const TxRec& r, const UnitCtx<T>& uv, const DevFrameParams& fp, WarpScratch& sm, int lane,
+                                           const uint8_t* smw) {
     const int bd = fp.bd;
     // (two uniform parameter loads and a select instead of a register-indexed constant load: planes 1 and 2 have the same size)
     const BlkCtx<T> c(r, uv, bd, r.plane ? fp.cw[1] : fp.cw[0], r.plane ? fp.ch[1] : fp.ch[0]);
@@ -570,8 +576,10 @@ __device__ __forceinline__ void intra_pred(const TxRec& r, const UnitCtx<T>& uv,
         return;
     }
     if (mode == SMOOTH_PRED || mode == SMOOTH_V_PRED || mode == SMOOTH_H_PRED) {
-        const uint8_t* ww = c_sm_weights + (w - 4);
-        const uint8_t* wh = c_sm_weights + (h - 4);
+        // (weights from the CTA's shared-memory copy: indexed per lane, the constant-memory table was read with up to 8 different
+        // addresses per warp and load, i.e. serialised)
+        const uint8_t* ww = smw + (w - 4);
+        const uint8_t* wh = smw + (h - 4);
         const int bl = left[h - 1], tr = above[w - 1];
         for (int idx = lane; idx < w * h; idx += 32) {
             const int i = idx >> lw, j = idx & (w - 1);
@@ -703,6 +711,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
     const DevFrameParams& fp = L.fp;
     const uint32_t bar = smem_u32(&us->bar);
     constexpr uint32_t unit_bytes = RES_ELEMS * sizeof(int16_t);
+    __shared__ uint8_t s_smw[128];   // smooth-predictor weights (see intra_pred)
+    if (tid < (int)sizeof(c_sm_weights)) s_smw[tid] = c_sm_weights[tid];
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1063,7 +1073,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) intra_unit_kernel(In
                         ii_save<T>(r, uc, fp.bd, pcw, pch, sm.tile, lane);
                         __syncwarp();
                     }
-                    intra_pred<T>(r, uc, fp, sm, lane);
+                    intra_pred<T>(r, uc, fp, sm, lane, s_smw);
                     if (ii) {
                         __syncwarp();
                         ii_blend<T>(r, uc, fp.bd, pcw, pch, psx, psy, sm.tile, L.wedge_master, lane);

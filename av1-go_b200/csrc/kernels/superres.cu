@@ -16,7 +16,9 @@
 
 namespace av1r {
 
-__constant__ int16_t c_upscale_filter[64][8];
+// (global memory, read as one 128-bit row per sample: neighbouring samples have different phases, and a constant-memory table
+// indexed per lane is read one address at a time)
+__device__ __align__(16) int16_t d_upscale_filter[64][8];
 static bool g_sr_const_loaded[64] = {false};
 
 template <typename T>
@@ -29,9 +31,12 @@ __global__ void __launch_bounds__(256) superres_kernel(SuperresLaunch L) {
     const int src_px = src_x >> 14, sub = (src_x & ((1 << 14) - 1)) >> 8;
     const int max_x = L.src_cw[plane] - 1;
     const T* src = reinterpret_cast<const T*>(L.src.p[plane] + (size_t)y * L.src.pitch[plane]);
+    const int4 fq = __ldg(reinterpret_cast<const int4*>(d_upscale_filter[sub]));
+    const int f[8] = {(int)(short)(fq.x & 0xffff), fq.x >> 16, (int)(short)(fq.y & 0xffff), fq.y >> 16,
+                      (int)(short)(fq.z & 0xffff), fq.z >> 16, (int)(short)(fq.w & 0xffff), fq.w >> 16};
     int sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) sum += (int)src[min(max(src_px + k - 3, 0), max_x)] * c_upscale_filter[sub][k];
+    for (int k = 0; k < 8; k++) sum += (int)src[min(max(src_px + k - 3, 0), max_x)] * f[k];
     const int pixmax = (1 << L.bd) - 1;
     reinterpret_cast<T*>(L.dst.p[plane] + (size_t)y * L.dst.pitch[plane])[x] = (T)min(max((sum + 64) >> 7, 0), pixmax);
 }
@@ -41,7 +46,7 @@ cudaError_t launch_superres(const SuperresLaunch& L, cudaStream_t s) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (!(dev < 64 && g_sr_const_loaded[dev])) {
-        if ((e = cudaMemcpyToSymbol(c_upscale_filter, av1t_upscale_filter, sizeof(av1t_upscale_filter))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(d_upscale_filter, av1t_upscale_filter, sizeof(av1t_upscale_filter))) != cudaSuccess) return e;
         if (dev < 64) g_sr_const_loaded[dev] = true;
     }
     // chroma planes are at most as large as luma: the grid is sized for luma and chroma CTAs outside their plane exit at once
