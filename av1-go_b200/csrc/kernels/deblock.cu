@@ -154,17 +154,19 @@ __global__ void __launch_bounds__(256) deblock_kernel(LfLaunch L) {
 }
 
 // ---- edge classification on the device (what the host pre-pass build_loopfilter_edges computes, stream_parser.cpp) -----------
-__constant__ uint8_t c_lf_txw[TX_SIZES_ALL] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
-__constant__ uint8_t c_lf_txh[TX_SIZES_ALL] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
-__constant__ uint8_t c_lf_bw[BLOCK_SIZES_ALL] = {4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64, 128, 128, 4, 16, 8, 32, 16, 64};
-__constant__ uint8_t c_lf_bh[BLOCK_SIZES_ALL] = {4, 8, 4, 8, 16, 8, 16, 32, 16, 32, 64, 32, 64, 128, 64, 128, 16, 4, 32, 8, 64, 16};
+// Width / height of a transform size and of a block size as shifts of packed immediates (log2 - 2, three bits per entry): these
+// are looked up per thread with a different index in every lane, which a constant-memory table serves one address at a time.
+__device__ __forceinline__ int lf_txw(int t) { return 4 << (int)((0x1132846d2244688ull >> (3 * t)) & 7); }
+__device__ __forceinline__ int lf_txh(int t) { return 4 << (int)((0xa161389940c688ull >> (3 * t)) & 7); }
+__device__ __forceinline__ int lf_bw(int b) { return 4 << (b < 21 ? (int)((0x2650b648db491240ull >> (3 * b)) & 7) : 4); }   // BLOCK_64X16 is entry 21
+__device__ __forceinline__ int lf_bh(int b) { return 4 << (b < 21 ? (int)((0x42c2b2c71a68a208ull >> (3 * b)) & 7) : 2); }
 
 // one warp per block: its mi cells (clipped to the frame) get the block's index
 __global__ void __launch_bounds__(256) lf_scatter_kernel(const LfBlk* __restrict__ blks, int n, uint32_t* __restrict__ mi_blk, int mi_cols, int mi_rows) {
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= n) return;
     const LfBlk b = blks[wid];
-    const int w4 = c_lf_bw[b.bsize] >> 2, h4 = c_lf_bh[b.bsize] >> 2;
+    const int w4 = lf_bw(b.bsize) >> 2, h4 = lf_bh(b.bsize) >> 2;
     const int cw = min(w4, mi_cols - b.mi_col), ch = min(h4, mi_rows - b.mi_row);
     const int lw = 31 - __clz(w4);
     for (int i = lane; i < (h4 << lw); i += 32) {
@@ -193,8 +195,8 @@ __global__ void __launch_bounds__(256) lf_classify_kernel(LfClassify L) {
         const int max_len = plane ? 8 : 16;
         const int li0 = plane == 0 ? 0 : plane + 1, li1 = plane == 0 ? 1 : plane + 1;
         const int txsz = lf_tx[idx];
-        const int txw = c_lf_txw[txsz], txh = c_lf_txh[txsz];
-        const int bwp = max(4, c_lf_bw[b.bsize] >> sx), bhp = max(4, c_lf_bh[b.bsize] >> sy);
+        const int txw = lf_txw(txsz), txh = lf_txh(txsz);
+        const int bwp = max(4, lf_bw(b.bsize) >> sx), bhp = max(4, lf_bh(b.bsize) >> sy);
         const int xp = c4 * 4, yp = r4 * 4;
         if (c4 > 0 && (xp & (txw - 1)) == 0 && (b.filt_inside || (xp & (bwp - 1)) == 0)) {
             int lvl = b.lvl[li0];
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(256) lf_classify_kernel(LfClassify L) {
                 lvl = L.blks[L.mi_blk[(size_t)mrow * mi_cols + pcol]].lvl[li0];
             }
             if (lvl) {
-                e.len_v = (uint8_t)min(max_len, min((int)c_lf_txw[lf_tx[idx - 1]], txw));
+                e.len_v = (uint8_t)min(max_len, min(lf_txw(lf_tx[idx - 1]), txw));
                 e.lvl_v = (uint8_t)lvl;
             }
         }
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) lf_classify_kernel(LfClassify L) {
                 lvl = L.blks[L.mi_blk[(size_t)prow * mi_cols + mcol]].lvl[li1];
             }
             if (lvl) {
-                e.len_h = (uint8_t)min(max_len, min((int)c_lf_txh[lf_tx[idx - pw4]], txh));
+                e.len_h = (uint8_t)min(max_len, min(lf_txh(lf_tx[idx - pw4]), txh));
                 e.lvl_h = (uint8_t)lvl;
             }
         }
