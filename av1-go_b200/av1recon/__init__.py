@@ -269,6 +269,20 @@ class Clip:
             raise RuntimeError(f"av1r_clip_decode -> {rc}: {self.dec.error()}")
         return ms.value, [tuple(cks[3 * i:3 * i + 3]) for i in range(n.value)]
 
+    def decode_passes(self, passes):
+        """`passes` replays back to back inside one fenced region -> (device_ms of all passes, checksums of the first pass); the
+        library checks that every later pass reproduces them."""
+        cap = int(self.info.frames_shown) + 4
+        cks = (C.c_uint64 * (3 * cap))()
+        n = C.c_int(0)
+        ms = C.c_float(0)
+        f = self.dec.l.av1r_clip_decode_passes
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        rc = f(self.dec.ctx, self.h, int(passes), cks, cap, C.byref(n), C.byref(ms))
+        if rc:
+            raise RuntimeError(f"av1r_clip_decode_passes -> {rc}: {self.dec.error()}")
+        return ms.value, [tuple(cks[3 * i:3 * i + 3]) for i in range(n.value)]
+
     def profile(self):
         st = StageTimes()
         rc = self.dec.l.av1r_clip_profile(self.dec.ctx, self.h, C.byref(st))

@@ -270,7 +270,12 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
         uint32_t cnt[2][NKEY + 1];
         memset(cnt, 0, sizeof(cnt));
         auto grp = [&](const TxRec& r) { return (kTxW[r.txsz] <= 16 && kTxH[r.txsz] <= 16) ? 0 : 1; };
-        auto key = [&](const TxRec& r) { return nosort ? 0 : (int)r.txsz * 17 + std::min<int>(r.txtp, 16); };
+        // Largest transforms first: a kernel ends with its last CTAs, so the expensive items must not be the ones that start last.
+        static const bool asc = getenv("AV1R_K1_ASC") != nullptr;         // (A/B switch: the ascending order of the first version)
+        auto key = [&](const TxRec& r) {
+            const int k = (int)r.txsz * 17 + std::min<int>(r.txtp, 16);
+            return nosort ? 0 : (asc ? k : NKEY - 1 - k);
+        };
         for (int i = 0; i < L.n_recs; i++)
             if (fw.tx[i].eob > 0) cnt[grp(fw.tx[i])][key(fw.tx[i]) + 1]++;
         for (int g = 0; g < 2; g++)
@@ -312,7 +317,11 @@ static void fill_arena(const FrameWork& fw, DevWork& dw, uint8_t* h) {
             const int obmc = (b.obmc_above + b.obmc_left) > 0;
             static const bool off = getenv("AV1R_K2_NOSORT") != nullptr;   // (A/B switch of the experiment)
             if (off) return 0;
-            return ((((lw - 2) * 6 + (lh - 2)) * 2 + warped) * 2 + comp) * 2 * 2 + masked * 2 + obmc;   // < 36 * 16
+            // The most expensive paths get the lowest keys (large, warped, compound blocks first): a 64x64 compound warped
+            // quadrant is ~100 us of work for its CTA on a full SM, and a kernel whose heaviest CTAs start last ends on them.
+            static const bool asc = getenv("AV1R_K2_ASC") != nullptr;       // (A/B switch: the ascending order of the first version)
+            const int k = ((((lw - 2) * 6 + (lh - 2)) * 2 + warped) * 2 + comp) * 2 * 2 + masked * 2 + obmc;   // < 36 * 16
+            return asc ? k : 36 * 16 - 1 - k;
         };
         constexpr int NKEY = 36 * 16;
         int k = 0;
@@ -393,6 +402,8 @@ struct FrameSlot {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t fg_ev = nullptr;   // film-grain templates of this slot's frame are ready (prepared on the side stream)
     bool fg_prepared = false;
+    cudaStream_t aux = nullptr;    // second stream of this slot's frame: the small-block K2 launch runs beside the large-block one
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     PinBuf staging;
     DevBuf arena;        // submit path: the frame's work-lists
     DevBuf residual;
@@ -471,6 +482,7 @@ struct EngineImpl {
     StreamParser sp;
     bool opened = false;
     std::vector<cudaStream_t> streams;
+    std::vector<cudaStream_t> aux_streams;   // one per stream (K2 fork)
     cudaStream_t side = nullptr;          // film-grain template preparation runs here, ahead of the frame it belongs to
     std::vector<std::unique_ptr<FrameSlot>> slots;
     int next_slot = 0, next_stream = 0;
@@ -605,6 +617,29 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     if (tm) tm->begin(st);
     CK(launch_itx(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, L.n_order_small, (const uint32_t*)(d_arena + L.coefs), res, fp, st));
     if (tm) tm->end(AV1R_ST_ITX, (L.n_order_small > 0) + (L.n_order > L.n_order_small), st);
+    // Deblocking edge classification reads work-lists only: it is queued here, *before* the stream waits for the reference frames,
+    // so that it runs while they are still being produced instead of sitting on the frame-to-frame dependency chain.
+    const bool lf_run = dw.lf_on && (cfg.inloop_filters & 1);
+    LfEdge* lf_edges_dev[3] = {nullptr, nullptr, nullptr};
+    if (lf_run && L.lf_device) {
+        // block list -> per-mi block index -> LfEdge planes (slot scratch)
+        size_t off[4], o = align_up((size_t)fp.mi_cols * fp.mi_rows * sizeof(uint32_t), 256);
+        for (int p = 0; p < 3; p++) { off[p] = o; o += align_up((size_t)fp.pw4[p] * fp.ph4[p] * sizeof(LfEdge), 256); }
+        { int e_ = ensure_slots(&FrameSlot::lfscratch, s, o, hw_lf); if (e_) return e_; }
+        LfClassify lc;
+        lc.blks = (const LfBlk*)(d_arena + L.lfblk);
+        lc.n_blks = L.n_lfblk;
+        lc.mi_blk = (uint32_t*)s.lfscratch.p;
+        for (int p = 0; p < 3; p++) {
+            lc.lf_tx[p] = d_arena + L.lftx[p];
+            lc.edges[p] = (LfEdge*)(s.lfscratch.p + off[p]);
+            lc.plane_on[p] = dw.lf_plane_on[p];
+            lf_edges_dev[p] = lc.edges[p];
+        }
+        lc.fp = fp;
+        CK(launch_lf_classify(lc, st));
+        if (tm) tm->end(AV1R_ST_DEBLOCK, 2, st);
+    }
     EP_ADD(9, t_h);
     t_h = EP_T();
     if (L.n_inter > 0) {
@@ -643,7 +678,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.mask_pitch = (uint32_t)align_up((size_t)fp.cw[0], 256);
         { int e_ = ensure_slots(&FrameSlot::diffmask, s, (size_t)xl.mask_pitch * fp.ch[0], hw_mask); if (e_) return e_; }
         xl.mask = s.diffmask.p;
-        CK(launch_inter(xl, st));
+        // (the stage profile keeps the two launches in sequence on one stream so that their times add up)
+        static const bool no_fork = getenv("AV1R_K2_NOFORK") != nullptr;   // (A/B switch)
+        CK(launch_inter(xl, st, (tm || no_fork) ? nullptr : s.aux, s.fork_ev, s.join_ev));
         if (tm) tm->end(AV1R_ST_INTER, (L.n_itiles_small > 0) + (L.n_itiles > L.n_itiles_small), st);
         CK(launch_inter_residual(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
         if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
@@ -711,33 +748,14 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     EP_ADD(11, t_h);
     t_h = EP_T();
     std::shared_ptr<DevFrameBuf> cur = recon;
-    if (dw.lf_on && (cfg.inloop_filters & 1)) {
+    if (lf_run) {
         LfLaunch ll;
         ll.frame = cur->pl;
         ll.fp = fp;
-        if (L.lf_device) {
-            // classify the edges on the device: block list -> per-mi block index -> LfEdge planes (slot scratch)
-            size_t off[4], o = align_up((size_t)fp.mi_cols * fp.mi_rows * sizeof(uint32_t), 256);
-            for (int p = 0; p < 3; p++) { off[p] = o; o += align_up((size_t)fp.pw4[p] * fp.ph4[p] * sizeof(LfEdge), 256); }
-            { int e_ = ensure_slots(&FrameSlot::lfscratch, s, o, hw_lf); if (e_) return e_; }
-            LfClassify lc;
-            lc.blks = (const LfBlk*)(d_arena + L.lfblk);
-            lc.n_blks = L.n_lfblk;
-            lc.mi_blk = (uint32_t*)s.lfscratch.p;
-            for (int p = 0; p < 3; p++) {
-                lc.lf_tx[p] = d_arena + L.lftx[p];
-                lc.edges[p] = (LfEdge*)(s.lfscratch.p + off[p]);
-                lc.plane_on[p] = dw.lf_plane_on[p];
-                ll.edges[p] = lc.edges[p];
-            }
-            lc.fp = fp;
-            CK(launch_lf_classify(lc, st));
-        } else {
-            for (int p = 0; p < 3; p++) ll.edges[p] = (const LfEdge*)(d_arena + L.lf[p]);
-        }
+        for (int p = 0; p < 3; p++) ll.edges[p] = L.lf_device ? lf_edges_dev[p] : (const LfEdge*)(d_arena + L.lf[p]);
         for (int p = 0; p < 3; p++) ll.plane_on[p] = dw.lf_plane_on[p];
         CK(launch_deblock(ll, st));
-        if (tm) tm->end(AV1R_ST_DEBLOCK, L.lf_device ? 4 : 2, st);
+        if (tm) tm->end(AV1R_ST_DEBLOCK, 2, st);
     }
     EP_ADD(12, t_h);
     t_h = EP_T();
@@ -923,6 +941,7 @@ int EngineImpl::acquire_slot(int& slot_idx) {
     int rc = wait_slot(s);
     if (rc) return rc;
     s.stream = streams[next_stream];
+    s.aux = aux_streams[next_stream];
     next_stream = (next_stream + 1) % (int)streams.size();
     return 0;
 }
@@ -1126,6 +1145,8 @@ Engine::~Engine() {
             if (s->ev0) cudaEventDestroy(s->ev0);
             if (s->ev1) cudaEventDestroy(s->ev1);
             if (s->fg_ev) cudaEventDestroy(s->fg_ev);
+            if (s->fork_ev) cudaEventDestroy(s->fork_ev);
+            if (s->join_ev) cudaEventDestroy(s->join_ev);
         }
         impl_->slots.clear();
         impl_->pending.clear();
@@ -1133,6 +1154,7 @@ Engine::~Engine() {
         impl_->pool.clear();
         for (auto& r : impl_->main_refs.refs) r.reset();
         for (auto st : impl_->streams) cudaStreamDestroy(st);
+        for (auto st : impl_->aux_streams) cudaStreamDestroy(st);
         if (impl_->side) cudaStreamDestroy(impl_->side);
     }
     delete impl_;
@@ -1161,12 +1183,16 @@ int Engine::open(const av1r_config& cfg) {
     CK(cudaSetDevice(cfg.device));
     E.streams.resize(E.cfg.streams);
     for (auto& st : E.streams) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    E.aux_streams.resize(E.cfg.streams);
+    for (auto& st : E.aux_streams) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&E.side, cudaStreamNonBlocking));
     for (int i = 0; i < E.cfg.frames_in_flight; i++) {
         auto s = std::make_unique<FrameSlot>();
         CK(cudaEventCreate(&s->ev0));
         CK(cudaEventCreate(&s->ev1));
         CK(cudaEventCreateWithFlags(&s->fg_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
         E.slots.push_back(std::move(s));
     }
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));
@@ -1917,8 +1943,16 @@ static int replay(EngineImpl& E, av1r_clip* clip) {
 }
 
 int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, float* device_ms) {
+    return clip_decode_passes(clip, 1, cks, cap, n_frames, device_ms);
+}
+
+// `passes` replays of the clip enqueued back to back between ONE pair of fencing events: pass k + 1's first key frames start while
+// pass k's last frames drain, as consecutive GOPs of a long file do in the streaming path (slots, frame buffers and reference events
+// are recycled exactly as there).  Every pass must reproduce the digests of the first one.
+int Engine::clip_decode_passes(av1r_clip* clip, int passes, uint64_t* cks, int cap, int* n_frames, float* device_ms) {
     EngineImpl& E = *impl_;
     std::string& err = E.err;
+    if (passes < 1) return AV1R_EINVAL;
     cudaSetDevice(E.cfg.device);
     int rc = flush();
     if (rc) return rc;
@@ -1938,8 +1972,10 @@ int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, 
     // fence: every stream starts after e0 (recorded on stream 0)
     CK(cudaEventRecord(e0, E.streams[0]));
     for (size_t i = 1; i < E.streams.size(); i++) CK(cudaStreamWaitEvent(E.streams[i], e0, 0));
-    rc = replay(E, clip);
-    if (rc) return rc;
+    for (int k = 0; k < passes; k++) {
+        rc = replay(E, clip);
+        if (rc) return rc;
+    }
     for (size_t i = 1; i < E.streams.size(); i++) {
         CK(cudaEventRecord(done[i], E.streams[i]));
         CK(cudaStreamWaitEvent(E.streams[0], done[i], 0));
@@ -1949,12 +1985,22 @@ int Engine::clip_decode(av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, 
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     if (device_ms) *device_ms = ms;
-    int k = 0;
     for (auto& p : E.pending) {
         rc = E.finish_pending(p);
         if (rc) return rc;
-        if (cks && k < cap) memcpy(cks + 3 * k, p.res.checksum, 24);
-        k++;
+    }
+    const size_t per_pass = E.pending.size() / (size_t)passes;
+    int k = 0;
+    for (size_t i = 0; i < E.pending.size(); i++) {
+        const auto& p = E.pending[i];
+        if (i < per_pass) {
+            if (cks && k < cap) memcpy(cks + 3 * k, p.res.checksum, 24);
+            k++;
+        } else if (memcmp(p.res.checksum, E.pending[i % per_pass].res.checksum, 24) != 0) {
+            err = "clip replay: a later pass produced different digests than the first one (non-deterministic reconstruction)";
+            E.pending.clear();
+            return AV1R_EIO;
+        }
     }
     E.pending.clear();
     if (n_frames) *n_frames = k;

@@ -61,6 +61,7 @@ public:
     // measurement: device-resident replay (include/av1r_stages.h)
     int clip_load(const uint8_t* const* tus, const size_t* lens, int n, struct ::av1r_clip** out);
     int clip_decode(struct ::av1r_clip* clip, uint64_t* cks, int cap, int* n_frames, float* device_ms);
+    int clip_decode_passes(struct ::av1r_clip* clip, int passes, uint64_t* cks, int cap, int* n_frames, float* device_ms);
     int clip_profile(struct ::av1r_clip* clip, struct ::av1r_stage_times* out);
     int verify(const uint8_t* data, size_t len, av1r_report* out, uint64_t* digests, int64_t cap_frames);
     int verify_items(std::vector<VerifyFile*>& files, const std::vector<VerifyItem>& items, bool stop_on_error, int* threads_used);

@@ -92,6 +92,10 @@ extern "C" int av1r_clip_decode(av1r_ctx* ctx, av1r_clip* clip, uint64_t* checks
     if (!ctx || !clip) return AV1R_EINVAL;
     return ctx->eng->clip_decode(clip, checksums, cap_frames, n_frames, device_ms);
 }
+extern "C" int av1r_clip_decode_passes(av1r_ctx* ctx, av1r_clip* clip, int passes, uint64_t* checksums, int cap_frames, int* n_frames, float* device_ms) {
+    if (!ctx || !clip) return AV1R_EINVAL;
+    return ctx->eng->clip_decode_passes(clip, passes, checksums, cap_frames, n_frames, device_ms);
+}
 extern "C" int av1r_clip_profile(av1r_ctx* ctx, av1r_clip* clip, av1r_stage_times* out) {
     if (!ctx || !clip || !out) return AV1R_EINVAL;
     return ctx->eng->clip_profile(clip, out);

@@ -295,37 +295,48 @@ __device__ void predict_tile(const uint8_t* ref, uint32_t pitch, int lastx, int 
 // The warp filter has a different 8-tap phase for every sample, so the work per sample is fixed: what can shrink is the number of
 // instructions around the 8 + 8 multiply-adds.  All 193 x 8 taps fit a signed byte, samples and the horizontal intermediate fit a
 // signed 16-bit lane, so a pair of taps times a pair of samples is one IDP.2A (same issue rate as IMAD on sm_100a:
-// tools/micro/idp_bench.cu): 5 per output instead of 8 IMAD + 8 unpacks, with the odd start positions handled by shifting the
+// tools/micro/idp_bench.cu): 4 or 5 per output instead of 8 IMAD + 8 unpacks, with the odd start positions handled by shifting the
 // 64-bit tap vector by one byte instead of re-packing samples.  The 15 x 15 support is fetched as 32-bit words (no clamps) when it
 // lies inside the reference; the horizontal intermediate is stored transposed so that the vertical pass reads packed row pairs.
 __device__ __align__(8) int8_t d_warped_filter8[193][8];
 
-__device__ __forceinline__ int dot8_packed(const uint32_t* w, int start, uint2 taps) {
-    // sum over t < 8 of taps[t] * sample[start + t], samples packed two per word in w[]
-    const int sh = (start & 1) << 3;
-    const uint32_t* q = w + (start >> 1);
-    const int t0 = (int)(taps.x << sh), t1 = (int)__funnelshift_l(taps.x, taps.y, sh), t2 = (int)__funnelshift_l(taps.y, 0u, sh);
-    int s = __dp2a_lo((int)q[0], t0, 0);
-    s = __dp2a_hi((int)q[1], t0, s);
-    s = __dp2a_lo((int)q[2], t1, s);
-    s = __dp2a_hi((int)q[3], t1, s);
-    s = __dp2a_lo((int)q[4], t2, s);
-    return s;
+// dot products of 8 taps with 8 consecutive 16-bit samples that start at an even / odd sample of the packed words q[]
+__device__ __forceinline__ int dot8_even(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint2 taps) {
+    int s = __dp2a_lo((int)q0, (int)taps.x, 0);
+    s = __dp2a_hi((int)q1, (int)taps.x, s);
+    s = __dp2a_lo((int)q2, (int)taps.y, s);
+    return __dp2a_hi((int)q3, (int)taps.y, s);
+}
+__device__ __forceinline__ int dot8_odd(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t q4, uint2 taps) {
+    const int t0 = (int)(taps.x << 8), t1 = (int)__funnelshift_l(taps.x, taps.y, 8), t2 = (int)(taps.y >> 24);
+    int s = __dp2a_lo((int)q0, t0, 0);
+    s = __dp2a_hi((int)q1, t0, s);
+    s = __dp2a_lo((int)q2, t1, s);
+    s = __dp2a_hi((int)q3, t1, s);
+    return __dp2a_lo((int)q4, t2, s);
 }
 
+// A lane finishes TWO neighbouring outputs of a row (horizontal pass) or of a column (vertical pass): their supports overlap in
+// seven of eight samples, so five shared-memory words serve both (ten before), and the parity of the start sample -- which
+// decides between the four-word and the five-word dot product -- is the same for every lane of the warp.  The model's matrix and
+// shears are read once per tile into registers (two 128-bit loads): through the reference the compiler re-read them from global
+// memory in every 8x8 block, because the shared-memory stores in between may alias.
+static constexpr int WS = 12;   // words per window row: 8 used; 12 keeps the eight rows a warp reads at once on different banks
 template <int NT>
-__device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr, int tw,
+__device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int lasty, int x0, int y0, int sx, int sy, const WarpRec& wr_g, int tw,
                             int th, int round1, InterSmem& sm, int32_t* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* win = reinterpret_cast<uint32_t*>(sm.refwin) + warp * 132;   // 15 rows x 8 words (+ slack for the fifth word of the last row)
-    uint32_t* wmt = reinterpret_cast<uint32_t*>(sm.mid) + warp * 80;       // transposed intermediate: 8 columns x 9 words (15 int16 + pad)
+    uint32_t* win = reinterpret_cast<uint32_t*>(sm.refwin) + warp * (15 * WS);   // 15 rows x 8 words
+    uint32_t* wmt = reinterpret_cast<uint32_t*>(sm.mid) + warp * 80;             // transposed intermediate: 8 columns x 9 words (15 int16 + pad)
+    const int4 ma = __ldg(reinterpret_cast<const int4*>(&wr_g)), mb = __ldg(reinterpret_cast<const int4*>(&wr_g) + 1);
+    const int alpha = (int)(short)(mb.z & 0xffff), beta = mb.z >> 16, gamma = (int)(short)(mb.w & 0xffff), delta = mb.w >> 16;
     const int nbx = tw >> 3, lnbx = 31 - __clz(nbx), nb = nbx * (th >> 3);
     const int rnd = 1 << (round1 - 1);
     for (int b = warp; b < nb; b += NT / 32) {
         const int i8 = b >> lnbx, j8 = b & (nbx - 1);
         const int src_x = (x0 + j8 * 8 + 4) << sx, src_y = (y0 + i8 * 8 + 4) << sy;
-        const long long dst_x = (long long)wr.mat[2] * src_x + (long long)wr.mat[3] * src_y + wr.mat[0];
-        const long long dst_y = (long long)wr.mat[4] * src_x + (long long)wr.mat[5] * src_y + wr.mat[1];
+        const long long dst_x = (long long)ma.z * src_x + (long long)ma.w * src_y + ma.x;
+        const long long dst_y = (long long)mb.x * src_x + (long long)mb.y * src_y + ma.y;
         const long long x4 = dst_x >> sx, y4 = dst_y >> sy;
         const int ix4 = (int)(x4 >> 16), sx4 = (int)(x4 & 0xFFFF), iy4 = (int)(y4 >> 16), sy4 = (int)(y4 & 0xFFFF);
         const int xl = ix4 - 7, yt = iy4 - 7;
@@ -342,8 +353,8 @@ __device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int l
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int idx = lane + 32 * u;
-                if (idx < 15 * 8) win[idx] = v[u];
+                const int idx = lane + 32 * u, r = idx >> 3, c = idx & 7;
+                if (r < 15) win[r * WS + c] = v[u];
             }
         } else {                                                     // leaves the reference frame: clamped samples, packed by pairs
             off = 0;
@@ -353,33 +364,46 @@ __device__ void warp_tile16(const uint8_t* ref, uint32_t pitch, int lastx, int l
                 if (r < 15) {
                     const uint16_t* row = (const uint16_t*)(ref + (size_t)min(max(yt + r, 0), lasty) * pitch);
                     const uint32_t a = __ldg(row + min(max(xl + 2 * c, 0), lastx)), bb = __ldg(row + min(max(xl + 2 * c + 1, 0), lastx));
-                    win[idx] = a | (bb << 16);
+                    win[r * WS + c] = a | (bb << 16);
                 }
             }
         }
         __syncwarp();
         int16_t* wmt16 = reinterpret_cast<int16_t*>(wmt);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {                                // horizontal: 15 rows x 8 columns
-            const int idx = lane + 32 * u;
-            if (idx < 15 * 8) {
-                const int r = idx >> 3, c = idx & 7;                 // i1 = r - 7, i2 = c - 4
-                const int sxx = sx4 + wr.alpha * (c - 4) + wr.beta * (r - 7);
-                const int offs = ((sxx + 512) >> 10) + 64;
-                const uint2 taps = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[offs]));
-                const int s = dot8_packed(win + r * 8, off + c, taps);
-                wmt16[c * 18 + r] = (int16_t)((s + 4) >> 3);
+        for (int u = 0; u < 2; u++) {                                // horizontal: 15 rows x 4 column pairs
+            const int t = lane + 32 * u;
+            if (t < 15 * 4) {
+                const int r = t >> 2, c = (t & 3) << 1;              // i1 = r - 7, i2 = c - 4 (and c - 3)
+                const int sxa = sx4 + alpha * (c - 4) + beta * (r - 7);
+                const uint2 ta = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[((sxa + 512) >> 10) + 64]));
+                const uint2 tb = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[((sxa + alpha + 512) >> 10) + 64]));
+                const uint32_t* q = win + r * WS + (c >> 1);
+                const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+                int sa, sb;
+                if (off == 0) {                                      // warp-uniform
+                    sa = dot8_even(q0, q1, q2, q3, ta);
+                    sb = dot8_odd(q0, q1, q2, q3, q4, tb);
+                } else {
+                    sa = dot8_odd(q0, q1, q2, q3, q4, ta);
+                    sb = dot8_even(q1, q2, q3, q4, tb);
+                }
+                wmt16[c * 18 + r] = (int16_t)((sa + 4) >> 3);
+                wmt16[c * 18 + 18 + r] = (int16_t)((sb + 4) >> 3);
             }
         }
         __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 2; u++) {                                // vertical: 8 x 8 outputs
-            const int idx = lane + 32 * u, orow = idx >> 3, c = idx & 7;   // i1 = orow - 4, i2 = c - 4
-            const int syy = sy4 + wr.gamma * (c - 4) + wr.delta * (orow - 4);
-            const int offs = ((syy + 512) >> 10) + 64;
-            const uint2 taps = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[offs]));
-            const int s = dot8_packed(wmt + c * 9, orow, taps);
-            out[(i8 * 8 + orow) * IT + j8 * 8 + c] = (s + rnd) >> round1;
+        {                                                            // vertical: 8 columns x 4 row pairs, one pair per lane
+            const int c = lane & 7, orow = (lane >> 3) << 1;         // i1 = orow - 4 (and orow - 3), i2 = c - 4
+            const int sya = sy4 + gamma * (c - 4) + delta * (orow - 4);
+            const uint2 ta = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[((sya + 512) >> 10) + 64]));
+            const uint2 tb = __ldg(reinterpret_cast<const uint2*>(d_warped_filter8[((sya + delta + 512) >> 10) + 64]));
+            const uint32_t* q = wmt + c * 9 + (orow >> 1);
+            const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+            const int sa = dot8_even(q0, q1, q2, q3, ta), sb = dot8_odd(q0, q1, q2, q3, q4, tb);
+            int32_t* o = out + (i8 * 8 + orow) * IT + j8 * 8 + c;
+            o[0] = (sa + rnd) >> round1;
+            o[IT] = (sb + rnd) >> round1;
         }
         __syncwarp();
     }
@@ -830,7 +854,7 @@ cudaError_t inter_copy_wedge_master(uint8_t* dst_dev, cudaStream_t s) {
     return cudaMemcpyAsync(dst_dev, src, 6 * 64 * 64, cudaMemcpyDeviceToDevice, s);
 }
 
-cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
+cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s, cudaStream_t aux, cudaEvent_t fork_ev, cudaEvent_t join_ev) {
     if (L.n <= 0 || L.n_tiles <= 0) return cudaSuccess;
     cudaError_t e = inter_upload_constants();
     if (e != cudaSuccess) return e;
@@ -848,13 +872,30 @@ cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
     }
     // the host lists the work items of small blocks (at most 16x16 luma samples) first: they run as two-warp CTAs
     const int n_small = L.n_tiles_small, n_large = L.n_tiles - L.n_tiles_small;
-    if (n_small > 0) {
-        if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, s>>>(L, 0);
-        else inter_pred_kernel<uint16_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, s>>>(L, 0);
+    // The two launches write disjoint blocks (overlapped-block prediction reads the *reference* frames with the neighbours' motion
+    // vectors, never the neighbours' predicted samples), so with a second stream they run side by side: the small-block launch is
+    // latency-bound (30 % issue-active) and hides entirely behind the large-block one on the frame's dependency chain.
+    const bool fork = aux && fork_ev && join_ev && n_small > 0 && n_large > 0;
+    cudaStream_t ss = fork ? aux : s;
+    if (fork) {
+        e = cudaEventRecord(fork_ev, s);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(aux, fork_ev, 0);
+        if (e != cudaSuccess) return e;
     }
     if (n_large > 0) {
         if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS><<<n_large, INTER_THREADS, 0, s>>>(L, n_small);
         else inter_pred_kernel<uint16_t, INTER_THREADS><<<n_large, INTER_THREADS, 0, s>>>(L, n_small);
+    }
+    if (n_small > 0) {
+        if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, ss>>>(L, 0);
+        else inter_pred_kernel<uint16_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, ss>>>(L, 0);
+    }
+    if (fork) {
+        e = cudaEventRecord(join_ev, aux);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(s, join_ev, 0);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }

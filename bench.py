@@ -274,9 +274,13 @@ CLIP_DESC = {
     "c2_small": "c2_small: 640x360 8-bit all-key clip (smoke-size version of c2)",
 }
 STEP_NOTE = "; step = one pass over the whole clip"
-TIMING_NOTE = ("per frame one H2D copy of its work-lists, then the reconstruction kernels, frames pipelined over 32 streams; value is timed with CUDA "
-               "events from the first H2D enqueue to the last kernel, max over ranks; the sequential host symbol parse is reported separately as "
-               "host_parse_ms")
+ENGINE_STREAMS = int(os.environ.get("AV1R_BENCH_STREAMS", "32"))
+ENGINE_FRAMES_IN_FLIGHT = int(os.environ.get("AV1R_BENCH_FIF", "64"))
+TIMING_NOTE = ("per frame one H2D copy of its work-lists, then the reconstruction kernels, frames pipelined over 32 streams; the K timed steps are "
+               "enqueued back to back (av1r_clip_decode_passes: no drain between steps, the first key frames of step k+1 overlap the tail of step "
+               "k as consecutive GOPs of a long file do) and bracketed by ONE pair of CUDA events from the first H2D enqueue of step 1 to the last "
+               "kernel of step K, max over ranks, every step's digests checked against the first pass; value_fenced_steps is the same with every "
+               "step fenced and drained on its own (rounds 1-2 definition); the sequential host symbol parse is reported separately as host_parse_ms")
 
 # tools / stages a clip must really contain to stand for its BASELINE config (block counts from the host parser, frames per stage)
 REQUIRED = {
@@ -349,7 +353,7 @@ def measure_clip(key, tus, blob, args, torch, dist, rank, world, local, steps, w
     """Device path + e2e + live roofline of one clip (or of this rank's share of a batch, given as one list of temporal units)."""
     import av1recon
     torch.cuda.set_device(local)
-    dec = av1recon.Decoder(device=local, streams=32, frames_in_flight=64)
+    dec = av1recon.Decoder(device=local, streams=ENGINE_STREAMS, frames_in_flight=ENGINE_FRAMES_IN_FLIGHT)
     clip = av1recon.Clip(dec, tus)
     info = clip.info
     hist = av1recon.tool_hist(info)
@@ -365,27 +369,32 @@ def measure_clip(key, tus, blob, args, torch, dist, rank, world, local, steps, w
     sampler = ClockSampler(local)
     if rank == 0 and sample_clocks:
         sampler.start()
-    total_ms = 0.0
-    for _ in range(steps):
-        ms, cks = clip.decode()
-        total_ms += ms
-        if cks != cks0:
-            raise RuntimeError("replay produced different digests: non-deterministic reconstruction")
+    # the K timed steps: enqueued back to back inside one fenced region (the library fails the call if any step's digests differ)
+    total_ms, cks = clip.decode_passes(steps)
+    if cks != cks0:
+        raise RuntimeError("replay produced different digests: non-deterministic reconstruction")
     torch.cuda.synchronize()
     clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
     total_ms = dist_max(torch, dist, world, local, total_ms)
     nfr = int(round(dist_sum(torch, dist, world, local, nfr_local)))
     value = nfr * steps / (total_ms / 1e3)
+    # the same steps, each fenced and drained on its own (what rounds 1-2 reported as `value`)
+    fenced_ms = 0.0
+    nfen = max(2, min(10, steps))
+    for _ in range(nfen):
+        ms, cks = clip.decode()
+        fenced_ms += ms
+        if cks != cks0:
+            raise RuntimeError("replay produced different digests: non-deterministic reconstruction")
+    fenced_ms = dist_max(torch, dist, world, local, fenced_ms)
+    value_fenced = nfr * nfen / (fenced_ms / 1e3)
     # the same pass with the work-lists already resident in HBM (kernel-only figure)
     clip.set_resident(True)
     clip.decode()
-    res_ms = 0.0
-    nres = max(2, min(5, steps))
-    for _ in range(nres):
-        ms, cks = clip.decode()
-        res_ms += ms
-        if cks != cks0:
-            raise RuntimeError("resident replay produced different digests")
+    nres = max(2, min(10, steps))
+    res_ms, cks = clip.decode_passes(nres)
+    if cks != cks0:
+        raise RuntimeError("resident replay produced different digests")
     res_ms = dist_max(torch, dist, world, local, res_ms)
     value_resident = nfr * nres / (res_ms / 1e3)
     clip.set_resident(False)
@@ -442,8 +451,8 @@ def measure_clip(key, tus, blob, args, torch, dist, rank, world, local, steps, w
         "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if info.bit_depth == 8 else "u16", "data": "synthetic",
         "config": workload_config(WORKLOAD_NAMES.get(key, key), world),
-        "engine": {"streams": 32, "frames_in_flight": 64, "frames_per_step_all_ranks": nfr, "timing": TIMING_NOTE},
-        "value_hbm_resident": value_resident,
+        "engine": {"streams": ENGINE_STREAMS, "frames_in_flight": ENGINE_FRAMES_IN_FLIGHT, "frames_per_step_all_ranks": nfr, "timing": TIMING_NOTE},
+        "value_hbm_resident": value_resident, "value_fenced_steps": value_fenced,
         "gpu_launches": launches_per_step * steps,
         "e2e": {"value": nfr / best, "unit": "frames/s", "h2d_bytes_per_step": int(info.worklist_bytes) + len(blob) * 0,
                 "d2h_bytes_per_step": 24 * nfr_local, "host_input_bytes_per_step": len(blob),
@@ -603,7 +612,7 @@ def workload_config(workload, world):
 def compact(line):
     """per_config entry: the figures the verdict asked for, without the long tables."""
     r = line["roofline"]
-    return {"workload": line["config"]["workload"].split(" --")[0].split(":")[0], "config": line["config"], "value": line["value"], "value_hbm_resident": line.get("value_hbm_resident"),
+    return {"workload": line["config"]["workload"].split(" --")[0].split(":")[0], "config": line["config"], "value": line["value"], "value_hbm_resident": line.get("value_hbm_resident"), "value_fenced_steps": line.get("value_fenced_steps"),
             "unit": "frames/s", "steps": line["steps"], "ms_per_step": line["ms_per_step"], "dtype": line["dtype"], "scaling": line["scaling"],
             "e2e": {k: line["e2e"][k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "host_parse_ms_per_step", "host_threads")},
             "cpu_baseline": line.get("cpu_baseline"),

@@ -112,6 +112,11 @@ int av1r_clip_load(struct av1r_ctx* ctx, const uint8_t* const* tus, const size_t
 int av1r_clip_info_get(const av1r_clip* clip, av1r_clip_info* out);
 /* checksums: caller array of cap_frames*3 uint64 (display order); *n_frames = frames produced. */
 int av1r_clip_decode(struct av1r_ctx* ctx, av1r_clip* clip, uint64_t* checksums, int cap_frames, int* n_frames, float* device_ms);
+/* `passes` replays enqueued back to back between one pair of fencing events (no drain between passes: the first frames of pass
+ * k + 1 overlap the last frames of pass k, as consecutive GOPs of a long file do in the streaming path); *device_ms covers all of
+ * them.  checksums / *n_frames describe the first pass; a later pass whose digests differ makes the call fail with AV1R_EIO. */
+int av1r_clip_decode_passes(struct av1r_ctx* ctx, av1r_clip* clip, int passes, uint64_t* checksums, int cap_frames, int* n_frames,
+                            float* device_ms);
 int av1r_clip_profile(struct av1r_ctx* ctx, av1r_clip* clip, av1r_stage_times* out);
 void av1r_clip_free(av1r_clip* clip);
 /* Default (0): every replay copies each frame's work-lists host -> device inside the timed pass ("from the first
