@@ -402,8 +402,6 @@ struct FrameSlot {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t fg_ev = nullptr;   // film-grain templates of this slot's frame are ready (prepared on the side stream)
     bool fg_prepared = false;
-    cudaStream_t aux = nullptr;    // second stream of this slot's frame: the small-block K2 launch runs beside the large-block one
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     PinBuf staging;
     DevBuf arena;        // submit path: the frame's work-lists
     DevBuf residual;
@@ -482,7 +480,6 @@ struct EngineImpl {
     StreamParser sp;
     bool opened = false;
     std::vector<cudaStream_t> streams;
-    std::vector<cudaStream_t> aux_streams;   // one per stream (K2 fork)
     cudaStream_t side = nullptr;          // film-grain template preparation runs here, ahead of the frame it belongs to
     std::vector<std::unique_ptr<FrameSlot>> slots;
     int next_slot = 0, next_stream = 0;
@@ -678,9 +675,9 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         xl.mask_pitch = (uint32_t)align_up((size_t)fp.cw[0], 256);
         { int e_ = ensure_slots(&FrameSlot::diffmask, s, (size_t)xl.mask_pitch * fp.ch[0], hw_mask); if (e_) return e_; }
         xl.mask = s.diffmask.p;
-        // (the stage profile keeps the two launches in sequence on one stream so that their times add up)
-        static const bool no_fork = getenv("AV1R_K2_NOFORK") != nullptr;   // (A/B switch)
-        CK(launch_inter(xl, st, (tm || no_fork) ? nullptr : s.aux, s.fork_ev, s.join_ev));
+        // (running the small-block launch on a second stream beside the large-block one was measured and is *slower*: c3 2425 ->
+        // 2130, c1 6950 -> 5900 frames/s -- 64 streams share the 32 hardware queues, and unrelated frames start to wait for each other)
+        CK(launch_inter(xl, st));
         if (tm) tm->end(AV1R_ST_INTER, (L.n_itiles_small > 0) + (L.n_itiles > L.n_itiles_small), st);
         CK(launch_inter_residual(d_recs, (const uint32_t*)(d_arena + L.order), L.n_order, recon->pl, res, fp, st));
         if (tm) tm->end(AV1R_ST_INTER, L.n_order > 0, st);
@@ -941,7 +938,6 @@ int EngineImpl::acquire_slot(int& slot_idx) {
     int rc = wait_slot(s);
     if (rc) return rc;
     s.stream = streams[next_stream];
-    s.aux = aux_streams[next_stream];
     next_stream = (next_stream + 1) % (int)streams.size();
     return 0;
 }
@@ -1145,8 +1141,6 @@ Engine::~Engine() {
             if (s->ev0) cudaEventDestroy(s->ev0);
             if (s->ev1) cudaEventDestroy(s->ev1);
             if (s->fg_ev) cudaEventDestroy(s->fg_ev);
-            if (s->fork_ev) cudaEventDestroy(s->fork_ev);
-            if (s->join_ev) cudaEventDestroy(s->join_ev);
         }
         impl_->slots.clear();
         impl_->pending.clear();
@@ -1154,7 +1148,6 @@ Engine::~Engine() {
         impl_->pool.clear();
         for (auto& r : impl_->main_refs.refs) r.reset();
         for (auto st : impl_->streams) cudaStreamDestroy(st);
-        for (auto st : impl_->aux_streams) cudaStreamDestroy(st);
         if (impl_->side) cudaStreamDestroy(impl_->side);
     }
     delete impl_;
@@ -1183,16 +1176,12 @@ int Engine::open(const av1r_config& cfg) {
     CK(cudaSetDevice(cfg.device));
     E.streams.resize(E.cfg.streams);
     for (auto& st : E.streams) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    E.aux_streams.resize(E.cfg.streams);
-    for (auto& st : E.aux_streams) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&E.side, cudaStreamNonBlocking));
     for (int i = 0; i < E.cfg.frames_in_flight; i++) {
         auto s = std::make_unique<FrameSlot>();
         CK(cudaEventCreate(&s->ev0));
         CK(cudaEventCreate(&s->ev1));
         CK(cudaEventCreateWithFlags(&s->fg_ev, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
         E.slots.push_back(std::move(s));
     }
     if (const char* e = getenv("AV1R_K3_CTAS")) E.k3_ctas = std::max(0, atoi(e));

@@ -854,7 +854,7 @@ cudaError_t inter_copy_wedge_master(uint8_t* dst_dev, cudaStream_t s) {
     return cudaMemcpyAsync(dst_dev, src, 6 * 64 * 64, cudaMemcpyDeviceToDevice, s);
 }
 
-cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s, cudaStream_t aux, cudaEvent_t fork_ev, cudaEvent_t join_ev) {
+cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s) {
     if (L.n <= 0 || L.n_tiles <= 0) return cudaSuccess;
     cudaError_t e = inter_upload_constants();
     if (e != cudaSuccess) return e;
@@ -872,30 +872,14 @@ cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s, cudaStream_t aux,
     }
     // the host lists the work items of small blocks (at most 16x16 luma samples) first: they run as two-warp CTAs
     const int n_small = L.n_tiles_small, n_large = L.n_tiles - L.n_tiles_small;
-    // The two launches write disjoint blocks (overlapped-block prediction reads the *reference* frames with the neighbours' motion
-    // vectors, never the neighbours' predicted samples), so with a second stream they run side by side: the small-block launch is
-    // latency-bound (30 % issue-active) and hides entirely behind the large-block one on the frame's dependency chain.
-    const bool fork = aux && fork_ev && join_ev && n_small > 0 && n_large > 0;
-    cudaStream_t ss = fork ? aux : s;
-    if (fork) {
-        e = cudaEventRecord(fork_ev, s);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamWaitEvent(aux, fork_ev, 0);
-        if (e != cudaSuccess) return e;
-    }
+    // the large-block launch first: its heaviest CTAs (listed first) are what the stage ends on
     if (n_large > 0) {
         if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS><<<n_large, INTER_THREADS, 0, s>>>(L, n_small);
         else inter_pred_kernel<uint16_t, INTER_THREADS><<<n_large, INTER_THREADS, 0, s>>>(L, n_small);
     }
     if (n_small > 0) {
-        if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, ss>>>(L, 0);
-        else inter_pred_kernel<uint16_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, ss>>>(L, 0);
-    }
-    if (fork) {
-        e = cudaEventRecord(join_ev, aux);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamWaitEvent(s, join_ev, 0);
-        if (e != cudaSuccess) return e;
+        if (L.fp.bd == 8) inter_pred_kernel<uint8_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, s>>>(L, 0);
+        else inter_pred_kernel<uint16_t, INTER_THREADS_SMALL><<<n_small, INTER_THREADS_SMALL, 0, s>>>(L, 0);
     }
     return cudaGetLastError();
 }

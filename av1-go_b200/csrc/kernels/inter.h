@@ -23,9 +23,7 @@ struct InterLaunch {
     DevFrameParams fp;
 };
 
-// aux != nullptr: the small-block launch runs on `aux` beside the large-block launch on `s` (forked after everything queued on `s`
-// so far, joined back into `s` before the call returns); the two launches write disjoint blocks
-cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s, cudaStream_t aux = nullptr, cudaEvent_t fork_ev = nullptr, cudaEvent_t join_ev = nullptr);
+cudaError_t launch_inter(const InterLaunch& L, cudaStream_t s);
 // frame += residual for the plain inter transform blocks (order = indices of records with eob > 0)
 cudaError_t launch_inter_residual(const TxRec* recs, const uint32_t* order, int n, const DevPlanes& cur, const DevResidual& res,
                                   const DevFrameParams& fp, cudaStream_t s);
