@@ -127,6 +127,28 @@ def test_cuda_verify_buffer_inter(built):
 
 
 @pytest.mark.gpu
+def test_cuda_clip_replay_passes_back_to_back(built):
+    """av1r_clip_decode_passes (what bench.py times): several replays of a clip enqueued back to back without a drain in between --
+    slots, frame buffers and reference events recycled across the pass boundary -- reproduce the digests of the single-pass replay
+    and of the whole-file verify path; more in-flight frames than slots on purpose."""
+    import av1recon
+    name = "inter_8b_alltools_352x288"
+    tus = _tus(name)
+    data = open(os.path.join(GOLD, name + ".ivf"), "rb").read()
+    rc, rep, digests = av1recon.verify_buffer(data)
+    assert rc == 0 and rep.status == 0, rep.message
+    dec = av1recon.Decoder(streams=4, frames_in_flight=8)
+    clip = av1recon.Clip(dec, tus * 2)          # the sequence twice: every repetition starts with its key frame
+    ms1, one = clip.decode()
+    ms5, five = clip.decode_passes(5)
+    assert one == five and len(one) == 2 * rep.frames
+    assert [tuple(int(x) for x in d) for d in digests] * 2 == [tuple(int(x) for x in d) for d in one]
+    assert ms5 > 0
+    clip.free()
+    dec.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.timeout(120)
 def test_cuda_verify_buffer_many_multi_tu_segments(built):
     """A batch container with more multi-TU GOP segments than the parser look-ahead budget (the C5 shape: the workers of later
