@@ -222,7 +222,9 @@ class ClipInfo(C.Structure):
                 ("coef_tokens", C.c_uint64), ("tx_blocks", C.c_uint64), ("intra_samples", C.c_uint64),
                 ("inter_samples", C.c_uint64), ("inter_ref_samples", C.c_uint64), ("lr_frames", C.c_uint64), ("cdef_frames", C.c_uint64),
                 ("deblock_frames", C.c_uint64), ("grain_frames", C.c_uint64), ("inter_blocks", C.c_uint64), ("obmc_neighbours", C.c_uint64),
-                ("tool_hist", C.c_uint64 * 24)]
+                ("tool_hist", C.c_uint64 * 24),
+                ("intra_frame_samples", C.c_uint64), ("intra_frame_coded_samples", C.c_uint64), ("intra_frame_tx_blocks", C.c_uint64),
+                ("intra_frames", C.c_uint64)]
 
 
 TOOL_NAMES = ["inter_blocks", "compound_avg", "compound_dist", "compound_wedge", "compound_diffwtd", "interintra", "interintra_wedge",
@@ -230,7 +232,7 @@ TOOL_NAMES = ["inter_blocks", "compound_avg", "compound_dist", "compound_wedge",
               "vartx_split", "switchable_filter", "palette", "intrabc"]
 
 
-STAGES = ["h2d", "itx", "intra", "inter", "deblock", "cdef", "lr", "grain", "digest", "superres"]
+STAGES = ["h2d", "itx", "intra", "inter", "deblock", "cdef", "lr", "grain", "digest", "superres", "intra_frame"]
 
 
 class StageTimes(C.Structure):
@@ -288,7 +290,7 @@ class Clip:
         rc = self.dec.l.av1r_clip_profile(self.dec.ctx, self.h, C.byref(st))
         if rc:
             raise RuntimeError(f"av1r_clip_profile -> {rc}: {self.dec.error()}")
-        return {STAGES[i]: (st.ms[i], st.launches[i]) for i in range(9)}
+        return {STAGES[i]: (st.ms[i], st.launches[i]) for i in range(len(STAGES)) if STAGES[i] != "superres" or st.launches[i]}
 
     def set_resident(self, resident):
         """resident=True: work-lists uploaded once, replays read them from HBM (kernel-only figure); default False: one H2D per

@@ -146,8 +146,16 @@ extern "C" int av1r_parse_stats(const uint8_t* data, size_t len, av1r_clip_info*
             out->deblock_frames += (fw.fh.lf.level[0] || fw.fh.lf.level[1]);
             out->grain_frames += fw.fh.show_frame && fw.fh.fg.apply_grain;
             for (int i = 0; i < 24; i++) out->tool_hist[i] += fw.tool_hist[i];
+            uint64_t isamp = 0;
             for (const TxRec& r : fw.tx)
-                if (r.mode != TXM_INTER) out->intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+                if (r.mode != TXM_INTER) isamp += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+            out->intra_samples += isamp;
+            if (fw.inter.empty()) {
+                out->intra_frame_samples += isamp;
+                out->intra_frame_coded_samples += fw.coded_samples;
+                out->intra_frame_tx_blocks += fw.tx.size();
+                out->intra_frames++;
+            }
             out->width = fw.fh.upscaled_width;
             out->height = fw.fh.frame_height;
             out->bit_depth = sp.hp.seq.bit_depth;

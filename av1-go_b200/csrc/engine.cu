@@ -741,7 +741,7 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         il.prof = (unsigned long long*)k3_prof.p;
         CK(launch_intra(il, st));
     }
-    if (tm) tm->end(AV1R_ST_INTRA, L.n_k3 > 0 ? 1 : 0, st);
+    if (tm) tm->end(L.n_inter > 0 ? AV1R_ST_INTRA : AV1R_ST_INTRA_FRAME, L.n_k3 > 0 ? 1 : 0, st);
     EP_ADD(11, t_h);
     t_h = EP_T();
     std::shared_ptr<DevFrameBuf> cur = recon;
@@ -1849,8 +1849,16 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
                         ci.deblock_frames += cf->dw.lf_on && (inloop & 1);
                         ci.grain_frames += fw.fh.show_frame && fw.fh.fg.apply_grain && apply_grain;
                         for (int i = 0; i < 24; i++) ci.tool_hist[i] += fw.tool_hist[i];
+                        uint64_t isamp = 0;
                         for (const TxRec& r : fw.tx)
-                            if (r.mode != TXM_INTER) ci.intra_samples += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+                            if (r.mode != TXM_INTER) isamp += (uint64_t)kTxW[r.txsz] * kTxH[r.txsz];
+                        ci.intra_samples += isamp;
+                        if (fw.inter.empty()) {
+                            ci.intra_frame_samples += isamp;
+                            ci.intra_frame_coded_samples += fw.coded_samples;
+                            ci.intra_frame_tx_blocks += fw.tx.size();
+                            ci.intra_frames++;
+                        }
                         ci.width = fw.fh.upscaled_width;
                         ci.height = fw.fh.frame_height;
                         ci.bit_depth = parser.hp.seq.bit_depth;
@@ -1880,6 +1888,8 @@ int Engine::clip_load(const uint8_t* const* tus, const size_t* lens, int n, av1r
         d.inter_ref_samples += a.inter_ref_samples; d.lr_frames += a.lr_frames; d.cdef_frames += a.cdef_frames;
         d.deblock_frames += a.deblock_frames; d.grain_frames += a.grain_frames; d.inter_blocks += a.inter_blocks;
         d.obmc_neighbours += a.obmc_neighbours;
+        d.intra_frame_samples += a.intra_frame_samples; d.intra_frame_coded_samples += a.intra_frame_coded_samples;
+        d.intra_frame_tx_blocks += a.intra_frame_tx_blocks; d.intra_frames += a.intra_frames;
         for (int i = 0; i < 24; i++) d.tool_hist[i] += a.tool_hist[i];
         if (a.frames_decoded) { d.width = a.width; d.height = a.height; d.bit_depth = a.bit_depth; d.frame_bytes = a.frame_bytes; }
         for (auto& cf : so.frames) clip->frames.push_back(std::move(cf));

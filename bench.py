@@ -334,7 +334,11 @@ def stage_model_bytes(info):
     bps = 1 if info.bit_depth == 8 else 2
     return {
         "itx": 4 * int(info.coef_tokens) + 32 * int(info.tx_blocks) + 2 * A,       # C (tokens) + records + residual write
-        "intra": bps * int(info.intra_samples) + 2 * A + 32 * int(info.tx_blocks),  # intra samples written + residual read + records
+        # the intra wavefront kernel is two kernels: the whole-frame build on frames without inter blocks (key frames: a dependency
+        # chain over the whole picture) and the scattered-unit build on inter frames; samples written + residual read + records
+        "intra_frame": bps * int(info.intra_frame_samples) + 2 * int(info.intra_frame_coded_samples) + 32 * int(info.intra_frame_tx_blocks),
+        "intra": bps * (int(info.intra_samples) - int(info.intra_frame_samples)) + 2 * (A - int(info.intra_frame_coded_samples))
+                 + 32 * (int(info.tx_blocks) - int(info.intra_frame_tx_blocks)),
         "inter": bps * (int(info.inter_ref_samples) + int(info.inter_samples)) + 40 * int(info.inter_blocks),   # Rbar*F_inter + F_inter
         "deblock": 2 * F * int(info.deblock_frames),
         "cdef": 2 * F * int(info.cdef_frames),
@@ -451,7 +455,8 @@ def measure_clip(key, tus, blob, args, torch, dist, rank, world, local, steps, w
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = tj.get(WORKLOAD_NAMES.get(key, key), {}).get(dom, {}).get("dram_bytes_per_launch")
+        per = tj.get(WORKLOAD_NAMES.get(key, key), {})
+        traffic = (per.get(dom) or per.get("intra" if dom == "intra_frame" else dom, {})).get("dram_bytes_per_launch")
     except Exception:
         traffic = None
     nf = int(info.frames_decoded)

@@ -98,10 +98,15 @@ typedef struct av1r_clip_info {
     uint64_t lr_frames, cdef_frames, deblock_frames, grain_frames;   /* frames on which each post-filter stage runs */
     uint64_t inter_blocks, obmc_neighbours;
     uint64_t tool_hist[24];        /* block counts per coding tool, order of TOOL_* in csrc/frame_state.h */
+    /* the share of intra_samples / coded_samples / tx_blocks that belongs to frames without inter blocks (key and intra-only
+     * frames): those run the whole-frame wavefront build of the intra kernel, a different kernel than the scattered units of inter frames */
+    uint64_t intra_frame_samples, intra_frame_coded_samples, intra_frame_tx_blocks, intra_frames;
 } av1r_clip_info;
 
 enum { AV1R_ST_H2D = 0, AV1R_ST_ITX, AV1R_ST_INTRA, AV1R_ST_INTER, AV1R_ST_DEBLOCK, AV1R_ST_CDEF, AV1R_ST_LR, AV1R_ST_GRAIN,
-       AV1R_ST_DIGEST, AV1R_ST_SUPERRES, AV1R_ST_COUNT };
+       AV1R_ST_DIGEST, AV1R_ST_SUPERRES,
+       AV1R_ST_INTRA_FRAME,   /* the intra kernel on frames without inter blocks (whole-frame wavefront); AV1R_ST_INTRA = inter frames' units */
+       AV1R_ST_COUNT };
 typedef struct av1r_stage_times {
     uint32_t struct_size;
     float ms[AV1R_ST_COUNT];       /* summed over the clip */

@@ -2,7 +2,7 @@
 # usage: bash tools/ab_libs.sh WORKLOAD tag...
 W=$1; shift
 cp av1-go_b200/lib/libav1r.so /tmp/cur.so
-for round in 1 2; do
+for round in $(seq ${ROUNDS:-2}); do
 for v in cur "$@"; do
   if [ $v = cur ]; then cp /tmp/cur.so av1-go_b200/lib/libav1r.so; else cp av1-go_b200/lib/libav1r_$v.so av1-go_b200/lib/libav1r.so; fi
   python bench.py --workload $W --steps 5 --warmup 3 --no-per-config --no-cpu-baseline 2>/dev/null | python -c "
