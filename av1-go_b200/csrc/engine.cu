@@ -500,6 +500,7 @@ struct EngineImpl {
     int k3_progressive = 2;                           // AV1R_K3_PROGRESSIVE: 0 whole-unit hand-over, 1 adaptive, 2 always cell-level (default)
     int k3_inter_mult = 6;                            // inter frames: CTAs = this x the unit wavefront (AV1R_K3_INTER_MULT)
     int k3_intra_run = 0;                             // consecutive frames without inter prediction issued so far
+    int k3_since_intra = 1 << 20;                     // frames issued since the last frame without inter prediction (large: none yet)
     int64_t frames_decoded = 0;
 
     int wait_slot(FrameSlot& s);
@@ -587,6 +588,8 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
     const WorkLayout& L = dw.lay;
     const DevFrameParams& fp = dw.fp;
     cudaStream_t st = s.stream;
+    const int since_intra = k3_since_intra;   // frames issued since the last frame without inter prediction
+    k3_since_intra = L.n_inter == 0 ? 0 : k3_since_intra + 1;
     auto t_h = EP_T();
     auto recon = get_frame(fp);
     if (!recon) return AV1R_ENOMEM;
@@ -731,6 +734,14 @@ int EngineImpl::run_frame(FrameSlot& s, const DevWork& dw, const uint8_t* d_aren
         }
         il.progressive = k3_progressive == 1 ? !(k3_intra_run >= 4 && saturated) : (k3_progressive != 0);
         if (il.progressive && k3_ctas <= 0 && L.n_inter == 0) il.ctas = std::min(L.n_k3units, (il.ctas * 7 + 4) / 5);
+        // A key frame at the head of a *long* GOP (at least 16 frames were issued since the previous intra frame, or it is the first
+        // frame) starts a long dependency chain and is rare: three times as many CTAs take the next units' record / residual loads
+        // off the wavefront (4K: 3.8 -> 3.2 ms per key frame; c3 +2.7 %, c1 +2.4 %).  They cost ~80 % more CTA-time per key frame,
+        // so runs of intra frames (all-intra content) and short GOPs (the 8-frame segments of the batch, where it measured -7 %)
+        // keep the narrow setting, the throughput optimum when many frames share the SMs (profiles/r2_k3_sweep.md).
+        static const bool key_wide = getenv("AV1R_K3_KEYWIDE_OFF") == nullptr;   // (A/B switch)
+        if (key_wide && k3_ctas <= 0 && L.n_inter == 0 && since_intra >= 16 && !L.k3upos_on)
+            il.ctas = std::min(L.n_k3units, 3 * (std::min((fp.mi_rows + 15) >> 4, (((fp.mi_cols + 15) >> 4) + 1) / 2) + 2));
         // block-copy frames list their units in decode order: rows overlap only as far as the CTAs reach ahead in that order
         if (L.k3upos_on && k3_ctas <= 0) il.ctas = std::min(L.n_k3units, std::max(il.ctas, 2 * ((fp.mi_cols + 15) >> 4)));
         il.frame = recon->pl;

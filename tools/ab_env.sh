@@ -1,7 +1,7 @@
 # on-box comparison of environment switches of one library build on the stage table of a workload
 # usage: bash tools/ab_env.sh WORKLOAD "VAR=val [VAR2=val]" ...      ("-" = no switch)
 W=$1; shift
-for round in 1 2; do
+for round in $(seq ${ROUNDS:-2}); do
 for v in "-" "$@"; do
   e=""; [ "$v" != "-" ] && e="$v"
   env $e python bench.py --workload $W --steps 5 --warmup 3 --no-per-config --no-cpu-baseline 2>/dev/null | python -c "
