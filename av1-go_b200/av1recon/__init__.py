@@ -40,6 +40,10 @@ class FrameHeaderInfo(C.Structure):
         ("lf_level", C.c_int * 4), ("cdef_enabled", C.c_int), ("cdef_bits", C.c_int), ("lr_type", C.c_int * 3),
         ("tx_mode", C.c_int), ("reduced_tx_set", C.c_int), ("header_bytes", C.c_int),
         ("film_grain", FilmGrainParams),
+        ("error_resilient_mode", C.c_int), ("disable_cdf_update", C.c_int), ("disable_frame_end_update_cdf", C.c_int),
+        ("enable_order_hint", C.c_int), ("coded_lossless", C.c_int),
+        ("segmentation_enabled", C.c_int), ("segmentation_update_map", C.c_int), ("segmentation_temporal_update", C.c_int),
+        ("delta_q_present", C.c_int), ("delta_lf_present", C.c_int),
     ]
 
 

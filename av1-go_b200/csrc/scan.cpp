@@ -45,6 +45,16 @@ static void fill_info(const HeaderParser& hp, const FrameHdr& fh, int tu, av1r_f
     o.reduced_tx_set = fh.reduced_tx_set;
     o.header_bytes = (int)fh.header_bytes;
     memcpy(&o.film_grain, &fh.fg, sizeof(o.film_grain));
+    o.error_resilient_mode = fh.error_resilient_mode;
+    o.disable_cdf_update = fh.disable_cdf_update;
+    o.disable_frame_end_update_cdf = fh.disable_frame_end_update_cdf;
+    o.enable_order_hint = hp.seq.enable_order_hint;
+    o.coded_lossless = fh.coded_lossless;
+    o.segmentation_enabled = fh.seg.enabled;
+    o.segmentation_update_map = fh.seg.update_map;
+    o.segmentation_temporal_update = fh.seg.temporal_update;
+    o.delta_q_present = fh.delta_q_present;
+    o.delta_lf_present = fh.delta_lf_present;
 }
 
 // Walk one temporal unit; calls cb for every frame header (incl. show_existing_frame).

@@ -47,6 +47,9 @@ typedef struct av1r_frame_header_info {
     int lf_level[4], cdef_enabled, cdef_bits, lr_type[3], tx_mode, reduced_tx_set;
     int header_bytes;
     av1r_film_grain_params film_grain;
+    /* syntax switches of the frame / sequence header (tests assert that the golden streams really use them) */
+    int error_resilient_mode, disable_cdf_update, disable_frame_end_update_cdf, enable_order_hint, coded_lossless;
+    int segmentation_enabled, segmentation_update_map, segmentation_temporal_update, delta_q_present, delta_lf_present;
 } av1r_frame_header_info;
 
 /* Header-only scan of a list of temporal units (no pixel work, no GPU): the native stand-in for

@@ -65,6 +65,24 @@ INTER_CASES = {
     # blocks inside inter frames
     "inter_8b_screen_352x288": ("screen", 352, 288, 8, 6, {"cpu-used": "2", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "1", "enable-restoration": "0", "enable-cdef": "0"}, {14: 4, 48: 9999}),
     "inter_10b_mono_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36"}, {14: 4, 48: 9999, 52: 1}),
+    # syntax paths off libaom's defaults (each stream differs from the all-tools ones in one header switch):
+    # lossless (base_q_idx 0: Walsh-Hadamard transform only, no in-loop filters)
+    "inter_8b_lossless_128x96": ("panzoom", 128, 96, 8, 3, {"cpu-used": "4", "lossless": "1"}, {14: 0, 48: 9999}),
+    # delta_q + delta_lf per superblock (per-block quantiser index and per-block deblocking levels)
+    "inter_8b_deltaq_lf_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "3", "cq-level": "36", "deltaq-mode": "1", "delta-lf-mode": "1"}, {14: 4, 48: 9999}),
+    # segmentation: variance AQ (spatially coded map, per-segment quantiser) and cyclic refresh (temporally predicted map)
+    "inter_8b_aq1_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "4", "cq-level": "36", "aq-mode": "1"}, {14: 4, 48: 9999}),
+    "inter_8b_aq3_256x160": ("panzoom", 256, 160, 8, 8, {"cpu-used": "5", "cq-level": "36", "aq-mode": "3"}, {14: 0, 48: 9999}),
+    # enable_order_hint = 0 (no temporal motion vectors, no skip mode, no distance-weighted compound)
+    "inter_8b_nohint_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "3", "cq-level": "36", "enable-order-hint": "0"}, {14: 4, 48: 9999}),
+    # disable_cdf_update = 1 / disable_frame_end_update_cdf = 1 with two tile columns / error_resilient_mode = 1 (cfg[12])
+    "inter_8b_nocdfupd_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "4", "cq-level": "36", "cdf-update-mode": "0"}, {14: 4, 48: 9999}),
+    "inter_8b_frameparallel_352x288": ("panzoom", 352, 288, 8, 6, {"cpu-used": "4", "cq-level": "36", "frame-parallel": "1", "tile-columns": "1"}, {14: 4, 48: 9999}),
+    "inter_8b_errres_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "4", "cq-level": "36"}, {14: 4, 48: 9999, 12: 1}),
+    # reduced_tx_set = 1
+    "inter_8b_reducedtx_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "3", "cq-level": "36", "reduced-tx-type-set": "1"}, {14: 4, 48: 9999}),
+    # odd frame size (410 x 230: the last mi column / row is half outside the picture) with 4 x 2 tiles at 10 bits
+    "inter_10b_tiles4x2_odd_410x230": ("panzoom", 410, 230, 10, 6, {"cpu-used": "4", "cq-level": "36", "tile-columns": "2", "tile-rows": "1"}, {14: 4, 48: 9999}),
     "inter_10b_qm_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36", "enable-qm": "1", "qm-min": "0", "qm-max": "15"}, {14: 4, 48: 9999}),
 }
 

@@ -46,6 +46,32 @@ def test_golden_streams_exercise_the_inter_tools(built):
         assert total.get(tool, 0) > 0, f"no golden stream uses {tool}: {total}"
 
 
+def test_syntax_switch_streams_use_their_switch(built):
+    """The golden streams named after a header switch really carry it (header scan, host only): lossless, delta_q / delta_lf,
+    segmentation with spatial and temporal map coding, enable_order_hint = 0, disable_cdf_update, disable_frame_end_update_cdf with
+    several tiles, error_resilient_mode, reduced_tx_set, an odd frame size under 4 x 2 tiles."""
+    import av1recon
+
+    def hdrs(name):
+        return [h for h in av1recon.scan_headers(_tus(name)) if not h.show_existing_frame]
+
+    assert all(h.coded_lossless and h.base_q_idx == 0 for h in hdrs("inter_8b_lossless_128x96"))
+    dq = hdrs("inter_8b_deltaq_lf_256x160")
+    assert any(h.delta_q_present and h.delta_lf_present for h in dq)
+    aq1 = hdrs("inter_8b_aq1_256x160")
+    assert all(h.segmentation_enabled for h in aq1) and any(h.segmentation_temporal_update for h in aq1)
+    assert any(h.segmentation_enabled and h.segmentation_update_map for h in hdrs("inter_8b_aq3_256x160"))
+    assert all(h.enable_order_hint == 0 for h in hdrs("inter_8b_nohint_256x160"))
+    assert all(h.disable_cdf_update for h in hdrs("inter_8b_nocdfupd_256x160"))
+    fp = hdrs("inter_8b_frameparallel_352x288")
+    assert all(h.disable_frame_end_update_cdf and not h.disable_cdf_update and h.tile_cols == 2 for h in fp)
+    er = hdrs("inter_8b_errres_256x160")
+    assert all(h.error_resilient_mode and h.primary_ref_frame == 7 for h in er)
+    assert all(h.reduced_tx_set for h in hdrs("inter_8b_reducedtx_256x160"))
+    odd = hdrs("inter_10b_tiles4x2_odd_410x230")
+    assert all(h.tile_cols == 4 and h.tile_rows == 2 and h.width == 410 and h.height == 230 and h.bit_depth == 10 for h in odd)
+
+
 @pytest.mark.parametrize("filters", [0, 7])
 def test_oracle_stage_isolation_vs_dav1d(built, filters):
     from oracle import dav1d_ref, oracle_lib
