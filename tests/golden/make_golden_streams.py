@@ -31,6 +31,8 @@ CASES = {
     # quantiser matrices (K1): per-frame qm levels between qm-min and qm-max
     # monochrome (cfg[52] = monochrome): luma only, one MD5 per frame
     "intra_8b_mono_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 0, 52: 1}),
+    # 10-bit key frames with loop restoration, CDEF, 128x128 superblocks and a non-zero deblocking sharpness
+    "intra_10b_lr_sb128_sharp3_520x296": ("panzoom", 520, 296, 10, 2, {"cpu-used": "2", "cq-level": "44", "enable-restoration": "1", "sb-size": "128", "sharpness": "3"}, {14: 0, 48: 0}),
     "intra_8b_qm_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30", "enable-qm": "1", "qm-min": "2", "qm-max": "10"}, {14: 0, 48: 0}),
     # screen content (tune-content=screen on a source of flat colours and recurring glyphs): palette mode, and intra block copy (K3:
     # the predictor is the frame being decoded displaced by a block vector; libaom only picks it with CDEF off or at low cpu-used).
@@ -81,6 +83,16 @@ INTER_CASES = {
     "inter_8b_errres_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "4", "cq-level": "36"}, {14: 4, 48: 9999, 12: 1}),
     # reduced_tx_set = 1
     "inter_8b_reducedtx_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "3", "cq-level": "36", "reduced-tx-type-set": "1"}, {14: 4, 48: 9999}),
+    # deblocking with loop_filter_sharpness != 0
+    "inter_8b_sharp5_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "4", "cq-level": "40", "sharpness": "5"}, {14: 4, 48: 9999}),
+    # every frame another size: dynamic (random) spatial resize = references both larger and smaller than the frame, odd sizes
+    # (cfg[16] = rc_resize_mode 2), and a random super-resolution denominator per frame (cfg[19] = rc_superres_mode 2)
+    "inter_8b_resize_dyn_352x288": ("panzoom", 352, 288, 8, 10, {"cpu-used": "4", "cq-level": "36"}, {14: 0, 48: 9999, 16: 2}),
+    "inter_8b_superres_rand_352x288": ("panzoom", 352, 288, 8, 10, {"cpu-used": "4", "cq-level": "36"}, {14: 0, 48: 9999, 19: 2}),
+    # film grain: monochrome 10-bit (lag 2), lag 3 with overlap, and the 8-point scaling function of libaom's test vector 16
+    "inter_10b_grain_mono_208x144": ("noise", 208, 144, 10, 6, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "9"}, {14: 4, 48: 9999, 52: 1}),
+    "inter_8b_grain11_208x144": ("noise", 208, 144, 8, 6, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "11"}, {14: 4, 48: 9999}),
+    "inter_8b_grain16_208x144": ("noise", 208, 144, 8, 6, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "16"}, {14: 4, 48: 9999}),
     # odd frame size (410 x 230: the last mi column / row is half outside the picture) with 4 x 2 tiles at 10 bits
     "inter_10b_tiles4x2_odd_410x230": ("panzoom", 410, 230, 10, 6, {"cpu-used": "4", "cq-level": "36", "tile-columns": "2", "tile-rows": "1"}, {14: 4, 48: 9999}),
     "inter_10b_qm_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36", "enable-qm": "1", "qm-min": "0", "qm-max": "15"}, {14: 4, 48: 9999}),
