@@ -33,6 +33,10 @@ CASES = {
     "intra_8b_mono_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 0, 52: 1}),
     # 10-bit key frames with loop restoration, CDEF, 128x128 superblocks and a non-zero deblocking sharpness
     "intra_10b_lr_sb128_sharp3_520x296": ("panzoom", 520, 296, 10, 2, {"cpu-used": "2", "cq-level": "44", "enable-restoration": "1", "sb-size": "128", "sharpness": "3"}, {14: 0, 48: 0}),
+    # key frames with segmentation + delta_q + delta_lf; 10-bit key frames with 2 x 2 tiles, loop restoration and super-resolution 8/13
+    "intra_8b_aq_deltaq_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "3", "cq-level": "36", "aq-mode": "1", "deltaq-mode": "1", "delta-lf-mode": "1"}, {14: 0, 48: 0}),
+    "intra_10b_tiles_lr_superres_520x296": ("panzoom", 520, 296, 10, 2, {"cpu-used": "3", "cq-level": "40", "enable-restoration": "1", "tile-columns": "1", "tile-rows": "1"},
+                                            {14: 0, 48: 0, 19: 1, 20: 13, 21: 13}),
     "intra_8b_qm_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30", "enable-qm": "1", "qm-min": "2", "qm-max": "10"}, {14: 0, 48: 0}),
     # screen content (tune-content=screen on a source of flat colours and recurring glyphs): palette mode, and intra block copy (K3:
     # the predictor is the frame being decoded displaced by a block vector; libaom only picks it with CDEF off or at low cpu-used).
@@ -93,6 +97,17 @@ INTER_CASES = {
     "inter_10b_grain_mono_208x144": ("noise", 208, 144, 10, 6, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "9"}, {14: 4, 48: 9999, 52: 1}),
     "inter_8b_grain11_208x144": ("noise", 208, 144, 8, 6, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "11"}, {14: 4, 48: 9999}),
     "inter_8b_grain16_208x144": ("noise", 208, 144, 8, 6, {"cpu-used": "4", "cq-level": "40", "film-grain-test": "16"}, {14: 4, 48: 9999}),
+    # separate chroma quantiser deltas; a frame header OBU followed by several tile group OBUs (2 x 2 tiles in 3 groups) instead of one
+    # OBU_FRAME; most sequence-level tool switches off at once (the symbols those tools would read are absent from the bitstream)
+    "inter_8b_chromadq_256x160": ("panzoom", 256, 160, 8, 6, {"cpu-used": "4", "cq-level": "36", "enable-chroma-deltaq": "1"}, {14: 4, 48: 9999}),
+    "inter_8b_tilegroups_352x288": ("panzoom", 352, 288, 8, 6, {"cpu-used": "4", "cq-level": "36", "tile-columns": "1", "tile-rows": "1", "num-tile-groups": "3"}, {14: 4, 48: 9999}),
+    "inter_8b_seqflags_off_256x160": ("panzoom", 256, 160, 8, 8, {"cpu-used": "2", "cq-level": "36", "enable-dual-filter": "0", "enable-dist-wtd-comp": "0",
+                                      "enable-ref-frame-mvs": "0", "enable-masked-comp": "0", "enable-interintra-comp": "0", "enable-intra-edge-filter": "0",
+                                      "enable-filter-intra": "0", "enable-cdef": "0", "enable-restoration": "0", "enable-warped-motion": "0",
+                                      "enable-cfl-intra": "0", "enable-palette": "0"}, {14: 6, 48: 9999}),
+    # extreme geometry: one 16 x 16 block per frame; a frame much taller than wide (one superblock column)
+    "inter_8b_smallest_16x16": ("panzoom", 16, 16, 8, 4, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 9999}),
+    "inter_8b_tall_72x520": ("panzoom", 72, 520, 8, 4, {"cpu-used": "4", "cq-level": "34"}, {14: 0, 48: 9999}),
     # odd frame size (410 x 230: the last mi column / row is half outside the picture) with 4 x 2 tiles at 10 bits
     "inter_10b_tiles4x2_odd_410x230": ("panzoom", 410, 230, 10, 6, {"cpu-used": "4", "cq-level": "36", "tile-columns": "2", "tile-rows": "1"}, {14: 4, 48: 9999}),
     "inter_10b_qm_208x144": ("panzoom", 208, 144, 10, 6, {"cpu-used": "3", "cq-level": "36", "enable-qm": "1", "qm-min": "0", "qm-max": "15"}, {14: 4, 48: 9999}),
