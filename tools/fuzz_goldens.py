@@ -1,6 +1,7 @@
-"""Sanitizer fuzz campaign over every golden stream (host half only): python tools/fuzz_goldens.py SEED MUTANTS_PER_STREAM\nNeeds build/asan/parse_fuzz (make build/asan/parse_fuzz); prints ok / rejected counts per 100 files and stops at the first report."""
+"""Sanitizer fuzz campaign over every golden stream (host half only): python tools/fuzz_goldens.py SEED MUTANTS_PER_STREAM
+Needs build/asan/parse_fuzz (make build/asan/parse_fuzz); prints ok / rejected counts per 100 files and stops at the first report."""
 import os, random, subprocess, sys, glob, tempfile, shutil
-ROOT="/root/repo"; GOLD=os.path.join(ROOT,"tests/golden/streams")
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); GOLD=os.path.join(ROOT,"tests/golden/streams")
 names=sorted(os.path.basename(p)[:-4] for p in glob.glob(GOLD+"/*.ivf"))
 seed=int(sys.argv[1]) if len(sys.argv)>1 else 1
 per=int(sys.argv[2]) if len(sys.argv)>2 else 30
