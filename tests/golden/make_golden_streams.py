@@ -105,6 +105,9 @@ INTER_CASES = {
                                       "enable-ref-frame-mvs": "0", "enable-masked-comp": "0", "enable-interintra-comp": "0", "enable-intra-edge-filter": "0",
                                       "enable-filter-intra": "0", "enable-cdef": "0", "enable-restoration": "0", "enable-warped-motion": "0",
                                       "enable-cfl-intra": "0", "enable-palette": "0"}, {14: 6, 48: 9999}),
+    # a hidden SWITCH_FRAME (frame_type 3: error-resilient, refreshes all eight slots, explicit reference order hints) between inter
+    # frames (cfg[49] = sframe_dist 2, cfg[50] = sframe_mode 1, error resilient, lag 8)
+    "inter_8b_sframe_256x160": ("panzoom", 256, 160, 8, 12, {"cpu-used": "5", "cq-level": "36"}, {14: 8, 48: 9999, 49: 2, 50: 1, 12: 1}),
     # extreme geometry: one 16 x 16 block per frame; a frame much taller than wide (one superblock column)
     "inter_8b_smallest_16x16": ("panzoom", 16, 16, 8, 4, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 9999}),
     "inter_8b_tall_72x520": ("panzoom", 72, 520, 8, 4, {"cpu-used": "4", "cq-level": "34"}, {14: 0, 48: 9999}),

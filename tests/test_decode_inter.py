@@ -68,6 +68,7 @@ def test_syntax_switch_streams_use_their_switch(built):
     er = hdrs("inter_8b_errres_256x160")
     assert all(h.error_resilient_mode and h.primary_ref_frame == 7 for h in er)
     assert all(h.reduced_tx_set for h in hdrs("inter_8b_reducedtx_256x160"))
+    assert any(h.frame_type == 3 and not h.show_frame and h.refresh_frame_flags == 255 for h in hdrs("inter_8b_sframe_256x160"))   # SWITCH_FRAME
     odd = hdrs("inter_10b_tiles4x2_odd_410x230")
     assert all(h.tile_cols == 4 and h.tile_rows == 2 and h.width == 410 and h.height == 230 and h.bit_depth == 10 for h in odd)
 
