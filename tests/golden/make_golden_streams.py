@@ -37,6 +37,9 @@ CASES = {
     "intra_8b_aq_deltaq_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "3", "cq-level": "36", "aq-mode": "1", "deltaq-mode": "1", "delta-lf-mode": "1"}, {14: 0, 48: 0}),
     "intra_10b_tiles_lr_superres_520x296": ("panzoom", 520, 296, 10, 2, {"cpu-used": "3", "cq-level": "40", "enable-restoration": "1", "tile-columns": "1", "tile-rows": "1"},
                                             {14: 0, 48: 0, 19: 1, 20: 13, 21: 13}),
+    # 10-bit screen content with palette, CDEF and loop restoration on
+    "intra_10b_screen_cdef_320x192": ("screen", 320, 192, 10, 2, {"cpu-used": "3", "cq-level": "30", "tune-content": "screen", "enable-intrabc": "0",
+                                      "enable-restoration": "1"}, {14: 0, 48: 0}),
     "intra_8b_qm_264x200": ("panzoom", 264, 200, 8, 2, {"cpu-used": "4", "cq-level": "30", "enable-qm": "1", "qm-min": "2", "qm-max": "10"}, {14: 0, 48: 0}),
     # screen content (tune-content=screen on a source of flat colours and recurring glyphs): palette mode, and intra block copy (K3:
     # the predictor is the frame being decoded displaced by a block vector; libaom only picks it with CDEF off or at low cpu-used).
@@ -108,6 +111,12 @@ INTER_CASES = {
     # a hidden SWITCH_FRAME (frame_type 3: error-resilient, refreshes all eight slots, explicit reference order hints) between inter
     # frames (cfg[49] = sframe_dist 2, cfg[50] = sframe_mode 1, error resilient, lag 8)
     "inter_8b_sframe_256x160": ("panzoom", 256, 160, 8, 12, {"cpu-used": "5", "cq-level": "36"}, {14: 8, 48: 9999, 49: 2, 50: 1, 12: 1}),
+    # 10-bit versions of the rarer paths: lossless; complexity AQ + delta_q + delta_lf with 128x128 superblocks; a new frame size on
+    # every frame
+    "inter_10b_lossless_128x96": ("panzoom", 128, 96, 10, 3, {"cpu-used": "4", "lossless": "1"}, {14: 0, 48: 9999}),
+    "inter_10b_aq2_deltaq_sb128_384x224": ("panzoom", 384, 224, 10, 6, {"cpu-used": "3", "cq-level": "36", "aq-mode": "2", "deltaq-mode": "1",
+                                           "delta-lf-mode": "1", "sb-size": "128"}, {14: 4, 48: 9999}),
+    "inter_10b_resize_dyn_304x208": ("panzoom", 304, 208, 10, 8, {"cpu-used": "4", "cq-level": "36"}, {14: 0, 48: 9999, 16: 2}),
     # extreme geometry: one 16 x 16 block per frame; a frame much taller than wide (one superblock column)
     "inter_8b_smallest_16x16": ("panzoom", 16, 16, 8, 4, {"cpu-used": "4", "cq-level": "30"}, {14: 0, 48: 9999}),
     "inter_8b_tall_72x520": ("panzoom", 72, 520, 8, 4, {"cpu-used": "4", "cq-level": "34"}, {14: 0, 48: 9999}),
