@@ -12,7 +12,7 @@ GOLD = os.path.join(ROOT, "tests", "golden", "streams")
 NAMES = ["intra_8b_200x136", "inter_8b_alltools_352x288", "intra_8b_lr_480x272", "inter_10b_grain_208x144",
          "intra_8b_superres_lr_328x200", "inter_8b_sb128_tiles_640x360"]
 # host-only runs also mutate the streams of the less common syntax paths (segmentation, delta_q / delta_lf, lossless, a new frame size
-# on every frame, separate tile group OBUs, screen content); the whole set of 52 was run through the sanitizer build with 4,700
+# on every frame, separate tile group OBUs, screen content); the whole set of 57 was run through the sanitizer build with 6,100
 # mutants without a report (tools/fuzz_goldens.py; not part of the suite for its run time)
 NAMES_HOST = NAMES + ["inter_8b_aq1_256x160", "inter_8b_aq3_256x160", "inter_8b_deltaq_lf_256x160", "inter_8b_lossless_128x96",
                       "inter_8b_resize_dyn_352x288", "inter_8b_superres_rand_352x288", "inter_8b_tilegroups_352x288",
