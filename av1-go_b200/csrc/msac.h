@@ -68,6 +68,7 @@ struct Msac {
     __attribute__((always_inline)) inline int symbol(uint16_t* c, int n) {
 #ifdef AV1R_MSAC_SSE2
         if (n == 3 || n == 4) return symbol_v4(c, n);
+        if (n >= 5 && n <= 16) return symbol_v16(c, n);
 #endif
         const uint32_t r = rng;
         const uint32_t v16 = (uint32_t)(dif >> 48);
@@ -127,6 +128,52 @@ struct Msac {
             __m128i nv = _mm_or_si128(_mm_and_si128(lt, up), _mm_andnot_si128(lt, dn));
             nv = _mm_or_si128(_mm_and_si128(en, nv), _mm_andnot_si128(en, cv));   // sentinel / counter lanes keep their value
             _mm_storel_epi64(reinterpret_cast<__m128i*>(c), nv);
+            c[n] = (uint16_t)(cnt_ + (cnt_ < 32));
+        }
+        return s;
+    }
+#endif
+#ifdef AV1R_MSAC_SSE2
+    // 5- to 16-symbol alphabets (partition, intra modes, transform types, end-of-block classes, motion vector classes ...): the same
+    // scheme on two vectors of eight 16-bit lanes.  The loads and stores cover c[0..15], i.e. they reach past c[n] into whatever
+    // follows this CDF (the next CDF of the context, or the pad behind it: tile.h); lanes >= n - 1 are written back unchanged.
+    __attribute__((always_inline)) inline int symbol_v16(uint16_t* c, int n) {
+        const uint32_t r = rng;
+        const uint32_t v16 = (uint32_t)(dif >> 48);
+        const __m128i c0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c)), c1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c + 8));
+        const __m128i i0 = _mm_set_epi16(7, 6, 5, 4, 3, 2, 1, 0), i1 = _mm_set_epi16(15, 14, 13, 12, 11, 10, 9, 8);
+        const __m128i nm1 = _mm_set1_epi16((short)(n - 1));
+        const __m128i en0 = _mm_cmpgt_epi16(nm1, i0), en1 = _mm_cmpgt_epi16(nm1, i1);                     // lanes < n - 1
+        const __m128i mp0 = _mm_slli_epi16(_mm_sub_epi16(nm1, i0), 2), mp1 = _mm_slli_epi16(_mm_sub_epi16(nm1, i1), 2);   // 4 * (n - 1 - i)
+        const __m128i rr = _mm_set1_epi16((short)(r & 0xff00));
+        __m128i v0 = _mm_mulhi_epu16(rr, _mm_slli_epi16(_mm_srli_epi16(c0, 6), 7));
+        __m128i v1 = _mm_mulhi_epu16(rr, _mm_slli_epi16(_mm_srli_epi16(c1, 6), 7));
+        v0 = _mm_and_si128(_mm_add_epi16(v0, mp0), en0);
+        v1 = _mm_and_si128(_mm_add_epi16(v1, mp1), en1);
+        const __m128i w = _mm_set1_epi16((short)v16), z = _mm_setzero_si128();
+        const __m128i le0 = _mm_cmpeq_epi16(_mm_subs_epu16(v0, w), z), le1 = _mm_cmpeq_epi16(_mm_subs_epu16(v1, w), z);   // v <= window
+        const unsigned mask = (unsigned)_mm_movemask_epi8(le0) | ((unsigned)_mm_movemask_epi8(le1) << 16);
+        const int s = __builtin_ctz(mask | 0x80000000u) >> 1;     // lane n - 1 holds 0: there always is one before lane 16
+        // split points below / at the symbol: lane s - 1 (the range itself for s == 0) and lane s
+        alignas(16) uint16_t t[24];
+        t[7] = (uint16_t)r;
+        _mm_store_si128(reinterpret_cast<__m128i*>(t + 8), v0);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(t + 16), v1);
+        const uint32_t u = t[7 + s], vv = s < 16 ? t[8 + s] : 0;
+        normalize(dif - ((uint64_t)vv << 48), u - vv);
+        if (update) {
+            const int cnt_ = c[n];
+            const __m128i rate = _mm_cvtsi32_si128(5 + (cnt_ > 15) + (cnt_ > 31));
+            const __m128i h = _mm_set1_epi16((short)0x8000);
+            const __m128i up0 = _mm_add_epi16(c0, _mm_srl_epi16(_mm_sub_epi16(h, c0), rate)), dn0 = _mm_sub_epi16(c0, _mm_srl_epi16(c0, rate));
+            const __m128i up1 = _mm_add_epi16(c1, _mm_srl_epi16(_mm_sub_epi16(h, c1), rate)), dn1 = _mm_sub_epi16(c1, _mm_srl_epi16(c1, rate));
+            const __m128i lt0 = _mm_andnot_si128(le0, en0), lt1 = _mm_andnot_si128(le1, en1);           // lanes i < s
+            __m128i n0 = _mm_or_si128(_mm_and_si128(lt0, up0), _mm_andnot_si128(lt0, dn0));
+            __m128i n1 = _mm_or_si128(_mm_and_si128(lt1, up1), _mm_andnot_si128(lt1, dn1));
+            n0 = _mm_or_si128(_mm_and_si128(en0, n0), _mm_andnot_si128(en0, c0));                        // other lanes keep their value
+            n1 = _mm_or_si128(_mm_and_si128(en1, n1), _mm_andnot_si128(en1, c1));
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(c), n0);
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(c + 8), n1);
             c[n] = (uint16_t)(cnt_ + (cnt_ < 32));
         }
         return s;

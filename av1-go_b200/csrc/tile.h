@@ -17,6 +17,7 @@ public:
     // returns 0, AV1R_EBITSTREAM or AV1R_ENOSYS (err holds the reason)
     int decode_tile(const uint8_t* data, size_t sz, int tile_row, int tile_col);
     CdfCtx cdf;
+    uint16_t cdf_tail_pad_[16] = {0};   // the 16-lane symbol decoder (msac.h) loads / stores 32 bytes from the start of a CDF
     std::string err;
 
 private:
